@@ -1,0 +1,424 @@
+#!/usr/bin/env python
+"""Benchmark of the s2v hot path:  python bench.py --gpus N --steps K --warmup W
+
+Workload (BASELINE.json configs[2], the configuration `metric` is quoted on):
+s2v GNN-DQN training step on NWB_AMS-shaped graphs (N = 975 nodes, 2850 directed edges,
+F = 7, p = 64, T = 5, mean pool), `--batch` graphs per GPU (weak scaling), synthetic node
+features, default-initialised weights.  One step = forward over the batch, loss gather +
+SmoothL1, backward through every kernel, (N>1: one NCCL all-reduce of the flat gradient
+buffer), Adam step.
+
+Prints ONE JSON line (rank 0).  `value` is whole-job graphs/s with inputs resident in HBM
+(CSR of the batch cached: topology is reused across steps); `e2e` is the same
+step driven from pinned HOST buffers through the public API: H2D of node features and
+edge_index, CSR build, forward, loss, backward, optimiser, D2H of the loss -- every step.
+
+`--impl reference` times the reference's own CPU arithmetic for this path (the dense
+restatement of QNet.forward, oracle/s2v_ref.py, kind "port": the reference is pure Python
+whose third-party imports are absent on the GPU box) on the host cores.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "s2v_fwd_bwd_graphs_per_sec_N975"
+UNIT = "graphs/s"
+TOPO = "NWB_AMS"
+P, T, F = 64, 5, 7
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=5)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--batch", type=int, default=4096, help="graphs per GPU")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    return ap.parse_args()
+
+
+def workload_config(batch, n_gpus):
+    return {"workload": "s2v GNN-DQN train step on NWB_AMS (N=975, E=2850, F=7, p=64, T=5, norm_agg)",
+            "graphs_per_gpu": batch, "global_batch": batch * n_gpus, "nodes_per_graph": 975,
+            "parallelism": "dp%d" % n_gpus,
+            "l2": "inputs exceed L2: per-GPU node features %.0f MB, each embedding plane %.2f GB"
+                  % (batch * 975 * F * 4 / 1e6, batch * 975 * P * 4 / 1e9)}
+
+
+# --------------------------------------------------------------------------------------
+# CPU reference arithmetic (oracle; timed as the baseline only)
+# --------------------------------------------------------------------------------------
+def cpu_reference_step_fn(kind, batch):
+    """Returns (step_fn, graphs_per_step, description). kind: 'dense' (reference arithmetic) or 'sparse'."""
+    import torch
+    from oracle import s2v_ref as R
+    from simmodel_b200 import graphs
+    topo = graphs.load_topology(TOPO)
+    gen = torch.Generator().manual_seed(0)
+    N = topo.num_nodes
+    xv = graphs.synth_nfm(topo, batch, gen)
+    Pm = {k: v.requires_grad_(True) for k, v in R.make_qnet_params(F, P, seed=0).items()}
+    sizes = [N] * batch
+    bt = R.batch_from_sizes(sizes, [topo.edge_index] * batch)
+    actions = torch.randint(0, N, (batch,), generator=gen).tolist()
+    targets = torch.randn(batch, generator=gen).tolist()
+    if kind == "dense":
+        W = torch.zeros(N, N)
+        W[topo.edge_index[0], topo.edge_index[1]] = 1.0
+        Ws = W.unsqueeze(0).repeat(batch, 1, 1)
+
+        def step():
+            for v in Pm.values():
+                v.grad = None
+            q = R.qnet_forward_dense(Pm, xv, Ws, bt.ptr, bt.batch, T, True)
+            R.dqn_loss(q.reshape(-1), actions, bt.ptr, targets).backward()
+        desc = "dense reference arithmetic (comb_opt.py:217-275 restated), fwd+bwd, B=%d AMS graphs per step" % batch
+    else:
+        x = xv.reshape(-1, F)
+
+        def step():
+            for v in Pm.values():
+                v.grad = None
+            q = R.qnet_forward_sparse(Pm, x, bt.edge_index, bt.ptr, N, T, True)
+            R.dqn_loss(q, actions, bt.ptr, targets).backward()
+        desc = "sparse CPU restatement (index_add), fwd+bwd, B=%d AMS graphs per step" % batch
+    return step, batch, desc
+
+
+def time_cpu(step, min_steps, budget_s, warmup=1):
+    for _ in range(warmup):
+        step()
+    times = []
+    t_end = time.perf_counter() + budget_s
+    while len(times) < min_steps or (time.perf_counter() < t_end and len(times) < 50):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if len(times) >= min_steps and time.perf_counter() >= t_end:
+            break
+    return times
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    sample_b = 2
+    step, gps, desc = cpu_reference_step_fn("dense", sample_b)
+    for _ in range(max(1, min(args.warmup, 3))):
+        step()
+    times = []
+    for _ in range(max(1, args.steps)):
+        t0 = time.perf_counter()
+        step()
+        times.append(time.perf_counter() - t0)
+        if sum(times) > 150:
+            break
+    ms = 1e3 * sum(times) / len(times)
+    val = gps / (ms / 1e3)
+    line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+            "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "node_updates_per_sec": val * 975 * T,
+            "config": workload_config(args.batch, args.gpus),
+            "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
+                             "sample": desc + "; torch %s CPU, %d threads" % (torch.__version__, cores)},
+            "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# clocks
+# --------------------------------------------------------------------------------------
+class ClockSampler:
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for ln in self.proc.stdout:
+            self.lines.append(ln.strip())
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for ln in self.lines:
+            parts = [s.strip() for s in ln.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0]))
+                mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": statistics.median(sm) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# --------------------------------------------------------------------------------------
+# B200 arm
+# --------------------------------------------------------------------------------------
+def run_b200(args):
+    import torch
+    import torch.distributed as dist
+    import simmodel_b200 as sb
+    from simmodel_b200 import _lib
+    from simmodel_b200.dist import allreduce_gradients
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    dev = torch.device("cuda", local_rank)
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+
+    topo = sb.graphs.load_topology(TOPO)
+    N, B = topo.num_nodes, args.batch
+    gen = torch.Generator().manual_seed(1000 + rank)
+    x_host = sb.graphs.synth_nfm(topo, B, gen).reshape(-1, F).contiguous().pin_memory()
+    ei_host = sb.graphs.batch_edge_index(topo, B).contiguous().pin_memory()
+    ptr_host = (torch.arange(B + 1, dtype=torch.int64) * N)
+    actions_host = torch.randint(0, N, (B,), generator=gen).pin_memory()
+    targets_host = torch.randn(B, generator=gen).pin_memory()
+
+    torch.manual_seed(0)
+    net = sb.QNet({"emb_dim": P, "emb_iter_T": T, "norm_agg": True, "node_dim": F}, verbose=False).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    loss_fn = torch.nn.SmoothL1Loss()
+    params = list(net.parameters())
+
+    # resident inputs
+    x = x_host.to(dev)
+    ptr = ptr_host.to(dev)
+    ei = ei_host.to(dev)
+    sel = actions_host.to(dev) + ptr[:-1]
+    targets = targets_host.to(dev)
+    torch.cuda.synchronize()
+    t0 = torch.cuda.Event(enable_timing=True)
+    t1 = torch.cuda.Event(enable_timing=True)
+    t0.record()
+    layout = sb.GraphLayout.from_batch(ei, ptr, N, validate=False)
+    t1.record()
+    torch.cuda.synchronize()
+    csr_ms = t0.elapsed_time(t1)
+    del ei
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        q = net.forward_graph(x, layout)
+        loss = loss_fn(q[sel], targets)
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(params, B, B * world)
+        opt.step()
+        return loss
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms = torch.tensor([e0.elapsed_time(e1)], device=dev)
+        if world > 1:
+            dist.all_reduce(ms, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms.item())
+
+    sampler = ClockSampler(local_rank)
+    launches0 = _lib.launch_count
+    for _ in range(args.warmup):
+        step()
+    launches_per_step = None
+    c0 = _lib.launch_count
+    step()
+    launches_per_step = _lib.launch_count - c0
+    if rank == 0:
+        sampler.start()
+    total_ms = timed(step, args.steps, 0)
+    clocks = sampler.stop() if rank == 0 else None
+    ms_per_step = total_ms / args.steps
+    value = B * world / (ms_per_step / 1e3)
+
+    # ---- end to end from pinned host buffers through the public API --------------------
+    e2e = None
+    if not args.no_e2e:
+        def step_e2e():
+            xd = x_host.to(dev, non_blocking=True)
+            eid = ei_host.to(dev, non_blocking=True)
+            ad = actions_host.to(dev, non_blocking=True)
+            td = targets_host.to(dev, non_blocking=True)
+            lay = sb.GraphLayout.from_batch(eid, ptr, N, validate=False)
+            opt.zero_grad(set_to_none=True)
+            q = net.forward_graph(xd, lay)
+            loss = loss_fn(q[ad + ptr[:-1]], td)
+            loss.backward()
+            if world > 1:
+                allreduce_gradients(params, B, B * world)
+            opt.step()
+            return float(loss.item())          # D2H read of the step's result
+        e2e_steps = max(3, min(args.steps, 10))
+        e2e_ms = timed(step_e2e, e2e_steps, 2) / e2e_steps
+        h2d = x_host.numel() * 4 + ei_host.numel() * 8 + actions_host.numel() * 8 + targets_host.numel() * 4
+        e2e = {"value": B * world / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+               "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
+               "includes": "H2D(x, edge_index int64, actions, targets) + CSR build + fwd + loss + bwd + Adam + D2H(loss)"}
+
+    # ---- roofline of the dominant kernels, timed alone with CUDA events ------------------
+    roofline, kernels = None, None
+    if rank == 0:
+        roofline, kernels = measure_roofline(sb, _lib, net, layout, x, dev, B, N)
+
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu_baseline = measure_cpu_baseline()
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+                "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
+                "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "node_updates_per_sec": value * N * T,
+                "config": workload_config(B, world), "csr_build_ms": csr_ms,
+                "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+                "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
+                "cpu_baseline": cpu_baseline}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
+    """Dominant kernels = one propagation round forward / backward.  Algorithmic bytes per
+    node-update (fused-epilogue variant): 4*(p*(dbar+1) + dbar + 1) for the gather
+    (neighbour rows + output row + column ids + rowptr) + 4*p for the one extra row the fused
+    epilogue reads (base forward, mu^{t-1} backward)."""
+    import ctypes as C
+    import torch
+    from simmodel_b200.layout import _p, _stream
+    L = _lib.lib()
+    n = layout.num_nodes
+    dbar = layout.num_edges / max(1, (layout.period or n))
+    bytes_per_node = 4 * (P * (dbar + 1) + dbar + 1) + 4 * P
+    alg_bytes = bytes_per_node * n
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(peaks_path):
+        with open(peaks_path) as f:
+            peak, peak_src = float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs, burst copy)"
+    else:
+        peak, peak_src = 6650.0, "fallback (B200_PROFILING.md)"
+    with torch.no_grad():
+        mu = net.embed_graph(x, layout)
+    base = torch.randn(n, P, device=dev)
+    out = torch.empty(n, P, device=dev)
+    du = torch.randn(n, P, device=dev)
+    ws = torch.empty(L.s2v_embed_backward_workspace_bytes(F, P), dtype=torch.uint8, device=dev)
+    g = layout.c_struct()
+    w2 = net.theta2.weight.detach()
+
+    def fwd():
+        _lib.check(L.s2v_embed_round_forward(C.byref(g), P, _p(w2), _p(base), _p(mu), _p(out), _stream()), "round fwd")
+
+    def bwd():
+        _lib.check(L.s2v_embed_round_backward(C.byref(g), F, P, _p(w2), _p(du), _p(mu), _p(out), _p(ws), ws.numel(),
+                                              _stream()), "round bwd")
+    res = []
+    for name, fn in (("k_embed_round (forward round)", fwd), ("k_embed_round_bwd (backward round)", bwd)):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(10)]
+        for a, b in evs:
+            a.record()
+            fn()
+            b.record()
+        torch.cuda.synchronize()
+        ms = statistics.mean(a.elapsed_time(b) for a, b in evs)
+        ach = alg_bytes / (ms / 1e3) / 1e9
+        res.append({"kernel": name, "ms": ms, "algorithmic_bytes": alg_bytes, "achieved_GBps": ach, "frac": ach / peak,
+                    "launches_per_step": T - 1})
+    dom = max(res, key=lambda r: r["ms"])
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "algorithmic_bytes_per_node_update": bytes_per_node, "node_updates_per_launch": n,
+                "avg_launch_ms": dom["ms"]}
+    return roofline, res
+
+
+def measure_cpu_baseline():
+    """Reference CPU arithmetic on this box's host cores, bounded sample (~10-20 s)."""
+    import torch
+    cores = os.cpu_count() or 1
+    torch.set_num_threads(cores)
+    step, gps, desc = cpu_reference_step_fn("dense", 2)
+    times = time_cpu(step, 3, 8.0)
+    dense = gps / statistics.mean(times)
+    step2, gps2, desc2 = cpu_reference_step_fn("sparse", 64)
+    times2 = time_cpu(step2, 3, 6.0)
+    sparse = gps2 / statistics.mean(times2)
+    return {"value": dense, "unit": UNIT, "cores": cores, "kind": "port",
+            "sample": "%s, %d steps; torch %s CPU" % (desc, len(times), torch.__version__),
+            "sparse_port": {"value": sparse, "unit": UNIT, "sample": "%s, %d steps" % (desc2, len(times2))}}
+
+
+def main():
+    args = parse()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_b200(args)
+
+
+if __name__ == "__main__":
+    main()

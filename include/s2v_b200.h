@@ -1,0 +1,206 @@
+/*
+ * s2v_b200.h -- C ABI of the B200-native struct2vec (s2v) hot path.
+ *
+ * Drop-in boundary for the s2v / GNN-embedding path of rvdweerd/simmodel.  The
+ * reference is pure Python; what its hot path "binds" are the torch / torch_scatter /
+ * torch_geometric library ops it calls.  Each entry point below names the reference
+ * lines it replaces (paths relative to the reference root).
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer owned by the caller (torch allocates all
+ *     buffers, workspaces and outputs); nothing is allocated or freed here;
+ *   - kernels are enqueued on `stream` (a cudaStream_t passed as void*) and never
+ *     synchronise; calls are capturable into CUDA graphs;
+ *   - return value: 0 on success, otherwise a cudaError_t value (> 0) or one of the
+ *     S2V_ERR_* codes (< 0); no exceptions cross the ABI; s2v_error_string() decodes;
+ *   - no global mutable state: re-entrant, callable from any host thread;
+ *   - all floating point is fp32, node/edge indices are int32 on the device
+ *     (edge_index arrives as the int64 torch/PyG tensor and is narrowed by
+ *     s2v_csr_build);
+ *   - reductions are atomics-free with a fixed summation order: results are
+ *     run-to-run bit-stable for a given device and problem size.
+ *
+ * Graph layout (s2v_graph_t)
+ *   Row form  : row i gathers the columns j with W[i,j] != 0, i.e. the edges with
+ *               edge_index[0] == i (conn_matrices.matmul(mu), comb_opt.py:241).
+ *   Transpose : column j lists the rows i that gather it (used by backward and for
+ *               the in-degree c_j of the theta4 term, comb_opt.py:236-237).
+ *   period==0 : "batched" layout, the CSR covers all num_nodes rows of the batch
+ *               (PyG Batch.from_data_list, comb_opt.py:299,344); ptr/gid give the
+ *               graph of each node.
+ *   period>0  : "replicated" layout, the CSR describes ONE graph of `period` nodes
+ *               and the batch is num_graphs copies of it with different features
+ *               (the PPO path: S time steps sharing one ei,
+ *               models_basic_lstm.py:507-518).  Row r = s*period + i.
+ */
+#ifndef S2V_B200_H
+#define S2V_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define S2V_ABI_VERSION 1
+
+#define S2V_ERR_BAD_ARG        (-1)  /* null pointer / negative size / inconsistent sizes     */
+#define S2V_ERR_UNSUPPORTED    (-2)  /* emb_dim not in {8,16,24,32,48,64}, node_dim > 32 */
+#define S2V_ERR_WORKSPACE      (-3)  /* workspace smaller than s2v_*_workspace_bytes()        */
+
+typedef struct s2v_graph {
+    int32_t num_nodes;        /* sum of real node counts over the batch (rows)            */
+    int32_t num_graphs;       /* B                                                         */
+    int32_t period;           /* 0 = batched CSR over num_nodes rows, >0 = replicated      */
+    int32_t num_edges;        /* entries in col / col_t                                    */
+    const int32_t* rowptr;    /* [n_csr+1], n_csr = period ? period : num_nodes            */
+    const int32_t* col;       /* [num_edges]                                               */
+    const int32_t* rowptr_t;  /* [n_csr+1]                                                 */
+    const int32_t* col_t;     /* [num_edges]                                               */
+    const int32_t* indeg;     /* [n_csr] column counts c_j                                 */
+    const int32_t* ptr;       /* [B+1] node offset of each graph (NULL iff period>0)       */
+    const int32_t* gid;       /* [num_nodes] graph id of each node (NULL iff period>0)     */
+    const int32_t* npad;      /* [B] padded size per graph, or NULL -> npad_scalar         */
+    int32_t npad_scalar;      /* xv.shape[1] of the reference call (comb_opt.py:221)       */
+    int32_t reserved;
+} s2v_graph_t;
+
+/* theta1a..theta4 of QNet (comb_opt.py:204-209) / PPO_GNN_Single_LSTM (models_basic_lstm.py:432-436),
+ * row-major nn.Linear layout: weight [out,in], bias [out]. */
+typedef struct s2v_embed_params {
+    int32_t node_dim;         /* F  */
+    int32_t emb_dim;          /* p  */
+    int32_t rounds;           /* T  */
+    int32_t reserved;
+    const float* theta1a_w;   /* [p,F] */
+    const float* theta1a_b;   /* [p]   */
+    const float* theta1b_w;   /* [p,p] */
+    const float* theta1b_b;
+    const float* theta2_w;    /* [p,p] */
+    const float* theta2_b;
+    const float* theta3_w;    /* [p,p] */
+    const float* theta3_b;
+    const float* theta4_w;    /* [p,1] */
+    const float* theta4_b;
+} s2v_embed_params_t;
+
+/* theta5..theta7 (comb_opt.py:210-212; theta{5,6,7}_{pi,v}, models_basic_lstm.py:449-460). */
+typedef struct s2v_head_params {
+    int32_t emb_dim;
+    int32_t norm_agg;         /* 1 = mean pool (scatter_mean), 0 = sum pool (scatter_add)  */
+    const float* theta5_w;    /* [1,2p] */
+    const float* theta5_b;    /* [1]    */
+    const float* theta6_w;    /* [p,p]  */
+    const float* theta6_b;
+    const float* theta7_w;    /* [p,p]  */
+    const float* theta7_b;
+} s2v_head_params_t;
+
+int         s2v_abi_version(void);
+const char* s2v_error_string(int code);
+
+/* Number of floats in the flat gradient buffers (parameter order of the reference
+ * constructors, so the concatenation [embed | head] is QNet.parameters() order). */
+int64_t s2v_embed_grad_floats(int32_t node_dim, int32_t emb_dim);   /* theta1a.w,b 1b.w,b 2.w,b 3.w,b 4.w,b */
+int64_t s2v_head_grad_floats(int32_t emb_dim);                      /* theta5.w,b 6.w,b 7.w,b               */
+
+/* ---------------------------------------------------------------------------------
+ * K1  deterministic CSR / CSC builder over a (batched) edge_index.
+ * Replaces: dense W = nx.to_numpy_matrix / F.pad / torch.stack(Ws).to(device)
+ * (simdata_utils.py:513, comb_opt.py:538,342), dense_to_sparse (simdata_utils.py:519),
+ * to_dense_adj (models_basic_lstm.py:515).
+ * edge_index: int64 [2,E] (row 0 = gathering node i, row 1 = column j), ids in [0,n).
+ * Output order inside a row / column is the input edge order (stable), so the result
+ * is bit-identical to a stable argsort (oracle/s2v_ref.py:csr_from_edge_index).
+ * workspace: s2v_csr_workspace_bytes(n, E) bytes.
+ * --------------------------------------------------------------------------------- */
+int64_t s2v_csr_workspace_bytes(int64_t n, int64_t num_edges);
+int s2v_csr_build(const int64_t* edge_index, int64_t num_edges, int64_t n,
+                  int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t, int32_t* indeg,
+                  void* workspace, int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * K2+K3  embedding forward: node MLP, theta4/theta3 degree term, T propagation rounds.
+ * Replaces comb_opt.py:230-242 and models_basic_lstm.py:491-503.
+ *   x    [num_nodes,F]      node features of the REAL nodes (padded rows never enter)
+ *   base [num_nodes,p] out  s1 + s3 + b2 (the round-invariant part of the pre-activation)
+ *   mus  [T,num_nodes,p] out  mu^1..mu^T (mu^T = mus[T-1] is the embedding; all rounds
+ *                            are kept for backward)
+ * --------------------------------------------------------------------------------- */
+int s2v_embed_forward(const s2v_graph_t* g, const s2v_embed_params_t* prm, const float* x,
+                      float* base, float* mus, void* stream);
+
+/* Embedding backward (autograd of the lines above, comb_opt.py:362 / models_basic_lstm.py:650).
+ *   dmu        [num_nodes,p]   gradient w.r.t. mu^T
+ *   dmu_masked 1 if dmu is already multiplied by [mu^T > 0] (fused head backward)
+ *   dus        [T,num_nodes,p] workspace for the pre-activation gradients du^t
+ *   workspace  s2v_embed_backward_workspace_bytes() bytes (per-CTA partial sums)
+ *   grad       [s2v_embed_grad_floats] out, overwritten                                  */
+int64_t s2v_embed_backward_workspace_bytes(int32_t node_dim, int32_t emb_dim);
+int s2v_embed_backward(const s2v_graph_t* g, const s2v_embed_params_t* prm, const float* x,
+                       const float* base, const float* mus, const float* dmu, int32_t dmu_masked,
+                       float* dus, void* workspace, int64_t workspace_bytes, float* grad, void* stream);
+
+/* One propagation round alone (comb_opt.py:241-242): mu_next = relu(base + theta2 (W mu_prev)),
+ * and one backward round: g = W^T du_t ; du_prev = (theta2^T g) * [mu_prev > 0] (the per-CTA
+ * partial sums of dtheta2 land in workspace).  Used by unit tests and to time the dominant
+ * kernels in isolation. */
+int s2v_embed_round_forward(const s2v_graph_t* g, int32_t emb_dim, const float* theta2_w, const float* base,
+                            const float* mu_prev, float* mu_next, void* stream);
+int s2v_embed_round_backward(const s2v_graph_t* g, int32_t node_dim, int32_t emb_dim, const float* theta2_w,
+                             const float* du_t, const float* mu_prev, float* du_prev, void* workspace,
+                             int64_t workspace_bytes, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * K5  pooling + Q / logit head.  Replaces comb_opt.py:248-273 (select list, scatter_mean /
+ * scatter_add, repeat_interleave, theta6, theta7, cat, relu, theta5) and
+ * models_basic_lstm.py:530-538, 548-562.
+ *   mu   [num_nodes,p]
+ *   pool [B,p] out, gstate [B,p] out (theta6 pool + b6), q [num_nodes] out
+ * --------------------------------------------------------------------------------- */
+int s2v_head_forward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu,
+                     float* pool, float* gstate, float* q, void* stream);
+
+/* Head backward.  dq [num_nodes]; dmu [num_nodes,p] out (multiplied by [mu>0] when
+ * mask_relu != 0, i.e. it is du^T); per_graph [B, 2p+4] workspace;
+ * grad [s2v_head_grad_floats] out, overwritten. */
+int64_t s2v_head_backward_workspace_bytes(int32_t emb_dim, int32_t num_graphs);
+int s2v_head_backward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu,
+                      const float* pool, const float* gstate, const float* dq, int32_t mask_relu,
+                      float* dmu, void* workspace, int64_t workspace_bytes, float* grad, void* stream);
+
+/* Per-graph mean / sum pool alone (critic 'v': theta5_v(mu.mean(dim=1)), models_basic_lstm.py:548-552)
+ * and its backward (dmu[i] = dpool[g(i)] / n_g). */
+int s2v_pool_forward(const s2v_graph_t* g, int32_t emb_dim, int32_t norm_agg, const float* mu, float* pool, void* stream);
+int s2v_pool_backward(const s2v_graph_t* g, int32_t emb_dim, int32_t norm_agg, const float* dpool, float* dmu, void* stream);
+
+/* du = dmu * [mu > 0]  (ReLU backward of the last round when the head is not fused). */
+int s2v_relu_mask(const float* dmu, const float* mu, float* du, int64_t n, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * K6/K7  invalid-action mask + per-graph reductions (bit-exact integer results).
+ *   s2v_list_argmax : DQN greedy action, comb_opt.py:319-326: np.argmax over
+ *       q[reachable_nodes]; reach_idx holds LOCAL node ids per graph (ascending neighbour
+ *       list, simdata_utils.py:641), reach_ptr [B+1].  Outputs per graph: position in the
+ *       list (first maximum), local node id, value.  Empty list -> (-1,-1,-inf).
+ *   s2v_masked_argmax : first maximum of q over mask != 0 (qvals[~reachable] = -inf;
+ *       max(dim=1), models_basic_lstm.py:563-564; probs.argmax(), rl_policy.py:536).
+ *       Empty mask -> arg -1, val -inf.  arg is the LOCAL node id.
+ *   s2v_masked_softmax_* : prob_logits[~reachable] = -inf; softmax(dim=1)
+ *       (models_basic_lstm.py:539-540); masked entries are exactly 0.
+ *   s2v_scatter_rows : dq = 0; dq[ptr[g] + arg[g]] = dval[g]  (backward of the masked max).
+ * --------------------------------------------------------------------------------- */
+int s2v_list_argmax(const s2v_graph_t* g, const float* q, const int32_t* reach_ptr, const int32_t* reach_idx,
+                    int64_t* pos_out, int64_t* node_out, float* val_out, void* stream);
+int s2v_masked_argmax(const s2v_graph_t* g, const float* q, const uint8_t* mask,
+                      int64_t* arg_out, float* val_out, void* stream);
+int s2v_masked_softmax_forward(const s2v_graph_t* g, const float* logits, const uint8_t* mask,
+                               float* prob, void* stream);
+int s2v_masked_softmax_backward(const s2v_graph_t* g, const float* prob, const float* dprob,
+                                float* dlogits, void* stream);
+int s2v_scatter_rows(const s2v_graph_t* g, const int64_t* arg, const float* dval, float* dq, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* S2V_B200_H */

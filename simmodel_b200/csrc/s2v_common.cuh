@@ -1,0 +1,248 @@
+// Shared device helpers for the s2v kernels (sm_100a).
+//
+// Tile model used by every node-wise kernel: a CTA of S2V_THREADS threads owns a
+// tile of S2V_TM consecutive node rows.  Row tiles live in shared memory row-major
+// with a leading dimension of P+4 floats (16-byte aligned rows, bank-conflict-free
+// for the access patterns below); weight matrices live in shared memory as
+// [k][n] so that one float4 read yields four output columns.
+//
+// Thread mapping (same for the row transform C = A * W and for the reduction
+// C = A^T * B over the rows of a tile):  tx = t % TXP selects four consecutive
+// output columns, ty = t / TXP selects the row group; thread rows are ty + RG*i.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include "s2v_b200.h"
+
+#define S2V_THREADS 128
+#define S2V_TM 64
+#define S2V_MAX_GRID 1024
+#define S2V_MAX_F 32
+
+template <int P>
+struct Cfg {
+    static_assert(P % 4 == 0 && P >= 8 && P <= 64, "emb_dim must be a multiple of 4 in [8,64]");
+    static constexpr int TXP = P / 4;                            // float4 column groups per row
+    static constexpr int RG = S2V_THREADS / TXP;                 // row groups
+    static constexpr int ACTIVE = TXP * RG;                      // threads that own outputs
+    static constexpr int NR = (S2V_TM + RG - 1) / RG;            // tile rows per thread (transform)
+    static constexpr int NRR = (P + RG - 1) / RG;                // output rows per thread (reduction, P x P)
+    static constexpr int LDA = P + 4;                            // leading dimension of row tiles
+    static constexpr int TILE_FLOATS = S2V_TM * LDA;
+    static constexpr int W_FLOATS = P * P;
+    // gather: LPR lanes (float4 each) cover one row, RPP rows per warp pass
+    static constexpr int LPR = P / 4;
+    static constexpr int RPP = 32 / LPR;
+};
+
+__device__ __forceinline__ float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
+__device__ __forceinline__ void st4(float* p, float4 v) { *reinterpret_cast<float4*>(p) = v; }
+__device__ __forceinline__ float4 ldg4(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+__device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0.f); }
+__device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
+__device__ __forceinline__ float relu(float v) { return v > 0.f ? v : 0.f; }
+
+// Row r of the batch -> (row in the CSR, offset to add to CSR column ids, graph id).
+__device__ __forceinline__ void row_info(const s2v_graph_t& g, int r, int& li, int& off, int& gi) {
+    if (g.period > 0) {
+        gi = r / g.period;
+        off = gi * g.period;
+        li = r - off;
+    } else {
+        li = r;
+        off = 0;
+        gi = __ldg(g.gid + r);
+    }
+}
+__device__ __forceinline__ int graph_npad(const s2v_graph_t& g, int gi) {
+    return g.npad ? __ldg(g.npad + gi) : g.npad_scalar;
+}
+__device__ __forceinline__ void graph_range(const s2v_graph_t& g, int gi, int& lo, int& hi) {
+    if (g.period > 0) { lo = gi * g.period; hi = lo + g.period; }
+    else { lo = __ldg(g.ptr + gi); hi = __ldg(g.ptr + gi + 1); }
+}
+
+// smem Wt[k*P + n] = W[n*P + k]   (y = x * W^T form)
+template <int P>
+__device__ __forceinline__ void load_w_transposed(float* Ws, const float* __restrict__ W) {
+    for (int e = threadIdx.x; e < P * P; e += S2V_THREADS) {
+        int n = e / P, k = e - n * P;
+        Ws[k * P + n] = __ldg(W + e);
+    }
+}
+// smem Ws[n*P + k] = W[n*P + k]   (y = g * W form)
+template <int P>
+__device__ __forceinline__ void load_w_plain(float* Ws, const float* __restrict__ W) {
+    for (int e = threadIdx.x * 4; e < P * P; e += S2V_THREADS * 4) st4(Ws + e, ldg4(W + e));
+}
+
+// Copy `rows` consecutive rows of a [*,P] global matrix into a row tile; rows beyond are zeroed.
+template <int P>
+__device__ __forceinline__ void load_tile(float* As, const float* __restrict__ src, int rows) {
+    constexpr int LDA = Cfg<P>::LDA;
+    constexpr int V = P / 4;
+    for (int e = threadIdx.x; e < S2V_TM * V; e += S2V_THREADS) {
+        int r = e / V, c = e - r * V;
+        float4 v = r < rows ? ldg4(src + (size_t)r * P + 4 * c) : f4zero();
+        st4(As + r * LDA + 4 * c, v);
+    }
+}
+
+// acc[i][0..3] += sum_k As[row_i][k] * Ws[k][4tx..4tx+3],  row_i = ty + RG*i
+template <int P>
+__device__ __forceinline__ void tile_gemm(const float* As, const float* Ws, float (&acc)[Cfg<P>::NR][4], int tx, int ty) {
+    constexpr int LDA = Cfg<P>::LDA, RG = Cfg<P>::RG, NR = Cfg<P>::NR;
+#pragma unroll 2
+    for (int k0 = 0; k0 < P; k0 += 4) {
+        float4 w0 = ld4(Ws + (k0 + 0) * P + 4 * tx);
+        float4 w1 = ld4(Ws + (k0 + 1) * P + 4 * tx);
+        float4 w2 = ld4(Ws + (k0 + 2) * P + 4 * tx);
+        float4 w3 = ld4(Ws + (k0 + 3) * P + 4 * tx);
+#pragma unroll
+        for (int i = 0; i < NR; ++i) {
+            int r = ty + RG * i;
+            if (NR * RG > S2V_TM && r >= S2V_TM) continue;
+            float4 a = ld4(As + r * LDA + k0);
+            acc[i][0] = fmaf(a.x, w0.x, acc[i][0]); acc[i][1] = fmaf(a.x, w0.y, acc[i][1]);
+            acc[i][2] = fmaf(a.x, w0.z, acc[i][2]); acc[i][3] = fmaf(a.x, w0.w, acc[i][3]);
+            acc[i][0] = fmaf(a.y, w1.x, acc[i][0]); acc[i][1] = fmaf(a.y, w1.y, acc[i][1]);
+            acc[i][2] = fmaf(a.y, w1.z, acc[i][2]); acc[i][3] = fmaf(a.y, w1.w, acc[i][3]);
+            acc[i][0] = fmaf(a.z, w2.x, acc[i][0]); acc[i][1] = fmaf(a.z, w2.y, acc[i][1]);
+            acc[i][2] = fmaf(a.z, w2.z, acc[i][2]); acc[i][3] = fmaf(a.z, w2.w, acc[i][3]);
+            acc[i][0] = fmaf(a.w, w3.x, acc[i][0]); acc[i][1] = fmaf(a.w, w3.y, acc[i][1]);
+            acc[i][2] = fmaf(a.w, w3.z, acc[i][2]); acc[i][3] = fmaf(a.w, w3.w, acc[i][3]);
+        }
+    }
+}
+
+// racc[i][0..3] += sum_{r<rows} As[r][ty + RG*i] * Bs[r][4tx..4tx+3]     (P x P output)
+template <int P>
+__device__ __forceinline__ void tile_reduce_gemm(const float* As, const float* Bs, int rows,
+                                                 float (&racc)[Cfg<P>::NRR][4], int tx, int ty) {
+    constexpr int LDA = Cfg<P>::LDA, RG = Cfg<P>::RG, NRR = Cfg<P>::NRR;
+#pragma unroll 4
+    for (int r = 0; r < rows; ++r) {
+        float4 b = ld4(Bs + r * LDA + 4 * tx);
+#pragma unroll
+        for (int i = 0; i < NRR; ++i) {
+            int n = ty + RG * i;
+            if (NRR * RG > P && n >= P) continue;
+            float a = As[r * LDA + n];
+            racc[i][0] = fmaf(a, b.x, racc[i][0]); racc[i][1] = fmaf(a, b.y, racc[i][1]);
+            racc[i][2] = fmaf(a, b.z, racc[i][2]); racc[i][3] = fmaf(a, b.w, racc[i][3]);
+        }
+    }
+}
+
+// Store the P x P reduction accumulators of this CTA to dst[n*P + k] (assign or accumulate).
+template <int P>
+__device__ __forceinline__ void store_racc(float* dst, const float (&racc)[Cfg<P>::NRR][4], int tx, int ty,
+                                           bool active, bool accumulate) {
+    constexpr int RG = Cfg<P>::RG, NRR = Cfg<P>::NRR;
+    if (!active) return;
+#pragma unroll
+    for (int i = 0; i < NRR; ++i) {
+        int n = ty + RG * i;
+        if (n >= P) continue;
+        float4 v = make_float4(racc[i][0], racc[i][1], racc[i][2], racc[i][3]);
+        float* d = dst + n * P + 4 * tx;
+        if (accumulate) v = f4add(ld4(d), v);
+        st4(d, v);
+    }
+}
+
+// Column sums held per thread (four columns, partial over the thread's rows) ->
+// dst[0..P) summed over row groups in fixed order.  scratch: RG*P floats of smem.
+template <int P>
+__device__ __forceinline__ void reduce_columns(float* scratch, const float (&v)[4], float* dst, int tx, int ty,
+                                               bool active, bool accumulate) {
+    constexpr int RG = Cfg<P>::RG;
+    __syncthreads();
+    if (active) st4(scratch + ty * P + 4 * tx, make_float4(v[0], v[1], v[2], v[3]));
+    __syncthreads();
+    if (threadIdx.x < P) {
+        float s = 0.f;
+        for (int g = 0; g < RG; ++g) s += scratch[g * P + threadIdx.x];
+        dst[threadIdx.x] = accumulate ? dst[threadIdx.x] + s : s;
+    }
+    __syncthreads();
+}
+
+// Sum of the neighbour rows of CSR row `li` (float4 slice c4 of each row), fixed order.
+__device__ __forceinline__ float4 gather_row(const float* __restrict__ src, const int32_t* __restrict__ rowptr,
+                                             const int32_t* __restrict__ col, int li, int off, int P, int c4) {
+    int beg = __ldg(rowptr + li), end = __ldg(rowptr + li + 1);
+    float4 acc = f4zero();
+    int k = beg;
+    for (; k + 4 <= end; k += 4) {
+        int j0 = __ldg(col + k), j1 = __ldg(col + k + 1), j2 = __ldg(col + k + 2), j3 = __ldg(col + k + 3);
+        float4 v0 = ldg4(src + (size_t)(off + j0) * P + 4 * c4);
+        float4 v1 = ldg4(src + (size_t)(off + j1) * P + 4 * c4);
+        float4 v2 = ldg4(src + (size_t)(off + j2) * P + 4 * c4);
+        float4 v3 = ldg4(src + (size_t)(off + j3) * P + 4 * c4);
+        acc = f4add(f4add(f4add(f4add(acc, v0), v1), v2), v3);
+    }
+    if (k < end) {
+        int n = end - k;
+        int j0 = __ldg(col + k);
+        int j1 = n > 1 ? __ldg(col + k + 1) : j0;
+        int j2 = n > 2 ? __ldg(col + k + 2) : j0;
+        float4 v0 = ldg4(src + (size_t)(off + j0) * P + 4 * c4);
+        float4 v1 = n > 1 ? ldg4(src + (size_t)(off + j1) * P + 4 * c4) : f4zero();
+        float4 v2 = n > 2 ? ldg4(src + (size_t)(off + j2) * P + 4 * c4) : f4zero();
+        acc = f4add(acc, v0);
+        if (n > 1) acc = f4add(acc, v1);
+        if (n > 2) acc = f4add(acc, v2);
+    }
+    return acc;
+}
+
+// Gather a tile: As[rl][:] = sum of neighbour rows of batch row row0+rl (zeros past num_nodes).
+template <int P>
+__device__ __forceinline__ void gather_tile(float* As, const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
+                                            const int32_t* __restrict__ col, const float* __restrict__ src,
+                                            int row0, int rows) {
+    constexpr int LDA = Cfg<P>::LDA, LPR = Cfg<P>::LPR, RPP = Cfg<P>::RPP;
+    constexpr int ROWS_PER_WARP = S2V_TM / (S2V_THREADS / 32);
+    int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    int sub = lane / LPR, c4 = lane - sub * LPR;
+    if (sub >= RPP) return;
+    for (int rr = sub; rr < ROWS_PER_WARP; rr += RPP) {
+        int rl = warp * ROWS_PER_WARP + rr;
+        float4 acc = f4zero();
+        if (rl < rows) {
+            int li, off, gi;
+            int r = row0 + rl;
+            if (g.period > 0) { gi = r / g.period; off = gi * g.period; li = r - off; }
+            else { li = r; off = 0; }
+            acc = gather_row(src, rowptr, col, li, off, P, c4);
+        }
+        st4(As + rl * LDA + 4 * c4, acc);
+    }
+}
+
+#define S2V_RETURN_IF(e) do { int _c = (int)(e); if (_c != 0) return _c; } while (0)
+
+// Persistent launch: one wave of resident CTAs (SM count x occupancy), never more than the tile count.
+static inline int s2v_persistent_grid(const void* kernel, int smem_bytes, int num_tiles) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, S2V_THREADS, smem_bytes);
+    if (per_sm < 1) per_sm = 1;
+    int grid = sms * per_sm;
+    if (grid > S2V_MAX_GRID) grid = S2V_MAX_GRID;
+    if (grid > num_tiles) grid = num_tiles;
+    return grid < 1 ? 1 : grid;
+}
+
+#define S2V_DISPATCH_P(P_, CALL)                         \
+    switch (P_) {                                        \
+        case 8: { constexpr int PP = 8; CALL; } break;   \
+        case 16: { constexpr int PP = 16; CALL; } break; \
+        case 24: { constexpr int PP = 24; CALL; } break; \
+        case 32: { constexpr int PP = 32; CALL; } break; \
+        case 48: { constexpr int PP = 48; CALL; } break; \
+        case 64: { constexpr int PP = 64; CALL; } break; \
+        default: return S2V_ERR_UNSUPPORTED;             \
+    }

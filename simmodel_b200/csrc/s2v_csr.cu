@@ -1,0 +1,180 @@
+// K1: deterministic CSR / CSC builder over a (batched) int64 edge_index.
+// Integer-only.  Result is bit-identical to a stable sort of the edges by row
+// (resp. column): inside a row the entries keep the input edge order
+// (oracle/s2v_ref.py:csr_from_edge_index).  Replaces the dense adjacency the
+// reference ships to the device (comb_opt.py:342,538; models_basic_lstm.py:515).
+//
+// histogram (integer atomics: order-independent counts) -> exclusive scan ->
+// bucket fill with edge ids (order inside a bucket arbitrary) -> per-row sort of the
+// edge ids (restores input order => deterministic) -> column ids.
+#include "s2v_common.cuh"
+
+#define SCAN_BLOCK 1024
+
+__global__ void k_csr_count(const int64_t* __restrict__ ei, int64_t E, int64_t n, int32_t* __restrict__ cnt_row,
+                            int32_t* __restrict__ cnt_col, int32_t* __restrict__ err) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = ei[e], d = ei[E + e];
+        if (s < 0 || s >= n || d < 0 || d >= n) { atomicExch(err, 1); continue; }
+        atomicAdd(cnt_row + s, 1);
+        atomicAdd(cnt_col + d, 1);
+    }
+}
+
+// out[i] = exclusive prefix inside the block, block_sums[b] = block total
+__global__ void __launch_bounds__(SCAN_BLOCK)
+k_scan_local(const int32_t* __restrict__ in, int32_t* __restrict__ out, int32_t* __restrict__ block_sums, int64_t n) {
+    __shared__ int32_t warp_tot[SCAN_BLOCK / 32];
+    int64_t i = blockIdx.x * (int64_t)SCAN_BLOCK + threadIdx.x;
+    int32_t v = i < n ? in[i] : 0;
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int32_t x = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+        int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+        if (lane >= o) x += y;
+    }
+    if (lane == 31) warp_tot[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        int32_t w = warp_tot[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+            if (lane >= o) w += y;
+        }
+        warp_tot[lane] = w;
+    }
+    __syncthreads();
+    int32_t incl = x + (warp > 0 ? warp_tot[warp - 1] : 0);
+    if (i < n) out[i] = incl - v;
+    if (threadIdx.x == SCAN_BLOCK - 1) block_sums[blockIdx.x] = incl;
+}
+
+// single block: exclusive scan of block_sums in place; writes the grand total to *total
+__global__ void __launch_bounds__(SCAN_BLOCK)
+k_scan_blocks(int32_t* __restrict__ block_sums, int nb, int32_t* __restrict__ total) {
+    __shared__ int32_t warp_tot[SCAN_BLOCK / 32];
+    __shared__ int32_t carry_s;
+    if (threadIdx.x == 0) carry_s = 0;
+    __syncthreads();
+    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int base = 0; base < nb; base += SCAN_BLOCK) {
+        int i = base + threadIdx.x;
+        int32_t v = i < nb ? block_sums[i] : 0;
+        int32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            int32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) warp_tot[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            int32_t w = warp_tot[lane];
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                int32_t y = __shfl_up_sync(0xffffffffu, w, o);
+                if (lane >= o) w += y;
+            }
+            warp_tot[lane] = w;
+        }
+        __syncthreads();
+        int32_t incl = x + (warp > 0 ? warp_tot[warp - 1] : 0) + carry_s;
+        if (i < nb) block_sums[i] = incl - v;
+        __syncthreads();
+        if (threadIdx.x == SCAN_BLOCK - 1) carry_s = incl;
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *total = carry_s;
+}
+
+__global__ void __launch_bounds__(SCAN_BLOCK)
+k_scan_add(int32_t* __restrict__ out, const int32_t* __restrict__ block_sums, const int32_t* __restrict__ total, int64_t n) {
+    int64_t i = blockIdx.x * (int64_t)SCAN_BLOCK + threadIdx.x;
+    if (i < n) out[i] += block_sums[blockIdx.x];
+    if (i == 0) out[n] = *total;
+}
+
+__global__ void k_csr_fill(const int64_t* __restrict__ ei, int64_t E, int64_t n, const int32_t* __restrict__ rowptr,
+                           const int32_t* __restrict__ rowptr_t, int32_t* __restrict__ cur_row,
+                           int32_t* __restrict__ cur_col, int32_t* __restrict__ eid_row, int32_t* __restrict__ eid_col) {
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
+        int64_t s = ei[e], d = ei[E + e];
+        if (s < 0 || s >= n || d < 0 || d >= n) continue;
+        eid_row[rowptr[s] + atomicAdd(cur_row + s, 1)] = (int32_t)e;
+        eid_col[rowptr_t[d] + atomicAdd(cur_col + d, 1)] = (int32_t)e;
+    }
+}
+
+// One thread per row: sort the edge ids of the bucket ascending (restores the input
+// order), then emit the other endpoint.  which = 1: emit ei[1][e] (row form), 0: ei[0][e].
+__global__ void k_csr_sort_emit(const int64_t* __restrict__ ei, int64_t E, int64_t n, const int32_t* __restrict__ ptr,
+                                int32_t* __restrict__ eid, int32_t* __restrict__ out, int which) {
+    for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        int beg = ptr[i], end = ptr[i + 1];
+        for (int a = beg + 1; a < end; ++a) {
+            int32_t key = eid[a];
+            int b = a - 1;
+            while (b >= beg && eid[b] > key) { eid[b + 1] = eid[b]; --b; }
+            eid[b + 1] = key;
+        }
+        const int64_t* other = ei + (which ? E : 0);
+        for (int a = beg; a < end; ++a) out[a] = (int32_t)other[eid[a]];
+    }
+}
+
+static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
+
+// workspace layout (int32): err[64] | cnt_row[n] | cnt_col[n] | eid_row[E] | eid_col[E] | block_sums[nb+1] x2 | totals[2]
+extern "C" int64_t s2v_csr_workspace_bytes(int64_t n, int64_t E) {
+    int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1;
+    return (64 + align_up(n, 64) * 2 + align_up(E, 64) * 2 + align_up(nb, 64) * 2 + 64) * 4;
+}
+
+static int scan_exclusive(const int32_t* in, int32_t* out, int32_t* block_sums, int32_t* total, int64_t n, cudaStream_t st) {
+    int nb = (int)((n + SCAN_BLOCK - 1) / SCAN_BLOCK);
+    if (nb < 1) nb = 1;
+    k_scan_local<<<nb, SCAN_BLOCK, 0, st>>>(in, out, block_sums, n);
+    k_scan_blocks<<<1, SCAN_BLOCK, 0, st>>>(block_sums, nb, total);
+    k_scan_add<<<nb, SCAN_BLOCK, 0, st>>>(out, block_sums, total, n);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int s2v_csr_build(const int64_t* edge_index, int64_t E, int64_t n,
+                             int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t, int32_t* indeg,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+    if (E < 0 || n < 0 || n >= INT32_MAX || E >= INT32_MAX) return S2V_ERR_BAD_ARG;
+    if (!rowptr || !rowptr_t || !workspace || (n > 0 && !indeg)) return S2V_ERR_BAD_ARG;
+    if (E > 0 && (!edge_index || !col || !col_t)) return S2V_ERR_BAD_ARG;
+    if (workspace_bytes < s2v_csr_workspace_bytes(n, E)) return S2V_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    int32_t* w = (int32_t*)workspace;
+    int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1;
+    int32_t* err = w;
+    int32_t* cnt_row = err + 64;
+    int32_t* cnt_col = cnt_row + align_up(n, 64);
+    int32_t* eid_row = cnt_col + align_up(n, 64);
+    int32_t* eid_col = eid_row + align_up(E, 64);
+    int32_t* bs_row = eid_col + align_up(E, 64);
+    int32_t* bs_col = bs_row + align_up(nb, 64);
+    int32_t* totals = bs_col + align_up(nb, 64);
+    S2V_RETURN_IF(cudaMemsetAsync(w, 0, (64 + align_up(n, 64) * 2) * 4, st));
+    int eb = (int)((E + 255) / 256);
+    if (eb > 148 * 32) eb = 148 * 32;
+    if (eb < 1) eb = 1;
+    int rb = (int)((n + 127) / 128);
+    if (rb > 148 * 32) rb = 148 * 32;
+    if (rb < 1) rb = 1;
+    if (E > 0) k_csr_count<<<eb, 256, 0, st>>>(edge_index, E, n, cnt_row, cnt_col, err);
+    if (n > 0) S2V_RETURN_IF(cudaMemcpyAsync(indeg, cnt_col, n * 4, cudaMemcpyDeviceToDevice, st));
+    S2V_RETURN_IF(scan_exclusive(cnt_row, rowptr, bs_row, totals, n, st));
+    S2V_RETURN_IF(scan_exclusive(cnt_col, rowptr_t, bs_col, totals + 1, n, st));
+    if (E > 0) {
+        S2V_RETURN_IF(cudaMemsetAsync(cnt_row, 0, align_up(n, 64) * 2 * 4, st));
+        k_csr_fill<<<eb, 256, 0, st>>>(edge_index, E, n, rowptr, rowptr_t, cnt_row, cnt_col, eid_row, eid_col);
+        k_csr_sort_emit<<<rb, 128, 0, st>>>(edge_index, E, n, rowptr, eid_row, col, 1);
+        k_csr_sort_emit<<<rb, 128, 0, st>>>(edge_index, E, n, rowptr_t, eid_col, col_t, 0);
+    }
+    return (int)cudaGetLastError();
+}

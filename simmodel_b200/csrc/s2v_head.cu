@@ -1,0 +1,422 @@
+// Pooling + Q / logit head of struct2vec and its backward.
+// Math (modules/gnn/comb_opt.py:248-273,
+// modules/ppo/models_basic_lstm.py:530-538,548-562):
+//   pool_g = (1/n_g) sum_{i in g} mu_i         (norm_agg; plain sum otherwise; count clamped >= 1)
+//   G_g    = theta6 pool_g + b6 ;  L_i = theta7 mu_i + b7
+//   q_i    = w5[:p] . relu(G_g(i)) + w5[p:] . relu(L_i) + b5
+#include "s2v_common.cuh"
+
+// ------------------------------------------------------------------------------------
+// pooling: one CTA per graph, fixed summation order
+// ------------------------------------------------------------------------------------
+template <int P>
+__device__ __forceinline__ void pool_graph(const float* __restrict__ mu, int lo, int hi, float* scratch, float* pool_s,
+                                           float scale) {
+    using C = Cfg<P>;
+    const int t = threadIdx.x;
+    const int tx = t % C::TXP, ty = t / C::TXP;
+    float4 s = f4zero();
+    if (t < C::ACTIVE)
+        for (int r = lo + ty; r < hi; r += C::RG) s = f4add(s, ldg4(mu + (size_t)r * P + 4 * tx));
+    if (t < C::ACTIVE) st4(scratch + ty * P + 4 * tx, s);
+    __syncthreads();
+    if (t < P) {
+        float a = 0.f;
+        for (int k = 0; k < C::RG; ++k) a += scratch[k * P + t];
+        pool_s[t] = a * scale;
+    }
+    __syncthreads();
+}
+
+template <int P>
+__global__ void __launch_bounds__(S2V_THREADS)
+k_pool(s2v_graph_t g, int norm_agg, const float* __restrict__ mu, float* __restrict__ pool,
+       const float* __restrict__ theta6_w, const float* __restrict__ theta6_b, float* __restrict__ gstate) {
+    using C = Cfg<P>;
+    __shared__ __align__(16) float scratch[C::RG * P];
+    __shared__ float pool_s[P];
+    const int gi = blockIdx.x;
+    int lo, hi;
+    graph_range(g, gi, lo, hi);
+    int n = hi - lo;
+    float scale = norm_agg ? 1.f / (float)(n > 1 ? n : 1) : 1.f;
+    pool_graph<P>(mu, lo, hi, scratch, pool_s, 1.f);
+    const int t = threadIdx.x;
+    if (t < P) {
+        // torch: sum / count (a true division), not sum * (1/count)
+        float pv = norm_agg ? pool_s[t] / (float)(n > 1 ? n : 1) : pool_s[t];
+        pool_s[t] = pv;
+        pool[(size_t)gi * P + t] = pv;
+    }
+    (void)scale;
+    __syncthreads();
+    if (gstate != nullptr && t < P) {
+        float a = __ldg(theta6_b + t);
+        for (int k = 0; k < P; ++k) a = fmaf(__ldg(theta6_w + t * P + k), pool_s[k], a);
+        gstate[(size_t)gi * P + t] = a;
+    }
+}
+
+template <int P>
+__global__ void __launch_bounds__(S2V_THREADS)
+k_pool_bwd(s2v_graph_t g, int norm_agg, const float* __restrict__ dpool, float* __restrict__ dmu) {
+    constexpr int V = P / 4;
+    const int64_t total = (int64_t)g.num_nodes * V;
+    for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < total; e += (int64_t)gridDim.x * blockDim.x) {
+        int r = (int)(e / V), c = (int)(e - (int64_t)r * V);
+        int li, off, gi;
+        row_info(g, r, li, off, gi);
+        int lo, hi;
+        graph_range(g, gi, lo, hi);
+        int n = hi - lo;
+        float4 d = ldg4(dpool + (size_t)gi * P + 4 * c);
+        if (norm_agg) { float dn = (float)(n > 1 ? n : 1); d.x /= dn; d.y /= dn; d.z /= dn; d.w /= dn; }
+        st4(dmu + (size_t)r * P + 4 * c, d);
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// head forward: tile kernel
+// ------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(S2V_THREADS)
+k_head(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const float* __restrict__ gstate,
+       float* __restrict__ q, int num_tiles) {
+    using C = Cfg<P>;
+    extern __shared__ __align__(16) float smem[];
+    float* Wt7 = smem;                        // Wt[k][n] = theta7[n][k]
+    float* As = Wt7 + C::W_FLOATS;            // mu tile
+    float* red = As + C::TILE_FLOATS;         // [TM][TXP]
+    float* vec = red + S2V_TM * C::TXP;       // b7, w5a, w5b
+    float* b7 = vec, *w5a = vec + P, *w5b = vec + 2 * P;
+    const int t = threadIdx.x;
+    const int tx = t % C::TXP, ty = t / C::TXP;
+    const bool active = t < C::ACTIVE;
+    load_w_transposed<P>(Wt7, prm.theta7_w);
+    if (t < P) {
+        b7[t] = __ldg(prm.theta7_b + t);
+        w5a[t] = __ldg(prm.theta5_w + t);
+        w5b[t] = __ldg(prm.theta5_w + P + t);
+    }
+    const float b5 = __ldg(prm.theta5_b);
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * S2V_TM;
+        const int rows = min(S2V_TM, g.num_nodes - row0);
+        load_tile<P>(As, mu + (size_t)row0 * P, rows);
+        __syncthreads();
+        if (active) {
+            float acc[C::NR][4];
+#pragma unroll
+            for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+            tile_gemm<P>(As, Wt7, acc, tx, ty);
+            float4 bb = ld4(b7 + 4 * tx), wa = ld4(w5a + 4 * tx), wb = ld4(w5b + 4 * tx);
+#pragma unroll
+            for (int i = 0; i < C::NR; ++i) {
+                int rl = ty + C::RG * i;
+                if (rl >= S2V_TM) continue;
+                float s = 0.f;
+                if (rl < rows) {
+                    int li, off, gi;
+                    row_info(g, row0 + rl, li, off, gi);
+                    float4 G = ldg4(gstate + (size_t)gi * P + 4 * tx);
+                    s = fmaf(wa.x, relu(G.x), s); s = fmaf(wa.y, relu(G.y), s);
+                    s = fmaf(wa.z, relu(G.z), s); s = fmaf(wa.w, relu(G.w), s);
+                    s = fmaf(wb.x, relu(acc[i][0] + bb.x), s); s = fmaf(wb.y, relu(acc[i][1] + bb.y), s);
+                    s = fmaf(wb.z, relu(acc[i][2] + bb.z), s); s = fmaf(wb.w, relu(acc[i][3] + bb.w), s);
+                }
+                red[rl * C::TXP + tx] = s;
+            }
+        }
+        __syncthreads();
+        if (t < rows) {
+            float s = b5;
+            for (int k = 0; k < C::TXP; ++k) s += red[t * C::TXP + k];
+            q[row0 + t] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// head backward
+// ------------------------------------------------------------------------------------
+// per graph workspace row: dG [P], dpool_scaled [P], s_g, pad
+template <int P>
+__global__ void __launch_bounds__(S2V_THREADS)
+k_head_bwd_graph(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ gstate,
+                 const float* __restrict__ dq, float* __restrict__ per_graph) {
+    __shared__ float red[S2V_THREADS];
+    __shared__ float dG[P];
+    const int gi = blockIdx.x, t = threadIdx.x;
+    int lo, hi;
+    graph_range(g, gi, lo, hi);
+    float s = 0.f;
+    for (int r = lo + t; r < hi; r += S2V_THREADS) s += __ldg(dq + r);
+    red[t] = s;
+    __syncthreads();
+    for (int w = S2V_THREADS / 2; w > 0; w >>= 1) {
+        if (t < w) red[t] += red[t + w];
+        __syncthreads();
+    }
+    const float sg = red[0];
+    float* out = per_graph + (size_t)gi * (2 * P + 4);
+    if (t < P) {
+        float G = __ldg(gstate + (size_t)gi * P + t);
+        float d = G > 0.f ? sg * __ldg(prm.theta5_w + t) : 0.f;
+        dG[t] = d;
+        out[t] = d;
+    }
+    __syncthreads();
+    if (t < P) {
+        float a = 0.f;
+        for (int n = 0; n < P; ++n) a = fmaf(__ldg(prm.theta6_w + n * P + t), dG[n], a);
+        int cnt = hi - lo;
+        if (prm.norm_agg) a /= (float)(cnt > 1 ? cnt : 1);
+        out[P + t] = a;
+    }
+    if (t == 0) { out[2 * P] = sg; out[2 * P + 1] = 0.f; }
+}
+
+template <int P>
+struct HeadPartial {
+    static constexpr int TH7 = 0;              // P*P  sum_i dL_i mu_i^T
+    static constexpr int B7 = P * P;           // P    sum_i dL_i
+    static constexpr int W5B = B7 + P;         // P    sum_i dq_i relu(L_i)
+    static constexpr int SIZE = W5B + P;
+};
+
+template <int P>
+__global__ void __launch_bounds__(S2V_THREADS)
+k_head_bwd(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const float* __restrict__ dq,
+           const float* __restrict__ per_graph, int mask_relu, float* __restrict__ dmu,
+           float* __restrict__ partial, int num_tiles) {
+    using C = Cfg<P>;
+    using HP = HeadPartial<P>;
+    extern __shared__ __align__(16) float smem[];
+    float* Wt7 = smem;                        // Wt[k][n] = theta7[n][k]   (L = mu theta7^T)
+    float* W7 = Wt7 + C::W_FLOATS;            // theta7 as stored [n][k]     (dmu = dL theta7)
+    float* As = W7 + C::W_FLOATS;             // mu tile
+    float* Bs = As + C::TILE_FLOATS;          // dL tile
+    float* vec = Bs + C::TILE_FLOATS;         // b7, w5b
+    float* b7 = vec, *w5b = vec + P;
+    float* scratch = vec + 2 * P;             // [RG][P]
+    const int t = threadIdx.x;
+    const int tx = t % C::TXP, ty = t / C::TXP;
+    const bool active = t < C::ACTIVE;
+    load_w_transposed<P>(Wt7, prm.theta7_w);
+    load_w_plain<P>(W7, prm.theta7_w);
+    if (t < P) { b7[t] = __ldg(prm.theta7_b + t); w5b[t] = __ldg(prm.theta5_w + P + t); }
+    float racc[C::NRR][4];
+#pragma unroll
+    for (int i = 0; i < C::NRR; ++i) racc[i][0] = racc[i][1] = racc[i][2] = racc[i][3] = 0.f;
+    float pB7[4] = {0.f, 0.f, 0.f, 0.f}, pW5[4] = {0.f, 0.f, 0.f, 0.f};
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * S2V_TM;
+        const int rows = min(S2V_TM, g.num_nodes - row0);
+        load_tile<P>(As, mu + (size_t)row0 * P, rows);
+        __syncthreads();
+        if (active) {
+            float acc[C::NR][4];
+#pragma unroll
+            for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+            tile_gemm<P>(As, Wt7, acc, tx, ty);
+            float4 bb = ld4(b7 + 4 * tx), wb = ld4(w5b + 4 * tx);
+#pragma unroll
+            for (int i = 0; i < C::NR; ++i) {
+                int rl = ty + C::RG * i;
+                if (rl >= S2V_TM) continue;
+                float4 dL = f4zero();
+                if (rl < rows) {
+                    float d = __ldg(dq + row0 + rl);
+                    float l0 = acc[i][0] + bb.x, l1 = acc[i][1] + bb.y, l2 = acc[i][2] + bb.z, l3 = acc[i][3] + bb.w;
+                    dL = make_float4(l0 > 0.f ? d * wb.x : 0.f, l1 > 0.f ? d * wb.y : 0.f,
+                                     l2 > 0.f ? d * wb.z : 0.f, l3 > 0.f ? d * wb.w : 0.f);
+                    pW5[0] = fmaf(d, relu(l0), pW5[0]); pW5[1] = fmaf(d, relu(l1), pW5[1]);
+                    pW5[2] = fmaf(d, relu(l2), pW5[2]); pW5[3] = fmaf(d, relu(l3), pW5[3]);
+                    pB7[0] += dL.x; pB7[1] += dL.y; pB7[2] += dL.z; pB7[3] += dL.w;
+                }
+                st4(Bs + rl * C::LDA + 4 * tx, dL);
+            }
+        }
+        __syncthreads();
+        if (active) {
+            tile_reduce_gemm<P>(Bs, As, rows, racc, tx, ty);
+            float acc[C::NR][4];
+#pragma unroll
+            for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+            tile_gemm<P>(Bs, W7, acc, tx, ty);
+#pragma unroll
+            for (int i = 0; i < C::NR; ++i) {
+                int rl = ty + C::RG * i;
+                if (rl >= rows) continue;
+                int li, off, gi;
+                row_info(g, row0 + rl, li, off, gi);
+                float4 dp = ldg4(per_graph + (size_t)gi * (2 * P + 4) + P + 4 * tx);
+                float4 o = make_float4(acc[i][0] + dp.x, acc[i][1] + dp.y, acc[i][2] + dp.z, acc[i][3] + dp.w);
+                if (mask_relu) {
+                    float4 m = ld4(As + rl * C::LDA + 4 * tx);
+                    o = make_float4(m.x > 0.f ? o.x : 0.f, m.y > 0.f ? o.y : 0.f, m.z > 0.f ? o.z : 0.f, m.w > 0.f ? o.w : 0.f);
+                }
+                st4(dmu + (size_t)(row0 + rl) * P + 4 * tx, o);
+            }
+        }
+        __syncthreads();
+    }
+    float* my = partial + (size_t)blockIdx.x * HP::SIZE;
+    store_racc<P>(my + HP::TH7, racc, tx, ty, active, false);
+    reduce_columns<P>(scratch, pB7, my + HP::B7, tx, ty, active, false);
+    reduce_columns<P>(scratch, pW5, my + HP::W5B, tx, ty, active, false);
+}
+
+// grad layout: theta5.w [2P] (global part, local part), theta5.b [1], theta6.w [P,P], theta6.b [P],
+//              theta7.w [P,P], theta7.b [P]
+template <int P>
+__global__ void __launch_bounds__(256)
+k_head_finalize(int num_graphs, const float* __restrict__ per_graph, const float* __restrict__ pool,
+                const float* __restrict__ gstate, const float* __restrict__ partial, int n_part,
+                float* __restrict__ grad) {
+    using HP = HeadPartial<P>;
+    const int t = threadIdx.x;
+    float* g5_w = grad;
+    float* g5_b = g5_w + 2 * P;
+    float* g6_w = g5_b + 1;
+    float* g6_b = g6_w + P * P;
+    float* g7_w = g6_b + P;
+    float* g7_b = g7_w + P * P;
+    const int PG = 2 * P + 4;
+    auto psum = [&](int off) {
+        float s = 0.f;
+        for (int c = 0; c < n_part; ++c) s += partial[(size_t)c * HP::SIZE + off];
+        return s;
+    };
+    if (blockIdx.x == 0) {
+        for (int e = t; e < P; e += blockDim.x) {
+            float a = 0.f, b = 0.f;
+            for (int gi = 0; gi < num_graphs; ++gi) {
+                float sg = per_graph[(size_t)gi * PG + 2 * P];
+                a = fmaf(sg, relu(gstate[(size_t)gi * P + e]), a);
+                b += per_graph[(size_t)gi * PG + e];
+            }
+            g5_w[e] = a;
+            g6_b[e] = b;
+            g5_w[P + e] = psum(HP::W5B + e);
+            g7_b[e] = psum(HP::B7 + e);
+        }
+        if (t == 0) {
+            float s = 0.f;
+            for (int gi = 0; gi < num_graphs; ++gi) s += per_graph[(size_t)gi * PG + 2 * P];
+            g5_b[0] = s;
+        }
+    } else if (blockIdx.x == 1) {
+        for (int e = t; e < P * P; e += blockDim.x) g7_w[e] = psum(HP::TH7 + e);
+    } else {
+        // dtheta6[n][k] = sum_g dG_g[n] pool_g[k]; blocks 2.. split the P*P outputs
+        int nb = gridDim.x - 2, b = blockIdx.x - 2;
+        for (int e = b * blockDim.x + t; e < P * P; e += nb * blockDim.x) {
+            int n = e / P, k = e - n * P;
+            float a = 0.f;
+            for (int gi = 0; gi < num_graphs; ++gi)
+                a = fmaf(per_graph[(size_t)gi * PG + n], pool[(size_t)gi * P + k], a);
+            g6_w[e] = a;
+        }
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// host launchers
+// ------------------------------------------------------------------------------------
+
+template <int P>
+static int head_forward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm, const float* mu,
+                             float* pool, float* gstate, float* q, cudaStream_t st) {
+    using C = Cfg<P>;
+    k_pool<P><<<g.num_graphs, S2V_THREADS, 0, st>>>(g, prm.norm_agg, mu, pool, prm.theta6_w, prm.theta6_b, gstate);
+    const int tiles = (g.num_nodes + S2V_TM - 1) / S2V_TM;
+    if (tiles > 0) {
+        int smem = (C::W_FLOATS + C::TILE_FLOATS + S2V_TM * C::TXP + 3 * P) * 4;
+        S2V_RETURN_IF(cudaFuncSetAttribute(k_head<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        int grid = s2v_persistent_grid((const void*)k_head<P>, smem, tiles);
+        k_head<P><<<grid, S2V_THREADS, smem, st>>>(g, prm, mu, gstate, q, tiles);
+    }
+    return (int)cudaGetLastError();
+}
+
+template <int P>
+static int head_backward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm, const float* mu,
+                              const float* pool, const float* gstate, const float* dq, int mask_relu,
+                              float* dmu, float* ws, float* grad, cudaStream_t st) {
+    using C = Cfg<P>;
+    using HP = HeadPartial<P>;
+    float* per_graph = ws;
+    float* partial = ws + (size_t)g.num_graphs * (2 * P + 4);
+    k_head_bwd_graph<P><<<g.num_graphs, S2V_THREADS, 0, st>>>(g, prm, gstate, dq, per_graph);
+    const int tiles = (g.num_nodes + S2V_TM - 1) / S2V_TM;
+    int smem = (2 * C::W_FLOATS + 2 * C::TILE_FLOATS + 2 * P + C::RG * P) * 4;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_head_bwd<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    int grid = s2v_persistent_grid((const void*)k_head_bwd<P>, smem, tiles);
+    k_head_bwd<P><<<grid, S2V_THREADS, smem, st>>>(g, prm, mu, dq, per_graph, mask_relu, dmu, partial, tiles);
+    k_head_finalize<P><<<2 + 16, 256, 0, st>>>(g.num_graphs, per_graph, pool, gstate, partial, grid, grad);
+    (void)HP::SIZE;
+    return (int)cudaGetLastError();
+}
+
+
+static int check_graph_h(const s2v_graph_t* g) {
+    if (!g || g->num_nodes < 0 || g->num_graphs < 0 || g->period < 0) return S2V_ERR_BAD_ARG;
+    if (g->period == 0 && (!g->ptr || !g->gid) && g->num_nodes > 0) return S2V_ERR_BAD_ARG;
+    if (g->period > 0 && (int64_t)g->period * g->num_graphs != g->num_nodes) return S2V_ERR_BAD_ARG;
+    return 0;
+}
+
+extern "C" int64_t s2v_head_grad_floats(int32_t P) { return 2 * (int64_t)P + 1 + 2 * ((int64_t)P * P + P); }
+
+extern "C" int64_t s2v_head_backward_workspace_bytes(int32_t P, int32_t num_graphs) {
+    return ((int64_t)num_graphs * (2 * P + 4) + (int64_t)S2V_MAX_GRID * (P * P + 2 * P)) * 4;
+}
+
+extern "C" int s2v_head_forward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu,
+                                float* pool, float* gstate, float* q, void* stream) {
+    S2V_RETURN_IF(check_graph_h(g));
+    if (!prm || !mu || !pool || !gstate || !q) return S2V_ERR_BAD_ARG;
+    if (g->num_graphs == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    S2V_DISPATCH_P(prm->emb_dim, return head_forward_impl<PP>(*g, *prm, mu, pool, gstate, q, st));
+    return 0;
+}
+
+extern "C" int s2v_head_backward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu,
+                                 const float* pool, const float* gstate, const float* dq, int32_t mask_relu,
+                                 float* dmu, void* workspace, int64_t workspace_bytes, float* grad, void* stream) {
+    S2V_RETURN_IF(check_graph_h(g));
+    if (!prm || !mu || !pool || !gstate || !dq || !dmu || !workspace || !grad) return S2V_ERR_BAD_ARG;
+    if (workspace_bytes < s2v_head_backward_workspace_bytes(prm->emb_dim, g->num_graphs)) return S2V_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (g->num_nodes == 0 || g->num_graphs == 0)
+        return (int)cudaMemsetAsync(grad, 0, s2v_head_grad_floats(prm->emb_dim) * 4, st);
+    S2V_DISPATCH_P(prm->emb_dim, return head_backward_impl<PP>(*g, *prm, mu, pool, gstate, dq, mask_relu, dmu,
+                                                                (float*)workspace, grad, st));
+    return 0;
+}
+
+extern "C" int s2v_pool_forward(const s2v_graph_t* g, int32_t P, int32_t norm_agg, const float* mu, float* pool, void* stream) {
+    S2V_RETURN_IF(check_graph_h(g));
+    if (!mu || !pool) return S2V_ERR_BAD_ARG;
+    if (g->num_graphs == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    S2V_DISPATCH_P(P, (k_pool<PP><<<g->num_graphs, S2V_THREADS, 0, st>>>(*g, norm_agg, mu, pool, nullptr, nullptr, nullptr)));
+    return (int)cudaGetLastError();
+}
+
+extern "C" int s2v_pool_backward(const s2v_graph_t* g, int32_t P, int32_t norm_agg, const float* dpool, float* dmu, void* stream) {
+    S2V_RETURN_IF(check_graph_h(g));
+    if (!dpool || !dmu) return S2V_ERR_BAD_ARG;
+    if (g->num_nodes == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+    int64_t total = (int64_t)g->num_nodes * (P / 4);
+    int blocks = (int)((total + S2V_THREADS - 1) / S2V_THREADS);
+    if (blocks > 148 * 16) blocks = 148 * 16;
+    S2V_DISPATCH_P(P, (k_pool_bwd<PP><<<blocks, S2V_THREADS, 0, st>>>(*g, norm_agg, dpool, dmu)));
+    return (int)cudaGetLastError();
+}

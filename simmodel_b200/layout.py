@@ -1,0 +1,138 @@
+"""Graph layout in HBM: deterministic CSR / CSC over a PyG-style batched edge_index.
+
+Replaces the dense padded adjacency the reference ships per call
+(comb_opt.py:342 ``torch.stack(Ws).to(device)``, :538 ``F.pad(W,...)``;
+models_basic_lstm.py:515 ``to_dense_adj(ei)``).  All index arrays are int32 device
+tensors; the CSR is built on the GPU by ``s2v_csr_build`` (csrc/s2v_csr.cu).
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+
+
+def _stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def _p(t):
+    return C.c_void_p(0 if t is None else t.data_ptr())
+
+
+def _require_cuda(t: torch.Tensor, name: str):
+    if not t.is_cuda:
+        raise _lib.S2VError("simmodel_b200: %s must be a CUDA tensor (got %s); there is no CPU path" % (name, t.device))
+
+
+class GraphLayout:
+    """CSR (row i -> columns j it gathers), its transpose, in-degrees and the
+    per-graph structure of one batch.
+
+    period == 0: batched -- the CSR spans all ``num_nodes`` rows (Batch.from_data_list).
+    period  > 0: replicated -- the CSR describes one graph of ``period`` nodes and the
+                 batch is ``num_graphs`` copies with different node features (PPO path).
+    """
+
+    def __init__(self, num_nodes, num_graphs, period, rowptr, col, rowptr_t, col_t, indeg, ptr, gid, npad):
+        self.num_nodes = int(num_nodes)
+        self.num_graphs = int(num_graphs)
+        self.period = int(period)
+        self.rowptr, self.col, self.rowptr_t, self.col_t, self.indeg = rowptr, col, rowptr_t, col_t, indeg
+        self.ptr, self.gid = ptr, gid
+        self.npad = npad                      # int or int32 tensor [B]
+        self._struct = None
+
+    @property
+    def device(self):
+        return self.rowptr.device
+
+    @property
+    def num_edges(self):
+        return int(self.col.numel())
+
+    def c_struct(self) -> _lib.Graph:
+        if self._struct is None:
+            g = _lib.Graph()
+            g.num_nodes, g.num_graphs, g.period, g.num_edges = self.num_nodes, self.num_graphs, self.period, self.num_edges
+            g.rowptr, g.col, g.rowptr_t, g.col_t, g.indeg = (_p(self.rowptr), _p(self.col), _p(self.rowptr_t),
+                                                              _p(self.col_t), _p(self.indeg))
+            g.ptr, g.gid = _p(self.ptr), _p(self.gid)
+            if isinstance(self.npad, torch.Tensor):
+                g.npad, g.npad_scalar = _p(self.npad), 0
+            else:
+                g.npad, g.npad_scalar = C.c_void_p(0), int(self.npad)
+            self._struct = g
+        return self._struct
+
+    def with_npad(self, npad) -> "GraphLayout":
+        """Same topology, different padded size(s): the only way Npad enters the result is
+        the theta4 term."""
+        if isinstance(npad, torch.Tensor):
+            npad = npad.to(device=self.device, dtype=torch.int32).contiguous()
+        return GraphLayout(self.num_nodes, self.num_graphs, self.period, self.rowptr, self.col, self.rowptr_t,
+                           self.col_t, self.indeg, self.ptr, self.gid, npad)
+
+    # ------------------------------------------------------------------
+    @staticmethod
+    def build_csr(edge_index: torch.Tensor, n: int, validate: bool = True):
+        """edge_index int64 [2,E] on the GPU, ids in [0,n) -> (rowptr, col, rowptr_t, col_t, indeg) int32."""
+        _require_cuda(edge_index, "edge_index")
+        if edge_index.dim() != 2 or edge_index.shape[0] != 2:
+            raise ValueError("edge_index must have shape [2,E]")
+        ei = edge_index.to(torch.int64).contiguous()
+        E = int(ei.shape[1])
+        dev = ei.device
+        L = _lib.lib()
+        rowptr = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        rowptr_t = torch.empty(n + 1, dtype=torch.int32, device=dev)
+        col = torch.empty(E, dtype=torch.int32, device=dev)
+        col_t = torch.empty(E, dtype=torch.int32, device=dev)
+        indeg = torch.empty(n, dtype=torch.int32, device=dev)
+        ws = torch.empty(L.s2v_csr_workspace_bytes(n, E), dtype=torch.uint8, device=dev)
+        with torch.cuda.device(dev):
+            _lib.check(L.s2v_csr_build(_p(ei), E, n, _p(rowptr), _p(col), _p(rowptr_t), _p(col_t), _p(indeg),
+                                       _p(ws), ws.numel(), _stream()), "s2v_csr_build")
+        _lib.launch_count += 10 if E > 0 else 6
+        if validate and int(ws[:4].view(torch.int32).item()) != 0:
+            raise ValueError("edge_index contains node ids outside [0, %d)" % n)
+        return rowptr, col, rowptr_t, col_t, indeg
+
+    @classmethod
+    def from_batch(cls, edge_index: torch.Tensor, ptr: torch.Tensor, n_pad, batch: torch.Tensor | None = None,
+                   validate: bool = True) -> "GraphLayout":
+        """Batched layout from a PyG-style (edge_index, ptr[, batch]) triple.
+        n_pad: int (xv.shape[1] of the reference call) or per-graph tensor."""
+        _require_cuda(edge_index, "edge_index")
+        dev = edge_index.device
+        ptr32 = ptr.to(device=dev, dtype=torch.int32).contiguous()
+        B = int(ptr32.numel() - 1)
+        n = int(ptr[-1]) if ptr.numel() else 0
+        if batch is None:
+            sizes = (ptr32[1:] - ptr32[:-1]).to(torch.int64)
+            gid = torch.repeat_interleave(torch.arange(B, device=dev, dtype=torch.int32), sizes)
+        else:
+            gid = batch.to(device=dev, dtype=torch.int32).contiguous()
+        if gid.numel() != n:
+            raise ValueError("batch vector length %d != ptr[-1] %d" % (gid.numel(), n))
+        rowptr, col, rowptr_t, col_t, indeg = cls.build_csr(edge_index, n, validate)
+        if isinstance(n_pad, torch.Tensor):
+            n_pad = n_pad.to(device=dev, dtype=torch.int32).contiguous()
+        return cls(n, B, 0, rowptr, col, rowptr_t, col_t, indeg, ptr32, gid, n_pad)
+
+    @classmethod
+    def replicated(cls, edge_index: torch.Tensor, num_nodes: int, copies: int, n_pad=None,
+                   validate: bool = True) -> "GraphLayout":
+        """``copies`` graphs sharing one topology (S time steps of a PPO rollout)."""
+        rowptr, col, rowptr_t, col_t, indeg = cls.build_csr(edge_index, num_nodes, validate)
+        return cls(num_nodes * copies, copies, num_nodes, rowptr, col, rowptr_t, col_t, indeg, None, None,
+                   num_nodes if n_pad is None else n_pad)
+
+    def replicate(self, copies: int) -> "GraphLayout":
+        """Re-use the CSR of a replicated layout for a different number of copies."""
+        if self.period <= 0:
+            raise ValueError("replicate() needs a replicated layout")
+        return GraphLayout(self.period * copies, copies, self.period, self.rowptr, self.col, self.rowptr_t,
+                           self.col_t, self.indeg, None, None, self.npad)

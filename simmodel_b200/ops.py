@@ -1,0 +1,335 @@
+"""torch.autograd bindings of the C-ABI kernels (thin: allocate, call, save).
+
+PyTorch is plumbing here (device memory, streams, autograd graph); every number is
+produced by the kernels in csrc/.  CUDA tensors only -- CPU tensors raise.
+"""
+from __future__ import annotations
+
+import ctypes as C
+
+import torch
+
+from . import _lib
+from .layout import GraphLayout, _p, _require_cuda, _stream
+
+EMBED_NAMES = ("theta1a", "theta1b", "theta2", "theta3", "theta4")
+HEAD_NAMES = ("theta5", "theta6", "theta7")
+
+
+def _f32c(t: torch.Tensor, name: str) -> torch.Tensor:
+    _require_cuda(t, name)
+    if t.dtype != torch.float32:
+        raise TypeError("simmodel_b200: %s must be float32 (got %s)" % (name, t.dtype))
+    return t if t.is_contiguous() else t.contiguous()
+
+
+def _embed_struct(T, w):
+    """w: 10 tensors theta1a.w,b 1b.w,b 2.w,b 3.w,b 4.w,b"""
+    prm = _lib.EmbedParams()
+    prm.node_dim, prm.emb_dim, prm.rounds = int(w[0].shape[1]), int(w[0].shape[0]), int(T)
+    (prm.theta1a_w, prm.theta1a_b, prm.theta1b_w, prm.theta1b_b, prm.theta2_w, prm.theta2_b,
+     prm.theta3_w, prm.theta3_b, prm.theta4_w, prm.theta4_b) = [_p(t) for t in w]
+    return prm
+
+
+def _head_struct(norm_agg, w):
+    """w: 6 tensors theta5.w,b 6.w,b 7.w,b"""
+    prm = _lib.HeadParams()
+    prm.emb_dim, prm.norm_agg = int(w[2].shape[0]), int(bool(norm_agg))
+    prm.theta5_w, prm.theta5_b, prm.theta6_w, prm.theta6_b, prm.theta7_w, prm.theta7_b = [_p(t) for t in w]
+    return prm
+
+
+def _split_embed_grad(flat, F, P):
+    sizes = [P * F, P, P * P, P, P * P, P, P * P, P, P, P]
+    shapes = [(P, F), (P,), (P, P), (P,), (P, P), (P,), (P, P), (P,), (P, 1), (P,)]
+    return [c.view(s) for c, s in zip(flat.split(sizes), shapes)]
+
+
+def _split_head_grad(flat, P):
+    sizes = [2 * P, 1, P * P, P, P * P, P]
+    shapes = [(1, 2 * P), (1,), (P, P), (P,), (P, P), (P,)]
+    return [c.view(s) for c, s in zip(flat.split(sizes), shapes)]
+
+
+def _embed_forward(layout, T, x, w):
+    L = _lib.lib()
+    n, P = layout.num_nodes, int(w[0].shape[0])
+    if x.shape[0] != n or x.shape[1] != w[0].shape[1]:
+        raise ValueError("x has shape %s, expected (%d, %d)" % (tuple(x.shape), n, w[0].shape[1]))
+    base = torch.empty(n, P, dtype=torch.float32, device=x.device)
+    mus = torch.empty(T, n, P, dtype=torch.float32, device=x.device)
+    prm = _embed_struct(T, w)
+    with torch.cuda.device(x.device):
+        _lib.check(L.s2v_embed_forward(C.byref(layout.c_struct()), C.byref(prm), _p(x), _p(base), _p(mus), _stream()),
+                   "s2v_embed_forward")
+    _lib.launch_count += T
+    return base, mus
+
+
+def _embed_backward(layout, T, x, w, base, mus, dmu, dmu_masked, dus=None):
+    L = _lib.lib()
+    n, P, F = layout.num_nodes, int(w[0].shape[0]), int(w[0].shape[1])
+    if dus is None:
+        dus = torch.empty(T, n, P, dtype=torch.float32, device=x.device)
+    ws = torch.empty(L.s2v_embed_backward_workspace_bytes(F, P), dtype=torch.uint8, device=x.device)
+    grad = torch.empty(L.s2v_embed_grad_floats(F, P), dtype=torch.float32, device=x.device)
+    prm = _embed_struct(T, w)
+    with torch.cuda.device(x.device):
+        _lib.check(L.s2v_embed_backward(C.byref(layout.c_struct()), C.byref(prm), _p(x), _p(base), _p(mus), _p(dmu),
+                                        int(dmu_masked), _p(dus), _p(ws), ws.numel(), _p(grad), _stream()),
+                   "s2v_embed_backward")
+    _lib.launch_count += T + 1 + (0 if dmu_masked else 1)
+    return _split_embed_grad(grad, F, P), grad
+
+
+def _head_forward(layout, norm_agg, mu, w):
+    L = _lib.lib()
+    n, B, P = layout.num_nodes, layout.num_graphs, int(w[2].shape[0])
+    pool = torch.empty(B, P, dtype=torch.float32, device=mu.device)
+    gstate = torch.empty(B, P, dtype=torch.float32, device=mu.device)
+    q = torch.empty(n, dtype=torch.float32, device=mu.device)
+    prm = _head_struct(norm_agg, w)
+    with torch.cuda.device(mu.device):
+        _lib.check(L.s2v_head_forward(C.byref(layout.c_struct()), C.byref(prm), _p(mu), _p(pool), _p(gstate), _p(q),
+                                      _stream()), "s2v_head_forward")
+    _lib.launch_count += 2
+    return pool, gstate, q
+
+
+def _head_backward(layout, norm_agg, mu, w, pool, gstate, dq, mask_relu, dmu_out=None):
+    L = _lib.lib()
+    n, B, P = layout.num_nodes, layout.num_graphs, int(w[2].shape[0])
+    if dmu_out is None:
+        dmu_out = torch.empty(n, P, dtype=torch.float32, device=mu.device)
+    ws = torch.empty(L.s2v_head_backward_workspace_bytes(P, B), dtype=torch.uint8, device=mu.device)
+    grad = torch.empty(L.s2v_head_grad_floats(P), dtype=torch.float32, device=mu.device)
+    prm = _head_struct(norm_agg, w)
+    with torch.cuda.device(mu.device):
+        _lib.check(L.s2v_head_backward(C.byref(layout.c_struct()), C.byref(prm), _p(mu), _p(pool), _p(gstate), _p(dq),
+                                       int(mask_relu), _p(dmu_out), _p(ws), ws.numel(), _p(grad), _stream()),
+                   "s2v_head_backward")
+    _lib.launch_count += 3
+    return dmu_out, _split_head_grad(grad, P), grad
+
+
+class _EmbedFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layout, T, x, *w):
+        w = [_f32c(t.detach(), "parameter") for t in w]
+        x = _f32c(x, "x")
+        base, mus = _embed_forward(layout, T, x, w)
+        ctx.layout, ctx.T = layout, T
+        ctx.save_for_backward(x, base, mus, *w)
+        return mus[T - 1]
+
+    @staticmethod
+    def backward(ctx, dmu):
+        x, base, mus, *w = ctx.saved_tensors
+        grads, _ = _embed_backward(ctx.layout, ctx.T, x, w, base, mus, _f32c(dmu, "dmu"), False)
+        return (None, None, None, *grads)
+
+
+class _HeadFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layout, norm_agg, mu, *w):
+        w = [_f32c(t.detach(), "parameter") for t in w]
+        mu = _f32c(mu, "mu")
+        pool, gstate, q = _head_forward(layout, norm_agg, mu, w)
+        ctx.layout, ctx.norm_agg = layout, norm_agg
+        ctx.save_for_backward(mu, pool, gstate, *w)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        mu, pool, gstate, *w = ctx.saved_tensors
+        dmu, grads, _ = _head_backward(ctx.layout, ctx.norm_agg, mu, w, pool, gstate, _f32c(dq, "dq"), False)
+        return (None, None, dmu, *grads)
+
+
+class _QNetFn(torch.autograd.Function):
+    """Embedding + head in one node: the head backward hands du^T (already multiplied by
+    [mu^T > 0]) straight to the embedding backward, written in place into the du workspace."""
+
+    @staticmethod
+    def forward(ctx, layout, T, norm_agg, x, *w):
+        w = [_f32c(t.detach(), "parameter") for t in w]
+        x = _f32c(x, "x")
+        base, mus = _embed_forward(layout, T, x, w[:10])
+        pool, gstate, q = _head_forward(layout, norm_agg, mus[T - 1], w[10:])
+        ctx.layout, ctx.T, ctx.norm_agg = layout, T, norm_agg
+        ctx.save_for_backward(x, base, mus, pool, gstate, *w)
+        return q
+
+    @staticmethod
+    def backward(ctx, dq):
+        x, base, mus, pool, gstate, *w = ctx.saved_tensors
+        T, layout = ctx.T, ctx.layout
+        n, P = layout.num_nodes, int(w[0].shape[0])
+        dus = torch.empty(T, n, P, dtype=torch.float32, device=x.device)
+        _, hgrads, _ = _head_backward(layout, ctx.norm_agg, mus[T - 1], w[10:], pool, gstate, _f32c(dq, "dq"), True,
+                                      dmu_out=dus[T - 1])
+        egrads, _ = _embed_backward(layout, T, x, w[:10], base, mus, dus[T - 1], True, dus=dus)
+        return (None, None, None, None, *egrads, *hgrads)
+
+
+class _PoolFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layout, norm_agg, mu):
+        L = _lib.lib()
+        mu = _f32c(mu, "mu")
+        P = int(mu.shape[1])
+        pool = torch.empty(layout.num_graphs, P, dtype=torch.float32, device=mu.device)
+        with torch.cuda.device(mu.device):
+            _lib.check(L.s2v_pool_forward(C.byref(layout.c_struct()), P, int(bool(norm_agg)), _p(mu), _p(pool), _stream()),
+                       "s2v_pool_forward")
+        _lib.launch_count += 1
+        ctx.layout, ctx.norm_agg, ctx.P = layout, norm_agg, P
+        return pool
+
+    @staticmethod
+    def backward(ctx, dpool):
+        L = _lib.lib()
+        dpool = _f32c(dpool, "dpool")
+        dmu = torch.empty(ctx.layout.num_nodes, ctx.P, dtype=torch.float32, device=dpool.device)
+        with torch.cuda.device(dpool.device):
+            _lib.check(L.s2v_pool_backward(C.byref(ctx.layout.c_struct()), ctx.P, int(bool(ctx.norm_agg)), _p(dpool),
+                                           _p(dmu), _stream()), "s2v_pool_backward")
+        _lib.launch_count += 1
+        return None, None, dmu
+
+
+def _mask_u8(mask: torch.Tensor, n: int) -> torch.Tensor:
+    _require_cuda(mask, "mask")
+    mask = mask.reshape(-1)
+    if mask.numel() != n:
+        raise ValueError("mask has %d entries, expected %d" % (mask.numel(), n))
+    if mask.dtype == torch.bool:
+        return mask.contiguous().view(torch.uint8)
+    return (mask != 0).view(torch.uint8)
+
+
+class _MaskedSoftmaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layout, logits, mask_u8):
+        L = _lib.lib()
+        logits = _f32c(logits, "logits")
+        prob = torch.empty_like(logits)
+        with torch.cuda.device(logits.device):
+            _lib.check(L.s2v_masked_softmax_forward(C.byref(layout.c_struct()), _p(logits), _p(mask_u8), _p(prob),
+                                                    _stream()), "s2v_masked_softmax_forward")
+        _lib.launch_count += 1
+        ctx.layout = layout
+        ctx.save_for_backward(prob)
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        L = _lib.lib()
+        (prob,) = ctx.saved_tensors
+        dprob = _f32c(dprob, "dprob")
+        dlogits = torch.empty_like(prob)
+        with torch.cuda.device(prob.device):
+            _lib.check(L.s2v_masked_softmax_backward(C.byref(ctx.layout.c_struct()), _p(prob), _p(dprob), _p(dlogits),
+                                                     _stream()), "s2v_masked_softmax_backward")
+        _lib.launch_count += 1
+        return None, dlogits, None
+
+
+def _masked_argmax_raw(layout, q, mask_u8):
+    L = _lib.lib()
+    B = layout.num_graphs
+    arg = torch.empty(B, dtype=torch.int64, device=q.device)
+    val = torch.empty(B, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(L.s2v_masked_argmax(C.byref(layout.c_struct()), _p(q), _p(mask_u8), _p(arg), _p(val), _stream()),
+                   "s2v_masked_argmax")
+    _lib.launch_count += 1
+    return arg, val
+
+
+class _MaskedMaxFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layout, q, mask_u8):
+        q = _f32c(q, "q")
+        arg, val = _masked_argmax_raw(layout, q, mask_u8)
+        ctx.layout = layout
+        ctx.save_for_backward(arg)
+        ctx.mark_non_differentiable(arg)
+        return val, arg
+
+    @staticmethod
+    def backward(ctx, dval, _darg):
+        L = _lib.lib()
+        (arg,) = ctx.saved_tensors
+        dval = _f32c(dval, "dval")
+        dq = torch.empty(ctx.layout.num_nodes, dtype=torch.float32, device=dval.device)
+        with torch.cuda.device(dval.device):
+            _lib.check(L.s2v_scatter_rows(C.byref(ctx.layout.c_struct()), _p(arg), _p(dval), _p(dq), _stream()),
+                       "s2v_scatter_rows")
+        _lib.launch_count += 1
+        return None, dq, None
+
+
+# ----------------------------------------------------------------------------------
+# public functional API (the native contract of SURVEY.md §8b)
+# ----------------------------------------------------------------------------------
+def s2v_embed(layout: GraphLayout, x: torch.Tensor, embed_weights, T: int) -> torch.Tensor:
+    """mu^T [num_nodes,p].  embed_weights: theta1a.w,b theta1b.w,b theta2.w,b theta3.w,b theta4.w,b."""
+    if x.requires_grad:
+        raise NotImplementedError("gradients w.r.t. node features are not part of the reference path")
+    return _EmbedFn.apply(layout, int(T), x, *embed_weights)
+
+
+def s2v_head(layout: GraphLayout, mu: torch.Tensor, head_weights, norm_agg: bool = True) -> torch.Tensor:
+    """q / logits [num_nodes].  head_weights: theta5.w,b theta6.w,b theta7.w,b."""
+    return _HeadFn.apply(layout, bool(norm_agg), mu, *head_weights)
+
+
+def s2v_qnet(layout: GraphLayout, x: torch.Tensor, embed_weights, head_weights, T: int, norm_agg: bool = True):
+    """Fused embedding + head: q [num_nodes] (QNet.forward, comb_opt.py:217-275)."""
+    if x.requires_grad:
+        raise NotImplementedError("gradients w.r.t. node features are not part of the reference path")
+    return _QNetFn.apply(layout, int(T), bool(norm_agg), x, *embed_weights, *head_weights)
+
+
+def segment_pool(layout: GraphLayout, mu: torch.Tensor, norm_agg: bool = True) -> torch.Tensor:
+    return _PoolFn.apply(layout, bool(norm_agg), mu)
+
+
+def masked_softmax(layout: GraphLayout, logits: torch.Tensor, mask: torch.Tensor) -> torch.Tensor:
+    """Per-graph softmax with logits[~mask] = -inf (models_basic_lstm.py:539-540)."""
+    flat = logits.reshape(-1)
+    return _MaskedSoftmaxFn.apply(layout, flat, _mask_u8(mask, flat.numel())).view(logits.shape)
+
+
+def masked_max(layout: GraphLayout, q: torch.Tensor, mask: torch.Tensor):
+    """Per-graph (max value, local argmax node) over mask (models_basic_lstm.py:563-564)."""
+    flat = q.reshape(-1)
+    return _MaskedMaxFn.apply(layout, flat, _mask_u8(mask, flat.numel()))
+
+
+@torch.no_grad()
+def masked_argmax(layout: GraphLayout, q: torch.Tensor, mask: torch.Tensor):
+    flat = _f32c(q.reshape(-1), "q")
+    return _masked_argmax_raw(layout, flat, _mask_u8(mask, flat.numel()))
+
+
+@torch.no_grad()
+def list_argmax(layout: GraphLayout, q: torch.Tensor, reach_ptr: torch.Tensor, reach_idx: torch.Tensor):
+    """Greedy action per graph over neighbour lists (comb_opt.py:319-326).
+    reach_ptr int32 [B+1], reach_idx int32 local node ids.  Returns (pos, node, value)."""
+    L = _lib.lib()
+    q = _f32c(q.reshape(-1), "q")
+    _require_cuda(reach_ptr, "reach_ptr")
+    reach_ptr = reach_ptr.to(torch.int32).contiguous()
+    reach_idx = reach_idx.to(device=q.device, dtype=torch.int32).contiguous()
+    B = layout.num_graphs
+    pos = torch.empty(B, dtype=torch.int64, device=q.device)
+    node = torch.empty(B, dtype=torch.int64, device=q.device)
+    val = torch.empty(B, dtype=torch.float32, device=q.device)
+    with torch.cuda.device(q.device):
+        _lib.check(L.s2v_list_argmax(C.byref(layout.c_struct()), _p(q), _p(reach_ptr), _p(reach_idx), _p(pos), _p(node),
+                                     _p(val), _stream()), "s2v_list_argmax")
+    _lib.launch_count += 1
+    return pos, node, val

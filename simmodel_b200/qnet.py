@@ -1,0 +1,231 @@
+"""Drop-in for the reference's struct2vec Q-network and its QFunction wrapper.
+
+Mirrors modules/gnn/comb_opt.py:184-366 (QNet, QFunction): same constructor config
+keys, same parameter names (``theta{1a,1b,2,3,4,5,6,7}.{weight,bias}``, so reference
+checkpoints load with strict=True), same ``forward(xv, Ws, pyg_data)`` contract and
+the same return values from predict / get_best_action / batch_update.  All arithmetic
+runs in the sm_100a kernels behind include/s2v_b200.h; there is no dense adjacency,
+no (B,Npad,Npad,p) tensor and no host round-trip inside forward.
+"""
+from __future__ import annotations
+
+import numpy as np
+import torch
+import torch.nn as nn
+
+from . import ops
+from ._lib import S2VError
+from .layout import GraphLayout
+
+
+class Data:
+    """Minimal stand-in for torch_geometric.data.Data (x, edge_index)."""
+
+    def __init__(self, x=None, edge_index=None, num_nodes=None):
+        self.x, self.edge_index = x, edge_index
+        self.num_nodes = int(num_nodes if num_nodes is not None else (x.shape[0] if x is not None else 0))
+
+
+class Batch:
+    """Minimal stand-in for torch_geometric.data.Batch: what the reference reads is
+    ``ptr``, ``batch`` and (in evaluation) ``edge_index`` (comb_opt.py:248,262,299,344)."""
+
+    def __init__(self, ptr, batch, edge_index=None, x=None):
+        self.ptr, self.batch, self.edge_index, self.x = ptr, batch, edge_index, x
+        self.num_graphs = int(ptr.numel() - 1)
+
+    @staticmethod
+    def from_data_list(data_list):
+        sizes = torch.tensor([int(d.num_nodes) for d in data_list], dtype=torch.int64)
+        ptr = torch.zeros(len(data_list) + 1, dtype=torch.int64)
+        ptr[1:] = torch.cumsum(sizes, 0)
+        batch = torch.repeat_interleave(torch.arange(len(data_list), dtype=torch.int64), sizes)
+        ei = None
+        eis = [getattr(d, "edge_index", None) for d in data_list]
+        if all(isinstance(e, torch.Tensor) and e.dim() == 2 and e.shape[0] == 2 for e in eis):
+            ei = torch.cat([e.to(torch.int64) + int(ptr[g]) for g, e in enumerate(eis)], dim=1)
+        xs = [getattr(d, "x", None) for d in data_list]
+        x = torch.cat(xs, dim=0) if all(isinstance(v, torch.Tensor) and v.dim() == 2 for v in xs) else None
+        return Batch(ptr, batch, ei, x)
+
+    def to(self, device):
+        f = lambda t: None if t is None else t.to(device)
+        return Batch(f(self.ptr), f(self.batch), f(self.edge_index), f(self.x))
+
+
+def _real_edge_index(pyg_data, total_nodes):
+    """pyg_data.edge_index when it is a genuine [2,E] tensor (evaluation path,
+    rl_utils.py:26-29); the training loop passes a dummy Data(torch.ones(V),[0,0])
+    (comb_opt.py:472,522) which must be ignored."""
+    ei = getattr(pyg_data, "edge_index", None)
+    if isinstance(ei, torch.Tensor) and ei.dim() == 2 and ei.shape[0] == 2 and ei.dtype in (torch.int64, torch.int32):
+        if ei.numel() == 0 or int(ei.max()) < total_nodes:
+            return ei
+    return None
+
+
+class QNet(nn.Module):
+    """struct2vec Q-network (comb_opt.py:184-287)."""
+
+    def __init__(self, config, verbose=True):
+        super().__init__()
+        self.emb_dim = config["emb_dim"]
+        self.T = config["emb_iter_T"]
+        self.norm_agg = config["norm_agg"]
+        self.node_dim = config["node_dim"]
+        # creation order == comb_opt.py:204-212 (same default init under the same seed)
+        self.theta1a = nn.Linear(self.node_dim, self.emb_dim, True, dtype=torch.float32)
+        self.theta1b = nn.Linear(self.emb_dim, self.emb_dim, True, dtype=torch.float32)
+        self.theta2 = nn.Linear(self.emb_dim, self.emb_dim, True, dtype=torch.float32)
+        self.theta3 = nn.Linear(self.emb_dim, self.emb_dim, True, dtype=torch.float32)
+        self.theta4 = nn.Linear(1, self.emb_dim, True, dtype=torch.float32)
+        self.theta5 = nn.Linear(2 * self.emb_dim, 1, True, dtype=torch.float32)
+        self.theta6 = nn.Linear(self.emb_dim, self.emb_dim, True, dtype=torch.float32)
+        self.theta7 = nn.Linear(self.emb_dim, self.emb_dim, True, dtype=torch.float32)
+        self.numTrainableParameters(verbose)
+
+    # -- parameter packs in the order the kernels expect -----------------------------
+    def embed_weights(self):
+        return [t for n in ops.EMBED_NAMES for t in (getattr(self, n).weight, getattr(self, n).bias)]
+
+    def head_weights(self):
+        return [t for n in ops.HEAD_NAMES for t in (getattr(self, n).weight, getattr(self, n).bias)]
+
+    @property
+    def device(self):
+        return self.theta2.weight.device
+
+    # -- native contract ----------------------------------------------------------------
+    def forward_graph(self, x: torch.Tensor, layout: GraphLayout) -> torch.Tensor:
+        """x f32[sum N, F] (real nodes only), layout -> q f32[sum N]."""
+        if not self.theta2.weight.is_cuda:
+            raise S2VError("simmodel_b200.QNet runs on CUDA only: call .to('cuda') first (no CPU fallback)")
+        return ops.s2v_qnet(layout, x, self.embed_weights(), self.head_weights(), self.T, self.norm_agg)
+
+    def embed_graph(self, x: torch.Tensor, layout: GraphLayout) -> torch.Tensor:
+        return ops.s2v_embed(layout, x, self.embed_weights(), self.T)
+
+    # -- reference contract ---------------------------------------------------------------
+    def forward(self, xv, Ws, pyg_data):
+        """xv f32[B,Npad,F], Ws f32[B,Npad,Npad] (0/1), pyg_data with .ptr/.batch
+        (and optionally a real .edge_index) -> f32[sum N], squeezed (comb_opt.py:217-275)."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise S2VError("simmodel_b200.QNet runs on CUDA only: call .to('cuda') first (no CPU fallback)")
+        xv = xv.to(dev)
+        n_pad = int(xv.shape[1])
+        B = int(xv.shape[0])
+        ptr = pyg_data.ptr.to(dev)
+        batch = pyg_data.batch.to(dev)
+        total = int(batch.numel())
+        if total == B * n_pad:
+            x = xv.reshape(-1, xv.shape[2])
+        else:                                   # drop padded rows (comb_opt.py:252-259)
+            local = torch.arange(total, device=dev) - ptr[batch]
+            x = xv.reshape(-1, xv.shape[2])[batch * n_pad + local]
+        ei = _real_edge_index(pyg_data, total)
+        if ei is not None:
+            ei = ei.to(dev)
+        else:
+            Ws = Ws.to(dev)
+            nz = Ws.nonzero()                   # (b, i, j) row-major == dense_to_sparse order
+            if not bool(((Ws == 0) | (Ws == 1)).all()):
+                raise NotImplementedError("weighted adjacency: the reference graphs carry 0/1 weights only")
+            off = ptr[nz[:, 0]]
+            ei = torch.stack((nz[:, 1] + off, nz[:, 2] + off))
+        layout = GraphLayout.from_batch(ei, ptr, n_pad, batch)
+        out = self.forward_graph(x.contiguous(), layout)
+        return out.squeeze()
+
+    def numTrainableParameters(self, verbose=True):
+        total = 0
+        lines = ["Qnet size:", "------------------------------------------"]
+        for name, p in self.named_parameters():
+            total += int(np.prod(p.shape))
+            lines.append("{:24s} {:12s} requires_grad={}".format(name, str(list(p.shape)), p.requires_grad))
+        lines += ["Total number of parameters: {}".format(total), "------------------------------------------"]
+        if verbose:
+            print("\n".join(lines))
+        assert total == sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return total
+
+
+class QFunction:
+    """comb_opt.py:289-366."""
+
+    def __init__(self, model, optimizer, lr_scheduler):
+        self.model = model
+        self.optimizer = optimizer
+        self.lr_scheduler = lr_scheduler
+        self.loss_fn = nn.SmoothL1Loss()
+
+    def predict(self, state_tsr, W, pyg_data):
+        pyg_batch = Batch.from_data_list([pyg_data]).to(self.model.device)
+        with torch.no_grad():
+            estimated_rewards = self.model(state_tsr.unsqueeze(0), W.unsqueeze(0), pyg_batch)
+        if estimated_rewards.dim() == 2 and estimated_rewards.shape[0] == 1:
+            return estimated_rewards[0]
+        if estimated_rewards.dim() == 1:
+            return estimated_rewards
+        assert False
+
+    def get_best_action(self, state_tsr, W, pyg_data, reachable_nodes, printing=False):
+        """Greedy action: (index in reachable_nodes, node id, value) (comb_opt.py:309-331).
+        The masked argmax runs on the GPU (s2v_list_argmax); only three scalars come back."""
+        dev = self.model.device
+        self.model.eval()
+        estimated_rewards = self.predict(state_tsr.to(dev), W.to(dev), pyg_data)
+        self.model.train()
+        n = int(estimated_rewards.numel())
+        layout = _single_graph_ranges(n, dev)
+        reach = torch.as_tensor(np.asarray(reachable_nodes), dtype=torch.int32, device=dev)
+        rptr = torch.tensor([0, reach.numel()], dtype=torch.int32, device=dev)
+        pos, node, val = ops.list_argmax(layout, estimated_rewards, rptr, reach)
+        # one D2H copy; int ids and the fp32 value are exact in float64
+        res = torch.stack((pos.to(torch.float64), node.to(torch.float64), val.to(torch.float64))).cpu().numpy()
+        action, action_nodeselect = int(res[0, 0]), int(res[1, 0])
+        best_reward = np.float32(res[2, 0])
+        if printing:
+            print("Selected action:", action, "node", action_nodeselect, "value:", best_reward)
+        return action, action_nodeselect, best_reward
+
+    def batch_update(self, states_tsrs, Ws, pyg_data, actions, targets):
+        """comb_opt.py:334-366."""
+        dev = self.model.device
+        Ws_tsr = torch.stack(Ws).to(dev)
+        xv = torch.stack(states_tsrs).to(dev)
+        pyg_batch = Batch.from_data_list(pyg_data).to(dev)
+        self.optimizer.zero_grad()
+        qvals = self.model(xv, Ws_tsr, pyg_batch)
+        sel = torch.tensor(actions, dtype=torch.int64, device=dev) + pyg_batch.ptr[:-1]
+        loss = self.loss_fn(qvals.reshape(-1)[sel], torch.tensor(targets, device=dev))
+        loss_val = loss.detach().cpu().item()
+        loss.backward()
+        self.optimizer.step()
+        self.lr_scheduler.step()
+        return loss_val
+
+
+class _Ranges:
+    """Graph ranges only (no CSR) for the mask / argmax kernels."""
+
+    def __init__(self, ptr32, n, B):
+        from . import _lib
+        import ctypes as C
+        self.ptr, self.num_nodes, self.num_graphs = ptr32, n, B
+        g = _lib.Graph()
+        g.num_nodes, g.num_graphs, g.period, g.num_edges = n, B, 0, 0
+        g.ptr = C.c_void_p(ptr32.data_ptr())
+        self._g = g
+
+    def c_struct(self):
+        return self._g
+
+
+def _single_graph_ranges(n, dev):
+    return _Ranges(torch.tensor([0, n], dtype=torch.int32, device=dev), n, 1)
+
+
+def ranges_from_ptr(ptr: torch.Tensor) -> _Ranges:
+    ptr32 = ptr.to(torch.int32).contiguous()
+    return _Ranges(ptr32, int(ptr[-1]), int(ptr.numel() - 1))
