@@ -24,7 +24,10 @@ from ._lib import S2VError
 from .layout import GraphLayout
 
 
-class PPO_GNN_Single_LSTM(nn.Module):
+class _PPOModelBase(nn.Module):
+    """Reference constructor / bookkeeping (models_basic_lstm.py:340-462); the kernel-backed
+    methods come from S2VKernelMixin (PPO_GNN_Single_LSTM at the end of this file)."""
+
     def __init__(self, config, hp, tp, device="cuda"):
         super().__init__()
         self.hp, self.tp, self.config = hp, tp, config
@@ -69,7 +72,43 @@ class PPO_GNN_Single_LSTM(nn.Module):
             self.theta6_v = nn.Linear(p, p, True, device=dev)
             self.theta7_v = nn.Linear(p, p, True, device=dev)
         self.optimizer = optim.Adam(self.parameters(), lr=self.hp.learning_rate)
-        self._layouts = {}
+
+    def put_data(self, transition_buffer, ei=None):
+        self.data.append(transition_buffer)
+        self.ei.append(ei)
+
+    def checkpoint(self, n_epi, mean_Return, mode=None):
+        """models_basic_lstm.py:375-391: same file names and dict keys."""
+        if mode == "best":
+            fname = self.tp["base_checkpoint_path"] + "best_model.tar"
+            with open(self.tp["base_checkpoint_path"] + "/model_best_save_history.txt", "a") as f:
+                f.write("BEST_timestep:" + str(n_epi) + ", avg det res:" + str(mean_Return) + "\n")
+        elif mode == "last":
+            fname = self.tp["base_checkpoint_path"] + "model_" + str(n_epi) + ".tar"
+        else:
+            return
+        torch.save({"weights": self.state_dict(), "optimizer": self.optimizer.state_dict()}, fname)
+
+    def numTrainableParameters(self):
+        ps = self.description + "\n------------------------------------------\n"
+        total = 0
+        for name, p in self.named_parameters():
+            if p.requires_grad:
+                total += int(np.prod(p.shape))
+            ps += "{:24s} {:12s} requires_grad={}\n".format(name, str(list(p.shape)), p.requires_grad)
+        ps += "Total number of trainable parameters: {}\n".format(total)
+        ps += "------------------------------------------"
+        assert total == sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return total, ps
+
+
+class S2VKernelMixin:
+    """The kernel-backed replacements for process_input / s2v / create_embeddings / pi / v.
+    Mix in FRONT of the reference class to keep its make_batch / train_net / learn:
+
+        class Model(S2VKernelMixin, reference.PPO_GNN_Single_LSTM): pass
+
+    Needs only the attributes the reference constructor creates (theta*, lstm, config, emb_dim, T)."""
 
     # -- helpers ----------------------------------------------------------------------------
     @property
@@ -85,6 +124,8 @@ class PPO_GNN_Single_LSTM(nn.Module):
     def _layout(self, ei: torch.Tensor, num_nodes: int, copies: int) -> GraphLayout:
         """CSR of one graph, cached per edge_index tensor (a rollout shares one ei for all
         its steps and all of v', v, pi; models_basic_lstm.py:606-624)."""
+        if not hasattr(self, "_layouts"):
+            self._layouts = {}
         key = (id(ei), ei._version, num_nodes, str(self.device))
         hit = self._layouts.get(key)
         if hit is None:
@@ -173,30 +214,6 @@ class PPO_GNN_Single_LSTM(nn.Module):
         arg, _ = ops.masked_argmax(layout, logits, reachable)
         return arg, lstm_hidden
 
-    def put_data(self, transition_buffer, ei=None):
-        self.data.append(transition_buffer)
-        self.ei.append(ei)
 
-    def checkpoint(self, n_epi, mean_Return, mode=None):
-        """models_basic_lstm.py:375-391: same file names and dict keys."""
-        if mode == "best":
-            fname = self.tp["base_checkpoint_path"] + "best_model.tar"
-            with open(self.tp["base_checkpoint_path"] + "/model_best_save_history.txt", "a") as f:
-                f.write("BEST_timestep:" + str(n_epi) + ", avg det res:" + str(mean_Return) + "\n")
-        elif mode == "last":
-            fname = self.tp["base_checkpoint_path"] + "model_" + str(n_epi) + ".tar"
-        else:
-            return
-        torch.save({"weights": self.state_dict(), "optimizer": self.optimizer.state_dict()}, fname)
-
-    def numTrainableParameters(self):
-        ps = self.description + "\n------------------------------------------\n"
-        total = 0
-        for name, p in self.named_parameters():
-            if p.requires_grad:
-                total += int(np.prod(p.shape))
-            ps += "{:24s} {:12s} requires_grad={}\n".format(name, str(list(p.shape)), p.requires_grad)
-        ps += "Total number of trainable parameters: {}\n".format(total)
-        ps += "------------------------------------------"
-        assert total == sum(p.numel() for p in self.parameters() if p.requires_grad)
-        return total, ps
+class PPO_GNN_Single_LSTM(S2VKernelMixin, _PPOModelBase):
+    """Drop-in for models_basic_lstm.py:407 PPO_GNN_Single_LSTM with config['qnet'] == 's2v'."""
