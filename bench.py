@@ -367,14 +367,18 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
     g = layout.c_struct()
     w2 = net.theta2.weight.detach()
 
+    flag = _lib.path_flag()
+    tensor = flag == 2 or (flag == 0 and n >= 4096)
+    sfx = "_tc (tcgen05 3xTF32)" if tensor else " (FFMA)"
+
     def fwd():
-        _lib.check(L.s2v_embed_round_forward(C.byref(g), P, _p(w2), _p(base), _p(mu), _p(out), _stream()), "round fwd")
+        _lib.check(L.s2v_embed_round_forward(C.byref(g), P, flag, _p(w2), _p(base), _p(mu), _p(out), _stream()), "round fwd")
 
     def bwd():
-        _lib.check(L.s2v_embed_round_backward(C.byref(g), F, P, _p(w2), _p(du), _p(mu), _p(out), _p(ws), ws.numel(),
+        _lib.check(L.s2v_embed_round_backward(C.byref(g), F, P, flag, _p(w2), _p(du), _p(mu), _p(out), _p(ws), ws.numel(),
                                               _stream()), "round bwd")
     res = []
-    for name, fn in (("k_embed_round (forward round)", fwd), ("k_embed_round_bwd (backward round)", bwd)):
+    for name, fn in (("k_embed_round" + sfx + ", forward round", fwd), ("k_embed_round_bwd" + sfx + ", backward round", bwd)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

@@ -71,7 +71,8 @@ typedef struct s2v_embed_params {
     int32_t node_dim;         /* F  */
     int32_t emb_dim;          /* p  */
     int32_t rounds;           /* T  */
-    int32_t reserved;
+    int32_t flags;            /* kernel path: 0 auto (tensor cores when p == 64 and num_nodes >= 4096),
+                                 1 CUDA-core FP32 (FFMA), 2 tcgen05 3xTF32 (p == 64 only)            */
     const float* theta1a_w;   /* [p,F] */
     const float* theta1a_b;   /* [p]   */
     const float* theta1b_w;   /* [p,p] */
@@ -145,11 +146,16 @@ int s2v_embed_backward(const s2v_graph_t* g, const s2v_embed_params_t* prm, cons
  * and one backward round: g = W^T du_t ; du_prev = (theta2^T g) * [mu_prev > 0] (the per-CTA
  * partial sums of dtheta2 land in workspace).  Used by unit tests and to time the dominant
  * kernels in isolation. */
-int s2v_embed_round_forward(const s2v_graph_t* g, int32_t emb_dim, const float* theta2_w, const float* base,
-                            const float* mu_prev, float* mu_next, void* stream);
-int s2v_embed_round_backward(const s2v_graph_t* g, int32_t node_dim, int32_t emb_dim, const float* theta2_w,
-                             const float* du_t, const float* mu_prev, float* du_prev, void* workspace,
-                             int64_t workspace_bytes, void* stream);
+int s2v_embed_round_forward(const s2v_graph_t* g, int32_t emb_dim, int32_t flags, const float* theta2_w,
+                            const float* base, const float* mu_prev, float* mu_next, void* stream);
+int s2v_embed_round_backward(const s2v_graph_t* g, int32_t node_dim, int32_t emb_dim, int32_t flags,
+                             const float* theta2_w, const float* du_t, const float* mu_prev, float* du_prev,
+                             void* workspace, int64_t workspace_bytes, void* stream);
+
+/* Self-test of the tcgen05 building blocks on one CTA (rows x 64 operands, fp32):
+ * mode 0: out[rows,64] = A W^T ; mode 1: out[rows,64] = A W ; mode 2: out[64,64] = A^T B (B [rows,64]);
+ * mode 3: out[rows,64] = A W with the A operand in tensor memory. */
+int s2v_debug_tc_gemm(int32_t mode, const float* A, const float* B, float* out, int64_t rows, void* stream);
 
 /* ---------------------------------------------------------------------------------
  * K5  pooling + Q / logit head.  Replaces comb_opt.py:248-273 (select list, scatter_mean /

@@ -166,6 +166,25 @@ def ppo_case(mb, name, topo, S, p, T, lstm_type, critic, seed, obs_mask_freq=Non
     v_o, _ = R.ppo_v_dense(P, nfm, ei, reachable, T, critic, lstm, hidden)
     assert torch.equal(prob_o, prob.detach()) and torch.equal(v_o, v.detach()), "dense PPO restatement differs"
     greedy = prob.detach().argmax(dim=1)    # rl_policy.py:536
+    # fp64 adjudication: the same arithmetic (oracle dense restatement, LSTM included) in double
+    P64 = {k: v_.double().requires_grad_(True) for k, v_ in P.items()}
+    lstm64, hidden64 = None, None
+    if lstm_type == "EMB":
+        lstm64 = torch.nn.LSTM(p, p).double()
+        hidden64 = (hidden[0].double(), hidden[1].double())
+
+        def lstm_fn(x, h):                  # functional LSTM on the fp64 leaves so that they receive gradients
+            return torch._VF.lstm(x, h, [P64["lstm.weight_ih_l0"], P64["lstm.weight_hh_l0"], P64["lstm.bias_ih_l0"],
+                                         P64["lstm.bias_hh_l0"]], True, 1, 0.0, False, False, False)[0::1][0], None
+        lstm64 = lambda x, h: (lstm_fn(x, h)[0], None)
+    prob64, _ = R.ppo_pi_dense(P64, nfm.double(), ei, reachable, T, lstm64, hidden64)
+    v64, _ = R.ppo_v_dense(P64, nfm.double(), ei, reachable, T, critic, lstm64, hidden64)
+    ((prob64 * wprob.double()).sum() + (v64 * wv.double()).sum()).backward()
+    g64 = {k: (P64[k].grad.detach() if P64[k].grad is not None else torch.zeros_like(P64[k])) for k in grads}
+    own = max(float((grads[k].double() - g64[k]).abs().max()) / _scale_of(g64[k]) for k in grads if _scale_of(g64[k]) > 1e-6)
+    print("  %-28s reference's own fp32 error vs fp64: prob %.1e v %.1e grads %.1e" % (
+        "", float((prob.detach().double() - prob64.detach()).abs().max()),
+        float((v.detach().double() - v64.detach()).abs().max()) / _scale_of(v64), own))
     print("  %-22s prob max %.3g  v scale %.3g" % (name, float(prob.max()), _scale_of(v)))
     meta = dict(kind="ppo", S=S, N=N, emb_dim=p, T=T, lstm_type=lstm_type, critic=critic, seed=seed, topo=topo.name)
     inp = dict(nfm=_np(nfm), edge_index=_np(ei).astype(np.int32), reachable=_np(reachable),
@@ -173,8 +192,10 @@ def ppo_case(mb, name, topo, S, p, T, lstm_type, critic, seed, obs_mask_freq=Non
     if hidden is not None:
         inp["h0"], inp["c0"] = _np(hidden[0]), _np(hidden[1])
     _save(name, meta, P={k: _np(v_) for k, v_ in P.items()}, inp=inp,
-          out=dict(prob=_np(prob), v=_np(v), mu=_np(mu), mu_s2v=_np(mu_s2v), greedy=_np(greedy)),
-          grad={k: _np(g) for k, g in grads.items()})
+          out=dict(prob=_np(prob), v=_np(v), mu=_np(mu), mu_s2v=_np(mu_s2v), greedy=_np(greedy),
+                   prob_f64=_np(prob64), v_f64=_np(v64)),
+          grad={k: _np(g) for k, g in grads.items()},
+          grad64={k: _np(g) for k, g in g64.items()})
 
 
 def main():

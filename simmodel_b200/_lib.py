@@ -23,7 +23,7 @@ class Graph(C.Structure):
 
 
 class EmbedParams(C.Structure):
-    _fields_ = [("node_dim", i32), ("emb_dim", i32), ("rounds", i32), ("reserved", i32),
+    _fields_ = [("node_dim", i32), ("emb_dim", i32), ("rounds", i32), ("flags", i32),
                 ("theta1a_w", vp), ("theta1a_b", vp), ("theta1b_w", vp), ("theta1b_b", vp),
                 ("theta2_w", vp), ("theta2_b", vp), ("theta3_w", vp), ("theta3_b", vp),
                 ("theta4_w", vp), ("theta4_b", vp)]
@@ -48,8 +48,9 @@ SIGNATURES = {
     "s2v_embed_forward": (C.c_int, [GP, EP, vp, vp, vp, vp]),
     "s2v_embed_backward_workspace_bytes": (i64, [i32, i32]),
     "s2v_embed_backward": (C.c_int, [GP, EP, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp]),
-    "s2v_embed_round_forward": (C.c_int, [GP, i32, vp, vp, vp, vp, vp]),
-    "s2v_embed_round_backward": (C.c_int, [GP, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
+    "s2v_embed_round_forward": (C.c_int, [GP, i32, i32, vp, vp, vp, vp, vp]),
+    "s2v_embed_round_backward": (C.c_int, [GP, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
+    "s2v_debug_tc_gemm": (C.c_int, [i32, vp, vp, vp, i64, vp]),
     "s2v_head_forward": (C.c_int, [GP, HP, vp, vp, vp, vp, vp]),
     "s2v_head_backward_workspace_bytes": (i64, [i32, i32]),
     "s2v_head_backward": (C.c_int, [GP, HP, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp]),
@@ -94,6 +95,14 @@ def lib():
 def check(code: int, what: str):
     if code != 0:
         raise S2VError("%s failed: %s (code %d)" % (what, lib().s2v_error_string(code).decode(), code))
+
+
+PATHS = {"auto": 0, "ffma": 1, "tc": 2}
+
+
+def path_flag() -> int:
+    """Kernel path selector from $S2V_B200_PATH (auto | ffma | tc); see s2v_embed_params_t.flags."""
+    return PATHS[os.environ.get("S2V_B200_PATH", "auto").lower()]
 
 
 launch_count = 0   # number of C-ABI calls that enqueue kernels (bench.py reports kernel launches from this)

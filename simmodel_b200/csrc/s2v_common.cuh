@@ -236,6 +236,35 @@ static inline int s2v_persistent_grid(const void* kernel, int smem_bytes, int nu
     return grid < 1 ? 1 : grid;
 }
 
+// dst[off0 + e] = sum_{c < n_part} partial[c*stride + off0 + e], e < len: fixed summation order
+// (four contiguous c-segments per element, combined in order) => deterministic.
+static __global__ void __launch_bounds__(256)
+k_reduce_partials(const float* __restrict__ partial, int stride, int n_part, int off0, int len, float* __restrict__ dst) {
+    __shared__ float sh[4][64];
+    const int x = threadIdx.x & 63, y = threadIdx.x >> 6;
+    const int e = blockIdx.x * 64 + x;
+    float s = 0.f;
+    if (e < len) {
+        int seg = (n_part + 3) / 4;
+        int c0 = y * seg, c1 = min(n_part, c0 + seg);
+        const float* p = partial + (size_t)c0 * stride + off0 + e;
+        for (int c = c0; c < c1; ++c, p += stride) s += *p;
+    }
+    sh[y][x] = s;
+    __syncthreads();
+    if (y == 0 && e < len) dst[off0 + e] = ((sh[0][x] + sh[1][x]) + sh[2][x]) + sh[3][x];
+}
+static inline void s2v_reduce_partials(const float* partial, int stride, int n_part, int off0, int len, float* dst,
+                                       cudaStream_t st) {
+    if (len <= 0) return;
+    k_reduce_partials<<<(len + 63) / 64, 256, 0, st>>>(partial, stride, n_part, off0, len, dst);
+}
+
+#define S2V_PATH_AUTO 0
+#define S2V_PATH_FFMA 1
+#define S2V_PATH_TENSOR 2
+#define S2V_TENSOR_MIN_NODES 4096
+
 #define S2V_DISPATCH_P(P_, CALL)                         \
     switch (P_) {                                        \
         case 8: { constexpr int PP = 8; CALL; } break;   \

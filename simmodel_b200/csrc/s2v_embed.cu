@@ -328,16 +328,16 @@ k_embed_final_bwd(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict
     }
 }
 
-// Fixed-order reduction of the per-CTA partials and the closed-form theta3/theta4 gradients.
+// Closed-form theta3/theta4 gradients and copies, from the fixed-order sums of the per-CTA
+// partials (k_reduce_partials, s2v_common.cuh).  sums has the EmbedPartial layout.
 // grad layout: theta1a.w [P,F], theta1a.b, theta1b.w [P,P], theta1b.b, theta2.w, theta2.b,
 //              theta3.w, theta3.b, theta4.w [P], theta4.b [P]
 template <int P>
 __global__ void __launch_bounds__(256)
-k_embed_finalize(s2v_embed_params_t prm, const float* __restrict__ partial, int partial_stride, int n_part,
-                 int have_th2, float* __restrict__ grad) {
+k_embed_finalize(s2v_embed_params_t prm, const float* __restrict__ sums, int have_th2, float* __restrict__ grad) {
     using EP = EmbedPartial<P>;
     const int F = prm.node_dim;
-    __shared__ float colD[P], A1[P], A0[P], r1[P], r0[P], dr1[P], dr0[P];
+    __shared__ float A1[P], A0[P], r1[P], r0[P];
     const int t = threadIdx.x;
     float* g1a_w = grad;
     float* g1a_b = g1a_w + P * F;
@@ -349,50 +349,38 @@ k_embed_finalize(s2v_embed_params_t prm, const float* __restrict__ partial, int 
     float* g3_b = g3_w + P * P;
     float* g4_w = g3_b + P;
     float* g4_b = g4_w + P;
-    auto psum = [&](int off) {
-        float s = 0.f;
-        for (int c = 0; c < n_part; ++c) s += partial[(size_t)c * partial_stride + off];
-        return s;
-    };
-    if (blockIdx.x == 0) {
-        for (int e = t; e < P; e += blockDim.x) {
-            colD[e] = psum(EP::COLD + e);
-            A1[e] = psum(EP::A1 + e);
-            A0[e] = psum(EP::A0 + e);
-            float w4 = prm.theta4_w[e], b4 = prm.theta4_b[e];
-            r1[e] = relu(w4 + b4);
-            r0[e] = relu(b4);
-            g1a_b[e] = psum(EP::B1A + e);
-        }
-        __syncthreads();
-        for (int e = t; e < P; e += blockDim.x) {
-            g1b_b[e] = colD[e];
-            g2_b[e] = colD[e];
-            g3_b[e] = colD[e];
-            float a = 0.f, b = 0.f;
-            for (int n = 0; n < P; ++n) {
-                float w = prm.theta3_w[n * P + e];
-                a = fmaf(w, A1[n], a);
-                b = fmaf(w, A0[n], b);
-            }
-            dr1[e] = a;
-            dr0[e] = b;
-            float w4 = prm.theta4_w[e], b4 = prm.theta4_b[e];
-            float m1 = (w4 + b4) > 0.f ? a : 0.f;
-            g4_w[e] = m1;
-            g4_b[e] = m1 + (b4 > 0.f ? b : 0.f);
-        }
-        for (int e = t; e < P * P; e += blockDim.x) {
-            int n = e / P, k = e - n * P;
-            g3_w[e] = A1[n] * r1[k] + A0[n] * r0[k];
-        }
-    } else if (blockIdx.x == 1) {
-        for (int e = t; e < P * P; e += blockDim.x) g2_w[e] = have_th2 ? psum(EP::TH2 + e) : 0.f;
-    } else if (blockIdx.x == 2) {
-        for (int e = t; e < P * P; e += blockDim.x) g1b_w[e] = psum(EP::TH1B + e);
-    } else {
-        for (int e = t; e < P * F; e += blockDim.x) g1a_w[e] = psum(EP::TH1A + e);
+    for (int e = t; e < P; e += blockDim.x) {
+        A1[e] = sums[EP::A1 + e];
+        A0[e] = sums[EP::A0 + e];
+        float w4 = prm.theta4_w[e], b4 = prm.theta4_b[e];
+        r1[e] = relu(w4 + b4);
+        r0[e] = relu(b4);
+        float cd = sums[EP::COLD + e];
+        g1a_b[e] = sums[EP::B1A + e];
+        g1b_b[e] = cd;
+        g2_b[e] = cd;
+        g3_b[e] = cd;
     }
+    __syncthreads();
+    for (int e = t; e < P; e += blockDim.x) {
+        float a = 0.f, b = 0.f;
+        for (int n = 0; n < P; ++n) {
+            float w = prm.theta3_w[n * P + e];
+            a = fmaf(w, A1[n], a);
+            b = fmaf(w, A0[n], b);
+        }
+        float w4 = prm.theta4_w[e], b4 = prm.theta4_b[e];
+        float m1 = (w4 + b4) > 0.f ? a : 0.f;
+        g4_w[e] = m1;
+        g4_b[e] = m1 + (b4 > 0.f ? b : 0.f);
+    }
+    for (int e = t; e < P * P; e += blockDim.x) {
+        int n = e / P, k = e - n * P;
+        g3_w[e] = A1[n] * r1[k] + A0[n] * r0[k];
+        g2_w[e] = have_th2 ? sums[EP::TH2 + e] : 0.f;
+        g1b_w[e] = sums[EP::TH1B + e];
+    }
+    for (int e = t; e < P * F; e += blockDim.x) g1a_w[e] = sums[EP::TH1A + e];
 }
 
 __global__ void k_relu_mask(const float4* __restrict__ dmu, const float4* __restrict__ mu, float4* __restrict__ du, int64_t n4) {
@@ -411,6 +399,20 @@ static int set_smem(K kernel, int bytes) {
     return (int)cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
+// tensor-core round kernels (s2v_embed_tc.cu), p = 64 only
+int s2v_tc_round_forward(const s2v_graph_t& g, const float* theta2_w, const float* base, const float* mu_prev,
+                         float* mu_next, cudaStream_t st);
+int s2v_tc_round_backward_grid(int num_nodes);
+int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
+                          float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st);
+
+// flags (s2v_embed_params_t.flags): 0 = auto, 1 = CUDA-core FP32 path, 2 = tensor-core path
+static bool use_tensor_path(int P, int flags, int num_nodes) {
+    if (P != 64 || flags == S2V_PATH_FFMA) return false;
+    if (flags == S2V_PATH_TENSOR) return true;
+    return num_nodes >= S2V_TENSOR_MIN_NODES;
+}
+
 template <int P>
 static int embed_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x,
                               float* base, float* mus, cudaStream_t st) {
@@ -423,7 +425,10 @@ static int embed_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& pr
         int grid = s2v_persistent_grid((const void*)k_embed_first<P>, smem, tiles);
         k_embed_first<P><<<grid, S2V_THREADS, smem, st>>>(g, prm, x, base, mus, tiles);
     }
-    {
+    if (use_tensor_path(P, prm.flags, g.num_nodes)) {
+        for (int t = 1; t < prm.rounds; ++t)
+            S2V_RETURN_IF(s2v_tc_round_forward(g, prm.theta2_w, base, mus + (t - 1) * plane, mus + t * plane, st));
+    } else {
         int smem = (C::W_FLOATS + C::TILE_FLOATS) * 4;
         S2V_RETURN_IF(set_smem(k_embed_round<P>, smem));
         int grid = s2v_persistent_grid((const void*)k_embed_round<P>, smem, tiles);
@@ -444,6 +449,7 @@ static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& p
     const int tiles = (g.num_nodes + S2V_TM - 1) / S2V_TM;
     const size_t plane = (size_t)g.num_nodes * P;
     const int stride = EP::size(prm.node_dim);
+    float* sums = partial + (size_t)S2V_MAX_GRID * stride;
     // du^T
     const float* du_last = dmu;
     if (!dmu_masked) {
@@ -456,27 +462,36 @@ static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& p
                                             (float4*)dst, n4);
         du_last = dst;
     }
-    int smem_r = (C::W_FLOATS + 2 * C::TILE_FLOATS) * 4;
-    S2V_RETURN_IF(set_smem(k_embed_round_bwd<P>, smem_r));
     int smem_f = (C::W_FLOATS + 2 * C::TILE_FLOATS + S2V_MAX_F * P + S2V_TM * S2V_MAX_F + P + C::RG * P) * 4;
     S2V_RETURN_IF(set_smem(k_embed_final_bwd<P>, smem_f));
-    int grid_r = s2v_persistent_grid((const void*)k_embed_round_bwd<P>, smem_r, tiles);
     int grid_f = s2v_persistent_grid((const void*)k_embed_final_bwd<P>, smem_f, tiles);
-    int n_part = grid_r > grid_f ? grid_r : grid_f;
-    if (grid_r != grid_f) { grid_r = grid_f = (grid_r < grid_f ? grid_r : grid_f); n_part = grid_r; }
+    int grid_r = 0;
     // rounds T..2 : du^t -> du^{t-1}
-    for (int t = T; t >= 2; --t) {
-        const float* du_t = (t == T) ? du_last : dus + (size_t)(t - 1) * plane;
-        k_embed_round_bwd<P><<<grid_r, S2V_THREADS, smem_r, st>>>(g, prm.theta2_w, du_t, mus + (size_t)(t - 2) * plane,
-                                                                  dus + (size_t)(t - 2) * plane, partial, stride,
-                                                                  t != T, tiles);
+    if (use_tensor_path(P, prm.flags, g.num_nodes)) {
+        grid_r = s2v_tc_round_backward_grid(g.num_nodes);
+        for (int t = T; t >= 2; --t) {
+            const float* du_t = (t == T) ? du_last : dus + (size_t)(t - 1) * plane;
+            S2V_RETURN_IF(s2v_tc_round_backward(g, prm.theta2_w, du_t, mus + (size_t)(t - 2) * plane,
+                                                dus + (size_t)(t - 2) * plane, partial, stride, t != T, grid_r, st));
+        }
+    } else {
+        int smem_r = (C::W_FLOATS + 2 * C::TILE_FLOATS) * 4;
+        S2V_RETURN_IF(set_smem(k_embed_round_bwd<P>, smem_r));
+        grid_r = s2v_persistent_grid((const void*)k_embed_round_bwd<P>, smem_r, tiles);
+        for (int t = T; t >= 2; --t) {
+            const float* du_t = (t == T) ? du_last : dus + (size_t)(t - 1) * plane;
+            k_embed_round_bwd<P><<<grid_r, S2V_THREADS, smem_r, st>>>(g, prm.theta2_w, du_t, mus + (size_t)(t - 2) * plane,
+                                                                      dus + (size_t)(t - 2) * plane, partial, stride,
+                                                                      t != T, tiles);
+        }
     }
     k_embed_final_bwd<P><<<grid_f, S2V_THREADS, smem_f, st>>>(g, prm, x, dus, du_last, T, partial, stride, tiles);
-    k_embed_finalize<P><<<4, 256, 0, st>>>(prm, partial, stride, n_part, T >= 2, grad);
+    if (T >= 2) s2v_reduce_partials(partial, stride, grid_r, EP::TH2, P * P, sums, st);
+    s2v_reduce_partials(partial, stride, grid_f, EP::TH1B, stride - EP::TH1B, sums, st);
+    k_embed_finalize<P><<<1, 256, 0, st>>>(prm, sums, T >= 2, grad);
     (void)base;
     return (int)cudaGetLastError();
 }
-
 
 static int check_graph(const s2v_graph_t* g) {
     if (!g || g->num_nodes < 0 || g->num_graphs < 0) return S2V_ERR_BAD_ARG;
@@ -493,7 +508,7 @@ extern "C" int64_t s2v_embed_grad_floats(int32_t F, int32_t P) {
 }
 
 extern "C" int64_t s2v_embed_backward_workspace_bytes(int32_t F, int32_t P) {
-    return (int64_t)S2V_MAX_GRID * (2 * P * P + 4 * P + P * F) * 4;
+    return (int64_t)(S2V_MAX_GRID + 1) * (2 * P * P + 4 * P + P * F) * 4;
 }
 
 extern "C" int s2v_embed_forward(const s2v_graph_t* g, const s2v_embed_params_t* prm, const float* x,
@@ -561,22 +576,28 @@ static int round_backward_impl(const s2v_graph_t& g, const float* theta2_w, cons
     return (int)cudaGetLastError();
 }
 
-extern "C" int s2v_embed_round_forward(const s2v_graph_t* g, int32_t emb_dim, const float* theta2_w, const float* base,
-                                       const float* mu_prev, float* mu_next, void* stream) {
+extern "C" int s2v_embed_round_forward(const s2v_graph_t* g, int32_t emb_dim, int32_t flags, const float* theta2_w,
+                                       const float* base, const float* mu_prev, float* mu_next, void* stream) {
     S2V_RETURN_IF(check_graph(g));
     if (!theta2_w || !base || !mu_prev || !mu_next) return S2V_ERR_BAD_ARG;
     if (g->num_nodes == 0) return 0;
+    if (use_tensor_path(emb_dim, flags, g->num_nodes))
+        return s2v_tc_round_forward(*g, theta2_w, base, mu_prev, mu_next, (cudaStream_t)stream);
     S2V_DISPATCH_P(emb_dim, return round_forward_impl<PP>(*g, theta2_w, base, mu_prev, mu_next, (cudaStream_t)stream));
     return 0;
 }
 
-extern "C" int s2v_embed_round_backward(const s2v_graph_t* g, int32_t node_dim, int32_t emb_dim, const float* theta2_w,
-                                        const float* du_t, const float* mu_prev, float* du_prev, void* workspace,
-                                        int64_t workspace_bytes, void* stream) {
+extern "C" int s2v_embed_round_backward(const s2v_graph_t* g, int32_t node_dim, int32_t emb_dim, int32_t flags,
+                                        const float* theta2_w, const float* du_t, const float* mu_prev, float* du_prev,
+                                        void* workspace, int64_t workspace_bytes, void* stream) {
     S2V_RETURN_IF(check_graph(g));
     if (!theta2_w || !du_t || !mu_prev || !du_prev || !workspace) return S2V_ERR_BAD_ARG;
     if (workspace_bytes < s2v_embed_backward_workspace_bytes(node_dim, emb_dim)) return S2V_ERR_WORKSPACE;
     if (g->num_nodes == 0) return 0;
+    if (use_tensor_path(emb_dim, flags, g->num_nodes))
+        return s2v_tc_round_backward(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace,
+                                     2 * emb_dim * emb_dim + 4 * emb_dim + emb_dim * node_dim, 0,
+                                     s2v_tc_round_backward_grid(g->num_nodes), (cudaStream_t)stream);
     S2V_DISPATCH_P(emb_dim, return round_backward_impl<PP>(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace,
                                                            node_dim, (cudaStream_t)stream));
     return 0;

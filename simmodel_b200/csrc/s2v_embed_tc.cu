@@ -1,0 +1,472 @@
+// Tensor-core (tcgen05 / TMEM) variants of the propagation round, p = 64 only.
+//
+// Same math as k_embed_round / k_embed_round_bwd (s2v_embed.cu) with the p x p contractions
+// moved to the 5th-generation tensor cores as 3xTF32 split-precision UMMAs (s2v_tc.cuh):
+// CUDA cores only gather neighbour rows, split them into hi/lo TF32 tiles in shared memory
+// (canonical SWIZZLE_128B layout, written directly by the gather lanes) and run the epilogue
+// from TMEM.  A CTA of 128 threads owns 64 consecutive node rows per tile (UMMA M = 64),
+// several CTAs per SM interleave their gather / MMA / epilogue phases.
+//
+//   forward :  D1[64x64]  = agg * theta2^T                        (A K-major, B K-major)
+//   backward:  D1[64x64]  = g * theta2                            (A K-major, B = theta2^T K-major)
+//              D2[128x64] += [g_hi ; g_lo]^T * mu_hi + [g_hi ; g_lo]^T * mu_lo
+//                            (both MN-major views of the same tiles; K = the 64 rows of the
+//                             tile; rows 0-63 of D2 + rows 64-127 of D2 = dtheta2 partial,
+//                             kept in TMEM across all tiles of the CTA)
+#include "s2v_common.cuh"
+#include "s2v_tc.cuh"
+
+namespace {
+
+constexpr int TCR = 64;                         // rows per tile
+constexpr int TC_THREADS = 128;
+constexpr uint32_t TILE_BYTES = TCR * 256;      // one hi or lo tile: 2 column blocks x 64 rows x 128 B
+constexpr int STG_LD = 68;                      // staging leading dimension (floats)
+
+// split a float4 chunk of row r into the hi / lo tiles
+__device__ __forceinline__ void store_split(uint8_t* hi_tile, uint8_t* lo_tile, int r, int c4, const float4& v) {
+    float4 hi, lo;
+    tc::split4(v, hi, lo);
+    uint32_t off = tc::tile_off<TCR>(r, c4);
+    *reinterpret_cast<float4*>(hi_tile + off) = hi;
+    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+}
+
+// same for an MN-major (SWIZZLE_128B_BASE32B) tile
+__device__ __forceinline__ void store_split_mn(uint8_t* hi_tile, uint8_t* lo_tile, int r, int c4, const float4& v) {
+    float4 hi, lo;
+    tc::split4(v, hi, lo);
+    uint32_t off = tc::tile_off_mn<TCR>(r, c4);
+    *reinterpret_cast<float4*>(hi_tile + off) = hi;
+    *reinterpret_cast<float4*>(lo_tile + off) = lo;
+}
+
+// Row owners (lanes 0-15 of each warp own row 16*warp + lane, the UMMA M = 64 lane mapping
+// lane = 32*(row/16) + row%16) copy their row of an MN-major tile into TMEM as the A operand
+// of the row transform: 64 columns of their lane.  (The 4-row swizzle of the tile spreads
+// consecutive rows over four bank groups: 2-way conflicts at most.)
+__device__ __forceinline__ void row_to_tmem(const uint8_t* tile, uint32_t a_tmem) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int r = 16 * warp + (lane & 15);
+    float v[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+#pragma unroll
+        for (int j = 0; j < 8; ++j) {
+            float4 x = *reinterpret_cast<const float4*>(tile + tc::tile_off_mn<TCR>(r, 8 * half + j));
+            v[4 * j] = x.x; v[4 * j + 1] = x.y; v[4 * j + 2] = x.z; v[4 * j + 3] = x.w;
+        }
+        tc::tmem_st32(a_tmem + ((uint32_t)(32 * warp) << 16) + 32 * half, v);
+    }
+}
+
+// D[64x64] = A * B^T with A in TMEM (hi at a_tmem, lo at a_tmem + 64 columns), B K-major in smem
+__device__ __forceinline__ void issue_transform_ts(uint32_t d_tmem, uint32_t a_tmem, uint32_t b_hi, uint32_t b_lo) {
+    constexpr uint32_t idesc = tc::idesc_tf32(64, 64, 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        tc::mma_tf32_ts(d_tmem, a_tmem + 64 + 8 * ks, tc::desc_kmajor<TCR>(b_hi, ks), idesc, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        tc::mma_tf32_ts(d_tmem, a_tmem + 8 * ks, tc::desc_kmajor<TCR>(b_lo, ks), idesc, true);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        tc::mma_tf32_ts(d_tmem, a_tmem + 8 * ks, tc::desc_kmajor<TCR>(b_hi, ks), idesc, true);
+}
+
+// W [64][64] row-major -> hi/lo tiles with tile(row, col) = transpose ? W[col][row] : W[row][col]
+__device__ __forceinline__ void load_weight_tiles(uint8_t* hi_tile, uint8_t* lo_tile, const float* __restrict__ W, bool transpose) {
+    for (int e = threadIdx.x; e < 64 * 64; e += TC_THREADS) {
+        int a = e >> 6, b = e & 63;
+        float v = __ldg(W + e);
+        int row = transpose ? b : a, col = transpose ? a : b;
+        float hi = tc::tf32_rn(v), lo = tc::tf32_rn(v - hi);
+        uint32_t off = tc::tile_off<TCR>(row, col >> 2) + (col & 3) * 4;
+        *reinterpret_cast<float*>(hi_tile + off) = hi;
+        *reinterpret_cast<float*>(lo_tile + off) = lo;
+    }
+}
+
+// D[64x64] = A * B^T with A (rows r, K-major) and B (rows n, K-major), 3xTF32; small terms first
+__device__ __forceinline__ void issue_transform(uint32_t d_tmem, uint32_t a_hi, uint32_t a_lo, uint32_t b_hi, uint32_t b_lo) {
+    constexpr uint32_t idesc = tc::idesc_tf32(64, 64, 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        tc::mma_tf32(d_tmem, tc::desc_kmajor<TCR>(a_lo, ks), tc::desc_kmajor<TCR>(b_hi, ks), idesc, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        tc::mma_tf32(d_tmem, tc::desc_kmajor<TCR>(a_hi, ks), tc::desc_kmajor<TCR>(b_lo, ks), idesc, true);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        tc::mma_tf32(d_tmem, tc::desc_kmajor<TCR>(a_hi, ks), tc::desc_kmajor<TCR>(b_hi, ks), idesc, true);
+}
+
+// D2[128x64] = [A_hi ; A_lo]^T * B_lo + [A_hi ; A_lo]^T * B_hi, K = the 64 rows of the tiles;
+// all tiles MN-major (SWIZZLE_128B_BASE32B).  a_hi must be followed directly by a_lo (M = 128
+// spans the four 32-column blocks at LBO = 8 KB).  One tile per call: the tensor core adds
+// into its fp32 accumulator with truncation, so long chains are summed on the CUDA cores
+// instead (flush_d2).
+__device__ __forceinline__ void issue_reduce(uint32_t d2_tmem, uint32_t a_hi, uint32_t b_hi, uint32_t b_lo) {
+    constexpr uint32_t idesc = tc::idesc_tf32(128, 64, 1, 1);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        tc::mma_tf32(d2_tmem, tc::desc_mnmajor<TCR>(a_hi, ks), tc::desc_mnmajor<TCR>(b_lo, ks), idesc, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 8; ++ks)
+        tc::mma_tf32(d2_tmem, tc::desc_mnmajor<TCR>(a_hi, ks), tc::desc_mnmajor<TCR>(b_hi, ks), idesc, true);
+}
+
+// racc[0..32) += D2[n][32h..32h+32) + D2[64+n][32h..32h+32) with n = 32*(warp&1) + lane, h = warp>>1.
+// Warp w can only read TMEM lanes 32w..32w+31 (rows 32w+lane of D2): each thread keeps the
+// column half it accumulates and hands the other half to warp w^2 through xbuf ([4][32][36] floats).
+__device__ __forceinline__ void flush_d2(uint32_t d2_tmem, float* xbuf, float (&racc)[32]) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, h = warp >> 1;
+    float keep[32], give[32];
+    tc::tmem_ld32(d2_tmem + ((uint32_t)(32 * warp) << 16) + 32 * h, keep);
+    tc::tmem_ld32(d2_tmem + ((uint32_t)(32 * warp) << 16) + 32 * (1 - h), give);
+    float* mine = xbuf + (warp * 32 + lane) * 36;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) st4(mine + i, make_float4(give[i], give[i + 1], give[i + 2], give[i + 3]));
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    const float* theirs = xbuf + ((warp ^ 2) * 32 + lane) * 36;
+#pragma unroll
+    for (int i = 0; i < 32; i += 4) {
+        float4 o = ld4(theirs + i);
+        racc[i] += keep[i] + o.x; racc[i + 1] += keep[i + 1] + o.y;
+        racc[i + 2] += keep[i + 2] + o.z; racc[i + 3] += keep[i + 3] + o.w;
+    }
+}
+
+// D1 (UMMA M = 64: row i lives in TMEM lane 32*(i/16) + i%16) -> staging[row][STG_LD] in shared memory
+__device__ __forceinline__ void d1_to_staging(uint32_t d1_tmem, float* stg) {
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    float v[32];
+#pragma unroll
+    for (int half = 0; half < 2; ++half) {
+        tc::tmem_ld32(d1_tmem + ((uint32_t)(32 * warp) << 16) + 32 * half, v);
+        if (lane < 16) {
+            float* dst = stg + (16 * warp + lane) * STG_LD + 32 * half;
+#pragma unroll
+            for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+        }
+    }
+}
+
+struct TcShared {
+    uint64_t bar;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+// ------------------------------------------------------------------------------------
+// forward round
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS)
+k_embed_round_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ base,
+                 const float* __restrict__ mu_prev, float* __restrict__ mu_next, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b_hi = smem;                        // theta2 [n][k]
+    uint8_t* b_lo = b_hi + TILE_BYTES;
+    uint8_t* a_hi = b_lo + TILE_BYTES;           // gathered tile; a_lo follows; both reused as staging
+    uint8_t* a_lo = a_hi + TILE_BYTES;
+    TcShared* sh = reinterpret_cast<TcShared*>(a_lo + TILE_BYTES);
+    float* stg = reinterpret_cast<float*>(a_hi);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+    if (warp == 0) tc::tmem_alloc<64>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    load_weight_tiles(b_hi, b_lo, theta2_w, false);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d1 = sh->tmem_base;
+    const uint32_t s_a_hi = tc::smem_u32(a_hi), s_a_lo = tc::smem_u32(a_lo), s_b_hi = tc::smem_u32(b_hi), s_b_lo = tc::smem_u32(b_lo);
+    uint32_t phase = 0;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+        // gather: half-warp per row, float4 per lane, fixed neighbour order; split into hi/lo tiles
+        {
+            const int sub = lane >> 4, c4 = lane & 15;
+            for (int rr = sub; rr < 16; rr += 2) {
+                int rl = warp * 16 + rr;
+                float4 acc = f4zero();
+                if (rl < rows) {
+                    int r = row0 + rl, li = r, off = 0;
+                    if (g.period > 0) { int gi = r / g.period; off = gi * g.period; li = r - off; }
+                    acc = gather_row(mu_prev, g.rowptr, g.col, li, off, 64, c4);
+                }
+                store_split(a_hi, a_lo, rl, c4, acc);
+            }
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (t == 0) {
+            tc::tc_fence_after_sync();
+            issue_transform(d1, s_a_hi, s_a_lo, s_b_hi, s_b_lo);
+            tc::mma_commit(&sh->bar);
+        }
+        // prefetch the base rows of the epilogue while the tensor core works
+        float4 bv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+            bv[i] = rl < rows ? ldg4(base + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero();
+        }
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        d1_to_staging(d1, stg);                 // the A tiles are dead once the MMAs have completed
+        tc::tc_fence_before_sync();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+            if (rl < rows) {
+                float4 v = ld4(stg + rl * STG_LD + 4 * c4);
+                st4(mu_next + (size_t)(row0 + rl) * 64 + 4 * c4,
+                    make_float4(relu(v.x + bv[i].x), relu(v.y + bv[i].y), relu(v.z + bv[i].z), relu(v.w + bv[i].w)));
+            }
+        }
+        __syncthreads();                        // staging is overwritten by the next gather
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(d1);
+}
+
+// ------------------------------------------------------------------------------------
+// backward round
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS)
+k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ du_t,
+                     const float* __restrict__ mu_prev, float* __restrict__ du_prev, float* __restrict__ partial,
+                     int partial_stride, int accumulate, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b_hi = smem;                        // theta2^T: tile(row k, col n) = theta2[n][k]
+    uint8_t* b_lo = b_hi + TILE_BYTES;
+    uint8_t* g_hi = b_lo + TILE_BYTES;           // gathered du tile (g_lo must follow g_hi)
+    uint8_t* g_lo = g_hi + TILE_BYTES;
+    uint8_t* m_hi = g_lo + TILE_BYTES;           // mu^{t-1} tile
+    uint8_t* m_lo = m_hi + TILE_BYTES;
+    TcShared* sh = reinterpret_cast<TcShared*>(m_lo + TILE_BYTES);
+    float* stg = reinterpret_cast<float*>(g_hi);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+    if (warp == 0) tc::tmem_alloc<256>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    load_weight_tiles(b_hi, b_lo, theta2_w, true);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    // TMEM columns: D1 [0,64)  D2 [64,128)  A_hi [128,192)  A_lo [192,256)
+    const uint32_t d1 = sh->tmem_base, d2 = sh->tmem_base + 64, a_tm = sh->tmem_base + 128;
+    const uint32_t s_g_hi = tc::smem_u32(g_hi), s_b_hi = tc::smem_u32(b_hi),
+                   s_b_lo = tc::smem_u32(b_lo), s_m_hi = tc::smem_u32(m_hi), s_m_lo = tc::smem_u32(m_lo);
+    uint32_t phase = 0;
+    float racc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) racc[i] = 0.f;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+        {
+            const int sub = lane >> 4, c4 = lane & 15;
+            for (int rr = sub; rr < 16; rr += 2) {
+                int rl = warp * 16 + rr;
+                float4 acc = f4zero(), m = f4zero();
+                if (rl < rows) {
+                    int r = row0 + rl, li = r, off = 0;
+                    if (g.period > 0) { int gi = r / g.period; off = gi * g.period; li = r - off; }
+                    m = ldg4(mu_prev + (size_t)r * 64 + 4 * c4);
+                    acc = gather_row(du_t, g.rowptr_t, g.col_t, li, off, 64, c4);
+                }
+                store_split_mn(g_hi, g_lo, rl, c4, acc);
+                store_split_mn(m_hi, m_lo, rl, c4, m);
+            }
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        row_to_tmem(g_hi, a_tm);                 // A operand of the row transform lives in TMEM
+        row_to_tmem(g_lo, a_tm + 64);
+        tc::tmem_st_wait();
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        if (t == 0) {
+            tc::tc_fence_after_sync();
+            issue_transform_ts(d1, a_tm, s_b_hi, s_b_lo);
+            issue_reduce(d2, s_g_hi, s_m_hi, s_m_lo);
+            tc::mma_commit(&sh->bar);
+        }
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        d1_to_staging(d1, stg);                 // overwrites g tiles: all MMAs reading them have completed
+        tc::tc_fence_before_sync();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+            if (rl < rows) {
+                float4 v = ld4(stg + rl * STG_LD + 4 * c4);
+                float4 m = *reinterpret_cast<const float4*>(m_hi + tc::tile_off_mn<TCR>(rl, c4));   // sign(mu) == sign(mu_hi)
+                st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * c4,
+                    make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f));
+            }
+        }
+        __syncthreads();                        // staging is re-used as the exchange buffer
+        flush_d2(d2, stg, racc);
+        __syncthreads();                        // ... and overwritten by the next gather
+    }
+    // dtheta2 partial of this CTA (EmbedPartial<64>::TH2 == 0)
+    {
+        float* my = partial + (size_t)blockIdx.x * partial_stride + (32 * (warp & 1) + lane) * 64 + 32 * (warp >> 1);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 x = make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]);
+            if (accumulate) x = f4add(ld4(my + i), x);
+            st4(my + i, x);
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(sh->tmem_base);
+}
+
+// ------------------------------------------------------------------------------------
+// debug / self-test kernel: out = A * W^T (mode 0), out = A * W (mode 1), out[64x64] = A^T * B (mode 2),
+// out = A * W with the A operand staged through TMEM (mode 3, the backward round's transform)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS)
+k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out, int rows) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b_hi = smem;
+    uint8_t* b_lo = b_hi + TILE_BYTES;
+    uint8_t* a_hi = b_lo + TILE_BYTES;
+    uint8_t* a_lo = a_hi + TILE_BYTES;
+    uint8_t* m_hi = a_lo + TILE_BYTES;
+    uint8_t* m_lo = m_hi + TILE_BYTES;
+    TcShared* sh = reinterpret_cast<TcShared*>(m_lo + TILE_BYTES);
+    float* stg = reinterpret_cast<float*>(a_hi);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (warp == 0) tc::tmem_alloc<256>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    if (mode != 2) load_weight_tiles(b_hi, b_lo, B, mode != 0);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d1 = sh->tmem_base, d2 = sh->tmem_base + 64, a_tm = sh->tmem_base + 128;
+    uint32_t phase = 0;
+    float racc[32];
+    for (int i = 0; i < 32; ++i) racc[i] = 0.f;
+    const int num_tiles = (rows + TCR - 1) / TCR;
+    for (int tile = 0; tile < num_tiles; ++tile) {
+        const int row0 = tile * TCR, nr = min(TCR, rows - row0);
+        for (int e = t; e < TCR * 16; e += TC_THREADS) {
+            int rl = e >> 4, c4 = e & 15;
+            float4 a = rl < nr ? ldg4(A + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero();
+            if (mode < 2) store_split(a_hi, a_lo, rl, c4, a);
+            else store_split_mn(a_hi, a_lo, rl, c4, a);
+            if (mode == 2) {
+                float4 b = rl < nr ? ldg4(B + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero();
+                store_split_mn(m_hi, m_lo, rl, c4, b);
+            }
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (mode == 3) {
+            row_to_tmem(a_hi, a_tm);
+            row_to_tmem(a_lo, a_tm + 64);
+            tc::tmem_st_wait();
+            tc::tc_fence_before_sync();
+            __syncthreads();
+        }
+        if (t == 0) {
+            tc::tc_fence_after_sync();
+            if (mode < 2) issue_transform(d1, tc::smem_u32(a_hi), tc::smem_u32(a_lo), tc::smem_u32(b_hi), tc::smem_u32(b_lo));
+            else if (mode == 2) issue_reduce(d2, tc::smem_u32(a_hi), tc::smem_u32(m_hi), tc::smem_u32(m_lo));
+            else issue_transform_ts(d1, a_tm, tc::smem_u32(b_hi), tc::smem_u32(b_lo));
+            tc::mma_commit(&sh->bar);
+        }
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        if (mode != 2) {
+            d1_to_staging(d1, stg);
+            tc::tc_fence_before_sync();
+            __syncthreads();
+            for (int e = t; e < TCR * 16; e += TC_THREADS) {
+                int rl = e >> 4, c4 = e & 15;
+                if (rl < nr) st4(out + (size_t)(row0 + rl) * 64 + 4 * c4, ld4(stg + rl * STG_LD + 4 * c4));
+            }
+        } else {
+            flush_d2(d2, stg, racc);
+        }
+        __syncthreads();
+    }
+    if (mode == 2) {
+        float* my = out + (32 * (warp & 1) + lane) * 64 + 32 * (warp >> 1);
+        for (int i = 0; i < 32; ++i) my[i] = racc[i];
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(sh->tmem_base);
+}
+
+constexpr int FWD_SMEM = 4 * TILE_BYTES + 64 + 1024;
+constexpr int BWD_SMEM = 6 * TILE_BYTES + 64 + 1024;
+
+int tc_grid(const void* kernel, int smem, int tiles) {
+    int dev = 0, sms = 0, per_sm = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TC_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    int grid = sms * per_sm;
+    if (grid > S2V_MAX_GRID) grid = S2V_MAX_GRID;
+    if (grid > tiles) grid = tiles;
+    return grid < 1 ? 1 : grid;
+}
+
+}  // namespace
+
+// Launchers used by s2v_embed.cu (p = 64 only).  grid_out: number of CTAs (= dtheta2 partials).
+int s2v_tc_round_forward(const s2v_graph_t& g, const float* theta2_w, const float* base, const float* mu_prev,
+                         float* mu_next, cudaStream_t st) {
+    const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
+    int grid = tc_grid((const void*)k_embed_round_tc, FWD_SMEM, tiles);
+    k_embed_round_tc<<<grid, TC_THREADS, FWD_SMEM, st>>>(g, theta2_w, base, mu_prev, mu_next, tiles);
+    return (int)cudaGetLastError();
+}
+
+int s2v_tc_round_backward_grid(int num_nodes) {
+    const int tiles = (num_nodes + TCR - 1) / TCR;
+    cudaFuncSetAttribute(k_embed_round_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    return tc_grid((const void*)k_embed_round_bwd_tc, BWD_SMEM, tiles);
+}
+
+int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
+                          float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st) {
+    const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    k_embed_round_bwd_tc<<<grid, TC_THREADS, BWD_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
+                                                            accumulate, tiles);
+    return (int)cudaGetLastError();
+}
+
+extern "C" int s2v_debug_tc_gemm(int32_t mode, const float* A, const float* B, float* out, int64_t rows, void* stream) {
+    if (!A || !B || !out || rows < 1 || mode < 0 || mode > 3) return S2V_ERR_BAD_ARG;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    k_tc_selftest<<<1, TC_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(mode, A, B, out, (int)rows);
+    return (int)cudaGetLastError();
+}

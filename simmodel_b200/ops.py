@@ -27,6 +27,7 @@ def _embed_struct(T, w):
     """w: 10 tensors theta1a.w,b 1b.w,b 2.w,b 3.w,b 4.w,b"""
     prm = _lib.EmbedParams()
     prm.node_dim, prm.emb_dim, prm.rounds = int(w[0].shape[1]), int(w[0].shape[0]), int(T)
+    prm.flags = _lib.path_flag()
     (prm.theta1a_w, prm.theta1a_b, prm.theta1b_w, prm.theta1b_b, prm.theta2_w, prm.theta2_b,
      prm.theta3_w, prm.theta3_b, prm.theta4_w, prm.theta4_b) = [_p(t) for t in w]
     return prm
@@ -79,7 +80,7 @@ def _embed_backward(layout, T, x, w, base, mus, dmu, dmu_masked, dus=None):
         _lib.check(L.s2v_embed_backward(C.byref(layout.c_struct()), C.byref(prm), _p(x), _p(base), _p(mus), _p(dmu),
                                         int(dmu_masked), _p(dus), _p(ws), ws.numel(), _p(grad), _stream()),
                    "s2v_embed_backward")
-    _lib.launch_count += T + 1 + (0 if dmu_masked else 1)
+    _lib.launch_count += T + 3 + (0 if dmu_masked else 1)
     return _split_embed_grad(grad, F, P), grad
 
 

@@ -159,18 +159,20 @@ def test_ppo_golden(case, cuda_device):
     prob, _ = model.pi(nfm, ei, reach, hidden)
     v, _ = model.v(nfm, ei, reach, hidden)
     assert prob.shape == G["out"]["prob"].shape and v.shape == G["out"]["v"].shape
-    # EMB cases run a cuDNN LSTM (not ours; different summation order than the CPU LSTM of the
-    # golden run) between our embedding and our head: 3e-5 there, 1e-5 everywhere else
-    tol = 3e-5 if meta["lstm_type"] == "EMB" else TOL
-    _check("prob", prob.detach().cpu().numpy(), G["out"]["prob"], tol=tol)
-    _check("v", v.detach().cpu().numpy(), G["out"]["v"], tol=tol)
+    # EMB cases run a cuDNN LSTM (not ours: its own summation order, run-to-run non-deterministic
+    # backward) between our embedding and our head, and the Manhattan5 case is cancellation-heavy
+    # (the reference's own fp32-vs-fp64 gradient error is 1.7e-5 there): 1e-4 for those, 1e-5 (or 2x the
+    # reference's own fp32 error) everywhere else.
+    tol = 1e-4 if meta["lstm_type"] == "EMB" else TOL
+    _check("prob", prob.detach().cpu().numpy(), G["out"]["prob"], G["out"]["prob_f64"], tol=tol)
+    _check("v", v.detach().cpu().numpy(), G["out"]["v"], G["out"]["v_f64"], tol=tol)
     # masked entries are exactly zero, positions identical (bit-exact)
     assert np.array_equal(prob.detach().cpu().numpy() == 0.0, G["out"]["prob"] == 0.0)
     loss = (prob * torch.from_numpy(G["inp"]["wprob"]).to(dev)).sum() + (v * torch.from_numpy(G["inp"]["wv"]).to(dev)).sum()
     loss.backward()
     for k, prm in model.named_parameters():
         g = prm.grad.cpu().numpy() if prm.grad is not None else np.zeros(tuple(prm.shape), dtype=np.float32)
-        _check("grad " + k, g, G["grad"][k], tol=tol, abs_floor=2e-7)
+        _check("grad " + k, g, G["grad"][k], G["grad64"][k], tol=tol, abs_floor=2e-7)
     mu = model.s2v(nfm, torch.from_numpy(_dense_from_ei(G["inp"]["edge_index"], meta["N"])))
     _check("mu_s2v", mu.detach().cpu().numpy(), G["out"]["mu_s2v"])
     mu2, _ = model.create_embeddings(meta["S"], nfm, ei, hidden)
@@ -367,13 +369,17 @@ def test_real_topologies_vs_sparse_oracle(topo_name, B, cuda_device):
     assert torch.equal(q_r.detach(), outs[0][0])
 
 
-def test_full_size_properties(cuda_device):
-    """BASELINE-sized batch (AMS, B=512): size-independent properties.
+@pytest.mark.parametrize("path", ["ffma", "tc"])
+def test_full_size_properties(path, cuda_device, monkeypatch):
+    """BASELINE-sized batch (AMS, B=512): size-independent properties, on both kernel paths
+    (CUDA-core FP32 and tcgen05 3xTF32, forced for every size so that single graphs and the batch
+    run the same kernels).
     (i) graphs are independent: every graph of the batch equals the same graph run alone (bit-exact);
     (ii) permutation: shuffling graph order permutes q (bit-exact);
     (iii) gradient of a batch = sum of per-half gradients (linearity, 1e-5);
     (iv) Npad enters only through the theta4 term: with theta4 = 0 and b4 <= 0 the result is Npad-invariant."""
     import simmodel_b200 as sb
+    monkeypatch.setenv("S2V_B200_PATH", path)
     dev = cuda_device
     topo = sb.graphs.load_topology("NWB_AMS")
     B, N = 512, topo.num_nodes

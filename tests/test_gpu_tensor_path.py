@@ -1,0 +1,85 @@
+"""tcgen05 / TMEM path (p = 64): building blocks against fp64, single rounds against the FFMA
+kernels, and the whole parity suite re-run with the tensor path forced on (S2V_B200_PATH=tc)."""
+import ctypes as C
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _ptr(t):
+    return C.c_void_p(t.data_ptr())
+
+
+@pytest.mark.parametrize("rows", [64, 200, 1000])
+@pytest.mark.parametrize("mode", [0, 1, 2, 3])
+def test_tc_building_blocks(mode, rows, cuda_device):
+    """3xTF32 UMMA with hand-built SWIZZLE_128B tiles: A W^T, A W (K-major operands, M = 64) and
+    A^T B over the rows (MN-major operands, stacked M = 128, accumulated in TMEM across tiles)."""
+    from simmodel_b200 import _lib
+    L = _lib.lib()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(rows * 3 + mode)
+    A = (torch.randn(rows, 64, generator=g) * torch.logspace(-2, 2, 64)).to(dev)
+    B = torch.randn(64 if mode != 2 else rows, 64, generator=g).to(dev)
+    out = torch.full((rows if mode != 2 else 64, 64), float("nan"), device=dev)
+    _lib.check(L.s2v_debug_tc_gemm(mode, _ptr(A), _ptr(B), _ptr(out), rows, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "s2v_debug_tc_gemm")
+    torch.cuda.synchronize()
+    A64, B64 = A.double(), B.double()
+    ref = A64 @ B64.t() if mode == 0 else A64 @ B64 if mode in (1, 3) else A64.t() @ B64
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    ref32 = (A @ B.t() if mode == 0 else A @ B if mode in (1, 3) else A.t() @ B).double()
+    err32 = float((ref32 - ref).abs().max() / ref.abs().max())
+    assert err < 2e-6, (mode, rows, err, err32)
+
+
+@pytest.mark.parametrize("topo_name,B", [("NWB_AMS", 9), ("Manhattan5", 7)])
+def test_single_round_tc_vs_ffma(topo_name, B, cuda_device):
+    import simmodel_b200 as sb
+    from simmodel_b200 import _lib
+    L = _lib.lib()
+    dev = cuda_device
+    topo = sb.graphs.load_topology(topo_name)
+    n = B * topo.num_nodes
+    lay = sb.GraphLayout.from_batch(sb.graphs.batch_edge_index(topo, B).to(dev),
+                                    (torch.arange(B + 1) * topo.num_nodes).to(dev), topo.num_nodes)
+    gen = torch.Generator().manual_seed(3)
+    w2 = (torch.randn(64, 64, generator=gen) / 8).to(dev)
+    base = torch.randn(n, 64, generator=gen).to(dev)
+    mu = torch.randn(n, 64, generator=gen).clamp(min=0).to(dev)
+    du = torch.randn(n, 64, generator=gen).to(dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = lay.c_struct()
+    outs = {}
+    for flag in (1, 2):
+        o = torch.empty(n, 64, device=dev)
+        _lib.check(L.s2v_embed_round_forward(C.byref(g), 64, flag, _ptr(w2), _ptr(base), _ptr(mu), _ptr(o), st), "fwd")
+        d = torch.empty(n, 64, device=dev)
+        ws = torch.zeros(L.s2v_embed_backward_workspace_bytes(7, 64), dtype=torch.uint8, device=dev)
+        _lib.check(L.s2v_embed_round_backward(C.byref(g), 7, 64, flag, _ptr(w2), _ptr(du), _ptr(mu), _ptr(d), _ptr(ws),
+                                              ws.numel(), st), "bwd")
+        torch.cuda.synchronize()
+        stride = 2 * 64 * 64 + 4 * 64 + 64 * 7
+        part = ws.view(torch.float32)[: 1024 * stride].view(1024, stride)[:, : 64 * 64].sum(0)
+        outs[flag] = (o, d, part)
+    for a, b, name in zip(outs[1], outs[2], ("mu_next", "du_prev", "dtheta2")):
+        err = float((a - b).abs().max() / a.abs().max())
+        assert err < 3e-6, (name, err)
+    # exact zero pattern of the ReLU mask must agree
+    assert torch.equal(outs[1][1] == 0, outs[2][1] == 0)
+
+
+def test_parity_suite_with_tensor_path_forced(cuda_device):
+    """Every p = 64 parity case again with the tcgen05 kernels forced on for all sizes."""
+    env = dict(os.environ, S2V_B200_PATH="tc")
+    out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu",
+                          "-q", "-x", "--tb=short", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
+                         timeout=900, cwd=ROOT)
+    assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
