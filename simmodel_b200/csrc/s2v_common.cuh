@@ -197,6 +197,90 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ src, cons
     return acc;
 }
 
+// p = 64 gather with memory-level parallelism.  A half-warp (16 lanes x float4 = one 256-byte
+// row) produces 8 consecutive tile rows [rl0, rl0+8): (1) lanes 0-7 fetch the CSR extents of the 8
+// rows, (2) all 8 neighbour-id lists (up to 16 ids each, one per lane) are fetched in one round
+// trip, (3) the neighbour rows are loaded in straight-line batches of 2 rows x 4 neighbours (8
+// independent 128-bit loads in flight per lane); rows with more than 4 (16) neighbours take extra
+// passes.  The per-row summation order is the CSR order, identical to gather_row, so results are
+// bit-identical to the simple form.  sink(rl, acc) is called by all 16 lanes for each row.
+// Step (1)+(2) for one tile can be issued while the previous tile is still in its GEMM / epilogue
+// (gather8_prefetch), leaving a single memory round trip in front of the data (gather8_consume).
+struct Gather8Meta {
+    int b, d, off;       // lanes 0-7 (and their mirrors 8-15): CSR begin, degree, graph offset of row rl0 + (lane&7)
+    int idx[8];          // lane c: c-th neighbour id of row rl0 + i
+};
+
+__device__ __forceinline__ void gather8_prefetch(Gather8Meta& m, const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
+                                                 const int32_t* __restrict__ col, int row0, int rows, int rl0) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = threadIdx.x & 15;
+    m.b = 0; m.d = 0; m.off = 0;
+    int rl = rl0 + (c & 7);
+    if (rl < rows) {
+        int r = row0 + rl, li = r;
+        if (g.period > 0) { int gi = r / g.period; m.off = gi * g.period; li = r - m.off; }
+        m.b = __ldg(rowptr + li);
+        m.d = __ldg(rowptr + li + 1) - m.b;
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int bi = __shfl_sync(FULL, m.b, i, 16), di = __shfl_sync(FULL, m.d, i, 16);
+        m.idx[i] = c < di ? __ldg(col + bi + c) : 0;
+    }
+}
+
+template <class Sink>
+__device__ __forceinline__ void gather8_consume(const Gather8Meta& m, const int32_t* __restrict__ col,
+                                                const float* __restrict__ src, int rl0, Sink&& sink) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = threadIdx.x & 15;
+    // all warp shuffles first: the loads below must not be separated by convergent operations,
+    // otherwise the compiler serialises them row by row (one memory round trip per row)
+    int dd[8], oo[8], jj[8][4];
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        dd[i] = __shfl_sync(FULL, m.d, i, 16);
+        oo[i] = __shfl_sync(FULL, m.off, i, 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) jj[i][k] = __shfl_sync(FULL, m.idx[i], k, 16);
+    }
+    float4 acc[8];
+#pragma unroll
+    for (int h = 0; h < 2; ++h) {             // two batches of 4 rows x 4 neighbours = 16 independent 128-bit loads
+        float4 v[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                v[i][k] = dd[4 * h + i] > k ? ldg4(src + (size_t)(oo[4 * h + i] + jj[4 * h + i][k]) * 64 + 4 * c) : f4zero();
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            acc[4 * h + i] = f4add(f4add(f4add(f4add(f4zero(), v[i][0]), v[i][1]), v[i][2]), v[i][3]);
+    }
+#pragma unroll
+    for (int i = 0; i < 8; ++i) {
+        int dmax = max(dd[i], __shfl_xor_sync(FULL, dd[i], 16));    // uniform over the warp
+        if (dmax > 4) {
+            int bi = __shfl_sync(FULL, m.b, i, 16);
+            for (int k = 4; k < dmax; ++k) {
+                int j = k < 16 ? __shfl_sync(FULL, m.idx[i], k, 16) : (k < dd[i] ? __ldg(col + bi + k) : 0);
+                if (k < dd[i]) acc[i] = f4add(acc[i], ldg4(src + (size_t)(oo[i] + j) * 64 + 4 * c));
+            }
+        }
+        sink(rl0 + i, acc[i]);
+    }
+}
+
+template <class Sink>
+__device__ __forceinline__ void gather8_p64(const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
+                                            const int32_t* __restrict__ col, const float* __restrict__ src,
+                                            int row0, int rows, int rl0, Sink&& sink) {
+    Gather8Meta m;
+    gather8_prefetch(m, g, rowptr, col, row0, rows, rl0);
+    gather8_consume(m, col, src, rl0, sink);
+}
+
 // Gather a tile: As[rl][:] = sum of neighbour rows of batch row row0+rl (zeros past num_nodes).
 template <int P>
 __device__ __forceinline__ void gather_tile(float* As, const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
@@ -205,6 +289,11 @@ __device__ __forceinline__ void gather_tile(float* As, const s2v_graph_t& g, con
     constexpr int LDA = Cfg<P>::LDA, LPR = Cfg<P>::LPR, RPP = Cfg<P>::RPP;
     constexpr int ROWS_PER_WARP = S2V_TM / (S2V_THREADS / 32);
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if constexpr (P == 64) {
+        gather8_p64(g, rowptr, col, src, row0, rows, warp * ROWS_PER_WARP + 8 * (lane >> 4),
+                    [&](int rl, const float4& acc) { st4(As + rl * LDA + 4 * (lane & 15), acc); });
+        return;
+    }
     int sub = lane / LPR, c4 = lane - sub * LPR;
     if (sub >= RPP) return;
     for (int rr = sub; rr < ROWS_PER_WARP; rr += RPP) {

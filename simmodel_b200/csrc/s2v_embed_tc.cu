@@ -16,6 +16,13 @@
 #include "s2v_common.cuh"
 #include "s2v_tc.cuh"
 
+#ifdef S2V_TC_TIMELINE
+__device__ long long g_timeline[16 * 8];
+#define TL(slot) do { if (blockIdx.x == 0 && threadIdx.x == 32 && tl_n < 8) g_timeline[tl_n * 16 + (slot)] = clock64(); } while (0)
+#else
+#define TL(slot) do {} while (0)
+#endif
+
 namespace {
 
 constexpr int TCR = 64;                         // rows per tile
@@ -185,31 +192,37 @@ k_embed_round_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
     const uint32_t d1 = sh->tmem_base;
     const uint32_t s_a_hi = tc::smem_u32(a_hi), s_a_lo = tc::smem_u32(a_lo), s_b_hi = tc::smem_u32(b_hi), s_b_lo = tc::smem_u32(b_lo);
     uint32_t phase = 0;
+    const int rl0 = warp * 16 + 8 * (lane >> 4);
+    Gather8Meta meta;
+    if (blockIdx.x < num_tiles)
+        gather8_prefetch(meta, g, g.rowptr, g.col, blockIdx.x * TCR, min(TCR, g.num_nodes - blockIdx.x * TCR), rl0);
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * TCR;
         const int rows = min(TCR, g.num_nodes - row0);
-        // gather: half-warp per row, float4 per lane, fixed neighbour order; split into hi/lo tiles
-        {
-            const int sub = lane >> 4, c4 = lane & 15;
-            for (int rr = sub; rr < 16; rr += 2) {
-                int rl = warp * 16 + rr;
-                float4 acc = f4zero();
-                if (rl < rows) {
-                    int r = row0 + rl, li = r, off = 0;
-                    if (g.period > 0) { int gi = r / g.period; off = gi * g.period; li = r - off; }
-                    acc = gather_row(mu_prev, g.rowptr, g.col, li, off, 64, c4);
-                }
-                store_split(a_hi, a_lo, rl, c4, acc);
-            }
-        }
+#ifdef S2V_TC_TIMELINE
+        const int tl_n = (tile - blockIdx.x) / gridDim.x - 2;
+#endif
+        TL(0);
+        // gather (8 rows per half-warp, fixed neighbour order; CSR metadata was prefetched) and split into hi/lo tiles
+        gather8_consume(meta, g.col, mu_prev, rl0,
+                        [&](int rl, const float4& acc) { store_split(a_hi, a_lo, rl, lane & 15, acc); });
+        TL(1);
         tc::fence_proxy_async_smem();
         __syncthreads();
+        TL(2);
         if (t == 0) {
             tc::tc_fence_after_sync();
             issue_transform(d1, s_a_hi, s_a_lo, s_b_hi, s_b_lo);
             tc::mma_commit(&sh->bar);
         }
+        __syncwarp();                           // lanes 1-31 of warp 0 must not sleep in try_wait before lane 0 has issued
+        TL(3);
+        {
+            const int nt = tile + gridDim.x;     // CSR metadata of the next tile: overlaps MMA + epilogue
+            if (nt < num_tiles) gather8_prefetch(meta, g, g.rowptr, g.col, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
+        }
+        TL(4);
         // prefetch the base rows of the epilogue while the tensor core works
         float4 bv[8];
 #pragma unroll
@@ -217,12 +230,15 @@ k_embed_round_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
             int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
             bv[i] = rl < rows ? ldg4(base + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero();
         }
+        TL(5);
         tc::mbar_wait(&sh->bar, phase);
         phase ^= 1;
         tc::tc_fence_after_sync();
+        TL(6);
         d1_to_staging(d1, stg);                 // the A tiles are dead once the MMAs have completed
         tc::tc_fence_before_sync();
         __syncthreads();
+        TL(7);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
@@ -232,7 +248,9 @@ k_embed_round_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
                     make_float4(relu(v.x + bv[i].x), relu(v.y + bv[i].y), relu(v.z + bv[i].z), relu(v.w + bv[i].w)));
             }
         }
+        TL(8);
         __syncthreads();                        // staging is overwritten by the next gather
+        TL(9);
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -273,24 +291,27 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
     float racc[32];
 #pragma unroll
     for (int i = 0; i < 32; ++i) racc[i] = 0.f;
+    const int rl0 = warp * 16 + 8 * (lane >> 4);
+    Gather8Meta meta;
+    if (blockIdx.x < num_tiles)
+        gather8_prefetch(meta, g, g.rowptr_t, g.col_t, blockIdx.x * TCR, min(TCR, g.num_nodes - blockIdx.x * TCR), rl0);
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * TCR;
         const int rows = min(TCR, g.num_nodes - row0);
         {
-            const int sub = lane >> 4, c4 = lane & 15;
-            for (int rr = sub; rr < 16; rr += 2) {
-                int rl = warp * 16 + rr;
-                float4 acc = f4zero(), m = f4zero();
-                if (rl < rows) {
-                    int r = row0 + rl, li = r, off = 0;
-                    if (g.period > 0) { int gi = r / g.period; off = gi * g.period; li = r - off; }
-                    m = ldg4(mu_prev + (size_t)r * 64 + 4 * c4);
-                    acc = gather_row(du_t, g.rowptr_t, g.col_t, li, off, 64, c4);
-                }
-                store_split_mn(g_hi, g_lo, rl, c4, acc);
-                store_split_mn(m_hi, m_lo, rl, c4, m);
-            }
+            const int c4 = lane & 15;
+            float4 m[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                m[i] = rl0 + i < rows ? ldg4(mu_prev + (size_t)(row0 + rl0 + i) * 64 + 4 * c4) : f4zero();
+            gather8_consume(meta, g.col_t, du_t, rl0,
+                            [&](int rl, const float4& acc) { store_split_mn(g_hi, g_lo, rl, c4, acc); });
+#pragma unroll
+            for (int i = 0; i < 8; ++i) store_split_mn(m_hi, m_lo, rl0 + i, c4, m[i]);
+            const int nt = tile + gridDim.x;     // CSR metadata of the next tile: overlaps MMA + epilogue
+            if (nt < num_tiles)
+                gather8_prefetch(meta, g, g.rowptr_t, g.col_t, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
         }
         tc::fence_proxy_async_smem();
         __syncthreads();
@@ -305,6 +326,7 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             issue_reduce(d2, s_g_hi, s_m_hi, s_m_lo);
             tc::mma_commit(&sh->bar);
         }
+        __syncwarp();                           // lanes 1-31 of warp 0 must not sleep in try_wait before lane 0 has issued
         tc::mbar_wait(&sh->bar, phase);
         phase ^= 1;
         tc::tc_fence_after_sync();
@@ -397,6 +419,7 @@ k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ B
             else issue_transform_ts(d1, a_tm, tc::smem_u32(b_hi), tc::smem_u32(b_lo));
             tc::mma_commit(&sh->bar);
         }
+        __syncwarp();                           // lanes 1-31 of warp 0 must not sleep in try_wait before lane 0 has issued
         tc::mbar_wait(&sh->bar, phase);
         phase ^= 1;
         tc::tc_fence_after_sync();
@@ -425,12 +448,24 @@ k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ B
 constexpr int FWD_SMEM = 4 * TILE_BYTES + 64 + 1024;
 constexpr int BWD_SMEM = 6 * TILE_BYTES + 64 + 1024;
 
-int tc_grid(const void* kernel, int smem, int tiles) {
-    int dev = 0, sms = 0, per_sm = 0;
+// Resident CTAs per SM from the kernel's own resource use (registers, shared memory, TMEM columns).
+int tc_grid(const void* kernel, int smem, int tmem_cols, int tiles) {
+    int dev = 0, sms = 0, smem_sm = 0, regs_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, TC_THREADS, smem);
-    if (per_sm < 1) per_sm = 1;
+    cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+    cudaDeviceGetAttribute(&regs_sm, cudaDevAttrMaxRegistersPerMultiprocessor, dev);
+    cudaFuncAttributes fa;
+    int per_sm = 1;
+    if (cudaFuncGetAttributes(&fa, kernel) == cudaSuccess) {
+        int regs_cta = ((fa.numRegs + 7) / 8 * 8) * TC_THREADS;
+        int by_regs = regs_cta > 0 ? regs_sm / regs_cta : 1;
+        int by_smem = smem_sm / (smem + (int)fa.sharedSizeBytes + 1024);      // 1 KB reserved per CTA
+        int by_tmem = 512 / tmem_cols;
+        per_sm = by_regs < by_smem ? by_regs : by_smem;
+        if (by_tmem < per_sm) per_sm = by_tmem;
+        if (per_sm < 1) per_sm = 1;
+    }
     int grid = sms * per_sm;
     if (grid > S2V_MAX_GRID) grid = S2V_MAX_GRID;
     if (grid > tiles) grid = tiles;
@@ -444,7 +479,7 @@ int s2v_tc_round_forward(const s2v_graph_t& g, const float* theta2_w, const floa
                          float* mu_next, cudaStream_t st) {
     const int tiles = (g.num_nodes + TCR - 1) / TCR;
     S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD_SMEM));
-    int grid = tc_grid((const void*)k_embed_round_tc, FWD_SMEM, tiles);
+    int grid = tc_grid((const void*)k_embed_round_tc, FWD_SMEM, 64, tiles);
     k_embed_round_tc<<<grid, TC_THREADS, FWD_SMEM, st>>>(g, theta2_w, base, mu_prev, mu_next, tiles);
     return (int)cudaGetLastError();
 }
@@ -452,7 +487,7 @@ int s2v_tc_round_forward(const s2v_graph_t& g, const float* theta2_w, const floa
 int s2v_tc_round_backward_grid(int num_nodes) {
     const int tiles = (num_nodes + TCR - 1) / TCR;
     cudaFuncSetAttribute(k_embed_round_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    return tc_grid((const void*)k_embed_round_bwd_tc, BWD_SMEM, tiles);
+    return tc_grid((const void*)k_embed_round_bwd_tc, BWD_SMEM, 256, tiles);
 }
 
 int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
@@ -463,6 +498,12 @@ int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const flo
                                                             accumulate, tiles);
     return (int)cudaGetLastError();
 }
+
+#ifdef S2V_TC_TIMELINE
+extern "C" int s2v_debug_timeline(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 16 * 8);
+}
+#endif
 
 extern "C" int s2v_debug_tc_gemm(int32_t mode, const float* A, const float* B, float* out, int64_t rows, void* stream) {
     if (!A || !B || !out || rows < 1 || mode < 0 || mode > 3) return S2V_ERR_BAD_ARG;
