@@ -215,6 +215,25 @@ k_head_bwd(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, c
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * S2V_TM;
         const int rows = min(S2V_TM, g.num_nodes - row0);
+        // A tile whose dq entries are all zero has dL = 0: nothing to add to dtheta7/db7/dw5b and
+        // dmu reduces to the pooled term.  The DQN loss touches ONE node per graph
+        // (qvals[actions + ptr[:-1]], comb_opt.py:355-356), so almost every tile takes this exit.
+        const bool live = __syncthreads_or(t < rows && __ldg(dq + row0 + t) != 0.f);
+        if (!live) {
+            constexpr int V = P / 4;
+            for (int e = t; e < rows * V; e += S2V_THREADS) {
+                int rl = e / V, c = e - rl * V;
+                int li, off, gi;
+                row_info(g, row0 + rl, li, off, gi);
+                float4 o = ldg4(per_graph + (size_t)gi * (2 * P + 4) + P + 4 * c);
+                if (mask_relu) {
+                    float4 m = ldg4(mu + (size_t)(row0 + rl) * P + 4 * c);
+                    o = make_float4(m.x > 0.f ? o.x : 0.f, m.y > 0.f ? o.y : 0.f, m.z > 0.f ? o.z : 0.f, m.w > 0.f ? o.w : 0.f);
+                }
+                st4(dmu + (size_t)(row0 + rl) * P + 4 * c, o);
+            }
+            continue;
+        }
         load_tile<P>(As, mu + (size_t)row0 * P, rows);
         __syncthreads();
         if (active) {
@@ -270,14 +289,87 @@ k_head_bwd(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, c
     reduce_columns<P>(scratch, pW5, my + HP::W5B, tx, ty, active, false);
 }
 
+// Per-graph quantities reduced over the graphs of the batch, 64 graphs per tile:
+//   dtheta6 += dG_g pool_g^T,  db6 += dG_g,  dw5[:P] += s_g relu(G_g),  db5 += s_g
+template <int P>
+struct HeadGraphPartial {
+    static constexpr int TH6 = 0;              // P*P
+    static constexpr int B6 = P * P;           // P
+    static constexpr int W5A = B6 + P;         // P
+    static constexpr int B5 = W5A + P;         // 4 (one used)
+    static constexpr int SIZE = B5 + 4;
+};
+
+template <int P>
+__global__ void __launch_bounds__(S2V_THREADS)
+k_head_graph_partials(int num_graphs, const float* __restrict__ per_graph, const float* __restrict__ pool,
+                      const float* __restrict__ gstate, float* __restrict__ partial, int num_tiles) {
+    using C = Cfg<P>;
+    using GP = HeadGraphPartial<P>;
+    extern __shared__ __align__(16) float smem[];
+    float* As = smem;                         // dG tile   [64 graphs][P]
+    float* Bs = As + C::TILE_FLOATS;          // pool tile
+    float* Gs = Bs + C::TILE_FLOATS;          // s_g relu(G_g) tile
+    float* sg = Gs + C::TILE_FLOATS;          // [64]
+    float* scratch = sg + S2V_TM;             // [RG][P]
+    const int t = threadIdx.x;
+    const int tx = t % C::TXP, ty = t / C::TXP;
+    const bool active = t < C::ACTIVE;
+    constexpr int PG = 2 * P + 4, V = P / 4;
+    float racc[C::NRR][4];
+#pragma unroll
+    for (int i = 0; i < C::NRR; ++i) racc[i][0] = racc[i][1] = racc[i][2] = racc[i][3] = 0.f;
+    float pB6[4] = {0.f, 0.f, 0.f, 0.f}, pW5[4] = {0.f, 0.f, 0.f, 0.f};
+    float pB5 = 0.f;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int g0 = tile * S2V_TM;
+        const int rows = min(S2V_TM, num_graphs - g0);
+        if (t < S2V_TM) sg[t] = t < rows ? __ldg(per_graph + (size_t)(g0 + t) * PG + 2 * P) : 0.f;
+        __syncthreads();
+        for (int e = t; e < S2V_TM * V; e += S2V_THREADS) {
+            int r = e / V, c = e - r * V;
+            float4 a = f4zero(), b = f4zero(), gq = f4zero();
+            if (r < rows) {
+                a = ldg4(per_graph + (size_t)(g0 + r) * PG + 4 * c);
+                b = ldg4(pool + (size_t)(g0 + r) * P + 4 * c);
+                float4 G = ldg4(gstate + (size_t)(g0 + r) * P + 4 * c);
+                float s = sg[r];
+                gq = make_float4(s * relu(G.x), s * relu(G.y), s * relu(G.z), s * relu(G.w));
+            }
+            st4(As + r * C::LDA + 4 * c, a);
+            st4(Bs + r * C::LDA + 4 * c, b);
+            st4(Gs + r * C::LDA + 4 * c, gq);
+        }
+        __syncthreads();
+        if (active) {
+            tile_reduce_gemm<P>(As, Bs, rows, racc, tx, ty);
+#pragma unroll
+            for (int i = 0; i < C::NR; ++i) {
+                int r = ty + C::RG * i;
+                if (r >= rows) continue;
+                float4 a = ld4(As + r * C::LDA + 4 * tx), gq = ld4(Gs + r * C::LDA + 4 * tx);
+                pB6[0] += a.x; pB6[1] += a.y; pB6[2] += a.z; pB6[3] += a.w;
+                pW5[0] += gq.x; pW5[1] += gq.y; pW5[2] += gq.z; pW5[3] += gq.w;
+            }
+        }
+        if (t == 0) for (int r = 0; r < rows; ++r) pB5 += sg[r];
+        __syncthreads();
+    }
+    float* my = partial + (size_t)blockIdx.x * GP::SIZE;
+    store_racc<P>(my + GP::TH6, racc, tx, ty, active, false);
+    reduce_columns<P>(scratch, pB6, my + GP::B6, tx, ty, active, false);
+    reduce_columns<P>(scratch, pW5, my + GP::W5A, tx, ty, active, false);
+    if (t == 0) { my[GP::B5] = pB5; my[GP::B5 + 1] = 0.f; my[GP::B5 + 2] = 0.f; my[GP::B5 + 3] = 0.f; }
+}
+
 // grad layout: theta5.w [2P] (global part, local part), theta5.b [1], theta6.w [P,P], theta6.b [P],
-//              theta7.w [P,P], theta7.b [P]
+//              theta7.w [P,P], theta7.b [P];  sums: HeadPartial | HeadGraphPartial
 template <int P>
 __global__ void __launch_bounds__(256)
-k_head_finalize(int num_graphs, const float* __restrict__ per_graph, const float* __restrict__ pool,
-                const float* __restrict__ gstate, const float* __restrict__ partial, int n_part,
-                float* __restrict__ grad) {
+k_head_finalize(const float* __restrict__ sums, float* __restrict__ grad) {
     using HP = HeadPartial<P>;
+    using GP = HeadGraphPartial<P>;
+    const float* sg = sums + HP::SIZE;
     const int t = threadIdx.x;
     float* g5_w = grad;
     float* g5_b = g5_w + 2 * P;
@@ -285,42 +377,16 @@ k_head_finalize(int num_graphs, const float* __restrict__ per_graph, const float
     float* g6_b = g6_w + P * P;
     float* g7_w = g6_b + P;
     float* g7_b = g7_w + P * P;
-    const int PG = 2 * P + 4;
-    auto psum = [&](int off) {
-        float s = 0.f;
-        for (int c = 0; c < n_part; ++c) s += partial[(size_t)c * HP::SIZE + off];
-        return s;
-    };
-    if (blockIdx.x == 0) {
-        for (int e = t; e < P; e += blockDim.x) {
-            float a = 0.f, b = 0.f;
-            for (int gi = 0; gi < num_graphs; ++gi) {
-                float sg = per_graph[(size_t)gi * PG + 2 * P];
-                a = fmaf(sg, relu(gstate[(size_t)gi * P + e]), a);
-                b += per_graph[(size_t)gi * PG + e];
-            }
-            g5_w[e] = a;
-            g6_b[e] = b;
-            g5_w[P + e] = psum(HP::W5B + e);
-            g7_b[e] = psum(HP::B7 + e);
-        }
-        if (t == 0) {
-            float s = 0.f;
-            for (int gi = 0; gi < num_graphs; ++gi) s += per_graph[(size_t)gi * PG + 2 * P];
-            g5_b[0] = s;
-        }
-    } else if (blockIdx.x == 1) {
-        for (int e = t; e < P * P; e += blockDim.x) g7_w[e] = psum(HP::TH7 + e);
-    } else {
-        // dtheta6[n][k] = sum_g dG_g[n] pool_g[k]; blocks 2.. split the P*P outputs
-        int nb = gridDim.x - 2, b = blockIdx.x - 2;
-        for (int e = b * blockDim.x + t; e < P * P; e += nb * blockDim.x) {
-            int n = e / P, k = e - n * P;
-            float a = 0.f;
-            for (int gi = 0; gi < num_graphs; ++gi)
-                a = fmaf(per_graph[(size_t)gi * PG + n], pool[(size_t)gi * P + k], a);
-            g6_w[e] = a;
-        }
+    for (int e = t; e < P; e += blockDim.x) {
+        g5_w[e] = sg[GP::W5A + e];
+        g5_w[P + e] = sums[HP::W5B + e];
+        g6_b[e] = sg[GP::B6 + e];
+        g7_b[e] = sums[HP::B7 + e];
+    }
+    if (t == 0) g5_b[0] = sg[GP::B5];
+    for (int e = t; e < P * P; e += blockDim.x) {
+        g6_w[e] = sg[GP::TH6 + e];
+        g7_w[e] = sums[HP::TH7 + e];
     }
 }
 
@@ -357,8 +423,18 @@ static int head_backward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm
     S2V_RETURN_IF(cudaFuncSetAttribute(k_head_bwd<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = s2v_persistent_grid((const void*)k_head_bwd<P>, smem, tiles);
     k_head_bwd<P><<<grid, S2V_THREADS, smem, st>>>(g, prm, mu, dq, per_graph, mask_relu, dmu, partial, tiles);
-    k_head_finalize<P><<<2 + 16, 256, 0, st>>>(g.num_graphs, per_graph, pool, gstate, partial, grid, grad);
-    (void)HP::SIZE;
+    // per-graph terms, then fixed-order sums of both partial sets
+    using GP = HeadGraphPartial<P>;
+    float* partial_g = partial + (size_t)S2V_MAX_GRID * HP::SIZE;
+    float* sums = partial_g + (size_t)S2V_MAX_GRID * GP::SIZE;
+    const int gtiles = (g.num_graphs + S2V_TM - 1) / S2V_TM;
+    int smem_g = (3 * C::TILE_FLOATS + S2V_TM + C::RG * P) * 4;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_head_graph_partials<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_g));
+    int grid_g = gtiles < 128 ? gtiles : 128;
+    k_head_graph_partials<P><<<grid_g, S2V_THREADS, smem_g, st>>>(g.num_graphs, per_graph, pool, gstate, partial_g, gtiles);
+    s2v_reduce_partials(partial, HP::SIZE, grid, 0, HP::SIZE, sums, st);
+    s2v_reduce_partials(partial_g, GP::SIZE, grid_g, 0, GP::SIZE, sums + HP::SIZE, st);
+    k_head_finalize<P><<<1, 256, 0, st>>>(sums, grad);
     return (int)cudaGetLastError();
 }
 
@@ -373,7 +449,7 @@ static int check_graph_h(const s2v_graph_t* g) {
 extern "C" int64_t s2v_head_grad_floats(int32_t P) { return 2 * (int64_t)P + 1 + 2 * ((int64_t)P * P + P); }
 
 extern "C" int64_t s2v_head_backward_workspace_bytes(int32_t P, int32_t num_graphs) {
-    return ((int64_t)num_graphs * (2 * P + 4) + (int64_t)S2V_MAX_GRID * (P * P + 2 * P)) * 4;
+    return ((int64_t)num_graphs * (2 * P + 4) + (int64_t)(S2V_MAX_GRID + 1) * (2 * P * P + 4 * P + 4)) * 4;
 }
 
 extern "C" int s2v_head_forward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu,
