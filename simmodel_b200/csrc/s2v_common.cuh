@@ -353,6 +353,9 @@ static inline void s2v_reduce_partials(const float* partial, int stride, int n_p
 #define S2V_PATH_FFMA 1
 #define S2V_PATH_TENSOR 2
 #define S2V_TENSOR_MIN_NODES 4096
+#ifndef S2V_TENSOR_FINAL
+#define S2V_TENSOR_FINAL 0      // tensor-core variant of the last backward stage (slower than FFMA so far)
+#endif
 
 #define S2V_DISPATCH_P(P_, CALL)                         \
     switch (P_) {                                        \

@@ -406,6 +406,12 @@ int s2v_tc_round_backward_grid(int num_nodes);
 int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
                           float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st);
 
+int s2v_tc_embed_first(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, float* base, float* mu1,
+                       cudaStream_t st);
+int s2v_tc_final_backward_grid(int num_nodes);
+int s2v_tc_final_backward(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, const float* dus,
+                          const float* du_last, float* partial, int partial_stride, int grid, cudaStream_t st);
+
 // flags (s2v_embed_params_t.flags): 0 = auto, 1 = CUDA-core FP32 path, 2 = tensor-core path
 static bool use_tensor_path(int P, int flags, int num_nodes) {
     if (P != 64 || flags == S2V_PATH_FFMA) return false;
@@ -419,13 +425,16 @@ static int embed_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& pr
     using C = Cfg<P>;
     const int tiles = (g.num_nodes + S2V_TM - 1) / S2V_TM;
     const size_t plane = (size_t)g.num_nodes * P;
-    {
+    const bool tensor = use_tensor_path(P, prm.flags, g.num_nodes);
+    if (tensor) {
+        S2V_RETURN_IF(s2v_tc_embed_first(g, prm, x, base, mus, st));
+    } else {
         int smem = (C::W_FLOATS + C::TILE_FLOATS + S2V_MAX_F * P + S2V_TM * S2V_MAX_F + 6 * P) * 4;
         S2V_RETURN_IF(set_smem(k_embed_first<P>, smem));
         int grid = s2v_persistent_grid((const void*)k_embed_first<P>, smem, tiles);
         k_embed_first<P><<<grid, S2V_THREADS, smem, st>>>(g, prm, x, base, mus, tiles);
     }
-    if (use_tensor_path(P, prm.flags, g.num_nodes)) {
+    if (tensor) {
         for (int t = 1; t < prm.rounds; ++t)
             S2V_RETURN_IF(s2v_tc_round_forward(g, prm.theta2_w, base, mus + (t - 1) * plane, mus + t * plane, st));
     } else {
@@ -485,7 +494,12 @@ static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& p
                                                                       t != T, tiles);
         }
     }
-    k_embed_final_bwd<P><<<grid_f, S2V_THREADS, smem_f, st>>>(g, prm, x, dus, du_last, T, partial, stride, tiles);
+    if (S2V_TENSOR_FINAL && use_tensor_path(P, prm.flags, g.num_nodes)) {
+        grid_f = s2v_tc_final_backward_grid(g.num_nodes);
+        S2V_RETURN_IF(s2v_tc_final_backward(g, prm, x, dus, du_last, partial, stride, grid_f, st));
+    } else {
+        k_embed_final_bwd<P><<<grid_f, S2V_THREADS, smem_f, st>>>(g, prm, x, dus, du_last, T, partial, stride, tiles);
+    }
     if (T >= 2) s2v_reduce_partials(partial, stride, grid_r, EP::TH2, P * P, sums, st);
     s2v_reduce_partials(partial, stride, grid_f, EP::TH1B, stride - EP::TH1B, sums, st);
     k_embed_finalize<P><<<1, 256, 0, st>>>(prm, sums, T >= 2, grad);

@@ -19,8 +19,12 @@
 #ifdef S2V_TC_TIMELINE
 __device__ long long g_timeline[16 * 8];
 #define TL(slot) do { if (blockIdx.x == 0 && threadIdx.x == 32 && tl_n < 8) g_timeline[tl_n * 16 + (slot)] = clock64(); } while (0)
+#define TL3(slot) do { if (blockIdx.x == 0 && threadIdx.x == 32 && tl_n >= 0 && tl_n < 8) g_timeline[tl_n * 16 + (slot)] = clock64(); } while (0)
+#define TL2(slot) do { if (blockIdx.x == 0 && threadIdx.x == 32 && tl_n >= 0 && tl_n < 8) g_timeline[tl_n * 16 + (slot)] = clock64(); } while (0)
 #else
 #define TL(slot) do {} while (0)
+#define TL2(slot) do {} while (0)
+#define TL3(slot) do {} while (0)
 #endif
 
 namespace {
@@ -299,6 +303,10 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * TCR;
         const int rows = min(TCR, g.num_nodes - row0);
+#ifdef S2V_TC_TIMELINE
+        const int tl_n = (tile - blockIdx.x) / gridDim.x - 2;
+#endif
+        TL3(0);
         {
             const int c4 = lane & 15;
             float4 m[8];
@@ -313,13 +321,16 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             if (nt < num_tiles)
                 gather8_prefetch(meta, g, g.rowptr_t, g.col_t, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
         }
+        TL3(1);
         tc::fence_proxy_async_smem();
         __syncthreads();
+        TL3(2);
         row_to_tmem(g_hi, a_tm);                 // A operand of the row transform lives in TMEM
         row_to_tmem(g_lo, a_tm + 64);
         tc::tmem_st_wait();
         tc::tc_fence_before_sync();
         __syncthreads();
+        TL3(3);
         if (t == 0) {
             tc::tc_fence_after_sync();
             issue_transform_ts(d1, a_tm, s_b_hi, s_b_lo);
@@ -327,12 +338,15 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             tc::mma_commit(&sh->bar);
         }
         __syncwarp();                           // lanes 1-31 of warp 0 must not sleep in try_wait before lane 0 has issued
+        TL3(4);
         tc::mbar_wait(&sh->bar, phase);
         phase ^= 1;
         tc::tc_fence_after_sync();
+        TL3(5);
         d1_to_staging(d1, stg);                 // overwrites g tiles: all MMAs reading them have completed
         tc::tc_fence_before_sync();
         __syncthreads();
+        TL3(6);
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
@@ -343,9 +357,11 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
                     make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f));
             }
         }
+        TL3(7);
         __syncthreads();                        // staging is re-used as the exchange buffer
         flush_d2(d2, stg, racc);
         __syncthreads();                        // ... and overwritten by the next gather
+        TL3(8);
     }
     // dtheta2 partial of this CTA (EmbedPartial<64>::TH2 == 0)
     {
@@ -356,6 +372,319 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             if (accumulate) x = f4add(ld4(my + i), x);
             st4(my + i, x);
         }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(sh->tmem_base);
+}
+
+// ------------------------------------------------------------------------------------
+// node MLP + degree term + round 1 (same math as k_embed_first, s2v_embed.cu):
+//   h = relu(theta1a x + b1a) on the CUDA cores (K = F is tiny), s1 = h theta1b^T on the tensor cores,
+//   base = s1 + b1b + b2 + b3 + c u1 + (Npad - c) u0,  mu^1 = relu(base)
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS)
+k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict__ x, float* __restrict__ base,
+                 float* __restrict__ mu1, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b_hi = smem;                        // theta1b [n][k]
+    uint8_t* b_lo = b_hi + TILE_BYTES;
+    uint8_t* a_hi = b_lo + TILE_BYTES;           // h tile; a_lo follows; both reused as staging
+    uint8_t* a_lo = a_hi + TILE_BYTES;
+    float* W1a = reinterpret_cast<float*>(a_lo + TILE_BYTES);   // [F][64]
+    float* xs = W1a + S2V_MAX_F * 64;                           // [64][F]
+    float* vec = xs + TCR * S2V_MAX_F;                          // b1a, cst, u1, u0, r1, r0 (6 x 64)
+    float* cw = vec + 6 * 64;                                   // [64] c_r, [64] Npad - c_r
+    TcShared* sh = reinterpret_cast<TcShared*>(cw + 128);
+    float* stg = reinterpret_cast<float*>(a_hi);
+    float* b1a = vec, *cst = vec + 64, *u1 = vec + 128, *u0 = vec + 192, *r1 = vec + 256, *r0 = vec + 320;
+    const int F = prm.node_dim;
+    const int t = threadIdx.x, warp = t >> 5;
+
+    if (warp == 0) tc::tmem_alloc<64>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    load_weight_tiles(b_hi, b_lo, prm.theta1b_w, false);
+    for (int e = t; e < 64 * F; e += TC_THREADS) { int n = e / F, f = e - n * F; W1a[f * 64 + n] = __ldg(prm.theta1a_w + e); }
+    if (t < 64) {
+        b1a[t] = __ldg(prm.theta1a_b + t);
+        float w4 = __ldg(prm.theta4_w + t), b4 = __ldg(prm.theta4_b + t);
+        r1[t] = relu(w4 + b4);
+        r0[t] = relu(b4);
+    }
+    __syncthreads();
+    if (t < 64) {
+        float a1 = 0.f, a0 = 0.f;
+        for (int k = 0; k < 64; ++k) {
+            float w = __ldg(prm.theta3_w + t * 64 + k);
+            a1 = fmaf(w, r1[k], a1);
+            a0 = fmaf(w, r0[k], a0);
+        }
+        u1[t] = a1;
+        u0[t] = a0;
+        cst[t] = __ldg(prm.theta1b_b + t) + __ldg(prm.theta2_b + t) + __ldg(prm.theta3_b + t);
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d1 = sh->tmem_base;
+    const uint32_t s_a_hi = tc::smem_u32(a_hi), s_a_lo = tc::smem_u32(a_lo), s_b_hi = tc::smem_u32(b_hi), s_b_lo = tc::smem_u32(b_lo);
+    uint32_t phase = 0;
+    const int c4 = t & 15, rbase = t >> 4;       // this thread's chunks: rows rbase + 8*i, columns 4*c4..4*c4+3
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+        for (int e = t; e < TCR * F; e += TC_THREADS) xs[e] = e < rows * F ? __ldg(x + (size_t)row0 * F + e) : 0.f;
+        if (t < TCR) {
+            float c = 0.f, d = 0.f;
+            if (t < rows) {
+                int li, off, gi;
+                row_info(g, row0 + t, li, off, gi);
+                c = (float)__ldg(g.indeg + li);
+                d = (float)graph_npad(g, gi) - c;
+            }
+            cw[t] = c;
+            cw[64 + t] = d;
+        }
+        __syncthreads();
+        {
+            float4 h[8];
+            const float4 bb = ld4(b1a + 4 * c4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = bb;
+            for (int f = 0; f < F; ++f) {
+                const float4 w = ld4(W1a + f * 64 + 4 * c4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float xv = xs[(rbase + 8 * i) * F + f];
+                    h[i].x = fmaf(xv, w.x, h[i].x); h[i].y = fmaf(xv, w.y, h[i].y);
+                    h[i].z = fmaf(xv, w.z, h[i].z); h[i].w = fmaf(xv, w.w, h[i].w);
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                store_split(a_hi, a_lo, rbase + 8 * i, c4, make_float4(relu(h[i].x), relu(h[i].y), relu(h[i].z), relu(h[i].w)));
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (t == 0) {
+            tc::tc_fence_after_sync();
+            issue_transform(d1, s_a_hi, s_a_lo, s_b_hi, s_b_lo);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        d1_to_staging(d1, stg);
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        {
+            const float4 c0 = ld4(cst + 4 * c4), v1 = ld4(u1 + 4 * c4), v0 = ld4(u0 + 4 * c4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int rl = rbase + 8 * i;
+                if (rl < rows) {
+                    float4 v = ld4(stg + rl * STG_LD + 4 * c4);
+                    float c = cw[rl], d = cw[64 + rl];
+                    float4 b;
+                    b.x = v.x + (c0.x + (c * v1.x + d * v0.x));
+                    b.y = v.y + (c0.y + (c * v1.y + d * v0.y));
+                    b.z = v.z + (c0.z + (c * v1.z + d * v0.z));
+                    b.w = v.w + (c0.w + (c * v1.w + d * v0.w));
+                    size_t o = (size_t)(row0 + rl) * 64 + 4 * c4;
+                    st4(base + o, b);
+                    st4(mu1 + o, make_float4(relu(b.x), relu(b.y), relu(b.z), relu(b.w)));
+                }
+            }
+        }
+        __syncthreads();
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(d1);
+}
+
+// ------------------------------------------------------------------------------------
+// last backward stage (same math as k_embed_final_bwd, s2v_embed.cu):
+//   D = sum_t du^t ;  dtheta1b += D^T h ;  dh = (D theta1b) * [h > 0] ;  dtheta1a += dh^T x ;
+//   column sums of D, c*D, (Npad-c)*D, dh
+// D and h tiles are MN-major in shared memory (operands of the reduction D2 = [D_hi;D_lo]^T h),
+// the row transform D * theta1b takes D from TMEM.  Partial layout: EmbedPartial<64> (s2v_embed.cu).
+// ------------------------------------------------------------------------------------
+constexpr int EP_TH1B = 64 * 64, EP_COLD = 2 * 64 * 64, EP_A1 = EP_COLD + 64, EP_A0 = EP_A1 + 64,
+              EP_B1A = EP_A0 + 64, EP_TH1A = EP_B1A + 64;
+
+__global__ void __launch_bounds__(TC_THREADS)
+k_embed_final_bwd_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict__ x, const float* __restrict__ dus,
+                     const float* __restrict__ du_last, int T, float* __restrict__ partial, int partial_stride,
+                     int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b_hi = smem;                        // theta1b^T: tile(row k, col n) = theta1b[n][k]
+    uint8_t* b_lo = b_hi + TILE_BYTES;
+    uint8_t* d_hi = b_lo + TILE_BYTES;           // D tile (d_lo must follow d_hi); later staging / dh
+    uint8_t* d_lo = d_hi + TILE_BYTES;
+    uint8_t* h_hi = d_lo + TILE_BYTES;           // h tile; later the D2 exchange buffer
+    uint8_t* h_lo = h_hi + TILE_BYTES;
+    float* W1a = reinterpret_cast<float*>(h_lo + TILE_BYTES);   // [F][64]
+    float* xs = W1a + S2V_MAX_F * 64;                           // [64][F]
+    float* b1a = xs + TCR * S2V_MAX_F;                          // [64]
+    float* cw = b1a + 64;                                       // [64] in-degree c_r, [64] Npad - c_r
+    TcShared* sh = reinterpret_cast<TcShared*>(cw + 128);
+    float* stg = reinterpret_cast<float*>(d_hi);
+    float* xbuf = reinterpret_cast<float*>(h_hi);
+    const int F = prm.node_dim;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const size_t plane = (size_t)g.num_nodes * 64;
+
+    if (warp == 0) tc::tmem_alloc<256>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    load_weight_tiles(b_hi, b_lo, prm.theta1b_w, true);
+    for (int e = t; e < 64 * F; e += TC_THREADS) { int n = e / F, f = e - n * F; W1a[f * 64 + n] = __ldg(prm.theta1a_w + e); }
+    if (t < 64) b1a[t] = __ldg(prm.theta1a_b + t);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d1 = sh->tmem_base, d2 = sh->tmem_base + 64, a_tm = sh->tmem_base + 128;
+    const uint32_t s_d_hi = tc::smem_u32(d_hi), s_b_hi = tc::smem_u32(b_hi), s_b_lo = tc::smem_u32(b_lo),
+                   s_h_hi = tc::smem_u32(h_hi), s_h_lo = tc::smem_u32(h_lo);
+    uint32_t phase = 0;
+    float racc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) racc[i] = 0.f;
+    float pD = 0.f, pA1 = 0.f, pA0 = 0.f, pB1a = 0.f;        // threads 0..63: column t
+    constexpr int MAXE = (64 * S2V_MAX_F + TC_THREADS - 1) / TC_THREADS;
+    float pth1a[MAXE];
+#pragma unroll
+    for (int i = 0; i < MAXE; ++i) pth1a[i] = 0.f;
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+#ifdef S2V_TC_TIMELINE
+        const int tl_n = (tile - blockIdx.x) / gridDim.x - 2;
+#endif
+        TL2(0);
+        // x tile and per-row degree weights
+        for (int e = t; e < TCR * F; e += TC_THREADS) xs[e] = e < rows * F ? __ldg(x + (size_t)row0 * F + e) : 0.f;
+        if (t < TCR) {
+            float c = 0.f, d = 0.f;
+            if (t < rows) {
+                int li, off, gi;
+                row_info(g, row0 + t, li, off, gi);
+                c = (float)__ldg(g.indeg + li);
+                d = (float)graph_npad(g, gi) - c;
+            }
+            cw[t] = c;
+            cw[64 + t] = d;
+        }
+        // D tile: fixed summation order t = 1..T
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+            float4 s4 = f4zero();
+            if (rl < rows) {
+                size_t o = (size_t)(row0 + rl) * 64 + 4 * c4;
+                for (int tt = 0; tt < T - 1; ++tt) s4 = f4add(s4, ldg4(dus + tt * plane + o));
+                s4 = f4add(s4, ldg4(du_last + o));
+            }
+            store_split_mn(d_hi, d_lo, rl, c4, s4);
+        }
+        TL2(1);
+        __syncthreads();                        // xs complete
+        // h tile (rows past the end give relu(b1a) but their D is zero)
+#pragma unroll 2
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+            float4 h = ld4(b1a + 4 * c4);
+            for (int f = 0; f < F; ++f) {
+                float xv = xs[rl * F + f];
+                float4 w = ld4(W1a + f * 64 + 4 * c4);
+                h.x = fmaf(xv, w.x, h.x); h.y = fmaf(xv, w.y, h.y); h.z = fmaf(xv, w.z, h.z); h.w = fmaf(xv, w.w, h.w);
+            }
+            store_split_mn(h_hi, h_lo, rl, c4, make_float4(relu(h.x), relu(h.y), relu(h.z), relu(h.w)));
+        }
+        tc::fence_proxy_async_smem();
+        TL2(2);
+        __syncthreads();
+        row_to_tmem(d_hi, a_tm);
+        row_to_tmem(d_lo, a_tm + 64);
+        tc::tmem_st_wait();
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        TL2(3);
+        if (t == 0) {
+            tc::tc_fence_after_sync();
+            issue_transform_ts(d1, a_tm, s_b_hi, s_b_lo);
+            issue_reduce(d2, s_d_hi, s_h_hi, s_h_lo);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        TL2(4);
+        // column sums of D on the CUDA cores while the tensor core works (D = hi + lo)
+        if (t < 64) {
+            const int c4 = t >> 2, w = t & 3;
+            for (int r = 0; r < rows; ++r) {
+                uint32_t off = tc::tile_off_mn<TCR>(r, c4) + 4 * w;
+                float v = *reinterpret_cast<const float*>(d_hi + off) + *reinterpret_cast<const float*>(d_lo + off);
+                pD += v;
+                pA1 = fmaf(cw[r], v, pA1);
+                pA0 = fmaf(cw[64 + r], v, pA0);
+            }
+        }
+        TL2(5);
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        TL2(6);
+        __syncthreads();                        // column sums done before the D tiles become staging
+        d1_to_staging(d1, stg);
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        // dh = (D theta1b) * [h > 0], kept in staging for dtheta1a / db1a
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+            float4 v = ld4(stg + rl * STG_LD + 4 * c4);
+            float4 h = *reinterpret_cast<const float4*>(h_hi + tc::tile_off_mn<TCR>(rl, c4));
+            float4 dh = make_float4(h.x > 0.f ? v.x : 0.f, h.y > 0.f ? v.y : 0.f, h.z > 0.f ? v.z : 0.f, h.w > 0.f ? v.w : 0.f);
+            if (rl >= rows) dh = f4zero();
+            st4(stg + rl * STG_LD + 4 * c4, dh);
+        }
+        __syncthreads();
+        TL2(7);
+        if (t < 64)
+            for (int r = 0; r < rows; ++r) pB1a += stg[r * STG_LD + t];
+#pragma unroll
+        for (int i = 0; i < MAXE; ++i) {
+            int e = t + i * TC_THREADS;
+            if (e < 64 * F) {
+                int k = e / F, f = e - k * F;
+                float s1 = pth1a[i];
+                for (int r = 0; r < rows; ++r) s1 = fmaf(stg[r * STG_LD + k], xs[r * F + f], s1);
+                pth1a[i] = s1;
+            }
+        }
+        TL2(8);
+        flush_d2(d2, xbuf, racc);               // h tiles are dead: exchange buffer
+        __syncthreads();
+        TL2(9);
+    }
+    float* my = partial + (size_t)blockIdx.x * partial_stride;
+    {
+        float* dst = my + EP_TH1B + (32 * (warp & 1) + lane) * 64 + 32 * (warp >> 1);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]));
+    }
+    if (t < 64) { my[EP_COLD + t] = pD; my[EP_A1 + t] = pA1; my[EP_A0 + t] = pA0; my[EP_B1A + t] = pB1a; }
+#pragma unroll
+    for (int i = 0; i < MAXE; ++i) {
+        int e = t + i * TC_THREADS;
+        if (e < 64 * F) my[EP_TH1A + e] = pth1a[i];
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -446,6 +775,8 @@ k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ B
 }
 
 constexpr int FWD_SMEM = 4 * TILE_BYTES + 64 + 1024;
+constexpr int FIRST_SMEM = 4 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 6 * 64 + 128) * 4 + 64 + 1024;
+constexpr int FIN_SMEM = 6 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 64 + 128) * 4 + 64 + 1024;
 constexpr int BWD_SMEM = 6 * TILE_BYTES + 64 + 1024;
 
 // Resident CTAs per SM from the kernel's own resource use (registers, shared memory, TMEM columns).
@@ -504,6 +835,29 @@ extern "C" int s2v_debug_timeline(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 16 * 8);
 }
 #endif
+
+int s2v_tc_embed_first(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, float* base, float* mu1,
+                       cudaStream_t st) {
+    const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_first_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM));
+    int grid = tc_grid((const void*)k_embed_first_tc, FIRST_SMEM, 64, tiles);
+    k_embed_first_tc<<<grid, TC_THREADS, FIRST_SMEM, st>>>(g, prm, x, base, mu1, tiles);
+    return (int)cudaGetLastError();
+}
+
+int s2v_tc_final_backward_grid(int num_nodes) {
+    const int tiles = (num_nodes + TCR - 1) / TCR;
+    cudaFuncSetAttribute(k_embed_final_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FIN_SMEM);
+    return tc_grid((const void*)k_embed_final_bwd_tc, FIN_SMEM, 256, tiles);
+}
+
+int s2v_tc_final_backward(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, const float* dus,
+                          const float* du_last, float* partial, int partial_stride, int grid, cudaStream_t st) {
+    const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_final_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FIN_SMEM));
+    k_embed_final_bwd_tc<<<grid, TC_THREADS, FIN_SMEM, st>>>(g, prm, x, dus, du_last, prm.rounds, partial, partial_stride, tiles);
+    return (int)cudaGetLastError();
+}
 
 extern "C" int s2v_debug_tc_gemm(int32_t mode, const float* A, const float* B, float* out, int64_t rows, void* stream) {
     if (!A || !B || !out || rows < 1 || mode < 0 || mode > 3) return S2V_ERR_BAD_ARG;
