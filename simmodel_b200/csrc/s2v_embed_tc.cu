@@ -557,10 +557,11 @@ k_embed_final_bwd_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restr
 #pragma unroll
     for (int i = 0; i < 32; ++i) racc[i] = 0.f;
     float pD = 0.f, pA1 = 0.f, pA0 = 0.f, pB1a = 0.f;        // threads 0..63: column t
-    constexpr int MAXE = (64 * S2V_MAX_F + TC_THREADS - 1) / TC_THREADS;
-    float pth1a[MAXE];
+    constexpr int MAXJ = S2V_MAX_F / 2;                       // thread -> column t % 64, features t / 64 + 2 j
+    const int kcol = t & 63, fgrp = t >> 6;
+    float pth1a[MAXJ];
 #pragma unroll
-    for (int i = 0; i < MAXE; ++i) pth1a[i] = 0.f;
+    for (int i = 0; i < MAXJ; ++i) pth1a[i] = 0.f;
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * TCR;
@@ -597,16 +598,24 @@ k_embed_final_bwd_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restr
         TL2(1);
         __syncthreads();                        // xs complete
         // h tile (rows past the end give relu(b1a) but their D is zero)
-#pragma unroll 2
-        for (int i = 0; i < 8; ++i) {
-            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
-            float4 h = ld4(b1a + 4 * c4);
+        {
+            const int c4 = t & 15, rbase = t >> 4;
+            float4 h[8];
+            const float4 bb = ld4(b1a + 4 * c4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) h[i] = bb;
             for (int f = 0; f < F; ++f) {
-                float xv = xs[rl * F + f];
-                float4 w = ld4(W1a + f * 64 + 4 * c4);
-                h.x = fmaf(xv, w.x, h.x); h.y = fmaf(xv, w.y, h.y); h.z = fmaf(xv, w.z, h.z); h.w = fmaf(xv, w.w, h.w);
+                const float4 w = ld4(W1a + f * 64 + 4 * c4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    float xv = xs[(rbase + 8 * i) * F + f];
+                    h[i].x = fmaf(xv, w.x, h[i].x); h[i].y = fmaf(xv, w.y, h[i].y);
+                    h[i].z = fmaf(xv, w.z, h[i].z); h[i].w = fmaf(xv, w.w, h[i].w);
+                }
             }
-            store_split_mn(h_hi, h_lo, rl, c4, make_float4(relu(h.x), relu(h.y), relu(h.z), relu(h.w)));
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                store_split_mn(h_hi, h_lo, rbase + 8 * i, c4, make_float4(relu(h[i].x), relu(h[i].y), relu(h[i].z), relu(h[i].w)));
         }
         tc::fence_proxy_async_smem();
         TL2(2);
@@ -659,14 +668,12 @@ k_embed_final_bwd_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restr
         TL2(7);
         if (t < 64)
             for (int r = 0; r < rows; ++r) pB1a += stg[r * STG_LD + t];
+        for (int r = 0; r < rows; ++r) {
+            const float a = stg[r * STG_LD + kcol];
 #pragma unroll
-        for (int i = 0; i < MAXE; ++i) {
-            int e = t + i * TC_THREADS;
-            if (e < 64 * F) {
-                int k = e / F, f = e - k * F;
-                float s1 = pth1a[i];
-                for (int r = 0; r < rows; ++r) s1 = fmaf(stg[r * STG_LD + k], xs[r * F + f], s1);
-                pth1a[i] = s1;
+            for (int j = 0; j < MAXJ; ++j) {
+                int f = fgrp + 2 * j;
+                if (f < F) pth1a[j] = fmaf(a, xs[r * F + f], pth1a[j]);
             }
         }
         TL2(8);
@@ -682,9 +689,9 @@ k_embed_final_bwd_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restr
     }
     if (t < 64) { my[EP_COLD + t] = pD; my[EP_A1 + t] = pA1; my[EP_A0 + t] = pA0; my[EP_B1A + t] = pB1a; }
 #pragma unroll
-    for (int i = 0; i < MAXE; ++i) {
-        int e = t + i * TC_THREADS;
-        if (e < 64 * F) my[EP_TH1A + e] = pth1a[i];
+    for (int j = 0; j < MAXJ; ++j) {
+        int f = fgrp + 2 * j;
+        if (f < F) my[EP_TH1A + kcol * F + f] = pth1a[j];
     }
     tc::tc_fence_before_sync();
     __syncthreads();
