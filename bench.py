@@ -368,8 +368,10 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
     w2 = net.theta2.weight.detach()
 
     flag = _lib.path_flag()
-    tensor = flag == 2 or (flag == 0 and n >= 4096)
-    sfx = "_tc (tcgen05 3xTF32)" if tensor else " (FFMA)"
+    tensor_f = flag == 2 or (flag == 0 and n >= 4096)        # same rule as csrc/s2v_embed.cu:use_tensor_path
+    tensor_b = flag == 2                                     # ... and use_tensor_path_bwd_round
+    sfx_f = "_tc (tcgen05 3xTF32)" if tensor_f else " (FFMA)"
+    sfx_b = "_tc (tcgen05 3xTF32)" if tensor_b else " (FFMA)"
 
     def fwd():
         _lib.check(L.s2v_embed_round_forward(C.byref(g), P, flag, _p(w2), _p(base), _p(mu), _p(out), _stream()), "round fwd")
@@ -378,7 +380,7 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
         _lib.check(L.s2v_embed_round_backward(C.byref(g), F, P, flag, _p(w2), _p(du), _p(mu), _p(out), _p(ws), ws.numel(),
                                               _stream()), "round bwd")
     res = []
-    for name, fn in (("k_embed_round" + sfx + ", forward round", fwd), ("k_embed_round_bwd" + sfx + ", backward round", bwd)):
+    for name, fn in (("k_embed_round" + sfx_f + ", forward round", fwd), ("k_embed_round_bwd" + sfx_b + ", backward round", bwd)):
         for _ in range(3):
             fn()
         torch.cuda.synchronize()

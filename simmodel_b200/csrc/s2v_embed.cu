@@ -418,6 +418,13 @@ static bool use_tensor_path(int P, int flags, int num_nodes) {
     if (flags == S2V_PATH_TENSOR) return true;
     return num_nodes >= S2V_TENSOR_MIN_NODES;
 }
+// Backward round: auto picks the kernel that measures faster on B200 (profiles/): the tcgen05
+// variant needs 96 KB of tiles + 256 TMEM columns per CTA (2 CTAs of 4 warps per SM) and is
+// latency-starved at 2.09 ms per round (AMS, 4.0 M rows) against 1.82 ms for the CUDA-core kernel.
+static bool use_tensor_path_bwd_round(int P, int flags, int num_nodes) {
+    (void)num_nodes;
+    return P == 64 && flags == S2V_PATH_TENSOR;
+}
 
 template <int P>
 static int embed_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x,
@@ -476,7 +483,7 @@ static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& p
     int grid_f = s2v_persistent_grid((const void*)k_embed_final_bwd<P>, smem_f, tiles);
     int grid_r = 0;
     // rounds T..2 : du^t -> du^{t-1}
-    if (use_tensor_path(P, prm.flags, g.num_nodes)) {
+    if (use_tensor_path_bwd_round(P, prm.flags, g.num_nodes)) {
         grid_r = s2v_tc_round_backward_grid(g.num_nodes);
         for (int t = T; t >= 2; --t) {
             const float* du_t = (t == T) ? du_last : dus + (size_t)(t - 1) * plane;
@@ -608,7 +615,7 @@ extern "C" int s2v_embed_round_backward(const s2v_graph_t* g, int32_t node_dim, 
     if (!theta2_w || !du_t || !mu_prev || !du_prev || !workspace) return S2V_ERR_BAD_ARG;
     if (workspace_bytes < s2v_embed_backward_workspace_bytes(node_dim, emb_dim)) return S2V_ERR_WORKSPACE;
     if (g->num_nodes == 0) return 0;
-    if (use_tensor_path(emb_dim, flags, g->num_nodes))
+    if (use_tensor_path_bwd_round(emb_dim, flags, g->num_nodes))
         return s2v_tc_round_backward(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace,
                                      2 * emb_dim * emb_dim + 4 * emb_dim + emb_dim * node_dim, 0,
                                      s2v_tc_round_backward_grid(g->num_nodes), (cudaStream_t)stream);

@@ -325,6 +325,11 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
         tc::fence_proxy_async_smem();
         __syncthreads();
         TL3(2);
+        if (t == 0) {                            // the reduction only needs the shared-memory tiles: start it now
+            tc::tc_fence_after_sync();
+            issue_reduce(d2, s_g_hi, s_m_hi, s_m_lo);
+        }
+        __syncwarp();
         row_to_tmem(g_hi, a_tm);                 // A operand of the row transform lives in TMEM
         row_to_tmem(g_lo, a_tm + 64);
         tc::tmem_st_wait();
@@ -334,7 +339,6 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
         if (t == 0) {
             tc::tc_fence_after_sync();
             issue_transform_ts(d1, a_tm, s_b_hi, s_b_lo);
-            issue_reduce(d2, s_g_hi, s_m_hi, s_m_lo);
             tc::mma_commit(&sh->bar);
         }
         __syncwarp();                           // lanes 1-31 of warp 0 must not sleep in try_wait before lane 0 has issued
