@@ -115,21 +115,39 @@ __device__ __forceinline__ void tile_gemm(const float* As, const float* Ws, floa
     }
 }
 
-// racc[i][0..3] += sum_{r<rows} As[r][ty + RG*i] * Bs[r][4tx..4tx+3]     (P x P output)
+// racc[i][0..3] += sum_{r<rows} As[r][NRR*ty + i] * Bs[r][4tx..4tx+3]     (P x P output)
+// The thread's output rows are consecutive so that its A values are 128-bit shared-memory loads.
 template <int P>
 __device__ __forceinline__ void tile_reduce_gemm(const float* As, const float* Bs, int rows,
                                                  float (&racc)[Cfg<P>::NRR][4], int tx, int ty) {
-    constexpr int LDA = Cfg<P>::LDA, RG = Cfg<P>::RG, NRR = Cfg<P>::NRR;
+    constexpr int LDA = Cfg<P>::LDA, NRR = Cfg<P>::NRR;
+    const int n0 = NRR * ty;
+    if (n0 >= P) return;
 #pragma unroll 4
     for (int r = 0; r < rows; ++r) {
         float4 b = ld4(Bs + r * LDA + 4 * tx);
+        if constexpr (NRR % 4 == 0) {
 #pragma unroll
-        for (int i = 0; i < NRR; ++i) {
-            int n = ty + RG * i;
-            if (NRR * RG > P && n >= P) continue;
-            float a = As[r * LDA + n];
-            racc[i][0] = fmaf(a, b.x, racc[i][0]); racc[i][1] = fmaf(a, b.y, racc[i][1]);
-            racc[i][2] = fmaf(a, b.z, racc[i][2]); racc[i][3] = fmaf(a, b.w, racc[i][3]);
+            for (int i = 0; i < NRR; i += 4) {
+                float4 a = ld4(As + r * LDA + n0 + i);
+                racc[i][0] = fmaf(a.x, b.x, racc[i][0]); racc[i][1] = fmaf(a.x, b.y, racc[i][1]);
+                racc[i][2] = fmaf(a.x, b.z, racc[i][2]); racc[i][3] = fmaf(a.x, b.w, racc[i][3]);
+                racc[i + 1][0] = fmaf(a.y, b.x, racc[i + 1][0]); racc[i + 1][1] = fmaf(a.y, b.y, racc[i + 1][1]);
+                racc[i + 1][2] = fmaf(a.y, b.z, racc[i + 1][2]); racc[i + 1][3] = fmaf(a.y, b.w, racc[i + 1][3]);
+                racc[i + 2][0] = fmaf(a.z, b.x, racc[i + 2][0]); racc[i + 2][1] = fmaf(a.z, b.y, racc[i + 2][1]);
+                racc[i + 2][2] = fmaf(a.z, b.z, racc[i + 2][2]); racc[i + 2][3] = fmaf(a.z, b.w, racc[i + 2][3]);
+                racc[i + 3][0] = fmaf(a.w, b.x, racc[i + 3][0]); racc[i + 3][1] = fmaf(a.w, b.y, racc[i + 3][1]);
+                racc[i + 3][2] = fmaf(a.w, b.z, racc[i + 3][2]); racc[i + 3][3] = fmaf(a.w, b.w, racc[i + 3][3]);
+            }
+        } else {
+#pragma unroll
+            for (int i = 0; i < NRR; ++i) {
+                int n = n0 + i;
+                if (n >= P) continue;
+                float a = As[r * LDA + n];
+                racc[i][0] = fmaf(a, b.x, racc[i][0]); racc[i][1] = fmaf(a, b.y, racc[i][1]);
+                racc[i][2] = fmaf(a, b.z, racc[i][2]); racc[i][3] = fmaf(a, b.w, racc[i][3]);
+            }
         }
     }
 }
@@ -138,11 +156,11 @@ __device__ __forceinline__ void tile_reduce_gemm(const float* As, const float* B
 template <int P>
 __device__ __forceinline__ void store_racc(float* dst, const float (&racc)[Cfg<P>::NRR][4], int tx, int ty,
                                            bool active, bool accumulate) {
-    constexpr int RG = Cfg<P>::RG, NRR = Cfg<P>::NRR;
+    constexpr int NRR = Cfg<P>::NRR;
     if (!active) return;
 #pragma unroll
     for (int i = 0; i < NRR; ++i) {
-        int n = ty + RG * i;
+        int n = NRR * ty + i;
         if (n >= P) continue;
         float4 v = make_float4(racc[i][0], racc[i][1], racc[i][2], racc[i][3]);
         float* d = dst + n * P + 4 * tx;
