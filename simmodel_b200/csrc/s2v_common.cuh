@@ -290,6 +290,75 @@ __device__ __forceinline__ void gather8_consume(const Gather8Meta& m, const int3
     }
 }
 
+// Same scheme for NR (<= 8) rows per half-warp, loads issued in batches of BATCH rows x 4 neighbours.
+template <int NR>
+struct GatherMeta {
+    int b, d, off;
+    int idx[NR];
+};
+
+template <int NR>
+__device__ __forceinline__ void gatherN_prefetch(GatherMeta<NR>& m, const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
+                                                 const int32_t* __restrict__ col, int row0, int rows, int rl0) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = threadIdx.x & 15;
+    m.b = 0; m.d = 0; m.off = 0;
+    int rl = rl0 + (c % NR);
+    if (rl < rows) {
+        int r = row0 + rl, li = r;
+        if (g.period > 0) { int gi = r / g.period; m.off = gi * g.period; li = r - m.off; }
+        m.b = __ldg(rowptr + li);
+        m.d = __ldg(rowptr + li + 1) - m.b;
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        int bi = __shfl_sync(FULL, m.b, i, 16), di = __shfl_sync(FULL, m.d, i, 16);
+        m.idx[i] = c < di ? __ldg(col + bi + c) : 0;
+    }
+}
+
+template <int NR, int BATCH, class Sink>
+__device__ __forceinline__ void gatherN_consume(const GatherMeta<NR>& m, const int32_t* __restrict__ col,
+                                                const float* __restrict__ src, int rl0, Sink&& sink) {
+    static_assert(NR % BATCH == 0, "NR must be a multiple of BATCH");
+    const unsigned FULL = 0xffffffffu;
+    const int c = threadIdx.x & 15;
+    int dd[NR], oo[NR], jj[NR][4];
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        dd[i] = __shfl_sync(FULL, m.d, i, 16);
+        oo[i] = __shfl_sync(FULL, m.off, i, 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) jj[i][k] = __shfl_sync(FULL, m.idx[i], k, 16);
+    }
+    float4 acc[NR];
+#pragma unroll
+    for (int h = 0; h < NR / BATCH; ++h) {
+        float4 v[BATCH][4];
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i)
+#pragma unroll
+            for (int k = 0; k < 4; ++k)
+                v[i][k] = dd[BATCH * h + i] > k
+                              ? ldg4(src + (size_t)(oo[BATCH * h + i] + jj[BATCH * h + i][k]) * 64 + 4 * c) : f4zero();
+#pragma unroll
+        for (int i = 0; i < BATCH; ++i)
+            acc[BATCH * h + i] = f4add(f4add(f4add(f4add(f4zero(), v[i][0]), v[i][1]), v[i][2]), v[i][3]);
+    }
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        int dmax = max(dd[i], __shfl_xor_sync(FULL, dd[i], 16));
+        if (dmax > 4) {
+            int bi = __shfl_sync(FULL, m.b, i, 16);
+            for (int k = 4; k < dmax; ++k) {
+                int j = k < 16 ? __shfl_sync(FULL, m.idx[i], k, 16) : (k < dd[i] ? __ldg(col + bi + k) : 0);
+                if (k < dd[i]) acc[i] = f4add(acc[i], ldg4(src + (size_t)(oo[i] + j) * 64 + 4 * c));
+            }
+        }
+        sink(rl0 + i, acc[i]);
+    }
+}
+
 template <class Sink>
 __device__ __forceinline__ void gather8_p64(const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
                                             const int32_t* __restrict__ col, const float* __restrict__ src,

@@ -262,12 +262,31 @@ k_embed_round_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
 }
 
 // ------------------------------------------------------------------------------------
-// backward round
+// backward round, 8 warps per CTA.
+// The tile working set (96 KB of operand tiles, 256 TMEM columns) allows only two CTAs per SM, so
+// the CTA is made wider instead: every half-warp gathers 4 rows (16 neighbour loads + 4 own-row
+// loads in flight per lane, 16 warps per SM), and the TMEM copies, the epilogue and the dtheta2
+// flush are split over twice as many threads.  Warp w works on TMEM lane quarter q = w & 3 and on
+// the column half hh = w >> 2.
 // ------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(TC_THREADS)
-k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ du_t,
-                     const float* __restrict__ mu_prev, float* __restrict__ du_prev, float* __restrict__ partial,
-                     int partial_stride, int accumulate, int num_tiles) {
+constexpr int TC_THREADS2 = 256;
+
+__device__ __forceinline__ void load_weight_tiles256(uint8_t* hi_tile, uint8_t* lo_tile, const float* __restrict__ W, bool transpose) {
+    for (int e = threadIdx.x; e < 64 * 64; e += TC_THREADS2) {
+        int a = e >> 6, b = e & 63;
+        float v = __ldg(W + e);
+        int row = transpose ? b : a, col = transpose ? a : b;
+        float hi = tc::tf32_rn(v), lo = tc::tf32_rn(v - hi);
+        uint32_t off = tc::tile_off<TCR>(row, col >> 2) + (col & 3) * 4;
+        *reinterpret_cast<float*>(hi_tile + off) = hi;
+        *reinterpret_cast<float*>(lo_tile + off) = lo;
+    }
+}
+
+__global__ void __launch_bounds__(TC_THREADS2, 2)
+k_embed_round_bwd_tc256(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ du_t,
+                        const float* __restrict__ mu_prev, float* __restrict__ du_prev, float* __restrict__ partial,
+                        int partial_stride, int accumulate, int num_tiles) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* b_hi = smem;                        // theta2^T: tile(row k, col n) = theta2[n][k]
@@ -279,26 +298,28 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
     TcShared* sh = reinterpret_cast<TcShared*>(m_lo + TILE_BYTES);
     float* stg = reinterpret_cast<float*>(g_hi);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int q = warp & 3, hh = warp >> 2;
 
     if (warp == 0) tc::tmem_alloc<256>(&sh->tmem_base);
     if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
-    load_weight_tiles(b_hi, b_lo, theta2_w, true);
+    load_weight_tiles256(b_hi, b_lo, theta2_w, true);
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
     // TMEM columns: D1 [0,64)  D2 [64,128)  A_hi [128,192)  A_lo [192,256)
     const uint32_t d1 = sh->tmem_base, d2 = sh->tmem_base + 64, a_tm = sh->tmem_base + 128;
-    const uint32_t s_g_hi = tc::smem_u32(g_hi), s_b_hi = tc::smem_u32(b_hi),
-                   s_b_lo = tc::smem_u32(b_lo), s_m_hi = tc::smem_u32(m_hi), s_m_lo = tc::smem_u32(m_lo);
+    const uint32_t s_g_hi = tc::smem_u32(g_hi), s_b_hi = tc::smem_u32(b_hi), s_b_lo = tc::smem_u32(b_lo),
+                   s_m_hi = tc::smem_u32(m_hi), s_m_lo = tc::smem_u32(m_lo);
+    const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
     uint32_t phase = 0;
-    float racc[32];
+    float racc[16];
 #pragma unroll
-    for (int i = 0; i < 32; ++i) racc[i] = 0.f;
-    const int rl0 = warp * 16 + 8 * (lane >> 4);
-    Gather8Meta meta;
+    for (int i = 0; i < 16; ++i) racc[i] = 0.f;
+    const int c4 = lane & 15, rl0 = 4 * (2 * warp + (lane >> 4));
+    GatherMeta<4> meta;
     if (blockIdx.x < num_tiles)
-        gather8_prefetch(meta, g, g.rowptr_t, g.col_t, blockIdx.x * TCR, min(TCR, g.num_nodes - blockIdx.x * TCR), rl0);
+        gatherN_prefetch<4>(meta, g, g.rowptr_t, g.col_t, blockIdx.x * TCR, min(TCR, g.num_nodes - blockIdx.x * TCR), rl0);
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * TCR;
@@ -308,18 +329,17 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
 #endif
         TL3(0);
         {
-            const int c4 = lane & 15;
-            float4 m[8];
+            float4 m[4];
 #pragma unroll
-            for (int i = 0; i < 8; ++i)
+            for (int i = 0; i < 4; ++i)
                 m[i] = rl0 + i < rows ? ldg4(mu_prev + (size_t)(row0 + rl0 + i) * 64 + 4 * c4) : f4zero();
-            gather8_consume(meta, g.col_t, du_t, rl0,
-                            [&](int rl, const float4& acc) { store_split_mn(g_hi, g_lo, rl, c4, acc); });
+            gatherN_consume<4, 4>(meta, g.col_t, du_t, rl0,
+                                  [&](int rl, const float4& acc) { store_split_mn(g_hi, g_lo, rl, c4, acc); });
 #pragma unroll
-            for (int i = 0; i < 8; ++i) store_split_mn(m_hi, m_lo, rl0 + i, c4, m[i]);
-            const int nt = tile + gridDim.x;     // CSR metadata of the next tile: overlaps MMA + epilogue
+            for (int i = 0; i < 4; ++i) store_split_mn(m_hi, m_lo, rl0 + i, c4, m[i]);
+            const int nt = tile + gridDim.x;
             if (nt < num_tiles)
-                gather8_prefetch(meta, g, g.rowptr_t, g.col_t, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
+                gatherN_prefetch<4>(meta, g, g.rowptr_t, g.col_t, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
         }
         TL3(1);
         tc::fence_proxy_async_smem();
@@ -330,9 +350,21 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             issue_reduce(d2, s_g_hi, s_m_hi, s_m_lo);
         }
         __syncwarp();
-        row_to_tmem(g_hi, a_tm);                 // A operand of the row transform lives in TMEM
-        row_to_tmem(g_lo, a_tm + 64);
-        tc::tmem_st_wait();
+        {   // A operand of the row transform -> TMEM: row owner = lane < 16 of quarter q, column half hh
+            const int r = 16 * q + (lane & 15);
+            float v[32];
+#pragma unroll
+            for (int part = 0; part < 2; ++part) {
+                const uint8_t* tile_p = part ? g_lo : g_hi;
+#pragma unroll
+                for (int j = 0; j < 8; ++j) {
+                    float4 x4 = *reinterpret_cast<const float4*>(tile_p + tc::tile_off_mn<TCR>(r, 8 * hh + j));
+                    v[4 * j] = x4.x; v[4 * j + 1] = x4.y; v[4 * j + 2] = x4.z; v[4 * j + 3] = x4.w;
+                }
+                tc::tmem_st32(a_tm + 64 * part + lane_sel + 32 * hh, v);
+            }
+            tc::tmem_st_wait();
+        }
         tc::tc_fence_before_sync();
         __syncthreads();
         TL3(3);
@@ -341,40 +373,68 @@ k_embed_round_bwd_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             issue_transform_ts(d1, a_tm, s_b_hi, s_b_lo);
             tc::mma_commit(&sh->bar);
         }
-        __syncwarp();                           // lanes 1-31 of warp 0 must not sleep in try_wait before lane 0 has issued
+        __syncwarp();
         TL3(4);
         tc::mbar_wait(&sh->bar, phase);
         phase ^= 1;
         tc::tc_fence_after_sync();
         TL3(5);
-        d1_to_staging(d1, stg);                 // overwrites g tiles: all MMAs reading them have completed
+        {   // D1 -> staging (overwrites the g tiles: every MMA reading them has completed)
+            float v[32];
+            tc::tmem_ld32(d1 + lane_sel + 32 * hh, v);
+            if (lane < 16) {
+                float* dst = stg + (16 * q + lane) * STG_LD + 32 * hh;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+            }
+        }
         tc::tc_fence_before_sync();
         __syncthreads();
         TL3(6);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+        for (int i = 0; i < 4; ++i) {
+            int e = t + TC_THREADS2 * i, rl = e >> 4, cc = e & 15;
             if (rl < rows) {
-                float4 v = ld4(stg + rl * STG_LD + 4 * c4);
-                float4 m = *reinterpret_cast<const float4*>(m_hi + tc::tile_off_mn<TCR>(rl, c4));   // sign(mu) == sign(mu_hi)
-                st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * c4,
-                    make_float4(m.x > 0.f ? v.x : 0.f, m.y > 0.f ? v.y : 0.f, m.z > 0.f ? v.z : 0.f, m.w > 0.f ? v.w : 0.f));
+                float4 v = ld4(stg + rl * STG_LD + 4 * cc);
+                float4 mm = *reinterpret_cast<const float4*>(m_hi + tc::tile_off_mn<TCR>(rl, cc));   // sign(mu) == sign(mu_hi)
+                st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * cc,
+                    make_float4(mm.x > 0.f ? v.x : 0.f, mm.y > 0.f ? v.y : 0.f, mm.z > 0.f ? v.z : 0.f, mm.w > 0.f ? v.w : 0.f));
             }
         }
         TL3(7);
         __syncthreads();                        // staging is re-used as the exchange buffer
-        flush_d2(d2, stg, racc);
+        {   // dtheta2 flush: thread holds D2[32q+lane][32hh..32hh+32); rows 0-63 = hi part, 64-127 = lo part
+            // of n = 32(q&1)+lane.  The q<2 thread accumulates columns [32hh, 32hh+16), its partner (q^2)
+            // the columns [32hh+16, 32hh+32); each hands the other 16 values through the exchange buffer.
+            float v[32];
+            tc::tmem_ld32(d2 + lane_sel + 32 * hh, v);
+            const bool upper = (q >> 1) != 0;      // warp-uniform: keep columns [16,32) and give [0,16), or the reverse
+            float keep[16], give[16];
+#pragma unroll
+            for (int i = 0; i < 16; ++i) { keep[i] = upper ? v[16 + i] : v[i]; give[i] = upper ? v[i] : v[16 + i]; }
+            float* xb = stg + (size_t)(warp * 32 + lane) * 20;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) st4(xb + i, make_float4(give[i], give[i + 1], give[i + 2], give[i + 3]));
+            tc::tc_fence_before_sync();
+            __syncthreads();
+            const float* theirs = stg + (size_t)((warp ^ 2) * 32 + lane) * 20;
+#pragma unroll
+            for (int i = 0; i < 16; i += 4) {
+                float4 o = ld4(theirs + i);
+                racc[i] += keep[i] + o.x; racc[i + 1] += keep[i + 1] + o.y;
+                racc[i + 2] += keep[i + 2] + o.z; racc[i + 3] += keep[i + 3] + o.w;
+            }
+        }
         __syncthreads();                        // ... and overwritten by the next gather
         TL3(8);
     }
-    // dtheta2 partial of this CTA (EmbedPartial<64>::TH2 == 0)
     {
-        float* my = partial + (size_t)blockIdx.x * partial_stride + (32 * (warp & 1) + lane) * 64 + 32 * (warp >> 1);
+        float* my = partial + (size_t)blockIdx.x * partial_stride + (32 * (q & 1) + lane) * 64 + 32 * hh + 16 * (q >> 1);
 #pragma unroll
-        for (int i = 0; i < 32; i += 4) {
-            float4 x = make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]);
-            if (accumulate) x = f4add(ld4(my + i), x);
-            st4(my + i, x);
+        for (int i = 0; i < 16; i += 4) {
+            float4 x4 = make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]);
+            if (accumulate) x4 = f4add(ld4(my + i), x4);
+            st4(my + i, x4);
         }
     }
     tc::tc_fence_before_sync();
@@ -828,16 +888,21 @@ int s2v_tc_round_forward(const s2v_graph_t& g, const float* theta2_w, const floa
 
 int s2v_tc_round_backward_grid(int num_nodes) {
     const int tiles = (num_nodes + TCR - 1) / TCR;
-    cudaFuncSetAttribute(k_embed_round_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
-    return tc_grid((const void*)k_embed_round_bwd_tc, BWD_SMEM, 256, tiles);
+    cudaFuncSetAttribute(k_embed_round_bwd_tc256, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM);
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    int grid = 2 * sms;                          // two 8-warp CTAs per SM (96 KB of tiles, 256 TMEM columns each)
+    if (grid > S2V_MAX_GRID) grid = S2V_MAX_GRID;
+    return grid < tiles ? grid : (tiles < 1 ? 1 : tiles);
 }
 
 int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
                           float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st) {
     const int tiles = (g.num_nodes + TCR - 1) / TCR;
-    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
-    k_embed_round_bwd_tc<<<grid, TC_THREADS, BWD_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
-                                                            accumulate, tiles);
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc256, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+    k_embed_round_bwd_tc256<<<grid, TC_THREADS2, BWD_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
+                                                                accumulate, tiles);
     return (int)cudaGetLastError();
 }
 
