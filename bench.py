@@ -394,9 +394,21 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
         ach = alg_bytes / (ms / 1e3) / 1e9
         res.append({"kernel": name, "ms": ms, "algorithmic_bytes": alg_bytes, "achieved_GBps": ach, "frac": ach / peak,
                     "launches_per_step": T - 1})
+    traffic_tab = {}
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic_tab = json.load(f)
+    except Exception:
+        pass
+    for r in res:
+        key = r["kernel"].split(" ")[0].split(",")[0]
+        ent = traffic_tab.get(key)
+        r["traffic"] = ent["bytes_per_node_update"] * n if ent else None
     dom = max(res, key=lambda r: r["ms"])
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": None, "peak_source": peak_src,
+                "frac": dom["frac"], "traffic": dom["traffic"],
+                "traffic_source": "ncu --set full dram__bytes_read+write per node-update (profiles/traffic.json) x rows of this launch",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_node_update": bytes_per_node, "node_updates_per_launch": n,
                 "avg_launch_ms": dom["ms"]}
     return roofline, res

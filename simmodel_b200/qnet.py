@@ -189,6 +189,19 @@ class QFunction:
             print("Selected action:", action, "node", action_nodeselect, "value:", best_reward)
         return action, action_nodeselect, best_reward
 
+    @torch.no_grad()
+    def get_best_actions_batch(self, x, layout, reach_ptr, reach_idx):
+        """All greedy actions of a batch in ONE forward + ONE arg-max launch:
+        replaces the 32 per-experience target-network calls of comb_opt.py:580-589.
+        x f32[sum N, F], layout GraphLayout, reach_ptr i32[B+1], reach_idx i32 local node ids
+        (ascending neighbour lists).  Returns device tensors (position in list, node id, value), each [B]."""
+        was_training = self.model.training
+        self.model.eval()
+        q = self.model.forward_graph(x, layout)
+        if was_training:
+            self.model.train()
+        return ops.list_argmax(layout, q, reach_ptr, reach_idx)
+
     def batch_update(self, states_tsrs, Ws, pyg_data, actions, targets):
         """comb_opt.py:334-366."""
         dev = self.model.device

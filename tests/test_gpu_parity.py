@@ -419,6 +419,31 @@ def test_full_size_properties(path, cuda_device, monkeypatch):
         assert torch.equal(qa, qb)
 
 
+def test_batched_target_evaluation_matches_per_graph_calls(cuda_device):
+    """QFunction.get_best_actions_batch (one forward + one arg-max) == B separate get_best_action calls
+    the reference's training loop makes for the target network (comb_opt.py:580-589): bit-exact ids."""
+    import simmodel_b200 as sb
+    dev = cuda_device
+    topo = sb.graphs.load_topology("Manhattan5")
+    B, N = 6, topo.num_nodes
+    gen = torch.Generator().manual_seed(21)
+    x = sb.graphs.synth_nfm(topo, B, gen)
+    torch.manual_seed(9)
+    net = sb.QNet({"emb_dim": 64, "emb_iter_T": 5, "norm_agg": True, "node_dim": 7}, verbose=False).to(dev)
+    qf = sb.QFunction(net, None, None)
+    W = torch.zeros(N, N)
+    W[topo.edge_index[0], topo.edge_index[1]] = 1.0
+    lists = [topo.neighbors(int(torch.randint(0, N, (1,), generator=gen))) for _ in range(B)]
+    single = [qf.get_best_action(x[b], W, sb.Data(torch.ones(N), [0, 0], num_nodes=N), lists[b]) for b in range(B)]
+    rptr = torch.tensor(np.concatenate([[0], np.cumsum([len(l) for l in lists])]), dtype=torch.int32, device=dev)
+    ridx = torch.tensor(np.concatenate(lists), dtype=torch.int32, device=dev)
+    lay = sb.GraphLayout.replicated(topo.edge_index.to(dev), N, B)
+    pos, node, val = qf.get_best_actions_batch(x.reshape(-1, 7).to(dev), lay, rptr, ridx)
+    assert [int(v) for v in pos] == [s_[0] for s_ in single]
+    assert [int(v) for v in node] == [s_[1] for s_ in single]
+    assert np.array_equal(val.cpu().numpy(), np.array([s_[2] for s_ in single], dtype=np.float32))
+
+
 def test_cpu_tensors_raise(cuda_device):
     """No CPU fallback: a module left on the CPU, or CPU inputs to the native contract, must raise."""
     import simmodel_b200 as sb
