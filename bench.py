@@ -321,9 +321,16 @@ def run_b200(args):
     if rank == 0:
         roofline, kernels = measure_roofline(sb, _lib, net, layout, x, dev, B, N)
 
-    cpu_baseline = None
+    cpu_baseline, small_batch = None, None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         cpu_baseline = measure_cpu_baseline()
+        try:
+            import warnings
+            with warnings.catch_warnings():
+                warnings.simplefilter("ignore")
+                small_batch = measure_small_batch(sb, dev)
+        except Exception as exc:      # informational only
+            small_batch = {"error": str(exc)[:200]}
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -333,7 +340,7 @@ def run_b200(args):
                 "config": workload_config(B, world), "csr_build_ms": csr_ms,
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
                 "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
-                "cpu_baseline": cpu_baseline}
+                "cpu_baseline": cpu_baseline, "small_batch_latency": small_batch}
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
@@ -412,6 +419,62 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
                 "algorithmic_bytes_per_node_update": bytes_per_node, "node_updates_per_launch": n,
                 "avg_launch_ms": dom["ms"]}
     return roofline, res
+
+
+def measure_small_batch(sb, dev):
+    """The reference's own DQN call shapes (BASELINE configs[2]: batch 32 train step, B = 1 acting forward),
+    eager and replayed from a CUDA graph (host wall clock per call, device synchronised)."""
+    import torch
+    topo = sb.graphs.load_topology(TOPO)
+    N = topo.num_nodes
+    torch.manual_seed(0)
+    net = sb.QNet({"emb_dim": P, "emb_iter_T": T, "norm_agg": True, "node_dim": F}, verbose=False).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4, capturable=True)
+    loss_fn = torch.nn.SmoothL1Loss()
+
+    def wall(fn, n=100):
+        for _ in range(10):
+            fn()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(n):
+            fn()
+        torch.cuda.synchronize()
+        return (time.perf_counter() - t0) / n * 1e3
+    out = {}
+    for B in (32, 1):
+        gen = torch.Generator().manual_seed(B)
+        x = sb.graphs.synth_nfm(topo, B, gen).reshape(-1, F).to(dev)
+        lay = sb.GraphLayout.replicated(topo.edge_index.to(dev), N, B)
+        sel = (torch.randint(0, N, (B,), generator=gen) + torch.arange(B) * N).to(dev)
+        tg = torch.randn(B, generator=gen).to(dev)
+
+        def train_step():
+            opt.zero_grad(set_to_none=False)
+            loss = loss_fn(net.forward_graph(x, lay)[sel], tg)
+            loss.backward()
+            opt.step()
+            return loss
+
+        def act():
+            with torch.no_grad():
+                return net.forward_graph(x, lay)
+        res = {"train_ms_eager": wall(train_step), "forward_ms_eager": wall(act)}
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                train_step()
+        torch.cuda.current_stream().wait_stream(side)
+        g_train, g_act = torch.cuda.CUDAGraph(), torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g_train):
+            train_step()
+        with torch.cuda.graph(g_act):
+            act()
+        res["train_ms_graph"] = wall(g_train.replay)
+        res["forward_ms_graph"] = wall(g_act.replay)
+        out["B%d" % B] = res
+    return out
 
 
 def measure_cpu_baseline():

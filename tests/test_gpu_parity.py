@@ -444,6 +444,49 @@ def test_batched_target_evaluation_matches_per_graph_calls(cuda_device):
     assert np.array_equal(val.cpu().numpy(), np.array([s_[2] for s_ in single], dtype=np.float32))
 
 
+def test_cuda_graph_capture_of_a_train_step(cuda_device):
+    """The C-ABI calls never synchronise or allocate: a whole train step (forward, loss, backward, Adam)
+    captures into a CUDA graph and its replay reproduces the eager step bit for bit."""
+    import copy
+    import simmodel_b200 as sb
+    dev = cuda_device
+    topo = sb.graphs.load_topology("Manhattan5")
+    B, N = 32, topo.num_nodes
+    gen = torch.Generator().manual_seed(2)
+    x = sb.graphs.synth_nfm(topo, B, gen).reshape(-1, 7).to(dev)
+    lay = sb.GraphLayout.replicated(topo.edge_index.to(dev), N, B)
+    sel = (torch.randint(0, N, (B,), generator=gen) + torch.arange(B) * N).to(dev)
+    tg = torch.randn(B, generator=gen).to(dev)
+    torch.manual_seed(4)
+    net = sb.QNet({"emb_dim": 64, "emb_iter_T": 5, "norm_agg": True, "node_dim": 7}, verbose=False).to(dev)
+    ref = copy.deepcopy(net)
+    loss_fn = torch.nn.SmoothL1Loss()
+
+    def step(model, opt):
+        opt.zero_grad(set_to_none=False)
+        loss = loss_fn(model.forward_graph(x, lay)[sel], tg)
+        loss.backward()
+        opt.step()
+        return loss
+    opt_ref = torch.optim.Adam(ref.parameters(), lr=1e-3, capturable=True)
+    for _ in range(4):
+        step(ref, opt_ref)                       # 3 warm-up steps + 1 captured step + ... see below
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3, capturable=True)
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        for _ in range(3):
+            step(net, opt)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        step(net, opt)                           # capture only records
+    graph.replay()                               # 4th step
+    torch.cuda.synchronize()
+    for a, b in zip(net.parameters(), ref.parameters()):
+        assert torch.equal(a, b)
+
+
 def test_cpu_tensors_raise(cuda_device):
     """No CPU fallback: a module left on the CPU, or CPU inputs to the native contract, must raise."""
     import simmodel_b200 as sb
