@@ -487,6 +487,29 @@ def test_cuda_graph_capture_of_a_train_step(cuda_device):
         assert torch.equal(a, b)
 
 
+def test_host_batch_prefetcher_keeps_batches_intact(cuda_device):
+    """Double-buffered H2D staging: every acquired batch holds exactly the host data submitted under its ticket,
+    also when the host buffers are rewritten right after submit and the consumer lags behind."""
+    from simmodel_b200.pipeline import HostBatchPrefetcher
+    dev = cuda_device
+    pf = HostBatchPrefetcher(dev, depth=2)
+    host = {"x": torch.empty(1 << 20, dtype=torch.float32).pin_memory(), "i": torch.empty(1 << 18, dtype=torch.int64).pin_memory()}
+    sums = []
+    tickets = []
+    for k in range(6):
+        host["x"].fill_(float(k))
+        host["i"].fill_(k)
+        torch.cuda.synchronize()                  # a real producer would wait for its own copy before rewriting
+        tickets.append(pf.submit(host))
+        if k >= 1:                                # consume with one step of lag
+            b = pf.acquire(tickets[k - 1])
+            heavy = torch.randn(2048, 2048, device=dev) @ torch.randn(2048, 2048, device=dev)   # keep the stream busy
+            sums.append((float(b["x"].sum()), int(b["i"].sum()), float(heavy.sum() * 0)))
+            pf.release(tickets[k - 1])
+    for k, (sx, si, _) in enumerate(sums):
+        assert sx == float(k) * (1 << 20) and si == k * (1 << 18)
+
+
 def test_cpu_tensors_raise(cuda_device):
     """No CPU fallback: a module left on the CPU, or CPU inputs to the native contract, must raise."""
     import simmodel_b200 as sb
