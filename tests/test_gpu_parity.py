@@ -497,9 +497,9 @@ def test_host_batch_prefetcher_keeps_batches_intact(cuda_device):
     sums = []
     tickets = []
     for k in range(6):
+        pf.copy_stream.synchronize()              # the producer waits for its own copies before rewriting host memory
         host["x"].fill_(float(k))
         host["i"].fill_(k)
-        torch.cuda.synchronize()                  # a real producer would wait for its own copy before rewriting
         tickets.append(pf.submit(host))
         if k >= 1:                                # consume with one step of lag
             b = pf.acquire(tickets[k - 1])
