@@ -45,17 +45,24 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="graphs per GPU")
+    ap.add_argument("--topo", default="NWB_AMS", choices=["NWB_AMS", "NWB_ROT", "NWB_UTR", "Manhattan5"],
+                    help="topology of the synthetic batch (default: the N=975 graph the metric is quoted on; "
+                         "NWB_ROT = BASELINE configs[4] scale sweep)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
 
 
+TOPO_SHAPES = {"NWB_AMS": (975, 2850), "NWB_ROT": (2602, 7266), "NWB_UTR": (1182, 3204), "Manhattan5": (25, 105)}
+
+
 def workload_config(batch, n_gpus):
-    return {"workload": "s2v GNN-DQN train step on NWB_AMS (N=975, E=2850, F=7, p=64, T=5, norm_agg)",
-            "graphs_per_gpu": batch, "global_batch": batch * n_gpus, "nodes_per_graph": 975,
+    n, e = TOPO_SHAPES[TOPO]
+    return {"workload": "s2v GNN-DQN train step on %s (N=%d, E=%d, F=7, p=64, T=5, norm_agg)" % (TOPO, n, e),
+            "graphs_per_gpu": batch, "global_batch": batch * n_gpus, "nodes_per_graph": n,
             "parallelism": "dp%d" % n_gpus,
             "l2": "inputs exceed L2: per-GPU node features %.0f MB, each embedding plane %.2f GB"
-                  % (batch * 975 * F * 4 / 1e6, batch * 975 * P * 4 / 1e9)}
+                  % (batch * n * F * 4 / 1e6, batch * n * P * 4 / 1e9)}
 
 
 # --------------------------------------------------------------------------------------
@@ -135,7 +142,7 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
             "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "node_updates_per_sec": val * 975 * T,
+            "node_updates_per_sec": val * TOPO_SHAPES[TOPO][0] * T,
             "config": workload_config(args.batch, args.gpus),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": desc + "; torch %s CPU, %d threads" % (torch.__version__, cores)},
@@ -513,7 +520,11 @@ def measure_cpu_baseline():
 
 
 def main():
+    global TOPO, METRIC
     args = parse()
+    TOPO = args.topo
+    if TOPO != "NWB_AMS":
+        METRIC = "s2v_fwd_bwd_graphs_per_sec_N%d" % TOPO_SHAPES[TOPO][0]
     if args.impl == "reference":
         run_reference(args)
     else:
