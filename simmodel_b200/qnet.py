@@ -127,6 +127,8 @@ class QNet(nn.Module):
         if ei is not None:
             ei = ei.to(dev)
         else:
+            if Ws is None:
+                raise ValueError("QNet.forward needs either a dense Ws or a pyg_data with a real edge_index")
             Ws = Ws.to(dev)
             nz = Ws.nonzero()                   # (b, i, j) row-major == dense_to_sparse order
             if not bool(((Ws == 0) | (Ws == 1)).all()):
@@ -150,6 +152,36 @@ class QNet(nn.Module):
         return total
 
 
+class _EdgeListCache:
+    """edge_index of a dense 0/1 adjacency, cached on the device per W tensor object.
+
+    The reference's replay memory stores one dense padded W per transition (comb_opt.py:535-547) and re-samples
+    the same tensor objects for many updates; shipping 32 x 3.8 MB of mostly zeros per update is what the
+    caller-side contract costs.  Here a W is converted once (row-major non-zeros == dense_to_sparse order) and
+    its 2 x E int64 edge list (45.6 KB for AMS) is kept on the GPU; a hit costs nothing but a dictionary lookup."""
+
+    def __init__(self, max_entries=8192):
+        self._d = {}
+        self._max = max_entries
+
+    def get(self, W: torch.Tensor, dev) -> torch.Tensor:
+        import weakref
+        key = id(W)
+        hit = self._d.get(key)
+        if hit is not None:
+            ref, version, ei = hit
+            if ref() is W and version == W._version and ei.device == dev:
+                return ei
+        Wd = W.to(dev)
+        if not bool(((Wd == 0) | (Wd == 1)).all()):
+            raise NotImplementedError("weighted adjacency: the reference graphs carry 0/1 weights only")
+        ei = Wd.nonzero().t().contiguous()
+        if len(self._d) >= self._max:
+            self._d.clear()
+        self._d[key] = (weakref.ref(W), W._version, ei)
+        return ei
+
+
 class QFunction:
     """comb_opt.py:289-366."""
 
@@ -158,11 +190,21 @@ class QFunction:
         self.optimizer = optimizer
         self.lr_scheduler = lr_scheduler
         self.loss_fn = nn.SmoothL1Loss()
+        self._edges = _EdgeListCache()
+
+    def _batch_with_edges(self, Ws, pyg_data_list, dev):
+        """Batch.from_data_list plus a real, offset edge_index built from the cached per-graph edge lists."""
+        pyg_batch = Batch.from_data_list(pyg_data_list).to(dev)
+        if _real_edge_index(pyg_batch, int(pyg_batch.batch.numel())) is None:
+            eis = [self._edges.get(W, dev) + pyg_batch.ptr[g] for g, W in enumerate(Ws)]
+            pyg_batch.edge_index = torch.cat(eis, dim=1) if len(eis) > 1 else eis[0]
+        return pyg_batch
 
     def predict(self, state_tsr, W, pyg_data):
-        pyg_batch = Batch.from_data_list([pyg_data]).to(self.model.device)
+        dev = self.model.device
+        pyg_batch = self._batch_with_edges([W], [pyg_data], dev)
         with torch.no_grad():
-            estimated_rewards = self.model(state_tsr.unsqueeze(0), W.unsqueeze(0), pyg_batch)
+            estimated_rewards = self.model(state_tsr.unsqueeze(0), None, pyg_batch)
         if estimated_rewards.dim() == 2 and estimated_rewards.shape[0] == 1:
             return estimated_rewards[0]
         if estimated_rewards.dim() == 1:
@@ -174,7 +216,7 @@ class QFunction:
         The masked argmax runs on the GPU (s2v_list_argmax); only three scalars come back."""
         dev = self.model.device
         self.model.eval()
-        estimated_rewards = self.predict(state_tsr.to(dev), W.to(dev), pyg_data)
+        estimated_rewards = self.predict(state_tsr.to(dev), W, pyg_data)
         self.model.train()
         n = int(estimated_rewards.numel())
         layout = _single_graph_ranges(n, dev)
@@ -205,11 +247,10 @@ class QFunction:
     def batch_update(self, states_tsrs, Ws, pyg_data, actions, targets):
         """comb_opt.py:334-366."""
         dev = self.model.device
-        Ws_tsr = torch.stack(Ws).to(dev)
         xv = torch.stack(states_tsrs).to(dev)
-        pyg_batch = Batch.from_data_list(pyg_data).to(dev)
+        pyg_batch = self._batch_with_edges(Ws, pyg_data, dev)      # no dense (B,Npad,Npad) tensor is shipped
         self.optimizer.zero_grad()
-        qvals = self.model(xv, Ws_tsr, pyg_batch)
+        qvals = self.model(xv, None, pyg_batch)
         sel = torch.tensor(actions, dtype=torch.int64, device=dev) + pyg_batch.ptr[:-1]
         loss = self.loss_fn(qvals.reshape(-1)[sel], torch.tensor(targets, device=dev))
         loss_val = loss.detach().cpu().item()
