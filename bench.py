@@ -401,10 +401,10 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
     w2 = net.theta2.weight.detach()
 
     flag = _lib.path_flag()
-    tensor_f = flag == 2 or (flag == 0 and n >= 4096)        # same rule as csrc/s2v_embed.cu:use_tensor_path
-    tensor_b = flag == 2                                     # ... and use_tensor_path_bwd_round
+    tensor_f = flag in (2, 3) or (flag == 0 and n >= 4096)   # same rules as csrc/s2v_embed.cu:use_tensor_path
     sfx_f = "_tc (tcgen05 3xTF32)" if tensor_f else " (FFMA)"
-    sfx_b = "_tc (tcgen05 3xTF32)" if tensor_b else " (FFMA)"
+    sfx_b = (" (FFMA)" if not tensor_f else "_tc256 (tcgen05 3xTF32)" if flag == 2
+             else "_ws (tcgen05 bf16x3, warp-specialised)")
 
     def fwd():
         _lib.check(L.s2v_embed_round_forward(C.byref(g), P, flag, _p(w2), _p(base), _p(mu), _p(out), _stream()), "round fwd")

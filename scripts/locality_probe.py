@@ -24,7 +24,7 @@ for name, e in variants.items():
     du = torch.randn(N, 64, device=dev)
     ws = torch.empty(L.s2v_embed_backward_workspace_bytes(7, 64), dtype=torch.uint8, device=dev)
     g = lay.c_struct()
-    for flag, nm in ((1, 'ffma'), (2, 'tc')):
+    for flag, nm in ((1, 'ffma'), (2, 'tc'), (3, 'tcws')):
         def fwd(): _lib.check(L.s2v_embed_round_forward(C.byref(g), 64, flag, _p(w2), _p(base), _p(mu), _p(out), _stream()), 'f')
         def bwd(): _lib.check(L.s2v_embed_round_backward(C.byref(g), 7, 64, flag, _p(w2), _p(du), _p(mu), _p(out), _p(ws), ws.numel(), _stream()), 'b')
         res = []

@@ -317,6 +317,36 @@ __device__ __forceinline__ void gatherN_prefetch(GatherMeta<NR>& m, const s2v_gr
     }
 }
 
+// The same prefetch split in its two dependent round trips, so that a software pipeline can keep three tiles in
+// flight per lane: CSR extents of tile k+2, neighbour ids of tile k+1, neighbour rows of tile k.
+struct GatherExt { int b, d, off; };
+
+template <int NR>
+__device__ __forceinline__ void gatherN_extents(GatherExt& e, const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
+                                                int row0, int rows, int rl0) {
+    const int c = threadIdx.x & 15;
+    e.b = 0; e.d = 0; e.off = 0;
+    int rl = rl0 + (c % NR);
+    if (rl < rows) {
+        int r = row0 + rl, li = r;
+        if (g.period > 0) { int gi = r / g.period; e.off = gi * g.period; li = r - e.off; }
+        e.b = __ldg(rowptr + li);
+        e.d = __ldg(rowptr + li + 1) - e.b;
+    }
+}
+
+template <int NR>
+__device__ __forceinline__ void gatherN_ids(GatherMeta<NR>& m, const GatherExt& e, const int32_t* __restrict__ col) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = threadIdx.x & 15;
+    m.b = e.b; m.d = e.d; m.off = e.off;
+#pragma unroll
+    for (int i = 0; i < NR; ++i) {
+        int bi = __shfl_sync(FULL, e.b, i, 16), di = __shfl_sync(FULL, e.d, i, 16);
+        m.idx[i] = c < di ? __ldg(col + bi + c) : 0;
+    }
+}
+
 template <int NR, int BATCH, class Sink>
 __device__ __forceinline__ void gatherN_consume(const GatherMeta<NR>& m, const int32_t* __restrict__ col,
                                                 const float* __restrict__ src, int rl0, Sink&& sink) {
@@ -357,6 +387,98 @@ __device__ __forceinline__ void gatherN_consume(const GatherMeta<NR>& m, const i
         }
         sink(rl0 + i, acc[i]);
     }
+}
+
+// Software-pipelined form for a persistent producer warp (p = 64, 4 rows per half-warp): one call issues, in this
+// order, every warp shuffle it needs (on registers loaded by the PREVIOUS call) and then every load -- the neighbour
+// rows of tile k, the neighbour ids of tile k+1 and the CSR extents of tile k+2 -- so that no shuffle sits between
+// two loads and a single memory round trip separates two calls.  Rows of degree 5 or 6 (1 % of the NWB rows, but
+// one in two 64-row tiles contains such a row) would cost the whole tile a second, serialised round trip in
+// gatherN_consume; here the first such row of the half-warp gets its two extra neighbour loads issued with the
+// main batch.  Anything beyond (a second long row in the same 4 rows, degree > 6) takes the slow loop.
+// Summation order per row = CSR order, bit-identical to gather_row.
+struct GatherPipe4 {
+    GatherExt ext1;          // CSR extents of the rows of tile k+1 (lane c: row rl0 + c % 4)
+    GatherMeta<4> cur;       // extents + neighbour ids of tile k
+};
+
+// rows_k2(row0, rows): extent of tile k+2 (rows = 0 past the end); more_loads(): the caller's own loads of tile k,
+// issued with the batch.
+template <class NextRows, class MoreLoads>
+__device__ __forceinline__ void gather4_pipe_step(GatherPipe4& p, const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
+                                                  const int32_t* __restrict__ col, const float* __restrict__ src,
+                                                  int rl0, NextRows&& rows_k2, MoreLoads&& more_loads, float4 (&acc)[4]) {
+    const unsigned FULL = 0xffffffffu;
+    const int c = threadIdx.x & 15;
+    // ---- shuffles (registers loaded one call ago) ----
+    int dd[4], oo[4], jj[4][4], b1[4], d1[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        dd[i] = __shfl_sync(FULL, p.cur.d, i, 16);
+        oo[i] = __shfl_sync(FULL, p.cur.off, i, 16);
+#pragma unroll
+        for (int k = 0; k < 4; ++k) jj[i][k] = __shfl_sync(FULL, p.cur.idx[i], k, 16);
+        b1[i] = __shfl_sync(FULL, p.ext1.b, i, 16);
+        d1[i] = __shfl_sync(FULL, p.ext1.d, i, 16);
+    }
+    int istar = -1, dstar = 0, ostar = 0, xstar = 0;      // first row of the half-warp with more than 4 neighbours
+#pragma unroll
+    for (int i = 3; i >= 0; --i)
+        if (dd[i] > 4) { istar = i; dstar = dd[i]; ostar = oo[i]; xstar = p.cur.idx[i]; }
+    const int j4 = __shfl_sync(FULL, xstar, 4, 16), j5 = __shfl_sync(FULL, xstar, 5, 16);
+    // ---- loads ----
+    float4 v[4][4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+#pragma unroll
+        for (int k = 0; k < 4; ++k)
+            v[i][k] = dd[i] > k ? ldg4(src + (size_t)(oo[i] + jj[i][k]) * 64 + 4 * c) : f4zero();
+    const float4 e4 = dstar > 4 ? ldg4(src + (size_t)(ostar + j4) * 64 + 4 * c) : f4zero();
+    const float4 e5 = dstar > 5 ? ldg4(src + (size_t)(ostar + j5) * 64 + 4 * c) : f4zero();
+    GatherMeta<4> nxt;
+    nxt.b = p.ext1.b; nxt.d = p.ext1.d; nxt.off = p.ext1.off;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) nxt.idx[i] = c < d1[i] ? __ldg(col + b1[i] + c) : 0;
+    GatherExt ext2;
+    ext2.b = 0; ext2.d = 0; ext2.off = 0;
+    {
+        int row0, rows;
+        rows_k2(row0, rows);
+        int rl = rl0 + (c & 3);
+        if (rl < rows) {
+            int r = row0 + rl, li = r;
+            if (g.period > 0) { int gi = r / g.period; ext2.off = gi * g.period; li = r - ext2.off; }
+            ext2.b = __ldg(rowptr + li);
+            ext2.d = __ldg(rowptr + li + 1);               // end; turned into the degree below, after the data adds
+        }
+    }
+    more_loads();
+    // ---- sums (CSR order) ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        acc[i] = f4add(f4add(f4add(f4add(f4zero(), v[i][0]), v[i][1]), v[i][2]), v[i][3]);
+        if (i == istar) {                                  // acc is never -0.0, so adding the zero of an absent neighbour is exact
+            if (dstar > 4) acc[i] = f4add(acc[i], e4);
+            if (dstar > 5) acc[i] = f4add(acc[i], e5);
+        }
+    }
+    // ---- slow path: further long rows (warp-uniform control flow: the shuffles below are full-warp) ----
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+        const int k0 = i == istar ? 6 : 4;                 // first neighbour not covered above (per half-warp)
+        const int need = dd[i] > k0 ? dd[i] : 0;
+        const int dmax = max(need, __shfl_xor_sync(FULL, need, 16));
+        if (dmax > 4) {
+            const int bi = __shfl_sync(FULL, p.cur.b, i, 16);
+            for (int k = 4; k < dmax; ++k) {
+                int j = k < 16 ? __shfl_sync(FULL, p.cur.idx[i], k, 16) : (k < need ? __ldg(col + bi + k) : 0);
+                if (k >= k0 && k < need) acc[i] = f4add(acc[i], ldg4(src + (size_t)(oo[i] + j) * 64 + 4 * c));
+            }
+        }
+    }
+    ext2.d -= ext2.b;
+    p.cur = nxt;
+    p.ext1 = ext2;
 }
 
 template <class Sink>
@@ -439,6 +561,7 @@ static inline void s2v_reduce_partials(const float* partial, int stride, int n_p
 #define S2V_PATH_AUTO 0
 #define S2V_PATH_FFMA 1
 #define S2V_PATH_TENSOR 2
+#define S2V_PATH_TENSOR_WS 3    // tensor path with the warp-specialised (producer / MMA / consumer) backward round
 #define S2V_TENSOR_MIN_NODES 4096
 #ifndef S2V_TENSOR_FINAL
 #define S2V_TENSOR_FINAL 0      // tensor-core variant of the last backward stage (slower than FFMA so far)

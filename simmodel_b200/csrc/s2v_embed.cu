@@ -403,6 +403,9 @@ static int set_smem(K kernel, int bytes) {
 int s2v_tc_round_forward(const s2v_graph_t& g, const float* theta2_w, const float* base, const float* mu_prev,
                          float* mu_next, cudaStream_t st);
 int s2v_tc_round_backward_grid(int num_nodes);
+int s2v_tc_round_backward_ws_grid(int num_nodes);
+int s2v_tc_round_backward_ws(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
+                             float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st);
 int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
                           float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st);
 
@@ -412,19 +415,22 @@ int s2v_tc_final_backward_grid(int num_nodes);
 int s2v_tc_final_backward(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, const float* dus,
                           const float* du_last, float* partial, int partial_stride, int grid, cudaStream_t st);
 
-// flags (s2v_embed_params_t.flags): 0 = auto, 1 = CUDA-core FP32 path, 2 = tensor-core path
+// flags (s2v_embed_params_t.flags): 0 = auto, 1 = CUDA-core FP32 path, 2 = tensor-core path with the 8-warp
+// backward round, 3 = tensor-core path with the warp-specialised backward round (what auto picks for large batches)
 static bool use_tensor_path(int P, int flags, int num_nodes) {
     if (P != 64 || flags == S2V_PATH_FFMA) return false;
-    if (flags == S2V_PATH_TENSOR) return true;
+    if (flags >= S2V_PATH_TENSOR && flags <= S2V_PATH_TENSOR_WS) return true;
     return num_nodes >= S2V_TENSOR_MIN_NODES;
 }
-// Backward round: auto picks the kernel that measures faster on B200 (profiles/): the tcgen05
-// variant needs 96 KB of tiles + 256 TMEM columns per CTA (2 CTAs of 4 warps per SM) and is
-// latency-starved at 2.09 ms per round (AMS, 4.0 M rows) against 1.82 ms for the CUDA-core kernel.
+// Backward round.  Three implementations of the same tile math (profiles/ holds the timings, AMS, 4.0 M rows):
+//   CUDA-core FP32 (k_embed_round_bwd)                      1.73 ms   (issue / shared-memory bound)
+//   tcgen05 3xTF32, 8-warp CTAs (k_embed_round_bwd_tc256)    1.76 ms   (latency-starved: 2 CTAs per SM)
+//   tcgen05 bf16x3, warp-specialised (k_embed_round_bwd_ws)  1.39 ms   <- auto, whenever the tensor path is on
+// S2V_PATH_TENSOR forces the 8-warp kernel, S2V_PATH_TENSOR_WS the warp-specialised one.
 static bool use_tensor_path_bwd_round(int P, int flags, int num_nodes) {
-    (void)num_nodes;
-    return P == 64 && flags == S2V_PATH_TENSOR;
+    return use_tensor_path(P, flags, num_nodes);
 }
+static bool use_ws_bwd_round(int flags) { return flags != S2V_PATH_TENSOR; }
 
 template <int P>
 static int embed_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x,
@@ -484,11 +490,16 @@ static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& p
     int grid_r = 0;
     // rounds T..2 : du^t -> du^{t-1}
     if (use_tensor_path_bwd_round(P, prm.flags, g.num_nodes)) {
-        grid_r = s2v_tc_round_backward_grid(g.num_nodes);
+        const bool ws = use_ws_bwd_round(prm.flags);
+        grid_r = ws ? s2v_tc_round_backward_ws_grid(g.num_nodes) : s2v_tc_round_backward_grid(g.num_nodes);
         for (int t = T; t >= 2; --t) {
             const float* du_t = (t == T) ? du_last : dus + (size_t)(t - 1) * plane;
-            S2V_RETURN_IF(s2v_tc_round_backward(g, prm.theta2_w, du_t, mus + (size_t)(t - 2) * plane,
-                                                dus + (size_t)(t - 2) * plane, partial, stride, t != T, grid_r, st));
+            if (ws)
+                S2V_RETURN_IF(s2v_tc_round_backward_ws(g, prm.theta2_w, du_t, mus + (size_t)(t - 2) * plane,
+                                                       dus + (size_t)(t - 2) * plane, partial, stride, t != T, grid_r, st));
+            else
+                S2V_RETURN_IF(s2v_tc_round_backward(g, prm.theta2_w, du_t, mus + (size_t)(t - 2) * plane,
+                                                    dus + (size_t)(t - 2) * plane, partial, stride, t != T, grid_r, st));
         }
     } else {
         int smem_r = (C::W_FLOATS + 2 * C::TILE_FLOATS) * 4;
@@ -615,10 +626,14 @@ extern "C" int s2v_embed_round_backward(const s2v_graph_t* g, int32_t node_dim, 
     if (!theta2_w || !du_t || !mu_prev || !du_prev || !workspace) return S2V_ERR_BAD_ARG;
     if (workspace_bytes < s2v_embed_backward_workspace_bytes(node_dim, emb_dim)) return S2V_ERR_WORKSPACE;
     if (g->num_nodes == 0) return 0;
-    if (use_tensor_path_bwd_round(emb_dim, flags, g->num_nodes))
-        return s2v_tc_round_backward(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace,
-                                     2 * emb_dim * emb_dim + 4 * emb_dim + emb_dim * node_dim, 0,
+    if (use_tensor_path_bwd_round(emb_dim, flags, g->num_nodes)) {
+        const int pstride = 2 * emb_dim * emb_dim + 4 * emb_dim + emb_dim * node_dim;
+        if (use_ws_bwd_round(flags))
+            return s2v_tc_round_backward_ws(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace, pstride, 0,
+                                            s2v_tc_round_backward_ws_grid(g->num_nodes), (cudaStream_t)stream);
+        return s2v_tc_round_backward(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace, pstride, 0,
                                      s2v_tc_round_backward_grid(g->num_nodes), (cudaStream_t)stream);
+    }
     S2V_DISPATCH_P(emb_dim, return round_backward_impl<PP>(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace,
                                                            node_dim, (cudaStream_t)stream));
     return 0;

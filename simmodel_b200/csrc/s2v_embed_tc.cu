@@ -20,10 +20,14 @@
 __device__ long long g_timeline[16 * 8];
 #define TL(slot) do { if (blockIdx.x == 0 && threadIdx.x == 32 && tl_n < 8) g_timeline[tl_n * 16 + (slot)] = clock64(); } while (0)
 #define TL3(slot) do { if (blockIdx.x == 0 && threadIdx.x == 32 && tl_n >= 0 && tl_n < 8) g_timeline[tl_n * 16 + (slot)] = clock64(); } while (0)
+#define TLW(cond, k, slot) do { if (blockIdx.x == 0 && (cond) && (k) >= 4 && (k) < 12) g_timeline[((k) - 4) * 16 + (slot)] = clock64(); } while (0)
 #define TL2(slot) do { if (blockIdx.x == 0 && threadIdx.x == 32 && tl_n >= 0 && tl_n < 8) g_timeline[tl_n * 16 + (slot)] = clock64(); } while (0)
+#define TLS(cond, k, slot) do { if (blockIdx.x == 0 && (cond) && (k) % 50 == 0 && (k) / 50 < 8) g_timeline[((k) / 50) * 16 + (slot)] = clock64(); } while (0)
 #else
+#define TLS(cond, k, slot) do {} while (0)
 #define TL(slot) do {} while (0)
 #define TL2(slot) do {} while (0)
+#define TLW(cond, k, slot) do {} while (0)
 #define TL3(slot) do {} while (0)
 #endif
 
@@ -500,6 +504,10 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * TCR;
         const int rows = min(TCR, g.num_nodes - row0);
+#ifdef S2V_TC_TIMELINE
+        const int tl_n = (tile - blockIdx.x) / gridDim.x - 2;
+#endif
+        TL2(0);
         for (int e = t; e < TCR * F; e += TC_THREADS) xs[e] = e < rows * F ? __ldg(x + (size_t)row0 * F + e) : 0.f;
         if (t < TCR) {
             float c = 0.f, d = 0.f;
@@ -513,6 +521,7 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
             cw[64 + t] = d;
         }
         __syncthreads();
+        TL2(1);
         {
             float4 h[8];
             const float4 bb = ld4(b1a + 4 * c4);
@@ -531,20 +540,25 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
             for (int i = 0; i < 8; ++i)
                 store_split(a_hi, a_lo, rbase + 8 * i, c4, make_float4(relu(h[i].x), relu(h[i].y), relu(h[i].z), relu(h[i].w)));
         }
+        TL2(2);
         tc::fence_proxy_async_smem();
         __syncthreads();
+        TL2(3);
         if (t == 0) {
             tc::tc_fence_after_sync();
             issue_transform(d1, s_a_hi, s_a_lo, s_b_hi, s_b_lo);
             tc::mma_commit(&sh->bar);
         }
         __syncwarp();
+        TL2(4);
         tc::mbar_wait(&sh->bar, phase);
         phase ^= 1;
         tc::tc_fence_after_sync();
+        TL2(5);
         d1_to_staging(d1, stg);
         tc::tc_fence_before_sync();
         __syncthreads();
+        TL2(6);
         {
             const float4 c0 = ld4(cst + 4 * c4), v1 = ld4(u1 + 4 * c4), v0 = ld4(u0 + 4 * c4);
 #pragma unroll
@@ -564,7 +578,9 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
                 }
             }
         }
+        TL2(7);
         __syncthreads();
+        TL2(8);
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -845,7 +861,531 @@ k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ B
     if (warp == 0) tc::tmem_dealloc<256>(sh->tmem_base);
 }
 
+// ------------------------------------------------------------------------------------
+// bf16x3 building blocks (backward kernels): 64-row x 64-column bf16 tiles of 8 KB, three per fp32 tile.
+// ------------------------------------------------------------------------------------
+constexpr uint32_t TILE16 = TCR * 128;          // one bf16 tile
+constexpr uint32_t TILE16X3 = 3 * TILE16;
+
+// split a float4 chunk of row r into the three bf16 tiles at t1, t1 + TILE16, t1 + 2 TILE16
+__device__ __forceinline__ void store_split3(uint8_t* t1, int r, int c4, const float4& v) {
+    uint2 p1, p2, p3;
+    tc::split3(v, p1, p2, p3);
+    const uint32_t off = tc::tile_off16(r, c4);
+    *reinterpret_cast<uint2*>(t1 + off) = p1;
+    *reinterpret_cast<uint2*>(t1 + TILE16 + off) = p2;
+    *reinterpret_cast<uint2*>(t1 + 2 * TILE16 + off) = p3;
+}
+// the six (i, j) products with i + j <= 4, smallest first
+__device__ __forceinline__ void pair6(int p, int& i, int& j) {
+    const int ii[6] = {2, 0, 1, 1, 0, 0}, jj[6] = {0, 2, 1, 0, 1, 0};
+    i = ii[p]; j = jj[p];
+}
+// D[64x64] (+)= A * B^T, A rows = tile rows (K-major), B rows = output columns (K-major); 24 MMAs
+__device__ __forceinline__ void issue_transform16(uint32_t d_tmem, uint32_t a1, uint32_t b1) {
+    constexpr uint32_t idesc = tc::idesc_bf16(64, 64, 0, 0);
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        int i, j;
+        pair6(p, i, j);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            tc::mma_bf16(d_tmem, tc::desc_k16(a1 + i * TILE16, ks), tc::desc_k16(b1 + j * TILE16, ks), idesc, p > 0 || ks > 0);
+    }
+}
+// D[64x64] (+)= A^T * B over the 64 rows of the tiles (both MN-major views); 24 MMAs
+__device__ __forceinline__ void issue_reduce16(uint32_t d_tmem, uint32_t a1, uint32_t b1, bool accumulate) {
+    constexpr uint32_t idesc = tc::idesc_bf16(64, 64, 1, 1);
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        int i, j;
+        pair6(p, i, j);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            tc::mma_bf16(d_tmem, tc::desc_mn16(a1 + i * TILE16, ks, TILE16), tc::desc_mn16(b1 + j * TILE16, ks, TILE16), idesc,
+                         accumulate || p > 0 || ks > 0);
+    }
+}
+// W [64][64] row-major -> three bf16 tiles with tile(row, col) = transpose ? W[col][row] : W[row][col]
+__device__ __forceinline__ void load_weight_tiles16(uint8_t* t1, const float* __restrict__ W, bool transpose, int nthreads) {
+    for (int e = threadIdx.x; e < 64 * 16; e += nthreads) {
+        const int row = e >> 4, c4 = e & 15;
+        float4 v;
+        if (transpose) v = make_float4(__ldg(W + (4 * c4) * 64 + row), __ldg(W + (4 * c4 + 1) * 64 + row),
+                                       __ldg(W + (4 * c4 + 2) * 64 + row), __ldg(W + (4 * c4 + 3) * 64 + row));
+        else v = ldg4(W + row * 64 + 4 * c4);
+        store_split3(t1, row, c4, v);
+    }
+}
+
+// self-test: mode 6: out[rows x 64] = A * W;  mode 7: out[64 x 64] = A^T * B over the rows (per-tile accumulators
+// summed on the CUDA cores)
+__global__ void __launch_bounds__(TC_THREADS)
+k_tc_selftest16(int mode, const float* __restrict__ A, const float* __restrict__ B, float* __restrict__ out, int rows) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w1 = smem;                          // 3 tiles each
+    uint8_t* a1 = w1 + TILE16X3;
+    uint8_t* m1 = a1 + TILE16X3;
+    TcShared* sh = reinterpret_cast<TcShared*>(m1 + TILE16X3);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (warp == 0) tc::tmem_alloc<64>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    if (mode == 6) load_weight_tiles16(w1, B, true, TC_THREADS);      // tile(row n, col k) = W[k][n]
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d = sh->tmem_base;
+    uint32_t phase = 0;
+    float racc[64];
+    for (int i = 0; i < 64; ++i) racc[i] = 0.f;
+    const int num_tiles = (rows + TCR - 1) / TCR;
+    for (int tile = 0; tile < num_tiles; ++tile) {
+        const int row0 = tile * TCR, nr = min(TCR, rows - row0);
+        for (int e = t; e < TCR * 16; e += TC_THREADS) {
+            int rl = e >> 4, c4 = e & 15;
+            store_split3(a1, rl, c4, rl < nr ? ldg4(A + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero());
+            if (mode == 7) store_split3(m1, rl, c4, rl < nr ? ldg4(B + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero());
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (t == 0) {
+            tc::tc_fence_after_sync();
+            if (mode == 6) issue_transform16(d, tc::smem_u32(a1), tc::smem_u32(w1));
+            else issue_reduce16(d, tc::smem_u32(a1), tc::smem_u32(m1), false);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        float v[32];
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            tc::tmem_ld32(d + ((uint32_t)(32 * warp) << 16) + 32 * half, v);
+            if (mode == 6) {
+                if (lane < 16 && 16 * warp + lane < nr)
+                    for (int i = 0; i < 32; ++i) out[(size_t)(row0 + 16 * warp + lane) * 64 + 32 * half + i] = v[i];
+            } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) racc[32 * half + i] += v[i];
+            }
+        }
+        tc::tc_fence_before_sync();
+        __syncthreads();
+    }
+    if (mode == 7 && lane < 16)
+        for (int i = 0; i < 64; ++i) out[(16 * warp + lane) * 64 + i] = racc[i];
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(sh->tmem_base);
+}
+
+// ------------------------------------------------------------------------------------
+// backward round, warp-specialised, bf16x3: one persistent CTA of 16 warps per SM.
+//   du^{t-1} = (g theta2) * [mu^{t-1} > 0],  dtheta2 += g^T mu^{t-1},  g = gather of du^t over the transposed CSR.
+// The gathered tile is needed by two contractions -- over its columns (row transform, K-major view) and over its
+// rows (theta-gradient, MN-major view).  For 16-bit operands both views are the same SWIZZLE_128B bytes
+// (s2v_tc.cuh), so the tile is split into three bf16 tiles once and read by both; fp32 accuracy comes from the six
+// bf16 products with i + j <= 4.  A bf16 UMMA costs 65 cycles for any M <= 128, N <= 128 (scripts/tc_rate.py), so
+// the products are stacked along M and N (tile orders [x3][x1][x2] for g, [x2][x1][x3] for mu and theta2 make
+// every stack contiguous) and the stacked blocks are summed when the accumulators are read: 24 MMAs per tile.
+//   warps 0-7   P : gather into REGISTERS (software pipeline over three tiles per lane: CSR extents of k+2,
+//                   neighbour ids of k+1, rows of k), split3, store the g tiles of stage s
+//   warps 8-11  F : lane 0 of warp 8 issues the MMAs of tile k:
+//                       D1w[k&1][64 x 128]  = g1 t3 | g3 t1  +  g2 [t2|t1]  +  g1 [t2|t1]   (K-major, M = 64, N = 64/128/128)
+//                       D2x[128 x 128]    (+)= [g1;g2]^T [m2|m1]                            (MN-major, all four blocks wanted)
+//                       D2y[128 x 128]     += [g3;g1]^T [m1|m3]                             (blocks g3 m1 and g1 m3 wanted; 2^-16 of
+//                                                                                            the result: lives in TMEM for the whole kernel)
+//                   all four warps then move D1w of tile k-1 to the staging buffer (summing its two column halves)
+//                   and, after every D2_GROUP tiles, add D2x into registers (the tensor core accumulates with
+//                   truncation: chains are kept short, the long sum runs on the CUDA cores)
+//   warps 12-15 E : stream the own mu^{t-1} rows (coalesced, two tiles ahead), split3 and store the m tiles, keep the
+//                   sign bits; staging -> ReLU mask -> du^{t-1} with coalesced 128-bit stores
+// Three shared-memory stages of 48 KB, two D1w buffers.  mbarriers (s = k % 3, n = k / 3):
+//   full_g[s]    8  P -> issuer                      full_m[s]   4  E -> issuer
+//   mma_done[s]  1  tcgen05.commit -> P, E (stage s reusable: tile k-3), F (D1w[k&1] complete)
+//   d1_free[k&1] 4  F -> issuer                      d2_free     4  F -> issuer (D2x read out after a group)
+//   stg_full[k&1] 4  F -> E                          stg_empty[k&1] 4  E -> F
+// ------------------------------------------------------------------------------------
+constexpr int WS_P_WARPS = 8, WS_F_WARP0 = 8, WS_E_WARP0 = 12;
+constexpr int WS_THREADS = 512;
+constexpr int WS_STAGES = 3;
+constexpr int WS_D2_GROUP = 4;                           // tiles accumulated in TMEM between two read-outs of D2x
+constexpr uint32_t WS_STAGE_BYTES = 2 * TILE16X3;        // [g3][g1][g2][m2][m1][m3]
+constexpr int WS_STG_FLOATS = TCR * STG_LD;              // one staging buffer (two: tile parity)
+constexpr uint32_t WS_G1 = TILE16, WS_G2 = 2 * TILE16, WS_G3 = 0;           // piece offsets inside the g tiles
+constexpr uint32_t WS_X1 = TILE16, WS_X2 = 0, WS_X3 = 2 * TILE16;           // ... inside the m / theta tiles
+
+struct WsShared {
+    uint64_t full_g[WS_STAGES], full_m[WS_STAGES], mma_done[WS_STAGES];
+    uint64_t d1_free[2], stg_full[2], stg_empty[2], d2_free;
+    uint32_t tmem_base;
+    uint32_t pad;
+};
+
+__device__ __forceinline__ void store_split3_at(uint8_t* base, uint32_t o1, uint32_t o2, uint32_t o3, int r, int c4, const float4& v) {
+    uint2 p1, p2, p3;
+    tc::split3(v, p1, p2, p3);
+    const uint32_t off = tc::tile_off16(r, c4);
+    *reinterpret_cast<uint2*>(base + o1 + off) = p1;
+    *reinterpret_cast<uint2*>(base + o2 + off) = p2;
+    *reinterpret_cast<uint2*>(base + o3 + off) = p3;
+}
+
+// D1w[64 x 128] = g1 t3 | g3 t1, += g2 [t2|t1], += g1 [t2|t1]   (g = stage tiles, w = theta2^T tiles [t2][t1][t3])
+__device__ __forceinline__ void issue_ws_transform(uint32_t d1w, uint32_t g, uint32_t w) {
+    constexpr uint32_t i64 = tc::idesc_bf16(64, 64, 0, 0), i128 = tc::idesc_bf16(64, 128, 0, 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) tc::mma_bf16(d1w, tc::desc_k16(g + WS_G1, ks), tc::desc_k16(w + WS_X3, ks), i64, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) tc::mma_bf16(d1w + 64, tc::desc_k16(g + WS_G3, ks), tc::desc_k16(w + WS_X1, ks), i64, ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) tc::mma_bf16(d1w, tc::desc_k16(g + WS_G2, ks), tc::desc_k16(w, ks), i128, true);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks) tc::mma_bf16(d1w, tc::desc_k16(g + WS_G1, ks), tc::desc_k16(w, ks), i128, true);
+}
+// D2y += [g3;g1]^T [m1|m3],  D2x (+)= [g1;g2]^T [m2|m1]      (m = the stage's m tiles [m2][m1][m3])
+__device__ __forceinline__ void issue_ws_reduce(uint32_t d2x, uint32_t d2y, uint32_t g, uint32_t m, bool acc_x, bool acc_y) {
+    constexpr uint32_t idesc = tc::idesc_bf16(128, 128, 1, 1);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+        tc::mma_bf16(d2y, tc::desc_mn16(g + WS_G3, ks, TILE16), tc::desc_mn16(m + WS_X1, ks, TILE16), idesc, acc_y || ks > 0);
+#pragma unroll
+    for (int ks = 0; ks < 4; ++ks)
+        tc::mma_bf16(d2x, tc::desc_mn16(g + WS_G1, ks, TILE16), tc::desc_mn16(m + WS_X2, ks, TILE16), idesc, acc_x || ks > 0);
+}
+
+__global__ void __launch_bounds__(WS_THREADS, 1)
+k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ du_t,
+                     const float* __restrict__ mu_prev, float* __restrict__ du_prev, float* __restrict__ partial,
+                     int partial_stride, int accumulate, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w_tiles = smem;                                 // theta2^T: tile(row n, col k) = theta2[k][n], pieces [t2][t1][t3]
+    uint8_t* stage0 = w_tiles + TILE16X3;
+    float* stg0 = reinterpret_cast<float*>(stage0 + WS_STAGES * WS_STAGE_BYTES);    // 2 staging buffers
+    WsShared* sh = reinterpret_cast<WsShared*>(stg0 + 2 * WS_STG_FLOATS);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+    if (warp == WS_F_WARP0) tc::tmem_alloc<512>(&sh->tmem_base);
+    if (t == 0) {
+        for (int i = 0; i < WS_STAGES; ++i) {
+            tc::mbar_init(&sh->full_g[i], WS_P_WARPS);
+            tc::mbar_init(&sh->full_m[i], 4);
+            tc::mbar_init(&sh->mma_done[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            tc::mbar_init(&sh->d1_free[i], 4);
+            tc::mbar_init(&sh->stg_full[i], 4);
+            tc::mbar_init(&sh->stg_empty[i], 4);
+        }
+        tc::mbar_init(&sh->d2_free, 4);
+        tc::fence_barrier_init();
+    }
+    for (int e = t; e < 64 * 16; e += WS_THREADS) {          // row n of the tile = column n of theta2
+        const int n = e >> 4, c4 = e & 15;
+        float4 v = make_float4(__ldg(theta2_w + (4 * c4) * 64 + n), __ldg(theta2_w + (4 * c4 + 1) * 64 + n),
+                               __ldg(theta2_w + (4 * c4 + 2) * 64 + n), __ldg(theta2_w + (4 * c4 + 3) * 64 + n));
+        store_split3_at(w_tiles, WS_X1, WS_X2, WS_X3, n, c4, v);
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t tmem = sh->tmem_base;
+    // TMEM columns: D1w[b] at 128 b (b < 2), D2x at 256, D2y at 384
+    const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
+    auto tile_rows = [&](int k, int& row0, int& rows) {
+        row0 = (blockIdx.x + k * (int)gridDim.x) * TCR;
+        rows = min(TCR, g.num_nodes - row0);
+    };
+
+    if (warp < WS_P_WARPS) {
+        // ================================ P: gather ================================
+        const int c4 = lane & 15, rl0 = 4 * (2 * warp + (lane >> 4));
+        GatherPipe4 pipe;
+        pipe.ext1.b = pipe.ext1.d = pipe.ext1.off = 0;
+        pipe.cur.b = pipe.cur.d = pipe.cur.off = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) pipe.cur.idx[i] = 0;
+        if (my_tiles > 0) {
+            int row0, rows;
+            tile_rows(0, row0, rows);
+            gatherN_prefetch<4>(pipe.cur, g, g.rowptr_t, g.col_t, row0, rows, rl0);
+            if (my_tiles > 1) { tile_rows(1, row0, rows); gatherN_extents<4>(pipe.ext1, g, g.rowptr_t, row0, rows, rl0); }
+        }
+        int s = 0, par = 0;                                   // s = k % 3, par = (k / 3) & 1
+        for (int k = 0; k < my_tiles; ++k) {
+            uint8_t* gt = stage0 + s * WS_STAGE_BYTES;
+            float4 acc[4];
+            TLW(t == 0, k, 0);
+            TLS(t == 0, k, 11);
+            gather4_pipe_step(pipe, g, g.rowptr_t, g.col_t, du_t, rl0,
+                              [&](int& r2, int& n2) { r2 = 0; n2 = 0; if (k + 2 < my_tiles) tile_rows(k + 2, r2, n2); },
+                              [&]() {}, acc);
+            TLW(t == 0, k, 1);
+            tc::mbar_wait(&sh->mma_done[s], par ^ 1);            // the MMAs of tile k-3 have finished reading stage s
+            TLW(t == 0, k, 2);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) store_split3_at(gt, WS_G1, WS_G2, WS_G3, rl0 + i, c4, acc[i]);
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&sh->full_g[s]);
+            TLW(t == 0, k, 3);
+            if (++s == WS_STAGES) { s = 0; par ^= 1; }
+        }
+    } else if (warp < WS_E_WARP0) {
+        // ================================ F: MMA issue, D1 -> staging, dtheta2 sums ================================
+        const int q = warp & 3;                               // TMEM lane quarter this warp can access
+        const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
+        const bool issuer = warp == WS_F_WARP0;
+        const uint32_t s_w = tc::smem_u32(w_tiles);
+        const uint32_t d2x = tmem + 256, d2y = tmem + 384;
+        float racc[64];                                       // sum over the column halves of D2x row 32q + lane
+#pragma unroll
+        for (int i = 0; i < 64; ++i) racc[i] = 0.f;
+
+        auto drain = [&](int j) {                              // tile j: D1w -> staging; group end: D2x -> racc
+            const int sj = j % WS_STAGES, pj = (j / WS_STAGES) & 1, bj = j & 1;
+            float* stg = stg0 + bj * WS_STG_FLOATS;
+            tc::mbar_wait(&sh->mma_done[sj], pj);
+            tc::mbar_wait(&sh->stg_empty[bj], ((j >> 1) & 1) ^ 1);
+            tc::tc_fence_after_sync();
+            TLW(t == 32 * WS_F_WARP0, j, 6);
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {                      // M = 64 layout: lanes < 16 of quarter q own row 16q + lane
+                float va[16], vb[16];
+                tc::tmem_ld16(tmem + 128 * bj + lane_sel + 16 * c, va);
+                tc::tmem_ld16(tmem + 128 * bj + lane_sel + 64 + 16 * c, vb);
+                if (lane < 16) {
+                    float* dst = stg + (16 * q + lane) * STG_LD + 16 * c;
+#pragma unroll
+                    for (int i = 0; i < 16; i += 4)
+                        st4(dst + i, make_float4(va[i] + vb[i], va[i + 1] + vb[i + 1], va[i + 2] + vb[i + 2], va[i + 3] + vb[i + 3]));
+                }
+            }
+            tc::tc_fence_before_sync();
+            __syncwarp();
+            if (lane == 0) { tc::mbar_arrive(&sh->d1_free[bj]); tc::mbar_arrive(&sh->stg_full[bj]); }
+            if (j % WS_D2_GROUP == WS_D2_GROUP - 1 || j == my_tiles - 1) {
+#pragma unroll
+                for (int c = 0; c < 4; ++c) {
+                    float va[16], vb[16];
+                    tc::tmem_ld16(d2x + lane_sel + 16 * c, va);
+                    tc::tmem_ld16(d2x + lane_sel + 64 + 16 * c, vb);
+#pragma unroll
+                    for (int i = 0; i < 16; ++i) racc[16 * c + i] += va[i] + vb[i];
+                }
+                tc::tc_fence_before_sync();
+                __syncwarp();
+                if (lane == 0) tc::mbar_arrive(&sh->d2_free);
+            }
+            TLW(t == 32 * WS_F_WARP0, j, 7);
+        };
+
+        int s = 0, par = 0;
+        for (int k = 0; k < my_tiles; ++k) {
+            const uint32_t s_g = tc::smem_u32(stage0 + s * WS_STAGE_BYTES), s_m = s_g + TILE16X3;
+            if (issuer) {                                      // row transform first: it does not touch D2x
+                if (lane == 0) {
+                    tc::mbar_wait(&sh->full_g[s], par);
+                    tc::mbar_wait(&sh->d1_free[k & 1], ((k >> 1) & 1) ^ 1);
+                    tc::tc_fence_after_sync();
+                    TLW(true, k, 4);
+                    issue_ws_transform(tmem + 128 * (k & 1), s_g, s_w);
+                }
+                __syncwarp();                                  // the other lanes must not sleep in try_wait before lane 0 has issued
+            }
+            if (k > 0) drain(k - 1);                           // may read D2x out (group end) -> d2_free
+            if (issuer) {
+                if (lane == 0) {
+                    const int grp = k / WS_D2_GROUP;
+                    tc::mbar_wait(&sh->full_m[s], par);
+                    if (k % WS_D2_GROUP == 0) tc::mbar_wait(&sh->d2_free, (grp & 1) ^ 1);
+                    tc::tc_fence_after_sync();
+                    issue_ws_reduce(d2x, d2y, s_g, s_m, k % WS_D2_GROUP != 0, k > 0);
+                    tc::mma_commit(&sh->mma_done[s]);
+                    TLW(true, k, 5);
+                }
+                __syncwarp();
+            }
+            if (++s == WS_STAGES) { s = 0; par ^= 1; }
+        }
+        if (my_tiles > 0) {
+            drain(my_tiles - 1);
+            // D2y: rows 0-63 (g3) x columns 0-63 (m1) and rows 64-127 (g1) x columns 64-127 (m3)
+#pragma unroll
+            for (int c = 0; c < 4; ++c) {
+                float va[16];
+                tc::tmem_ld16(d2y + lane_sel + (q >= 2 ? 64 : 0) + 16 * c, va);
+#pragma unroll
+                for (int i = 0; i < 16; ++i) racc[16 * c + i] += va[i];
+            }
+        }
+        // dtheta2 partial of this CTA, row n = 32 (q & 1) + lane: warps q < 2 hold the g1 (+ g3) part, q >= 2 the g2
+        // (+ g1 m3) part.  Every MMA has completed, so stage 0 serves as the exchange buffer [64][65].
+        float* xch = reinterpret_cast<float*>(stage0) + ((q & 1) * 32 + lane) * 65;
+        if (q >= 2) {
+#pragma unroll
+            for (int i = 0; i < 64; ++i) xch[i] = racc[i];
+        }
+        tc::tc_fence_before_sync();
+        tc::named_bar_sync(2, 128);
+        if (q < 2) {
+            float* my = partial + (size_t)blockIdx.x * partial_stride + (32 * q + lane) * 64;
+#pragma unroll
+            for (int i = 0; i < 64; i += 4) {
+                float4 x4 = make_float4(racc[i] + xch[i], racc[i + 1] + xch[i + 1], racc[i + 2] + xch[i + 2], racc[i + 3] + xch[i + 3]);
+                if (accumulate) x4 = f4add(ld4(my + i), x4);
+                st4(my + i, x4);
+            }
+        }
+    } else {
+        // ================================ E: own rows, masked store ================================
+        const int et = t - 32 * WS_E_WARP0;                   // 0..127: chunk e = et + 128 i -> row e >> 4, columns 4 (e & 15)
+        uint32_t sgn_a = 0u, sgn_b = 0u, sgn_c = 0u;          // [mu > 0] bits of this thread's 8 chunks: tiles k-1, k, k+1
+        float4 m[8];
+        auto load_m = [&](int k) {
+            int row0, rows;
+            tile_rows(k, row0, rows);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int e = et + 128 * i, rl = e >> 4, cc = e & 15;
+                m[i] = rl < rows ? ldg4(mu_prev + (size_t)(row0 + rl) * 64 + 4 * cc) : f4zero();
+            }
+        };
+        auto store_m = [&](int k) -> uint32_t {                // registers -> m tiles of stage k % 3; returns the sign bits
+            const int sk = k % WS_STAGES, pk = (k / WS_STAGES) & 1;
+            uint8_t* mt = stage0 + sk * WS_STAGE_BYTES + TILE16X3;
+            tc::mbar_wait(&sh->mma_done[sk], pk ^ 1);            // stage free (tile k-3)
+            uint32_t bits = 0u;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int e = et + 128 * i;
+                store_split3_at(mt, WS_X1, WS_X2, WS_X3, e >> 4, e & 15, m[i]);
+                bits |= (m[i].x > 0.f ? 1u : 0u) << (4 * i) | (m[i].y > 0.f ? 1u : 0u) << (4 * i + 1) |
+                        (m[i].z > 0.f ? 1u : 0u) << (4 * i + 2) | (m[i].w > 0.f ? 1u : 0u) << (4 * i + 3);
+            }
+            tc::fence_proxy_async_smem();
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&sh->full_m[sk]);
+            return bits;
+        };
+        auto store_du = [&](int j, uint32_t bits) {            // staging -> ReLU mask -> du^{t-1} rows of tile j
+            const int bj = j & 1;
+            int row0, rows;
+            tile_rows(j, row0, rows);
+            const float* stg = stg0 + bj * WS_STG_FLOATS;
+            tc::mbar_wait(&sh->stg_full[bj], (j >> 1) & 1);
+            TLW(et == 0, j, 9);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                int e = et + 128 * i, rl = e >> 4, cc = e & 15;
+                if (rl < rows) {
+                    float4 v = ld4(stg + rl * STG_LD + 4 * cc);
+                    st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * cc,
+                        make_float4((bits >> (4 * i)) & 1u ? v.x : 0.f, (bits >> (4 * i + 1)) & 1u ? v.y : 0.f,
+                                    (bits >> (4 * i + 2)) & 1u ? v.z : 0.f, (bits >> (4 * i + 3)) & 1u ? v.w : 0.f));
+                }
+            }
+            __syncwarp();
+            if (lane == 0) tc::mbar_arrive(&sh->stg_empty[bj]);
+            TLW(et == 0, j, 10);
+        };
+
+        if (my_tiles > 0) {
+            load_m(0);
+            sgn_b = store_m(0);
+            if (my_tiles > 1) load_m(1);
+        }
+        for (int k = 0; k < my_tiles; ++k) {
+            if (k + 1 < my_tiles) {
+                sgn_c = store_m(k + 1);
+                TLW(et == 0, k, 8);
+                if (k + 2 < my_tiles) load_m(k + 2);            // in flight during the store below
+            }
+            if (k > 0) store_du(k - 1, sgn_a);
+            sgn_a = sgn_b;
+            sgn_b = sgn_c;
+        }
+        if (my_tiles > 0) store_du(my_tiles - 1, sgn_a);
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == WS_F_WARP0) tc::tmem_dealloc<512>(tmem);
+}
+
+// Tensor-pipe timing probe (one CTA): cycles per MMA sequence of the backward round, issued back to back by one
+// thread and waited for with one commit: out[0] = reduce (16 SS MMAs, MN-major, M = 128), out[1] = transform with A
+// from TMEM (24 MMAs, M = 64), out[2] = transform SS K-major (24 MMAs, M = 64), out[3] = both backward sequences;
+// out[4..7] = the bf16 sequences (see the loop).
+__global__ void __launch_bounds__(TC_THREADS)
+k_tc_rate(float* __restrict__ out, int reps) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    TcShared* sh = reinterpret_cast<TcShared*>(smem + 6 * TILE_BYTES);
+    const int t = threadIdx.x, warp = t >> 5;
+    for (int e = t; e < 6 * (int)TILE_BYTES / 4; e += TC_THREADS) reinterpret_cast<float*>(smem)[e] = 1.0f;
+    if (warp == 0) tc::tmem_alloc<256>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    if (t == 0) {
+        const uint32_t d1 = sh->tmem_base, d2 = d1 + 64, a_tm = d1 + 128;
+        const uint32_t b_hi = tc::smem_u32(smem), b_lo = b_hi + TILE_BYTES, g_hi = b_lo + TILE_BYTES, g_lo = g_hi + TILE_BYTES,
+                       m_hi = g_lo + TILE_BYTES, m_lo = m_hi + TILE_BYTES;
+        uint32_t phase = 0;
+        for (int mode = 0; mode < 8; ++mode) {
+            long long t0 = clock64();
+            for (int r = 0; r < reps; ++r) {
+                if (mode == 0 || mode == 3) issue_reduce(d2, g_hi, m_hi, m_lo);
+                if (mode == 1 || mode == 3) issue_transform_ts(d1, a_tm, b_hi, b_lo);
+                if (mode == 2) issue_transform(d1, g_hi, g_lo, b_hi, b_lo);
+                if (mode == 4 || mode == 6) issue_transform16(d1, g_hi, b_hi);         // 24 bf16 MMAs, K-major, M = 64
+                if (mode == 5 || mode == 6) issue_reduce16(d2, g_hi, m_hi, false);     // 24 bf16 MMAs, MN-major, M = 64
+                if (mode == 7) {                                                       // 8 bf16 MMAs, MN-major, M = 128
+                    constexpr uint32_t idesc = tc::idesc_bf16(128, 64, 1, 1);
+#pragma unroll
+                    for (int ks = 0; ks < 8; ++ks)
+                        tc::mma_bf16(d2, tc::desc_mn16(g_hi, ks & 3, TILE16), tc::desc_mn16(m_hi, ks & 3, TILE16), idesc, ks > 0);
+                }
+            }
+            tc::mma_commit(&sh->bar);
+            tc::mbar_wait(&sh->bar, phase);
+            phase ^= 1;
+            out[mode] = (float)(clock64() - t0) / reps;
+        }
+        // cycles per single bf16 MMA (K = 16) by shape: out[8 + 6*major + 3*(M==128) + {0,1,2 for N = 64,128,256}]
+        for (int major = 0; major < 2; ++major)
+            for (int mi = 0; mi < 2; ++mi)
+                for (int ni = 0; ni < 3; ++ni) {
+                    const int M = mi ? 128 : 64, N = 64 << ni;
+                    const uint32_t idesc = tc::idesc_bf16(M, N, major, major);
+                    long long t0 = clock64();
+                    for (int r = 0; r < reps; ++r)
+#pragma unroll
+                        for (int ks = 0; ks < 4; ++ks) {
+                            uint64_t da = major ? tc::desc_mn16(g_hi, ks, TILE16) : tc::desc_k16(g_hi, ks);
+                            uint64_t db = major ? tc::desc_mn16(b_hi, ks, TILE16) : tc::desc_k16(b_hi, ks);
+                            tc::mma_bf16(d1, da, db, idesc, true);
+                        }
+                    tc::mma_commit(&sh->bar);
+                    tc::mbar_wait(&sh->bar, phase);
+                    phase ^= 1;
+                    out[8 + 6 * major + 3 * mi + ni] = (float)(clock64() - t0) / (4 * reps);
+                }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<256>(sh->tmem_base);
+}
+
 constexpr int FWD_SMEM = 4 * TILE_BYTES + 64 + 1024;
+constexpr int WS_SMEM = TILE16X3 + WS_STAGES * WS_STAGE_BYTES + 2 * WS_STG_FLOATS * 4 + 256 + 1024;
 constexpr int FIRST_SMEM = 4 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 6 * 64 + 128) * 4 + 64 + 1024;
 constexpr int FIN_SMEM = 6 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 64 + 128) * 4 + 64 + 1024;
 constexpr int BWD_SMEM = 6 * TILE_BYTES + 64 + 1024;
@@ -897,6 +1437,23 @@ int s2v_tc_round_backward_grid(int num_nodes) {
     return grid < tiles ? grid : (tiles < 1 ? 1 : tiles);
 }
 
+int s2v_tc_round_backward_ws_grid(int num_nodes) {
+    const int tiles = (num_nodes + TCR - 1) / TCR;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    return sms < tiles ? sms : (tiles < 1 ? 1 : tiles);
+}
+
+int s2v_tc_round_backward_ws(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
+                             float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st) {
+    const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+    k_embed_round_bwd_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
+                                                            accumulate, tiles);
+    return (int)cudaGetLastError();
+}
+
 int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
                           float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st) {
     const int tiles = (g.num_nodes + TCR - 1) / TCR;
@@ -936,6 +1493,18 @@ int s2v_tc_final_backward(const s2v_graph_t& g, const s2v_embed_params_t& prm, c
 }
 
 extern "C" int s2v_debug_tc_gemm(int32_t mode, const float* A, const float* B, float* out, int64_t rows, void* stream) {
+    if (mode == 5) {                             // timing probe: out[0..3] = cycles per MMA sequence, rows = repetitions
+        if (!out || rows < 1) return S2V_ERR_BAD_ARG;
+        S2V_RETURN_IF(cudaFuncSetAttribute(k_tc_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        k_tc_rate<<<1, TC_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(out, (int)rows);
+        return (int)cudaGetLastError();
+    }
+    if (mode == 6 || mode == 7) {                // bf16x3 building blocks
+        if (!A || !B || !out || rows < 1) return S2V_ERR_BAD_ARG;
+        S2V_RETURN_IF(cudaFuncSetAttribute(k_tc_selftest16, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
+        k_tc_selftest16<<<1, TC_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(mode, A, B, out, (int)rows);
+        return (int)cudaGetLastError();
+    }
     if (!A || !B || !out || rows < 1 || mode < 0 || mode > 3) return S2V_ERR_BAD_ARG;
     S2V_RETURN_IF(cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     k_tc_selftest<<<1, TC_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(mode, A, B, out, (int)rows);

@@ -72,9 +72,49 @@ __device__ __forceinline__ uint64_t desc_mnmajor(uint32_t tile_saddr, int ks) {
     uint64_t d = smem_desc(tile_saddr + ks * 1024, R * 128, 512);
     return (d & ~(7ull << 61)) | (1ull << 61);
 }
+// 64-column bf16 tiles (128-byte rows, SWIZZLE_128B; see the bf16x3 notes below).  K-major view: rows = MN, k-step ks
+// covers columns 16*ks..16*ks+15.  MN-major view: columns = MN (64 per tile, further tiles at lbo_bytes), k-step ks
+// covers rows 16*ks..16*ks+15.
+__device__ __forceinline__ uint64_t desc_k16(uint32_t tile_saddr, int ks) { return smem_desc(tile_saddr + ks * 32, 16, 1024); }
+__device__ __forceinline__ uint64_t desc_mn16(uint32_t tile_saddr, int ks, uint32_t lbo_bytes) {
+    return smem_desc(tile_saddr + ks * 2048, lbo_bytes, 1024);
+}
 // Instruction descriptor, kind::tf32, fp32 accumulate (cute::UMMA::InstrDescriptor)
 __host__ __device__ constexpr uint32_t idesc_tf32(int M, int N, int a_mn_major, int b_mn_major) {
     return (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
+           ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+// ---- bf16x3 split precision (backward kernels) ---------------------------------------------
+// x = x1 + x2 + x3 with x_i bf16 (8 mantissa bits each, 24 in total); A*B ~= sum of the six products with
+// i + j <= 4 (the dropped ones are below 2^-24 relative).  For 16-bit operands the K-major and the MN-major
+// SWIZZLE_128B atoms are the SAME bytes: a row of 64 bf16 is 128 B, its eight 16-byte chunks XOR (row & 7):
+//   element (r, c):  r*128 + (((c/8) ^ (r&7)) * 16) + (c%8)*2
+// read as K-major (MN = rows, K = columns, k-step of 16 columns = +32 B, SBO = 1024 B) by a row transform and
+// as MN-major (MN = columns, K = rows, K atom = 8 rows at SBO = 1024 B, k-step of 16 rows = +2048 B, LBO = the
+// stride between stacked 64-column tiles) by a reduction over the rows -- one tile serves both contractions,
+// which 32-bit operands cannot do (their MN-major layout swizzles 32-byte granules with a 4-row period).
+__device__ __forceinline__ uint32_t pack_bf16x2(float lo, float hi) {
+    uint32_t r;
+    asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(hi), "f"(lo));
+    return r;
+}
+__device__ __forceinline__ float bf16_lo_f32(uint32_t p) { return __uint_as_float(p << 16); }
+__device__ __forceinline__ float bf16_hi_f32(uint32_t p) { return __uint_as_float(p & 0xffff0000u); }
+// four consecutive columns -> three packed groups (8 bytes each)
+__device__ __forceinline__ void split3(const float4& v, uint2& p1, uint2& p2, uint2& p3) {
+    p1.x = pack_bf16x2(v.x, v.y); p1.y = pack_bf16x2(v.z, v.w);
+    float rx = v.x - bf16_lo_f32(p1.x), ry = v.y - bf16_hi_f32(p1.x), rz = v.z - bf16_lo_f32(p1.y), rw = v.w - bf16_hi_f32(p1.y);
+    p2.x = pack_bf16x2(rx, ry); p2.y = pack_bf16x2(rz, rw);
+    rx -= bf16_lo_f32(p2.x); ry -= bf16_hi_f32(p2.x); rz -= bf16_lo_f32(p2.y); rw -= bf16_hi_f32(p2.y);
+    p3.x = pack_bf16x2(rx, ry); p3.y = pack_bf16x2(rz, rw);
+}
+// byte offset of the 8-byte group holding columns 4*c4..4*c4+3 of row r (64-column bf16 tile, 128-byte rows)
+__device__ __forceinline__ uint32_t tile_off16(int r, int c4) {
+    return (uint32_t)(r * 128 + ((((c4 >> 1) ^ (r & 7))) << 4) + ((c4 & 1) << 3));
+}
+__host__ __device__ constexpr uint32_t idesc_bf16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) |
            ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
 }
 
@@ -101,6 +141,14 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     __trap();
 }
 
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// named barrier among a subset of the CTA's warps (id 1..15; id 0 is __syncthreads)
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads) {
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
 // ---- tcgen05 ----------------------------------------------------------------------------
 __device__ __forceinline__ void fence_proxy_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before_sync() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -124,6 +172,16 @@ __device__ __forceinline__ void mma_tf32(uint32_t d_tmem, uint64_t a_desc, uint6
         "{\n\t.reg .pred p;\n\t"
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
+        : "memory");
+}
+// bf16 operands (kind::f16), fp32 accumulate
+__device__ __forceinline__ void mma_bf16(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, bool accumulate) {
+    uint32_t acc = accumulate ? 1u : 0u;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(acc)
         : "memory");
 }
@@ -164,6 +222,24 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, float (&v)[32]) {
                  : "memory");
 #pragma unroll
     for (int i = 0; i < 32; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// 32 lanes x 16 consecutive columns
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 "
+        "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;"
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15])
+                 :
+                 : "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
 }
 
 // registers -> TMEM: thread i of the warp writes lane (lane_base + i), 32 consecutive columns

@@ -369,7 +369,7 @@ def test_real_topologies_vs_sparse_oracle(topo_name, B, cuda_device):
     assert torch.equal(q_r.detach(), outs[0][0])
 
 
-@pytest.mark.parametrize("path", ["ffma", "tc"])
+@pytest.mark.parametrize("path", ["ffma", "tc", "tcws"])
 def test_full_size_properties(path, cuda_device, monkeypatch):
     """BASELINE-sized batch (AMS, B=512): size-independent properties, on both kernel paths
     (CUDA-core FP32 and tcgen05 3xTF32, forced for every size so that single graphs and the batch

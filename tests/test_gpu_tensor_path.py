@@ -21,7 +21,8 @@ def _ptr(t):
 @pytest.mark.parametrize("mode", [0, 1, 2, 3])
 def test_tc_building_blocks(mode, rows, cuda_device):
     """3xTF32 UMMA with hand-built SWIZZLE_128B tiles: A W^T, A W (K-major operands, M = 64) and
-    A^T B over the rows (MN-major operands, stacked M = 128, accumulated in TMEM across tiles)."""
+    A^T B over the rows (MN-major operands, stacked M = 128, accumulated in TMEM across tiles); mode 3 feeds A from
+    TMEM."""
     from simmodel_b200 import _lib
     L = _lib.lib()
     dev = cuda_device
@@ -40,7 +41,28 @@ def test_tc_building_blocks(mode, rows, cuda_device):
     assert err < 2e-6, (mode, rows, err, err32)
 
 
-@pytest.mark.parametrize("topo_name,B", [("NWB_AMS", 9), ("Manhattan5", 7)])
+@pytest.mark.parametrize("rows", [64, 200, 1000])
+@pytest.mark.parametrize("mode", [6, 7])
+def test_bf16x3_building_blocks(mode, rows, cuda_device):
+    """bf16x3 split-precision UMMAs (six products): A W with K-major views (mode 6) and A^T B over the rows with
+    MN-major views of the SAME tile layout (mode 7)."""
+    from simmodel_b200 import _lib
+    L = _lib.lib()
+    dev = cuda_device
+    g = torch.Generator().manual_seed(rows * 5 + mode)
+    A = (torch.randn(rows, 64, generator=g) * torch.logspace(-2, 2, 64)).to(dev)
+    B = torch.randn(64 if mode == 6 else rows, 64, generator=g).to(dev)
+    out = torch.full((rows if mode == 6 else 64, 64), float("nan"), device=dev)
+    _lib.check(L.s2v_debug_tc_gemm(mode, _ptr(A), _ptr(B), _ptr(out), rows, C.c_void_p(torch.cuda.current_stream().cuda_stream)),
+               "s2v_debug_tc_gemm")
+    torch.cuda.synchronize()
+    A64, B64 = A.double(), B.double()
+    ref = A64 @ B64 if mode == 6 else A64.t() @ B64
+    err = float((out.double() - ref).abs().max() / ref.abs().max())
+    assert err < 1e-6, (mode, rows, err)
+
+
+@pytest.mark.parametrize("topo_name,B", [("NWB_AMS", 9), ("Manhattan5", 7), ("NWB_AMS", 64)])
 def test_single_round_tc_vs_ffma(topo_name, B, cuda_device):
     import simmodel_b200 as sb
     from simmodel_b200 import _lib
@@ -58,7 +80,7 @@ def test_single_round_tc_vs_ffma(topo_name, B, cuda_device):
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     g = lay.c_struct()
     outs = {}
-    for flag in (1, 2):
+    for flag in (1, 2, 3):
         o = torch.empty(n, 64, device=dev)
         _lib.check(L.s2v_embed_round_forward(C.byref(g), 64, flag, _ptr(w2), _ptr(base), _ptr(mu), _ptr(o), st), "fwd")
         d = torch.empty(n, 64, device=dev)
@@ -69,16 +91,19 @@ def test_single_round_tc_vs_ffma(topo_name, B, cuda_device):
         stride = 2 * 64 * 64 + 4 * 64 + 64 * 7
         part = ws.view(torch.float32)[: 1024 * stride].view(1024, stride)[:, : 64 * 64].sum(0)
         outs[flag] = (o, d, part)
-    for a, b, name in zip(outs[1], outs[2], ("mu_next", "du_prev", "dtheta2")):
-        err = float((a - b).abs().max() / a.abs().max())
-        assert err < 3e-6, (name, err)
-    # exact zero pattern of the ReLU mask must agree
-    assert torch.equal(outs[1][1] == 0, outs[2][1] == 0)
+    for flag in (2, 3):                      # 2: 8-warp CTAs (3xTF32), 3: warp-specialised pipeline (bf16x3)
+        for a, b, name in zip(outs[1], outs[flag], ("mu_next", "du_prev", "dtheta2")):
+            err = float((a - b).abs().max() / a.abs().max())
+            assert err < 3e-6, (flag, name, err)
+        # exact zero pattern of the ReLU mask must agree
+        assert torch.equal(outs[1][1] == 0, outs[flag][1] == 0)
 
 
-def test_parity_suite_with_tensor_path_forced(cuda_device):
-    """Every p = 64 parity case again with the tcgen05 kernels forced on for all sizes."""
-    env = dict(os.environ, S2V_B200_PATH="tc")
+@pytest.mark.parametrize("path", ["tc", "tcws"])
+def test_parity_suite_with_tensor_path_forced(path, cuda_device):
+    """Every p = 64 parity case again with the tcgen05 kernels forced on for all sizes (tc: 8-warp 3xTF32 backward
+    round, tcws: warp-specialised bf16x3 backward round -- the one auto picks for large batches)."""
+    env = dict(os.environ, S2V_B200_PATH=path)
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu",
                           "-q", "-x", "--tb=short", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
                          timeout=900, cwd=ROOT)
