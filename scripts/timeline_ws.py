@@ -15,7 +15,7 @@ for _ in range(3):
     assert L.s2v_embed_round_backward(C.byref(g), 7, 64, FLAG, _p(w2), _p(du), _p(mu), _p(out), _p(ws), ws.numel(), _stream()) == 0
 torch.cuda.synchronize()
 buf = (C.c_longlong * 128)(); assert L.s2v_debug_timeline(buf) == 0
-T = np.array(list(buf)).reshape(8, 16); t = T[:, :12]
+T = np.array(list(buf)).reshape(8, 16); t = T[:, :12]; X = T - T[0, 0]
 print('P0 of tiles 0,50,..,350 (CTA 0): cycles per tile over each 50-tile span', np.diff(T[:, 11]) / 50)
 t0 = t[0, 0]
 print('flag', FLAG, 'slots: P0 gather issue, P1 gathered, P2 stage free, P3 full_g arrive | I4 operands ready, I5 committed | F6 drain start, F7 drain end | E8 m stored, E9 staging ready, E10 du stored')
@@ -23,3 +23,7 @@ for k, row in enumerate(t[:6]):
     print('k=%d ' % (k + 4) + ' '.join('%7d' % (v - t0) for v in row[:11]))
 print('P: period', np.diff(t[:6, 0]), ' gather', (t[:6, 1] - t[:6, 0]), ' stage wait', (t[:6, 2] - t[:6, 1]), ' store', (t[:6, 3] - t[:6, 2]))
 print('I: issue', (t[:6, 5] - t[:6, 4]), ' F: drain', (t[:6, 7] - t[:6, 6]), ' | E: du store', (t[:6, 10] - t[:6, 9]))
+print('issuer warp, per loop iteration k (tile k issue, tile k-1 drain):')
+for k in range(1, 6):
+    print('  k=%d: operands ready %6d | transform issued +%5d | mma_done(k-1) +%5d | staging free +%5d | drained +%5d | full_m/d2_free ok +%5d | reduce issued, committed +%5d | next operands ready +%5d'
+          % (k + 4, X[k, 4], X[k, 12] - X[k, 4], X[k - 1, 13] - X[k, 12], X[k - 1, 6] - X[k - 1, 13], X[k - 1, 7] - X[k - 1, 6], X[k, 14] - X[k - 1, 7], X[k, 5] - X[k, 14], X[k + 1, 4] - X[k, 5] if k < 5 else 0))

@@ -13,6 +13,7 @@
 //                            (both MN-major views of the same tiles; K = the 64 rows of the
 //                             tile; rows 0-63 of D2 + rows 64-127 of D2 = dtheta2 partial,
 //                             kept in TMEM across all tiles of the CTA)
+#include <cstdlib>
 #include "s2v_common.cuh"
 #include "s2v_tc.cuh"
 
@@ -219,7 +220,7 @@ k_embed_round_tc(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
         tc::fence_proxy_async_smem();
         __syncthreads();
         TL(2);
-        if (t == 0) {
+        if (warp == 0) {
             tc::tc_fence_after_sync();
             issue_transform(d1, s_a_hi, s_a_lo, s_b_hi, s_b_lo);
             tc::mma_commit(&sh->bar);
@@ -349,7 +350,7 @@ k_embed_round_bwd_tc256(s2v_graph_t g, const float* __restrict__ theta2_w, const
         tc::fence_proxy_async_smem();
         __syncthreads();
         TL3(2);
-        if (t == 0) {                            // the reduction only needs the shared-memory tiles: start it now
+        if (warp == 0) {                            // the reduction only needs the shared-memory tiles: start it now
             tc::tc_fence_after_sync();
             issue_reduce(d2, s_g_hi, s_m_hi, s_m_lo);
         }
@@ -372,7 +373,7 @@ k_embed_round_bwd_tc256(s2v_graph_t g, const float* __restrict__ theta2_w, const
         tc::tc_fence_before_sync();
         __syncthreads();
         TL3(3);
-        if (t == 0) {
+        if (warp == 0) {
             tc::tc_fence_after_sync();
             issue_transform_ts(d1, a_tm, s_b_hi, s_b_lo);
             tc::mma_commit(&sh->bar);
@@ -544,7 +545,7 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
         tc::fence_proxy_async_smem();
         __syncthreads();
         TL2(3);
-        if (t == 0) {
+        if (warp == 0) {
             tc::tc_fence_after_sync();
             issue_transform(d1, s_a_hi, s_a_lo, s_b_hi, s_b_lo);
             tc::mma_commit(&sh->bar);
@@ -706,7 +707,7 @@ k_embed_final_bwd_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restr
         tc::tc_fence_before_sync();
         __syncthreads();
         TL2(3);
-        if (t == 0) {
+        if (warp == 0) {
             tc::tc_fence_after_sync();
             issue_transform_ts(d1, a_tm, s_b_hi, s_b_lo);
             issue_reduce(d2, s_d_hi, s_h_hi, s_h_lo);
@@ -828,7 +829,7 @@ k_tc_selftest(int mode, const float* __restrict__ A, const float* __restrict__ B
             tc::tc_fence_before_sync();
             __syncthreads();
         }
-        if (t == 0) {
+        if (warp == 0) {
             tc::tc_fence_after_sync();
             if (mode < 2) issue_transform(d1, tc::smem_u32(a_hi), tc::smem_u32(a_lo), tc::smem_u32(b_hi), tc::smem_u32(b_lo));
             else if (mode == 2) issue_reduce(d2, tc::smem_u32(a_hi), tc::smem_u32(m_hi), tc::smem_u32(m_lo));
@@ -950,7 +951,7 @@ k_tc_selftest16(int mode, const float* __restrict__ A, const float* __restrict__
         }
         tc::fence_proxy_async_smem();
         __syncthreads();
-        if (t == 0) {
+        if (warp == 0) {
             tc::tc_fence_after_sync();
             if (mode == 6) issue_transform16(d, tc::smem_u32(a1), tc::smem_u32(w1));
             else issue_reduce16(d, tc::smem_u32(a1), tc::smem_u32(m1), false);
@@ -1003,6 +1004,11 @@ k_tc_selftest16(int mode, const float* __restrict__ A, const float* __restrict__
 //                   truncation: chains are kept short, the long sum runs on the CUDA cores)
 //   warps 12-15 E : stream the own mu^{t-1} rows (coalesced, two tiles ahead), split3 and store the m tiles, keep the
 //                   sign bits; staging -> ReLU mask -> du^{t-1} with coalesced 128-bit stores
+// Variants measured and dropped (AMS, 4.0 M rows; this kernel: 1.31 ms): producers that keep the rows of tile k+1
+// in flight while storing tile k (setmaxnreg 152/128/80): 1.40 ms; queueing both MMA groups of a tile before the
+// previous tile is drained: 1.44 ms; compile-time stage indices (descriptor = base + immediate): 1.47 ms.  With
+// the MMAs, the shared-memory stores and the global stores switched off one at a time (-DS2V_WS_EXPERIMENTS,
+// scripts/ws_experiments.py) the gather alone runs in 0.81 ms; MMAs add 0.34 ms, tile stores 0.27 ms.
 // Three shared-memory stages of 48 KB, two D1w buffers.  mbarriers (s = k % 3, n = k / 3):
 //   full_g[s]    8  P -> issuer                      full_m[s]   4  E -> issuer
 //   mma_done[s]  1  tcgen05.commit -> P, E (stage s reusable: tile k-3), F (D1w[k&1] complete)
@@ -1034,7 +1040,9 @@ __device__ __forceinline__ void store_split3_at(uint8_t* base, uint32_t o1, uint
     *reinterpret_cast<uint2*>(base + o3 + off) = p3;
 }
 
-// D1w[64 x 128] = g1 t3 | g3 t1, += g2 [t2|t1], += g1 [t2|t1]   (g = stage tiles, w = theta2^T tiles [t2][t1][t3])
+// D1w[64 x 128] = g1 t3 | g3 t1, += g2 [t2|t1], += g1 [t2|t1]   (g = stage tiles, w = theta2^T tiles [t2][t1][t3]).
+// (Compile-time stage indices with base + immediate descriptors were tried: fewer instructions per MMA, but the
+// six-way dispatch measured 12 % slower end to end.)
 __device__ __forceinline__ void issue_ws_transform(uint32_t d1w, uint32_t g, uint32_t w) {
     constexpr uint32_t i64 = tc::idesc_bf16(64, 64, 0, 0), i128 = tc::idesc_bf16(64, 128, 0, 0);
 #pragma unroll
@@ -1068,6 +1076,13 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
     float* stg0 = reinterpret_cast<float*>(stage0 + WS_STAGES * WS_STAGE_BYTES);    // 2 staging buffers
     WsShared* sh = reinterpret_cast<WsShared*>(stg0 + 2 * WS_STG_FLOATS);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+#ifdef S2V_WS_EXPERIMENTS
+    const int xf = accumulate >> 8;             // timing experiments: bit i switches one piece of work off (results are garbage)
+    accumulate &= 1;
+#define WS_X(bit) (xf & (1 << (bit)))
+#else
+#define WS_X(bit) 0
+#endif
 
     if (warp == WS_F_WARP0) tc::tmem_alloc<512>(&sh->tmem_base);
     if (t == 0) {
@@ -1094,7 +1109,10 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
-    const uint32_t tmem = sh->tmem_base;
+    // The CTA owns all 512 TMEM columns, so the allocation starts at lane 0, column 0: the constant keeps the MMA
+    // operands in uniform registers.
+    if (sh->tmem_base != 0) __trap();
+    constexpr uint32_t tmem = 0;
     // TMEM columns: D1w[b] at 128 b (b < 2), D2x at 256, D2y at 384
     const int my_tiles = blockIdx.x < num_tiles ? (num_tiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
     auto tile_rows = [&](int k, int& row0, int& rows) {
@@ -1129,7 +1147,8 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             tc::mbar_wait(&sh->mma_done[s], par ^ 1);            // the MMAs of tile k-3 have finished reading stage s
             TLW(t == 0, k, 2);
 #pragma unroll
-            for (int i = 0; i < 4; ++i) store_split3_at(gt, WS_G1, WS_G2, WS_G3, rl0 + i, c4, acc[i]);
+            for (int i = 0; i < 4; ++i)
+                if (!WS_X(3)) store_split3_at(gt, WS_G1, WS_G2, WS_G3, rl0 + i, c4, acc[i]);
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh->full_g[s]);
@@ -1151,6 +1170,7 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             const int sj = j % WS_STAGES, pj = (j / WS_STAGES) & 1, bj = j & 1;
             float* stg = stg0 + bj * WS_STG_FLOATS;
             tc::mbar_wait(&sh->mma_done[sj], pj);
+            TLW(t == 32 * WS_F_WARP0, j, 13);
             tc::mbar_wait(&sh->stg_empty[bj], ((j >> 1) & 1) ^ 1);
             tc::tc_fence_after_sync();
             TLW(t == 32 * WS_F_WARP0, j, 6);
@@ -1159,7 +1179,7 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
                 float va[16], vb[16];
                 tc::tmem_ld16(tmem + 128 * bj + lane_sel + 16 * c, va);
                 tc::tmem_ld16(tmem + 128 * bj + lane_sel + 64 + 16 * c, vb);
-                if (lane < 16) {
+                if (lane < 16 && !WS_X(5)) {
                     float* dst = stg + (16 * q + lane) * STG_LD + 16 * c;
 #pragma unroll
                     for (int i = 0; i < 16; i += 4)
@@ -1188,28 +1208,24 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
         int s = 0, par = 0;
         for (int k = 0; k < my_tiles; ++k) {
             const uint32_t s_g = tc::smem_u32(stage0 + s * WS_STAGE_BYTES), s_m = s_g + TILE16X3;
-            if (issuer) {                                      // row transform first: it does not touch D2x
-                if (lane == 0) {
-                    tc::mbar_wait(&sh->full_g[s], par);
-                    tc::mbar_wait(&sh->d1_free[k & 1], ((k >> 1) & 1) ^ 1);
-                    tc::tc_fence_after_sync();
-                    TLW(true, k, 4);
-                    issue_ws_transform(tmem + 128 * (k & 1), s_g, s_w);
-                }
-                __syncwarp();                                  // the other lanes must not sleep in try_wait before lane 0 has issued
+            if (issuer) {                                      // whole warp (uniform operands), one elected lane issues;
+                tc::mbar_wait(&sh->full_g[s], par);            // row transform first: it does not touch D2x
+                tc::mbar_wait(&sh->d1_free[k & 1], ((k >> 1) & 1) ^ 1);
+                tc::tc_fence_after_sync();
+                TLW(lane == 0, k, 4);
+                if (!WS_X(1)) issue_ws_transform(128 * (k & 1), s_g, s_w);
+                TLW(lane == 0, k, 12);
             }
-            if (k > 0) drain(k - 1);                           // may read D2x out (group end) -> d2_free
+            if (k > 0) drain(k - 1);                           // reads D2x out at a group end -> d2_free
             if (issuer) {
-                if (lane == 0) {
-                    const int grp = k / WS_D2_GROUP;
-                    tc::mbar_wait(&sh->full_m[s], par);
-                    if (k % WS_D2_GROUP == 0) tc::mbar_wait(&sh->d2_free, (grp & 1) ^ 1);
-                    tc::tc_fence_after_sync();
-                    issue_ws_reduce(d2x, d2y, s_g, s_m, k % WS_D2_GROUP != 0, k > 0);
-                    tc::mma_commit(&sh->mma_done[s]);
-                    TLW(true, k, 5);
-                }
-                __syncwarp();
+                const int grp = k / WS_D2_GROUP;
+                tc::mbar_wait(&sh->full_m[s], par);
+                if (k % WS_D2_GROUP == 0) tc::mbar_wait(&sh->d2_free, (grp & 1) ^ 1);
+                tc::tc_fence_after_sync();
+                TLW(lane == 0, k, 14);
+                if (!WS_X(0)) issue_ws_reduce(256, 384, s_g, s_m, k % WS_D2_GROUP != 0, k > 0);
+                tc::mma_commit(&sh->mma_done[s]);
+                TLW(lane == 0, k, 5);
             }
             if (++s == WS_STAGES) { s = 0; par ^= 1; }
         }
@@ -1264,7 +1280,7 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 int e = et + 128 * i;
-                store_split3_at(mt, WS_X1, WS_X2, WS_X3, e >> 4, e & 15, m[i]);
+                if (!WS_X(4)) store_split3_at(mt, WS_X1, WS_X2, WS_X3, e >> 4, e & 15, m[i]);
                 bits |= (m[i].x > 0.f ? 1u : 0u) << (4 * i) | (m[i].y > 0.f ? 1u : 0u) << (4 * i + 1) |
                         (m[i].z > 0.f ? 1u : 0u) << (4 * i + 2) | (m[i].w > 0.f ? 1u : 0u) << (4 * i + 3);
             }
@@ -1283,7 +1299,7 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 int e = et + 128 * i, rl = e >> 4, cc = e & 15;
-                if (rl < rows) {
+                if (rl < rows && !WS_X(2)) {
                     float4 v = ld4(stg + rl * STG_LD + 4 * cc);
                     st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * cc,
                         make_float4((bits >> (4 * i)) & 1u ? v.x : 0.f, (bits >> (4 * i + 1)) & 1u ? v.y : 0.f,
@@ -1334,7 +1350,7 @@ k_tc_rate(float* __restrict__ out, int reps) {
     tc::tc_fence_before_sync();
     __syncthreads();
     tc::tc_fence_after_sync();
-    if (t == 0) {
+    if (warp == 0) {                             // warp-collective issue (s2v_tc.cuh)
         const uint32_t d1 = sh->tmem_base, d2 = d1 + 64, a_tm = d1 + 128;
         const uint32_t b_hi = tc::smem_u32(smem), b_lo = b_hi + TILE_BYTES, g_hi = b_lo + TILE_BYTES, g_lo = g_hi + TILE_BYTES,
                        m_hi = g_lo + TILE_BYTES, m_lo = m_hi + TILE_BYTES;
@@ -1357,7 +1373,7 @@ k_tc_rate(float* __restrict__ out, int reps) {
             tc::mma_commit(&sh->bar);
             tc::mbar_wait(&sh->bar, phase);
             phase ^= 1;
-            out[mode] = (float)(clock64() - t0) / reps;
+            if (t == 0) out[mode] = (float)(clock64() - t0) / reps;
         }
         // cycles per single bf16 MMA (K = 16) by shape: out[8 + 6*major + 3*(M==128) + {0,1,2 for N = 64,128,256}]
         for (int major = 0; major < 2; ++major)
@@ -1376,7 +1392,7 @@ k_tc_rate(float* __restrict__ out, int reps) {
                     tc::mma_commit(&sh->bar);
                     tc::mbar_wait(&sh->bar, phase);
                     phase ^= 1;
-                    out[8 + 6 * major + 3 * mi + ni] = (float)(clock64() - t0) / (4 * reps);
+                    if (t == 0) out[8 + 6 * major + 3 * mi + ni] = (float)(clock64() - t0) / (4 * reps);
                 }
     }
     tc::tc_fence_before_sync();
@@ -1449,6 +1465,9 @@ int s2v_tc_round_backward_ws(const s2v_graph_t& g, const float* theta2_w, const 
                              float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st) {
     const int tiles = (g.num_nodes + TCR - 1) / TCR;
     S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+#ifdef S2V_WS_EXPERIMENTS
+    if (const char* e = getenv("S2V_WS_EXP")) accumulate |= atoi(e) << 8;
+#endif
     k_embed_round_bwd_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
                                                             accumulate, tiles);
     return (int)cudaGetLastError();
