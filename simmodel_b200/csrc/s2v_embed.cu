@@ -408,6 +408,9 @@ int s2v_tc_round_backward_ws(const s2v_graph_t& g, const float* theta2_w, const 
                              float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st);
 int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
                           float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st);
+bool s2v_tc_final_backward_ws_ok(int node_dim);
+int s2v_tc_final_backward_ws(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, const float* dus,
+                             const float* du_last, float* partial, int partial_stride, int grid, cudaStream_t st);
 
 int s2v_tc_embed_first(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, float* base, float* mu1,
                        cudaStream_t st);
@@ -512,7 +515,10 @@ static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& p
                                                                       t != T, tiles);
         }
     }
-    if (S2V_TENSOR_FINAL && use_tensor_path(P, prm.flags, g.num_nodes)) {
+    if (use_tensor_path(P, prm.flags, g.num_nodes) && use_ws_bwd_round(prm.flags) && s2v_tc_final_backward_ws_ok(prm.node_dim)) {
+        grid_f = s2v_tc_round_backward_ws_grid(g.num_nodes);
+        S2V_RETURN_IF(s2v_tc_final_backward_ws(g, prm, x, dus, du_last, partial, stride, grid_f, st));
+    } else if (S2V_TENSOR_FINAL && use_tensor_path(P, prm.flags, g.num_nodes)) {
         grid_f = s2v_tc_final_backward_grid(g.num_nodes);
         S2V_RETURN_IF(s2v_tc_final_backward(g, prm, x, dus, du_last, partial, stride, grid_f, st));
     } else {

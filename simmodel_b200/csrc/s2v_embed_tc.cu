@@ -1065,17 +1065,46 @@ __device__ __forceinline__ void issue_ws_reduce(uint32_t d2x, uint32_t d2y, uint
         tc::mma_bf16(d2x, tc::desc_mn16(g + WS_G1, ks, TILE16), tc::desc_mn16(m + WS_X2, ks, TILE16), idesc, acc_x || ks > 0);
 }
 
+// The same pipeline runs the LAST backward stage (FINAL = true; math of k_embed_final_bwd, s2v_embed.cu):
+//   D = sum_t du^t ;  dtheta1b += D^T h ;  dh = (D theta1b) * [h > 0] ;  dtheta1a += dh^T x ;  column sums of D, c D,
+//   (Npad - c) D, dh.
+// D takes the place of g (P streams and sums the T planes instead of gathering), h = relu(theta1a x + b1a) the place
+// of mu (E recomputes it from the x tile), theta1b the place of theta2; instead of storing dh, E reduces it against x.
+struct WsArgs {
+    const float* w;          // theta2 | theta1b  [64][64]
+    const float* src;        // du^t (gathered) | du^1..du^{T-1} planes
+    const float* own;        // mu^{t-1}        | du^T (last plane)
+    float* dst;              // du^{t-1}        | unused
+    const float* x;          // FINAL: node features [n][F]
+    const float* th1a_w;     // FINAL: theta1a [64][F]
+    const float* th1a_b;     // FINAL: [64]
+    int F, T;                // FINAL: node_dim (<= WS_MAX_F), rounds
+    float* partial;          // per-CTA partial sums (EmbedPartial<64> layout, s2v_embed.cu)
+    int partial_stride, accumulate, num_tiles;
+};
+constexpr int WS_MAX_F = 8;
+constexpr int WS_EP_TH1B = 64 * 64, WS_EP_COLD = 2 * 64 * 64, WS_EP_A1 = WS_EP_COLD + 64, WS_EP_A0 = WS_EP_A1 + 64,
+              WS_EP_B1A = WS_EP_A0 + 64, WS_EP_TH1A = WS_EP_B1A + 64;
+
+template <bool FINAL>
 __global__ void __launch_bounds__(WS_THREADS, 1)
-k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ du_t,
-                     const float* __restrict__ mu_prev, float* __restrict__ du_prev, float* __restrict__ partial,
-                     int partial_stride, int accumulate, int num_tiles) {
+k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-    uint8_t* w_tiles = smem;                                 // theta2^T: tile(row n, col k) = theta2[k][n], pieces [t2][t1][t3]
+    uint8_t* w_tiles = smem;                                 // W^T: tile(row n, col k) = W[k][n], pieces [t2][t1][t3]
     uint8_t* stage0 = w_tiles + TILE16X3;
     float* stg0 = reinterpret_cast<float*>(stage0 + WS_STAGES * WS_STAGE_BYTES);    // 2 staging buffers
-    WsShared* sh = reinterpret_cast<WsShared*>(stg0 + 2 * WS_STG_FLOATS);
+    float* xs0 = stg0 + 2 * WS_STG_FLOATS;                   // FINAL: 3 x tiles [64][F]
+    float* pscr = xs0 + 3 * TCR * WS_MAX_F;                  // FINAL: [16][64] reduction scratch of the producers
+    WsShared* sh = reinterpret_cast<WsShared*>(pscr + 16 * 64);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const float* __restrict__ theta2_w = a.w;
+    const float* __restrict__ du_t = a.src;
+    const float* __restrict__ mu_prev = a.own;
+    float* __restrict__ du_prev = a.dst;
+    float* __restrict__ partial = a.partial;
+    const int partial_stride = a.partial_stride, num_tiles = a.num_tiles;
+    int accumulate = a.accumulate;
 #ifdef S2V_WS_EXPERIMENTS
     const int xf = accumulate >> 8;             // timing experiments: bit i switches one piece of work off (results are garbage)
     accumulate &= 1;
@@ -1121,28 +1150,69 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
     };
 
     if (warp < WS_P_WARPS) {
-        // ================================ P: gather ================================
+        // ================================ P: gather (FINAL: sum of the T planes) ================================
         const int c4 = lane & 15, rl0 = 4 * (2 * warp + (lane >> 4));
         GatherPipe4 pipe;
         pipe.ext1.b = pipe.ext1.d = pipe.ext1.off = 0;
         pipe.cur.b = pipe.cur.d = pipe.cur.off = 0;
 #pragma unroll
         for (int i = 0; i < 4; ++i) pipe.cur.idx[i] = 0;
-        if (my_tiles > 0) {
+        if (!FINAL && my_tiles > 0) {
             int row0, rows;
             tile_rows(0, row0, rows);
             gatherN_prefetch<4>(pipe.cur, g, g.rowptr_t, g.col_t, row0, rows, rl0);
             if (my_tiles > 1) { tile_rows(1, row0, rows); gatherN_extents<4>(pipe.ext1, g, g.rowptr_t, row0, rows, rl0); }
         }
+        float4 pD = f4zero(), pA1 = f4zero(), pA0 = f4zero();  // FINAL: column sums of D, c D, (Npad - c) D over this lane's rows
         int s = 0, par = 0;                                   // s = k % 3, par = (k / 3) & 1
         for (int k = 0; k < my_tiles; ++k) {
             uint8_t* gt = stage0 + s * WS_STAGE_BYTES;
             float4 acc[4];
             TLW(t == 0, k, 0);
             TLS(t == 0, k, 11);
-            gather4_pipe_step(pipe, g, g.rowptr_t, g.col_t, du_t, rl0,
-                              [&](int& r2, int& n2) { r2 = 0; n2 = 0; if (k + 2 < my_tiles) tile_rows(k + 2, r2, n2); },
-                              [&]() {}, acc);
+            if constexpr (!FINAL) {
+                gather4_pipe_step(pipe, g, g.rowptr_t, g.col_t, du_t, rl0,
+                                  [&](int& r2, int& n2) { r2 = 0; n2 = 0; if (k + 2 < my_tiles) tile_rows(k + 2, r2, n2); },
+                                  [&]() {}, acc);
+            } else {
+                int row0, rows;
+                tile_rows(k, row0, rows);
+                const size_t plane = (size_t)g.num_nodes * 64;
+                float cf[4], df[4];
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    cf[i] = 0.f; df[i] = 0.f; acc[i] = f4zero();
+                    if (rl0 + i < rows) {
+                        int li, off, gi;
+                        row_info(g, row0 + rl0 + i, li, off, gi);
+                        cf[i] = (float)__ldg(g.indeg + li);
+                        df[i] = (float)graph_npad(g, gi) - cf[i];
+                    }
+                }
+                for (int p0 = 0; p0 < a.T; p0 += 5) {          // fixed summation order t = 1..T, 20 loads in flight per lane
+                    float4 v[4][5];
+#pragma unroll
+                    for (int j = 0; j < 5; ++j) {
+                        const int pl = p0 + j;
+                        const float* base = pl < a.T - 1 ? a.src + (size_t)pl * plane : a.own;
+#pragma unroll
+                        for (int i = 0; i < 4; ++i)
+                            v[i][j] = (pl < a.T && rl0 + i < rows) ? ldg4(base + (size_t)(row0 + rl0 + i) * 64 + 4 * c4) : f4zero();
+                    }
+#pragma unroll
+                    for (int j = 0; j < 5; ++j)
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) acc[i] = f4add(acc[i], v[i][j]);
+                }
+#pragma unroll
+                for (int i = 0; i < 4; ++i) {
+                    pD = f4add(pD, acc[i]);
+                    pA1.x = fmaf(cf[i], acc[i].x, pA1.x); pA1.y = fmaf(cf[i], acc[i].y, pA1.y);
+                    pA1.z = fmaf(cf[i], acc[i].z, pA1.z); pA1.w = fmaf(cf[i], acc[i].w, pA1.w);
+                    pA0.x = fmaf(df[i], acc[i].x, pA0.x); pA0.y = fmaf(df[i], acc[i].y, pA0.y);
+                    pA0.z = fmaf(df[i], acc[i].z, pA0.z); pA0.w = fmaf(df[i], acc[i].w, pA0.w);
+                }
+            }
             TLW(t == 0, k, 1);
             tc::mbar_wait(&sh->mma_done[s], par ^ 1);            // the MMAs of tile k-3 have finished reading stage s
             TLW(t == 0, k, 2);
@@ -1154,6 +1224,23 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             if (lane == 0) tc::mbar_arrive(&sh->full_g[s]);
             TLW(t == 0, k, 3);
             if (++s == WS_STAGES) { s = 0; par ^= 1; }
+        }
+        if constexpr (FINAL) {                                 // column sums over the 16 half-warps, fixed order
+            float* my = partial + (size_t)blockIdx.x * partial_stride;
+            const int hw = t >> 4;                             // 0..15
+            const float4 vals[3] = {pD, pA1, pA0};
+            const int offs[3] = {WS_EP_COLD, WS_EP_A1, WS_EP_A0};
+#pragma unroll
+            for (int q3 = 0; q3 < 3; ++q3) {
+                st4(pscr + hw * 64 + 4 * c4, vals[q3]);
+                tc::named_bar_sync(3, 32 * WS_P_WARPS);
+                if (t < 64) {
+                    float sum = 0.f;
+                    for (int h2 = 0; h2 < 16; ++h2) sum += pscr[h2 * 64 + t];
+                    my[offs[q3] + t] = sum;
+                }
+                tc::named_bar_sync(3, 32 * WS_P_WARPS);
+            }
         }
     } else if (warp < WS_E_WARP0) {
         // ================================ F: MMA issue, D1 -> staging, dtheta2 sums ================================
@@ -1250,7 +1337,7 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
         tc::tc_fence_before_sync();
         tc::named_bar_sync(2, 128);
         if (q < 2) {
-            float* my = partial + (size_t)blockIdx.x * partial_stride + (32 * q + lane) * 64;
+            float* my = partial + (size_t)blockIdx.x * partial_stride + (FINAL ? WS_EP_TH1B : 0) + (32 * q + lane) * 64;
 #pragma unroll
             for (int i = 0; i < 64; i += 4) {
                 float4 x4 = make_float4(racc[i] + xch[i], racc[i + 1] + xch[i + 1], racc[i + 2] + xch[i + 2], racc[i + 3] + xch[i + 3]);
@@ -1259,41 +1346,85 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             }
         }
     } else {
-        // ================================ E: own rows, masked store ================================
+        // ================================ E: own rows (FINAL: h tile), epilogue ================================
         const int et = t - 32 * WS_E_WARP0;                   // 0..127: chunk e = et + 128 i -> row e >> 4, columns 4 (e & 15)
         uint32_t sgn_a = 0u, sgn_b = 0u, sgn_c = 0u;          // [mu > 0] bits of this thread's 8 chunks: tiles k-1, k, k+1
         float4 m[8];
+        // FINAL: theta1a columns 4cc..4cc+3 of this thread, its partial sums of dh and dh x^T, the x values it stages
+        const int F = FINAL ? a.F : 0;
+        float4 w1a[WS_MAX_F], b1a4 = f4zero(), pB1a = f4zero(), pth1a[WS_MAX_F];
+        float xr[4] = {0.f, 0.f, 0.f, 0.f};
+        if constexpr (FINAL) {
+            const int cc = et & 15;
+#pragma unroll
+            for (int f = 0; f < WS_MAX_F; ++f) {
+                pth1a[f] = f4zero();
+                w1a[f] = f < F ? make_float4(__ldg(a.th1a_w + (4 * cc) * F + f), __ldg(a.th1a_w + (4 * cc + 1) * F + f),
+                                             __ldg(a.th1a_w + (4 * cc + 2) * F + f), __ldg(a.th1a_w + (4 * cc + 3) * F + f))
+                               : f4zero();
+            }
+            b1a4 = ldg4(a.th1a_b + 4 * cc);
+        }
         auto load_m = [&](int k) {
             int row0, rows;
             tile_rows(k, row0, rows);
+            if constexpr (FINAL) {                             // the tile's x values are rows * F consecutive floats
 #pragma unroll
-            for (int i = 0; i < 8; ++i) {
-                int e = et + 128 * i, rl = e >> 4, cc = e & 15;
-                m[i] = rl < rows ? ldg4(mu_prev + (size_t)(row0 + rl) * 64 + 4 * cc) : f4zero();
+                for (int j = 0; j < 4; ++j) xr[j] = 4 * et + j < rows * F ? __ldg(a.x + (size_t)row0 * F + 4 * et + j) : 0.f;
+            } else {
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    int e = et + 128 * i, rl = e >> 4, cc = e & 15;
+                    m[i] = rl < rows ? ldg4(mu_prev + (size_t)(row0 + rl) * 64 + 4 * cc) : f4zero();
+                }
             }
         };
         auto store_m = [&](int k) -> uint32_t {                // registers -> m tiles of stage k % 3; returns the sign bits
             const int sk = k % WS_STAGES, pk = (k / WS_STAGES) & 1;
             uint8_t* mt = stage0 + sk * WS_STAGE_BYTES + TILE16X3;
+            const float* xs = xs0 + sk * TCR * WS_MAX_F;
+            if constexpr (FINAL) {                             // x tile -> shared memory
+                float* xw = xs0 + sk * TCR * WS_MAX_F;
+                tc::named_bar_sync(1, 128);                    // every E thread is done with the x tile of k-3
+#pragma unroll
+                for (int j = 0; j < 4; ++j) xw[4 * et + j] = xr[j];
+                tc::named_bar_sync(1, 128);
+            }
             tc::mbar_wait(&sh->mma_done[sk], pk ^ 1);            // stage free (tile k-3)
             uint32_t bits = 0u;
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                int e = et + 128 * i;
-                if (!WS_X(4)) store_split3_at(mt, WS_X1, WS_X2, WS_X3, e >> 4, e & 15, m[i]);
-                bits |= (m[i].x > 0.f ? 1u : 0u) << (4 * i) | (m[i].y > 0.f ? 1u : 0u) << (4 * i + 1) |
-                        (m[i].z > 0.f ? 1u : 0u) << (4 * i + 2) | (m[i].w > 0.f ? 1u : 0u) << (4 * i + 3);
+                const int e = et + 128 * i;
+                float4 val;
+                if constexpr (FINAL) {                         // h = relu(theta1a x + b1a), chunk by chunk
+                    const int rl = e >> 4;
+                    float4 h = b1a4;
+#pragma unroll
+                    for (int f = 0; f < WS_MAX_F; ++f)
+                        if (f < F) {
+                            const float xv = xs[rl * F + f];
+                            h.x = fmaf(xv, w1a[f].x, h.x); h.y = fmaf(xv, w1a[f].y, h.y);
+                            h.z = fmaf(xv, w1a[f].z, h.z); h.w = fmaf(xv, w1a[f].w, h.w);
+                        }
+                    val = make_float4(relu(h.x), relu(h.y), relu(h.z), relu(h.w));
+                } else {
+                    val = m[i];
+                }
+                if (!WS_X(4)) store_split3_at(mt, WS_X1, WS_X2, WS_X3, e >> 4, e & 15, val);
+                bits |= (val.x > 0.f ? 1u : 0u) << (4 * i) | (val.y > 0.f ? 1u : 0u) << (4 * i + 1) |
+                        (val.z > 0.f ? 1u : 0u) << (4 * i + 2) | (val.w > 0.f ? 1u : 0u) << (4 * i + 3);
             }
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh->full_m[sk]);
             return bits;
         };
-        auto store_du = [&](int j, uint32_t bits) {            // staging -> ReLU mask -> du^{t-1} rows of tile j
+        auto store_du = [&](int j, uint32_t bits) {            // staging -> ReLU mask -> du^{t-1} rows of tile j (FINAL: reduce dh)
             const int bj = j & 1;
             int row0, rows;
             tile_rows(j, row0, rows);
             const float* stg = stg0 + bj * WS_STG_FLOATS;
+            const float* xs = xs0 + (j % WS_STAGES) * TCR * WS_MAX_F;
             tc::mbar_wait(&sh->stg_full[bj], (j >> 1) & 1);
             TLW(et == 0, j, 9);
 #pragma unroll
@@ -1301,9 +1432,20 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
                 int e = et + 128 * i, rl = e >> 4, cc = e & 15;
                 if (rl < rows && !WS_X(2)) {
                     float4 v = ld4(stg + rl * STG_LD + 4 * cc);
-                    st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * cc,
-                        make_float4((bits >> (4 * i)) & 1u ? v.x : 0.f, (bits >> (4 * i + 1)) & 1u ? v.y : 0.f,
-                                    (bits >> (4 * i + 2)) & 1u ? v.z : 0.f, (bits >> (4 * i + 3)) & 1u ? v.w : 0.f));
+                    v = make_float4((bits >> (4 * i)) & 1u ? v.x : 0.f, (bits >> (4 * i + 1)) & 1u ? v.y : 0.f,
+                                    (bits >> (4 * i + 2)) & 1u ? v.z : 0.f, (bits >> (4 * i + 3)) & 1u ? v.w : 0.f);
+                    if constexpr (FINAL) {
+                        pB1a = f4add(pB1a, v);
+#pragma unroll
+                        for (int f = 0; f < WS_MAX_F; ++f)
+                            if (f < F) {
+                                const float xv = xs[rl * F + f];
+                                pth1a[f].x = fmaf(v.x, xv, pth1a[f].x); pth1a[f].y = fmaf(v.y, xv, pth1a[f].y);
+                                pth1a[f].z = fmaf(v.z, xv, pth1a[f].z); pth1a[f].w = fmaf(v.w, xv, pth1a[f].w);
+                            }
+                    } else {
+                        st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * cc, v);
+                    }
                 }
             }
             __syncwarp();
@@ -1327,6 +1469,25 @@ k_embed_round_bwd_ws(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             sgn_b = sgn_c;
         }
         if (my_tiles > 0) store_du(my_tiles - 1, sgn_a);
+        if constexpr (FINAL) {                                 // sum_i dh_i and sum_i dh_i x_i^T over the 8 row groups, fixed order
+            float* my = partial + (size_t)blockIdx.x * partial_stride;
+            float* scr = xs0;                                  // [8][64]
+            const int cc = et & 15, rg = et >> 4;
+            for (int f = -1; f < F; ++f) {
+                float4 val = pB1a;
+#pragma unroll
+                for (int ff = 0; ff < WS_MAX_F; ++ff) if (ff == f) val = pth1a[ff];
+                tc::named_bar_sync(1, 128);
+                st4(scr + rg * 64 + 4 * cc, val);
+                tc::named_bar_sync(1, 128);
+                if (et < 64) {
+                    float sum = 0.f;
+                    for (int r8 = 0; r8 < 8; ++r8) sum += scr[r8 * 64 + et];
+                    if (f < 0) my[WS_EP_B1A + et] = sum;
+                    else my[WS_EP_TH1A + et * F + f] = sum;
+                }
+            }
+        }
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -1401,7 +1562,7 @@ k_tc_rate(float* __restrict__ out, int reps) {
 }
 
 constexpr int FWD_SMEM = 4 * TILE_BYTES + 64 + 1024;
-constexpr int WS_SMEM = TILE16X3 + WS_STAGES * WS_STAGE_BYTES + 2 * WS_STG_FLOATS * 4 + 256 + 1024;
+constexpr int WS_SMEM = TILE16X3 + WS_STAGES * WS_STAGE_BYTES + 2 * WS_STG_FLOATS * 4 + (3 * TCR * WS_MAX_F + 16 * 64) * 4 + 256 + 1024;
 constexpr int FIRST_SMEM = 4 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 6 * 64 + 128) * 4 + 64 + 1024;
 constexpr int FIN_SMEM = 6 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 64 + 128) * 4 + 64 + 1024;
 constexpr int BWD_SMEM = 6 * TILE_BYTES + 64 + 1024;
@@ -1463,13 +1624,29 @@ int s2v_tc_round_backward_ws_grid(int num_nodes) {
 
 int s2v_tc_round_backward_ws(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
                              float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st) {
-    const int tiles = (g.num_nodes + TCR - 1) / TCR;
-    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_ws, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+    WsArgs a{};
+    a.w = theta2_w; a.src = du_t; a.own = mu_prev; a.dst = du_prev;
+    a.partial = partial; a.partial_stride = partial_stride; a.accumulate = accumulate;
+    a.num_tiles = (g.num_nodes + TCR - 1) / TCR;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_bwd_ws<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
 #ifdef S2V_WS_EXPERIMENTS
-    if (const char* e = getenv("S2V_WS_EXP")) accumulate |= atoi(e) << 8;
+    if (const char* e = getenv("S2V_WS_EXP")) a.accumulate |= atoi(e) << 8;
 #endif
-    k_embed_round_bwd_ws<<<grid, WS_THREADS, WS_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
-                                                            accumulate, tiles);
+    k_embed_bwd_ws<false><<<grid, WS_THREADS, WS_SMEM, st>>>(g, a);
+    return (int)cudaGetLastError();
+}
+
+// Last backward stage on the same pipeline (node_dim <= WS_MAX_F); partial rows [0, grid) receive TH1B .. TH1A.
+bool s2v_tc_final_backward_ws_ok(int node_dim) { return node_dim <= WS_MAX_F; }
+int s2v_tc_final_backward_ws(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, const float* dus,
+                             const float* du_last, float* partial, int partial_stride, int grid, cudaStream_t st) {
+    WsArgs a{};
+    a.w = prm.theta1b_w; a.src = dus; a.own = du_last; a.dst = nullptr;
+    a.x = x; a.th1a_w = prm.theta1a_w; a.th1a_b = prm.theta1a_b; a.F = prm.node_dim; a.T = prm.rounds;
+    a.partial = partial; a.partial_stride = partial_stride; a.accumulate = 0;
+    a.num_tiles = (g.num_nodes + TCR - 1) / TCR;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_bwd_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+    k_embed_bwd_ws<true><<<grid, WS_THREADS, WS_SMEM, st>>>(g, a);
     return (int)cudaGetLastError();
 }
 
