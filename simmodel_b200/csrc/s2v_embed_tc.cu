@@ -1353,9 +1353,13 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
         // FINAL: theta1a columns 4cc..4cc+3 of this thread, its partial sums of dh and dh x^T, the x values it stages
         const int F = FINAL ? a.F : 0;
         float4 w1a[WS_MAX_F], b1a4 = f4zero(), pB1a = f4zero(), pth1a[WS_MAX_F];
-        float xr[4] = {0.f, 0.f, 0.f, 0.f};
+        float xr[WS_MAX_F];                                   // FINAL: thread et < 64 stages row et of the x tile
+#pragma unroll
+        for (int f = 0; f < WS_MAX_F; ++f) xr[f] = 0.f;
         if constexpr (FINAL) {
             const int cc = et & 15;
+            for (int e = et; e < 3 * TCR * WS_MAX_F; e += 128) xs0[e] = 0.f;   // rows are padded to WS_MAX_F floats; the pads stay zero
+            tc::named_bar_sync(1, 128);
 #pragma unroll
             for (int f = 0; f < WS_MAX_F; ++f) {
                 pth1a[f] = f4zero();
@@ -1368,9 +1372,10 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
         auto load_m = [&](int k) {
             int row0, rows;
             tile_rows(k, row0, rows);
-            if constexpr (FINAL) {                             // the tile's x values are rows * F consecutive floats
+            if constexpr (FINAL) {
 #pragma unroll
-                for (int j = 0; j < 4; ++j) xr[j] = 4 * et + j < rows * F ? __ldg(a.x + (size_t)row0 * F + 4 * et + j) : 0.f;
+                for (int f = 0; f < WS_MAX_F; ++f)
+                    xr[f] = (et < rows && f < F) ? __ldg(a.x + (size_t)(row0 + et) * F + f) : 0.f;
             } else {
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
@@ -1386,8 +1391,10 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
             if constexpr (FINAL) {                             // x tile -> shared memory
                 float* xw = xs0 + sk * TCR * WS_MAX_F;
                 tc::named_bar_sync(1, 128);                    // every E thread is done with the x tile of k-3
-#pragma unroll
-                for (int j = 0; j < 4; ++j) xw[4 * et + j] = xr[j];
+                if (et < TCR) {
+                    st4(xw + et * WS_MAX_F, make_float4(xr[0], xr[1], xr[2], xr[3]));
+                    st4(xw + et * WS_MAX_F + 4, make_float4(xr[4], xr[5], xr[6], xr[7]));
+                }
                 tc::named_bar_sync(1, 128);
             }
             tc::mbar_wait(&sh->mma_done[sk], pk ^ 1);            // stage free (tile k-3)
@@ -1398,14 +1405,14 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
                 float4 val;
                 if constexpr (FINAL) {                         // h = relu(theta1a x + b1a), chunk by chunk
                     const int rl = e >> 4;
+                    const float4 xa = ld4(xs + rl * WS_MAX_F), xb = ld4(xs + rl * WS_MAX_F + 4);
+                    const float xv[WS_MAX_F] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
                     float4 h = b1a4;
 #pragma unroll
-                    for (int f = 0; f < WS_MAX_F; ++f)
-                        if (f < F) {
-                            const float xv = xs[rl * F + f];
-                            h.x = fmaf(xv, w1a[f].x, h.x); h.y = fmaf(xv, w1a[f].y, h.y);
-                            h.z = fmaf(xv, w1a[f].z, h.z); h.w = fmaf(xv, w1a[f].w, h.w);
-                        }
+                    for (int f = 0; f < WS_MAX_F; ++f) {       // theta1a columns past F are zero
+                        h.x = fmaf(xv[f], w1a[f].x, h.x); h.y = fmaf(xv[f], w1a[f].y, h.y);
+                        h.z = fmaf(xv[f], w1a[f].z, h.z); h.w = fmaf(xv[f], w1a[f].w, h.w);
+                    }
                     val = make_float4(relu(h.x), relu(h.y), relu(h.z), relu(h.w));
                 } else {
                     val = m[i];
@@ -1436,13 +1443,13 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
                                     (bits >> (4 * i + 2)) & 1u ? v.z : 0.f, (bits >> (4 * i + 3)) & 1u ? v.w : 0.f);
                     if constexpr (FINAL) {
                         pB1a = f4add(pB1a, v);
+                        const float4 xa = ld4(xs + rl * WS_MAX_F), xb = ld4(xs + rl * WS_MAX_F + 4);
+                        const float xv[WS_MAX_F] = {xa.x, xa.y, xa.z, xa.w, xb.x, xb.y, xb.z, xb.w};
 #pragma unroll
-                        for (int f = 0; f < WS_MAX_F; ++f)
-                            if (f < F) {
-                                const float xv = xs[rl * F + f];
-                                pth1a[f].x = fmaf(v.x, xv, pth1a[f].x); pth1a[f].y = fmaf(v.y, xv, pth1a[f].y);
-                                pth1a[f].z = fmaf(v.z, xv, pth1a[f].z); pth1a[f].w = fmaf(v.w, xv, pth1a[f].w);
-                            }
+                        for (int f = 0; f < WS_MAX_F; ++f) {   // x columns past F are zero
+                            pth1a[f].x = fmaf(v.x, xv[f], pth1a[f].x); pth1a[f].y = fmaf(v.y, xv[f], pth1a[f].y);
+                            pth1a[f].z = fmaf(v.z, xv[f], pth1a[f].z); pth1a[f].w = fmaf(v.w, xv[f], pth1a[f].w);
+                        }
                     } else {
                         st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * cc, v);
                     }
@@ -1646,6 +1653,9 @@ int s2v_tc_final_backward_ws(const s2v_graph_t& g, const s2v_embed_params_t& prm
     a.partial = partial; a.partial_stride = partial_stride; a.accumulate = 0;
     a.num_tiles = (g.num_nodes + TCR - 1) / TCR;
     S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_bwd_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+#ifdef S2V_WS_EXPERIMENTS
+    if (const char* e = getenv("S2V_WS_EXP_FINAL")) a.accumulate |= atoi(e) << 8;
+#endif
     k_embed_bwd_ws<true><<<grid, WS_THREADS, WS_SMEM, st>>>(g, a);
     return (int)cudaGetLastError();
 }
