@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2V_ABI_VERSION 1
+#define S2V_ABI_VERSION 2
 
 #define S2V_ERR_BAD_ARG        (-1)  /* null pointer / negative size / inconsistent sizes     */
 #define S2V_ERR_UNSUPPORTED    (-2)  /* emb_dim not in {8,16,24,32,48,64}, node_dim > 32 */
@@ -97,6 +97,8 @@ typedef struct s2v_head_params {
     const float* theta6_b;
     const float* theta7_w;    /* [p,p]  */
     const float* theta7_b;
+    int32_t flags;            /* kernel path, as s2v_embed_params_t.flags (ABI 2)            */
+    int32_t reserved;
 } s2v_head_params_t;
 
 int         s2v_abi_version(void);

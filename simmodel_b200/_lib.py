@@ -32,7 +32,7 @@ class EmbedParams(C.Structure):
 class HeadParams(C.Structure):
     _fields_ = [("emb_dim", i32), ("norm_agg", i32),
                 ("theta5_w", vp), ("theta5_b", vp), ("theta6_w", vp), ("theta6_b", vp),
-                ("theta7_w", vp), ("theta7_b", vp)]
+                ("theta7_w", vp), ("theta7_b", vp), ("flags", i32), ("reserved", i32)]
 
 
 GP, EP, HP = C.POINTER(Graph), C.POINTER(EmbedParams), C.POINTER(HeadParams)
@@ -86,7 +86,7 @@ def lib():
                     fn = getattr(handle, name)
                     fn.restype = res
                     fn.argtypes = args
-                if handle.s2v_abi_version() != 1:
+                if handle.s2v_abi_version() != 2:
                     raise S2VError("simmodel_b200: ABI version mismatch")
                 _lib = handle
     return _lib

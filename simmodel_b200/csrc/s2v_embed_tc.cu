@@ -474,7 +474,8 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
     if (warp == 0) tc::tmem_alloc<64>(&sh->tmem_base);
     if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
     load_weight_tiles(b_hi, b_lo, prm.theta1b_w, false);
-    for (int e = t; e < 64 * F; e += TC_THREADS) { int n = e / F, f = e - n * F; W1a[f * 64 + n] = __ldg(prm.theta1a_w + e); }
+    const int FS = (F + 3) & ~3;                 // x rows and theta1a are padded to a multiple of four features (zeros)
+    for (int e = t; e < 64 * FS; e += TC_THREADS) { int f = e >> 6, n = e & 63; W1a[e] = f < F ? __ldg(prm.theta1a_w + n * F + f) : 0.f; }
     if (t < 64) {
         b1a[t] = __ldg(prm.theta1a_b + t);
         float w4 = __ldg(prm.theta4_w + t), b4 = __ldg(prm.theta4_b + t);
@@ -502,6 +503,24 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
     uint32_t phase = 0;
     const int c4 = t & 15, rbase = t >> 4;       // this thread's chunks: rows rbase + 8*i, columns 4*c4..4*c4+3
 
+    float xr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cn = 0.f, dn = 0.f;
+    auto prefetch = [&](int tl) {                // row t of tile tl: features (F <= 8), in-degree, Npad - in-degree
+        const int r = tl * TCR + t;
+        cn = 0.f; dn = 0.f;
+#pragma unroll
+        for (int f = 0; f < 8; ++f) xr[f] = 0.f;
+        if (r < g.num_nodes) {
+            int li, off, gi;
+            row_info(g, r, li, off, gi);
+            cn = (float)__ldg(g.indeg + li);
+            dn = (float)graph_npad(g, gi) - cn;
+            if (F <= 8) {
+#pragma unroll
+                for (int f = 0; f < 8; ++f) if (f < F) xr[f] = __ldg(x + (size_t)r * F + f);
+            }
+        }
+    };
+    if (t < TCR && blockIdx.x < num_tiles) prefetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * TCR;
         const int rows = min(TCR, g.num_nodes - row0);
@@ -509,17 +528,18 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
         const int tl_n = (tile - blockIdx.x) / gridDim.x - 2;
 #endif
         TL2(0);
-        for (int e = t; e < TCR * F; e += TC_THREADS) xs[e] = e < rows * F ? __ldg(x + (size_t)row0 * F + e) : 0.f;
+        // thread t < 64 stages row t: x (padded to FS floats), in-degree c and Npad - c; for F <= 8 the values were
+        // loaded one tile ahead
         if (t < TCR) {
-            float c = 0.f, d = 0.f;
-            if (t < rows) {
-                int li, off, gi;
-                row_info(g, row0 + t, li, off, gi);
-                c = (float)__ldg(g.indeg + li);
-                d = (float)graph_npad(g, gi) - c;
+            if (F > 8) {
+                for (int f = 0; f < FS; ++f) xs[t * FS + f] = (t < rows && f < F) ? __ldg(x + (size_t)(row0 + t) * F + f) : 0.f;
+            } else {
+                st4(xs + t * FS, make_float4(xr[0], xr[1], xr[2], xr[3]));
+                if (FS > 4) st4(xs + t * FS + 4, make_float4(xr[4], xr[5], xr[6], xr[7]));
             }
-            cw[t] = c;
-            cw[64 + t] = d;
+            cw[t] = cn;
+            cw[64 + t] = dn;
+            prefetch(tile + gridDim.x);                  // zeros past the last row
         }
         __syncthreads();
         TL2(1);
@@ -528,13 +548,20 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
             const float4 bb = ld4(b1a + 4 * c4);
 #pragma unroll
             for (int i = 0; i < 8; ++i) h[i] = bb;
-            for (int f = 0; f < F; ++f) {
-                const float4 w = ld4(W1a + f * 64 + 4 * c4);
+            for (int f0 = 0; f0 < FS; f0 += 4) {     // padded features are zero in x and in theta1a
+                const float4 w0 = ld4(W1a + f0 * 64 + 4 * c4), w1 = ld4(W1a + (f0 + 1) * 64 + 4 * c4),
+                             w2 = ld4(W1a + (f0 + 2) * 64 + 4 * c4), w3 = ld4(W1a + (f0 + 3) * 64 + 4 * c4);
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
-                    float xv = xs[(rbase + 8 * i) * F + f];
-                    h[i].x = fmaf(xv, w.x, h[i].x); h[i].y = fmaf(xv, w.y, h[i].y);
-                    h[i].z = fmaf(xv, w.z, h[i].z); h[i].w = fmaf(xv, w.w, h[i].w);
+                    const float4 xv = ld4(xs + (rbase + 8 * i) * FS + f0);
+                    h[i].x = fmaf(xv.x, w0.x, h[i].x); h[i].y = fmaf(xv.x, w0.y, h[i].y);
+                    h[i].z = fmaf(xv.x, w0.z, h[i].z); h[i].w = fmaf(xv.x, w0.w, h[i].w);
+                    h[i].x = fmaf(xv.y, w1.x, h[i].x); h[i].y = fmaf(xv.y, w1.y, h[i].y);
+                    h[i].z = fmaf(xv.y, w1.z, h[i].z); h[i].w = fmaf(xv.y, w1.w, h[i].w);
+                    h[i].x = fmaf(xv.z, w2.x, h[i].x); h[i].y = fmaf(xv.z, w2.y, h[i].y);
+                    h[i].z = fmaf(xv.z, w2.z, h[i].z); h[i].w = fmaf(xv.z, w2.w, h[i].w);
+                    h[i].x = fmaf(xv.w, w3.x, h[i].x); h[i].y = fmaf(xv.w, w3.y, h[i].y);
+                    h[i].z = fmaf(xv.w, w3.z, h[i].z); h[i].w = fmaf(xv.w, w3.w, h[i].w);
                 }
             }
 #pragma unroll
@@ -582,6 +609,107 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
         TL2(7);
         __syncthreads();
         TL2(8);
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(d1);
+}
+
+// ------------------------------------------------------------------------------------
+// Q / logit head (same math as k_head, s2v_head.cu): L = mu theta7^T + b7 on the tensor cores (3xTF32),
+//   q_i = w5[:p] . relu(G_g(i)) + w5[p:] . relu(L_i) + b5
+// The row owner (lane < 16 of each warp, UMMA M = 64 layout) reads its accumulator row from TMEM and does both
+// dot products; G comes from k_pool (per graph, L2-resident).  mu rows are loaded one tile ahead.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS)
+k_head_tc(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const float* __restrict__ gstate,
+          float* __restrict__ q, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* b_hi = smem;                        // theta7 [n][k]
+    uint8_t* b_lo = b_hi + TILE_BYTES;
+    uint8_t* a_hi = b_lo + TILE_BYTES;           // mu tile
+    uint8_t* a_lo = a_hi + TILE_BYTES;
+    float* vec = reinterpret_cast<float*>(a_lo + TILE_BYTES);   // b7, w5a, w5b
+    TcShared* sh = reinterpret_cast<TcShared*>(vec + 3 * 64);
+    float* b7 = vec, *w5a = vec + 64, *w5b = vec + 128;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+
+    if (warp == 0) tc::tmem_alloc<64>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    load_weight_tiles(b_hi, b_lo, prm.theta7_w, false);
+    if (t < 64) {
+        b7[t] = __ldg(prm.theta7_b + t);
+        w5a[t] = __ldg(prm.theta5_w + t);
+        w5b[t] = __ldg(prm.theta5_w + 64 + t);
+    }
+    const float b5 = __ldg(prm.theta5_b);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d1 = sh->tmem_base;
+    const uint32_t s_a_hi = tc::smem_u32(a_hi), s_a_lo = tc::smem_u32(a_lo), s_b_hi = tc::smem_u32(b_hi), s_b_lo = tc::smem_u32(b_lo);
+    uint32_t phase = 0;
+    float4 m[8];
+    auto load_rows = [&](int tile) {
+        const int row0 = tile * TCR, rows = min(TCR, g.num_nodes - row0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+            m[i] = rl < rows ? ldg4(mu + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero();
+        }
+    };
+    if (blockIdx.x < num_tiles) load_rows(blockIdx.x);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i;
+            store_split(a_hi, a_lo, e >> 4, e & 15, m[i]);
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            tc::tc_fence_after_sync();
+            issue_transform(d1, s_a_hi, s_a_lo, s_b_hi, s_b_lo);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        if (tile + (int)gridDim.x < num_tiles) load_rows(tile + gridDim.x);     // in flight during the MMAs and the epilogue
+        // graph part of the row owner's q while the tensor core works
+        const int rl = 16 * warp + (lane & 15);
+        float sg = 0.f;
+        if (lane < 16 && rl < rows) {
+            int li, off, gi;
+            row_info(g, row0 + rl, li, off, gi);
+            const float* G = gstate + (size_t)gi * 64;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float4 gv = ldg4(G + 4 * c), wa = ld4(w5a + 4 * c);
+                sg = fmaf(wa.x, relu(gv.x), sg); sg = fmaf(wa.y, relu(gv.y), sg);
+                sg = fmaf(wa.z, relu(gv.z), sg); sg = fmaf(wa.w, relu(gv.w), sg);
+            }
+        }
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        float sl = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tc::tmem_ld32(d1 + ((uint32_t)(32 * warp) << 16) + 32 * half, v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 bb = ld4(b7 + 32 * half + 4 * c), wb = ld4(w5b + 32 * half + 4 * c);
+                sl = fmaf(wb.x, relu(v[4 * c] + bb.x), sl); sl = fmaf(wb.y, relu(v[4 * c + 1] + bb.y), sl);
+                sl = fmaf(wb.z, relu(v[4 * c + 2] + bb.z), sl); sl = fmaf(wb.w, relu(v[4 * c + 3] + bb.w), sl);
+            }
+        }
+        if (lane < 16 && rl < rows) q[row0 + rl] = (sg + sl) + b5;
+        tc::tc_fence_before_sync();
+        __syncthreads();                        // the accumulator and the A tiles are free again
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -1681,6 +1809,16 @@ int s2v_tc_embed_first(const s2v_graph_t& g, const s2v_embed_params_t& prm, cons
     S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_first_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM));
     int grid = tc_grid((const void*)k_embed_first_tc, FIRST_SMEM, 64, tiles);
     k_embed_first_tc<<<grid, TC_THREADS, FIRST_SMEM, st>>>(g, prm, x, base, mu1, tiles);
+    return (int)cudaGetLastError();
+}
+
+int s2v_tc_head_forward(const s2v_graph_t& g, const s2v_head_params_t& prm, const float* mu, const float* gstate, float* q,
+                        cudaStream_t st) {
+    const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    constexpr int HEAD_SMEM = 4 * TILE_BYTES + 3 * 64 * 4 + 64 + 1024;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM));
+    int grid = tc_grid((const void*)k_head_tc, HEAD_SMEM, 64, tiles);
+    k_head_tc<<<grid, TC_THREADS, HEAD_SMEM, st>>>(g, prm, mu, gstate, q, tiles);
     return (int)cudaGetLastError();
 }
 

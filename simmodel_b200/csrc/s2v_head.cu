@@ -220,17 +220,32 @@ k_head_bwd(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, c
         // (qvals[actions + ptr[:-1]], comb_opt.py:355-356), so almost every tile takes this exit.
         const bool live = __syncthreads_or(t < rows && __ldg(dq + row0 + t) != 0.f);
         if (!live) {
+            // streaming exit: all loads of the thread's chunks are issued before the first store; the graph of a row
+            // comes from one division per tile (replicated layout) instead of one per chunk
             constexpr int V = P / 4;
-            for (int e = t; e < rows * V; e += S2V_THREADS) {
-                int rl = e / V, c = e - rl * V;
-                int li, off, gi;
-                row_info(g, row0 + rl, li, off, gi);
-                float4 o = ldg4(per_graph + (size_t)gi * (2 * P + 4) + P + 4 * c);
-                if (mask_relu) {
-                    float4 m = ldg4(mu + (size_t)(row0 + rl) * P + 4 * c);
-                    o = make_float4(m.x > 0.f ? o.x : 0.f, m.y > 0.f ? o.y : 0.f, m.z > 0.f ? o.z : 0.f, m.w > 0.f ? o.w : 0.f);
+            constexpr int NI = (S2V_TM * V + S2V_THREADS - 1) / S2V_THREADS;
+            int gi0 = 0, nb = S2V_TM;                           // rows [0, nb) of the tile belong to graph gi0
+            if (g.period > 0) { gi0 = row0 / g.period; nb = (gi0 + 1) * g.period - row0; }
+            float4 o[NI], m[NI];
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int e = t + i * S2V_THREADS, rl = e / V, c = e - rl * V;
+                o[i] = f4zero(); m[i] = make_float4(1.f, 1.f, 1.f, 1.f);
+                if (e < rows * V) {
+                    int gi;
+                    if (g.period > 0) gi = rl < nb ? gi0 : gi0 + 1 + (rl - nb) / g.period;
+                    else gi = __ldg(g.gid + row0 + rl);
+                    o[i] = ldg4(per_graph + (size_t)gi * (2 * P + 4) + P + 4 * c);
+                    if (mask_relu) m[i] = ldg4(mu + (size_t)(row0 + rl) * P + 4 * c);
                 }
-                st4(dmu + (size_t)(row0 + rl) * P + 4 * c, o);
+            }
+#pragma unroll
+            for (int i = 0; i < NI; ++i) {
+                const int e = t + i * S2V_THREADS, rl = e / V, c = e - rl * V;
+                if (e < rows * V)
+                    st4(dmu + (size_t)(row0 + rl) * P + 4 * c,
+                        make_float4(m[i].x > 0.f ? o[i].x : 0.f, m[i].y > 0.f ? o[i].y : 0.f,
+                                    m[i].z > 0.f ? o[i].z : 0.f, m[i].w > 0.f ? o[i].w : 0.f));
             }
             continue;
         }
@@ -394,13 +409,24 @@ k_head_finalize(const float* __restrict__ sums, float* __restrict__ grad) {
 // host launchers
 // ------------------------------------------------------------------------------------
 
+int s2v_tc_head_forward(const s2v_graph_t& g, const s2v_head_params_t& prm, const float* mu, const float* gstate, float* q,
+                        cudaStream_t st);          // s2v_embed_tc.cu (p = 64)
+// same rule as the embedding (s2v_embed.cu:use_tensor_path)
+static bool head_tensor_path(int P, int flags, int num_nodes) {
+    if (P != 64 || flags == S2V_PATH_FFMA) return false;
+    if (flags >= S2V_PATH_TENSOR && flags <= S2V_PATH_TENSOR_WS) return true;
+    return num_nodes >= S2V_TENSOR_MIN_NODES;
+}
+
 template <int P>
 static int head_forward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm, const float* mu,
                              float* pool, float* gstate, float* q, cudaStream_t st) {
     using C = Cfg<P>;
     k_pool<P><<<g.num_graphs, S2V_THREADS, 0, st>>>(g, prm.norm_agg, mu, pool, prm.theta6_w, prm.theta6_b, gstate);
     const int tiles = (g.num_nodes + S2V_TM - 1) / S2V_TM;
-    if (tiles > 0) {
+    if (tiles > 0 && head_tensor_path(P, prm.flags, g.num_nodes)) {
+        S2V_RETURN_IF(s2v_tc_head_forward(g, prm, mu, gstate, q, st));
+    } else if (tiles > 0) {
         int smem = (C::W_FLOATS + C::TILE_FLOATS + S2V_TM * C::TXP + 3 * P) * 4;
         S2V_RETURN_IF(cudaFuncSetAttribute(k_head<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int grid = s2v_persistent_grid((const void*)k_head<P>, smem, tiles);

@@ -37,6 +37,7 @@ def _head_struct(norm_agg, w):
     """w: 6 tensors theta5.w,b 6.w,b 7.w,b"""
     prm = _lib.HeadParams()
     prm.emb_dim, prm.norm_agg = int(w[2].shape[0]), int(bool(norm_agg))
+    prm.flags = _lib.path_flag()
     prm.theta5_w, prm.theta5_b, prm.theta6_w, prm.theta6_b, prm.theta7_w, prm.theta7_b = [_p(t) for t in w]
     return prm
 

@@ -329,6 +329,37 @@ def test_random_small_graphs_vs_dense_oracle(seed, cuda_device):
         _check("grad " + k, prm.grad.cpu().numpy(), Pg[k].grad.numpy(), tol=2e-5)
 
 
+@pytest.mark.parametrize("path", ["ffma", "tcws"])
+@pytest.mark.parametrize("node_dim", [1, 3, 4, 8, 12, 32])
+def test_node_dim_variants_vs_sparse_oracle(node_dim, path, cuda_device, monkeypatch):
+    """Feature widths other than the reference's 7 (nfm_gen.py:248): rows padded to a multiple of four features in the
+    tensor kernels, the F > 8 fall-backs of the first stage and of the last backward stage."""
+    import simmodel_b200 as sb
+    from oracle import s2v_ref as R
+    monkeypatch.setenv("S2V_B200_PATH", path)
+    dev = cuda_device
+    topo = sb.graphs.load_topology("NWB_UTR")
+    B, T = 3, 3
+    gen = torch.Generator().manual_seed(node_dim)
+    x = torch.rand(B * topo.num_nodes, node_dim, generator=gen) * 2 - 0.5
+    ei = sb.graphs.batch_edge_index(topo, B)
+    ptr = torch.arange(B + 1, dtype=torch.int64) * topo.num_nodes
+    P = R.make_qnet_params(node_dim, 64, seed=node_dim, scale=0.5)
+    Pg = {k: v.clone().requires_grad_(True) for k, v in P.items()}
+    q_ref = R.qnet_forward_sparse(Pg, x, ei, ptr, topo.num_nodes, T, True)
+    w = torch.randn(q_ref.numel(), generator=gen)
+    (q_ref * w).sum().backward()
+    net = sb.QNet({"emb_dim": 64, "emb_iter_T": T, "norm_agg": True, "node_dim": node_dim}, verbose=False)
+    net.load_state_dict(P)
+    net = net.to(dev)
+    layout = sb.GraphLayout.from_batch(ei.to(dev), ptr.to(dev), topo.num_nodes)
+    q = net.forward_graph(x.to(dev), layout)
+    (q * w.to(dev)).sum().backward()
+    _check("q", q.detach().cpu().numpy(), q_ref.detach().numpy())
+    for (k, prm) in net.named_parameters():
+        _check("grad " + k, prm.grad.cpu().numpy(), Pg[k].grad.numpy(), tol=2e-5)
+
+
 @pytest.mark.parametrize("topo_name,B", [("NWB_AMS", 32), ("NWB_ROT", 8), ("NWB_UTR", 5)])
 def test_real_topologies_vs_sparse_oracle(topo_name, B, cuda_device):
     """Config-sized batches on the real road graphs (isolated node 970 of AMS, degree-1 nodes)
