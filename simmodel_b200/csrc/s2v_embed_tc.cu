@@ -1384,16 +1384,14 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
         auto drain = [&](int j) {                              // tile j: D1w -> staging; group end: D2x -> racc
             const int sj = j % WS_STAGES, pj = (j / WS_STAGES) & 1, bj = j & 1;
             float* stg = stg0 + bj * WS_STG_FLOATS;
-            tc::mbar_wait(&sh->mma_done[sj], pj);
+            tc::mbar_wait2(&sh->mma_done[sj], pj, &sh->stg_empty[bj], ((j >> 1) & 1) ^ 1);
             TLW(t == 32 * WS_F_WARP0, j, 13);
-            tc::mbar_wait(&sh->stg_empty[bj], ((j >> 1) & 1) ^ 1);
             tc::tc_fence_after_sync();
             TLW(t == 32 * WS_F_WARP0, j, 6);
 #pragma unroll
             for (int c = 0; c < 4; ++c) {                      // M = 64 layout: lanes < 16 of quarter q own row 16q + lane
                 float va[16], vb[16];
-                tc::tmem_ld16(tmem + 128 * bj + lane_sel + 16 * c, va);
-                tc::tmem_ld16(tmem + 128 * bj + lane_sel + 64 + 16 * c, vb);
+                tc::tmem_ld16x2(tmem + 128 * bj + lane_sel + 16 * c, tmem + 128 * bj + lane_sel + 64 + 16 * c, va, vb);
                 if (lane < 16 && !WS_X(5)) {
                     float* dst = stg + (16 * q + lane) * STG_LD + 16 * c;
 #pragma unroll
@@ -1408,8 +1406,7 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
 #pragma unroll
                 for (int c = 0; c < 4; ++c) {
                     float va[16], vb[16];
-                    tc::tmem_ld16(d2x + lane_sel + 16 * c, va);
-                    tc::tmem_ld16(d2x + lane_sel + 64 + 16 * c, vb);
+                    tc::tmem_ld16x2(d2x + lane_sel + 16 * c, d2x + lane_sel + 64 + 16 * c, va, vb);
 #pragma unroll
                     for (int i = 0; i < 16; ++i) racc[16 * c + i] += va[i] + vb[i];
                 }
@@ -1424,8 +1421,7 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
         for (int k = 0; k < my_tiles; ++k) {
             const uint32_t s_g = tc::smem_u32(stage0 + s * WS_STAGE_BYTES), s_m = s_g + TILE16X3;
             if (issuer) {                                      // whole warp (uniform operands), one elected lane issues;
-                tc::mbar_wait(&sh->full_g[s], par);            // row transform first: it does not touch D2x
-                tc::mbar_wait(&sh->d1_free[k & 1], ((k >> 1) & 1) ^ 1);
+                tc::mbar_wait2(&sh->full_g[s], par, &sh->d1_free[k & 1], ((k >> 1) & 1) ^ 1);   // row transform first: it does not touch D2x
                 tc::tc_fence_after_sync();
                 TLW(lane == 0, k, 4);
                 if (!WS_X(1)) issue_ws_transform(128 * (k & 1), s_g, s_w);
@@ -1434,8 +1430,8 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
             if (k > 0) drain(k - 1);                           // reads D2x out at a group end -> d2_free
             if (issuer) {
                 const int grp = k / WS_D2_GROUP;
-                tc::mbar_wait(&sh->full_m[s], par);
-                if (k % WS_D2_GROUP == 0) tc::mbar_wait(&sh->d2_free, (grp & 1) ^ 1);
+                if (k % WS_D2_GROUP == 0) tc::mbar_wait2(&sh->full_m[s], par, &sh->d2_free, (grp & 1) ^ 1);
+                else tc::mbar_wait(&sh->full_m[s], par);
                 tc::tc_fence_after_sync();
                 TLW(lane == 0, k, 14);
                 if (!WS_X(0)) issue_ws_reduce(256, 384, s_g, s_m, k % WS_D2_GROUP != 0, k > 0);
