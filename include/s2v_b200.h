@@ -42,10 +42,10 @@
 extern "C" {
 #endif
 
-#define S2V_ABI_VERSION 2
+#define S2V_ABI_VERSION 3
 
 #define S2V_ERR_BAD_ARG        (-1)  /* null pointer / negative size / inconsistent sizes     */
-#define S2V_ERR_UNSUPPORTED    (-2)  /* emb_dim not in {8,16,24,32,48,64}, node_dim > 32 */
+#define S2V_ERR_UNSUPPORTED    (-2)  /* emb_dim not in {8,16,24,32,48,64}, node_dim > 32; GAT: heads*channels > 128 */
 #define S2V_ERR_WORKSPACE      (-3)  /* workspace smaller than s2v_*_workspace_bytes()        */
 
 typedef struct s2v_graph {
@@ -209,6 +209,36 @@ int s2v_masked_softmax_forward(const s2v_graph_t* g, const float* logits, const 
 int s2v_masked_softmax_backward(const s2v_graph_t* g, const float* prob, const float* dprob,
                                 float* dlogits, void* stream);
 int s2v_scatter_rows(const s2v_graph_t* g, const int64_t* arg, const float* dval, float* dq, void* stream);
+
+/* ---------------------------------------------------------------------------------
+ * GATv2 edge-attention layer (ABI 3; SURVEY.md 8f rank 1, --qnet gat2).
+ * Replaces GATv2Conv.propagate/message + torch_geometric.utils.softmax + the scatter-add
+ * aggregation of the third-party PyG layer behind self.gat(pyg_data.x, pyg_data.edge_index)
+ * (comb_opt.py:48-62,94,163-171; models_basic_lstm.py:326-338,414-426,509-513).
+ * The two node-wise linear layers x_l = lin_l(x), x_r = lin_r(x) are plain GEMMs and stay
+ * with the caller (one cuBLAS GEMM over the concatenated weights).
+ *   g        layout built from the edge_index WITHOUT self loops (remove_self_loops);
+ *            the kernels append the self edge of every node last (add_self_loops order).
+ *            Message direction: source edge_index[0] -> target edge_index[1], i.e. target j
+ *            aggregates the rows listed in the transposed CSR (rowptr_t / col_t).
+ *   heads H, channels C (per head); H*C <= 128
+ *   xl, xr   [num_nodes, H*C] with row stride ld floats (two halves of one [n, 2HC] GEMM output)
+ *   att [H*C], bias [H*C]
+ *   out      [num_nodes, H*C] = sum_j softmax_j(att . lrelu(xr[i] + xl[j], 0.2)) xl[j] + bias,
+ *            ReLU applied when apply_relu != 0 (BasicGNN between layers)
+ *   stats    [num_nodes, 2H] out: per target and head (max score, softmax denominator + 1e-16)
+ * Backward: dout [num_nodes, H*C] (already multiplied by the ReLU mask when the layer had one)
+ *   -> dxl, dxr (row stride ld), grad_att [H*C], grad_bias [H*C] (overwritten; fixed-order sums).
+ * --------------------------------------------------------------------------------- */
+#define S2V_GAT_MAX_GRID 2048
+int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
+                         const float* xl, const float* xr, const float* att, const float* bias,
+                         int32_t apply_relu, float* out, float* stats, void* stream);
+int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels, int64_t num_nodes);
+int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
+                          const float* xl, const float* xr, const float* att, const float* stats,
+                          const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
+                          void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

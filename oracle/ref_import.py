@@ -20,6 +20,8 @@ import os
 import sys
 import types
 
+import torch
+
 REFERENCE_ROOT = os.environ.get("SIMMODEL_REFERENCE", "/root/reference")
 
 _ABSENT_ROOTS = {"torch_geometric", "torch_scatter", "torch_sparse", "matplotlib", "gym", "stable_baselines3",
@@ -67,9 +69,17 @@ def load_reference():
         sys.meta_path.append(_StubFinder())
         sys.path.insert(0, REFERENCE_ROOT)
         _installed = True
+    from oracle import gat_ref, s2v_ref
+    # the gat2 branch subclasses PyG classes at import time (comb_opt.py:48-62, models_basic_lstm.py:10-11,326):
+    # put the restatements (oracle/gat_ref.py) into the fabricated torch_geometric modules BEFORE importing
+    import torch_geometric.nn.conv as _pyg_conv
+    import torch_geometric.nn.models as _pyg_models
+    import torch_geometric.nn.models.basic_gnn as _pyg_basic
+    _pyg_conv.GATv2Conv, _pyg_conv.MessagePassing = gat_ref.GATv2Conv, gat_ref.MessagePassing
+    _pyg_basic.BasicGNN = gat_ref.BasicGNN
+    _pyg_models.GAT = lambda **kw: torch.nn.Identity()     # QNet_GAT.__init__ (GATv1, not on our path) must construct
     import modules.gnn.comb_opt as comb_opt
     import modules.ppo.models_basic_lstm as models_basic_lstm
-    from oracle import s2v_ref
 
     comb_opt.scatter_mean = lambda src, index, dim=0: s2v_ref.scatter_mean(src, index)
     comb_opt.scatter_add = lambda src, index, dim=0: s2v_ref.scatter_add(src, index)
@@ -78,7 +88,11 @@ def load_reference():
     class _Batch:
         @staticmethod
         def from_data_list(data_list):
+            if all(hasattr(d, "edge_index") and hasattr(d, "x") for d in data_list):      # gat2 branch
+                return gat_ref.batch_from_data_list(data_list)
             return s2v_ref.batch_from_sizes([d.num_nodes for d in data_list])
 
     comb_opt.Batch = _Batch
+    models_basic_lstm.Batch = _Batch
+    models_basic_lstm.Data = gat_ref.Data
     return comb_opt, models_basic_lstm

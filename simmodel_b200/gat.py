@@ -1,0 +1,225 @@
+"""GATv2 embedding branch (``--qnet gat2``).
+
+Mirrors what the reference builds from torch_geometric (third party, ~2.0.4):
+``GATv2(BasicGNN)`` with ``GATv2Conv`` layers (modules/gnn/comb_opt.py:48-62, 156-182;
+modules/ppo/models_basic_lstm.py:326-338, 414-426) -- same constructor arguments and the
+same state-dict keys (``gat.convs.{k}.{att,bias,lin_l.weight,lin_l.bias,lin_r.weight,lin_r.bias}``,
+checked against the reference's shipped checkpoint), so reference checkpoints load strict.
+
+Per layer: the two node-wise linear layers are ONE plain GEMM over the concatenated
+weights (cuBLAS through torch -- a library GEMM); everything edge-wise -- attention scores,
+per-target segment softmax, weighted neighbour sum, bias, inter-layer ReLU, and the whole
+backward of those -- runs in the sm_100a kernels of csrc/s2v_gat.cu behind the C ABI
+(s2v_gat_attn_forward / _backward).  CUDA only; there is no CPU path.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import math
+
+import torch
+import torch.nn as nn
+
+from . import _lib, ops
+from ._lib import S2VError
+from .layout import GraphLayout, _p, _require_cuda, _stream
+
+
+def strip_self_loops(edge_index: torch.Tensor) -> torch.Tensor:
+    """remove_self_loops of GATv2Conv.forward; the kernels add the self edge of every node themselves."""
+    return edge_index[:, edge_index[0] != edge_index[1]].contiguous()
+
+
+def gat_layout_from_batch(edge_index, ptr, batch=None) -> GraphLayout:
+    """Batched layout for the GAT kernels (PyG Batch.from_data_list order)."""
+    _require_cuda(edge_index, "edge_index")
+    return GraphLayout.from_batch(strip_self_loops(edge_index), ptr, 0, batch)
+
+
+def gat_layout_replicated(edge_index, num_nodes: int, copies: int) -> GraphLayout:
+    """S copies of one topology (models_basic_lstm.py:509-513 builds a Batch of S Data(e, ei))."""
+    _require_cuda(edge_index, "edge_index")
+    return GraphLayout.replicated(strip_self_loops(edge_index), num_nodes, copies)
+
+
+class _GATConvFn(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, layout, heads, relu, x, wl, bl, wr, br, att, bias):
+        L = _lib.lib()
+        x = ops._f32c(x, "x")
+        n, HC = layout.num_nodes, int(wl.shape[0])
+        Cc = HC // heads
+        if x.shape[0] != n or x.shape[1] != wl.shape[1]:
+            raise ValueError("x has shape %s, expected (%d, %d)" % (tuple(x.shape), n, wl.shape[1]))
+        wcat = torch.cat((wl.detach(), wr.detach()), dim=0)                  # [2HC, in]
+        bcat = torch.cat((bl.detach(), br.detach()), dim=0)
+        xlr = torch.addmm(bcat, x, wcat.t())                                 # [n, 2HC]: x_l | x_r  (plain GEMM)
+        att_f = ops._f32c(att.detach().reshape(-1), "att")
+        bias_f = ops._f32c(bias.detach(), "bias")
+        out = torch.empty(n, HC, dtype=torch.float32, device=x.device)
+        stats = torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
+        with torch.cuda.device(x.device):
+            _lib.check(L.s2v_gat_attn_forward(C.byref(layout.c_struct()), heads, Cc, 2 * HC, _p(xlr),
+                                              C.c_void_p(xlr.data_ptr() + 4 * HC), _p(att_f), _p(bias_f), int(relu),
+                                              _p(out), _p(stats), _stream()), "s2v_gat_attn_forward")
+        _lib.launch_count += 1
+        ctx.layout, ctx.heads, ctx.relu = layout, heads, relu
+        ctx.save_for_backward(x, xlr, stats, out, att_f, wcat)
+        return out
+
+    @staticmethod
+    def backward(ctx, dout):
+        L = _lib.lib()
+        x, xlr, stats, out, att_f, wcat = ctx.saved_tensors
+        layout, heads = ctx.layout, ctx.heads
+        n, HC = layout.num_nodes, int(out.shape[1])
+        Cc = HC // heads
+        dout = ops._f32c(dout, "dout")
+        with torch.cuda.device(x.device):
+            if ctx.relu:
+                masked = torch.empty_like(dout)
+                _lib.check(L.s2v_relu_mask(_p(dout), _p(out), _p(masked), dout.numel(), _stream()), "s2v_relu_mask")
+                _lib.launch_count += 1
+                dout = masked
+            dxlr = torch.empty(n, 2 * HC, dtype=torch.float32, device=x.device)
+            gab = torch.empty(2, HC, dtype=torch.float32, device=x.device)
+            ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(heads, Cc, n), dtype=torch.uint8, device=x.device)
+            _lib.check(L.s2v_gat_attn_backward(C.byref(layout.c_struct()), heads, Cc, 2 * HC, _p(xlr),
+                                               C.c_void_p(xlr.data_ptr() + 4 * HC), _p(att_f), _p(stats), _p(dout),
+                                               _p(dxlr), C.c_void_p(dxlr.data_ptr() + 4 * HC), _p(gab[0]), _p(gab[1]),
+                                               _p(ws), ws.numel(), _stream()), "s2v_gat_attn_backward")
+        _lib.launch_count += 3
+        dw = dxlr.t().mm(x)                                                   # [2HC, in]   (plain GEMMs)
+        db = dxlr.sum(0)
+        dx = dxlr.mm(wcat) if ctx.needs_input_grad[3] else None
+        return (None, None, None, dx, dw[:HC], db[:HC], dw[HC:], db[HC:], gab[0].view(1, heads, Cc), gab[1])
+
+
+class GATv2Conv(nn.Module):
+    """torch_geometric.nn.conv.GATv2Conv in the reference's configuration: concat=True, add_self_loops=True,
+    share_weights=False, negative_slope 0.2, dropout 0, bias=True.  Init follows PyG (glorot weights and att,
+    Linear bias U(-1/sqrt(in), 1/sqrt(in)), zero output bias)."""
+
+    def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0,
+                 add_self_loops=True, bias=True, share_weights=False, **kwargs):
+        super().__init__()
+        if not (concat and add_self_loops and bias) or share_weights or dropout != 0.0 or negative_slope != 0.2:
+            raise NotImplementedError("simmodel_b200.GATv2Conv covers the reference's configuration only "
+                                      "(concat, self loops, separate lin_l/lin_r, slope 0.2, no dropout)")
+        if heads * out_channels > 128:
+            raise NotImplementedError("GATv2Conv kernels cover heads*out_channels <= 128 (got %d)" % (heads * out_channels))
+        self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.lin_l = nn.Linear(in_channels, heads * out_channels, bias=True)
+        self.lin_r = nn.Linear(in_channels, heads * out_channels, bias=True)
+        self.att = nn.Parameter(torch.empty(1, heads, out_channels))
+        self.bias = nn.Parameter(torch.zeros(heads * out_channels))
+        self.reset_parameters()
+
+    def reset_parameters(self):
+        for lin in (self.lin_l, self.lin_r):
+            a = math.sqrt(6.0 / (lin.in_features + lin.out_features))
+            nn.init.uniform_(lin.weight, -a, a)
+            nn.init.uniform_(lin.bias, -1.0 / math.sqrt(lin.in_features), 1.0 / math.sqrt(lin.in_features))
+        a = math.sqrt(6.0 / (self.heads + self.out_channels))
+        nn.init.uniform_(self.att, -a, a)
+        nn.init.zeros_(self.bias)
+
+    def forward_layout(self, x, layout: GraphLayout, relu: bool = False):
+        if not self.att.is_cuda:
+            raise S2VError("simmodel_b200.GATv2Conv runs on CUDA only: call .to('cuda') first (no CPU fallback)")
+        return _GATConvFn.apply(layout, self.heads, bool(relu), x, self.lin_l.weight, self.lin_l.bias,
+                                self.lin_r.weight, self.lin_r.bias, self.att, self.bias)
+
+    def forward(self, x, edge_index):
+        n = int(x.shape[0])
+        ptr = torch.tensor([0, n], dtype=torch.int64, device=x.device)
+        return self.forward_layout(x, gat_layout_from_batch(edge_index.to(x.device), ptr))
+
+
+class GATv2(nn.Module):
+    """The reference's ``GATv2(BasicGNN)`` (comb_opt.py:50-62 / models_basic_lstm.py:326-338): ``num_layers``
+    GATv2Conv layers, widths hidden .. hidden, out; heads falls back to 1 for a layer whose width it does not
+    divide; ReLU between layers, none after the last (BasicGNN, jk=None, norm=None, dropout 0)."""
+
+    def __init__(self, in_channels, hidden_channels, num_layers, out_channels=None, heads=1, dropout=0.0,
+                 share_weights=False, concat=True, **kwargs):
+        super().__init__()
+        if dropout != 0.0:
+            raise NotImplementedError("dropout is 0 in every reference configuration")
+        if num_layers < 2:
+            raise NotImplementedError("BasicGNN with fewer than 2 layers is not used by the reference")
+        self.in_channels, self.hidden_channels, self.num_layers = in_channels, hidden_channels, num_layers
+        self.out_channels = hidden_channels if out_channels is None else out_channels
+        self.supports_edge_weight = False
+        self.supports_edge_attr = False
+        widths = [hidden_channels] * (num_layers - 1) + [self.out_channels]
+        self.convs = nn.ModuleList()
+        cin = in_channels
+        for w in widths:
+            h = heads if w % heads == 0 else 1
+            self.convs.append(GATv2Conv(cin, w // h, heads=h, concat=concat, share_weights=share_weights))
+            cin = w
+
+    def forward_layout(self, x, layout: GraphLayout):
+        for k, conv in enumerate(self.convs):
+            x = conv.forward_layout(x, layout, relu=k < self.num_layers - 1)
+        return x
+
+    def forward(self, x, edge_index):
+        n = int(x.shape[0])
+        ptr = torch.tensor([0, n], dtype=torch.int64, device=x.device)
+        return self.forward_layout(x, gat_layout_from_batch(edge_index.to(x.device), ptr))
+
+
+class QNet_GATv2(nn.Module):
+    """Drop-in for comb_opt.py:156-182 QNet_GATv2 (forward: QNet_GAT.forward, 84-135): GATv2 embedding
+    (hidden = emb_dim, heads 2, 5 layers) + the s2v Q head (theta5/6/7 with mean or sum pooling)."""
+
+    def __init__(self, config, verbose=True):
+        super().__init__()
+        self.emb_dim = config["emb_dim"]
+        self.num_layers = config["emb_iter_T"]
+        self.node_dim = config["node_dim"]
+        self.norm_agg = config["norm_agg"]
+        self.gat = GATv2(in_channels=self.node_dim, hidden_channels=self.emb_dim, heads=2, num_layers=5,
+                         out_channels=self.emb_dim, share_weights=False, concat=True)
+        self.theta5 = nn.Linear(2 * self.emb_dim, 1, True, dtype=torch.float32)
+        self.theta6 = nn.Linear(self.emb_dim, self.emb_dim, True, dtype=torch.float32)
+        self.theta7 = nn.Linear(self.emb_dim, self.emb_dim, True, dtype=torch.float32)
+        self.numTrainableParameters(verbose)
+
+    def head_weights(self):
+        return [t for n in ops.HEAD_NAMES for t in (getattr(self, n).weight, getattr(self, n).bias)]
+
+    @property
+    def device(self):
+        return self.theta6.weight.device
+
+    def forward_graph(self, x, layout: GraphLayout):
+        """x f32[sum N, F], GAT layout (self loops stripped) -> q f32[sum N]."""
+        if self.device.type != "cuda":
+            raise S2VError("simmodel_b200.QNet_GATv2 runs on CUDA only: call .to('cuda') first (no CPU fallback)")
+        mu = self.gat.forward_layout(x, layout)
+        return ops.s2v_head(layout, mu, self.head_weights(), self.norm_agg)
+
+    def forward(self, xv, Ws, pyg_data):
+        """Reference contract: xv and Ws are ignored (comb_opt.py:84-94 reads pyg_data.x / .edge_index / .ptr /
+        .batch only); returns q over all nodes of the batch, squeezed."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise S2VError("simmodel_b200.QNet_GATv2 runs on CUDA only: call .to('cuda') first (no CPU fallback)")
+        x = pyg_data.x.to(dev, torch.float32).contiguous()
+        layout = gat_layout_from_batch(pyg_data.edge_index.to(dev), pyg_data.ptr.to(dev), pyg_data.batch.to(dev))
+        return self.forward_graph(x, layout).squeeze()
+
+    def numTrainableParameters(self, verbose=True):
+        total = 0
+        lines = ["Qnet size:", "------------------------------------------"]
+        for name, p in self.named_parameters():
+            total += int(p.numel())
+            lines.append("{:24s} {:12s} requires_grad={}".format(name, str(list(p.shape)), p.requires_grad))
+        lines += ["Total number of parameters: {}".format(total), "------------------------------------------"]
+        if verbose:
+            print("\n".join(lines))
+        assert total == sum(p.numel() for p in self.parameters() if p.requires_grad)
+        return total

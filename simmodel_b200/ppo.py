@@ -21,6 +21,7 @@ import torch.optim as optim
 
 from . import ops
 from ._lib import S2VError
+from .gat import GATv2, strip_self_loops
 from .layout import GraphLayout
 
 
@@ -38,22 +39,28 @@ class _PPOModelBase(nn.Module):
         self.num_epochs = hp.batch_size
         assert config["lstm_type"] in ["None", "EMB", "FE"]
         assert config["critic"] in ["q", "v"]
-        if config["qnet"] != "s2v":
-            raise NotImplementedError("simmodel_b200 implements the s2v embedding (qnet='s2v'); "
-                                      "gat2 is the next row of SURVEY.md §8f")
+        if config["qnet"] not in ("s2v", "gat2"):
+            raise NotImplementedError("simmodel_b200 implements qnet='s2v' and qnet='gat2'")
         if tp is not None and tp.get("base_checkpoint_path"):
             Path(tp["base_checkpoint_path"]).mkdir(parents=True, exist_ok=True)
         self.description = "PPO policy, s2v extractor (B200 kernels), lstm, action masking"
         dev = torch.device(device)
-        # creation order == models_basic_lstm.py:429-460
-        self.emb_dim = config["emb_dim"]
-        self.T = config["emb_iterT"]
-        p = self.emb_dim
-        self.theta1a = nn.Linear(self.node_dim, p, True, device=dev)
-        self.theta1b = nn.Linear(p, p, True, device=dev)
-        self.theta2 = nn.Linear(p, p, True, device=dev)
-        self.theta3 = nn.Linear(p, p, True, device=dev)
-        self.theta4 = nn.Linear(1, p, True, device=dev)
+        # creation order == models_basic_lstm.py:414-460
+        if config["qnet"] == "gat2":
+            self.description = "PPO policy, GATv2 extractor (B200 kernels), lstm, action masking"
+            self.gat = GATv2(in_channels=self.node_dim, hidden_channels=self.emb_dim * 2, heads=config["gat_heads"],
+                             num_layers=config["emb_iterT"], out_channels=self.emb_dim,
+                             share_weights=config["gat_share_weights"], concat=config["gat_concat"]).to(dev)
+            p = self.emb_dim
+        else:
+            self.emb_dim = config["emb_dim"]
+            self.T = config["emb_iterT"]
+            p = self.emb_dim
+            self.theta1a = nn.Linear(self.node_dim, p, True, device=dev)
+            self.theta1b = nn.Linear(p, p, True, device=dev)
+            self.theta2 = nn.Linear(p, p, True, device=dev)
+            self.theta3 = nn.Linear(p, p, True, device=dev)
+            self.theta4 = nn.Linear(1, p, True, device=dev)
         if config["lstm_type"] == "EMB":
             self.lstm_on = True
             self.lstm = nn.LSTM(p, p, device=dev)
@@ -113,7 +120,7 @@ class S2VKernelMixin:
     # -- helpers ----------------------------------------------------------------------------
     @property
     def device(self):
-        return self.theta2.weight.device
+        return self.theta6_pi.weight.device
 
     def embed_weights(self):
         return [t for n in ops.EMBED_NAMES for t in (getattr(self, n).weight, getattr(self, n).bias)]
@@ -123,15 +130,18 @@ class S2VKernelMixin:
 
     def _layout(self, ei: torch.Tensor, num_nodes: int, copies: int) -> GraphLayout:
         """CSR of one graph, cached per edge_index tensor (a rollout shares one ei for all
-        its steps and all of v', v, pi; models_basic_lstm.py:606-624)."""
+        its steps and all of v', v, pi; models_basic_lstm.py:606-624).  For qnet='gat2' the
+        self loops are stripped (GATv2Conv removes them and adds one per node; the kernels add it)."""
         if not hasattr(self, "_layouts"):
             self._layouts = {}
-        key = (id(ei), ei._version, num_nodes, str(self.device))
+        gat = self.config["qnet"] == "gat2"
+        key = (id(ei), ei._version, num_nodes, str(self.device), gat)
         hit = self._layouts.get(key)
         if hit is None:
             if len(self._layouts) >= 64:
                 self._layouts.clear()
-            base = GraphLayout.replicated(ei.to(self.device), num_nodes, 1)
+            dev_ei = ei.to(self.device)
+            base = GraphLayout.replicated(strip_self_loops(dev_ei) if gat else dev_ei, num_nodes, 1)
             hit = (ei, base)                   # keep ei alive so id() stays unique
             self._layouts[key] = hit
         return hit[1].replicate(copies)
@@ -177,7 +187,11 @@ class S2VKernelMixin:
         assert ei.dim() == 2
         num_nodes = int(nfm.shape[1])
         layout = self._layout(ei, num_nodes, int(seq_len))
-        mu = ops.s2v_embed(layout, nfm.reshape(seq_len * num_nodes, -1).contiguous(), self.embed_weights(), self.T)
+        x = nfm.reshape(seq_len * num_nodes, -1).contiguous()
+        if self.config["qnet"] == "gat2":          # Batch of S x Data(e, ei) -> self.gat(x, edge_index), :509-513
+            mu = self.gat.forward_layout(x, layout)
+        else:
+            mu = ops.s2v_embed(layout, x, self.embed_weights(), self.T)
         mu = mu.view(seq_len, num_nodes, self.emb_dim)
         if self.config["lstm_type"] == "EMB":
             mu, lstm_hidden = self.lstm(mu, lstm_hidden)
@@ -216,4 +230,4 @@ class S2VKernelMixin:
 
 
 class PPO_GNN_Single_LSTM(S2VKernelMixin, _PPOModelBase):
-    """Drop-in for models_basic_lstm.py:407 PPO_GNN_Single_LSTM with config['qnet'] == 's2v'."""
+    """Drop-in for models_basic_lstm.py:407 PPO_GNN_Single_LSTM with config['qnet'] in ('s2v', 'gat2')."""
