@@ -48,6 +48,8 @@ def parse():
     ap.add_argument("--topo", default="NWB_AMS", choices=["NWB_AMS", "NWB_ROT", "NWB_UTR", "Manhattan5"],
                     help="topology of the synthetic batch (default: the N=975 graph the metric is quoted on; "
                          "NWB_ROT = BASELINE configs[4] scale sweep)")
+    ap.add_argument("--qnet", default="s2v", choices=["s2v", "gat2"],
+                    help="s2v = the headline path; gat2 = the GATv2 branch (SURVEY.md 8f-1: QNet_GATv2 train step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -447,6 +449,155 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
     return roofline, res
 
 
+# --------------------------------------------------------------------------------------
+# GATv2 branch (--qnet gat2): QNet_GATv2 train step on the same synthetic batch
+# --------------------------------------------------------------------------------------
+def run_gat(args):
+    """One step = QNet_GATv2 forward (5 GATv2Conv layers, heads 2, hidden 64 + Q head), loss gather + SmoothL1,
+    backward, Adam.  Single GPU.  The edge-attention kernels are timed alone for the roofline; the lin_l / lin_r
+    GEMMs are cuBLAS (library) and reported as their share of the step."""
+    import ctypes as C
+    import torch
+    import simmodel_b200 as sb
+    from simmodel_b200 import _lib
+    from simmodel_b200.layout import _p, _stream
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    L = _lib.lib()
+    topo = sb.graphs.load_topology(TOPO)
+    N, B = topo.num_nodes, args.batch
+    gen = torch.Generator().manual_seed(1000)
+    x_host = sb.graphs.synth_nfm(topo, B, gen).reshape(-1, F).contiguous().pin_memory()
+    ei_host = sb.graphs.batch_edge_index(topo, B).contiguous().pin_memory()
+    ptr = (torch.arange(B + 1, dtype=torch.int64) * N).to(dev)
+    actions_host = torch.randint(0, N, (B,), generator=gen).pin_memory()
+    targets_host = torch.randn(B, generator=gen).pin_memory()
+    torch.manual_seed(0)
+    net = sb.QNet_GATv2({"emb_dim": P, "emb_iter_T": T, "norm_agg": True, "node_dim": F}, verbose=False).to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    loss_fn = torch.nn.SmoothL1Loss()
+    x = x_host.to(dev)
+    sel = actions_host.to(dev) + ptr[:-1]
+    targets = targets_host.to(dev)
+    layout = sb.gat.gat_layout_from_batch(ei_host.to(dev), ptr)
+
+    def step():
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(net.forward_graph(x, layout)[sel], targets)
+        loss.backward()
+        opt.step()
+        return loss
+
+    def step_e2e():
+        xb = x_host.to(dev, non_blocking=True)
+        lay = sb.gat.gat_layout_from_batch(ei_host.to(dev, non_blocking=True), ptr)
+        opt.zero_grad(set_to_none=True)
+        loss = loss_fn(net.forward_graph(xb, lay)[actions_host.to(dev, non_blocking=True) + ptr[:-1]],
+                       targets_host.to(dev, non_blocking=True))
+        loss.backward()
+        opt.step()
+        return float(loss)                      # D2H read of the step's result
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / steps
+    for _ in range(args.warmup):
+        step()
+    c0 = _lib.launch_count
+    step()
+    launches_per_step = _lib.launch_count - c0
+    sampler = ClockSampler(dev.index or 0)
+    sampler.start()
+    ms = timed(step, args.steps, 0)
+    clocks = sampler.stop()
+    e2e_ms = None if args.no_e2e else timed(step_e2e, max(3, min(args.steps, 10)), 2)
+    # ---- the edge-attention kernels alone (hidden layer shape: H=2, C=32) ----
+    n, H, Cc = layout.num_nodes, 2, P // 2
+    HC = H * Cc
+    dbar = layout.num_edges / n
+    xlr = torch.randn(n, 2 * HC, device=dev)
+    att, bias = torch.randn(HC, device=dev) * 0.1, torch.randn(HC, device=dev) * 0.1
+    out, stats = torch.empty(n, HC, device=dev), torch.empty(n, H, 4, device=dev)
+    dout, dxlr, gab = torch.randn(n, HC, device=dev), torch.empty(n, 2 * HC, device=dev), torch.empty(2, HC, device=dev)
+    ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(H, Cc), dtype=torch.uint8, device=dev)
+    g = layout.c_struct()
+    xr_p, dxr_p = C.c_void_p(xlr.data_ptr() + 4 * HC), C.c_void_p(dxlr.data_ptr() + 4 * HC)
+
+    def k_fwd():
+        _lib.check(L.s2v_gat_attn_forward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(bias), 1, _p(out), _p(stats),
+                                          _stream()), "gat fwd")
+
+    def k_bwd():
+        _lib.check(L.s2v_gat_attn_backward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(stats), _p(dout), _p(dxlr),
+                                           dxr_p, _p(gab[0]), _p(gab[1]), _p(ws), ws.numel(), _stream()), "gat bwd")
+    peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
+    # forward: (dbar+1) x_l rows + x_r row read, out row written, ids + rowptr, stats written
+    fwd_bytes = 4 * (HC * (dbar + 3) + dbar + 1 + 2 * H)
+    # backward (both kernels): target pass reads (dbar+1) x_l rows + x_r + dout + stats, writes dx_r + D;
+    # source pass reads x_l + (dbar+1) x (x_r, dout, stats, D) rows, writes dx_l; ids + rowptr twice
+    bwd_bytes = 4 * (HC * (dbar + 1 + 3) + 3 * H + HC * (1 + 2 * (dbar + 1) + 1) + 3 * H * (dbar + 1) + 2 * (dbar + 1))
+    kernels = []
+    for name, fn, bpn in (("k_gat_fwd<2> (H=2, C=32)", k_fwd, fwd_bytes),
+                          ("k_gat_bwd_target + k_gat_bwd_source<2> (H=2, C=32)", k_bwd, bwd_bytes)):
+        k_ms = timed(fn, 10, 3)
+        ach = bpn * n / (k_ms / 1e3) / 1e9
+        kernels.append({"kernel": name, "ms": k_ms, "algorithmic_bytes": bpn * n, "achieved_GBps": ach, "frac": ach / peak,
+                        "launches_per_step": 5})
+    dom = max(kernels, key=lambda r: r["ms"])
+    edge_ms = sum(k["ms"] * k["launches_per_step"] for k in kernels)
+    roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
+                "frac": dom["frac"], "traffic": None, "algorithmic_bytes_per_row": dom["algorithmic_bytes"] / n,
+                "rows_per_launch": n, "avg_launch_ms": dom["ms"],
+                "edge_kernels_share_of_step": edge_ms / ms,
+                "note": "lin_l/lin_r GEMMs (fp32 cuBLAS, library) and torch reductions make up the rest of the step"}
+    cpu_baseline = None
+    if not args.no_cpu_baseline:
+        from oracle import gat_ref as G
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        b0 = 8
+        Pm = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in net.state_dict().items()}
+        xs = x_host[: b0 * N].clone()
+        eis = sb.graphs.batch_edge_index(topo, b0)
+        ptr0 = torch.arange(b0 + 1, dtype=torch.int64) * N
+        sel0 = actions_host[:b0] + ptr0[:-1]
+
+        def cpu_step():
+            for v in Pm.values():
+                v.grad = None
+            q = G.qnet_gat_forward(Pm, xs, eis, ptr0, 5, True)
+            loss_fn(q[sel0], targets_host[:b0]).backward()
+        times = time_cpu(cpu_step, 3, 10.0)
+        cpu_baseline = {"value": b0 / statistics.mean(times), "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": "oracle/gat_ref.py (PyG GATv2Conv restated, torch CPU), fwd+bwd, B=%d graphs per step, %d steps"
+                                  % (b0, len(times))}
+    n_t, e_t = TOPO_SHAPES[TOPO]
+    line = {"metric": "gat2_fwd_bwd_graphs_per_sec_N%d" % n_t, "value": B / (ms / 1e3), "unit": UNIT, "n_gpus": 1,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
+            "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": "QNet_GATv2 GNN-DQN train step on %s (N=%d, E=%d, F=7, emb 64, 5 GATv2Conv layers, heads 2)"
+                                   % (TOPO, n_t, e_t), "graphs_per_gpu": B, "global_batch": B, "nodes_per_graph": n_t,
+                       "parallelism": "dp1", "l2": "inputs exceed L2: every activation plane %.2f GB" % (B * n_t * P * 4 / 1e9)},
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
+            "e2e": None if e2e_ms is None else {
+                "value": B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 8 + actions_host.numel() * 8 + targets_host.numel() * 4,
+                "d2h_bytes_per_step": 4},
+            "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+
+
 def measure_small_batch(sb, dev):
     """The reference's own DQN call shapes (BASELINE configs[2]: batch 32 train step, B = 1 acting forward),
     eager and replayed from a CUDA graph (host wall clock per call, device synchronised)."""
@@ -527,6 +678,8 @@ def main():
         METRIC = "s2v_fwd_bwd_graphs_per_sec_N%d" % TOPO_SHAPES[TOPO][0]
     if args.impl == "reference":
         run_reference(args)
+    elif args.qnet == "gat2":
+        run_gat(args)
     else:
         run_b200(args)
 

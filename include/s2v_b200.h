@@ -226,7 +226,8 @@ int s2v_scatter_rows(const s2v_graph_t* g, const int64_t* arg, const float* dval
  *   att [H*C], bias [H*C]
  *   out      [num_nodes, H*C] = sum_j softmax_j(att . lrelu(xr[i] + xl[j], 0.2)) xl[j] + bias,
  *            ReLU applied when apply_relu != 0 (BasicGNN between layers)
- *   stats    [num_nodes, 2H] out: per target and head (max score, softmax denominator + 1e-16)
+ *   stats    [num_nodes, H, 4] out: per target and head (max score, 1 / den, D, den = softmax denominator + 1e-16);
+ *            the backward writes D = sum_j a_ij da_ij into the third slot
  * Backward: dout [num_nodes, H*C] (already multiplied by the ReLU mask when the layer had one)
  *   -> dxl, dxr (row stride ld), grad_att [H*C], grad_bias [H*C] (overwritten; fixed-order sums).
  * --------------------------------------------------------------------------------- */
@@ -234,9 +235,9 @@ int s2v_scatter_rows(const s2v_graph_t* g, const int64_t* arg, const float* dval
 int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                          const float* xl, const float* xr, const float* att, const float* bias,
                          int32_t apply_relu, float* out, float* stats, void* stream);
-int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels, int64_t num_nodes);
+int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels);
 int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
-                          const float* xl, const float* xr, const float* att, const float* stats,
+                          const float* xl, const float* xr, const float* att, float* stats,
                           const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
                           void* workspace, int64_t workspace_bytes, void* stream);
 

@@ -50,6 +50,11 @@ __device__ __forceinline__ Vec<VEC> vzero() { Vec<VEC> r;
     return r; }
 
 __device__ __forceinline__ float lrelu(float s) { return s > 0.f ? s : s * GAT_SLOPE; }
+// ex / den from the stored reciprocal with one Newton step (== the correctly rounded quotient up to the last bit)
+__device__ __forceinline__ float qdiv(float ex, float inv, float den) {
+    const float q = ex * inv;
+    return fmaf(fmaf(-q, den, ex), inv, q);
+}
 
 // sum over the lanes of one head (lph consecutive lanes); every lane of the warp takes part
 __device__ __forceinline__ float head_sum(float v, int lph, int lane) {
@@ -99,7 +104,7 @@ k_gat_fwd(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ x
         const int beg = __ldg(g.rowptr_t + li), deg = __ldg(g.rowptr_t + li + 1) - beg, cnt = deg + 1;
         const Vec<VEC> xri = ldv<VEC>(xr + (size_t)r * ld + ch);
         Vec<VEC> acc = vzero<VEC>();
-        float m = -INFINITY, den;
+        float m = -INFINITY, inv, den;
         if (cnt <= GAT_FAST) {
             const int jl = lane < deg ? __ldg(g.col_t + beg + lane) + off : r;
             int js[GAT_FAST];
@@ -116,10 +121,10 @@ k_gat_fwd(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ x
             float S = 0.f;
 #pragma unroll
             for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) { sc[k] = expf(sc[k] - m); S += sc[k]; }
-            den = S + 1e-16f;
+            den = S + 1e-16f; inv = 1.f / den;
 #pragma unroll
             for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) {
-                const float al = sc[k] / den;
+                const float al = qdiv(sc[k], inv, den);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) acc.v[v] = fmaf(rows[k].v[v], al, acc.v[v]);
             }
@@ -135,11 +140,11 @@ k_gat_fwd(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ x
                 const Vec<VEC> row = ldv<VEC>(xl + (size_t)j * ld + ch);
                 S += expf(head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane) - m);
             }
-            den = S + 1e-16f;
+            den = S + 1e-16f; inv = 1.f / den;
             for (int k = 0; k < cnt; ++k) {
                 const int j = k < deg ? __ldg(g.col_t + beg + k) + off : r;
                 const Vec<VEC> row = ldv<VEC>(xl + (size_t)j * ld + ch);
-                const float al = expf(head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane) - m) / den;
+                const float al = qdiv(expf(head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane) - m), inv, den);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) acc.v[v] = fmaf(row.v[v], al, acc.v[v]);
             }
@@ -148,7 +153,7 @@ k_gat_fwd(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ x
 #pragma unroll
             for (int v = 0; v < VEC; ++v) { float o = acc.v[v] + b.v[v]; acc.v[v] = apply_relu ? relu(o) : o; }
             stv<VEC>(out + (size_t)r * HC + ch, acc);
-            if (lane % lph == 0) { stats[(size_t)r * 2 * H + 2 * head] = m; stats[(size_t)r * 2 * H + 2 * head + 1] = den; }
+            if (lane % lph == 0) *reinterpret_cast<float4*>(stats + ((size_t)r * H + head) * 4) = make_float4(m, inv, 0.f, den);
         }
     }
 }
@@ -171,8 +176,8 @@ __device__ __forceinline__ void bwd_a_edge(const Vec<VEC>& a, const Vec<VEC>& xr
 template <int VEC>
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
-                 const float* __restrict__ att, const float* __restrict__ stats, const float* __restrict__ dout,
-                 float* __restrict__ dxr, float* __restrict__ dsum, float* __restrict__ partials) {
+                 const float* __restrict__ att, float* __restrict__ stats, const float* __restrict__ dout,
+                 float* __restrict__ dxr, float* __restrict__ partials) {
     __shared__ float red[GAT_WARPS][2 * 128];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int HC = H * C, lanes = HC / VEC, lph = C / VEC;
@@ -188,7 +193,7 @@ k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restr
         const int beg = __ldg(g.rowptr_t + li), deg = __ldg(g.rowptr_t + li + 1) - beg, cnt = deg + 1;
         const Vec<VEC> xri = ldv<VEC>(xr + (size_t)r * ld + ch);
         const Vec<VEC> doi = ldv<VEC>(dout + (size_t)r * HC + ch);
-        const float m = __ldg(stats + (size_t)r * 2 * H + 2 * head), den = __ldg(stats + (size_t)r * 2 * H + 2 * head + 1);
+        const float m = stats[((size_t)r * H + head) * 4], inv = stats[((size_t)r * H + head) * 4 + 1], den = stats[((size_t)r * H + head) * 4 + 3];
         Vec<VEC> dx = vzero<VEC>();
         float D = 0.f;
         if (cnt <= GAT_FAST) {
@@ -204,7 +209,7 @@ k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restr
             for (int k = 0; k < GAT_FAST; ++k) {
                 const float e = head_sum(active ? score_partial<VEC>(a, xri, rows[k]) : 0.f, lph, lane);
                 dal[k] = head_sum(active ? dot_partial<VEC>(doi, rows[k]) : 0.f, lph, lane);
-                al[k] = k < cnt ? expf(e - m) / den : 0.f;
+                al[k] = k < cnt ? qdiv(expf(e - m), inv, den) : 0.f;
             }
 #pragma unroll
             for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) D = fmaf(al[k], dal[k], D);
@@ -216,19 +221,19 @@ k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restr
                 const Vec<VEC> row = ldv<VEC>(xl + (size_t)j * ld + ch);
                 const float e = head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane);
                 const float dl = head_sum(active ? dot_partial<VEC>(doi, row) : 0.f, lph, lane);
-                D = fmaf(expf(e - m) / den, dl, D);
+                D = fmaf(qdiv(expf(e - m), inv, den), dl, D);
             }
             for (int k = 0; k < cnt; ++k) {
                 const int j = k < deg ? __ldg(g.col_t + beg + k) + off : r;
                 const Vec<VEC> row = ldv<VEC>(xl + (size_t)j * ld + ch);
                 const float e = head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane);
                 const float dl = head_sum(active ? dot_partial<VEC>(doi, row) : 0.f, lph, lane);
-                bwd_a_edge<VEC>(a, xri, row, expf(e - m) / den, dl, D, dx, datt);
+                bwd_a_edge<VEC>(a, xri, row, qdiv(expf(e - m), inv, den), dl, D, dx, datt);
             }
         }
         if (active) {
             stv<VEC>(dxr + (size_t)r * ld + ch, dx);
-            if (lane % lph == 0) dsum[(size_t)r * H + head] = D;
+            if (lane % lph == 0) stats[((size_t)r * H + head) * 4 + 2] = D;
 #pragma unroll
             for (int v = 0; v < VEC; ++v) dbias.v[v] += doi.v[v];
         }
@@ -267,7 +272,7 @@ template <int VEC>
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_source(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
                  const float* __restrict__ att, const float* __restrict__ stats, const float* __restrict__ dout,
-                 const float* __restrict__ dsum, float* __restrict__ dxl) {
+                 float* __restrict__ dxl) {
     const int lane = threadIdx.x & 31;
     const int HC = H * C, lanes = HC / VEC, lph = C / VEC;
     const bool active = lane < lanes;
@@ -287,35 +292,301 @@ k_gat_bwd_source(const s2v_graph_t g, int H, int C, int ld, const float* __restr
 #pragma unroll
             for (int k = 0; k < GAT_FAST; ++k) is[k] = __shfl_sync(0xffffffffu, il, k);
             Vec<VEC> xrs[GAT_FAST], dos[GAT_FAST];
-            float ms[GAT_FAST], dens[GAT_FAST], Ds[GAT_FAST];
+            float4 st[GAT_FAST];
 #pragma unroll
             for (int k = 0; k < GAT_FAST; ++k) {
                 const bool on = k < cnt;
                 xrs[k] = on ? ldv<VEC>(xr + (size_t)is[k] * ld + ch) : vzero<VEC>();
                 dos[k] = on ? ldv<VEC>(dout + (size_t)is[k] * HC + ch) : vzero<VEC>();
-                ms[k] = on ? __ldg(stats + (size_t)is[k] * 2 * H + 2 * head) : 0.f;
-                dens[k] = on ? __ldg(stats + (size_t)is[k] * 2 * H + 2 * head + 1) : 1.f;
-                Ds[k] = on ? __ldg(dsum + (size_t)is[k] * H + head) : 0.f;
+                st[k] = on ? ldg4(stats + ((size_t)is[k] * H + head) * 4) : f4zero();
             }
 #pragma unroll
             for (int k = 0; k < GAT_FAST; ++k) {
                 const float e = head_sum(active ? score_partial<VEC>(a, xrs[k], xlj) : 0.f, lph, lane);
                 const float dl = head_sum(active ? dot_partial<VEC>(dos[k], xlj) : 0.f, lph, lane);
-                if (k < cnt) bwd_b_edge<VEC>(a, xlj, xrs[k], dos[k], expf(e - ms[k]) / dens[k], dl, Ds[k], dx);
+                if (k < cnt) bwd_b_edge<VEC>(a, xlj, xrs[k], dos[k], qdiv(expf(e - st[k].x), st[k].y, st[k].w), dl, st[k].z, dx);
             }
         } else {
             for (int k = 0; k < cnt; ++k) {
                 const int i = k < deg ? __ldg(g.col + beg + k) + off : r;
                 const Vec<VEC> xri = ldv<VEC>(xr + (size_t)i * ld + ch);
                 const Vec<VEC> doi = ldv<VEC>(dout + (size_t)i * HC + ch);
-                const float m = __ldg(stats + (size_t)i * 2 * H + 2 * head), den = __ldg(stats + (size_t)i * 2 * H + 2 * head + 1);
-                const float D = __ldg(dsum + (size_t)i * H + head);
+                const float4 st = ldg4(stats + ((size_t)i * H + head) * 4);
                 const float e = head_sum(active ? score_partial<VEC>(a, xri, xlj) : 0.f, lph, lane);
                 const float dl = head_sum(active ? dot_partial<VEC>(doi, xlj) : 0.f, lph, lane);
-                bwd_b_edge<VEC>(a, xlj, xri, doi, expf(e - m) / den, dl, D, dx);
+                bwd_b_edge<VEC>(a, xlj, xri, doi, qdiv(expf(e - st.x), st.y, st.w), dl, st.z, dx);
             }
         }
         if (active) stv<VEC>(dxl + (size_t)r * ld + ch, dx);
+    }
+}
+
+// ============================================================================================================
+// Specialised kernels for the reference's shapes: 128-bit lanes, LPR lanes per row (H*C = 4*LPR), LPH lanes per
+// head (C = 4*LPH), 32/LPR rows per warp; CSR extents and neighbour ids of the next rows are prefetched two / one
+// iterations ahead (one memory round trip per row on the critical path instead of three).
+//   <32,8>: H*C = 128, C = 32 (PPO hidden layers)   <16,8>: H*C = 64, C = 32 (DQN QNet_GATv2)
+//   <16,4>: H*C = 64,  C = 16 (PPO output layer)
+// ============================================================================================================
+template <int LPH>
+__device__ __forceinline__ float hsum(float v) {
+#pragma unroll
+    for (int o = LPH >> 1; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float score4(const float4& a, const float4& xr, const float4& xl) {
+    float e = a.x * lrelu(xr.x + xl.x);
+    e = fmaf(a.y, lrelu(xr.y + xl.y), e);
+    e = fmaf(a.z, lrelu(xr.z + xl.z), e);
+    return fmaf(a.w, lrelu(xr.w + xl.w), e);
+}
+__device__ __forceinline__ float dot4(const float4& a, const float4& b) {
+    return fmaf(a.w, b.w, fmaf(a.z, b.z, fmaf(a.y, b.y, a.x * b.x)));
+}
+__device__ __forceinline__ float dlr(float s) { return s > 0.f ? 1.f : GAT_SLOPE; }
+
+// Pipelined row metadata: (beg, deg, off) of a row from the CSR given by (rp, ci); ids of its first LPR neighbours.
+struct RowMeta { int r, beg, deg, off; };
+__device__ __forceinline__ RowMeta row_meta(const s2v_graph_t& g, const int* __restrict__ rp, int r) {
+    RowMeta m; m.r = r; m.beg = 0; m.deg = -1; m.off = 0;          // deg -1 => cnt 0: row out of range
+    if (r < g.num_nodes) {
+        int li = r;
+        if (g.period > 0) { const int gi = r / g.period; m.off = gi * g.period; li = r - m.off; }
+        m.beg = __ldg(rp + li);
+        m.deg = __ldg(rp + li + 1) - m.beg;
+    }
+    return m;
+}
+__device__ __forceinline__ int row_ids(const RowMeta& m, const int* __restrict__ ci, int sl) {
+    return sl < m.deg ? __ldg(ci + m.beg + sl) + m.off : m.r;
+}
+
+#define GAT_ROW_LOOP(RP, CI)                                                                                    \
+    const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;                                       \
+    const int ch = sl * 4, head = sl / LPH;                                                                     \
+    const int step = gridDim.x * GAT_WARPS * RPW;                                                               \
+    int r0 = (blockIdx.x * GAT_WARPS + (threadIdx.x >> 5)) * RPW;                                               \
+    RowMeta cur = row_meta(g, RP, r0 + sub);                                                                    \
+    int jl = row_ids(cur, CI, sl);                                                                              \
+    RowMeta nxt = row_meta(g, RP, r0 + step + sub);                                                             \
+    for (; r0 < g.num_nodes; r0 += step)
+
+#define GAT_ROW_ADVANCE(RP, CI)                                                                                 \
+    const int jl_n = row_ids(nxt, CI, sl);                                                                      \
+    const RowMeta nn = row_meta(g, RP, nxt.r + step);
+
+#define GAT_ROW_ROTATE() cur = nxt; jl = jl_n; nxt = nn;
+
+template <int LPR>
+__device__ __forceinline__ int warp_max_cnt(int cnt) {
+    if (LPR < 32) cnt = max(cnt, __shfl_xor_sync(0xffffffffu, cnt, 16));
+    return cnt;
+}
+
+template <int LPR, int LPH>
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gat_fwd4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
+           const float* __restrict__ att, const float* __restrict__ bias, int apply_relu,
+           float* __restrict__ out, float* __restrict__ stats) {
+    constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
+    GAT_ROW_LOOP(g.rowptr_t, g.col_t) {
+        GAT_ROW_ADVANCE(g.rowptr_t, g.col_t)
+        const float4 a = ldg4(att + ch), b = ldg4(bias + ch);
+        const int r = cur.r, cnt = cur.deg + 1;
+        const bool valid = cnt > 0;
+        const float4 xri = valid ? ldg4(xr + (size_t)r * ld + ch) : f4zero();
+        float4 acc = f4zero();
+        float m = -INFINITY, inv = 0.f, den = 1.f;
+        if (warp_max_cnt<LPR>(cnt) <= GAT_FAST) {
+            int js[GAT_FAST];
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
+            float4 rows[GAT_FAST];
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) rows[k] = k < cnt ? ldg4(xl + (size_t)js[k] * ld + ch) : f4zero();
+            float sc[GAT_FAST];
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) sc[k] = hsum<LPH>(score4(a, xri, rows[k]));
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) m = fmaxf(m, sc[k]);
+            float S = 0.f;
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) { sc[k] = expf(sc[k] - m); S += sc[k]; }
+            den = S + 1e-16f; inv = 1.f / den;
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) {
+                const float al = qdiv(sc[k], inv, den);
+                acc.x = fmaf(rows[k].x, al, acc.x); acc.y = fmaf(rows[k].y, al, acc.y);
+                acc.z = fmaf(rows[k].z, al, acc.z); acc.w = fmaf(rows[k].w, al, acc.w);
+            }
+        } else {
+            const int mc = warp_max_cnt<LPR>(cnt);
+            float S = 0.f;
+            for (int pass = 0; pass < 3; ++pass) {
+                for (int k = 0; k < mc; ++k) {
+                    const bool on = k < cnt;
+                    const int j = on && k < cur.deg ? __ldg(g.col_t + cur.beg + k) + cur.off : r;
+                    const float4 row = on ? ldg4(xl + (size_t)j * ld + ch) : f4zero();
+                    const float e = hsum<LPH>(score4(a, xri, row));
+                    if (!on) continue;
+                    if (pass == 0) m = fmaxf(m, e);
+                    else if (pass == 1) S += expf(e - m);
+                    else {
+                        const float al = qdiv(expf(e - m), inv, den);
+                        acc.x = fmaf(row.x, al, acc.x); acc.y = fmaf(row.y, al, acc.y);
+                        acc.z = fmaf(row.z, al, acc.z); acc.w = fmaf(row.w, al, acc.w);
+                    }
+                }
+                if (pass == 1) den = S + 1e-16f; inv = 1.f / den;
+            }
+        }
+        if (valid) {
+            float4 o = make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w);
+            if (apply_relu) o = make_float4(relu(o.x), relu(o.y), relu(o.z), relu(o.w));
+            st4(out + (size_t)r * HC + ch, o);
+            if (sl % LPH == 0) st4(stats + ((size_t)r * H + head) * 4, make_float4(m, inv, 0.f, den));
+        }
+        GAT_ROW_ROTATE()
+    }
+}
+
+__device__ __forceinline__ void bwd_a_edge4(const float4& a, const float4& xri, const float4& row, float de, float4& dx, float4& datt) {
+    float s;
+    s = xri.x + row.x; dx.x = fmaf(de * a.x, dlr(s), dx.x); datt.x = fmaf(de, lrelu(s), datt.x);
+    s = xri.y + row.y; dx.y = fmaf(de * a.y, dlr(s), dx.y); datt.y = fmaf(de, lrelu(s), datt.y);
+    s = xri.z + row.z; dx.z = fmaf(de * a.z, dlr(s), dx.z); datt.z = fmaf(de, lrelu(s), datt.z);
+    s = xri.w + row.w; dx.w = fmaf(de * a.w, dlr(s), dx.w); datt.w = fmaf(de, lrelu(s), datt.w);
+}
+
+template <int LPR, int LPH>
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gat_bwd_target4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
+                  const float* __restrict__ att, float* __restrict__ stats, const float* __restrict__ dout,
+                  float* __restrict__ dxr, float* __restrict__ partials) {
+    constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
+    __shared__ float red[GAT_WARPS * RPW][2 * HC];
+    float4 datt = f4zero(), dbias = f4zero();
+    GAT_ROW_LOOP(g.rowptr_t, g.col_t) {
+        GAT_ROW_ADVANCE(g.rowptr_t, g.col_t)
+        const float4 a = ldg4(att + ch);
+        const int r = cur.r, cnt = cur.deg + 1;
+        const bool valid = cnt > 0;
+        const float4 xri = valid ? ldg4(xr + (size_t)r * ld + ch) : f4zero();
+        const float4 doi = valid ? ldg4(dout + (size_t)r * HC + ch) : f4zero();
+        float4 st = valid ? ld4(stats + ((size_t)r * H + head) * 4) : f4zero();
+        float4 dx = f4zero();
+        float D = 0.f;
+        if (warp_max_cnt<LPR>(cnt) <= GAT_FAST) {
+            int js[GAT_FAST];
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
+            float4 rows[GAT_FAST];
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) rows[k] = k < cnt ? ldg4(xl + (size_t)js[k] * ld + ch) : f4zero();
+            float al[GAT_FAST], dal[GAT_FAST];
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) {
+                const float e = hsum<LPH>(score4(a, xri, rows[k]));
+                dal[k] = hsum<LPH>(dot4(doi, rows[k]));
+                al[k] = k < cnt ? qdiv(expf(e - st.x), st.y, st.w) : 0.f;
+            }
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) D = fmaf(al[k], dal[k], D);
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) bwd_a_edge4(a, xri, rows[k], al[k] * (dal[k] - D), dx, datt);
+        } else {
+            const int mc = warp_max_cnt<LPR>(cnt);
+            for (int pass = 0; pass < 2; ++pass)
+                for (int k = 0; k < mc; ++k) {
+                    const bool on = k < cnt;
+                    const int j = on && k < cur.deg ? __ldg(g.col_t + cur.beg + k) + cur.off : r;
+                    const float4 row = on ? ldg4(xl + (size_t)j * ld + ch) : f4zero();
+                    const float e = hsum<LPH>(score4(a, xri, row));
+                    const float dl = hsum<LPH>(dot4(doi, row));
+                    if (!on) continue;
+                    const float alk = qdiv(expf(e - st.x), st.y, st.w);
+                    if (pass == 0) D = fmaf(alk, dl, D);
+                    else bwd_a_edge4(a, xri, row, alk * (dl - D), dx, datt);
+                }
+        }
+        if (valid) {
+            st4(dxr + (size_t)r * ld + ch, dx);
+            if (sl % LPH == 0) stats[((size_t)r * H + head) * 4 + 2] = D;
+            dbias = f4add(dbias, doi);
+        }
+        GAT_ROW_ROTATE()
+    }
+    {
+        const int lane_ = threadIdx.x & 31, slot = (threadIdx.x >> 5) * RPW + lane_ / LPR, c4 = (lane_ % LPR) * 4;
+        st4(&red[slot][c4], datt);
+        st4(&red[slot][HC + c4], dbias);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < 2 * HC; c += GAT_THREADS) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < GAT_WARPS * RPW; ++w) s += red[w][c];
+        partials[(size_t)blockIdx.x * 2 * HC + c] = s;
+    }
+}
+
+template <int LPR, int LPH>
+__global__ void __launch_bounds__(GAT_THREADS)
+k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
+                  const float* __restrict__ att, const float* __restrict__ stats, const float* __restrict__ dout,
+                  float* __restrict__ dxl) {
+    constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
+    GAT_ROW_LOOP(g.rowptr, g.col) {
+        GAT_ROW_ADVANCE(g.rowptr, g.col)
+        const float4 a = ldg4(att + ch);
+        const int r = cur.r, cnt = cur.deg + 1;
+        const bool valid = cnt > 0;
+        const float4 xlj = valid ? ldg4(xl + (size_t)r * ld + ch) : f4zero();
+        float4 dx = f4zero();
+        if (warp_max_cnt<LPR>(cnt) <= GAT_FAST) {
+            int is[GAT_FAST];
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) is[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
+            float4 xrs[GAT_FAST], dos[GAT_FAST], sts[GAT_FAST];
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) {
+                const bool on = k < cnt;
+                xrs[k] = on ? ldg4(xr + (size_t)is[k] * ld + ch) : f4zero();
+                dos[k] = on ? ldg4(dout + (size_t)is[k] * HC + ch) : f4zero();
+                sts[k] = on ? ldg4(stats + ((size_t)is[k] * H + head) * 4) : f4zero();
+            }
+#pragma unroll
+            for (int k = 0; k < GAT_FAST; ++k) {
+                const float e = hsum<LPH>(score4(a, xrs[k], xlj));
+                const float dl = hsum<LPH>(dot4(dos[k], xlj));
+                if (k < cnt) {
+                    const float al = qdiv(expf(e - sts[k].x), sts[k].y, sts[k].w), de = al * (dl - sts[k].z);
+                    dx.x = fmaf(al, dos[k].x, dx.x); dx.x = fmaf(de * a.x, dlr(xrs[k].x + xlj.x), dx.x);
+                    dx.y = fmaf(al, dos[k].y, dx.y); dx.y = fmaf(de * a.y, dlr(xrs[k].y + xlj.y), dx.y);
+                    dx.z = fmaf(al, dos[k].z, dx.z); dx.z = fmaf(de * a.z, dlr(xrs[k].z + xlj.z), dx.z);
+                    dx.w = fmaf(al, dos[k].w, dx.w); dx.w = fmaf(de * a.w, dlr(xrs[k].w + xlj.w), dx.w);
+                }
+            }
+        } else {
+            const int mc = warp_max_cnt<LPR>(cnt);
+            for (int k = 0; k < mc; ++k) {
+                const bool on = k < cnt;
+                const int i = on && k < cur.deg ? __ldg(g.col + cur.beg + k) + cur.off : r;
+                const float4 xri = on ? ldg4(xr + (size_t)i * ld + ch) : f4zero();
+                const float4 doi = on ? ldg4(dout + (size_t)i * HC + ch) : f4zero();
+                const float4 st = on ? ldg4(stats + ((size_t)i * H + head) * 4) : f4zero();
+                const float e = hsum<LPH>(score4(a, xri, xlj));
+                const float dl = hsum<LPH>(dot4(doi, xlj));
+                if (!on) continue;
+                const float al = qdiv(expf(e - st.x), st.y, st.w), de = al * (dl - st.z);
+                dx.x = fmaf(al, doi.x, dx.x); dx.x = fmaf(de * a.x, dlr(xri.x + xlj.x), dx.x);
+                dx.y = fmaf(al, doi.y, dx.y); dx.y = fmaf(de * a.y, dlr(xri.y + xlj.y), dx.y);
+                dx.z = fmaf(al, doi.z, dx.z); dx.z = fmaf(de * a.z, dlr(xri.z + xlj.z), dx.z);
+                dx.w = fmaf(al, doi.w, dx.w); dx.w = fmaf(de * a.w, dlr(xri.w + xlj.w), dx.w);
+            }
+        }
+        if (valid) st4(dxl + (size_t)r * ld + ch, dx);
+        GAT_ROW_ROTATE()
     }
 }
 
@@ -337,6 +608,15 @@ int gat_vec(int H, int C) {
     return 0;
 }
 
+// 0 = generic kernels, else the specialised <LPR,LPH> variant
+int gat_special(int H, int C, int ld) {
+    if (ld % 4 != 0) return 0;
+    if (H * C == 128 && C == 32) return 1;
+    if (H * C == 64 && C == 32) return 2;
+    if (H * C == 64 && C == 16) return 3;
+    return 0;
+}
+
 int gat_check(const s2v_graph_t* g, int H, int C, int ld) {
     if (!g || g->num_nodes < 0 || g->period < 0) return S2V_ERR_BAD_ARG;
     if (g->period == 0 && g->num_nodes > 0 && !g->gid) return S2V_ERR_BAD_ARG;
@@ -347,12 +627,13 @@ int gat_check(const s2v_graph_t* g, int H, int C, int ld) {
     return 0;
 }
 
-int gat_grid(int num_nodes) {
+int gat_grid(int num_nodes, int rows_per_cta) {
     int dev = 0, sms = 148;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    const int want = (num_nodes + GAT_WARPS - 1) / GAT_WARPS;
-    const int cap = sms * 8;                       // 8 CTAs of 256 threads per SM = full occupancy; multiple of the SM count
+    const int want = (num_nodes + rows_per_cta - 1) / rows_per_cta;
+    int cap = sms * 8;                             // 8 CTAs of 256 threads per SM; a multiple of the SM count
+    if (cap > S2V_GAT_MAX_GRID) cap = S2V_GAT_MAX_GRID;
     return want < cap ? (want > 0 ? want : 1) : cap;
 }
 
@@ -364,6 +645,12 @@ int gat_grid(int num_nodes) {
         case 2: { constexpr int V = 2; CALL; break; } \
         default: { constexpr int V = 1; CALL; break; } \
     }
+#define GAT_SPECIAL(SP_, CALL)                                            \
+    switch (SP_) {                                                        \
+        case 1: { constexpr int LPR = 32, LPH = 8; CALL; break; }         \
+        case 2: { constexpr int LPR = 16, LPH = 8; CALL; break; }         \
+        default: { constexpr int LPR = 16, LPH = 4; CALL; break; }        \
+    }
 
 extern "C" int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                                     const float* xl, const float* xr, const float* att, const float* bias,
@@ -371,25 +658,30 @@ extern "C" int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t
     S2V_RETURN_IF(gat_check(g, heads, channels, ld));
     if (!xl || !xr || !att || !bias || !out || !stats) return S2V_ERR_BAD_ARG;
     if (g->num_nodes == 0) return 0;
-    const int grid = gat_grid(g->num_nodes);
-    GAT_DISPATCH(gat_vec(heads, channels),
-                 (k_gat_fwd<V><<<grid, GAT_THREADS, 0, (cudaStream_t)stream>>>(*g, heads, channels, ld, xl, xr, att, bias,
-                                                                                apply_relu, out, stats)));
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sp = gat_special(heads, channels, ld);
+    if (sp) {
+        const int grid = gat_grid(g->num_nodes, GAT_WARPS * (sp == 1 ? 1 : 2));
+        GAT_SPECIAL(sp, (k_gat_fwd4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, bias, apply_relu, out, stats)));
+    } else {
+        const int grid = gat_grid(g->num_nodes, GAT_WARPS);
+        GAT_DISPATCH(gat_vec(heads, channels),
+                     (k_gat_fwd<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, bias, apply_relu, out, stats)));
+    }
     return (int)cudaGetLastError();
 }
 
-extern "C" int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels, int64_t num_nodes) {
-    // per-CTA partials of (datt, dbias) for the largest grid, + D_i per node and head
-    return (int64_t)sizeof(float) * ((int64_t)S2V_GAT_MAX_GRID * 2 * heads * channels + num_nodes * heads);
+extern "C" int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels) {
+    return (int64_t)sizeof(float) * S2V_GAT_MAX_GRID * 2 * heads * channels;   // per-CTA partials of (datt, dbias)
 }
 
 extern "C" int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
-                                     const float* xl, const float* xr, const float* att, const float* stats,
+                                     const float* xl, const float* xr, const float* att, float* stats,
                                      const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
                                      void* workspace, int64_t workspace_bytes, void* stream) {
     S2V_RETURN_IF(gat_check(g, heads, channels, ld));
     if (!xl || !xr || !att || !stats || !dout || !dxl || !dxr || !grad_att || !grad_bias || !workspace) return S2V_ERR_BAD_ARG;
-    if (workspace_bytes < s2v_gat_attn_backward_workspace_bytes(heads, channels, g->num_nodes)) return S2V_ERR_WORKSPACE;
+    if (workspace_bytes < s2v_gat_attn_backward_workspace_bytes(heads, channels)) return S2V_ERR_WORKSPACE;
     const int HC = heads * channels;
     cudaStream_t st = (cudaStream_t)stream;
     if (g->num_nodes == 0) {
@@ -397,17 +689,23 @@ extern "C" int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_
         cudaMemsetAsync(grad_bias, 0, sizeof(float) * HC, st);
         return (int)cudaGetLastError();
     }
-    int grid = gat_grid(g->num_nodes);
-    if (grid > S2V_GAT_MAX_GRID) grid = S2V_GAT_MAX_GRID;
     float* partials = (float*)workspace;
-    float* dsum = partials + (size_t)S2V_GAT_MAX_GRID * 2 * HC;
-    GAT_DISPATCH(gat_vec(heads, channels),
-                 (k_gat_bwd_target<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dxr, dsum, partials)));
+    const int sp = gat_special(heads, channels, ld);
+    int grid;
+    if (sp) {
+        grid = gat_grid(g->num_nodes, GAT_WARPS * (sp == 1 ? 1 : 2));
+        GAT_SPECIAL(sp, (k_gat_bwd_target4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, stats, dout, dxr, partials)));
+        S2V_RETURN_IF(cudaGetLastError());
+        GAT_SPECIAL(sp, (k_gat_bwd_source4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, stats, dout, dxl)));
+    } else {
+        grid = gat_grid(g->num_nodes, GAT_WARPS);
+        GAT_DISPATCH(gat_vec(heads, channels),
+                     (k_gat_bwd_target<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dxr, partials)));
+        S2V_RETURN_IF(cudaGetLastError());
+        GAT_DISPATCH(gat_vec(heads, channels),
+                     (k_gat_bwd_source<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dxl)));
+    }
     S2V_RETURN_IF(cudaGetLastError());
-    GAT_DISPATCH(gat_vec(heads, channels),
-                 (k_gat_bwd_source<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dsum, dxl)));
-    S2V_RETURN_IF(cudaGetLastError());
-    // partials are [grid][datt HC | dbias HC]
     k_gat_reduce<<<(2 * HC + 127) / 128, 128, 0, st>>>(partials, grid, HC, grad_att, grad_bias);
     return (int)cudaGetLastError();
 }

@@ -57,7 +57,7 @@ class _GATConvFn(torch.autograd.Function):
         att_f = ops._f32c(att.detach().reshape(-1), "att")
         bias_f = ops._f32c(bias.detach(), "bias")
         out = torch.empty(n, HC, dtype=torch.float32, device=x.device)
-        stats = torch.empty(n, 2 * heads, dtype=torch.float32, device=x.device)
+        stats = torch.empty(n, heads, 4, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             _lib.check(L.s2v_gat_attn_forward(C.byref(layout.c_struct()), heads, Cc, 2 * HC, _p(xlr),
                                               C.c_void_p(xlr.data_ptr() + 4 * HC), _p(att_f), _p(bias_f), int(relu),
@@ -83,7 +83,7 @@ class _GATConvFn(torch.autograd.Function):
                 dout = masked
             dxlr = torch.empty(n, 2 * HC, dtype=torch.float32, device=x.device)
             gab = torch.empty(2, HC, dtype=torch.float32, device=x.device)
-            ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(heads, Cc, n), dtype=torch.uint8, device=x.device)
+            ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(heads, Cc), dtype=torch.uint8, device=x.device)
             _lib.check(L.s2v_gat_attn_backward(C.byref(layout.c_struct()), heads, Cc, 2 * HC, _p(xlr),
                                                C.c_void_p(xlr.data_ptr() + 4 * HC), _p(att_f), _p(stats), _p(dout),
                                                _p(dxlr), C.c_void_p(dxlr.data_ptr() + 4 * HC), _p(gab[0]), _p(gab[1]),
