@@ -49,7 +49,7 @@ __device__ __forceinline__ Vec<VEC> vzero() { Vec<VEC> r;
     for (int v = 0; v < VEC; ++v) r.v[v] = 0.f;
     return r; }
 
-__device__ __forceinline__ float lrelu(float s) { return s > 0.f ? s : s * GAT_SLOPE; }
+__device__ __forceinline__ float lrelu(float s) { return fmaxf(s, s * GAT_SLOPE); }   // slope < 1
 // ex / den from the stored reciprocal with one Newton step (== the correctly rounded quotient up to the last bit)
 __device__ __forceinline__ float qdiv(float ex, float inv, float den) {
     const float q = ex * inv;
@@ -383,8 +383,35 @@ __device__ __forceinline__ int warp_max_cnt(int cnt) {
     return cnt;
 }
 
+// Register-resident paths for rows with at most NS neighbours (incl. the self edge); NS = 4 or 8 is chosen per warp.
+template <int LPR, int LPH, int NS>
+__device__ __forceinline__ void fwd_fast(const float* __restrict__ xl, int ld, int ch, int jl, int cnt, const float4& a,
+                                         const float4& xri, float4& acc, float& m, float& inv, float& den) {
+    int js[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
+    float4 rows[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) rows[k] = k < cnt ? ldg4(xl + (size_t)js[k] * ld + ch) : f4zero();
+    float sc[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) sc[k] = hsum<LPH>(score4(a, xri, rows[k]));
+#pragma unroll
+    for (int k = 0; k < NS; ++k) if (k < cnt) m = fmaxf(m, sc[k]);
+    float S = 0.f;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) if (k < cnt) { sc[k] = expf(sc[k] - m); S += sc[k]; }
+    den = S + 1e-16f; inv = 1.f / den;
+#pragma unroll
+    for (int k = 0; k < NS; ++k) if (k < cnt) {
+        const float al = qdiv(sc[k], inv, den);
+        acc.x = fmaf(rows[k].x, al, acc.x); acc.y = fmaf(rows[k].y, al, acc.y);
+        acc.z = fmaf(rows[k].z, al, acc.z); acc.w = fmaf(rows[k].w, al, acc.w);
+    }
+}
+
 template <int LPR, int LPH>
-__global__ void __launch_bounds__(GAT_THREADS)
+__global__ void __launch_bounds__(GAT_THREADS, 3)
 k_gat_fwd4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
            const float* __restrict__ att, const float* __restrict__ bias, int apply_relu,
            float* __restrict__ out, float* __restrict__ stats) {
@@ -397,30 +424,10 @@ k_gat_fwd4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const floa
         const float4 xri = valid ? ldg4(xr + (size_t)r * ld + ch) : f4zero();
         float4 acc = f4zero();
         float m = -INFINITY, inv = 0.f, den = 1.f;
-        if (warp_max_cnt<LPR>(cnt) <= GAT_FAST) {
-            int js[GAT_FAST];
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
-            float4 rows[GAT_FAST];
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) rows[k] = k < cnt ? ldg4(xl + (size_t)js[k] * ld + ch) : f4zero();
-            float sc[GAT_FAST];
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) sc[k] = hsum<LPH>(score4(a, xri, rows[k]));
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) m = fmaxf(m, sc[k]);
-            float S = 0.f;
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) { sc[k] = expf(sc[k] - m); S += sc[k]; }
-            den = S + 1e-16f; inv = 1.f / den;
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) {
-                const float al = qdiv(sc[k], inv, den);
-                acc.x = fmaf(rows[k].x, al, acc.x); acc.y = fmaf(rows[k].y, al, acc.y);
-                acc.z = fmaf(rows[k].z, al, acc.z); acc.w = fmaf(rows[k].w, al, acc.w);
-            }
-        } else {
-            const int mc = warp_max_cnt<LPR>(cnt);
+        const int mc = warp_max_cnt<LPR>(cnt);
+        if (mc <= 4) fwd_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, xri, acc, m, inv, den);
+        else if (mc <= GAT_FAST) fwd_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, xri, acc, m, inv, den);
+        else {
             float S = 0.f;
             for (int pass = 0; pass < 3; ++pass) {
                 for (int k = 0; k < mc; ++k) {
@@ -437,7 +444,7 @@ k_gat_fwd4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const floa
                         acc.z = fmaf(row.z, al, acc.z); acc.w = fmaf(row.w, al, acc.w);
                     }
                 }
-                if (pass == 1) den = S + 1e-16f; inv = 1.f / den;
+                if (pass == 1) { den = S + 1e-16f; inv = 1.f / den; }
             }
         }
         if (valid) {
@@ -458,8 +465,31 @@ __device__ __forceinline__ void bwd_a_edge4(const float4& a, const float4& xri, 
     s = xri.w + row.w; dx.w = fmaf(de * a.w, dlr(s), dx.w); datt.w = fmaf(de, lrelu(s), datt.w);
 }
 
+template <int LPR, int LPH, int NS>
+__device__ __forceinline__ void bwd_target_fast(const float* __restrict__ xl, int ld, int ch, int jl, int cnt, const float4& a,
+                                                const float4& xri, const float4& doi, const float4& st, float& D,
+                                                float4& dx, float4& datt) {
+    int js[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
+    float4 rows[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) rows[k] = k < cnt ? ldg4(xl + (size_t)js[k] * ld + ch) : f4zero();
+    float al[NS], dal[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const float e = hsum<LPH>(score4(a, xri, rows[k]));
+        dal[k] = hsum<LPH>(dot4(doi, rows[k]));
+        al[k] = k < cnt ? qdiv(expf(e - st.x), st.y, st.w) : 0.f;
+    }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) if (k < cnt) D = fmaf(al[k], dal[k], D);
+#pragma unroll
+    for (int k = 0; k < NS; ++k) if (k < cnt) bwd_a_edge4(a, xri, rows[k], al[k] * (dal[k] - D), dx, datt);
+}
+
 template <int LPR, int LPH>
-__global__ void __launch_bounds__(GAT_THREADS)
+__global__ void __launch_bounds__(GAT_THREADS, 2)
 k_gat_bwd_target4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
                   const float* __restrict__ att, float* __restrict__ stats, const float* __restrict__ dout,
                   float* __restrict__ dxr, float* __restrict__ partials) {
@@ -473,29 +503,13 @@ k_gat_bwd_target4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
         const bool valid = cnt > 0;
         const float4 xri = valid ? ldg4(xr + (size_t)r * ld + ch) : f4zero();
         const float4 doi = valid ? ldg4(dout + (size_t)r * HC + ch) : f4zero();
-        float4 st = valid ? ld4(stats + ((size_t)r * H + head) * 4) : f4zero();
+        const float4 st = valid ? ld4(stats + ((size_t)r * H + head) * 4) : f4zero();
         float4 dx = f4zero();
         float D = 0.f;
-        if (warp_max_cnt<LPR>(cnt) <= GAT_FAST) {
-            int js[GAT_FAST];
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
-            float4 rows[GAT_FAST];
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) rows[k] = k < cnt ? ldg4(xl + (size_t)js[k] * ld + ch) : f4zero();
-            float al[GAT_FAST], dal[GAT_FAST];
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) {
-                const float e = hsum<LPH>(score4(a, xri, rows[k]));
-                dal[k] = hsum<LPH>(dot4(doi, rows[k]));
-                al[k] = k < cnt ? qdiv(expf(e - st.x), st.y, st.w) : 0.f;
-            }
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) D = fmaf(al[k], dal[k], D);
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) if (k < cnt) bwd_a_edge4(a, xri, rows[k], al[k] * (dal[k] - D), dx, datt);
-        } else {
-            const int mc = warp_max_cnt<LPR>(cnt);
+        const int mc = warp_max_cnt<LPR>(cnt);
+        if (mc <= 4) bwd_target_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, xri, doi, st, D, dx, datt);
+        else if (mc <= GAT_FAST) bwd_target_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, xri, doi, st, D, dx, datt);
+        else {
             for (int pass = 0; pass < 2; ++pass)
                 for (int k = 0; k < mc; ++k) {
                     const bool on = k < cnt;
@@ -530,8 +544,43 @@ k_gat_bwd_target4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
     }
 }
 
+__device__ __forceinline__ void bwd_b_edge4(const float4& a, const float4& xlj, const float4& xri, const float4& doi,
+                                            float al, float de, float4& dx) {
+    dx.x = fmaf(al, doi.x, dx.x); dx.x = fmaf(de * a.x, dlr(xri.x + xlj.x), dx.x);
+    dx.y = fmaf(al, doi.y, dx.y); dx.y = fmaf(de * a.y, dlr(xri.y + xlj.y), dx.y);
+    dx.z = fmaf(al, doi.z, dx.z); dx.z = fmaf(de * a.z, dlr(xri.z + xlj.z), dx.z);
+    dx.w = fmaf(al, doi.w, dx.w); dx.w = fmaf(de * a.w, dlr(xri.w + xlj.w), dx.w);
+}
+
+template <int LPR, int LPH, int NS>
+__device__ __forceinline__ void bwd_source_fast(const float* __restrict__ xr, const float* __restrict__ dout,
+                                                const float* __restrict__ stats, int ld, int ch, int head, int il, int cnt,
+                                                const float4& a, const float4& xlj, float4& dx) {
+    constexpr int HC = 4 * LPR, H = LPR / LPH;
+    int is[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) is[k] = __shfl_sync(0xffffffffu, il, k, LPR);
+    float4 xrs[NS], dos[NS], sts[NS];
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const bool on = k < cnt;
+        xrs[k] = on ? ldg4(xr + (size_t)is[k] * ld + ch) : f4zero();
+        dos[k] = on ? ldg4(dout + (size_t)is[k] * HC + ch) : f4zero();
+        sts[k] = on ? ldg4(stats + ((size_t)is[k] * H + head) * 4) : f4zero();
+    }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) {
+        const float e = hsum<LPH>(score4(a, xrs[k], xlj));
+        const float dl = hsum<LPH>(dot4(dos[k], xlj));
+        if (k < cnt) {
+            const float al = qdiv(expf(e - sts[k].x), sts[k].y, sts[k].w);
+            bwd_b_edge4(a, xlj, xrs[k], dos[k], al, al * (dl - sts[k].z), dx);
+        }
+    }
+}
+
 template <int LPR, int LPH>
-__global__ void __launch_bounds__(GAT_THREADS)
+__global__ void __launch_bounds__(GAT_THREADS, 2)
 k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
                   const float* __restrict__ att, const float* __restrict__ stats, const float* __restrict__ dout,
                   float* __restrict__ dxl) {
@@ -543,32 +592,10 @@ k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
         const bool valid = cnt > 0;
         const float4 xlj = valid ? ldg4(xl + (size_t)r * ld + ch) : f4zero();
         float4 dx = f4zero();
-        if (warp_max_cnt<LPR>(cnt) <= GAT_FAST) {
-            int is[GAT_FAST];
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) is[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
-            float4 xrs[GAT_FAST], dos[GAT_FAST], sts[GAT_FAST];
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) {
-                const bool on = k < cnt;
-                xrs[k] = on ? ldg4(xr + (size_t)is[k] * ld + ch) : f4zero();
-                dos[k] = on ? ldg4(dout + (size_t)is[k] * HC + ch) : f4zero();
-                sts[k] = on ? ldg4(stats + ((size_t)is[k] * H + head) * 4) : f4zero();
-            }
-#pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) {
-                const float e = hsum<LPH>(score4(a, xrs[k], xlj));
-                const float dl = hsum<LPH>(dot4(dos[k], xlj));
-                if (k < cnt) {
-                    const float al = qdiv(expf(e - sts[k].x), sts[k].y, sts[k].w), de = al * (dl - sts[k].z);
-                    dx.x = fmaf(al, dos[k].x, dx.x); dx.x = fmaf(de * a.x, dlr(xrs[k].x + xlj.x), dx.x);
-                    dx.y = fmaf(al, dos[k].y, dx.y); dx.y = fmaf(de * a.y, dlr(xrs[k].y + xlj.y), dx.y);
-                    dx.z = fmaf(al, dos[k].z, dx.z); dx.z = fmaf(de * a.z, dlr(xrs[k].z + xlj.z), dx.z);
-                    dx.w = fmaf(al, dos[k].w, dx.w); dx.w = fmaf(de * a.w, dlr(xrs[k].w + xlj.w), dx.w);
-                }
-            }
-        } else {
-            const int mc = warp_max_cnt<LPR>(cnt);
+        const int mc = warp_max_cnt<LPR>(cnt);
+        if (mc <= 4) bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, a, xlj, dx);
+        else if (mc <= GAT_FAST) bwd_source_fast<LPR, LPH, GAT_FAST>(xr, dout, stats, ld, ch, head, jl, cnt, a, xlj, dx);
+        else {
             for (int k = 0; k < mc; ++k) {
                 const bool on = k < cnt;
                 const int i = on && k < cur.deg ? __ldg(g.col + cur.beg + k) + cur.off : r;
@@ -578,11 +605,8 @@ k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
                 const float e = hsum<LPH>(score4(a, xri, xlj));
                 const float dl = hsum<LPH>(dot4(doi, xlj));
                 if (!on) continue;
-                const float al = qdiv(expf(e - st.x), st.y, st.w), de = al * (dl - st.z);
-                dx.x = fmaf(al, doi.x, dx.x); dx.x = fmaf(de * a.x, dlr(xri.x + xlj.x), dx.x);
-                dx.y = fmaf(al, doi.y, dx.y); dx.y = fmaf(de * a.y, dlr(xri.y + xlj.y), dx.y);
-                dx.z = fmaf(al, doi.z, dx.z); dx.z = fmaf(de * a.z, dlr(xri.z + xlj.z), dx.z);
-                dx.w = fmaf(al, doi.w, dx.w); dx.w = fmaf(de * a.w, dlr(xri.w + xlj.w), dx.w);
+                const float al = qdiv(expf(e - st.x), st.y, st.w);
+                bwd_b_edge4(a, xlj, xri, doi, al, al * (dl - st.z), dx);
             }
         }
         if (valid) st4(dxl + (size_t)r * ld + ch, dx);
@@ -590,14 +614,22 @@ k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
     }
 }
 
-// grad_att[c] / grad_bias[c] = sum over CTAs of partials[b][c] / partials[b][HC + c], fixed order
-__global__ void k_gat_reduce(const float* __restrict__ partials, int nblocks, int HC, float* __restrict__ grad_att,
-                             float* __restrict__ grad_bias) {
-    const int c = blockIdx.x * blockDim.x + threadIdx.x;
-    if (c >= 2 * HC) return;
+// grad_att[c] / grad_bias[c] = sum over CTAs of partials[b][c] / partials[b][HC + c]; one CTA per column, fixed
+// per-thread strides and a fixed shared-memory tree => bit-stable
+__global__ void __launch_bounds__(128)
+k_gat_reduce(const float* __restrict__ partials, int nblocks, int HC, float* __restrict__ grad_att,
+             float* __restrict__ grad_bias) {
+    __shared__ float red[128];
+    const int c = blockIdx.x;
     float s = 0.f;
-    for (int b = 0; b < nblocks; ++b) s += partials[(size_t)b * 2 * HC + c];
-    if (c < HC) grad_att[c] = s; else grad_bias[c - HC] = s;
+    for (int b = threadIdx.x; b < nblocks; b += 128) s += partials[(size_t)b * 2 * HC + c];
+    red[threadIdx.x] = s;
+    __syncthreads();
+    for (int o = 64; o > 0; o >>= 1) {
+        if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { if (c < HC) grad_att[c] = red[0]; else grad_bias[c - HC] = red[0]; }
 }
 
 int gat_vec(int H, int C) {
@@ -706,6 +738,6 @@ extern "C" int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_
                      (k_gat_bwd_source<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dxl)));
     }
     S2V_RETURN_IF(cudaGetLastError());
-    k_gat_reduce<<<(2 * HC + 127) / 128, 128, 0, st>>>(partials, grid, HC, grad_att, grad_bias);
+    k_gat_reduce<<<2 * HC, 128, 0, st>>>(partials, grid, HC, grad_att, grad_bias);
     return (int)cudaGetLastError();
 }
