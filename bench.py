@@ -528,7 +528,7 @@ def run_gat(args):
     xlr = torch.randn(n, 2 * HC, device=dev)
     att, bias = torch.randn(HC, device=dev) * 0.1, torch.randn(HC, device=dev) * 0.1
     out, stats = torch.empty(n, HC, device=dev), torch.empty(n, H, 4, device=dev)
-    dout, dxlr, gab = torch.randn(n, HC, device=dev), torch.empty(n, 2 * HC, device=dev), torch.empty(2, HC, device=dev)
+    dout, dxlr, gab = torch.randn(n, HC, device=dev), torch.empty(n, 2 * HC, device=dev), torch.empty(4, HC, device=dev)
     ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(H, Cc), dtype=torch.uint8, device=dev)
     g = layout.c_struct()
     xr_p, dxr_p = C.c_void_p(xlr.data_ptr() + 4 * HC), C.c_void_p(dxlr.data_ptr() + 4 * HC)
@@ -539,7 +539,7 @@ def run_gat(args):
 
     def k_bwd():
         _lib.check(L.s2v_gat_attn_backward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(stats), _p(dout), _p(dxlr),
-                                           dxr_p, _p(gab[0]), _p(gab[1]), _p(ws), ws.numel(), _stream()), "gat bwd")
+                                           dxr_p, _p(gab[0]), _p(gab[1]), _p(gab[2]), _p(ws), ws.numel(), _stream()), "gat bwd")
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
     # forward: (dbar+1) x_l rows + x_r row read, out row written, ids + rowptr, stats written

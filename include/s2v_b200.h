@@ -229,7 +229,8 @@ int s2v_scatter_rows(const s2v_graph_t* g, const int64_t* arg, const float* dval
  *   stats    [num_nodes, H, 4] out: per target and head (max score, 1 / den, D, den = softmax denominator + 1e-16);
  *            the backward writes D = sum_j a_ij da_ij into the third slot
  * Backward: dout [num_nodes, H*C] (already multiplied by the ReLU mask when the layer had one)
- *   -> dxl, dxr (row stride ld), grad_att [H*C], grad_bias [H*C] (overwritten; fixed-order sums).
+ *   -> dxl, dxr (row stride ld), grad_att [H*C], grad_bias [H*C], grad_lin_bias [2*H*C] = column sums of
+ *      dxl | dxr, i.e. the gradients of lin_l.bias | lin_r.bias (all overwritten; fixed-order sums).
  * --------------------------------------------------------------------------------- */
 #define S2V_GAT_MAX_GRID 2048
 int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
@@ -239,7 +240,7 @@ int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels);
 int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                           const float* xl, const float* xr, const float* att, float* stats,
                           const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
-                          void* workspace, int64_t workspace_bytes, void* stream);
+                          float* grad_lin_bias, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus
 }

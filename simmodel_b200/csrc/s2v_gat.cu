@@ -178,14 +178,14 @@ __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
                  const float* __restrict__ att, float* __restrict__ stats, const float* __restrict__ dout,
                  float* __restrict__ dxr, float* __restrict__ partials) {
-    __shared__ float red[GAT_WARPS][2 * 128];
+    __shared__ float red[GAT_WARPS][3 * 128];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int HC = H * C, lanes = HC / VEC, lph = C / VEC;
     const bool active = lane < lanes;
     const int ch = active ? lane * VEC : 0;
     const int head = ch / C;
     const Vec<VEC> a = ldv<VEC>(att + ch);
-    Vec<VEC> datt = vzero<VEC>(), dbias = vzero<VEC>();
+    Vec<VEC> datt = vzero<VEC>(), dbias = vzero<VEC>(), dbr = vzero<VEC>();
     const int warp = blockIdx.x * GAT_WARPS + wid, nwarps = gridDim.x * GAT_WARPS;
     for (int r = warp; r < g.num_nodes; r += nwarps) {
         int li, off, gi;
@@ -235,21 +235,21 @@ k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restr
             stv<VEC>(dxr + (size_t)r * ld + ch, dx);
             if (lane % lph == 0) stats[((size_t)r * H + head) * 4 + 2] = D;
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) dbias.v[v] += doi.v[v];
+            for (int v = 0; v < VEC; ++v) { dbias.v[v] += doi.v[v]; dbr.v[v] += dx.v[v]; }
         }
     }
     // per-CTA partial sums, fixed order over warps
     if (active) {
 #pragma unroll
-        for (int v = 0; v < VEC; ++v) { red[wid][ch + v] = datt.v[v]; red[wid][128 + ch + v] = dbias.v[v]; }
+        for (int v = 0; v < VEC; ++v) { red[wid][ch + v] = datt.v[v]; red[wid][128 + ch + v] = dbias.v[v]; red[wid][256 + ch + v] = dbr.v[v]; }
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * HC; c += GAT_THREADS) {
-        const int idx = c < HC ? c : 128 + (c - HC);
+    for (int c = threadIdx.x; c < 3 * HC; c += GAT_THREADS) {
+        const int idx = 128 * (c / HC) + c % HC;
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < GAT_WARPS; ++w) s += red[w][idx];
-        partials[(size_t)blockIdx.x * 2 * HC + c] = s;
+        partials[(size_t)blockIdx.x * 4 * HC + c] = s;
     }
 }
 
@@ -272,7 +272,9 @@ template <int VEC>
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_source(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
                  const float* __restrict__ att, const float* __restrict__ stats, const float* __restrict__ dout,
-                 float* __restrict__ dxl) {
+                 float* __restrict__ dxl, float* __restrict__ partials) {
+    __shared__ float red[GAT_WARPS][128];
+    Vec<VEC> dbl = vzero<VEC>();
     const int lane = threadIdx.x & 31;
     const int HC = H * C, lanes = HC / VEC, lph = C / VEC;
     const bool active = lane < lanes;
@@ -317,7 +319,22 @@ k_gat_bwd_source(const s2v_graph_t g, int H, int C, int ld, const float* __restr
                 bwd_b_edge<VEC>(a, xlj, xri, doi, qdiv(expf(e - st.x), st.y, st.w), dl, st.z, dx);
             }
         }
-        if (active) stv<VEC>(dxl + (size_t)r * ld + ch, dx);
+        if (active) {
+            stv<VEC>(dxl + (size_t)r * ld + ch, dx);
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) dbl.v[v] += dx.v[v];
+        }
+    }
+    if (active) {
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) red[threadIdx.x >> 5][ch + v] = dbl.v[v];
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < HC; c += GAT_THREADS) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < GAT_WARPS; ++w) s += red[w][c];
+        partials[(size_t)blockIdx.x * 4 * HC + 3 * HC + c] = s;
     }
 }
 
@@ -494,8 +511,8 @@ k_gat_bwd_target4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
                   const float* __restrict__ att, float* __restrict__ stats, const float* __restrict__ dout,
                   float* __restrict__ dxr, float* __restrict__ partials) {
     constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
-    __shared__ float red[GAT_WARPS * RPW][2 * HC];
-    float4 datt = f4zero(), dbias = f4zero();
+    __shared__ float red[GAT_WARPS * RPW][3 * HC];
+    float4 datt = f4zero(), dbias = f4zero(), dbr = f4zero();
     GAT_ROW_LOOP(g.rowptr_t, g.col_t) {
         GAT_ROW_ADVANCE(g.rowptr_t, g.col_t)
         const float4 a = ldg4(att + ch);
@@ -527,6 +544,7 @@ k_gat_bwd_target4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
             st4(dxr + (size_t)r * ld + ch, dx);
             if (sl % LPH == 0) stats[((size_t)r * H + head) * 4 + 2] = D;
             dbias = f4add(dbias, doi);
+            dbr = f4add(dbr, dx);
         }
         GAT_ROW_ROTATE()
     }
@@ -534,13 +552,14 @@ k_gat_bwd_target4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
         const int lane_ = threadIdx.x & 31, slot = (threadIdx.x >> 5) * RPW + lane_ / LPR, c4 = (lane_ % LPR) * 4;
         st4(&red[slot][c4], datt);
         st4(&red[slot][HC + c4], dbias);
+        st4(&red[slot][2 * HC + c4], dbr);
     }
     __syncthreads();
-    for (int c = threadIdx.x; c < 2 * HC; c += GAT_THREADS) {
+    for (int c = threadIdx.x; c < 3 * HC; c += GAT_THREADS) {
         float s = 0.f;
 #pragma unroll
         for (int w = 0; w < GAT_WARPS * RPW; ++w) s += red[w][c];
-        partials[(size_t)blockIdx.x * 2 * HC + c] = s;
+        partials[(size_t)blockIdx.x * 4 * HC + c] = s;
     }
 }
 
@@ -555,11 +574,12 @@ __device__ __forceinline__ void bwd_b_edge4(const float4& a, const float4& xlj, 
 template <int LPR, int LPH, int NS>
 __device__ __forceinline__ void bwd_source_fast(const float* __restrict__ xr, const float* __restrict__ dout,
                                                 const float* __restrict__ stats, int ld, int ch, int head, int il, int cnt,
-                                                const float4& a, const float4& xlj, float4& dx) {
+                                                int k0, const float4& a, const float4& xlj, float4& dx) {
     constexpr int HC = 4 * LPR, H = LPR / LPH;
     int is[NS];
 #pragma unroll
-    for (int k = 0; k < NS; ++k) is[k] = __shfl_sync(0xffffffffu, il, k, LPR);
+    for (int k = 0; k < NS; ++k) is[k] = __shfl_sync(0xffffffffu, il, k0 + k, LPR);
+    cnt -= k0;
     float4 xrs[NS], dos[NS], sts[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
@@ -583,8 +603,10 @@ template <int LPR, int LPH>
 __global__ void __launch_bounds__(GAT_THREADS, 2)
 k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
                   const float* __restrict__ att, const float* __restrict__ stats, const float* __restrict__ dout,
-                  float* __restrict__ dxl) {
+                  float* __restrict__ dxl, float* __restrict__ partials) {
     constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
+    __shared__ float red[GAT_WARPS * RPW][HC];
+    float4 dbl = f4zero();
     GAT_ROW_LOOP(g.rowptr, g.col) {
         GAT_ROW_ADVANCE(g.rowptr, g.col)
         const float4 a = ldg4(att + ch);
@@ -593,9 +615,10 @@ k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
         const float4 xlj = valid ? ldg4(xl + (size_t)r * ld + ch) : f4zero();
         float4 dx = f4zero();
         const int mc = warp_max_cnt<LPR>(cnt);
-        if (mc <= 4) bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, a, xlj, dx);
-        else if (mc <= GAT_FAST) bwd_source_fast<LPR, LPH, GAT_FAST>(xr, dout, stats, ld, ch, head, jl, cnt, a, xlj, dx);
-        else {
+        if (mc <= GAT_FAST) {             // the edges of a source are independent: batches of four keep the registers low
+            bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, 0, a, xlj, dx);
+            if (mc > 4) bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, 4, a, xlj, dx);
+        } else {
             for (int k = 0; k < mc; ++k) {
                 const bool on = k < cnt;
                 const int i = on && k < cur.deg ? __ldg(g.col + cur.beg + k) + cur.off : r;
@@ -609,27 +632,43 @@ k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, con
                 bwd_b_edge4(a, xlj, xri, doi, al, al * (dl - st.z), dx);
             }
         }
-        if (valid) st4(dxl + (size_t)r * ld + ch, dx);
+        if (valid) { st4(dxl + (size_t)r * ld + ch, dx); dbl = f4add(dbl, dx); }
         GAT_ROW_ROTATE()
+    }
+    {
+        const int lane_ = threadIdx.x & 31;
+        st4(&red[(threadIdx.x >> 5) * RPW + lane_ / LPR][(lane_ % LPR) * 4], dbl);
+    }
+    __syncthreads();
+    for (int c = threadIdx.x; c < HC; c += GAT_THREADS) {
+        float s = 0.f;
+#pragma unroll
+        for (int w = 0; w < GAT_WARPS * RPW; ++w) s += red[w][c];
+        partials[(size_t)blockIdx.x * 4 * HC + 3 * HC + c] = s;
     }
 }
 
-// grad_att[c] / grad_bias[c] = sum over CTAs of partials[b][c] / partials[b][HC + c]; one CTA per column, fixed
-// per-thread strides and a fixed shared-memory tree => bit-stable
+// Column sums of the per-CTA partials [grid][datt | dbias | sum dx_r | sum dx_l]; one CTA per column, fixed per-thread
+// strides and a fixed shared-memory tree => bit-stable.  grad_lin_bias = [sum dx_l | sum dx_r] (lin_l.bias | lin_r.bias).
 __global__ void __launch_bounds__(128)
 k_gat_reduce(const float* __restrict__ partials, int nblocks, int HC, float* __restrict__ grad_att,
-             float* __restrict__ grad_bias) {
+             float* __restrict__ grad_bias, float* __restrict__ grad_lin_bias) {
     __shared__ float red[128];
     const int c = blockIdx.x;
     float s = 0.f;
-    for (int b = threadIdx.x; b < nblocks; b += 128) s += partials[(size_t)b * 2 * HC + c];
+    for (int b = threadIdx.x; b < nblocks; b += 128) s += partials[(size_t)b * 4 * HC + c];
     red[threadIdx.x] = s;
     __syncthreads();
     for (int o = 64; o > 0; o >>= 1) {
         if (threadIdx.x < o) red[threadIdx.x] += red[threadIdx.x + o];
         __syncthreads();
     }
-    if (threadIdx.x == 0) { if (c < HC) grad_att[c] = red[0]; else grad_bias[c - HC] = red[0]; }
+    if (threadIdx.x == 0) {
+        if (c < HC) grad_att[c] = red[0];
+        else if (c < 2 * HC) grad_bias[c - HC] = red[0];
+        else if (c < 3 * HC) grad_lin_bias[HC + (c - 2 * HC)] = red[0];
+        else grad_lin_bias[c - 3 * HC] = red[0];
+    }
 }
 
 int gat_vec(int H, int C) {
@@ -704,21 +743,22 @@ extern "C" int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t
 }
 
 extern "C" int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels) {
-    return (int64_t)sizeof(float) * S2V_GAT_MAX_GRID * 2 * heads * channels;   // per-CTA partials of (datt, dbias)
+    return (int64_t)sizeof(float) * S2V_GAT_MAX_GRID * 4 * heads * channels;   // per-CTA partials (datt, dbias, sum dx_r, sum dx_l)
 }
 
 extern "C" int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                                      const float* xl, const float* xr, const float* att, float* stats,
                                      const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
-                                     void* workspace, int64_t workspace_bytes, void* stream) {
+                                     float* grad_lin_bias, void* workspace, int64_t workspace_bytes, void* stream) {
     S2V_RETURN_IF(gat_check(g, heads, channels, ld));
-    if (!xl || !xr || !att || !stats || !dout || !dxl || !dxr || !grad_att || !grad_bias || !workspace) return S2V_ERR_BAD_ARG;
+    if (!xl || !xr || !att || !stats || !dout || !dxl || !dxr || !grad_att || !grad_bias || !grad_lin_bias || !workspace) return S2V_ERR_BAD_ARG;
     if (workspace_bytes < s2v_gat_attn_backward_workspace_bytes(heads, channels)) return S2V_ERR_WORKSPACE;
     const int HC = heads * channels;
     cudaStream_t st = (cudaStream_t)stream;
     if (g->num_nodes == 0) {
         cudaMemsetAsync(grad_att, 0, sizeof(float) * HC, st);
         cudaMemsetAsync(grad_bias, 0, sizeof(float) * HC, st);
+        cudaMemsetAsync(grad_lin_bias, 0, sizeof(float) * 2 * HC, st);
         return (int)cudaGetLastError();
     }
     float* partials = (float*)workspace;
@@ -728,16 +768,16 @@ extern "C" int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_
         grid = gat_grid(g->num_nodes, GAT_WARPS * (sp == 1 ? 1 : 2));
         GAT_SPECIAL(sp, (k_gat_bwd_target4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, stats, dout, dxr, partials)));
         S2V_RETURN_IF(cudaGetLastError());
-        GAT_SPECIAL(sp, (k_gat_bwd_source4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, stats, dout, dxl)));
+        GAT_SPECIAL(sp, (k_gat_bwd_source4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, stats, dout, dxl, partials)));
     } else {
         grid = gat_grid(g->num_nodes, GAT_WARPS);
         GAT_DISPATCH(gat_vec(heads, channels),
                      (k_gat_bwd_target<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dxr, partials)));
         S2V_RETURN_IF(cudaGetLastError());
         GAT_DISPATCH(gat_vec(heads, channels),
-                     (k_gat_bwd_source<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dxl)));
+                     (k_gat_bwd_source<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dxl, partials)));
     }
     S2V_RETURN_IF(cudaGetLastError());
-    k_gat_reduce<<<2 * HC, 128, 0, st>>>(partials, grid, HC, grad_att, grad_bias);
+    k_gat_reduce<<<4 * HC, 128, 0, st>>>(partials, grid, HC, grad_att, grad_bias, grad_lin_bias);
     return (int)cudaGetLastError();
 }
