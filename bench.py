@@ -50,6 +50,15 @@ def parse():
                          "NWB_ROT = BASELINE configs[4] scale sweep)")
     ap.add_argument("--qnet", default="s2v", choices=["s2v", "gat2"],
                     help="s2v = the headline path; gat2 = the GATv2 branch (SURVEY.md 8f-1: QNet_GATv2 train step)")
+    ap.add_argument("--workload", default="dqn", choices=["dqn", "ppo"],
+                    help="dqn = the headline GNN-DQN train step; ppo = one PPO epoch over --batch rollouts of --ppo-steps "
+                         "steps per GPU (BASELINE configs[3]: PPO-GNN-LSTM on NWB_AMS, lstm EMB 64, critic q)")
+    ap.add_argument("--ppo-steps", type=int, default=50)
+    ap.add_argument("--ppo-lstm", default="EMB", choices=["EMB", "None"],
+                    help="lstm_type of the PPO model (EMB = configs[3]; None isolates the GNN + heads from the cuDNN LSTM)")
+    ap.add_argument("--ppo-batched", action="store_true",
+                    help="ppo workload through PPO_GNN_Single_LSTM.evaluate_rollouts (all rollouts of the rank in one GNN "
+                         "pass, s' embedded once) instead of the reference's per-rollout v(s'), v(s), pi(s) calls")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -458,17 +467,23 @@ def run_gat(args):
     GEMMs are cuBLAS (library) and reported as their share of the step."""
     import ctypes as C
     import torch
+    import torch.distributed as dist
     import simmodel_b200 as sb
     from simmodel_b200 import _lib
+    from simmodel_b200.dist import allreduce_gradients
     from simmodel_b200.layout import _p, _stream
     if not torch.cuda.is_available():
         raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
     dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
     torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
     L = _lib.lib()
     topo = sb.graphs.load_topology(TOPO)
     N, B = topo.num_nodes, args.batch
-    gen = torch.Generator().manual_seed(1000)
+    gen = torch.Generator().manual_seed(1000 + rank)
     x_host = sb.graphs.synth_nfm(topo, B, gen).reshape(-1, F).contiguous().pin_memory()
     ei_host = sb.graphs.batch_edge_index(topo, B).contiguous().pin_memory()
     ptr = (torch.arange(B + 1, dtype=torch.int64) * N).to(dev)
@@ -477,6 +492,7 @@ def run_gat(args):
     torch.manual_seed(0)
     net = sb.QNet_GATv2({"emb_dim": P, "emb_iter_T": T, "norm_agg": True, "node_dim": F}, verbose=False).to(dev)
     opt = torch.optim.Adam(net.parameters(), lr=1e-4)
+    params = list(net.parameters())
     loss_fn = torch.nn.SmoothL1Loss()
     x = x_host.to(dev)
     sel = actions_host.to(dev) + ptr[:-1]
@@ -487,6 +503,8 @@ def run_gat(args):
         opt.zero_grad(set_to_none=True)
         loss = loss_fn(net.forward_graph(x, layout)[sel], targets)
         loss.backward()
+        if world > 1:
+            allreduce_gradients(params, B, B * world)
         opt.step()
         return loss
 
@@ -497,12 +515,16 @@ def run_gat(args):
         loss = loss_fn(net.forward_graph(xb, lay)[actions_host.to(dev, non_blocking=True) + ptr[:-1]],
                        targets_host.to(dev, non_blocking=True))
         loss.backward()
+        if world > 1:
+            allreduce_gradients(params, B, B * world)
         opt.step()
-        return float(loss)                      # D2H read of the step's result
+        return float(loss.detach())             # D2H read of the step's result
 
     def timed(fn, steps, warmup):
         for _ in range(warmup):
             fn()
+        if world > 1:
+            dist.barrier()
         torch.cuda.synchronize()
         e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0.record()
@@ -510,7 +532,11 @@ def run_gat(args):
             fn()
         e1.record()
         torch.cuda.synchronize()
-        return e0.elapsed_time(e1) / steps
+        ms_t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms_t.item())
     for _ in range(args.warmup):
         step()
     c0 = _lib.launch_count
@@ -562,7 +588,7 @@ def run_gat(args):
                 "edge_kernels_share_of_step": edge_ms / ms,
                 "note": "lin_l/lin_r GEMMs (fp32 cuBLAS, library) and torch reductions make up the rest of the step"}
     cpu_baseline = None
-    if not args.no_cpu_baseline:
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import gat_ref as G
         cores = os.cpu_count() or 1
         torch.set_num_threads(cores)
@@ -583,18 +609,182 @@ def run_gat(args):
                         "sample": "oracle/gat_ref.py (PyG GATv2Conv restated, torch CPU), fwd+bwd, B=%d graphs per step, %d steps"
                                   % (b0, len(times))}
     n_t, e_t = TOPO_SHAPES[TOPO]
-    line = {"metric": "gat2_fwd_bwd_graphs_per_sec_N%d" % n_t, "value": B / (ms / 1e3), "unit": UNIT, "n_gpus": 1,
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    line = {"metric": "gat2_fwd_bwd_graphs_per_sec_N%d" % n_t, "value": B * world / (ms / 1e3), "unit": UNIT, "n_gpus": world,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
             "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": "QNet_GATv2 GNN-DQN train step on %s (N=%d, E=%d, F=7, emb 64, 5 GATv2Conv layers, heads 2)"
-                                   % (TOPO, n_t, e_t), "graphs_per_gpu": B, "global_batch": B, "nodes_per_graph": n_t,
-                       "parallelism": "dp1", "l2": "inputs exceed L2: every activation plane %.2f GB" % (B * n_t * P * 4 / 1e9)},
+                                   % (TOPO, n_t, e_t), "graphs_per_gpu": B, "global_batch": B * world, "nodes_per_graph": n_t,
+                       "parallelism": "dp%d" % world, "l2": "inputs exceed L2: every activation plane %.2f GB" % (B * n_t * P * 4 / 1e9)},
             "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
             "e2e": None if e2e_ms is None else {
-                "value": B / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
+                "value": B * world / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 8 + actions_host.numel() * 8 + targets_host.numel() * 4,
                 "d2h_bytes_per_step": 4},
             "roofline": roofline, "kernels": kernels, "cpu_baseline": cpu_baseline}
+    print(json.dumps(line), flush=True)
+
+
+# --------------------------------------------------------------------------------------
+# PPO workload (--workload ppo): one PPO epoch of the reference's train_net over R rollouts per GPU
+# --------------------------------------------------------------------------------------
+def run_ppo(args):
+    """BASELINE configs[3]: PPO-GNN-LSTM (lstm_type EMB, lstm_hdim 64, critic q) on NWB_AMS, R = --batch rollouts of
+    S = --ppo-steps steps per GPU (whole rollouts per rank).  One step = one epoch of
+    models_basic_lstm.py:595-652: per rollout v(s'), v(s), pi(s) through the public pi()/v() (three embedding passes,
+    the reference's call pattern), clipped-surrogate + SmoothL1 loss, mean over all steps of all rollouts, backward,
+    (all-reduce), Adam.  --qnet selects the s2v or the GATv2 embedding.  Metric unit: rollout steps (graphs) per second."""
+    import types
+    import torch
+    import torch.distributed as dist
+    import torch.nn.functional as Fn
+    import simmodel_b200 as sb
+    from simmodel_b200 import _lib
+    from simmodel_b200.dist import allreduce_gradients
+    world, rank = int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py (impl b200) needs a CUDA device; there is no CPU fallback")
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", device_id=dev)
+    _lib.lib()
+    topo = sb.graphs.load_topology(TOPO)
+    N, R, S = topo.num_nodes, args.batch, args.ppo_steps
+    config = {"lstm_type": args.ppo_lstm, "qnet": args.qnet, "critic": "q", "emb_dim": P, "emb_iterT": T, "gat_concat": True,
+              "gat_heads": 4, "gat_share_weights": False}
+    hp = types.SimpleNamespace(node_dim=F, emb_dim=P, parallel_rollouts=R, batch_size=1, learning_rate=1e-4,
+                               discount=0.99, gae_lambda=0.95, ppo_clip=0.2)
+    torch.manual_seed(0)
+    model = sb.PPO_GNN_Single_LSTM(config, hp, {"base_checkpoint_path": None}, device=dev)
+    params = list(model.parameters())
+    gen = torch.Generator().manual_seed(2000 + rank)
+    ei = topo.edge_index.to(dev)
+    host = []
+    for _ in range(R):                                  # a rollout: S consecutive observations of one episode
+        nfm = sb.graphs.synth_nfm(topo, S + 1, gen)
+        reach = torch.zeros(S + 1, N, dtype=torch.bool)
+        cur = nfm[:, :, 1].argmax(dim=1)
+        for t in range(S + 1):
+            reach[t, topo.neighbors(int(cur[t])) or [int(cur[t])]] = True
+        a = torch.stack([reach[t].nonzero()[0] for t in range(S)])                   # a reachable action per step
+        host.append(dict(nfm=nfm.pin_memory(), reach=reach.pin_memory(), a=a.pin_memory(),
+                         r=torch.randn(S, 1, generator=gen).pin_memory(), prob_a=(torch.rand(S, 1, generator=gen) * 0.5 + 0.25).pin_memory(),
+                         done=torch.ones(S, 1).pin_memory()))
+    h2d = sum(v.numel() * v.element_size() for v in host[0].values()) * R
+
+    def to_dev(b):
+        return {k: v.to(dev, non_blocking=True) for k, v in b.items()}
+    resident = [to_dev(b) for b in host]
+
+    def epoch(batches):
+        losses = []
+        for b in batches:
+            hidden = (torch.zeros(1, N, P, device=dev), torch.zeros(1, N, P, device=dev))
+            nfm, nfm_p, reach, reach_p = b["nfm"][:-1], b["nfm"][1:], b["reach"][:-1], b["reach"][1:]
+            v_prime = model.v(nfm_p, ei, reach_p, hidden)[0]
+            td = b["r"] + hp.discount * v_prime * b["done"]
+            v_s = model.v(nfm, ei, reach, hidden)[0]
+            delta = (td - v_s).detach()
+            k = torch.arange(S, device=dev, dtype=torch.float32)                    # GAE as one discounted suffix sum
+            w = (hp.discount * hp.gae_lambda) ** k
+            adv = torch.flip(torch.cumsum(torch.flip(delta[:, 0] * w, [0]), 0), [0]) / w
+            pi, _ = model.pi(nfm, ei, reach, hidden)
+            ratio = torch.exp(torch.log(pi.gather(1, b["a"])) - torch.log(b["prob_a"]))
+            surr1, surr2 = ratio * adv[:, None], torch.clamp(ratio, 1 - hp.ppo_clip, 1 + hp.ppo_clip) * adv[:, None]
+            losses.append((-torch.min(surr1, surr2) + Fn.smooth_l1_loss(v_s, td.detach())).squeeze(-1))
+        loss = torch.cat(losses).mean()
+        model.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(params, R * S, R * S * world)
+        model.optimizer.step()
+        return loss
+
+    def stack(batches):
+        return {k: torch.stack([b[k] for b in batches]) for k in batches[0]}
+
+    def epoch_batched(bt):
+        hidden = (torch.zeros(1, R * N, P, device=dev), torch.zeros(1, R * N, P, device=dev))
+        nfm, reach = bt["nfm"], bt["reach"]
+        pi, v_s, v_prime = model.evaluate_rollouts(nfm[:, :-1], nfm[:, 1:], ei, reach[:, :-1], reach[:, 1:], hidden, hidden,
+                                                   prime_is_shift=True)
+        td = bt["r"] + hp.discount * v_prime * bt["done"]
+        delta = (td - v_s).detach()
+        w = ((hp.discount * hp.gae_lambda) ** torch.arange(S, device=dev, dtype=torch.float32))[None, :, None]
+        adv = torch.flip(torch.cumsum(torch.flip(delta * w, [1]), 1), [1]) / w
+        ratio = torch.exp(torch.log(pi.gather(2, bt["a"])) - torch.log(bt["prob_a"]))
+        surr1, surr2 = ratio * adv, torch.clamp(ratio, 1 - hp.ppo_clip, 1 + hp.ppo_clip) * adv
+        per_rollout_l2 = Fn.smooth_l1_loss(v_s, td.detach(), reduction="none").mean(dim=(1, 2), keepdim=True)
+        loss = (-torch.min(surr1, surr2) + per_rollout_l2).mean()
+        model.optimizer.zero_grad(set_to_none=True)
+        loss.backward()
+        if world > 1:
+            allreduce_gradients(params, R * S, R * S * world)
+        model.optimizer.step()
+        return loss
+    resident_stacked = stack(resident) if args.ppo_batched else None
+
+    def step():
+        return epoch_batched(resident_stacked) if args.ppo_batched else epoch(resident)
+
+    def step_e2e():
+        if args.ppo_batched:
+            return float(epoch_batched(stack([to_dev(b) for b in host])).detach())
+        return float(epoch([to_dev(b) for b in host]).detach())
+
+    def timed(fn, steps, warmup):
+        for _ in range(warmup):
+            fn()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            fn()
+        e1.record()
+        torch.cuda.synchronize()
+        ms_t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+        if world > 1:
+            dist.all_reduce(ms_t, op=dist.ReduceOp.MAX)
+            dist.barrier()
+        return float(ms_t.item())
+    for _ in range(args.warmup):
+        step()
+    c0 = _lib.launch_count
+    step()
+    launches = _lib.launch_count - c0
+    sampler = ClockSampler(dev.index or 0)
+    if rank == 0:
+        sampler.start()
+    ms = timed(step, args.steps, 0)
+    clocks = sampler.stop() if rank == 0 else None
+    e2e_ms = None if args.no_e2e else timed(step_e2e, max(3, min(args.steps, 10)), 1)
+    if world > 1:
+        dist.destroy_process_group()
+    if rank != 0:
+        return
+    n_t, e_t = TOPO_SHAPES[TOPO]
+    line = {"metric": "ppo_%s_epoch_rollout_steps_per_sec_N%d" % (args.qnet, n_t), "value": R * S * world / (ms / 1e3),
+            "unit": "rollout-steps/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "node_updates_per_sec": (R * (S + 1) if args.ppo_batched else 3 * R * S) * world * n_t * T / (ms / 1e3),
+            "config": {"workload": "PPO-GNN-LSTM epoch (qnet %s, lstm %s 64, critic q) on %s (N=%d, E=%d): %s, loss, backward, Adam"
+                                   % (args.qnet, args.ppo_lstm, TOPO, n_t, e_t,
+                                      "evaluate_rollouts: one GNN pass over all rollouts (s' embedded once)" if args.ppo_batched
+                                      else "per rollout v(s'), v(s), pi(s) through pi()/v() (the reference's call pattern)"),
+                       "rollouts_per_gpu": R, "steps_per_rollout": S, "global_rollouts": R * world, "nodes_per_graph": n_t,
+                       "parallelism": "dp%d (whole rollouts per rank)" % world,
+                       "l2": "per rollout pass %d rows x 256 B = %.1f MB per plane; %d passes per epoch"
+                             % (S * n_t, S * n_t * 256 / 1e6, 3 * R)},
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "clocks": clocks,
+            "e2e": None if e2e_ms is None else {"value": R * S * world / (e2e_ms / 1e3), "unit": "rollout-steps/s",
+                                                "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}}
     print(json.dumps(line), flush=True)
 
 
@@ -678,6 +868,8 @@ def main():
         METRIC = "s2v_fwd_bwd_graphs_per_sec_N%d" % TOPO_SHAPES[TOPO][0]
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "ppo":
+        run_ppo(args)
     elif args.qnet == "gat2":
         run_gat(args)
     else:

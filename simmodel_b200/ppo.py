@@ -219,6 +219,57 @@ class S2VKernelMixin:
             v = v.unsqueeze(-1)
         return v, lstm_hidden
 
+    # -- batched rollouts (caller-side batching of the reference's per-rollout loop) ---------------------
+    def evaluate_rollouts(self, nfm, nfm_prime, ei, reachable, reachable_prime, first_hidden=None, second_hidden=None,
+                          prime_is_shift=False):
+        """What one PPO epoch needs from R rollouts that share a topology, in ONE pass over the GNN
+        (models_basic_lstm.py:606-624 calls v(s'), v(s), pi(s) per rollout: three embedding passes each).
+
+        nfm, nfm_prime f32[R,S,N,F]; reachable, reachable_prime bool[R,S,N]; hidden = (h, c) each [1, R*N, p]
+        (rollout-major: rollout r owns rows r*N..(r+1)*N) or None.  prime_is_shift: the caller guarantees
+        nfm_prime[:, :-1] == nfm[:, 1:] (consecutive steps of one episode), so only the last s' is embedded anew.
+        Returns pi(s) f32[R,S,N], v(s) f32[R,S,1], v(s') f32[R,S,1] -- per graph-step the same arithmetic as pi()/v():
+        the GNN embedding of a step does not depend on the batch around it, pi and v over s share embedding and
+        LSTM output, and the LSTM (cuDNN, out of scope) runs with batch R*N instead of N."""
+        dev = self.device
+        if dev.type != "cuda":
+            raise S2VError("simmodel_b200.PPO_GNN_Single_LSTM runs on CUDA only (no CPU fallback)")
+        if self.config["lstm_type"] == "FE":
+            raise NotImplementedError("evaluate_rollouts covers lstm_type 'None' and 'EMB'")
+        nfm, nfm_prime = nfm.to(dev), nfm_prime.to(dev)
+        R, S, N, Fd = nfm.shape
+        p = self.emb_dim
+        extra = nfm_prime[:, -1:] if prime_is_shift else nfm_prime
+        allx = torch.cat((nfm, extra), dim=1)                                  # [R, S+1 | 2S, N, F]
+        G = int(allx.shape[1])
+        layout = self._layout(ei, N, R * G)
+        x = allx.reshape(R * G * N, Fd).contiguous()
+        if self.config["qnet"] == "gat2":
+            mu = self.gat.forward_layout(x, layout)
+        else:
+            mu = ops.s2v_embed(layout, x, self.embed_weights(), self.T)
+        mu = mu.view(R, G, N, p)
+        mu_s = mu[:, :S]
+        mu_p = mu[:, 1:S + 1] if prime_is_shift else mu[:, S:]
+        if self.config["lstm_type"] == "EMB":
+            def run_lstm(m, hidden):                                           # (seq S, batch R*N, p), rollout-major batch
+                out, _ = self.lstm(m.permute(1, 0, 2, 3).reshape(S, R * N, p), hidden)
+                return out.view(S, R, N, p).permute(1, 0, 2, 3)
+            mu_s, mu_p = run_lstm(mu_s, first_hidden), run_lstm(mu_p, second_hidden)
+        lay_s = self._layout(ei, N, R * S)
+        flat_s = mu_s.reshape(R * S * N, p).contiguous()
+        flat_p = mu_p.reshape(R * S * N, p).contiguous()
+        reach_s, reach_p = reachable.to(dev).reshape(R * S, N), reachable_prime.to(dev).reshape(R * S, N)
+        logits = ops.s2v_head(lay_s, flat_s, self.head_weights("_pi"), True)
+        prob = ops.masked_softmax(lay_s, logits, reach_s).view(R, S, N)
+        if self.config["critic"] == "v":
+            v_s = F.linear(ops.segment_pool(lay_s, flat_s, True), self.theta5_v.weight, self.theta5_v.bias)
+            v_p = F.linear(ops.segment_pool(lay_s, flat_p, True), self.theta5_v.weight, self.theta5_v.bias)
+        else:
+            v_s, _ = ops.masked_max(lay_s, ops.s2v_head(lay_s, flat_s, self.head_weights("_v"), True), reach_s)
+            v_p, _ = ops.masked_max(lay_s, ops.s2v_head(lay_s, flat_p, self.head_weights("_v"), True), reach_p)
+        return prob, v_s.reshape(R, S, 1), v_p.reshape(R, S, 1)
+
     @torch.no_grad()
     def greedy_action(self, nfm, ei, reachable, hidden):
         """probs.argmax() of the deterministic policy (rl_policy.py:533-536), on the GPU."""

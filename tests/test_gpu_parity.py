@@ -181,6 +181,69 @@ def test_ppo_golden(case, cuda_device):
     assert np.array_equal(arg.cpu().numpy(), G["out"]["greedy"])
 
 
+@pytest.mark.parametrize("qnet,lstm,critic,shift", [("s2v", "None", "q", True), ("s2v", "EMB", "q", False),
+                                                    ("gat2", "EMB", "q", True), ("s2v", "None", "v", False)])
+def test_ppo_evaluate_rollouts_equals_per_rollout_calls(qnet, lstm, critic, shift, cuda_device):
+    """evaluate_rollouts (R rollouts, one GNN pass) == the reference's per-rollout v(s'), v(s), pi(s) calls, values
+    and parameter gradients (the embedding of a step is independent of its batch: bit-exact without the LSTM)."""
+    import types
+    import simmodel_b200 as sb
+    dev = cuda_device
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    topo = sb.graphs.load_topology("Manhattan5")
+    N, R, S, p = topo.num_nodes, 3, 6, 64
+    config = {"lstm_type": lstm, "qnet": qnet, "critic": critic, "emb_dim": p, "emb_iterT": 5, "gat_concat": True,
+              "gat_heads": 4, "gat_share_weights": False}
+    hp = types.SimpleNamespace(node_dim=7, emb_dim=p, parallel_rollouts=R, batch_size=1, learning_rate=1e-3)
+    torch.manual_seed(3)
+    model = sb.PPO_GNN_Single_LSTM(config, hp, {"base_checkpoint_path": None}, device=dev)
+    gen = torch.Generator().manual_seed(4)
+    allobs = sb.graphs.synth_nfm(topo, R * (S + 1), gen).view(R, S + 1, N, 7)
+    nfm = allobs[:, :S].contiguous()
+    nfm_p = allobs[:, 1:].contiguous() if shift else sb.graphs.synth_nfm(topo, R * S, gen).view(R, S, N, 7)
+    reach = torch.rand(R, S, N, generator=gen) < 0.3
+    reach[:, :, 0] = True
+    reach_p = torch.rand(R, S, N, generator=gen) < 0.3
+    reach_p[:, :, 1] = True
+    ei = topo.edge_index
+    h1 = h2 = None
+    if lstm == "EMB":
+        h1 = (torch.randn(1, R * N, p, generator=gen).to(dev) * 0.1, torch.randn(1, R * N, p, generator=gen).to(dev) * 0.1)
+        h2 = (torch.randn(1, R * N, p, generator=gen).to(dev) * 0.1, torch.randn(1, R * N, p, generator=gen).to(dev) * 0.1)
+    wp, wv, wq = (torch.randn(R, S, N, generator=gen).to(dev), torch.randn(R, S, 1, generator=gen).to(dev),
+                  torch.randn(R, S, 1, generator=gen).to(dev))
+    prob, v_s, v_p = model.evaluate_rollouts(nfm, nfm_p, ei, reach, reach_p, h1, h2, prime_is_shift=shift)
+    model.zero_grad()
+    ((prob * wp).sum() + (v_s * wv).sum() + (v_p * wq).sum()).backward()
+    g_batched = {k: prm.grad.clone() for k, prm in model.named_parameters() if prm.grad is not None}
+    model.zero_grad()
+    loss = 0.0
+    probs, vss, vps = [], [], []
+    for r in range(R):
+        sl = slice(r * N, (r + 1) * N)
+        hid1 = None if h1 is None else (h1[0][:, sl].contiguous(), h1[1][:, sl].contiguous())
+        hid2 = None if h2 is None else (h2[0][:, sl].contiguous(), h2[1][:, sl].contiguous())
+        vp_r = model.v(nfm_p[r], ei, reach_p[r], hid2)[0]
+        vs_r = model.v(nfm[r], ei, reach[r], hid1)[0]
+        pi_r = model.pi(nfm[r], ei, reach[r], hid1)[0]
+        loss = loss + (pi_r * wp[r]).sum() + (vs_r * wv[r]).sum() + (vp_r * wq[r]).sum()
+        probs.append(pi_r.detach()); vss.append(vs_r.detach()); vps.append(vp_r.detach())
+    loss.backward()
+    tol = 2e-5 if lstm == "EMB" else (2e-6 if critic == "v" else 0.0)     # 'v': a cuBLAS GEMV whose M differs
+    for name, new, ref in (("prob", prob, torch.stack(probs)), ("v_s", v_s, torch.stack(vss)), ("v_p", v_p, torch.stack(vps))):
+        if tol == 0.0:
+            assert torch.equal(new.detach(), ref), name
+        else:
+            _check(name, new.detach().cpu().numpy(), ref.cpu().numpy(), tol=tol)
+    for k, prm in model.named_parameters():
+        if prm.grad is not None:
+            # both sides are fp32 sums over the same terms grouped differently (one batch vs R x 3 calls accumulated
+            # by autograd): a few 1e-6 of scale without the LSTM, cuDNN's batch-dependent order with it
+            _check("grad " + k, g_batched[k].cpu().numpy(), prm.grad.cpu().numpy(), tol=3e-5 if lstm != "EMB" else 1e-4,
+                   abs_floor=2e-7)
+
+
 def _dense_from_ei(ei, n):
     W = np.zeros((n, n), dtype=np.float32)
     W[ei[0], ei[1]] = 1.0
