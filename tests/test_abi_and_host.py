@@ -133,3 +133,16 @@ def test_bench_reference_arm_contract():
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "graphs/s" and line["value"] > 0
     assert line["cpu_baseline"]["kind"] == "port" and line["e2e"]["h2d_bytes_per_step"] == 0
+
+
+def test_sb3_mirror_state_dict_keys():
+    """SB3 consumer: parameter names of the mirrors == the reference's (golden produced by the
+    unmodified modules/ppo/models_sb3_s2v.py classes)."""
+    import simmodel_b200 as sb
+    from conftest import load_golden
+    meta, G = load_golden("sb3_m3m5mix_pad25")
+    ex = sb.sb3.Struc2VecExtractor(meta["n_pad"], meta["emb_dim"], meta["T"], 7)
+    ac = sb.sb3.s2v_ACNetwork(meta["emb_dim"], 1, 1, meta["emb_dim"])
+    assert ["extractor." + k for k in ex.state_dict()] == [k for k in G["P"] if k.startswith("extractor.")]
+    assert ["acnet." + k for k in ac.state_dict()] == [k for k in G["P"] if k.startswith("acnet.")]
+    assert ex.features_dim == meta["n_pad"] * (meta["emb_dim"] + 1)
