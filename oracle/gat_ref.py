@@ -178,10 +178,10 @@ class GATv2Conv(nn.Module):
     def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0,
                  add_self_loops=True, bias=True, share_weights=False, **kwargs):
         super().__init__()
-        assert concat and add_self_loops and bias and not share_weights and dropout == 0.0, "only the reference's configuration"
+        assert concat and add_self_loops and bias and dropout == 0.0, "only the reference's configurations"
         self.heads, self.out_channels, self.negative_slope = heads, out_channels, negative_slope
         self.lin_l = PygLinear(in_channels, heads * out_channels)
-        self.lin_r = PygLinear(in_channels, heads * out_channels)
+        self.lin_r = self.lin_l if share_weights else PygLinear(in_channels, heads * out_channels)   # gatv2_conv.py: shared module
         self.att = nn.Parameter(torch.empty(1, heads, out_channels))
         self.bias = nn.Parameter(torch.zeros(heads * out_channels))
         a = math.sqrt(6.0 / (heads + out_channels))

@@ -60,27 +60,34 @@ def _rows_contract(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
 
 
 class _GATConvFn(torch.autograd.Function):
+    """wr / br None => share_weights=True (x_r = x_l = lin_l(x); models_ngo.py:241-249)."""
+
     @staticmethod
     def forward(ctx, layout, heads, relu, x, wl, bl, wr, br, att, bias):
         L = _lib.lib()
         x = ops._f32c(x, "x")
         n, HC = layout.num_nodes, int(wl.shape[0])
         Cc = HC // heads
+        shared = wr is None
         if x.shape[0] != n or x.shape[1] != wl.shape[1]:
             raise ValueError("x has shape %s, expected (%d, %d)" % (tuple(x.shape), n, wl.shape[1]))
-        wcat = torch.cat((wl.detach(), wr.detach()), dim=0)                  # [2HC, in]
-        bcat = torch.cat((bl.detach(), br.detach()), dim=0)
+        if shared:
+            wcat, bcat = wl.detach(), bl.detach()
+        else:
+            wcat = torch.cat((wl.detach(), wr.detach()), dim=0)              # [2HC, in]
+            bcat = torch.cat((bl.detach(), br.detach()), dim=0)
         xlr = torch.addmm(bcat, x, wcat.t())                                 # [n, 2HC]: x_l | x_r  (plain GEMM)
+        ld = int(xlr.shape[1])
+        xr_ptr = _p(xlr) if shared else C.c_void_p(xlr.data_ptr() + 4 * HC)
         att_f = ops._f32c(att.detach().reshape(-1), "att")
         bias_f = ops._f32c(bias.detach(), "bias")
         out = torch.empty(n, HC, dtype=torch.float32, device=x.device)
         stats = torch.empty(n, heads, 4, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            _lib.check(L.s2v_gat_attn_forward(C.byref(layout.c_struct()), heads, Cc, 2 * HC, _p(xlr),
-                                              C.c_void_p(xlr.data_ptr() + 4 * HC), _p(att_f), _p(bias_f), int(relu),
-                                              _p(out), _p(stats), _stream()), "s2v_gat_attn_forward")
+            _lib.check(L.s2v_gat_attn_forward(C.byref(layout.c_struct()), heads, Cc, ld, _p(xlr), xr_ptr, _p(att_f),
+                                              _p(bias_f), int(relu), _p(out), _p(stats), _stream()), "s2v_gat_attn_forward")
         _lib.launch_count += 1
-        ctx.layout, ctx.heads, ctx.relu = layout, heads, relu
+        ctx.layout, ctx.heads, ctx.relu, ctx.shared = layout, heads, relu, shared
         ctx.save_for_backward(x, xlr, stats, out, att_f, wcat)
         return out
 
@@ -88,7 +95,7 @@ class _GATConvFn(torch.autograd.Function):
     def backward(ctx, dout):
         L = _lib.lib()
         x, xlr, stats, out, att_f, wcat = ctx.saved_tensors
-        layout, heads = ctx.layout, ctx.heads
+        layout, heads, shared = ctx.layout, ctx.heads, ctx.shared
         n, HC = layout.num_nodes, int(out.shape[1])
         Cc = HC // heads
         dout = ops._f32c(dout, "dout")
@@ -98,14 +105,22 @@ class _GATConvFn(torch.autograd.Function):
                 _lib.check(L.s2v_relu_mask(_p(dout), _p(out), _p(masked), dout.numel(), _stream()), "s2v_relu_mask")
                 _lib.launch_count += 1
                 dout = masked
-            dxlr = torch.empty(n, 2 * HC, dtype=torch.float32, device=x.device)
+            # shared weights: dx_l and dx_r land in two planes that are summed afterwards (both feed lin_l)
+            dxlr = torch.empty((2, n, HC) if shared else (n, 2 * HC), dtype=torch.float32, device=x.device)
+            ld = HC if shared else 2 * HC
+            dxr_ptr = C.c_void_p(dxlr.data_ptr() + 4 * (n * HC if shared else HC))
+            xr_ptr = _p(xlr) if shared else C.c_void_p(xlr.data_ptr() + 4 * HC)
             gab = torch.empty(4, HC, dtype=torch.float32, device=x.device)       # datt | dbias | dlin_l.bias | dlin_r.bias
             ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(heads, Cc), dtype=torch.uint8, device=x.device)
-            _lib.check(L.s2v_gat_attn_backward(C.byref(layout.c_struct()), heads, Cc, 2 * HC, _p(xlr),
-                                               C.c_void_p(xlr.data_ptr() + 4 * HC), _p(att_f), _p(stats), _p(dout),
-                                               _p(dxlr), C.c_void_p(dxlr.data_ptr() + 4 * HC), _p(gab[0]), _p(gab[1]),
+            _lib.check(L.s2v_gat_attn_backward(C.byref(layout.c_struct()), heads, Cc, ld, _p(xlr), xr_ptr, _p(att_f),
+                                               _p(stats), _p(dout), _p(dxlr), dxr_ptr, _p(gab[0]), _p(gab[1]),
                                                _p(gab[2]), _p(ws), ws.numel(), _stream()), "s2v_gat_attn_backward")
         _lib.launch_count += 3
+        if shared:
+            dxs = dxlr[0] + dxlr[1]
+            dw = _rows_contract(dxs, x)
+            dx = dxs.mm(wcat) if ctx.needs_input_grad[3] else None
+            return (None, None, None, dx, dw, gab[2] + gab[3], None, None, gab[0].view(1, heads, Cc), gab[1])
         dw = _rows_contract(dxlr, x)                                          # [2HC, in]   (plain GEMMs)
         dx = dxlr.mm(wcat) if ctx.needs_input_grad[3] else None
         return (None, None, None, dx, dw[:HC], gab[2], dw[HC:], gab[3], gab[0].view(1, heads, Cc), gab[1])
@@ -119,20 +134,22 @@ class GATv2Conv(nn.Module):
     def __init__(self, in_channels, out_channels, heads=1, concat=True, negative_slope=0.2, dropout=0.0,
                  add_self_loops=True, bias=True, share_weights=False, **kwargs):
         super().__init__()
-        if not (concat and add_self_loops and bias) or share_weights or dropout != 0.0 or negative_slope != 0.2:
-            raise NotImplementedError("simmodel_b200.GATv2Conv covers the reference's configuration only "
-                                      "(concat, self loops, separate lin_l/lin_r, slope 0.2, no dropout)")
+        if not (concat and add_self_loops and bias) or dropout != 0.0 or negative_slope != 0.2:
+            raise NotImplementedError("simmodel_b200.GATv2Conv covers the reference's configurations only "
+                                      "(concat, self loops, slope 0.2, no dropout; share_weights either way)")
         if heads * out_channels > 128:
             raise NotImplementedError("GATv2Conv kernels cover heads*out_channels <= 128 (got %d)" % (heads * out_channels))
         self.in_channels, self.out_channels, self.heads = in_channels, out_channels, heads
+        self.share_weights = bool(share_weights)
         self.lin_l = nn.Linear(in_channels, heads * out_channels, bias=True)
-        self.lin_r = nn.Linear(in_channels, heads * out_channels, bias=True)
+        # PyG: `self.lin_r = self.lin_l` when sharing -- one module under two names (both appear in the state dict)
+        self.lin_r = self.lin_l if share_weights else nn.Linear(in_channels, heads * out_channels, bias=True)
         self.att = nn.Parameter(torch.empty(1, heads, out_channels))
         self.bias = nn.Parameter(torch.zeros(heads * out_channels))
         self.reset_parameters()
 
     def reset_parameters(self):
-        for lin in (self.lin_l, self.lin_r):
+        for lin in ((self.lin_l,) if self.share_weights else (self.lin_l, self.lin_r)):
             a = math.sqrt(6.0 / (lin.in_features + lin.out_features))
             nn.init.uniform_(lin.weight, -a, a)
             nn.init.uniform_(lin.bias, -1.0 / math.sqrt(lin.in_features), 1.0 / math.sqrt(lin.in_features))
@@ -143,6 +160,9 @@ class GATv2Conv(nn.Module):
     def forward_layout(self, x, layout: GraphLayout, relu: bool = False):
         if not self.att.is_cuda:
             raise S2VError("simmodel_b200.GATv2Conv runs on CUDA only: call .to('cuda') first (no CPU fallback)")
+        if self.share_weights:
+            return _GATConvFn.apply(layout, self.heads, bool(relu), x, self.lin_l.weight, self.lin_l.bias, None, None,
+                                    self.att, self.bias)
         return _GATConvFn.apply(layout, self.heads, bool(relu), x, self.lin_l.weight, self.lin_l.bias,
                                 self.lin_r.weight, self.lin_r.bias, self.att, self.bias)
 

@@ -139,6 +139,34 @@ def test_gat_conv_vs_oracle(heads, C, n, deg, seed, cuda_device):
             _check("grad " + k, prm.grad.cpu().numpy(), P[k].grad.numpy(), tol=3e-6)
 
 
+@pytest.mark.parametrize("heads,C", [(2, 32), (4, 12)])
+def test_gat_conv_shared_weights_vs_oracle(heads, C, cuda_device):
+    """share_weights=True (models_ngo.py:241-249: x_r = x_l = lin_l(x)): forward, input and parameter gradients."""
+    import simmodel_b200 as sb
+    from oracle import gat_ref as R
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(11)
+    n, cin = 120, 24
+    ei = (torch.rand(n, n, generator=gen) < 4.0 / n).nonzero().t().contiguous()
+    x = torch.randn(n, cin, generator=gen)
+    conv = sb.GATv2Conv(cin, C, heads=heads, share_weights=True)
+    assert conv.lin_r is conv.lin_l and "lin_r.weight" in conv.state_dict()
+    P = {k: v.detach().clone().double().requires_grad_(True) for k, v in conv.state_dict().items() if not k.startswith("lin_r")}
+    x64 = x.double().requires_grad_(True)
+    w = torch.randn(n, heads * C, generator=gen)
+    ref = R.gatv2_conv(x64, ei, P["lin_l.weight"], P["lin_l.bias"], P["lin_l.weight"], P["lin_l.bias"], P["att"], P["bias"])
+    (torch.relu(ref) * w.double()).sum().backward()
+    conv = conv.to(dev)
+    xd = x.to(dev).requires_grad_(True)
+    layout = sb.gat.gat_layout_from_batch(ei.to(dev), torch.tensor([0, n], device=dev))
+    out = conv.forward_layout(xd, layout, relu=True)
+    (out * w.to(dev)).sum().backward()
+    _check("out", out.detach().cpu().numpy(), torch.relu(ref).detach().numpy(), tol=3e-6)
+    _check("dx", xd.grad.cpu().numpy(), x64.grad.numpy(), tol=3e-6)
+    for k, prm in conv.named_parameters():
+        _check("grad " + k, prm.grad.cpu().numpy(), P[k].grad.numpy(), tol=3e-6)
+
+
 def test_gat_replicated_equals_batched_and_bit_stable(cuda_device):
     """S copies of one topology: replicated layout (PPO path) == batched layout (DQN path) bit for bit, run-to-run
     bit-stable gradients (no atomics)."""
@@ -175,3 +203,32 @@ def test_gat_no_cpu_path():
     conv = sb.GATv2Conv(7, 16, heads=2)
     with pytest.raises(sb.S2VError):
         conv(torch.zeros(4, 7), torch.zeros(2, 0, dtype=torch.int64))
+
+
+def test_qfunction_with_gat_qnet(cuda_device):
+    """QFunction.predict / get_best_action / batch_update drive QNet_GATv2 the way comb_opt.py does for --qnet gat2:
+    pyg_data = Data(x=nfm, edge_index=EI) (comb_opt.py:472,522), state_tsr / W are dummies."""
+    import simmodel_b200 as sb
+    meta, G = load_golden("gat_dqn_manhattan5_b4")
+    dev = cuda_device
+    net = sb.QNet_GATv2({"emb_dim": 64, "emb_iter_T": 5, "norm_agg": True, "node_dim": 7}, verbose=False)
+    net.load_state_dict({k: torch.from_numpy(v) for k, v in G["P"].items()}, strict=True)
+    net = net.to(dev)
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    qf = sb.QFunction(net, opt, torch.optim.lr_scheduler.ExponentialLR(opt, gamma=0.99999))
+    ptr = G["inp"]["ptr"].astype(np.int64)
+    ei = G["inp"]["edge_index"].astype(np.int64)
+    zerovec = torch.zeros(1)
+    datas = []
+    for b in range(4):
+        m = (ei[0] >= ptr[b]) & (ei[0] < ptr[b + 1])
+        datas.append(sb.Data(torch.from_numpy(G["inp"]["x"][ptr[b]:ptr[b + 1]]), torch.from_numpy(ei[:, m] - ptr[b])))
+    q0 = qf.predict(zerovec, zerovec, datas[0])
+    # a graph alone == the same graph inside the golden batch, up to the library GEMM's batch-dependent rounding
+    _check("predict", q0.cpu().numpy(), G["out"]["q"][:25], tol=2e-5)
+    reach = [1, 5, 6]
+    a, node, val = qf.get_best_action(zerovec, zerovec, datas[0], reach)
+    ref = q0.cpu().numpy()[reach]
+    assert a == int(np.argmax(ref)) and node == reach[a] and val == ref[a]
+    loss = qf.batch_update([zerovec] * 4, [zerovec] * 4, datas, G["inp"]["actions"].tolist(), G["inp"]["targets"].tolist())
+    assert abs(loss - float(G["out"]["loss"])) <= 1e-5 * max(1.0, abs(float(G["out"]["loss"])))
