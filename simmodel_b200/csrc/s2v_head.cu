@@ -145,15 +145,18 @@ k_head(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const
 template <int P>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_head_bwd_graph(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ gstate,
-                 const float* __restrict__ dq, float* __restrict__ per_graph) {
+                 const float* __restrict__ dq, float* __restrict__ per_graph, unsigned int* __restrict__ nnz_total) {
     __shared__ float red[S2V_THREADS];
     __shared__ float dG[P];
     const int gi = blockIdx.x, t = threadIdx.x;
     int lo, hi;
     graph_range(g, gi, lo, hi);
     float s = 0.f;
-    for (int r = lo + t; r < hi; r += S2V_THREADS) s += __ldg(dq + r);
+    int nz = 0;
+    for (int r = lo + t; r < hi; r += S2V_THREADS) { const float d = __ldg(dq + r); s += d; nz += d != 0.f; }
     red[t] = s;
+    nz = __reduce_add_sync(0xffffffffu, nz);            // integer count: the atomic sum is order-independent
+    if ((t & 31) == 0 && nz) atomicAdd(nnz_total, (unsigned int)nz);
     __syncthreads();
     for (int w = S2V_THREADS / 2; w > 0; w >>= 1) {
         if (t < w) red[t] += red[t + w];
@@ -186,11 +189,45 @@ struct HeadPartial {
     static constexpr int SIZE = W5B + P;
 };
 
+// dq with few non-zeros (the DQN loss touches one node per graph): dmu_i = dpool_g(i) [* (mu_i > 0)] for every row, as
+// one streaming pass with all loads of a thread in flight; k_head_bwd then only revisits the tiles that hold a non-zero dq.
+#define HEAD_SPARSE(nnz, n) ((unsigned long long)(nnz) * 8ull < (unsigned long long)(n))
+template <int P>
+__global__ void __launch_bounds__(256)
+k_head_bwd_stream(s2v_graph_t g, const float* __restrict__ mu, const float* __restrict__ per_graph, int mask_relu,
+                  float* __restrict__ dmu, const unsigned int* __restrict__ nnz_total) {
+    if (!HEAD_SPARSE(*nnz_total, g.num_nodes)) return;
+    constexpr int V = P / 4, U = 4;
+    const long long total = (long long)g.num_nodes * V, stride = (long long)gridDim.x * 256;
+    for (long long e0 = (long long)blockIdx.x * 256 + threadIdx.x; e0 < total; e0 += stride * U) {
+        float4 o[U], m[U];
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long e = e0 + u * stride;
+            o[u] = f4zero(); m[u] = make_float4(1.f, 1.f, 1.f, 1.f);
+            if (e < total) {
+                const int r = (int)(e / V), c = (int)(e - (long long)r * V);
+                const int gi = g.period > 0 ? r / g.period : __ldg(g.gid + r);
+                o[u] = ldg4(per_graph + (size_t)gi * (2 * P + 4) + P + 4 * c);
+                if (mask_relu) m[u] = ldg4(mu + (size_t)r * P + 4 * c);
+            }
+        }
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            const long long e = e0 + u * stride;
+            if (e < total)
+                st4(dmu + e * 4, make_float4(m[u].x > 0.f ? o[u].x : 0.f, m[u].y > 0.f ? o[u].y : 0.f,
+                                             m[u].z > 0.f ? o[u].z : 0.f, m[u].w > 0.f ? o[u].w : 0.f));
+        }
+    }
+}
+
 template <int P>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_head_bwd(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const float* __restrict__ dq,
            const float* __restrict__ per_graph, int mask_relu, float* __restrict__ dmu,
-           float* __restrict__ partial, int num_tiles) {
+           float* __restrict__ partial, int num_tiles, const unsigned int* __restrict__ nnz_total) {
+    const bool streamed = nnz_total != nullptr && HEAD_SPARSE(*nnz_total, g.num_nodes);
     using C = Cfg<P>;
     using HP = HeadPartial<P>;
     extern __shared__ __align__(16) float smem[];
@@ -219,6 +256,7 @@ k_head_bwd(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, c
         // dmu reduces to the pooled term.  The DQN loss touches ONE node per graph
         // (qvals[actions + ptr[:-1]], comb_opt.py:355-356), so almost every tile takes this exit.
         const bool live = __syncthreads_or(t < rows && __ldg(dq + row0 + t) != 0.f);
+        if (!live && streamed) continue;                       // k_head_bwd_stream wrote these rows
         if (!live) {
             // streaming exit: all loads of the thread's chunks are issued before the first store; the graph of a row
             // comes from one division per tile (replicated layout) instead of one per chunk
@@ -435,6 +473,10 @@ static int head_forward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm,
     return (int)cudaGetLastError();
 }
 
+static inline int64_t head_ws_floats(int P, int num_graphs) {
+    return (int64_t)num_graphs * (2 * P + 4) + (int64_t)(S2V_MAX_GRID + 1) * (2 * P * P + 4 * P + 4);
+}
+
 template <int P>
 static int head_backward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm, const float* mu,
                               const float* pool, const float* gstate, const float* dq, int mask_relu,
@@ -443,12 +485,22 @@ static int head_backward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm
     using HP = HeadPartial<P>;
     float* per_graph = ws;
     float* partial = ws + (size_t)g.num_graphs * (2 * P + 4);
-    k_head_bwd_graph<P><<<g.num_graphs, S2V_THREADS, 0, st>>>(g, prm, gstate, dq, per_graph);
+    unsigned int* nnz_total = reinterpret_cast<unsigned int*>(ws + head_ws_floats(P, g.num_graphs));
+    S2V_RETURN_IF(cudaMemsetAsync(nnz_total, 0, sizeof(unsigned int), st));
+    k_head_bwd_graph<P><<<g.num_graphs, S2V_THREADS, 0, st>>>(g, prm, gstate, dq, per_graph, nnz_total);
     const int tiles = (g.num_nodes + S2V_TM - 1) / S2V_TM;
+    const bool split = g.num_nodes >= S2V_TENSOR_MIN_NODES;      // small batches: one launch less matters more
+    if (split) {
+        const long long chunks = (long long)g.num_nodes * (P / 4);
+        long long want = (chunks + 256 * 4 - 1) / (256 * 4);
+        int sgrid = (int)(want < 148 * 8 ? want : 148 * 8);
+        k_head_bwd_stream<P><<<sgrid, 256, 0, st>>>(g, mu, per_graph, mask_relu, dmu, nnz_total);
+    }
     int smem = (2 * C::W_FLOATS + 2 * C::TILE_FLOATS + 2 * P + C::RG * P) * 4;
     S2V_RETURN_IF(cudaFuncSetAttribute(k_head_bwd<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int grid = s2v_persistent_grid((const void*)k_head_bwd<P>, smem, tiles);
-    k_head_bwd<P><<<grid, S2V_THREADS, smem, st>>>(g, prm, mu, dq, per_graph, mask_relu, dmu, partial, tiles);
+    k_head_bwd<P><<<grid, S2V_THREADS, smem, st>>>(g, prm, mu, dq, per_graph, mask_relu, dmu, partial, tiles,
+                                                   split ? nnz_total : nullptr);
     // per-graph terms, then fixed-order sums of both partial sets
     using GP = HeadGraphPartial<P>;
     float* partial_g = partial + (size_t)S2V_MAX_GRID * HP::SIZE;
@@ -475,7 +527,7 @@ static int check_graph_h(const s2v_graph_t* g) {
 extern "C" int64_t s2v_head_grad_floats(int32_t P) { return 2 * (int64_t)P + 1 + 2 * ((int64_t)P * P + P); }
 
 extern "C" int64_t s2v_head_backward_workspace_bytes(int32_t P, int32_t num_graphs) {
-    return ((int64_t)num_graphs * (2 * P + 4) + (int64_t)(S2V_MAX_GRID + 1) * (2 * P * P + 4 * P + 4)) * 4;
+    return head_ws_floats(P, num_graphs) * 4 + 64;      // + the non-zero counter of dq
 }
 
 extern "C" int s2v_head_forward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu,
