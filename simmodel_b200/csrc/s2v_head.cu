@@ -190,7 +190,8 @@ struct HeadPartial {
 };
 
 // dq with few non-zeros (the DQN loss touches one node per graph): dmu_i = dpool_g(i) [* (mu_i > 0)] for every row, as
-// one streaming pass with all loads of a thread in flight; k_head_bwd then only revisits the tiles that hold a non-zero dq.
+// one streaming pass with all loads of a thread in flight; k_head_bwd_rows then revisits only the rows with a non-zero dq
+// (k_head_bwd, the tile kernel, handles dense dq -- the PPO losses -- and small batches).
 #define HEAD_SPARSE(nnz, n) ((unsigned long long)(nnz) * 8ull < (unsigned long long)(n))
 template <int P>
 __global__ void __launch_bounds__(256)
@@ -222,12 +223,115 @@ k_head_bwd_stream(s2v_graph_t g, const float* __restrict__ mu, const float* __re
     }
 }
 
+// Sparse dq, second pass: only the ROWS with dq != 0 carry a local term.  Per such row (one warp):
+//   L = theta7 mu_i + b7 ; dL = dq_i w5b * [L > 0] ; dtheta7 += dL mu_i^T ; db7 += dL ; dw5b += dq_i relu(L) ;
+//   dmu_i = theta7^T dL + dpool_g(i)  [* (mu_i > 0)]   (overwrites what k_head_bwd_stream wrote for the row).
+// CTA c owns a contiguous slab of rows, warp w a quarter of it, scanned 32 rows at a time in row order; dtheta7 is
+// accumulated per warp in shared memory (lane = column k: conflict-free) and the four warps are summed in fixed order.
+template <int P>
+__global__ void __launch_bounds__(S2V_THREADS)
+k_head_bwd_rows(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const float* __restrict__ dq,
+                const float* __restrict__ per_graph, int mask_relu, float* __restrict__ dmu,
+                float* __restrict__ partial, int rows_per_cta, const unsigned int* __restrict__ nnz_total) {
+    using HP = HeadPartial<P>;
+    if (!HEAD_SPARSE(*nnz_total, g.num_nodes)) return;
+    constexpr int LDW = P + 1, NW = S2V_THREADS / 32, KPL = (P + 31) / 32;     // KPL = outputs / columns per lane
+    extern __shared__ __align__(16) float smem[];
+    float* W7 = smem;                              // theta7[n][k], row stride P+1
+    float* acc = W7 + P * LDW;                     // [NW][P*P] per-warp dtheta7
+    float* bmu = acc + NW * P * P;                 // [NW][P]
+    float* bdl = bmu + NW * P;                     // [NW][P]
+    float* vec = bdl + NW * P;                     // b7 [P], w5b [P]
+    float* red = vec + 2 * P;                      // [NW][2P]
+    const int t = threadIdx.x, w = t >> 5, lane = t & 31;
+    for (int e = t; e < P * P; e += S2V_THREADS) W7[(e / P) * LDW + e % P] = __ldg(prm.theta7_w + e);
+    for (int e = t; e < NW * P * P; e += S2V_THREADS) acc[e] = 0.f;
+    if (t < P) { vec[t] = __ldg(prm.theta7_b + t); vec[P + t] = __ldg(prm.theta5_w + P + t); }
+    __syncthreads();
+    float pB7[KPL], pW5[KPL];
+#pragma unroll
+    for (int q = 0; q < KPL; ++q) pB7[q] = pW5[q] = 0.f;
+    float* my_acc = acc + w * P * P, *my_mu = bmu + w * P, *my_dl = bdl + w * P;
+    const int sub = rows_per_cta / NW;
+    const long long lo = (long long)blockIdx.x * rows_per_cta + (long long)w * sub;
+    const long long hi = lo + sub < (long long)g.num_nodes ? lo + sub : (long long)g.num_nodes;
+    for (long long base = lo; base < hi; base += 32) {
+        const long long r = base + lane;
+        const float d = r < hi ? __ldg(dq + r) : 0.f;
+        unsigned live = __ballot_sync(0xffffffffu, d != 0.f);
+        while (live) {
+            const int b = __ffs(live) - 1;
+            live &= live - 1;
+            const int rr = (int)(base + b);
+            const float dd = __shfl_sync(0xffffffffu, d, b);
+            float muv[KPL];
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {
+                const int k = lane + 32 * q;
+                muv[q] = k < P ? __ldg(mu + (size_t)rr * P + k) : 0.f;
+                if (k < P) my_mu[k] = muv[q];
+            }
+            __syncwarp();
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {                                     // lane = output n
+                const int n = lane + 32 * q;
+                if (n < P) {
+                    float L = vec[n];
+                    for (int k = 0; k < P; ++k) L = fmaf(W7[n * LDW + k], my_mu[k], L);
+                    const float dl = L > 0.f ? dd * vec[P + n] : 0.f;
+                    pW5[q] = fmaf(dd, relu(L), pW5[q]);
+                    pB7[q] += dl;
+                    my_dl[n] = dl;
+                }
+            }
+            __syncwarp();
+            int li, off, gi;
+            row_info(g, rr, li, off, gi);
+#pragma unroll
+            for (int q = 0; q < KPL; ++q) {                                     // lane = column k
+                const int k = lane + 32 * q;
+                if (k < P) {
+                    float o = __ldg(per_graph + (size_t)gi * (2 * P + 4) + P + k);
+                    for (int n = 0; n < P; ++n) {
+                        const float dl = my_dl[n];                              // warp-uniform
+                        if (dl != 0.f) {
+                            my_acc[n * P + k] = fmaf(dl, muv[q], my_acc[n * P + k]);
+                            o = fmaf(W7[n * LDW + k], dl, o);
+                        }
+                    }
+                    dmu[(size_t)rr * P + k] = (!mask_relu || muv[q] > 0.f) ? o : 0.f;
+                }
+            }
+            __syncwarp();
+        }
+    }
+#pragma unroll
+    for (int q = 0; q < KPL; ++q) {
+        const int n = lane + 32 * q;
+        if (n < P) { red[w * 2 * P + n] = pB7[q]; red[w * 2 * P + P + n] = pW5[q]; }
+    }
+    __syncthreads();
+    float* my = partial + (size_t)blockIdx.x * HP::SIZE;
+    for (int e = t; e < P * P; e += S2V_THREADS) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww) s2 += acc[ww * P * P + e];
+        my[HP::TH7 + e] = s2;
+    }
+    if (t < 2 * P) {
+        float s2 = 0.f;
+#pragma unroll
+        for (int ww = 0; ww < NW; ++ww) s2 += red[ww * 2 * P + t];
+        my[(t < P ? HP::B7 : HP::W5B - P) + t] = s2;
+    }
+}
+
 template <int P>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_head_bwd(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const float* __restrict__ dq,
            const float* __restrict__ per_graph, int mask_relu, float* __restrict__ dmu,
            float* __restrict__ partial, int num_tiles, const unsigned int* __restrict__ nnz_total) {
-    const bool streamed = nnz_total != nullptr && HEAD_SPARSE(*nnz_total, g.num_nodes);
+    if (nnz_total != nullptr && HEAD_SPARSE(*nnz_total, g.num_nodes)) return;   // sparse dq: stream + rows kernels
     using C = Cfg<P>;
     using HP = HeadPartial<P>;
     extern __shared__ __align__(16) float smem[];
@@ -256,7 +360,6 @@ k_head_bwd(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, c
         // dmu reduces to the pooled term.  The DQN loss touches ONE node per graph
         // (qvals[actions + ptr[:-1]], comb_opt.py:355-356), so almost every tile takes this exit.
         const bool live = __syncthreads_or(t < rows && __ldg(dq + row0 + t) != 0.f);
-        if (!live && streamed) continue;                       // k_head_bwd_stream wrote these rows
         if (!live) {
             // streaming exit: all loads of the thread's chunks are issued before the first store; the graph of a row
             // comes from one division per tile (replicated layout) instead of one per chunk
@@ -501,6 +604,13 @@ static int head_backward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm
     int grid = s2v_persistent_grid((const void*)k_head_bwd<P>, smem, tiles);
     k_head_bwd<P><<<grid, S2V_THREADS, smem, st>>>(g, prm, mu, dq, per_graph, mask_relu, dmu, partial, tiles,
                                                    split ? nnz_total : nullptr);
+    if (split) {                                   // same grid => same partial rows, whichever of the two kernels is active
+        int rpc = (g.num_nodes + grid - 1) / grid;
+        rpc = (rpc + S2V_THREADS - 1) / S2V_THREADS * S2V_THREADS;
+        int smem_r = (P * (P + 1) + 4 * P * P + 4 * P + 4 * P + 2 * P + 4 * 2 * P) * 4;
+        S2V_RETURN_IF(cudaFuncSetAttribute(k_head_bwd_rows<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_r));
+        k_head_bwd_rows<P><<<grid, S2V_THREADS, smem_r, st>>>(g, prm, mu, dq, per_graph, mask_relu, dmu, partial, rpc, nnz_total);
+    }
     // per-graph terms, then fixed-order sums of both partial sets
     using GP = HeadGraphPartial<P>;
     float* partial_g = partial + (size_t)S2V_MAX_GRID * HP::SIZE;

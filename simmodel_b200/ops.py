@@ -111,7 +111,7 @@ def _head_backward(layout, norm_agg, mu, w, pool, gstate, dq, mask_relu, dmu_out
         _lib.check(L.s2v_head_backward(C.byref(layout.c_struct()), C.byref(prm), _p(mu), _p(pool), _p(gstate), _p(dq),
                                        int(mask_relu), _p(dmu_out), _p(ws), ws.numel(), _p(grad), _stream()),
                    "s2v_head_backward")
-    _lib.launch_count += 7 if n >= 4096 else 6       # + the streaming pass of large batches
+    _lib.launch_count += 8 if n >= 4096 else 6       # + the streaming pass and the sparse-rows pass of large batches
     return dmu_out, _split_head_grad(grad, P), grad
 
 
