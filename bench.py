@@ -553,6 +553,7 @@ def run_gat(args):
     dbar = layout.num_edges / n
     xlr = torch.randn(n, 2 * HC, device=dev)
     att, bias = torch.randn(HC, device=dev) * 0.1, torch.randn(HC, device=dev) * 0.1
+    lin_bias = torch.randn(2 * HC, device=dev) * 0.1           # as in the step: bias-free GEMM output + biases added at load
     out, stats = torch.empty(n, HC, device=dev), torch.empty(n, H, 4, device=dev)
     dout, dxlr, gab = torch.randn(n, HC, device=dev), torch.empty(n, 2 * HC, device=dev), torch.empty(4, HC, device=dev)
     ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(H, Cc), dtype=torch.uint8, device=dev)
@@ -560,11 +561,11 @@ def run_gat(args):
     xr_p, dxr_p = C.c_void_p(xlr.data_ptr() + 4 * HC), C.c_void_p(dxlr.data_ptr() + 4 * HC)
 
     def k_fwd():
-        _lib.check(L.s2v_gat_attn_forward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(bias), 1, _p(out), _p(stats),
+        _lib.check(L.s2v_gat_attn_forward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(bias), _p(lin_bias), 1, _p(out), _p(stats),
                                           _stream()), "gat fwd")
 
     def k_bwd():
-        _lib.check(L.s2v_gat_attn_backward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(stats), _p(dout), _p(dxlr),
+        _lib.check(L.s2v_gat_attn_backward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(lin_bias), _p(stats), _p(dout), _p(dxlr),
                                            dxr_p, _p(gab[0]), _p(gab[1]), _p(gab[2]), _p(ws), ws.numel(), _stream()), "gat bwd")
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0

@@ -224,6 +224,10 @@ int s2v_scatter_rows(const s2v_graph_t* g, const int64_t* arg, const float* dval
  *   heads H, channels C (per head); H*C <= 128
  *   xl, xr   [num_nodes, H*C] with row stride ld floats (two halves of one [n, 2HC] GEMM output)
  *   att [H*C], bias [H*C]
+ *   lin_bias [2*H*C] = lin_l.bias | lin_r.bias, or NULL.  When given, xl / xr are the BIAS-FREE products x W_l^T and
+ *            x W_r^T (the caller's GEMM then needs no bias epilogue pass over [n, 2HC]) and the kernels add b_l / b_r
+ *            to every x_l / x_r row as it is loaded -- the same fp32 add the epilogue would have done, so results are
+ *            identical to passing biased rows.  NULL: xl / xr already contain their biases.
  *   out      [num_nodes, H*C] = sum_j softmax_j(att . lrelu(xr[i] + xl[j], 0.2)) xl[j] + bias,
  *            ReLU applied when apply_relu != 0 (BasicGNN between layers)
  *   stats    [num_nodes, H, 4] out: per target and head (max score, 1 / den, D, den = softmax denominator + 1e-16);
@@ -235,11 +239,11 @@ int s2v_scatter_rows(const s2v_graph_t* g, const int64_t* arg, const float* dval
 #define S2V_GAT_MAX_GRID 2048
 int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                          const float* xl, const float* xr, const float* att, const float* bias,
-                         int32_t apply_relu, float* out, float* stats, void* stream);
+                         const float* lin_bias, int32_t apply_relu, float* out, float* stats, void* stream);
 int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels);
 int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
-                          const float* xl, const float* xr, const float* att, float* stats,
-                          const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
+                          const float* xl, const float* xr, const float* att, const float* lin_bias,
+                          float* stats, const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
                           float* grad_lin_bias, void* workspace, int64_t workspace_bytes, void* stream);
 
 #ifdef __cplusplus

@@ -49,6 +49,12 @@ __device__ __forceinline__ Vec<VEC> vzero() { Vec<VEC> r;
     for (int v = 0; v < VEC; ++v) r.v[v] = 0.f;
     return r; }
 
+template <int VEC>
+__device__ __forceinline__ Vec<VEC> vadd(Vec<VEC> a, const Vec<VEC>& b) {
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) a.v[v] += b.v[v];
+    return a;
+}
 __device__ __forceinline__ float lrelu(float s) { return fmaxf(s, s * GAT_SLOPE); }   // slope < 1
 // ex / den from the stored reciprocal with one Newton step (== the correctly rounded quotient up to the last bit)
 __device__ __forceinline__ float qdiv(float ex, float inv, float den) {
@@ -89,20 +95,24 @@ __device__ __forceinline__ float dot_partial(const Vec<VEC>& a, const Vec<VEC>& 
 template <int VEC>
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_fwd(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
-          const float* __restrict__ att, const float* __restrict__ bias, int apply_relu,
-          float* __restrict__ out, float* __restrict__ stats) {
+          const float* __restrict__ att, const float* __restrict__ bias, const float* __restrict__ lin_bias,
+          int apply_relu, float* __restrict__ out, float* __restrict__ stats) {
     const int lane = threadIdx.x & 31;
     const int HC = H * C, lanes = HC / VEC, lph = C / VEC;
     const bool active = lane < lanes;
     const int ch = active ? lane * VEC : 0;
     const int head = ch / C;
-    const Vec<VEC> a = ldv<VEC>(att + ch), b = ldv<VEC>(bias + ch);
+    const Vec<VEC> a = ldv<VEC>(att + ch);
+    const Vec<VEC> b = ldv<VEC>(bias + ch);
+    // x_l / x_r may arrive without their Linear biases (see the header): every row gets its bias as it is loaded, the
+    // same fp32 add a GEMM epilogue would have done
+    const Vec<VEC> bl = lin_bias ? ldv<VEC>(lin_bias + ch) : vzero<VEC>(), br = lin_bias ? ldv<VEC>(lin_bias + HC + ch) : vzero<VEC>();
     const int warp = blockIdx.x * GAT_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * GAT_WARPS;
     for (int r = warp; r < g.num_nodes; r += nwarps) {
         int li, off, gi;
         row_info(g, r, li, off, gi);
         const int beg = __ldg(g.rowptr_t + li), deg = __ldg(g.rowptr_t + li + 1) - beg, cnt = deg + 1;
-        const Vec<VEC> xri = ldv<VEC>(xr + (size_t)r * ld + ch);
+        const Vec<VEC> xri = vadd<VEC>(ldv<VEC>(xr + (size_t)r * ld + ch), br);
         Vec<VEC> acc = vzero<VEC>();
         float m = -INFINITY, inv, den;
         if (cnt <= GAT_FAST) {
@@ -112,7 +122,7 @@ k_gat_fwd(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ x
             for (int k = 0; k < GAT_FAST; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k);
             Vec<VEC> rows[GAT_FAST];
 #pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) rows[k] = k < cnt ? ldv<VEC>(xl + (size_t)js[k] * ld + ch) : vzero<VEC>();
+            for (int k = 0; k < GAT_FAST; ++k) rows[k] = k < cnt ? vadd<VEC>(ldv<VEC>(xl + (size_t)js[k] * ld + ch), bl) : vzero<VEC>();
             float sc[GAT_FAST];
 #pragma unroll
             for (int k = 0; k < GAT_FAST; ++k) sc[k] = head_sum(active ? score_partial<VEC>(a, xri, rows[k]) : 0.f, lph, lane);
@@ -131,19 +141,19 @@ k_gat_fwd(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ x
         } else {
             for (int k = 0; k < cnt; ++k) {
                 const int j = k < deg ? __ldg(g.col_t + beg + k) + off : r;
-                const Vec<VEC> row = ldv<VEC>(xl + (size_t)j * ld + ch);
+                const Vec<VEC> row = vadd<VEC>(ldv<VEC>(xl + (size_t)j * ld + ch), bl);
                 m = fmaxf(m, head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane));
             }
             float S = 0.f;
             for (int k = 0; k < cnt; ++k) {
                 const int j = k < deg ? __ldg(g.col_t + beg + k) + off : r;
-                const Vec<VEC> row = ldv<VEC>(xl + (size_t)j * ld + ch);
+                const Vec<VEC> row = vadd<VEC>(ldv<VEC>(xl + (size_t)j * ld + ch), bl);
                 S += expf(head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane) - m);
             }
             den = S + 1e-16f; inv = 1.f / den;
             for (int k = 0; k < cnt; ++k) {
                 const int j = k < deg ? __ldg(g.col_t + beg + k) + off : r;
-                const Vec<VEC> row = ldv<VEC>(xl + (size_t)j * ld + ch);
+                const Vec<VEC> row = vadd<VEC>(ldv<VEC>(xl + (size_t)j * ld + ch), bl);
                 const float al = qdiv(expf(head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane) - m), inv, den);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) acc.v[v] = fmaf(row.v[v], al, acc.v[v]);
@@ -176,8 +186,8 @@ __device__ __forceinline__ void bwd_a_edge(const Vec<VEC>& a, const Vec<VEC>& xr
 template <int VEC>
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
-                 const float* __restrict__ att, float* __restrict__ stats, const float* __restrict__ dout,
-                 float* __restrict__ dxr, float* __restrict__ partials) {
+                 const float* __restrict__ att, const float* __restrict__ lin_bias, float* __restrict__ stats,
+                 const float* __restrict__ dout, float* __restrict__ dxr, float* __restrict__ partials) {
     __shared__ float red[GAT_WARPS][3 * 128];
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const int HC = H * C, lanes = HC / VEC, lph = C / VEC;
@@ -185,13 +195,14 @@ k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restr
     const int ch = active ? lane * VEC : 0;
     const int head = ch / C;
     const Vec<VEC> a = ldv<VEC>(att + ch);
+    const Vec<VEC> bl = lin_bias ? ldv<VEC>(lin_bias + ch) : vzero<VEC>(), br = lin_bias ? ldv<VEC>(lin_bias + HC + ch) : vzero<VEC>();
     Vec<VEC> datt = vzero<VEC>(), dbias = vzero<VEC>(), dbr = vzero<VEC>();
     const int warp = blockIdx.x * GAT_WARPS + wid, nwarps = gridDim.x * GAT_WARPS;
     for (int r = warp; r < g.num_nodes; r += nwarps) {
         int li, off, gi;
         row_info(g, r, li, off, gi);
         const int beg = __ldg(g.rowptr_t + li), deg = __ldg(g.rowptr_t + li + 1) - beg, cnt = deg + 1;
-        const Vec<VEC> xri = ldv<VEC>(xr + (size_t)r * ld + ch);
+        const Vec<VEC> xri = vadd<VEC>(ldv<VEC>(xr + (size_t)r * ld + ch), br);
         const Vec<VEC> doi = ldv<VEC>(dout + (size_t)r * HC + ch);
         const float m = stats[((size_t)r * H + head) * 4], inv = stats[((size_t)r * H + head) * 4 + 1], den = stats[((size_t)r * H + head) * 4 + 3];
         Vec<VEC> dx = vzero<VEC>();
@@ -203,7 +214,7 @@ k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restr
             for (int k = 0; k < GAT_FAST; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k);
             Vec<VEC> rows[GAT_FAST];
 #pragma unroll
-            for (int k = 0; k < GAT_FAST; ++k) rows[k] = k < cnt ? ldv<VEC>(xl + (size_t)js[k] * ld + ch) : vzero<VEC>();
+            for (int k = 0; k < GAT_FAST; ++k) rows[k] = k < cnt ? vadd<VEC>(ldv<VEC>(xl + (size_t)js[k] * ld + ch), bl) : vzero<VEC>();
             float al[GAT_FAST], dal[GAT_FAST];
 #pragma unroll
             for (int k = 0; k < GAT_FAST; ++k) {
@@ -218,14 +229,14 @@ k_gat_bwd_target(const s2v_graph_t g, int H, int C, int ld, const float* __restr
         } else {
             for (int k = 0; k < cnt; ++k) {
                 const int j = k < deg ? __ldg(g.col_t + beg + k) + off : r;
-                const Vec<VEC> row = ldv<VEC>(xl + (size_t)j * ld + ch);
+                const Vec<VEC> row = vadd<VEC>(ldv<VEC>(xl + (size_t)j * ld + ch), bl);
                 const float e = head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane);
                 const float dl = head_sum(active ? dot_partial<VEC>(doi, row) : 0.f, lph, lane);
                 D = fmaf(qdiv(expf(e - m), inv, den), dl, D);
             }
             for (int k = 0; k < cnt; ++k) {
                 const int j = k < deg ? __ldg(g.col_t + beg + k) + off : r;
-                const Vec<VEC> row = ldv<VEC>(xl + (size_t)j * ld + ch);
+                const Vec<VEC> row = vadd<VEC>(ldv<VEC>(xl + (size_t)j * ld + ch), bl);
                 const float e = head_sum(active ? score_partial<VEC>(a, xri, row) : 0.f, lph, lane);
                 const float dl = head_sum(active ? dot_partial<VEC>(doi, row) : 0.f, lph, lane);
                 bwd_a_edge<VEC>(a, xri, row, qdiv(expf(e - m), inv, den), dl, D, dx, datt);
@@ -271,8 +282,8 @@ __device__ __forceinline__ void bwd_b_edge(const Vec<VEC>& a, const Vec<VEC>& xl
 template <int VEC>
 __global__ void __launch_bounds__(GAT_THREADS)
 k_gat_bwd_source(const s2v_graph_t g, int H, int C, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
-                 const float* __restrict__ att, const float* __restrict__ stats, const float* __restrict__ dout,
-                 float* __restrict__ dxl, float* __restrict__ partials) {
+                 const float* __restrict__ att, const float* __restrict__ lin_bias, const float* __restrict__ stats,
+                 const float* __restrict__ dout, float* __restrict__ dxl, float* __restrict__ partials) {
     __shared__ float red[GAT_WARPS][128];
     Vec<VEC> dbl = vzero<VEC>();
     const int lane = threadIdx.x & 31;
@@ -281,12 +292,13 @@ k_gat_bwd_source(const s2v_graph_t g, int H, int C, int ld, const float* __restr
     const int ch = active ? lane * VEC : 0;
     const int head = ch / C;
     const Vec<VEC> a = ldv<VEC>(att + ch);
+    const Vec<VEC> bl = lin_bias ? ldv<VEC>(lin_bias + ch) : vzero<VEC>(), br = lin_bias ? ldv<VEC>(lin_bias + HC + ch) : vzero<VEC>();
     const int warp = blockIdx.x * GAT_WARPS + (threadIdx.x >> 5), nwarps = gridDim.x * GAT_WARPS;
     for (int r = warp; r < g.num_nodes; r += nwarps) {
         int li, off, gi;
         row_info(g, r, li, off, gi);
         const int beg = __ldg(g.rowptr + li), deg = __ldg(g.rowptr + li + 1) - beg, cnt = deg + 1;
-        const Vec<VEC> xlj = ldv<VEC>(xl + (size_t)r * ld + ch);
+        const Vec<VEC> xlj = vadd<VEC>(ldv<VEC>(xl + (size_t)r * ld + ch), bl);
         Vec<VEC> dx = vzero<VEC>();
         if (cnt <= GAT_FAST) {
             const int il = lane < deg ? __ldg(g.col + beg + lane) + off : r;
@@ -298,7 +310,7 @@ k_gat_bwd_source(const s2v_graph_t g, int H, int C, int ld, const float* __restr
 #pragma unroll
             for (int k = 0; k < GAT_FAST; ++k) {
                 const bool on = k < cnt;
-                xrs[k] = on ? ldv<VEC>(xr + (size_t)is[k] * ld + ch) : vzero<VEC>();
+                xrs[k] = on ? vadd<VEC>(ldv<VEC>(xr + (size_t)is[k] * ld + ch), br) : vzero<VEC>();
                 dos[k] = on ? ldv<VEC>(dout + (size_t)is[k] * HC + ch) : vzero<VEC>();
                 st[k] = on ? ldg4(stats + ((size_t)is[k] * H + head) * 4) : f4zero();
             }
@@ -311,7 +323,7 @@ k_gat_bwd_source(const s2v_graph_t g, int H, int C, int ld, const float* __restr
         } else {
             for (int k = 0; k < cnt; ++k) {
                 const int i = k < deg ? __ldg(g.col + beg + k) + off : r;
-                const Vec<VEC> xri = ldv<VEC>(xr + (size_t)i * ld + ch);
+                const Vec<VEC> xri = vadd<VEC>(ldv<VEC>(xr + (size_t)i * ld + ch), br);
                 const Vec<VEC> doi = ldv<VEC>(dout + (size_t)i * HC + ch);
                 const float4 st = ldg4(stats + ((size_t)i * H + head) * 4);
                 const float e = head_sum(active ? score_partial<VEC>(a, xri, xlj) : 0.f, lph, lane);
@@ -378,11 +390,13 @@ __device__ __forceinline__ int row_ids(const RowMeta& m, const int* __restrict__
     return sl < m.deg ? __ldg(ci + m.beg + sl) + m.off : m.r;
 }
 
-#define GAT_ROW_LOOP(RP, CI)                                                                                    \
+#define GAT_ROW_SETUP()                                                                                         \
     const int lane = threadIdx.x & 31, sub = lane / LPR, sl = lane % LPR;                                       \
     const int ch = sl * 4, head = sl / LPH;                                                                     \
     const int step = gridDim.x * GAT_WARPS * RPW;                                                               \
-    int r0 = (blockIdx.x * GAT_WARPS + (threadIdx.x >> 5)) * RPW;                                               \
+    int r0 = (blockIdx.x * GAT_WARPS + (threadIdx.x >> 5)) * RPW;
+
+#define GAT_ROW_LOOP(RP, CI)                                                                                    \
     RowMeta cur = row_meta(g, RP, r0 + sub);                                                                    \
     int jl = row_ids(cur, CI, sl);                                                                              \
     RowMeta nxt = row_meta(g, RP, r0 + step + sub);                                                             \
@@ -403,13 +417,13 @@ __device__ __forceinline__ int warp_max_cnt(int cnt) {
 // Register-resident paths for rows with at most NS neighbours (incl. the self edge); NS = 4 or 8 is chosen per warp.
 template <int LPR, int LPH, int NS>
 __device__ __forceinline__ void fwd_fast(const float* __restrict__ xl, int ld, int ch, int jl, int cnt, const float4& a,
-                                         const float4& xri, float4& acc, float& m, float& inv, float& den) {
+                                         const float4& bl, const float4& xri, float4& acc, float& m, float& inv, float& den) {
     int js[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
     float4 rows[NS];
 #pragma unroll
-    for (int k = 0; k < NS; ++k) rows[k] = k < cnt ? ldg4(xl + (size_t)js[k] * ld + ch) : f4zero();
+    for (int k = 0; k < NS; ++k) rows[k] = k < cnt ? f4add(ldg4(xl + (size_t)js[k] * ld + ch), bl) : f4zero();
     float sc[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) sc[k] = hsum<LPH>(score4(a, xri, rows[k]));
@@ -430,27 +444,30 @@ __device__ __forceinline__ void fwd_fast(const float* __restrict__ xl, int ld, i
 template <int LPR, int LPH>
 __global__ void __launch_bounds__(GAT_THREADS, 3)
 k_gat_fwd4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
-           const float* __restrict__ att, const float* __restrict__ bias, int apply_relu,
-           float* __restrict__ out, float* __restrict__ stats) {
+           const float* __restrict__ att, const float* __restrict__ bias, const float* __restrict__ lin_bias,
+           int apply_relu, float* __restrict__ out, float* __restrict__ stats) {
     constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
+    GAT_ROW_SETUP()
+    const float4 a = ldg4(att + ch), b = ldg4(bias + ch);
+    // x_l / x_r may arrive without their Linear biases: every row gets its bias as it is loaded
+    const float4 bl = lin_bias ? ldg4(lin_bias + ch) : f4zero(), br = lin_bias ? ldg4(lin_bias + HC + ch) : f4zero();
     GAT_ROW_LOOP(g.rowptr_t, g.col_t) {
         GAT_ROW_ADVANCE(g.rowptr_t, g.col_t)
-        const float4 a = ldg4(att + ch), b = ldg4(bias + ch);
         const int r = cur.r, cnt = cur.deg + 1;
         const bool valid = cnt > 0;
-        const float4 xri = valid ? ldg4(xr + (size_t)r * ld + ch) : f4zero();
+        const float4 xri = valid ? f4add(ldg4(xr + (size_t)r * ld + ch), br) : f4zero();
         float4 acc = f4zero();
         float m = -INFINITY, inv = 0.f, den = 1.f;
         const int mc = warp_max_cnt<LPR>(cnt);
-        if (mc <= 4) fwd_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, xri, acc, m, inv, den);
-        else if (mc <= GAT_FAST) fwd_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, xri, acc, m, inv, den);
+        if (mc <= 4) fwd_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, bl, xri, acc, m, inv, den);
+        else if (mc <= GAT_FAST) fwd_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, bl, xri, acc, m, inv, den);
         else {
             float S = 0.f;
             for (int pass = 0; pass < 3; ++pass) {
                 for (int k = 0; k < mc; ++k) {
                     const bool on = k < cnt;
                     const int j = on && k < cur.deg ? __ldg(g.col_t + cur.beg + k) + cur.off : r;
-                    const float4 row = on ? ldg4(xl + (size_t)j * ld + ch) : f4zero();
+                    const float4 row = on ? f4add(ldg4(xl + (size_t)j * ld + ch), bl) : f4zero();
                     const float e = hsum<LPH>(score4(a, xri, row));
                     if (!on) continue;
                     if (pass == 0) m = fmaxf(m, e);
@@ -484,14 +501,14 @@ __device__ __forceinline__ void bwd_a_edge4(const float4& a, const float4& xri, 
 
 template <int LPR, int LPH, int NS>
 __device__ __forceinline__ void bwd_target_fast(const float* __restrict__ xl, int ld, int ch, int jl, int cnt, const float4& a,
-                                                const float4& xri, const float4& doi, const float4& st, float& D,
+                                                const float4& bl, const float4& xri, const float4& doi, const float4& st, float& D,
                                                 float4& dx, float4& datt) {
     int js[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
     float4 rows[NS];
 #pragma unroll
-    for (int k = 0; k < NS; ++k) rows[k] = k < cnt ? ldg4(xl + (size_t)js[k] * ld + ch) : f4zero();
+    for (int k = 0; k < NS; ++k) rows[k] = k < cnt ? f4add(ldg4(xl + (size_t)js[k] * ld + ch), bl) : f4zero();
     float al[NS], dal[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
@@ -508,30 +525,32 @@ __device__ __forceinline__ void bwd_target_fast(const float* __restrict__ xl, in
 template <int LPR, int LPH>
 __global__ void __launch_bounds__(GAT_THREADS, 2)
 k_gat_bwd_target4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
-                  const float* __restrict__ att, float* __restrict__ stats, const float* __restrict__ dout,
-                  float* __restrict__ dxr, float* __restrict__ partials) {
+                  const float* __restrict__ att, const float* __restrict__ lin_bias, float* __restrict__ stats,
+                  const float* __restrict__ dout, float* __restrict__ dxr, float* __restrict__ partials) {
     constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
     __shared__ float red[GAT_WARPS * RPW][3 * HC];
     float4 datt = f4zero(), dbias = f4zero(), dbr = f4zero();
+    GAT_ROW_SETUP()
+    const float4 a = ldg4(att + ch);
+    const float4 bl = lin_bias ? ldg4(lin_bias + ch) : f4zero(), br = lin_bias ? ldg4(lin_bias + HC + ch) : f4zero();
     GAT_ROW_LOOP(g.rowptr_t, g.col_t) {
         GAT_ROW_ADVANCE(g.rowptr_t, g.col_t)
-        const float4 a = ldg4(att + ch);
         const int r = cur.r, cnt = cur.deg + 1;
         const bool valid = cnt > 0;
-        const float4 xri = valid ? ldg4(xr + (size_t)r * ld + ch) : f4zero();
+        const float4 xri = valid ? f4add(ldg4(xr + (size_t)r * ld + ch), br) : f4zero();
         const float4 doi = valid ? ldg4(dout + (size_t)r * HC + ch) : f4zero();
         const float4 st = valid ? ld4(stats + ((size_t)r * H + head) * 4) : f4zero();
         float4 dx = f4zero();
         float D = 0.f;
         const int mc = warp_max_cnt<LPR>(cnt);
-        if (mc <= 4) bwd_target_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, xri, doi, st, D, dx, datt);
-        else if (mc <= GAT_FAST) bwd_target_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, xri, doi, st, D, dx, datt);
+        if (mc <= 4) bwd_target_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, bl, xri, doi, st, D, dx, datt);
+        else if (mc <= GAT_FAST) bwd_target_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, bl, xri, doi, st, D, dx, datt);
         else {
             for (int pass = 0; pass < 2; ++pass)
                 for (int k = 0; k < mc; ++k) {
                     const bool on = k < cnt;
                     const int j = on && k < cur.deg ? __ldg(g.col_t + cur.beg + k) + cur.off : r;
-                    const float4 row = on ? ldg4(xl + (size_t)j * ld + ch) : f4zero();
+                    const float4 row = on ? f4add(ldg4(xl + (size_t)j * ld + ch), bl) : f4zero();
                     const float e = hsum<LPH>(score4(a, xri, row));
                     const float dl = hsum<LPH>(dot4(doi, row));
                     if (!on) continue;
@@ -574,7 +593,7 @@ __device__ __forceinline__ void bwd_b_edge4(const float4& a, const float4& xlj, 
 template <int LPR, int LPH, int NS>
 __device__ __forceinline__ void bwd_source_fast(const float* __restrict__ xr, const float* __restrict__ dout,
                                                 const float* __restrict__ stats, int ld, int ch, int head, int il, int cnt,
-                                                int k0, const float4& a, const float4& xlj, float4& dx) {
+                                                int k0, const float4& a, const float4& br, const float4& xlj, float4& dx) {
     constexpr int HC = 4 * LPR, H = LPR / LPH;
     int is[NS];
 #pragma unroll
@@ -584,7 +603,7 @@ __device__ __forceinline__ void bwd_source_fast(const float* __restrict__ xr, co
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         const bool on = k < cnt;
-        xrs[k] = on ? ldg4(xr + (size_t)is[k] * ld + ch) : f4zero();
+        xrs[k] = on ? f4add(ldg4(xr + (size_t)is[k] * ld + ch), br) : f4zero();
         dos[k] = on ? ldg4(dout + (size_t)is[k] * HC + ch) : f4zero();
         sts[k] = on ? ldg4(stats + ((size_t)is[k] * H + head) * 4) : f4zero();
     }
@@ -602,27 +621,29 @@ __device__ __forceinline__ void bwd_source_fast(const float* __restrict__ xr, co
 template <int LPR, int LPH>
 __global__ void __launch_bounds__(GAT_THREADS, 2)
 k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
-                  const float* __restrict__ att, const float* __restrict__ stats, const float* __restrict__ dout,
-                  float* __restrict__ dxl, float* __restrict__ partials) {
+                  const float* __restrict__ att, const float* __restrict__ lin_bias, const float* __restrict__ stats,
+                  const float* __restrict__ dout, float* __restrict__ dxl, float* __restrict__ partials) {
     constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
     __shared__ float red[GAT_WARPS * RPW][HC];
     float4 dbl = f4zero();
+    GAT_ROW_SETUP()
+    const float4 a = ldg4(att + ch);
+    const float4 bl = lin_bias ? ldg4(lin_bias + ch) : f4zero(), br = lin_bias ? ldg4(lin_bias + HC + ch) : f4zero();
     GAT_ROW_LOOP(g.rowptr, g.col) {
         GAT_ROW_ADVANCE(g.rowptr, g.col)
-        const float4 a = ldg4(att + ch);
         const int r = cur.r, cnt = cur.deg + 1;
         const bool valid = cnt > 0;
-        const float4 xlj = valid ? ldg4(xl + (size_t)r * ld + ch) : f4zero();
+        const float4 xlj = valid ? f4add(ldg4(xl + (size_t)r * ld + ch), bl) : f4zero();
         float4 dx = f4zero();
         const int mc = warp_max_cnt<LPR>(cnt);
         if (mc <= GAT_FAST) {             // the edges of a source are independent: batches of four keep the registers low
-            bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, 0, a, xlj, dx);
-            if (mc > 4) bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, 4, a, xlj, dx);
+            bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, 0, a, br, xlj, dx);
+            if (mc > 4) bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, 4, a, br, xlj, dx);
         } else {
             for (int k = 0; k < mc; ++k) {
                 const bool on = k < cnt;
                 const int i = on && k < cur.deg ? __ldg(g.col + cur.beg + k) + cur.off : r;
-                const float4 xri = on ? ldg4(xr + (size_t)i * ld + ch) : f4zero();
+                const float4 xri = on ? f4add(ldg4(xr + (size_t)i * ld + ch), br) : f4zero();
                 const float4 doi = on ? ldg4(dout + (size_t)i * HC + ch) : f4zero();
                 const float4 st = on ? ldg4(stats + ((size_t)i * H + head) * 4) : f4zero();
                 const float e = hsum<LPH>(score4(a, xri, xlj));
@@ -725,7 +746,7 @@ int gat_grid(int num_nodes, int rows_per_cta) {
 
 extern "C" int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                                     const float* xl, const float* xr, const float* att, const float* bias,
-                                    int32_t apply_relu, float* out, float* stats, void* stream) {
+                                    const float* lin_bias, int32_t apply_relu, float* out, float* stats, void* stream) {
     S2V_RETURN_IF(gat_check(g, heads, channels, ld));
     if (!xl || !xr || !att || !bias || !out || !stats) return S2V_ERR_BAD_ARG;
     if (g->num_nodes == 0) return 0;
@@ -733,11 +754,11 @@ extern "C" int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t
     const int sp = gat_special(heads, channels, ld);
     if (sp) {
         const int grid = gat_grid(g->num_nodes, GAT_WARPS * (sp == 1 ? 1 : 2));
-        GAT_SPECIAL(sp, (k_gat_fwd4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, bias, apply_relu, out, stats)));
+        GAT_SPECIAL(sp, (k_gat_fwd4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, bias, lin_bias, apply_relu, out, stats)));
     } else {
         const int grid = gat_grid(g->num_nodes, GAT_WARPS);
         GAT_DISPATCH(gat_vec(heads, channels),
-                     (k_gat_fwd<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, bias, apply_relu, out, stats)));
+                     (k_gat_fwd<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, bias, lin_bias, apply_relu, out, stats)));
     }
     return (int)cudaGetLastError();
 }
@@ -747,8 +768,8 @@ extern "C" int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t 
 }
 
 extern "C" int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
-                                     const float* xl, const float* xr, const float* att, float* stats,
-                                     const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
+                                     const float* xl, const float* xr, const float* att, const float* lin_bias,
+                                     float* stats, const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
                                      float* grad_lin_bias, void* workspace, int64_t workspace_bytes, void* stream) {
     S2V_RETURN_IF(gat_check(g, heads, channels, ld));
     if (!xl || !xr || !att || !stats || !dout || !dxl || !dxr || !grad_att || !grad_bias || !grad_lin_bias || !workspace) return S2V_ERR_BAD_ARG;
@@ -766,16 +787,16 @@ extern "C" int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_
     int grid;
     if (sp) {
         grid = gat_grid(g->num_nodes, GAT_WARPS * (sp == 1 ? 1 : 2));
-        GAT_SPECIAL(sp, (k_gat_bwd_target4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, stats, dout, dxr, partials)));
+        GAT_SPECIAL(sp, (k_gat_bwd_target4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, lin_bias, stats, dout, dxr, partials)));
         S2V_RETURN_IF(cudaGetLastError());
-        GAT_SPECIAL(sp, (k_gat_bwd_source4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, stats, dout, dxl, partials)));
+        GAT_SPECIAL(sp, (k_gat_bwd_source4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, lin_bias, stats, dout, dxl, partials)));
     } else {
         grid = gat_grid(g->num_nodes, GAT_WARPS);
         GAT_DISPATCH(gat_vec(heads, channels),
-                     (k_gat_bwd_target<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dxr, partials)));
+                     (k_gat_bwd_target<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, lin_bias, stats, dout, dxr, partials)));
         S2V_RETURN_IF(cudaGetLastError());
         GAT_DISPATCH(gat_vec(heads, channels),
-                     (k_gat_bwd_source<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, stats, dout, dxl, partials)));
+                     (k_gat_bwd_source<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, lin_bias, stats, dout, dxl, partials)));
     }
     S2V_RETURN_IF(cudaGetLastError());
     k_gat_reduce<<<4 * HC, 128, 0, st>>>(partials, grid, HC, grad_att, grad_bias, grad_lin_bias);

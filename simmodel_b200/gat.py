@@ -71,12 +71,9 @@ class _GATConvFn(torch.autograd.Function):
         shared = wr is None
         if x.shape[0] != n or x.shape[1] != wl.shape[1]:
             raise ValueError("x has shape %s, expected (%d, %d)" % (tuple(x.shape), n, wl.shape[1]))
-        if shared:
-            wcat, bcat = wl.detach(), bl.detach()
-        else:
-            wcat = torch.cat((wl.detach(), wr.detach()), dim=0)              # [2HC, in]
-            bcat = torch.cat((bl.detach(), br.detach()), dim=0)
-        xlr = torch.addmm(bcat, x, wcat.t())                                 # [n, 2HC]: x_l | x_r  (plain GEMM)
+        wcat = wl.detach() if shared else torch.cat((wl.detach(), wr.detach()), dim=0)      # [2HC, in]
+        bcat = torch.cat((bl.detach(), bl.detach() if shared else br.detach()), dim=0)     # lin_l.bias | lin_r.bias
+        xlr = x.mm(wcat.t())                             # [n, 2HC]: x_l | x_r without biases (plain GEMM, no epilogue pass)
         ld = int(xlr.shape[1])
         xr_ptr = _p(xlr) if shared else C.c_void_p(xlr.data_ptr() + 4 * HC)
         att_f = ops._f32c(att.detach().reshape(-1), "att")
@@ -85,16 +82,17 @@ class _GATConvFn(torch.autograd.Function):
         stats = torch.empty(n, heads, 4, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             _lib.check(L.s2v_gat_attn_forward(C.byref(layout.c_struct()), heads, Cc, ld, _p(xlr), xr_ptr, _p(att_f),
-                                              _p(bias_f), int(relu), _p(out), _p(stats), _stream()), "s2v_gat_attn_forward")
+                                              _p(bias_f), _p(bcat), int(relu), _p(out), _p(stats), _stream()),
+                       "s2v_gat_attn_forward")
         _lib.launch_count += 1
         ctx.layout, ctx.heads, ctx.relu, ctx.shared = layout, heads, relu, shared
-        ctx.save_for_backward(x, xlr, stats, out, att_f, wcat)
+        ctx.save_for_backward(x, xlr, stats, out, att_f, wcat, bcat)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         L = _lib.lib()
-        x, xlr, stats, out, att_f, wcat = ctx.saved_tensors
+        x, xlr, stats, out, att_f, wcat, bcat = ctx.saved_tensors
         layout, heads, shared = ctx.layout, ctx.heads, ctx.shared
         n, HC = layout.num_nodes, int(out.shape[1])
         Cc = HC // heads
@@ -113,7 +111,7 @@ class _GATConvFn(torch.autograd.Function):
             gab = torch.empty(4, HC, dtype=torch.float32, device=x.device)       # datt | dbias | dlin_l.bias | dlin_r.bias
             ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(heads, Cc), dtype=torch.uint8, device=x.device)
             _lib.check(L.s2v_gat_attn_backward(C.byref(layout.c_struct()), heads, Cc, ld, _p(xlr), xr_ptr, _p(att_f),
-                                               _p(stats), _p(dout), _p(dxlr), dxr_ptr, _p(gab[0]), _p(gab[1]),
+                                               _p(bcat), _p(stats), _p(dout), _p(dxlr), dxr_ptr, _p(gab[0]), _p(gab[1]),
                                                _p(gab[2]), _p(ws), ws.numel(), _stream()), "s2v_gat_attn_backward")
         _lib.launch_count += 3
         if shared:
