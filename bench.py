@@ -547,41 +547,45 @@ def run_gat(args):
     ms = timed(step, args.steps, 0)
     clocks = sampler.stop()
     e2e_ms = None if args.no_e2e else timed(step_e2e, max(3, min(args.steps, 10)), 2)
-    # ---- the edge-attention kernels alone (hidden layer shape: H=2, C=32) ----
-    n, H, Cc = layout.num_nodes, 2, P // 2
-    HC = H * Cc
+    # ---- the edge-attention kernels alone: the model's layer shape (H=2, C=32) and the PPO gat2 shapes ----
+    n = layout.num_nodes
     dbar = layout.num_edges / n
-    xlr = torch.randn(n, 2 * HC, device=dev)
-    att, bias = torch.randn(HC, device=dev) * 0.1, torch.randn(HC, device=dev) * 0.1
-    lin_bias = torch.randn(2 * HC, device=dev) * 0.1           # as in the step: bias-free GEMM output + biases added at load
-    out, stats = torch.empty(n, HC, device=dev), torch.empty(n, H, 4, device=dev)
-    dout, dxlr, gab = torch.randn(n, HC, device=dev), torch.empty(n, 2 * HC, device=dev), torch.empty(4, HC, device=dev)
-    ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(H, Cc), dtype=torch.uint8, device=dev)
     g = layout.c_struct()
-    xr_p, dxr_p = C.c_void_p(xlr.data_ptr() + 4 * HC), C.c_void_p(dxlr.data_ptr() + 4 * HC)
-
-    def k_fwd():
-        _lib.check(L.s2v_gat_attn_forward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(bias), _p(lin_bias), 1, _p(out), _p(stats),
-                                          _stream()), "gat fwd")
-
-    def k_bwd():
-        _lib.check(L.s2v_gat_attn_backward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(lin_bias), _p(stats), _p(dout), _p(dxlr),
-                                           dxr_p, _p(gab[0]), _p(gab[1]), _p(gab[2]), _p(ws), ws.numel(), _stream()), "gat bwd")
     peaks_path = os.path.join(ROOT, "MEASURED_PEAKS.json")
     peak = float(json.load(open(peaks_path))["hbm_gbs"]) if os.path.exists(peaks_path) else 6650.0
-    # forward: (dbar+1) x_l rows + x_r row read, out row written, ids + rowptr, stats written
-    fwd_bytes = 4 * (HC * (dbar + 3) + dbar + 1 + 2 * H)
-    # backward (both kernels): target pass reads (dbar+1) x_l rows + x_r + dout + stats, writes dx_r + D;
-    # source pass reads x_l + (dbar+1) x (x_r, dout, stats, D) rows, writes dx_l; ids + rowptr twice
-    bwd_bytes = 4 * (HC * (dbar + 1 + 3) + 3 * H + HC * (1 + 2 * (dbar + 1) + 1) + 3 * H * (dbar + 1) + 2 * (dbar + 1))
     kernels = []
-    for name, fn, bpn in (("k_gat_fwd<2> (H=2, C=32)", k_fwd, fwd_bytes),
-                          ("k_gat_bwd_target + k_gat_bwd_source<2> (H=2, C=32)", k_bwd, bwd_bytes)):
-        k_ms = timed(fn, 10, 3)
-        ach = bpn * n / (k_ms / 1e3) / 1e9
-        kernels.append({"kernel": name, "ms": k_ms, "algorithmic_bytes": bpn * n, "achieved_GBps": ach, "frac": ach / peak,
-                        "launches_per_step": 5})
-    dom = max(kernels, key=lambda r: r["ms"])
+    shapes = [(2, P // 2, 5)] + ([(4, 32, 0), (4, 16, 0)] if n * 256 * 4 * 8 < 60e9 else [])    # (heads, channels, launches per step)
+    for H, Cc, per_step in shapes:
+        HC = H * Cc
+        xlr = torch.randn(n, 2 * HC, device=dev)
+        att, bias = torch.randn(HC, device=dev) * 0.1, torch.randn(HC, device=dev) * 0.1
+        lin_bias = torch.randn(2 * HC, device=dev) * 0.1       # as in the step: bias-free GEMM output + biases added at load
+        out, stats = torch.empty(n, HC, device=dev), torch.empty(n, H, 4, device=dev)
+        dout, dxlr, gab = torch.randn(n, HC, device=dev), torch.empty(n, 2 * HC, device=dev), torch.empty(4, HC, device=dev)
+        ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(H, Cc), dtype=torch.uint8, device=dev)
+        xr_p, dxr_p = C.c_void_p(xlr.data_ptr() + 4 * HC), C.c_void_p(dxlr.data_ptr() + 4 * HC)
+
+        def k_fwd():
+            _lib.check(L.s2v_gat_attn_forward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(bias), _p(lin_bias), 1,
+                                              _p(out), _p(stats), _stream()), "gat fwd")
+
+        def k_bwd():
+            _lib.check(L.s2v_gat_attn_backward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(lin_bias), _p(stats), _p(dout),
+                                               _p(dxlr), dxr_p, _p(gab[0]), _p(gab[1]), _p(gab[2]), _p(ws), ws.numel(), _stream()),
+                       "gat bwd")
+        # forward: (dbar+1) x_l rows + x_r row read, out row written, ids + rowptr, statistics written
+        fwd_bytes = 4 * (HC * (dbar + 3) + dbar + 1 + 4 * H)
+        # backward (both kernels): target pass reads (dbar+1) x_l rows + x_r + dout + statistics, writes dx_r + D;
+        # source pass reads x_l + (dbar+1) x (x_r, dout, statistics) rows, writes dx_l; ids + rowptr twice
+        bwd_bytes = 4 * (HC * (dbar + 1 + 3) + 5 * H + HC * (1 + 2 * (dbar + 1) + 1) + 4 * H * (dbar + 1) + 2 * (dbar + 1))
+        for name, fn, bpn in (("k_gat_fwd4 (H=%d, C=%d)" % (H, Cc), k_fwd, fwd_bytes),
+                              ("k_gat_bwd_target4 + k_gat_bwd_source4 (H=%d, C=%d)" % (H, Cc), k_bwd, bwd_bytes)):
+            k_ms = timed(fn, 10, 3)
+            ach = bpn * n / (k_ms / 1e3) / 1e9
+            kernels.append({"kernel": name, "ms": k_ms, "algorithmic_bytes": bpn * n, "achieved_GBps": ach, "frac": ach / peak,
+                            "launches_per_step": per_step})
+        del xlr, out, stats, dout, dxlr
+    dom = max(kernels[:2], key=lambda r: r["ms"])
     edge_ms = sum(k["ms"] * k["launches_per_step"] for k in kernels)
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
                 "frac": dom["frac"], "traffic": None, "algorithmic_bytes_per_row": dom["algorithmic_bytes"] / n,

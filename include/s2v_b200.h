@@ -246,6 +246,25 @@ int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels,
                           float* stats, const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
                           float* grad_lin_bias, void* workspace, int64_t workspace_bytes, void* stream);
 
+/* ---------------------------------------------------------------------------------
+ * Node-wise linear layers of the GATv2 branch on the tensor cores (tcgen05, bf16x3 split precision, fp32
+ * accumulate; ~3e-7 of the output scale).  Replace the lin_l / lin_r matmuls inside GATv2Conv.forward and their
+ * autograd (torch_geometric GATv2Conv: x_l = self.lin_l(x), x_r = self.lin_r(x); comb_opt.py:94) for feature
+ * widths that are multiples of 64.  Rows = nodes; all matrices row-major fp32, leading dimensions in floats.
+ *   s2v_rows_gemm64 :  out[n, 64 nb] = A[n, 64 kb] * Wt, optionally * (mask > 0)  (mask [n, 64 nb])
+ *        transpose_w = 0: W is [64 nb, 64 kb], out = A W^T      (forward: kb = 1, nb = 2)
+ *        transpose_w = 1: W is [64 kb, 64 nb], out = A W        (backward dx: kb = 2, nb = 1; mask = the layer
+ *                                                                input, i.e. the ReLU mask of the previous layer)
+ *        supported (kb, nb, transpose_w): (1, 2, 0), (2, 1, 1); anything else returns S2V_ERR_UNSUPPORTED
+ *   s2v_rows_reduce64 : out[64 ab, 64] = A[n, 64 ab]^T B[n, 64]  (weight gradient; ab = 2), per-CTA partials in
+ *        workspace summed in fixed order.
+ * --------------------------------------------------------------------------------- */
+int s2v_rows_gemm64(const float* A, int32_t lda, int32_t k_blocks, const float* W, int32_t n_blocks, int32_t transpose_w,
+                    const float* mask, int32_t ldm, float* out, int32_t ldo, int64_t n, void* stream);
+int64_t s2v_rows_reduce64_workspace_bytes(int32_t a_blocks);
+int s2v_rows_reduce64(const float* A, int32_t lda, int32_t a_blocks, const float* B, int32_t ldb, float* out,
+                      void* workspace, int64_t workspace_bytes, int64_t n, void* stream);
+
 #ifdef __cplusplus
 }
 #endif

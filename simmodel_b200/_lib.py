@@ -64,6 +64,9 @@ SIGNATURES = {
     "s2v_scatter_rows": (C.c_int, [GP, vp, vp, vp, vp]),
     "s2v_gat_attn_forward": (C.c_int, [GP, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
     "s2v_gat_attn_backward_workspace_bytes": (i64, [i32, i32]),
+    "s2v_rows_gemm64": (C.c_int, [vp, i32, i32, vp, i32, i32, vp, i32, vp, i32, i64, vp]),
+    "s2v_rows_reduce64_workspace_bytes": (i64, [i32]),
+    "s2v_rows_reduce64": (C.c_int, [vp, i32, i32, vp, i32, vp, vp, i64, i64, vp]),
     "s2v_gat_attn_backward": (C.c_int, [GP, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
 }
 

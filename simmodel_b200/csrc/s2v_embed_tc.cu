@@ -1698,6 +1698,206 @@ constexpr int FIRST_SMEM = 4 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 
 constexpr int FIN_SMEM = 6 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 64 + 128) * 4 + 64 + 1024;
 constexpr int BWD_SMEM = 6 * TILE_BYTES + 64 + 1024;
 
+// ------------------------------------------------------------------------------------
+// Node-wise linear layers of the GATv2 branch on the tensor cores (bf16x3, fp32 accuracy ~3e-7 of scale):
+//   k_rows_gemm16<KB,NB,MASK>:  out[n, 64 NB] = A[n, 64 KB] * Wt   (+ optional (mask > 0) on the output)
+//       forward  x_l | x_r = x [Wl;Wr]^T :  KB = 1, NB = 2, B tile(nb)(n, k) = W[64 nb + n][k]
+//       backward dx = [dx_l | dx_r] [Wl;Wr] * [x > 0] :  KB = 2, NB = 1, B tile(kb)(k, n) = W[64 kb + n][k]
+//   k_rows_reduce16<AB>:  partial[cta][64 AB, 64] = sum over the CTA's tiles of A[:, 64 ab ..]^T B   (dW = dxlr^T x)
+// Tile = 64 rows; same single-tile pipeline as k_head_tc: rows of the next tile are in flight (registers) during the
+// MMAs and the epilogue, several CTAs per SM interleave their phases.
+// ------------------------------------------------------------------------------------
+__device__ __forceinline__ void issue_transform16_acc(uint32_t d_tmem, uint32_t a1, uint32_t b1, bool accumulate) {
+    constexpr uint32_t idesc = tc::idesc_bf16(64, 64, 0, 0);
+#pragma unroll
+    for (int p = 0; p < 6; ++p) {
+        int i, j;
+        pair6(p, i, j);
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            tc::mma_bf16(d_tmem, tc::desc_k16(a1 + i * TILE16, ks), tc::desc_k16(b1 + j * TILE16, ks), idesc,
+                         accumulate || p > 0 || ks > 0);
+    }
+}
+
+template <int KB, int NB, bool MASK>
+__global__ void __launch_bounds__(TC_THREADS)
+k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W, int transpose_w,
+              const float* __restrict__ M, int ldm, float* __restrict__ out, int ldo, int n, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w1 = smem;                                   // NB x KB weight blocks, three bf16 tiles each
+    uint8_t* a1 = w1 + NB * KB * TILE16X3;                // KB row tiles; reused as the fp32 staging of the epilogue
+    TcShared* sh = reinterpret_cast<TcShared*>(a1 + KB * TILE16X3);
+    float* stg = reinterpret_cast<float*>(a1);
+    const int t = threadIdx.x, warp = t >> 5;
+    if (warp == 0) tc::tmem_alloc<64 * NB>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    for (int nb = 0; nb < NB; ++nb)
+        for (int kb = 0; kb < KB; ++kb)                    // W is [64 NB, 64] (forward) or [64 KB, 64] (transposed use)
+            load_weight_tiles16(w1 + (nb * KB + kb) * TILE16X3, W + (size_t)(transpose_w ? kb : nb) * 64 * 64, transpose_w != 0,
+                                TC_THREADS);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d = sh->tmem_base;
+    const uint32_t s_a = tc::smem_u32(a1), s_w = tc::smem_u32(w1);
+    uint32_t phase = 0;
+    float4 m[KB][8];
+    auto load_rows = [&](int tile) {
+        const int row0 = tile * TCR, rows = min(TCR, n - row0);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+                m[kb][i] = rl < rows ? ldg4(A + (size_t)(row0 + rl) * lda + 64 * kb + 4 * c4) : f4zero();
+            }
+    };
+    if (blockIdx.x < num_tiles) load_rows(blockIdx.x);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR, rows = min(TCR, n - row0);
+#pragma unroll
+        for (int kb = 0; kb < KB; ++kb)
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = t + TC_THREADS * i;
+                store_split3(a1 + kb * TILE16X3, e >> 4, e & 15, m[kb][i]);
+            }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            tc::tc_fence_after_sync();
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int kb = 0; kb < KB; ++kb)
+                    issue_transform16_acc(d + 64 * nb, s_a + kb * TILE16X3, s_w + (nb * KB + kb) * TILE16X3, kb > 0);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        if (tile + (int)gridDim.x < num_tiles) load_rows(tile + gridDim.x);      // in flight during the MMAs and the epilogue
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+#pragma unroll
+        for (int nb = 0; nb < NB; ++nb) {
+            d1_to_staging(d + 64 * nb, stg);               // the A tiles are dead once the MMAs have completed
+            tc::tc_fence_before_sync();
+            __syncthreads();
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                const int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+                if (rl < rows) {
+                    float4 v = ld4(stg + rl * STG_LD + 4 * c4);
+                    if (MASK) {
+                        const float4 mk = ldg4(M + (size_t)(row0 + rl) * ldm + 64 * nb + 4 * c4);
+                        v = make_float4(mk.x > 0.f ? v.x : 0.f, mk.y > 0.f ? v.y : 0.f, mk.z > 0.f ? v.z : 0.f, mk.w > 0.f ? v.w : 0.f);
+                    }
+                    st4(out + (size_t)(row0 + rl) * ldo + 64 * nb + 4 * c4, v);
+                }
+            }
+            __syncthreads();                               // staging (= A tiles) free again
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64 * NB>(d);
+}
+
+template <int AB>
+__global__ void __launch_bounds__(TC_THREADS)
+k_rows_reduce16(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ partial,
+                int n, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* a1 = smem;                                   // AB column blocks of A, three bf16 tiles each
+    uint8_t* b1 = a1 + AB * TILE16X3;
+    TcShared* sh = reinterpret_cast<TcShared*>(b1 + TILE16X3);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    if (warp == 0) tc::tmem_alloc<64 * AB>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d = sh->tmem_base;
+    const uint32_t s_a = tc::smem_u32(a1), s_b = tc::smem_u32(b1);
+    uint32_t phase = 0;
+    float racc[AB][64];                                   // row 16 warp + lane (lane < 16) of each 64 x 64 block
+#pragma unroll
+    for (int ab = 0; ab < AB; ++ab)
+#pragma unroll
+        for (int i = 0; i < 64; ++i) racc[ab][i] = 0.f;
+    float4 ma[AB][8], mb[8];
+    auto load_rows = [&](int tile) {
+        const int row0 = tile * TCR, rows = min(TCR, n - row0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+#pragma unroll
+            for (int ab = 0; ab < AB; ++ab)
+                ma[ab][i] = rl < rows ? ldg4(A + (size_t)(row0 + rl) * lda + 64 * ab + 4 * c4) : f4zero();
+            mb[i] = rl < rows ? ldg4(B + (size_t)(row0 + rl) * ldb + 4 * c4) : f4zero();
+        }
+    };
+    if (blockIdx.x < num_tiles) load_rows(blockIdx.x);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int e = t + TC_THREADS * i;
+#pragma unroll
+            for (int ab = 0; ab < AB; ++ab) store_split3(a1 + ab * TILE16X3, e >> 4, e & 15, ma[ab][i]);
+            store_split3(b1, e >> 4, e & 15, mb[i]);
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            tc::tc_fence_after_sync();
+#pragma unroll
+            for (int ab = 0; ab < AB; ++ab) issue_reduce16(d + 64 * ab, s_a + ab * TILE16X3, s_b, false);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        if (tile + (int)gridDim.x < num_tiles) load_rows(tile + gridDim.x);
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        // the tensor core adds into its accumulator with truncation: every tile is summed on the CUDA cores
+#pragma unroll
+        for (int ab = 0; ab < AB; ++ab)
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                float v[32];
+                tc::tmem_ld32(d + 64 * ab + ((uint32_t)(32 * warp) << 16) + 32 * half, v);
+#pragma unroll
+                for (int i = 0; i < 32; ++i) racc[ab][32 * half + i] += v[i];
+            }
+        tc::tc_fence_before_sync();
+        __syncthreads();                                   // accumulators and tiles free again
+    }
+    if (lane < 16) {
+        float* my = partial + (size_t)blockIdx.x * (AB * 64 * 64);
+#pragma unroll
+        for (int ab = 0; ab < AB; ++ab)
+#pragma unroll
+            for (int i = 0; i < 64; i += 4)
+                st4(my + (size_t)(ab * 64 + 16 * warp + lane) * 64 + i, make_float4(racc[ab][i], racc[ab][i + 1], racc[ab][i + 2], racc[ab][i + 3]));
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64 * AB>(d);
+}
+
+// out[c] = sum over CTAs of partial[b][c], fixed order (one thread per element, coalesced across threads)
+__global__ void k_sum_cta_partials(const float* __restrict__ partial, int nblocks, int width, float* __restrict__ out) {
+    const int c = blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= width) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * width + c];
+    out[c] = s;
+}
+
 // Resident CTAs per SM from the kernel's own resource use (registers, shared memory, TMEM columns).
 int tc_grid(const void* kernel, int smem, int tmem_cols, int tiles) {
     int dev = 0, sms = 0, smem_sm = 0, regs_sm = 0;
@@ -1848,5 +2048,56 @@ extern "C" int s2v_debug_tc_gemm(int32_t mode, const float* A, const float* B, f
     if (!A || !B || !out || rows < 1 || mode < 0 || mode > 3) return S2V_ERR_BAD_ARG;
     S2V_RETURN_IF(cudaFuncSetAttribute(k_tc_selftest, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD_SMEM));
     k_tc_selftest<<<1, TC_THREADS, BWD_SMEM, (cudaStream_t)stream>>>(mode, A, B, out, (int)rows);
+    return (int)cudaGetLastError();
+}
+
+
+// ------------------------------------------------------------------------------------
+// C ABI: node-wise linear layers of the GATv2 branch on the tensor cores (include/s2v_b200.h)
+// ------------------------------------------------------------------------------------
+extern "C" int s2v_rows_gemm64(const float* A, int32_t lda, int32_t k_blocks, const float* W, int32_t n_blocks,
+                               int32_t transpose_w, const float* mask, int32_t ldm, float* out, int32_t ldo, int64_t n,
+                               void* stream) {
+    if (!A || !W || !out || n < 0 || lda < 64 * k_blocks || ldo < 64 * n_blocks || (mask && ldm < 64 * n_blocks)) return S2V_ERR_BAD_ARG;
+    if ((lda | ldo | (mask ? ldm : 0)) % 4 != 0) return S2V_ERR_BAD_ARG;
+    if (n == 0) return 0;
+    if (n > 0x7fffffff - 64) return S2V_ERR_BAD_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int tiles = (int)((n + TCR - 1) / TCR);
+#define S2V_ROWS_GEMM_LAUNCH(KB_, NB_, MASK_)                                                                              \
+    {                                                                                                                      \
+        constexpr int SMEM = (NB_ * KB_ + KB_) * (int)TILE16X3 + 64 + 1024;                                                \
+        S2V_RETURN_IF(cudaFuncSetAttribute(k_rows_gemm16<KB_, NB_, MASK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); \
+        const int grid = tc_grid((const void*)k_rows_gemm16<KB_, NB_, MASK_>, SMEM, 64 * NB_, tiles);                      \
+        k_rows_gemm16<KB_, NB_, MASK_><<<grid, TC_THREADS, SMEM, st>>>(A, lda, W, transpose_w, mask, ldm, out, ldo, (int)n, tiles); \
+        return (int)cudaGetLastError();                                                                                    \
+    }
+    if (k_blocks == 1 && n_blocks == 2 && !transpose_w && !mask) S2V_ROWS_GEMM_LAUNCH(1, 2, false)
+    if (k_blocks == 2 && n_blocks == 1 && transpose_w && mask) S2V_ROWS_GEMM_LAUNCH(2, 1, true)
+    if (k_blocks == 2 && n_blocks == 1 && transpose_w && !mask) S2V_ROWS_GEMM_LAUNCH(2, 1, false)
+#undef S2V_ROWS_GEMM_LAUNCH
+    return S2V_ERR_UNSUPPORTED;
+}
+
+extern "C" int64_t s2v_rows_reduce64_workspace_bytes(int32_t a_blocks) {
+    return (int64_t)S2V_MAX_GRID * a_blocks * 64 * 64 * (int64_t)sizeof(float);
+}
+
+extern "C" int s2v_rows_reduce64(const float* A, int32_t lda, int32_t a_blocks, const float* B, int32_t ldb, float* out,
+                                 void* workspace, int64_t workspace_bytes, int64_t n, void* stream) {
+    if (!A || !B || !out || !workspace || n < 0 || lda < 64 * a_blocks || ldb < 64 || (lda | ldb) % 4 != 0) return S2V_ERR_BAD_ARG;
+    if (a_blocks != 2) return S2V_ERR_UNSUPPORTED;
+    if (workspace_bytes < s2v_rows_reduce64_workspace_bytes(a_blocks)) return S2V_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int width = a_blocks * 64 * 64;
+    if (n == 0) return (int)cudaMemsetAsync(out, 0, sizeof(float) * width, st);
+    if (n > 0x7fffffff - 64) return S2V_ERR_BAD_ARG;
+    const int tiles = (int)((n + TCR - 1) / TCR);
+    constexpr int SMEM = 3 * (int)TILE16X3 + 64 + 1024;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_rows_reduce16<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const int grid = tc_grid((const void*)k_rows_reduce16<2>, SMEM, 128, tiles);
+    k_rows_reduce16<2><<<grid, TC_THREADS, SMEM, st>>>(A, lda, B, ldb, (float*)workspace, (int)n, tiles);
+    S2V_RETURN_IF(cudaGetLastError());
+    k_sum_cta_partials<<<(width + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, width, out);
     return (int)cudaGetLastError();
 }

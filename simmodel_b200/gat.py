@@ -59,11 +59,23 @@ def _rows_contract(a: torch.Tensor, b: torch.Tensor) -> torch.Tensor:
     return out
 
 
+TENSOR_MIN_NODES = 4096
+
+
+def _tensor_lin(x_dim: int, HC: int, n: int, shared: bool) -> bool:
+    """lin_l / lin_r (and their backward) on the tcgen05 kernels: in = 64, heads*channels = 64 (the hidden layers of
+    QNet_GATv2), large batches; S2V_B200_PATH=ffma keeps every GEMM in fp32 round-to-nearest (cuBLAS)."""
+    return (not shared) and x_dim == 64 and HC == 64 and n >= TENSOR_MIN_NODES and _lib.path_flag() != _lib.PATHS["ffma"]
+
+
 class _GATConvFn(torch.autograd.Function):
-    """wr / br None => share_weights=True (x_r = x_l = lin_l(x); models_ngo.py:241-249)."""
+    """wr / br None => share_weights=True (x_r = x_l = lin_l(x); models_ngo.py:241-249).
+    relu: 0 none, 1 ReLU on the output with the mask applied in this layer's backward, 2 ReLU on the output whose
+    backward mask the CONSUMER applies (the next layer's dx GEMM epilogue: its input is this output).
+    mask_dx: this layer's input is a ReLU output whose producer left the mask to us."""
 
     @staticmethod
-    def forward(ctx, layout, heads, relu, x, wl, bl, wr, br, att, bias):
+    def forward(ctx, layout, heads, relu, mask_dx, x, wl, bl, wr, br, att, bias):
         L = _lib.lib()
         x = ops._f32c(x, "x")
         n, HC = layout.num_nodes, int(wl.shape[0])
@@ -73,7 +85,16 @@ class _GATConvFn(torch.autograd.Function):
             raise ValueError("x has shape %s, expected (%d, %d)" % (tuple(x.shape), n, wl.shape[1]))
         wcat = wl.detach() if shared else torch.cat((wl.detach(), wr.detach()), dim=0)      # [2HC, in]
         bcat = torch.cat((bl.detach(), bl.detach() if shared else br.detach()), dim=0)     # lin_l.bias | lin_r.bias
-        xlr = x.mm(wcat.t())                             # [n, 2HC]: x_l | x_r without biases (plain GEMM, no epilogue pass)
+        tensor = _tensor_lin(int(x.shape[1]), HC, n, shared)
+        if tensor:
+            xlr = torch.empty(n, 2 * HC, dtype=torch.float32, device=x.device)
+            wcat = wcat.contiguous()
+            with torch.cuda.device(x.device):
+                _lib.check(L.s2v_rows_gemm64(_p(x), int(x.shape[1]), 1, _p(wcat), 2, 0, None, 0, _p(xlr), 2 * HC, n, _stream()),
+                           "s2v_rows_gemm64")
+            _lib.launch_count += 1
+        else:
+            xlr = x.mm(wcat.t())                         # [n, 2HC]: x_l | x_r without biases (plain GEMM, no epilogue pass)
         ld = int(xlr.shape[1])
         xr_ptr = _p(xlr) if shared else C.c_void_p(xlr.data_ptr() + 4 * HC)
         att_f = ops._f32c(att.detach().reshape(-1), "att")
@@ -82,10 +103,10 @@ class _GATConvFn(torch.autograd.Function):
         stats = torch.empty(n, heads, 4, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             _lib.check(L.s2v_gat_attn_forward(C.byref(layout.c_struct()), heads, Cc, ld, _p(xlr), xr_ptr, _p(att_f),
-                                              _p(bias_f), _p(bcat), int(relu), _p(out), _p(stats), _stream()),
+                                              _p(bias_f), _p(bcat), int(relu != 0), _p(out), _p(stats), _stream()),
                        "s2v_gat_attn_forward")
         _lib.launch_count += 1
-        ctx.layout, ctx.heads, ctx.relu, ctx.shared = layout, heads, relu, shared
+        ctx.layout, ctx.heads, ctx.relu, ctx.shared, ctx.tensor, ctx.mask_dx = layout, heads, relu, shared, tensor, mask_dx
         ctx.save_for_backward(x, xlr, stats, out, att_f, wcat, bcat)
         return out
 
@@ -98,7 +119,7 @@ class _GATConvFn(torch.autograd.Function):
         Cc = HC // heads
         dout = ops._f32c(dout, "dout")
         with torch.cuda.device(x.device):
-            if ctx.relu:
+            if ctx.relu == 1:
                 masked = torch.empty_like(dout)
                 _lib.check(L.s2v_relu_mask(_p(dout), _p(out), _p(masked), dout.numel(), _stream()), "s2v_relu_mask")
                 _lib.launch_count += 1
@@ -117,11 +138,27 @@ class _GATConvFn(torch.autograd.Function):
         if shared:
             dxs = dxlr[0] + dxlr[1]
             dw = _rows_contract(dxs, x)
-            dx = dxs.mm(wcat) if ctx.needs_input_grad[3] else None
-            return (None, None, None, dx, dw, gab[2] + gab[3], None, None, gab[0].view(1, heads, Cc), gab[1])
-        dw = _rows_contract(dxlr, x)                                          # [2HC, in]   (plain GEMMs)
-        dx = dxlr.mm(wcat) if ctx.needs_input_grad[3] else None
-        return (None, None, None, dx, dw[:HC], gab[2], dw[HC:], gab[3], gab[0].view(1, heads, Cc), gab[1])
+            dx = dxs.mm(wcat) if ctx.needs_input_grad[4] else None
+            return (None, None, None, None, dx, dw, gab[2] + gab[3], None, None, gab[0].view(1, heads, Cc), gab[1])
+        if ctx.tensor:
+            dw = torch.empty(2 * HC, int(x.shape[1]), dtype=torch.float32, device=x.device)
+            dx = None
+            with torch.cuda.device(x.device):
+                ws2 = torch.empty(L.s2v_rows_reduce64_workspace_bytes(2), dtype=torch.uint8, device=x.device)
+                _lib.check(L.s2v_rows_reduce64(_p(dxlr), 2 * HC, 2, _p(x), int(x.shape[1]), _p(dw), _p(ws2), ws2.numel(), n,
+                                               _stream()), "s2v_rows_reduce64")
+                if ctx.needs_input_grad[4]:
+                    dx = torch.empty_like(x)
+                    _lib.check(L.s2v_rows_gemm64(_p(dxlr), 2 * HC, 2, _p(wcat), 1, 1, _p(x) if ctx.mask_dx else None,
+                                                 int(x.shape[1]), _p(dx), int(x.shape[1]), n, _stream()), "s2v_rows_gemm64")
+            _lib.launch_count += 3
+        else:
+            dw = _rows_contract(dxlr, x)                                      # [2HC, in]   (plain GEMMs)
+            dx = dxlr.mm(wcat) if ctx.needs_input_grad[4] else None
+            if dx is not None and ctx.mask_dx:                                # the producer left its ReLU mask to us
+                with torch.cuda.device(x.device):
+                    _lib.check(L.s2v_relu_mask(_p(dx), _p(x), _p(dx), dx.numel(), _stream()), "s2v_relu_mask")
+        return (None, None, None, None, dx, dw[:HC], gab[2], dw[HC:], gab[3], gab[0].view(1, heads, Cc), gab[1])
 
 
 class GATv2Conv(nn.Module):
@@ -155,14 +192,20 @@ class GATv2Conv(nn.Module):
         nn.init.uniform_(self.att, -a, a)
         nn.init.zeros_(self.bias)
 
-    def forward_layout(self, x, layout: GraphLayout, relu: bool = False):
+    def forward_layout(self, x, layout: GraphLayout, relu: bool = False, relu_mask_by_consumer: bool = False,
+                       mask_dx: bool = False):
+        """relu_mask_by_consumer / mask_dx: see _GATConvFn (GATv2.forward_layout pairs them between adjacent layers)."""
         if not self.att.is_cuda:
             raise S2VError("simmodel_b200.GATv2Conv runs on CUDA only: call .to('cuda') first (no CPU fallback)")
+        mode = 0 if not relu else (2 if relu_mask_by_consumer else 1)
         if self.share_weights:
-            return _GATConvFn.apply(layout, self.heads, bool(relu), x, self.lin_l.weight, self.lin_l.bias, None, None,
+            return _GATConvFn.apply(layout, self.heads, mode, bool(mask_dx), x, self.lin_l.weight, self.lin_l.bias, None, None,
                                     self.att, self.bias)
-        return _GATConvFn.apply(layout, self.heads, bool(relu), x, self.lin_l.weight, self.lin_l.bias,
+        return _GATConvFn.apply(layout, self.heads, mode, bool(mask_dx), x, self.lin_l.weight, self.lin_l.bias,
                                 self.lin_r.weight, self.lin_r.bias, self.att, self.bias)
+
+    def uses_tensor_lin(self, n: int) -> bool:
+        return _tensor_lin(self.in_channels, self.heads * self.out_channels, n, self.share_weights)
 
     def forward(self, x, edge_index):
         n = int(x.shape[0])
@@ -195,8 +238,14 @@ class GATv2(nn.Module):
             cin = w
 
     def forward_layout(self, x, layout: GraphLayout):
+        n = layout.num_nodes
         for k, conv in enumerate(self.convs):
-            x = conv.forward_layout(x, layout, relu=k < self.num_layers - 1)
+            # a layer whose lin GEMMs run on the tensor-core kernels applies the ReLU mask of its INPUT in the epilogue
+            # of its dx GEMM; the producing layer then skips its own masking pass
+            fused_here = k > 0 and conv.uses_tensor_lin(n)
+            fused_next = k + 1 < self.num_layers and self.convs[k + 1].uses_tensor_lin(n)
+            x = conv.forward_layout(x, layout, relu=k < self.num_layers - 1, relu_mask_by_consumer=fused_next,
+                                    mask_dx=fused_here)
         return x
 
     def forward(self, x, edge_index):

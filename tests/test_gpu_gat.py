@@ -232,3 +232,78 @@ def test_qfunction_with_gat_qnet(cuda_device):
     assert a == int(np.argmax(ref)) and node == reach[a] and val == ref[a]
     loss = qf.batch_update([zerovec] * 4, [zerovec] * 4, datas, G["inp"]["actions"].tolist(), G["inp"]["targets"].tolist())
     assert abs(loss - float(G["out"]["loss"])) <= 1e-5 * max(1.0, abs(float(G["out"]["loss"])))
+
+
+@pytest.mark.parametrize("n", [64, 1000, 5000])
+def test_tensor_core_lin_kernels(n, cuda_device):
+    """s2v_rows_gemm64 / s2v_rows_reduce64 (tcgen05, bf16x3) against fp64: forward x [Wl;Wr]^T, backward dx with and
+    without the ReLU mask, weight gradient dxlr^T x; ragged last tile; run-to-run bit stability."""
+    import ctypes as C
+    from simmodel_b200 import _lib
+    from simmodel_b200.layout import _p, _stream
+    L = _lib.lib()
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(n)
+    x = torch.randn(n, 64, generator=gen).to(dev)
+    w = (torch.randn(128, 64, generator=gen) * 0.2).to(dev)
+    dy = torch.randn(n, 128, generator=gen).to(dev)
+    y = torch.empty(n, 128, device=dev)
+    _lib.check(L.s2v_rows_gemm64(_p(x), 64, 1, _p(w), 2, 0, None, 0, _p(y), 128, n, _stream()), "fwd")
+    _check("y", y.cpu().numpy(), (x.double() @ w.double().t()).cpu().numpy(), tol=2e-6)
+    dx = torch.empty(n, 64, device=dev)
+    _lib.check(L.s2v_rows_gemm64(_p(dy), 128, 2, _p(w), 1, 1, None, 0, _p(dx), 64, n, _stream()), "dx")
+    ref = dy.double() @ w.double()
+    _check("dx", dx.cpu().numpy(), ref.cpu().numpy(), tol=2e-6)
+    _lib.check(L.s2v_rows_gemm64(_p(dy), 128, 2, _p(w), 1, 1, _p(x), 64, _p(dx), 64, n, _stream()), "dx masked")
+    _check("dx masked", dx.cpu().numpy(), (ref * (x > 0)).cpu().numpy(), tol=2e-6)
+    assert bool(((dx == 0) == ((x <= 0) | (ref.float() == 0) | (dx == 0))).all())
+    ws = torch.empty(L.s2v_rows_reduce64_workspace_bytes(2), dtype=torch.uint8, device=dev)
+    outs = []
+    for _ in range(2):
+        dw = torch.empty(128, 64, device=dev)
+        _lib.check(L.s2v_rows_reduce64(_p(dy), 128, 2, _p(x), 64, _p(dw), _p(ws), ws.numel(), n, _stream()), "dw")
+        outs.append(dw)
+    assert torch.equal(outs[0], outs[1])
+    _check("dw", outs[0].cpu().numpy(), (dy.double().t() @ x.double()).cpu().numpy(), tol=3e-6)
+    assert L.s2v_rows_gemm64(_p(x), 64, 1, _p(w), 3, 0, None, 0, _p(y), 192, n, _stream()) == -2      # unsupported shape
+
+
+def test_gat_large_batch_tensor_lin_vs_oracle(cuda_device, monkeypatch):
+    """>= 4096 rows: the hidden layers' lin_l / lin_r GEMMs run on the tcgen05 kernels (ReLU mask fused into the dx
+    epilogue).  QNet_GATv2 on 4 UTR graphs against the CPU oracle (fp32, adjudicated in fp64); the all-cuBLAS path
+    (S2V_B200_PATH=ffma) on the same inputs for comparison."""
+    import simmodel_b200 as sb
+    from oracle import gat_ref as R
+    dev = cuda_device
+    topo = sb.graphs.load_topology("NWB_UTR")
+    B = 4
+    gen = torch.Generator().manual_seed(5)
+    x = sb.graphs.synth_nfm(topo, B, gen).reshape(-1, 7)
+    ei = sb.graphs.batch_edge_index(topo, B)
+    ptr = torch.arange(B + 1, dtype=torch.int64) * topo.num_nodes
+    torch.manual_seed(1)
+    net = sb.QNet_GATv2({"emb_dim": 64, "emb_iter_T": 5, "norm_agg": True, "node_dim": 7}, verbose=False)
+    with torch.no_grad():
+        for k, prm in net.named_parameters():
+            if k.endswith(".bias") and "convs" in k and "lin_" not in k:
+                prm.copy_(torch.randn(prm.shape) * 0.1)
+    P = {k: v.detach().clone() for k, v in net.state_dict().items()}
+    sel = torch.randint(0, topo.num_nodes, (B,), generator=gen) + ptr[:-1]
+    tg = torch.randn(B, generator=gen)
+    refs = {}
+    for name, dt in (("f32", torch.float32), ("f64", torch.float64)):
+        Pg = {k: v.detach().to(dt).clone().requires_grad_(True) for k, v in P.items()}
+        q = R.qnet_gat_forward(Pg, x.to(dt), ei, ptr, 5, True)
+        torch.nn.SmoothL1Loss()(q[sel], tg.to(dt)).backward()
+        refs[name] = (q.detach(), {k: v.grad for k, v in Pg.items()})
+    net = net.to(dev)
+    layout = sb.gat.gat_layout_from_batch(ei.to(dev), ptr.to(dev))
+    assert net.gat.convs[1].uses_tensor_lin(layout.num_nodes) and not net.gat.convs[0].uses_tensor_lin(layout.num_nodes)
+    for path, tol in (("auto", 1e-4), ("ffma", 2e-5)):
+        monkeypatch.setenv("S2V_B200_PATH", path)
+        net.zero_grad()
+        q = net.forward_graph(x.to(dev), layout)
+        torch.nn.SmoothL1Loss()(q[sel.to(dev)], tg.to(dev)).backward()
+        _check("q " + path, q.detach().cpu().numpy(), refs["f32"][0].numpy(), refs["f64"][0].numpy(), tol=1e-5)
+        for k, prm in net.named_parameters():
+            _check("grad %s %s" % (k, path), prm.grad.cpu().numpy(), refs["f32"][1][k].numpy(), refs["f64"][1][k].numpy(), tol=tol)
