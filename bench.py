@@ -560,31 +560,33 @@ def run_gat(args):
         xlr = torch.randn(n, 2 * HC, device=dev)
         att, bias = torch.randn(HC, device=dev) * 0.1, torch.randn(HC, device=dev) * 0.1
         lin_bias = torch.randn(2 * HC, device=dev) * 0.1       # as in the step: bias-free GEMM output + biases added at load
-        out, stats = torch.empty(n, HC, device=dev), torch.empty(n, H, 4, device=dev)
+        out = torch.empty(n, HC, device=dev)
+        ef = int(L.s2v_gat_edge_floats(C.byref(g), H))
+        alpha = torch.empty(ef, device=dev)
         dout, dxlr, gab = torch.randn(n, HC, device=dev), torch.empty(n, 2 * HC, device=dev), torch.empty(4, HC, device=dev)
-        ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(H, Cc), dtype=torch.uint8, device=dev)
+        ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(H, Cc, ef), dtype=torch.uint8, device=dev)
         xr_p, dxr_p = C.c_void_p(xlr.data_ptr() + 4 * HC), C.c_void_p(dxlr.data_ptr() + 4 * HC)
 
         def k_fwd():
             _lib.check(L.s2v_gat_attn_forward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(bias), _p(lin_bias), 1,
-                                              _p(out), _p(stats), _stream()), "gat fwd")
+                                              _p(out), None, _p(alpha), _stream()), "gat fwd")
 
         def k_bwd():
-            _lib.check(L.s2v_gat_attn_backward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(lin_bias), _p(stats), _p(dout),
+            _lib.check(L.s2v_gat_attn_backward(C.byref(g), H, Cc, 2 * HC, _p(xlr), xr_p, _p(att), _p(lin_bias), None, _p(alpha), _p(layout.row_to_col), _p(dout),
                                                _p(dxlr), dxr_p, _p(gab[0]), _p(gab[1]), _p(gab[2]), _p(ws), ws.numel(), _stream()),
                        "gat bwd")
         # forward: (dbar+1) x_l rows + x_r row read, out row written, ids + rowptr, statistics written
-        fwd_bytes = 4 * (HC * (dbar + 3) + dbar + 1 + 4 * H)
+        fwd_bytes = 4 * (HC * (dbar + 3) + dbar + 1 + H * (dbar + 1))
         # backward (both kernels): target pass reads (dbar+1) x_l rows + x_r + dout + statistics, writes dx_r + D;
         # source pass reads x_l + (dbar+1) x (x_r, dout, statistics) rows, writes dx_l; ids + rowptr twice
-        bwd_bytes = 4 * (HC * (dbar + 1 + 3) + 5 * H + HC * (1 + 2 * (dbar + 1) + 1) + 4 * H * (dbar + 1) + 2 * (dbar + 1))
+        bwd_bytes = 4 * (HC * (dbar + 1 + 3) + 2 * H * (dbar + 1) + HC * (1 + 2 * (dbar + 1) + 1) + 2 * H * (dbar + 1) + 3 * (dbar + 1))
         for name, fn, bpn in (("k_gat_fwd4 (H=%d, C=%d)" % (H, Cc), k_fwd, fwd_bytes),
                               ("k_gat_bwd_target4 + k_gat_bwd_source4 (H=%d, C=%d)" % (H, Cc), k_bwd, bwd_bytes)):
             k_ms = timed(fn, 10, 3)
             ach = bpn * n / (k_ms / 1e3) / 1e9
             kernels.append({"kernel": name, "ms": k_ms, "algorithmic_bytes": bpn * n, "achieved_GBps": ach, "frac": ach / peak,
                             "launches_per_step": per_step})
-        del xlr, out, stats, dout, dxlr
+        del xlr, out, alpha, dout, dxlr
     dom = max(kernels[:2], key=lambda r: r["ms"])
     edge_ms = sum(k["ms"] * k["launches_per_step"] for k in kernels)
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",

@@ -123,6 +123,11 @@ int64_t s2v_csr_workspace_bytes(int64_t n, int64_t num_edges);
 int s2v_csr_build(const int64_t* edge_index, int64_t num_edges, int64_t n,
                   int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t, int32_t* indeg,
                   void* workspace, int64_t workspace_bytes, void* stream);
+/* Optional: row_to_col[k] = position in col_t of the edge stored at position k of col (the GATv2 backward walks both
+ * forms and exchanges per-edge values).  build_workspace: the workspace of the s2v_csr_build call that produced the
+ * CSR, untouched since; scratch: [num_edges] int32. */
+int s2v_csr_row_to_col(const void* build_workspace, int64_t n, int64_t num_edges, int32_t* scratch, int32_t* row_to_col,
+                       void* stream);
 
 /* ---------------------------------------------------------------------------------
  * K2+K3  embedding forward: node MLP, theta4/theta3 degree term, T propagation rounds.
@@ -230,8 +235,15 @@ int s2v_scatter_rows(const s2v_graph_t* g, const int64_t* arg, const float* dval
  *            identical to passing biased rows.  NULL: xl / xr already contain their biases.
  *   out      [num_nodes, H*C] = sum_j softmax_j(att . lrelu(xr[i] + xl[j], 0.2)) xl[j] + bias,
  *            ReLU applied when apply_relu != 0 (BasicGNN between layers)
- *   stats    [num_nodes, H, 4] out: per target and head (max score, 1 / den, D, den = softmax denominator + 1e-16);
- *            the backward writes D = sum_j a_ij da_ij into the third slot
+ *   What the forward keeps for the backward depends on the kernel variant (s2v_gat_uses_edge_alpha):
+ *   alpha    [s2v_gat_edge_floats] out (specialised shapes 4x32, 2x32, 4x16): the attention weight of every edge and
+ *            head -- the incoming edges of target r in col_t order, copy-major for replicated layouts, then the self
+ *            edges [num_nodes, H].  Backward then recomputes neither scores nor softmax: the target pass stores
+ *            de = alpha (dalpha - D) per edge next to alpha and the source pass fetches both through row_to_col
+ *            (s2v_csr_row_to_col).  Pass NULL to force the generic kernels.
+ *   stats    [num_nodes, H, 4] out (generic kernels; may be NULL when alpha is given and the shape is specialised):
+ *            per target and head (max score, 1 / den, D, den = softmax denominator + 1e-16); the backward writes
+ *            D = sum_j a_ij da_ij into the third slot and recomputes alpha from it
  * Backward: dout [num_nodes, H*C] (already multiplied by the ReLU mask when the layer had one)
  *   -> dxl, dxr (row stride ld), grad_att [H*C], grad_bias [H*C], grad_lin_bias [2*H*C] = column sums of
  *      dxl | dxr, i.e. the gradients of lin_l.bias | lin_r.bias (all overwritten; fixed-order sums).
@@ -239,11 +251,13 @@ int s2v_scatter_rows(const s2v_graph_t* g, const int64_t* arg, const float* dval
 #define S2V_GAT_MAX_GRID 2048
 int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                          const float* xl, const float* xr, const float* att, const float* bias,
-                         const float* lin_bias, int32_t apply_relu, float* out, float* stats, void* stream);
-int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels);
+                         const float* lin_bias, int32_t apply_relu, float* out, float* stats, float* alpha, void* stream);
+int64_t s2v_gat_edge_floats(const s2v_graph_t* g, int32_t heads);
+int s2v_gat_uses_edge_alpha(int32_t heads, int32_t channels, int32_t ld);
+int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels, int64_t edge_floats);
 int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                           const float* xl, const float* xr, const float* att, const float* lin_bias,
-                          float* stats, const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
+                          float* stats, const float* alpha, const int32_t* row_to_col, const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
                           float* grad_lin_bias, void* workspace, int64_t workspace_bytes, void* stream);
 
 /* ---------------------------------------------------------------------------------

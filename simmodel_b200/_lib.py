@@ -45,6 +45,7 @@ SIGNATURES = {
     "s2v_head_grad_floats": (i64, [i32]),
     "s2v_csr_workspace_bytes": (i64, [i64, i64]),
     "s2v_csr_build": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "s2v_csr_row_to_col": (C.c_int, [vp, i64, i64, vp, vp, vp]),
     "s2v_embed_forward": (C.c_int, [GP, EP, vp, vp, vp, vp]),
     "s2v_embed_backward_workspace_bytes": (i64, [i32, i32]),
     "s2v_embed_backward": (C.c_int, [GP, EP, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp]),
@@ -62,12 +63,14 @@ SIGNATURES = {
     "s2v_masked_softmax_forward": (C.c_int, [GP, vp, vp, vp, vp]),
     "s2v_masked_softmax_backward": (C.c_int, [GP, vp, vp, vp, vp]),
     "s2v_scatter_rows": (C.c_int, [GP, vp, vp, vp, vp]),
-    "s2v_gat_attn_forward": (C.c_int, [GP, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp]),
-    "s2v_gat_attn_backward_workspace_bytes": (i64, [i32, i32]),
+    "s2v_gat_attn_forward": (C.c_int, [GP, i32, i32, i32, vp, vp, vp, vp, vp, i32, vp, vp, vp, vp]),
+    "s2v_gat_edge_floats": (i64, [GP, i32]),
+    "s2v_gat_uses_edge_alpha": (C.c_int, [i32, i32, i32]),
+    "s2v_gat_attn_backward_workspace_bytes": (i64, [i32, i32, i64]),
     "s2v_rows_gemm64": (C.c_int, [vp, i32, i32, vp, i32, i32, vp, i32, vp, i32, i64, vp]),
     "s2v_rows_reduce64_workspace_bytes": (i64, [i32]),
     "s2v_rows_reduce64": (C.c_int, [vp, i32, i32, vp, i32, vp, vp, i64, i64, vp]),
-    "s2v_gat_attn_backward": (C.c_int, [GP, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "s2v_gat_attn_backward": (C.c_int, [GP, i32, i32, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
 }
 
 _lib = None

@@ -124,12 +124,38 @@ __global__ void k_csr_sort_emit(const int64_t* __restrict__ ei, int64_t E, int64
     }
 }
 
+// position of every edge in the column form, then row-form position -> column-form position
+__global__ void k_csr_inv(const int32_t* __restrict__ eid_col, int64_t E, int32_t* __restrict__ inv) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < E; p += (int64_t)gridDim.x * blockDim.x) inv[eid_col[p]] = (int32_t)p;
+}
+__global__ void k_csr_map(const int32_t* __restrict__ eid_row, const int32_t* __restrict__ inv, int64_t E, int32_t* __restrict__ row_to_col) {
+    for (int64_t p = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; p < E; p += (int64_t)gridDim.x * blockDim.x) row_to_col[p] = inv[eid_row[p]];
+}
+
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 // workspace layout (int32): err[64] | cnt_row[n] | cnt_col[n] | eid_row[E] | eid_col[E] | block_sums[nb+1] x2 | totals[2]
 extern "C" int64_t s2v_csr_workspace_bytes(int64_t n, int64_t E) {
     int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1;
     return (64 + align_up(n, 64) * 2 + align_up(E, 64) * 2 + align_up(nb, 64) * 2 + 64) * 4;
+}
+
+// Entry k of row i (edge i -> col[k]) is entry row_to_col[k] of column col[k] in the transposed form.  Needs the
+// workspace of the s2v_csr_build call that produced the CSR (same n, E, same stream order) plus scratch [E] int32.
+extern "C" int s2v_csr_row_to_col(const void* build_workspace, int64_t n, int64_t E, int32_t* scratch, int32_t* row_to_col,
+                                  void* stream) {
+    if (E < 0 || n < 0 || n >= INT32_MAX || E >= INT32_MAX) return S2V_ERR_BAD_ARG;
+    if (E == 0) return 0;
+    if (!build_workspace || !scratch || !row_to_col) return S2V_ERR_BAD_ARG;
+    const int32_t* w = (const int32_t*)build_workspace;
+    const int32_t* eid_row = w + 64 + align_up(n, 64) * 2;
+    const int32_t* eid_col = eid_row + align_up(E, 64);
+    int eb = (int)((E + 255) / 256);
+    if (eb > 148 * 32) eb = 148 * 32;
+    cudaStream_t st = (cudaStream_t)stream;
+    k_csr_inv<<<eb, 256, 0, st>>>(eid_col, E, scratch);
+    k_csr_map<<<eb, 256, 0, st>>>(eid_row, scratch, E, row_to_col);
+    return (int)cudaGetLastError();
 }
 
 static int scan_exclusive(const int32_t* in, int32_t* out, int32_t* block_sums, int32_t* total, int64_t n, cudaStream_t st) {

@@ -374,13 +374,14 @@ __device__ __forceinline__ float dot4(const float4& a, const float4& b) {
 }
 __device__ __forceinline__ float dlr(float s) { return s > 0.f ? 1.f : GAT_SLOPE; }
 
-// Pipelined row metadata: (beg, deg, off) of a row from the CSR given by (rp, ci); ids of its first LPR neighbours.
-struct RowMeta { int r, beg, deg, off; };
+// Pipelined row metadata: (beg, deg, off, graph copy) of a row from the CSR given by (rp, ci); ids of its first LPR
+// neighbours.
+struct RowMeta { int r, beg, deg, off, gi; };
 __device__ __forceinline__ RowMeta row_meta(const s2v_graph_t& g, const int* __restrict__ rp, int r) {
-    RowMeta m; m.r = r; m.beg = 0; m.deg = -1; m.off = 0;          // deg -1 => cnt 0: row out of range
+    RowMeta m; m.r = r; m.beg = 0; m.deg = -1; m.off = 0; m.gi = 0;          // deg -1 => cnt 0: row out of range
     if (r < g.num_nodes) {
         int li = r;
-        if (g.period > 0) { const int gi = r / g.period; m.off = gi * g.period; li = r - m.off; }
+        if (g.period > 0) { m.gi = r / g.period; m.off = m.gi * g.period; li = r - m.off; }
         m.beg = __ldg(rp + li);
         m.deg = __ldg(rp + li + 1) - m.beg;
     }
@@ -388,6 +389,9 @@ __device__ __forceinline__ RowMeta row_meta(const s2v_graph_t& g, const int* __r
 }
 __device__ __forceinline__ int row_ids(const RowMeta& m, const int* __restrict__ ci, int sl) {
     return sl < m.deg ? __ldg(ci + m.beg + sl) + m.off : m.r;
+}
+__device__ __forceinline__ int row_map(const RowMeta& m, const int* __restrict__ map, int sl) {
+    return sl < m.deg ? __ldg(map + m.beg + sl) : -1;
 }
 
 #define GAT_ROW_SETUP()                                                                                         \
@@ -414,10 +418,42 @@ __device__ __forceinline__ int warp_max_cnt(int cnt) {
     return cnt;
 }
 
+// Per-edge attention weights: alpha / dedge are [E_total + n][H] with E_total = copies * E_csr -- the incoming edges of
+// target r at ((gi * E_csr + beg_t + k) * H + head) in column-form (CSC) order, its self edge at ((E_total + r) * H + head).
+struct EdgeIdx {
+    size_t e0, s0;          // index of edge 0 / of the self edge for this lane's head
+    __device__ __forceinline__ size_t at(int k, int deg, int H) const { return k < deg ? e0 + (size_t)k * H : s0; }
+};
+template <int H>
+__device__ __forceinline__ EdgeIdx edge_idx(const s2v_graph_t& g, const RowMeta& m, int head) {
+    const int e_csr = g.num_edges;
+    const size_t copies = g.period > 0 ? (size_t)(g.num_nodes / g.period) : 1;
+    EdgeIdx x;
+    x.e0 = ((size_t)m.gi * e_csr + m.beg) * H + head;
+    x.s0 = (copies * e_csr + (size_t)m.r) * H + head;
+    return x;
+}
+
+// The NS per-edge values of a head are identical in all LPH lanes of the head: lane q of the head stores the value of
+// edge q (and q + LPH when NS > LPH), so one store instruction covers every edge of the rows of the warp.
+template <int LPH, int NS, int H>
+__device__ __forceinline__ void store_edge_values(float* __restrict__ dst, const float (&v)[NS], int q, int cnt, const EdgeIdx& ex) {
+#pragma unroll
+    for (int base = 0; base < NS; base += LPH) {
+        const int k = base + q;
+        float x = v[base];
+#pragma unroll
+        for (int i = 1; i < LPH; ++i) if (base + i < NS) x = (q == i) ? v[base + i] : x;
+        if (k < cnt && k < NS) dst[ex.at(k, cnt - 1, H)] = x;
+    }
+}
+
 // Register-resident paths for rows with at most NS neighbours (incl. the self edge); NS = 4 or 8 is chosen per warp.
 template <int LPR, int LPH, int NS>
 __device__ __forceinline__ void fwd_fast(const float* __restrict__ xl, int ld, int ch, int jl, int cnt, const float4& a,
-                                         const float4& bl, const float4& xri, float4& acc, float& m, float& inv, float& den) {
+                                         const float4& bl, const float4& xri, float4& acc, float* __restrict__ alpha,
+                                         const EdgeIdx& ex, int q) {
+    constexpr int H = LPR / LPH;
     int js[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
@@ -427,42 +463,46 @@ __device__ __forceinline__ void fwd_fast(const float* __restrict__ xl, int ld, i
     float sc[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) sc[k] = hsum<LPH>(score4(a, xri, rows[k]));
+    float m = -INFINITY;
 #pragma unroll
     for (int k = 0; k < NS; ++k) if (k < cnt) m = fmaxf(m, sc[k]);
     float S = 0.f;
 #pragma unroll
     for (int k = 0; k < NS; ++k) if (k < cnt) { sc[k] = expf(sc[k] - m); S += sc[k]; }
-    den = S + 1e-16f; inv = 1.f / den;
+    const float den = S + 1e-16f, inv = 1.f / den;
 #pragma unroll
     for (int k = 0; k < NS; ++k) if (k < cnt) {
-        const float al = qdiv(sc[k], inv, den);
-        acc.x = fmaf(rows[k].x, al, acc.x); acc.y = fmaf(rows[k].y, al, acc.y);
-        acc.z = fmaf(rows[k].z, al, acc.z); acc.w = fmaf(rows[k].w, al, acc.w);
+        sc[k] = qdiv(sc[k], inv, den);
+        acc.x = fmaf(rows[k].x, sc[k], acc.x); acc.y = fmaf(rows[k].y, sc[k], acc.y);
+        acc.z = fmaf(rows[k].z, sc[k], acc.z); acc.w = fmaf(rows[k].w, sc[k], acc.w);
     }
+    store_edge_values<LPH, NS, H>(alpha, sc, q, cnt, ex);
 }
 
 template <int LPR, int LPH>
-__global__ void __launch_bounds__(GAT_THREADS, 3)
+__global__ void __launch_bounds__(GAT_THREADS, 4)   // latency-bound: occupancy beats the few spilled registers (A/B measured)
 k_gat_fwd4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
            const float* __restrict__ att, const float* __restrict__ bias, const float* __restrict__ lin_bias,
-           int apply_relu, float* __restrict__ out, float* __restrict__ stats) {
+           int apply_relu, float* __restrict__ out, float* __restrict__ alpha) {
     constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
     GAT_ROW_SETUP()
     const float4 a = ldg4(att + ch), b = ldg4(bias + ch);
     // x_l / x_r may arrive without their Linear biases: every row gets its bias as it is loaded
     const float4 bl = lin_bias ? ldg4(lin_bias + ch) : f4zero(), br = lin_bias ? ldg4(lin_bias + HC + ch) : f4zero();
+    const int q = sl % LPH;
+    const bool writer = q == 0;
     GAT_ROW_LOOP(g.rowptr_t, g.col_t) {
         GAT_ROW_ADVANCE(g.rowptr_t, g.col_t)
         const int r = cur.r, cnt = cur.deg + 1;
         const bool valid = cnt > 0;
         const float4 xri = valid ? f4add(ldg4(xr + (size_t)r * ld + ch), br) : f4zero();
+        const EdgeIdx ex = edge_idx<H>(g, cur, head);
         float4 acc = f4zero();
-        float m = -INFINITY, inv = 0.f, den = 1.f;
         const int mc = warp_max_cnt<LPR>(cnt);
-        if (mc <= 4) fwd_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, bl, xri, acc, m, inv, den);
-        else if (mc <= GAT_FAST) fwd_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, bl, xri, acc, m, inv, den);
+        if (mc <= 4) fwd_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, bl, xri, acc, alpha, ex, q);
+        else if (mc <= GAT_FAST) fwd_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, bl, xri, acc, alpha, ex, q);
         else {
-            float S = 0.f;
+            float m = -INFINITY, S = 0.f, inv = 0.f, den = 1.f;
             for (int pass = 0; pass < 3; ++pass) {
                 for (int k = 0; k < mc; ++k) {
                     const bool on = k < cnt;
@@ -474,6 +514,7 @@ k_gat_fwd4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const floa
                     else if (pass == 1) S += expf(e - m);
                     else {
                         const float al = qdiv(expf(e - m), inv, den);
+                        if (writer) alpha[ex.at(k, cur.deg, H)] = al;
                         acc.x = fmaf(row.x, al, acc.x); acc.y = fmaf(row.y, al, acc.y);
                         acc.z = fmaf(row.z, al, acc.z); acc.w = fmaf(row.w, al, acc.w);
                     }
@@ -485,7 +526,6 @@ k_gat_fwd4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const floa
             float4 o = make_float4(acc.x + b.x, acc.y + b.y, acc.z + b.z, acc.w + b.w);
             if (apply_relu) o = make_float4(relu(o.x), relu(o.y), relu(o.z), relu(o.w));
             st4(out + (size_t)r * HC + ch, o);
-            if (sl % LPH == 0) st4(stats + ((size_t)r * H + head) * 4, make_float4(m, inv, 0.f, den));
         }
         GAT_ROW_ROTATE()
     }
@@ -501,67 +541,78 @@ __device__ __forceinline__ void bwd_a_edge4(const float4& a, const float4& xri, 
 
 template <int LPR, int LPH, int NS>
 __device__ __forceinline__ void bwd_target_fast(const float* __restrict__ xl, int ld, int ch, int jl, int cnt, const float4& a,
-                                                const float4& bl, const float4& xri, const float4& doi, const float4& st, float& D,
-                                                float4& dx, float4& datt) {
+                                                const float4& bl, const float4& xri, const float4& doi,
+                                                const float* __restrict__ alpha, float* __restrict__ dedge, const EdgeIdx& ex,
+                                                int q, float4& dx, float4& datt) {
+    constexpr int H = LPR / LPH;
     int js[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) js[k] = __shfl_sync(0xffffffffu, jl, k, LPR);
     float4 rows[NS];
-#pragma unroll
-    for (int k = 0; k < NS; ++k) rows[k] = k < cnt ? f4add(ldg4(xl + (size_t)js[k] * ld + ch), bl) : f4zero();
     float al[NS], dal[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
-        const float e = hsum<LPH>(score4(a, xri, rows[k]));
-        dal[k] = hsum<LPH>(dot4(doi, rows[k]));
-        al[k] = k < cnt ? qdiv(expf(e - st.x), st.y, st.w) : 0.f;
+        rows[k] = k < cnt ? f4add(ldg4(xl + (size_t)js[k] * ld + ch), bl) : f4zero();
+        al[k] = k < cnt ? __ldg(alpha + ex.at(k, cnt - 1, H)) : 0.f;
     }
+#pragma unroll
+    for (int k = 0; k < NS; ++k) dal[k] = hsum<LPH>(dot4(doi, rows[k]));
+    float D = 0.f;
 #pragma unroll
     for (int k = 0; k < NS; ++k) if (k < cnt) D = fmaf(al[k], dal[k], D);
 #pragma unroll
-    for (int k = 0; k < NS; ++k) if (k < cnt) bwd_a_edge4(a, xri, rows[k], al[k] * (dal[k] - D), dx, datt);
+    for (int k = 0; k < NS; ++k) if (k < cnt) {
+        dal[k] = al[k] * (dal[k] - D);
+        bwd_a_edge4(a, xri, rows[k], dal[k], dx, datt);
+    }
+    store_edge_values<LPH, NS, H>(dedge, dal, q, cnt, ex);
 }
 
 template <int LPR, int LPH>
-__global__ void __launch_bounds__(GAT_THREADS, 2)
+__global__ void __launch_bounds__(GAT_THREADS, 3)
 k_gat_bwd_target4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
-                  const float* __restrict__ att, const float* __restrict__ lin_bias, float* __restrict__ stats,
-                  const float* __restrict__ dout, float* __restrict__ dxr, float* __restrict__ partials) {
+                  const float* __restrict__ att, const float* __restrict__ lin_bias, const float* __restrict__ alpha,
+                  float* __restrict__ dedge, const float* __restrict__ dout, float* __restrict__ dxr,
+                  float* __restrict__ partials) {
     constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
     __shared__ float red[GAT_WARPS * RPW][3 * HC];
     float4 datt = f4zero(), dbias = f4zero(), dbr = f4zero();
     GAT_ROW_SETUP()
     const float4 a = ldg4(att + ch);
     const float4 bl = lin_bias ? ldg4(lin_bias + ch) : f4zero(), br = lin_bias ? ldg4(lin_bias + HC + ch) : f4zero();
+    const int q = sl % LPH;
+    const bool writer = q == 0;
     GAT_ROW_LOOP(g.rowptr_t, g.col_t) {
         GAT_ROW_ADVANCE(g.rowptr_t, g.col_t)
         const int r = cur.r, cnt = cur.deg + 1;
         const bool valid = cnt > 0;
         const float4 xri = valid ? f4add(ldg4(xr + (size_t)r * ld + ch), br) : f4zero();
         const float4 doi = valid ? ldg4(dout + (size_t)r * HC + ch) : f4zero();
-        const float4 st = valid ? ld4(stats + ((size_t)r * H + head) * 4) : f4zero();
+        const EdgeIdx ex = edge_idx<H>(g, cur, head);
         float4 dx = f4zero();
-        float D = 0.f;
         const int mc = warp_max_cnt<LPR>(cnt);
-        if (mc <= 4) bwd_target_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, bl, xri, doi, st, D, dx, datt);
-        else if (mc <= GAT_FAST) bwd_target_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, bl, xri, doi, st, D, dx, datt);
+        if (mc <= 4) bwd_target_fast<LPR, LPH, 4>(xl, ld, ch, jl, cnt, a, bl, xri, doi, alpha, dedge, ex, q, dx, datt);
+        else if (mc <= GAT_FAST) bwd_target_fast<LPR, LPH, GAT_FAST>(xl, ld, ch, jl, cnt, a, bl, xri, doi, alpha, dedge, ex, q, dx, datt);
         else {
+            float D = 0.f;
             for (int pass = 0; pass < 2; ++pass)
                 for (int k = 0; k < mc; ++k) {
                     const bool on = k < cnt;
                     const int j = on && k < cur.deg ? __ldg(g.col_t + cur.beg + k) + cur.off : r;
                     const float4 row = on ? f4add(ldg4(xl + (size_t)j * ld + ch), bl) : f4zero();
-                    const float e = hsum<LPH>(score4(a, xri, row));
                     const float dl = hsum<LPH>(dot4(doi, row));
                     if (!on) continue;
-                    const float alk = qdiv(expf(e - st.x), st.y, st.w);
+                    const float alk = __ldg(alpha + ex.at(k, cur.deg, H));
                     if (pass == 0) D = fmaf(alk, dl, D);
-                    else bwd_a_edge4(a, xri, row, alk * (dl - D), dx, datt);
+                    else {
+                        const float de = alk * (dl - D);
+                        if (writer) dedge[ex.at(k, cur.deg, H)] = de;
+                        bwd_a_edge4(a, xri, row, de, dx, datt);
+                    }
                 }
         }
         if (valid) {
             st4(dxr + (size_t)r * ld + ch, dx);
-            if (sl % LPH == 0) stats[((size_t)r * H + head) * 4 + 2] = D;
             dbias = f4add(dbias, doi);
             dbr = f4add(dbr, dx);
         }
@@ -590,67 +641,65 @@ __device__ __forceinline__ void bwd_b_edge4(const float4& a, const float4& xlj, 
     dx.w = fmaf(al, doi.w, dx.w); dx.w = fmaf(de * a.w, dlr(xri.w + xlj.w), dx.w);
 }
 
-template <int LPR, int LPH, int NS>
+// Batch of four out-edges of a source: no score, no softmax -- alpha and de = alpha (dalpha - D) of every edge were
+// stored by the target passes (column-form order) and are fetched through the row-form -> column-form edge map.
+template <int LPR, int LPH>
 __device__ __forceinline__ void bwd_source_fast(const float* __restrict__ xr, const float* __restrict__ dout,
-                                                const float* __restrict__ stats, int ld, int ch, int head, int il, int cnt,
-                                                int k0, const float4& a, const float4& br, const float4& xlj, float4& dx) {
-    constexpr int HC = 4 * LPR, H = LPR / LPH;
-    int is[NS];
+                                                const float* __restrict__ alpha, const float* __restrict__ dedge, int ld, int ch,
+                                                int il, int ml, int cnt, int k0, size_t ebase, size_t sidx, int head,
+                                                const float4& a, const float4& br, const float4& xlj, float4& dx) {
+    constexpr int NS = 4, HC = 4 * LPR, H = LPR / LPH;
+    int is[NS], ms[NS];
 #pragma unroll
-    for (int k = 0; k < NS; ++k) is[k] = __shfl_sync(0xffffffffu, il, k0 + k, LPR);
+    for (int k = 0; k < NS; ++k) { is[k] = __shfl_sync(0xffffffffu, il, k0 + k, LPR); ms[k] = __shfl_sync(0xffffffffu, ml, k0 + k, LPR); }
     cnt -= k0;
-    float4 xrs[NS], dos[NS], sts[NS];
+    float4 xrs[NS], dos[NS];
+    float al[NS], de[NS];
 #pragma unroll
     for (int k = 0; k < NS; ++k) {
         const bool on = k < cnt;
+        const size_t idx = ms[k] >= 0 ? (ebase + (size_t)ms[k]) * H + head : sidx;
         xrs[k] = on ? f4add(ldg4(xr + (size_t)is[k] * ld + ch), br) : f4zero();
         dos[k] = on ? ldg4(dout + (size_t)is[k] * HC + ch) : f4zero();
-        sts[k] = on ? ldg4(stats + ((size_t)is[k] * H + head) * 4) : f4zero();
+        al[k] = on ? __ldg(alpha + idx) : 0.f;
+        de[k] = on ? __ldg(dedge + idx) : 0.f;
     }
 #pragma unroll
-    for (int k = 0; k < NS; ++k) {
-        const float e = hsum<LPH>(score4(a, xrs[k], xlj));
-        const float dl = hsum<LPH>(dot4(dos[k], xlj));
-        if (k < cnt) {
-            const float al = qdiv(expf(e - sts[k].x), sts[k].y, sts[k].w);
-            bwd_b_edge4(a, xlj, xrs[k], dos[k], al, al * (dl - sts[k].z), dx);
-        }
-    }
+    for (int k = 0; k < NS; ++k) if (k < cnt) bwd_b_edge4(a, xlj, xrs[k], dos[k], al[k], de[k], dx);
 }
 
 template <int LPR, int LPH>
-__global__ void __launch_bounds__(GAT_THREADS, 2)
+__global__ void __launch_bounds__(GAT_THREADS, 3)
 k_gat_bwd_source4(const s2v_graph_t g, int ld, const float* __restrict__ xl, const float* __restrict__ xr,
-                  const float* __restrict__ att, const float* __restrict__ lin_bias, const float* __restrict__ stats,
-                  const float* __restrict__ dout, float* __restrict__ dxl, float* __restrict__ partials) {
+                  const float* __restrict__ att, const float* __restrict__ lin_bias, const float* __restrict__ alpha,
+                  const float* __restrict__ dedge, const int* __restrict__ row_to_col, const float* __restrict__ dout,
+                  float* __restrict__ dxl, float* __restrict__ partials) {
     constexpr int RPW = 32 / LPR, HC = 4 * LPR, H = LPR / LPH;
     __shared__ float red[GAT_WARPS * RPW][HC];
     float4 dbl = f4zero();
     GAT_ROW_SETUP()
     const float4 a = ldg4(att + ch);
     const float4 bl = lin_bias ? ldg4(lin_bias + ch) : f4zero(), br = lin_bias ? ldg4(lin_bias + HC + ch) : f4zero();
+    const size_t copies = g.period > 0 ? (size_t)(g.num_nodes / g.period) : 1;
     GAT_ROW_LOOP(g.rowptr, g.col) {
         GAT_ROW_ADVANCE(g.rowptr, g.col)
+        const int ml = row_map(cur, row_to_col, sl);          // -1 beyond the out-edges: the self edge
         const int r = cur.r, cnt = cur.deg + 1;
         const bool valid = cnt > 0;
         const float4 xlj = valid ? f4add(ldg4(xl + (size_t)r * ld + ch), bl) : f4zero();
+        const size_t ebase = (size_t)cur.gi * g.num_edges, sidx = (copies * g.num_edges + (size_t)r) * H + head;
         float4 dx = f4zero();
         const int mc = warp_max_cnt<LPR>(cnt);
         if (mc <= GAT_FAST) {             // the edges of a source are independent: batches of four keep the registers low
-            bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, 0, a, br, xlj, dx);
-            if (mc > 4) bwd_source_fast<LPR, LPH, 4>(xr, dout, stats, ld, ch, head, jl, cnt, 4, a, br, xlj, dx);
+            bwd_source_fast<LPR, LPH>(xr, dout, alpha, dedge, ld, ch, jl, ml, cnt, 0, ebase, sidx, head, a, br, xlj, dx);
+            if (mc > 4) bwd_source_fast<LPR, LPH>(xr, dout, alpha, dedge, ld, ch, jl, ml, cnt, 4, ebase, sidx, head, a, br, xlj, dx);
         } else {
-            for (int k = 0; k < mc; ++k) {
-                const bool on = k < cnt;
-                const int i = on && k < cur.deg ? __ldg(g.col + cur.beg + k) + cur.off : r;
-                const float4 xri = on ? f4add(ldg4(xr + (size_t)i * ld + ch), br) : f4zero();
-                const float4 doi = on ? ldg4(dout + (size_t)i * HC + ch) : f4zero();
-                const float4 st = on ? ldg4(stats + ((size_t)i * H + head) * 4) : f4zero();
-                const float e = hsum<LPH>(score4(a, xri, xlj));
-                const float dl = hsum<LPH>(dot4(doi, xlj));
-                if (!on) continue;
-                const float al = qdiv(expf(e - st.x), st.y, st.w);
-                bwd_b_edge4(a, xlj, xri, doi, al, al * (dl - st.z), dx);
+            for (int k = 0; k < cnt; ++k) {
+                const int i = k < cur.deg ? __ldg(g.col + cur.beg + k) + cur.off : r;
+                const size_t idx = k < cur.deg ? (ebase + (size_t)__ldg(row_to_col + cur.beg + k)) * H + head : sidx;
+                const float4 xri = f4add(ldg4(xr + (size_t)i * ld + ch), br);
+                const float4 doi = ldg4(dout + (size_t)i * HC + ch);
+                bwd_b_edge4(a, xlj, xri, doi, __ldg(alpha + idx), __ldg(dedge + idx), dx);
             }
         }
         if (valid) { st4(dxl + (size_t)r * ld + ch, dx); dbl = f4add(dbl, dx); }
@@ -744,18 +793,29 @@ int gat_grid(int num_nodes, int rows_per_cta) {
         default: { constexpr int LPR = 16, LPH = 4; CALL; break; }        \
     }
 
+static int64_t gat_edge_floats(const s2v_graph_t* g, int heads) {
+    const int64_t copies = g->period > 0 ? g->num_nodes / g->period : 1;
+    return (copies * (int64_t)g->num_edges + g->num_nodes) * heads;
+}
+
+extern "C" int64_t s2v_gat_edge_floats(const s2v_graph_t* g, int32_t heads) {
+    return g && heads > 0 ? gat_edge_floats(g, heads) : 0;
+}
+
 extern "C" int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                                     const float* xl, const float* xr, const float* att, const float* bias,
-                                    const float* lin_bias, int32_t apply_relu, float* out, float* stats, void* stream) {
+                                    const float* lin_bias, int32_t apply_relu, float* out, float* stats, float* alpha,
+                                    void* stream) {
     S2V_RETURN_IF(gat_check(g, heads, channels, ld));
-    if (!xl || !xr || !att || !bias || !out || !stats) return S2V_ERR_BAD_ARG;
+    if (!xl || !xr || !att || !bias || !out || (!stats && !alpha)) return S2V_ERR_BAD_ARG;
     if (g->num_nodes == 0) return 0;
     cudaStream_t st = (cudaStream_t)stream;
-    const int sp = gat_special(heads, channels, ld);
+    const int sp = alpha ? gat_special(heads, channels, ld) : 0;
     if (sp) {
         const int grid = gat_grid(g->num_nodes, GAT_WARPS * (sp == 1 ? 1 : 2));
-        GAT_SPECIAL(sp, (k_gat_fwd4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, bias, lin_bias, apply_relu, out, stats)));
+        GAT_SPECIAL(sp, (k_gat_fwd4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, bias, lin_bias, apply_relu, out, alpha)));
     } else {
+        if (!stats) return S2V_ERR_BAD_ARG;
         const int grid = gat_grid(g->num_nodes, GAT_WARPS);
         GAT_DISPATCH(gat_vec(heads, channels),
                      (k_gat_fwd<V><<<grid, GAT_THREADS, 0, st>>>(*g, heads, channels, ld, xl, xr, att, bias, lin_bias, apply_relu, out, stats)));
@@ -763,17 +823,28 @@ extern "C" int s2v_gat_attn_forward(const s2v_graph_t* g, int32_t heads, int32_t
     return (int)cudaGetLastError();
 }
 
-extern "C" int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels) {
-    return (int64_t)sizeof(float) * S2V_GAT_MAX_GRID * 4 * heads * channels;   // per-CTA partials (datt, dbias, sum dx_r, sum dx_l)
+// 1 when the (heads, channels, ld) combination runs the specialised kernels, which keep per-edge attention weights
+// (alpha, [s2v_gat_edge_floats]) instead of per-node softmax statistics and need the row_to_col edge map in backward
+extern "C" int s2v_gat_uses_edge_alpha(int32_t heads, int32_t channels, int32_t ld) {
+    return gat_vec(heads, channels) && gat_special(heads, channels, ld) ? 1 : 0;
+}
+
+extern "C" int64_t s2v_gat_attn_backward_workspace_bytes(int32_t heads, int32_t channels, int64_t edge_floats) {
+    // per-CTA partials (datt, dbias, sum dx_r, sum dx_l) + de per edge and head (specialised kernels)
+    return (int64_t)sizeof(float) * ((int64_t)S2V_GAT_MAX_GRID * 4 * heads * channels + (edge_floats > 0 ? edge_floats : 0));
 }
 
 extern "C" int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels, int32_t ld,
                                      const float* xl, const float* xr, const float* att, const float* lin_bias,
-                                     float* stats, const float* dout, float* dxl, float* dxr, float* grad_att, float* grad_bias,
+                                     float* stats, const float* alpha, const int32_t* row_to_col, const float* dout,
+                                     float* dxl, float* dxr, float* grad_att, float* grad_bias,
                                      float* grad_lin_bias, void* workspace, int64_t workspace_bytes, void* stream) {
     S2V_RETURN_IF(gat_check(g, heads, channels, ld));
-    if (!xl || !xr || !att || !stats || !dout || !dxl || !dxr || !grad_att || !grad_bias || !grad_lin_bias || !workspace) return S2V_ERR_BAD_ARG;
-    if (workspace_bytes < s2v_gat_attn_backward_workspace_bytes(heads, channels)) return S2V_ERR_WORKSPACE;
+    if (!xl || !xr || !att || (!stats && !alpha) || !dout || !dxl || !dxr || !grad_att || !grad_bias || !grad_lin_bias || !workspace) return S2V_ERR_BAD_ARG;
+    const int sp = alpha ? gat_special(heads, channels, ld) : 0;
+    if (sp && g->num_edges > 0 && !row_to_col) return S2V_ERR_BAD_ARG;
+    if (!sp && !stats) return S2V_ERR_BAD_ARG;
+    if (workspace_bytes < s2v_gat_attn_backward_workspace_bytes(heads, channels, sp ? gat_edge_floats(g, heads) : 0)) return S2V_ERR_WORKSPACE;
     const int HC = heads * channels;
     cudaStream_t st = (cudaStream_t)stream;
     if (g->num_nodes == 0) {
@@ -783,13 +854,13 @@ extern "C" int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_
         return (int)cudaGetLastError();
     }
     float* partials = (float*)workspace;
-    const int sp = gat_special(heads, channels, ld);
+    float* dedge = partials + (size_t)S2V_GAT_MAX_GRID * 4 * HC;
     int grid;
     if (sp) {
         grid = gat_grid(g->num_nodes, GAT_WARPS * (sp == 1 ? 1 : 2));
-        GAT_SPECIAL(sp, (k_gat_bwd_target4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, lin_bias, stats, dout, dxr, partials)));
+        GAT_SPECIAL(sp, (k_gat_bwd_target4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, lin_bias, alpha, dedge, dout, dxr, partials)));
         S2V_RETURN_IF(cudaGetLastError());
-        GAT_SPECIAL(sp, (k_gat_bwd_source4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, lin_bias, stats, dout, dxl, partials)));
+        GAT_SPECIAL(sp, (k_gat_bwd_source4<LPR, LPH><<<grid, GAT_THREADS, 0, st>>>(*g, ld, xl, xr, att, lin_bias, alpha, dedge, row_to_col, dout, dxl, partials)));
     } else {
         grid = gat_grid(g->num_nodes, GAT_WARPS);
         GAT_DISPATCH(gat_vec(heads, channels),

@@ -33,13 +33,13 @@ def strip_self_loops(edge_index: torch.Tensor) -> torch.Tensor:
 def gat_layout_from_batch(edge_index, ptr, batch=None) -> GraphLayout:
     """Batched layout for the GAT kernels (PyG Batch.from_data_list order)."""
     _require_cuda(edge_index, "edge_index")
-    return GraphLayout.from_batch(strip_self_loops(edge_index), ptr, 0, batch)
+    return GraphLayout.from_batch(strip_self_loops(edge_index), ptr, 0, batch, edge_map=True)
 
 
 def gat_layout_replicated(edge_index, num_nodes: int, copies: int) -> GraphLayout:
     """S copies of one topology (models_basic_lstm.py:509-513 builds a Batch of S Data(e, ei))."""
     _require_cuda(edge_index, "edge_index")
-    return GraphLayout.replicated(strip_self_loops(edge_index), num_nodes, copies)
+    return GraphLayout.replicated(strip_self_loops(edge_index), num_nodes, copies, edge_map=True)
 
 
 _CHUNK = 4096
@@ -100,11 +100,21 @@ class _GATConvFn(torch.autograd.Function):
         att_f = ops._f32c(att.detach().reshape(-1), "att")
         bias_f = ops._f32c(bias.detach(), "bias")
         out = torch.empty(n, HC, dtype=torch.float32, device=x.device)
-        stats = torch.empty(n, heads, 4, dtype=torch.float32, device=x.device)
+        # what the backward needs from the softmax: per-edge weights (specialised shapes, with the layout's edge map)
+        # or 16 bytes of statistics per node and head (generic kernels)
+        edge_alpha = bool(L.s2v_gat_uses_edge_alpha(heads, Cc, ld)) and (layout.row_to_col is not None or layout.num_edges == 0)
+        if edge_alpha:
+            edge_floats = int(L.s2v_gat_edge_floats(C.byref(layout.c_struct()), heads))
+            stats = torch.empty(edge_floats, dtype=torch.float32, device=x.device)
+        else:
+            edge_floats = 0
+            stats = torch.empty(n, heads, 4, dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
             _lib.check(L.s2v_gat_attn_forward(C.byref(layout.c_struct()), heads, Cc, ld, _p(xlr), xr_ptr, _p(att_f),
-                                              _p(bias_f), _p(bcat), int(relu != 0), _p(out), _p(stats), _stream()),
+                                              _p(bias_f), _p(bcat), int(relu != 0), _p(out),
+                                              None if edge_alpha else _p(stats), _p(stats) if edge_alpha else None, _stream()),
                        "s2v_gat_attn_forward")
+        ctx.edge_floats = edge_floats
         _lib.launch_count += 1
         ctx.layout, ctx.heads, ctx.relu, ctx.shared, ctx.tensor, ctx.mask_dx = layout, heads, relu, shared, tensor, mask_dx
         ctx.save_for_backward(x, xlr, stats, out, att_f, wcat, bcat)
@@ -130,9 +140,11 @@ class _GATConvFn(torch.autograd.Function):
             dxr_ptr = C.c_void_p(dxlr.data_ptr() + 4 * (n * HC if shared else HC))
             xr_ptr = _p(xlr) if shared else C.c_void_p(xlr.data_ptr() + 4 * HC)
             gab = torch.empty(4, HC, dtype=torch.float32, device=x.device)       # datt | dbias | dlin_l.bias | dlin_r.bias
-            ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(heads, Cc), dtype=torch.uint8, device=x.device)
+            ef = ctx.edge_floats
+            ws = torch.empty(L.s2v_gat_attn_backward_workspace_bytes(heads, Cc, ef), dtype=torch.uint8, device=x.device)
             _lib.check(L.s2v_gat_attn_backward(C.byref(layout.c_struct()), heads, Cc, ld, _p(xlr), xr_ptr, _p(att_f),
-                                               _p(bcat), _p(stats), _p(dout), _p(dxlr), dxr_ptr, _p(gab[0]), _p(gab[1]),
+                                               _p(bcat), None if ef else _p(stats), _p(stats) if ef else None,
+                                               _p(layout.row_to_col) if ef else None, _p(dout), _p(dxlr), dxr_ptr, _p(gab[0]), _p(gab[1]),
                                                _p(gab[2]), _p(ws), ws.numel(), _stream()), "s2v_gat_attn_backward")
         _lib.launch_count += 3
         if shared:

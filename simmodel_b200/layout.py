@@ -36,13 +36,14 @@ class GraphLayout:
                  batch is ``num_graphs`` copies with different node features (PPO path).
     """
 
-    def __init__(self, num_nodes, num_graphs, period, rowptr, col, rowptr_t, col_t, indeg, ptr, gid, npad):
+    def __init__(self, num_nodes, num_graphs, period, rowptr, col, rowptr_t, col_t, indeg, ptr, gid, npad, row_to_col=None):
         self.num_nodes = int(num_nodes)
         self.num_graphs = int(num_graphs)
         self.period = int(period)
         self.rowptr, self.col, self.rowptr_t, self.col_t, self.indeg = rowptr, col, rowptr_t, col_t, indeg
         self.ptr, self.gid = ptr, gid
         self.npad = npad                      # int or int32 tensor [B]
+        self.row_to_col = row_to_col          # int32 [E] or None: col position -> col_t position of the same edge (GATv2)
         self._struct = None
 
     @property
@@ -73,12 +74,13 @@ class GraphLayout:
         if isinstance(npad, torch.Tensor):
             npad = npad.to(device=self.device, dtype=torch.int32).contiguous()
         return GraphLayout(self.num_nodes, self.num_graphs, self.period, self.rowptr, self.col, self.rowptr_t,
-                           self.col_t, self.indeg, self.ptr, self.gid, npad)
+                           self.col_t, self.indeg, self.ptr, self.gid, npad, self.row_to_col)
 
     # ------------------------------------------------------------------
     @staticmethod
-    def build_csr(edge_index: torch.Tensor, n: int, validate: bool = True):
-        """edge_index int64 [2,E] on the GPU, ids in [0,n) -> (rowptr, col, rowptr_t, col_t, indeg) int32."""
+    def build_csr(edge_index: torch.Tensor, n: int, validate: bool = True, edge_map: bool = False):
+        """edge_index int64 [2,E] on the GPU, ids in [0,n) -> (rowptr, col, rowptr_t, col_t, indeg) int32
+        (+ row_to_col int32 [E] when edge_map)."""
         _require_cuda(edge_index, "edge_index")
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise ValueError("edge_index must have shape [2,E]")
@@ -98,11 +100,18 @@ class GraphLayout:
         _lib.launch_count += 10 if E > 0 else 6
         if validate and int(ws[:4].view(torch.int32).item()) != 0:
             raise ValueError("edge_index contains node ids outside [0, %d)" % n)
+        if edge_map:
+            r2c = torch.empty(E, dtype=torch.int32, device=dev)
+            scratch = torch.empty(E, dtype=torch.int32, device=dev)
+            with torch.cuda.device(dev):
+                _lib.check(L.s2v_csr_row_to_col(_p(ws), n, E, _p(scratch), _p(r2c), _stream()), "s2v_csr_row_to_col")
+            _lib.launch_count += 2 if E > 0 else 0
+            return rowptr, col, rowptr_t, col_t, indeg, r2c
         return rowptr, col, rowptr_t, col_t, indeg
 
     @classmethod
     def from_batch(cls, edge_index: torch.Tensor, ptr: torch.Tensor, n_pad, batch: torch.Tensor | None = None,
-                   validate: bool = True) -> "GraphLayout":
+                   validate: bool = True, edge_map: bool = False) -> "GraphLayout":
         """Batched layout from a PyG-style (edge_index, ptr[, batch]) triple.
         n_pad: int (xv.shape[1] of the reference call) or per-graph tensor."""
         _require_cuda(edge_index, "edge_index")
@@ -117,22 +126,22 @@ class GraphLayout:
             gid = batch.to(device=dev, dtype=torch.int32).contiguous()
         if gid.numel() != n:
             raise ValueError("batch vector length %d != ptr[-1] %d" % (gid.numel(), n))
-        rowptr, col, rowptr_t, col_t, indeg = cls.build_csr(edge_index, n, validate)
+        rowptr, col, rowptr_t, col_t, indeg, *r2c = cls.build_csr(edge_index, n, validate, edge_map)
         if isinstance(n_pad, torch.Tensor):
             n_pad = n_pad.to(device=dev, dtype=torch.int32).contiguous()
-        return cls(n, B, 0, rowptr, col, rowptr_t, col_t, indeg, ptr32, gid, n_pad)
+        return cls(n, B, 0, rowptr, col, rowptr_t, col_t, indeg, ptr32, gid, n_pad, r2c[0] if r2c else None)
 
     @classmethod
     def replicated(cls, edge_index: torch.Tensor, num_nodes: int, copies: int, n_pad=None,
-                   validate: bool = True) -> "GraphLayout":
+                   validate: bool = True, edge_map: bool = False) -> "GraphLayout":
         """``copies`` graphs sharing one topology (S time steps of a PPO rollout)."""
-        rowptr, col, rowptr_t, col_t, indeg = cls.build_csr(edge_index, num_nodes, validate)
+        rowptr, col, rowptr_t, col_t, indeg, *r2c = cls.build_csr(edge_index, num_nodes, validate, edge_map)
         return cls(num_nodes * copies, copies, num_nodes, rowptr, col, rowptr_t, col_t, indeg, None, None,
-                   num_nodes if n_pad is None else n_pad)
+                   num_nodes if n_pad is None else n_pad, r2c[0] if r2c else None)
 
     def replicate(self, copies: int) -> "GraphLayout":
         """Re-use the CSR of a replicated layout for a different number of copies."""
         if self.period <= 0:
             raise ValueError("replicate() needs a replicated layout")
         return GraphLayout(self.period * copies, copies, self.period, self.rowptr, self.col, self.rowptr_t,
-                           self.col_t, self.indeg, None, None, self.npad)
+                           self.col_t, self.indeg, None, None, self.npad, self.row_to_col)

@@ -141,7 +141,7 @@ class S2VKernelMixin:
             if len(self._layouts) >= 64:
                 self._layouts.clear()
             dev_ei = ei.to(self.device)
-            base = GraphLayout.replicated(strip_self_loops(dev_ei) if gat else dev_ei, num_nodes, 1)
+            base = GraphLayout.replicated(strip_self_loops(dev_ei) if gat else dev_ei, num_nodes, 1, edge_map=gat)
             hit = (ei, base)                   # keep ei alive so id() stays unique
             self._layouts[key] = hit
         return hit[1].replicate(copies)
