@@ -45,7 +45,7 @@ def parse():
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--batch", type=int, default=4096, help="graphs per GPU")
-    ap.add_argument("--topo", default="NWB_AMS", choices=["NWB_AMS", "NWB_ROT", "NWB_UTR", "Manhattan5"],
+    ap.add_argument("--topo", default="NWB_AMS", choices=["NWB_AMS", "NWB_ROT", "NWB_UTR", "Manhattan5", "MemTask"],
                     help="topology of the synthetic batch (default: the N=975 graph the metric is quoted on; "
                          "NWB_ROT = BASELINE configs[4] scale sweep)")
     ap.add_argument("--qnet", default="s2v", choices=["s2v", "gat2"],
@@ -64,7 +64,8 @@ def parse():
     return ap.parse_args()
 
 
-TOPO_SHAPES = {"NWB_AMS": (975, 2850), "NWB_ROT": (2602, 7266), "NWB_UTR": (1182, 3204), "Manhattan5": (25, 105)}
+TOPO_SHAPES = {"NWB_AMS": (975, 2850), "NWB_ROT": (2602, 7266), "NWB_UTR": (1182, 3204), "Manhattan5": (25, 105),
+               "MemTask": (8, 22)}
 
 
 def workload_config(batch, n_gpus):
@@ -772,6 +773,32 @@ def run_ppo(args):
     ms = timed(step, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
     e2e_ms = None if args.no_e2e else timed(step_e2e, max(3, min(args.steps, 10)), 1)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline and args.qnet == "s2v":
+        # the reference's arithmetic (dense W, (S,N,N,p) theta4 tensor; oracle/s2v_ref.py restating models_basic_lstm.py:479-566)
+        # on a bounded sample: v(s'), v(s), pi(s) forward + backward for the first steps of one rollout
+        from oracle import s2v_ref as Rf
+        cores = os.cpu_count() or 1
+        torch.set_num_threads(cores)
+        s_cpu = max(1, min(S, int(2.5e8 // (N * N * P))))       # keep the (S,N,N,p) tensor under ~1 GB
+        Pm = {k: v.detach().cpu().clone().requires_grad_(True) for k, v in model.state_dict().items()}
+        b0 = host[0]
+        nfm_c, reach_c = b0["nfm"][:s_cpu + 1].clone(), b0["reach"][:s_cpu + 1].clone()
+        ei_c = topo.edge_index
+        lstm_c = torch.nn.LSTM(P, P) if args.ppo_lstm == "EMB" else None
+        hid_c = (torch.zeros(1, N, P), torch.zeros(1, N, P)) if lstm_c is not None else None
+
+        def cpu_step():
+            for v in Pm.values():
+                v.grad = None
+            vp, _ = Rf.ppo_v_dense(Pm, nfm_c[1:], ei_c, reach_c[1:], T, "q", lstm_c, hid_c)
+            vs, _ = Rf.ppo_v_dense(Pm, nfm_c[:-1], ei_c, reach_c[:-1], T, "q", lstm_c, hid_c)
+            pi, _ = Rf.ppo_pi_dense(Pm, nfm_c[:-1], ei_c, reach_c[:-1], T, lstm_c, hid_c)
+            (vp.sum() + vs.sum() + pi.gather(1, b0["a"][:s_cpu]).log().sum()).backward()
+        times = time_cpu(cpu_step, 2, 10.0)
+        cpu_baseline = {"value": s_cpu / statistics.mean(times), "unit": "rollout-steps/s", "cores": cores, "kind": "port",
+                        "sample": "dense reference arithmetic (models_basic_lstm.py:479-566 restated): v(s'), v(s), pi(s) fwd+bwd "
+                                  "for %d steps of one rollout on %s, %d repetitions; torch %s CPU" % (s_cpu, TOPO, len(times), torch.__version__)}
     if world > 1:
         dist.destroy_process_group()
     if rank != 0:
@@ -791,7 +818,8 @@ def run_ppo(args):
                              % (S * n_t, S * n_t * 256 / 1e6, 3 * R)},
             "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "clocks": clocks,
             "e2e": None if e2e_ms is None else {"value": R * S * world / (e2e_ms / 1e3), "unit": "rollout-steps/s",
-                                                "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4}}
+                                                "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
+            "cpu_baseline": cpu_baseline}
     print(json.dumps(line), flush=True)
 
 
