@@ -307,3 +307,46 @@ def test_gat_large_batch_tensor_lin_vs_oracle(cuda_device, monkeypatch):
         _check("q " + path, q.detach().cpu().numpy(), refs["f32"][0].numpy(), refs["f64"][0].numpy(), tol=1e-5)
         for k, prm in net.named_parameters():
             _check("grad %s %s" % (k, path), prm.grad.cpu().numpy(), refs["f32"][1][k].numpy(), refs["f64"][1][k].numpy(), tol=tol)
+
+
+@pytest.mark.parametrize("heads,C", [(2, 32), (4, 32), (4, 16), (4, 12)])
+def test_gat_conv_edge_cases(heads, C, cuda_device):
+    """No edges at all (every node attends to itself only: out = x_l + bias), and a hub with 40 incoming / outgoing
+    edges (beyond the register-resident slots and beyond the ids a lane group prefetches), specialised and generic
+    kernels, batched and replicated layouts."""
+    import simmodel_b200 as sb
+    from oracle import gat_ref as R
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(heads * 100 + C)
+    n, cin = 41, 16
+    conv = sb.GATv2Conv(cin, C, heads=heads)
+    with torch.no_grad():
+        conv.bias.copy_(torch.randn(heads * C, generator=gen) * 0.1)
+    P = {k: v.detach().clone().double().requires_grad_(True) for k, v in conv.state_dict().items()}
+    conv = conv.to(dev)
+    hub = torch.arange(1, n)
+    eis = {"no_edges": torch.zeros(2, 0, dtype=torch.int64),
+           "hub": torch.cat((torch.stack((hub, torch.zeros_like(hub))), torch.stack((torch.zeros_like(hub), hub)),
+                             torch.tensor([[5, 7, 7], [6, 8, 7]])), dim=1)}
+    for name, ei in eis.items():
+        for copies in (1, 3):
+            x = torch.randn(copies * n, cin, generator=gen)
+            w = torch.randn(copies * n, heads * C, generator=gen)
+            x64 = x.double().requires_grad_(True)
+            for t in P.values():
+                t.grad = None
+            ei_b = torch.cat([ei + k * n for k in range(copies)], dim=1)
+            ref = R.gatv2_conv(x64, ei_b, P["lin_l.weight"], P["lin_l.bias"], P["lin_r.weight"], P["lin_r.bias"], P["att"], P["bias"])
+            (ref * w.double()).sum().backward()
+            layouts = [sb.gat.gat_layout_from_batch(ei_b.to(dev), torch.arange(copies + 1, device=dev) * n)]
+            if copies > 1:
+                layouts.append(sb.gat.gat_layout_replicated(ei.to(dev), n, copies))
+            for layout in layouts:
+                conv.zero_grad()
+                xd = x.to(dev).requires_grad_(True)
+                out = conv.forward_layout(xd, layout)
+                (out * w.to(dev)).sum().backward()
+                _check("%s out" % name, out.detach().cpu().numpy(), ref.detach().numpy(), tol=3e-6)
+                _check("%s dx" % name, xd.grad.cpu().numpy(), x64.grad.numpy(), tol=3e-6)
+                for k, prm in conv.named_parameters():
+                    _check("%s grad %s" % (name, k), prm.grad.cpu().numpy(), P[k].grad.numpy(), tol=3e-6, abs_floor=1e-12)
