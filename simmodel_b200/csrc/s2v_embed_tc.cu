@@ -1777,6 +1777,16 @@ k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W,
             tc::mma_commit(&sh->bar);
         }
         __syncwarp();
+        float4 mk[MASK ? NB : 1][8];                       // the mask rows of this tile: in flight during the MMAs
+        if (MASK) {
+#pragma unroll
+            for (int nb = 0; nb < NB; ++nb)
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+                    mk[nb][i] = rl < rows ? ldg4(M + (size_t)(row0 + rl) * ldm + 64 * nb + 4 * c4) : f4zero();
+                }
+        }
         if (tile + (int)gridDim.x < num_tiles) load_rows(tile + gridDim.x);      // in flight during the MMAs and the epilogue
         tc::mbar_wait(&sh->bar, phase);
         phase ^= 1;
@@ -1792,8 +1802,8 @@ k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W,
                 if (rl < rows) {
                     float4 v = ld4(stg + rl * STG_LD + 4 * c4);
                     if (MASK) {
-                        const float4 mk = ldg4(M + (size_t)(row0 + rl) * ldm + 64 * nb + 4 * c4);
-                        v = make_float4(mk.x > 0.f ? v.x : 0.f, mk.y > 0.f ? v.y : 0.f, mk.z > 0.f ? v.z : 0.f, mk.w > 0.f ? v.w : 0.f);
+                        const float4 k4 = mk[nb][i];
+                        v = make_float4(k4.x > 0.f ? v.x : 0.f, k4.y > 0.f ? v.y : 0.f, k4.z > 0.f ? v.z : 0.f, k4.w > 0.f ? v.w : 0.f);
                     }
                     st4(out + (size_t)(row0 + rl) * ldo + 64 * nb + 4 * c4, v);
                 }
@@ -1842,7 +1852,8 @@ k_rows_reduce16(const float* __restrict__ A, int lda, const float* __restrict__ 
         }
     };
     if (blockIdx.x < num_tiles) load_rows(blockIdx.x);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+    int it = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, ++it) {
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int e = t + TC_THREADS * i;
@@ -1852,10 +1863,13 @@ k_rows_reduce16(const float* __restrict__ A, int lda, const float* __restrict__ 
         }
         tc::fence_proxy_async_smem();
         __syncthreads();
+        // the tensor core adds into its accumulator with truncation: at most four tiles are chained in TMEM, then the
+        // group is summed on the CUDA cores (same rule as the s2v backward pipeline)
+        const bool first = (it & 3) == 0, last = (it & 3) == 3 || tile + (int)gridDim.x >= num_tiles;
         if (warp == 0) {
             tc::tc_fence_after_sync();
 #pragma unroll
-            for (int ab = 0; ab < AB; ++ab) issue_reduce16(d + 64 * ab, s_a + ab * TILE16X3, s_b, false);
+            for (int ab = 0; ab < AB; ++ab) issue_reduce16(d + 64 * ab, s_a + ab * TILE16X3, s_b, !first);
             tc::mma_commit(&sh->bar);
         }
         __syncwarp();
@@ -1863,16 +1877,17 @@ k_rows_reduce16(const float* __restrict__ A, int lda, const float* __restrict__ 
         tc::mbar_wait(&sh->bar, phase);
         phase ^= 1;
         tc::tc_fence_after_sync();
-        // the tensor core adds into its accumulator with truncation: every tile is summed on the CUDA cores
+        if (last) {
 #pragma unroll
-        for (int ab = 0; ab < AB; ++ab)
+            for (int ab = 0; ab < AB; ++ab)
 #pragma unroll
-            for (int half = 0; half < 2; ++half) {
-                float v[32];
-                tc::tmem_ld32(d + 64 * ab + ((uint32_t)(32 * warp) << 16) + 32 * half, v);
+                for (int half = 0; half < 2; ++half) {
+                    float v[32];
+                    tc::tmem_ld32(d + 64 * ab + ((uint32_t)(32 * warp) << 16) + 32 * half, v);
 #pragma unroll
-                for (int i = 0; i < 32; ++i) racc[ab][32 * half + i] += v[i];
-            }
+                    for (int i = 0; i < 32; ++i) racc[ab][32 * half + i] += v[i];
+                }
+        }
         tc::tc_fence_before_sync();
         __syncthreads();                                   // accumulators and tiles free again
     }
