@@ -461,20 +461,20 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
     uint8_t* b_lo = b_hi + TILE_BYTES;
     uint8_t* a_hi = b_lo + TILE_BYTES;           // h tile; a_lo follows; both reused as staging
     uint8_t* a_lo = a_hi + TILE_BYTES;
-    float* W1a = reinterpret_cast<float*>(a_lo + TILE_BYTES);   // [F][64]
-    float* xs = W1a + S2V_MAX_F * 64;                           // [64][F]
-    float* vec = xs + TCR * S2V_MAX_F;                          // b1a, cst, u1, u0, r1, r0 (6 x 64)
+    const int F = prm.node_dim;
+    const int FS = (F + 3) & ~3;                 // x rows and theta1a are padded to a multiple of four features (zeros)
+    float* W1a = reinterpret_cast<float*>(a_lo + TILE_BYTES);   // [FS][64]   (sized by the actual F: F = 7 leaves room
+    float* xs = W1a + FS * 64;                                  // [64][FS]    for a third CTA per SM, first_smem_bytes)
+    float* vec = xs + TCR * FS;                                 // b1a, cst, u1, u0, r1, r0 (6 x 64)
     float* cw = vec + 6 * 64;                                   // [64] c_r, [64] Npad - c_r
     TcShared* sh = reinterpret_cast<TcShared*>(cw + 128);
     float* stg = reinterpret_cast<float*>(a_hi);
     float* b1a = vec, *cst = vec + 64, *u1 = vec + 128, *u0 = vec + 192, *r1 = vec + 256, *r0 = vec + 320;
-    const int F = prm.node_dim;
     const int t = threadIdx.x, warp = t >> 5;
 
     if (warp == 0) tc::tmem_alloc<64>(&sh->tmem_base);
     if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
     load_weight_tiles(b_hi, b_lo, prm.theta1b_w, false);
-    const int FS = (F + 3) & ~3;                 // x rows and theta1a are padded to a multiple of four features (zeros)
     for (int e = t; e < 64 * FS; e += TC_THREADS) { int f = e >> 6, n = e & 63; W1a[e] = f < F ? __ldg(prm.theta1a_w + n * F + f) : 0.f; }
     if (t < 64) {
         b1a[t] = __ldg(prm.theta1a_b + t);
@@ -1694,7 +1694,10 @@ k_tc_rate(float* __restrict__ out, int reps) {
 
 constexpr int FWD_SMEM = 4 * TILE_BYTES + 64 + 1024;
 constexpr int WS_SMEM = TILE16X3 + WS_STAGES * WS_STAGE_BYTES + 2 * WS_STG_FLOATS * 4 + (3 * TCR * WS_MAX_F + 16 * 64) * 4 + 256 + 1024;
-constexpr int FIRST_SMEM = 4 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 6 * 64 + 128) * 4 + 64 + 1024;
+static inline int first_smem_bytes(int F) {
+    const int FS = (F + 3) & ~3;
+    return 4 * (int)TILE_BYTES + (FS * 64 + TCR * FS + 6 * 64 + 128) * 4 + 64 + 1024;
+}
 constexpr int FIN_SMEM = 6 * TILE_BYTES + (S2V_MAX_F * 64 + TCR * S2V_MAX_F + 64 + 128) * 4 + 64 + 1024;
 constexpr int BWD_SMEM = 6 * TILE_BYTES + 64 + 1024;
 
@@ -2017,6 +2020,7 @@ extern "C" int s2v_debug_timeline(long long* host_out) {
 int s2v_tc_embed_first(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, float* base, float* mu1,
                        cudaStream_t st) {
     const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    const int FIRST_SMEM = first_smem_bytes(prm.node_dim);
     S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_first_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM));
     int grid = tc_grid((const void*)k_embed_first_tc, FIRST_SMEM, 64, tiles);
     k_embed_first_tc<<<grid, TC_THREADS, FIRST_SMEM, st>>>(g, prm, x, base, mu1, tiles);

@@ -198,7 +198,7 @@ __global__ void __launch_bounds__(256)
 k_head_bwd_stream(s2v_graph_t g, const float* __restrict__ mu, const float* __restrict__ per_graph, int mask_relu,
                   float* __restrict__ dmu, const unsigned int* __restrict__ nnz_total) {
     if (!HEAD_SPARSE(*nnz_total, g.num_nodes)) return;
-    constexpr int V = P / 4, U = 4;
+    constexpr int V = P / 4, U = 8;
     const long long total = (long long)g.num_nodes * V, stride = (long long)gridDim.x * 256;
     for (long long e0 = (long long)blockIdx.x * 256 + threadIdx.x; e0 < total; e0 += stride * U) {
         float4 o[U], m[U];
@@ -595,7 +595,7 @@ static int head_backward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm
     const bool split = g.num_nodes >= S2V_TENSOR_MIN_NODES;      // small batches: one launch less matters more
     if (split) {
         const long long chunks = (long long)g.num_nodes * (P / 4);
-        long long want = (chunks + 256 * 4 - 1) / (256 * 4);
+        long long want = (chunks + 256 * 8 - 1) / (256 * 8);
         int sgrid = (int)(want < 148 * 8 ? want : 148 * 8);
         k_head_bwd_stream<P><<<sgrid, 256, 0, st>>>(g, mu, per_graph, mask_relu, dmu, nnz_total);
     }
