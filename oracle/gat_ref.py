@@ -153,6 +153,7 @@ def batch_from_data_list(data_list):
     b.x = torch.cat([d.x for d in data_list], dim=0)
     b.edge_index = torch.cat([d.edge_index.to(torch.int64) + int(b.ptr[k]) for k, d in enumerate(data_list)], dim=1)
     b.num_graphs = len(data_list)
+    b.num_nodes = int(b.ptr[-1])
     return b
 
 

@@ -146,3 +146,19 @@ def test_sb3_mirror_state_dict_keys():
     assert ["extractor." + k for k in ex.state_dict()] == [k for k in G["P"] if k.startswith("extractor.")]
     assert ["acnet." + k for k in ac.state_dict()] == [k for k in G["P"] if k.startswith("acnet.")]
     assert ex.features_dim == meta["n_pad"] * (meta["emb_dim"] + 1)
+
+
+def test_ngo_mirror_state_dict_keys():
+    """models_ngo mirror: parameter names == the unmodified reference's MaskablePPOPolicy (incl. the
+    duplicated lin_r entries of the shared-weight GATv2 layers)."""
+    import types
+    import simmodel_b200 as sb
+    from conftest import load_golden
+    for case in ("ngo_m3m5_seq3_nolstm_q", "ngo_m5m3mem_seq2_lstm_q", "ngo_m3m5_seq1_nolstm_v"):
+        meta, G = load_golden(case)
+        hp = types.SimpleNamespace(emb_dim=64, node_dim=7, lstm_on=meta["lstm_on"], hidden_size=64, recurrent_layers=1,
+                                   max_possible_nodes=meta["max_nodes"], critic=meta["critic"])
+        pol = sb.ngo.MaskablePPOPolicy(None, meta["max_nodes"], False, False, init_log_std_dev=0.0, hp=hp)
+        assert list(pol.state_dict().keys()) == list(G["P"].keys())
+        total, _ = pol.numTrainableParameters()
+        assert total == sum(p.numel() for p in pol.parameters() if p.requires_grad)
