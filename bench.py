@@ -414,7 +414,7 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
 
     flag = _lib.path_flag()
     tensor_f = flag in (2, 3) or (flag == 0 and n >= 4096)   # same rules as csrc/s2v_embed.cu:use_tensor_path
-    sfx_f = "_tc (tcgen05 3xTF32)" if tensor_f else " (FFMA)"
+    sfx_f = ("_tc (tcgen05 3xTF32)" if os.environ.get("S2V_B200_FWD_TF32") else "_tc16 (tcgen05 bf16x3)") if tensor_f else " (FFMA)"
     sfx_b = (" (FFMA)" if not tensor_f else "_tc256 (tcgen05 3xTF32)" if flag == 2
              else "_ws (tcgen05 bf16x3, warp-specialised)")
 
