@@ -588,10 +588,19 @@ def run_gat(args):
             kernels.append({"kernel": name, "ms": k_ms, "algorithmic_bytes": bpn * n, "achieved_GBps": ach, "frac": ach / peak,
                             "launches_per_step": per_step})
         del xlr, out, alpha, dout, dxlr
+    try:                                            # DRAM bytes per row from the ncu --set full capture (H*C = 64 kernels)
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            tt = json.load(f)
+        kernels[0]["traffic"] = tt["k_gat_fwd4"]["bytes_per_node_update"] * n
+        kernels[1]["traffic"] = tt["k_gat_bwd_target4+k_gat_bwd_source4"]["bytes_per_node_update"] * n
+    except Exception:
+        pass
     dom = max(kernels[:2], key=lambda r: r["ms"])
     edge_ms = sum(k["ms"] * k["launches_per_step"] for k in kernels)
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": None, "algorithmic_bytes_per_row": dom["algorithmic_bytes"] / n,
+                "frac": dom["frac"], "traffic": dom.get("traffic"),
+                "traffic_source": "ncu --set full dram__bytes_read+write per row (profiles/traffic.json) x rows of this launch",
+                "algorithmic_bytes_per_row": dom["algorithmic_bytes"] / n,
                 "rows_per_launch": n, "avg_launch_ms": dom["ms"],
                 "edge_kernels_share_of_step": edge_ms / ms,
                 "note": "lin_l/lin_r GEMMs (fp32 cuBLAS, library) and torch reductions make up the rest of the step"}
