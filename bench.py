@@ -603,7 +603,7 @@ def run_gat(args):
                 "algorithmic_bytes_per_row": dom["algorithmic_bytes"] / n,
                 "rows_per_launch": n, "avg_launch_ms": dom["ms"],
                 "edge_kernels_share_of_step": edge_ms / ms,
-                "note": "lin_l/lin_r GEMMs (fp32 cuBLAS, library) and torch reductions make up the rest of the step"}
+                "note": "the rest of the step: lin_l/lin_r GEMMs (tcgen05 bf16x3 kernels for the 64-wide layers, cuBLAS for the first), Q head, Adam"}
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         from oracle import gat_ref as G
