@@ -350,3 +350,100 @@ def test_gat_conv_edge_cases(heads, C, cuda_device):
                 _check("%s dx" % name, xd.grad.cpu().numpy(), x64.grad.numpy(), tol=3e-6)
                 for k, prm in conv.named_parameters():
                     _check("%s grad %s" % (name, k), prm.grad.cpu().numpy(), P[k].grad.numpy(), tol=3e-6, abs_floor=1e-12)
+
+
+@pytest.mark.parametrize("heads,C", [(2, 32), (4, 32), (4, 12)])
+def test_gat_kernels_stay_inside_their_buffers(heads, C, cuda_device):
+    """Every output / workspace buffer of the GAT entry points is surrounded by canary zones that must survive the
+    forward and the backward (specialised per-edge-alpha kernels and the generic statistics kernels; ragged row counts,
+    a hub node beyond the register-resident slots)."""
+    import ctypes as Ct
+    import simmodel_b200 as sb
+    from simmodel_b200 import _lib
+    from simmodel_b200.layout import _p, _stream
+    L = _lib.lib()
+    dev = cuda_device
+    gen = torch.Generator().manual_seed(3)
+    n, HC, GUARD = 1237, heads * C, 4096
+    hub = torch.arange(1, 41)
+    ei = torch.cat(((torch.rand(n, n, generator=gen) < 3.0 / n).nonzero().t(), torch.stack((hub, torch.zeros_like(hub))),
+                    torch.stack((torch.zeros_like(hub), hub))), dim=1)
+    layout = sb.gat.gat_layout_from_batch(ei.to(dev), torch.tensor([0, n], device=dev))
+    g = layout.c_struct()
+    edge_alpha = bool(L.s2v_gat_uses_edge_alpha(heads, C, 2 * HC))
+    ef = int(L.s2v_gat_edge_floats(Ct.byref(g), heads)) if edge_alpha else 0
+
+    class Guarded:
+        def __init__(self, numel, dtype=torch.float32):
+            self.full = torch.full((numel + 2 * GUARD,), 12345.0 if dtype == torch.float32 else 77, dtype=dtype, device=dev)
+            self.view = self.full[GUARD:GUARD + numel]
+            self.fill = self.full[0].item()
+
+        def intact(self):
+            return bool((self.full[:GUARD] == self.fill).all()) and bool((self.full[-GUARD:] == self.fill).all())
+    xlr = torch.randn(n, 2 * HC, generator=gen).to(dev)
+    att, bias, lb = (torch.randn(k, generator=gen).to(dev) * 0.1 for k in (HC, HC, 2 * HC))
+    dout = torch.randn(n, HC, generator=gen).to(dev)
+    out, keep = Guarded(n * HC), Guarded(ef if edge_alpha else n * heads * 4)
+    dxlr, gab = Guarded(n * 2 * HC), Guarded(4 * HC)
+    ws = Guarded(int(L.s2v_gat_attn_backward_workspace_bytes(heads, C, ef)), torch.uint8)
+    xr_p = Ct.c_void_p(xlr.data_ptr() + 4 * HC)
+    _lib.check(L.s2v_gat_attn_forward(Ct.byref(g), heads, C, 2 * HC, _p(xlr), xr_p, _p(att), _p(bias), _p(lb), 1, _p(out.view),
+                                      None if edge_alpha else _p(keep.view), _p(keep.view) if edge_alpha else None, _stream()), "fwd")
+    _lib.check(L.s2v_gat_attn_backward(Ct.byref(g), heads, C, 2 * HC, _p(xlr), xr_p, _p(att), _p(lb),
+                                       None if edge_alpha else _p(keep.view), _p(keep.view) if edge_alpha else None,
+                                       _p(layout.row_to_col), _p(dout), _p(dxlr.view), Ct.c_void_p(dxlr.view.data_ptr() + 4 * HC),
+                                       _p(gab.view[:HC]), _p(gab.view[HC:2 * HC]), _p(gab.view[2 * HC:]), _p(ws.view), ws.view.numel(),
+                                       _stream()), "bwd")
+    torch.cuda.synchronize()
+    for name, b in (("out", out), ("alpha/stats", keep), ("dxlr", dxlr), ("grads", gab), ("workspace", ws)):
+        assert b.intact(), name + " canary overwritten"
+    assert bool(torch.isfinite(out.view).all()) and bool(torch.isfinite(dxlr.view).all()) and bool(torch.isfinite(gab.view).all())
+    if edge_alpha:                                                     # every alpha slot was written: rows sum to one per head
+        assert bool((keep.view >= 0).all()) and bool((keep.view <= 1.0 + 1e-6).all())
+
+
+def test_lin_and_head_backward_kernels_stay_inside_their_buffers(cuda_device):
+    """Canary zones around the outputs of the tensor-core lin kernels (ragged last tile) and of the head backward's
+    streaming + per-row passes (sparse dq, >= 4096 rows)."""
+    import simmodel_b200 as sb
+    from simmodel_b200 import _lib, ops
+    from simmodel_b200.layout import _p, _stream
+    L = _lib.lib()
+    dev = cuda_device
+    GUARD = 4096
+    gen = torch.Generator().manual_seed(9)
+
+    def guarded(numel):
+        full = torch.full((numel + 2 * GUARD,), 12345.0, device=dev)
+        return full, full[GUARD:GUARD + numel]
+
+    def intact(full):
+        return bool((full[:GUARD] == 12345.0).all()) and bool((full[-GUARD:] == 12345.0).all())
+    n = 4999
+    x, w, dy = torch.randn(n, 64, generator=gen).to(dev), (torch.randn(128, 64, generator=gen) * 0.2).to(dev), torch.randn(n, 128, generator=gen).to(dev)
+    fy, y = guarded(n * 128)
+    fdx, dx = guarded(n * 64)
+    fdw, dw = guarded(128 * 64)
+    fws, ws = guarded(int(L.s2v_rows_reduce64_workspace_bytes(2)) // 4)
+    _lib.check(L.s2v_rows_gemm64(_p(x), 64, 1, _p(w), 2, 0, None, 0, _p(y), 128, n, _stream()), "fwd")
+    _lib.check(L.s2v_rows_gemm64(_p(dy), 128, 2, _p(w), 1, 1, _p(x), 64, _p(dx), 64, n, _stream()), "dx")
+    _lib.check(L.s2v_rows_reduce64(_p(dy), 128, 2, _p(x), 64, _p(dw), _p(ws), ws.numel() * 4, n, _stream()), "dw")
+    torch.cuda.synchronize()
+    assert intact(fy) and intact(fdx) and intact(fdw) and intact(fws)
+    # head backward, sparse dq on 5 UTR graphs (5910 rows): stream + per-row passes write dmu
+    topo = sb.graphs.load_topology("NWB_UTR")
+    B = 5
+    layout = sb.GraphLayout.replicated(topo.edge_index.to(dev), topo.num_nodes, B)
+    nn_ = layout.num_nodes
+    torch.manual_seed(0)
+    net = sb.QNet({"emb_dim": 64, "emb_iter_T": 5, "norm_agg": True, "node_dim": 7}, verbose=False).to(dev)
+    mu = torch.randn(nn_, 64, generator=gen).to(dev)
+    hw = [t.detach() for t in net.head_weights()]
+    pool, gstate, q = ops._head_forward(layout, True, mu, hw)
+    dq = torch.zeros(nn_, device=dev)
+    dq[torch.tensor([0, 63, 64, 1181, 1182, nn_ - 1], device=dev)] = torch.randn(6, generator=gen).to(dev)
+    fdmu, dmu = guarded(nn_ * 64)
+    ops._head_backward(layout, True, mu, hw, pool, gstate, dq, True, dmu_out=dmu.view(nn_, 64))
+    torch.cuda.synchronize()
+    assert intact(fdmu) and bool(torch.isfinite(dmu).all())
