@@ -59,6 +59,9 @@ def parse():
     ap.add_argument("--ppo-batched", action="store_true",
                     help="ppo workload through PPO_GNN_Single_LSTM.evaluate_rollouts (all rollouts of the rank in one GNN "
                          "pass, s' embedded once) instead of the reference's per-rollout v(s'), v(s), pi(s) calls")
+    ap.add_argument("--ref-kind", default="dense", choices=["dense", "sparse"],
+                    help="--impl reference: dense = the reference's own arithmetic (dense W, (B,N,N,p) theta4 tensor; B = 2 "
+                         "graphs per step is what fits), sparse = the index_add restatement of the same math (B = 64 per step)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -75,6 +78,17 @@ def workload_config(batch, n_gpus):
             "parallelism": "dp%d" % n_gpus,
             "l2": "inputs exceed L2: per-GPU node features %.0f MB, each embedding plane %.2f GB"
                   % (batch * n * F * 4 / 1e6, batch * n * P * 4 / 1e9)}
+
+
+def reference_config(sample_b, kind):
+    """Config of the --impl reference line: the same workload, with the sample that is REALLY timed per step
+    (the dense reference arithmetic materialises a (B,N,N,p) tensor: 243 MB per AMS graph, so B = 2)."""
+    n, e = TOPO_SHAPES[TOPO]
+    return {"workload": "s2v GNN-DQN train step on %s (N=%d, E=%d, F=7, p=64, T=5, norm_agg)" % (TOPO, n, e),
+            "graphs_per_step": sample_b, "global_batch": sample_b, "nodes_per_graph": n, "parallelism": "host cores, 1 process",
+            "ref_kind": kind,
+            "note": "bounded sample of the workload: %d graphs per step (the B200 arm runs %s graphs per GPU per step); "
+                    "throughput in graphs/s is the comparable quantity" % (sample_b, "--batch")}
 
 
 # --------------------------------------------------------------------------------------
@@ -138,8 +152,8 @@ def run_reference(args):
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    sample_b = 2
-    step, gps, desc = cpu_reference_step_fn("dense", sample_b)
+    sample_b = 2 if args.ref_kind == "dense" else 64
+    step, gps, desc = cpu_reference_step_fn(args.ref_kind, sample_b)
     for _ in range(max(1, min(args.warmup, 3))):
         step()
     times = []
@@ -155,11 +169,47 @@ def run_reference(args):
             "steps": len(times), "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "node_updates_per_sec": val * TOPO_SHAPES[TOPO][0] * T,
-            "config": workload_config(args.batch, args.gpus),
+            "config": reference_config(sample_b, args.ref_kind),
             "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port",
                              "sample": desc + "; torch %s CPU, %d threads" % (torch.__version__, cores)},
             "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
+
+
+def count_kernel_launches(fn):
+    """Kernels launched by one call of fn, COUNTED from a CUPTI trace (torch.profiler): own = kernels of
+    libs2v_b200.so (every one is named k_*), library = everything else (torch elementwise / Adam / NCCL)."""
+    import re
+    import torch
+    try:
+        from torch.profiler import ProfilerActivity, profile
+        with profile(activities=[ProfilerActivity.CUDA]) as prof:
+            fn()
+            torch.cuda.synchronize()
+        own, other, names = 0, 0, {}
+        for ev in prof.events():
+            if getattr(ev, "device_type", None) is None or "cuda" not in str(ev.device_type).lower():
+                continue
+            nm = ev.name
+            if nm.startswith("Memcpy") or nm.startswith("Memset"):
+                continue
+            if re.search(r"(^|::|\s)k_[a-z0-9_]+", nm):
+                own += 1
+                short = re.search(r"k_[a-z0-9_]+", nm).group(0)
+                names[short] = names.get(short, 0) + 1
+            else:
+                other += 1
+        if own + other > 0:
+            return {"own": own, "library": other, "by_kernel": names, "source": "CUPTI trace of one step (torch.profiler)"}
+    except Exception as exc:          # no CUPTI on this box: fall back to the count kept by the bindings
+        err = str(exc)[:120]
+    else:
+        err = "empty trace"
+    from simmodel_b200 import _lib
+    c0 = _lib.launch_count
+    fn()
+    return {"own": _lib.launch_count - c0, "library": None, "by_kernel": None,
+            "source": "count kept by the ctypes bindings (CUPTI unavailable: %s)" % err}
 
 
 # --------------------------------------------------------------------------------------
@@ -258,13 +308,17 @@ def run_b200(args):
     sel = actions_host.to(dev) + ptr[:-1]
     targets = targets_host.to(dev)
     torch.cuda.synchronize()
-    t0 = torch.cuda.Event(enable_timing=True)
-    t1 = torch.cuda.Event(enable_timing=True)
-    t0.record()
-    layout = sb.GraphLayout.from_batch(ei, ptr, N, validate=False)
-    t1.record()
-    torch.cuda.synchronize()
-    csr_ms = t0.elapsed_time(t1)
+    layout = sb.GraphLayout.from_batch(ei, ptr, N, validate=False)          # cold call (module load, first launches)
+    csr_times = []
+    for _ in range(7):                                                       # warm builds: what a step really pays
+        t0 = torch.cuda.Event(enable_timing=True)
+        t1 = torch.cuda.Event(enable_timing=True)
+        t0.record()
+        layout = sb.GraphLayout.from_batch(ei, ptr, N, validate=False)
+        t1.record()
+        torch.cuda.synchronize()
+        csr_times.append(t0.elapsed_time(t1))
+    csr_ms = statistics.median(csr_times)
     del ei
 
     def step():
@@ -297,13 +351,10 @@ def run_b200(args):
         return float(ms.item())
 
     sampler = ClockSampler(local_rank)
-    launches0 = _lib.launch_count
     for _ in range(args.warmup):
         step()
-    launches_per_step = None
-    c0 = _lib.launch_count
-    step()
-    launches_per_step = _lib.launch_count - c0
+    launch_info = count_kernel_launches(step)
+    launches_per_step = launch_info["own"]
     if rank == 0:
         sampler.start()
     total_ms = timed(step, args.steps, 0)
@@ -376,7 +427,9 @@ def run_b200(args):
                 "vs_baseline": None, "dtype": "f32", "data": "synthetic",
                 "node_updates_per_sec": value * N * T,
                 "config": workload_config(B, world), "csr_build_ms": csr_ms,
+                "csr_build_note": "median of 7 warm s2v_csr_build calls over the batch's int64 edge_index (cold first call excluded)",
                 "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+                "gpu_launches_detail": launch_info,
                 "clocks": clocks, "e2e": e2e, "roofline": roofline, "kernels": kernels,
                 "cpu_baseline": cpu_baseline, "small_batch_latency": small_batch}
         print(json.dumps(line), flush=True)
@@ -450,8 +503,14 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
         ent = traffic_tab.get(key)
         r["traffic"] = ent["bytes_per_node_update"] * n if ent else None
     dom = max(res, key=lambda r: r["ms"])
+    for r in res:
+        r["frac_nominal"] = r["achieved_GBps"] / 8000.0
+        r["dram_frac"] = (r["traffic"] / (r["ms"] / 1e3) / 1e9 / peak) if r["traffic"] else None
     roofline = {"bound": "hbm", "kernel": dom["kernel"], "achieved": dom["achieved_GBps"], "peak": peak, "unit": "GB/s",
-                "frac": dom["frac"], "traffic": dom["traffic"],
+                "frac": dom["frac"], "frac_nominal": dom["frac_nominal"], "dram_frac": dom["dram_frac"],
+                "frac_note": "frac = algorithmic bytes / time / measured copy peak; frac_nominal = the same against the 8 TB/s "
+                             "nominal HBM3e figure; dram_frac = measured DRAM traffic (ncu) / time / measured copy peak",
+                "traffic": dom["traffic"],
                 "traffic_source": "ncu --set full dram__bytes_read+write per node-update (profiles/traffic.json) x rows of this launch",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_node_update": bytes_per_node, "node_updates_per_launch": n,
@@ -540,9 +599,8 @@ def run_gat(args):
         return float(ms_t.item())
     for _ in range(args.warmup):
         step()
-    c0 = _lib.launch_count
-    step()
-    launches_per_step = _lib.launch_count - c0
+    launch_info = count_kernel_launches(step)
+    launches_per_step = launch_info["own"]
     sampler = ClockSampler(dev.index or 0)
     sampler.start()
     ms = timed(step, args.steps, 0)
@@ -636,7 +694,8 @@ def run_gat(args):
             "config": {"workload": "QNet_GATv2 GNN-DQN train step on %s (N=%d, E=%d, F=7, emb 64, 5 GATv2Conv layers, heads 2)"
                                    % (TOPO, n_t, e_t), "graphs_per_gpu": B, "global_batch": B * world, "nodes_per_graph": n_t,
                        "parallelism": "dp%d" % world, "l2": "inputs exceed L2: every activation plane %.2f GB" % (B * n_t * P * 4 / 1e9)},
-            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step, "clocks": clocks,
+            "gpu_launches": launches_per_step * args.steps, "gpu_launches_per_step": launches_per_step,
+            "gpu_launches_detail": launch_info, "clocks": clocks,
             "e2e": None if e2e_ms is None else {
                 "value": B * world / (e2e_ms / 1e3), "unit": UNIT, "ms_per_step": e2e_ms,
                 "h2d_bytes_per_step": x_host.numel() * 4 + ei_host.numel() * 8 + actions_host.numel() * 8 + targets_host.numel() * 4,
@@ -773,9 +832,8 @@ def run_ppo(args):
         return float(ms_t.item())
     for _ in range(args.warmup):
         step()
-    c0 = _lib.launch_count
-    step()
-    launches = _lib.launch_count - c0
+    launch_info = count_kernel_launches(step)
+    launches = launch_info["own"]
     sampler = ClockSampler(dev.index or 0)
     if rank == 0:
         sampler.start()
@@ -825,7 +883,8 @@ def run_ppo(args):
                        "parallelism": "dp%d (whole rollouts per rank)" % world,
                        "l2": "per rollout pass %d rows x 256 B = %.1f MB per plane; %d passes per epoch"
                              % (S * n_t, S * n_t * 256 / 1e6, 3 * R)},
-            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "clocks": clocks,
+            "gpu_launches": launches * args.steps, "gpu_launches_per_step": launches, "gpu_launches_detail": launch_info,
+            "clocks": clocks,
             "e2e": None if e2e_ms is None else {"value": R * S * world / (e2e_ms / 1e3), "unit": "rollout-steps/s",
                                                 "ms_per_step": e2e_ms, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4},
             "cpu_baseline": cpu_baseline}

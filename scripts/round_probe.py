@@ -5,6 +5,8 @@ sys.path.insert(0, '.')
 import simmodel_b200 as sb
 from simmodel_b200 import _lib
 from simmodel_b200.layout import _p, _stream
+import os
+if os.environ.get('S2V_PROBE_LIB'): _lib.LIB_PATH = os.environ['S2V_PROBE_LIB']
 L = _lib.lib(); dev = torch.device('cuda'); B = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 flags = [int(a) for a in sys.argv[2:]] or [1, 2, 3]
 topo = sb.graphs.load_topology('NWB_AMS'); n = topo.num_nodes
