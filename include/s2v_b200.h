@@ -123,6 +123,15 @@ int64_t s2v_csr_workspace_bytes(int64_t n, int64_t num_edges);
 int s2v_csr_build(const int64_t* edge_index, int64_t num_edges, int64_t n,
                   int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t, int32_t* indeg,
                   void* workspace, int64_t workspace_bytes, void* stream);
+/* Same builder over the edge list as a trainer holds it on the host: int32 or int64 ids (index_bytes 4 | 8) that are
+ * either global (eptr == nptr == NULL) or LOCAL to their graph -- then eptr[B+1] is the first edge and nptr[B+1] the
+ * first node of every graph, and the builder adds nptr[g] to both endpoints of the edges of graph g on the device.
+ * Replaces the offset pass of Batch.from_data_list (comb_opt.py:299,344) and halves the bytes a batch ships
+ * (int32 local ids instead of int64 global ids).  Output identical to s2v_csr_build on the offset list. */
+int s2v_csr_build_local(const void* edge_index, int32_t index_bytes, int64_t num_edges, int64_t n,
+                        const int32_t* eptr, const int32_t* nptr, int32_t num_graphs,
+                        int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t, int32_t* indeg,
+                        void* workspace, int64_t workspace_bytes, void* stream);
 /* Optional: row_to_col[k] = position in col_t of the edge stored at position k of col (the GATv2 backward walks both
  * forms and exchanges per-edge values).  build_workspace: the workspace of the s2v_csr_build call that produced the
  * CSR, untouched since; scratch: [num_edges] int32. */

@@ -210,6 +210,35 @@ def s2v_embed_sparse(P: dict, x: torch.Tensor, edge_index: torch.Tensor, n_pad_n
     return mu
 
 
+def s2v_embed_sparse_masked(P: dict, x: torch.Tensor, edge_index: torch.Tensor, n_pad_node: torch.Tensor, T: int, masks):
+    """Same arithmetic as s2v_embed_sparse with the ReLU DECISIONS of the T rounds prescribed: mu^t = z^t * masks[t]
+    (masks[t] bool [sumN, p]).  The gradient of a ReLU network is discontinuous where a pre-activation crosses zero; an
+    implementation that rounds differently may decide an element within fp32 resolution of the kink the other way, and
+    a loss that touches every node then routes that element's whole contribution differently.  Holding the decisions
+    fixed makes the comparison well posed: gradients must agree to rounding, and the decisions themselves are compared
+    separately (count of elements with (z^t > 0) != masks[t], each of which must sit at the kink).
+    Returns (mu^T, [z^1..z^T])."""
+    dt = x.dtype
+    n = x.shape[0]
+    p = P["theta2.weight"].shape[0]
+    s1 = _lin(P, "theta1b", F.relu(_lin(P, "theta1a", x)))
+    w4 = P["theta4.weight"].reshape(-1)
+    b4 = P["theta4.bias"]
+    r1 = F.relu(w4 + b4)
+    r0 = F.relu(b4)
+    c = in_degree(edge_index, n).to(dt)
+    z3 = c[:, None] * r1[None, :] + (n_pad_node.to(dt) - c)[:, None] * r0[None, :]
+    s3 = _lin(P, "theta3", z3)
+    mu = torch.zeros(n, p, dtype=dt)
+    zs = []
+    for t in range(T):
+        agg = torch.zeros(n, p, dtype=dt).index_add_(0, edge_index[0], mu[edge_index[1]])
+        z = s1 + _lin(P, "theta2", agg) + s3
+        zs.append(z)
+        mu = z * masks[t].to(dt)
+    return mu, zs
+
+
 def head_sparse(P: dict, mu: torch.Tensor, ptr: torch.Tensor, batch: torch.Tensor, norm_agg: bool = True,
                 names=("theta5", "theta6", "theta7")) -> torch.Tensor:
     t5, t6, t7 = names

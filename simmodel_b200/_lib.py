@@ -45,6 +45,7 @@ SIGNATURES = {
     "s2v_head_grad_floats": (i64, [i32]),
     "s2v_csr_workspace_bytes": (i64, [i64, i64]),
     "s2v_csr_build": (C.c_int, [vp, i64, i64, vp, vp, vp, vp, vp, vp, i64, vp]),
+    "s2v_csr_build_local": (C.c_int, [vp, i32, i64, i64, vp, vp, i32, vp, vp, vp, vp, vp, vp, i64, vp]),
     "s2v_csr_row_to_col": (C.c_int, [vp, i64, i64, vp, vp, vp]),
     "s2v_embed_forward": (C.c_int, [GP, EP, vp, vp, vp, vp]),
     "s2v_embed_backward_workspace_bytes": (i64, [i32, i32]),

@@ -11,10 +11,39 @@
 
 #define SCAN_BLOCK 1024
 
-__global__ void k_csr_count(const int64_t* __restrict__ ei, int64_t E, int64_t n, int32_t* __restrict__ cnt_row,
+// Edge list as the caller holds it: int64 (torch / PyG) or int32 ids, global (batch-wide) or LOCAL to their graph.
+// Local ids come with eptr[B+1] (first edge of every graph) and nptr[B+1] (first node): the node offset of edge e
+// is nptr[g] for the g with eptr[g] <= e < eptr[g+1] (binary search; both arrays are a few KB and stay in L1 / L2).
+// Shipping int32 local ids halves the host-to-device bytes of a batch and needs no offset pass on the host.
+struct EdgeList {
+    const void* ei;          // [2, E]
+    int64_t E;
+    const int32_t* eptr;     // NULL: ids are global
+    const int32_t* nptr;
+    int32_t B;
+    int32_t is32;
+};
+__device__ __forceinline__ int64_t edge_offset(const EdgeList& L, int64_t e) {
+    if (!L.eptr) return 0;
+    int lo = 0, hi = L.B;                       // invariant: eptr[lo] <= e < eptr[hi]
+    while (hi - lo > 1) {
+        const int mid = (lo + hi) >> 1;
+        if ((int64_t)__ldg(L.eptr + mid) <= e) lo = mid; else hi = mid;
+    }
+    return __ldg(L.nptr + lo);
+}
+__device__ __forceinline__ int64_t edge_raw(const EdgeList& L, int which, int64_t e) {
+    return L.is32 ? (int64_t)__ldg((const int32_t*)L.ei + which * L.E + e) : __ldg((const int64_t*)L.ei + which * L.E + e);
+}
+// local ids must also stay inside their own graph: [0, nptr[g+1] - nptr[g]) -- checked through the global range of the
+// batch only (an id past its graph lands in a later graph of the batch; the caller validates per-graph sizes)
+
+__global__ void k_csr_count(EdgeList L, int64_t n, int32_t* __restrict__ cnt_row,
                             int32_t* __restrict__ cnt_col, int32_t* __restrict__ err) {
+    const int64_t E = L.E;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t s = ei[e], d = ei[E + e];
+        const int64_t off = edge_offset(L, e);
+        int64_t s = edge_raw(L, 0, e) + off, d = edge_raw(L, 1, e) + off;
         if (s < 0 || s >= n || d < 0 || d >= n) { atomicExch(err, 1); continue; }
         atomicAdd(cnt_row + s, 1);
         atomicAdd(cnt_col + d, 1);
@@ -96,11 +125,13 @@ k_scan_add(int32_t* __restrict__ out, const int32_t* __restrict__ block_sums, co
     if (i == 0) out[n] = *total;
 }
 
-__global__ void k_csr_fill(const int64_t* __restrict__ ei, int64_t E, int64_t n, const int32_t* __restrict__ rowptr,
+__global__ void k_csr_fill(EdgeList L, int64_t n, const int32_t* __restrict__ rowptr,
                            const int32_t* __restrict__ rowptr_t, int32_t* __restrict__ cur_row,
                            int32_t* __restrict__ cur_col, int32_t* __restrict__ eid_row, int32_t* __restrict__ eid_col) {
+    const int64_t E = L.E;
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
-        int64_t s = ei[e], d = ei[E + e];
+        const int64_t off = edge_offset(L, e);
+        int64_t s = edge_raw(L, 0, e) + off, d = edge_raw(L, 1, e) + off;
         if (s < 0 || s >= n || d < 0 || d >= n) continue;
         eid_row[rowptr[s] + atomicAdd(cur_row + s, 1)] = (int32_t)e;
         eid_col[rowptr_t[d] + atomicAdd(cur_col + d, 1)] = (int32_t)e;
@@ -109,7 +140,7 @@ __global__ void k_csr_fill(const int64_t* __restrict__ ei, int64_t E, int64_t n,
 
 // One thread per row: sort the edge ids of the bucket ascending (restores the input
 // order), then emit the other endpoint.  which = 1: emit ei[1][e] (row form), 0: ei[0][e].
-__global__ void k_csr_sort_emit(const int64_t* __restrict__ ei, int64_t E, int64_t n, const int32_t* __restrict__ ptr,
+__global__ void k_csr_sort_emit(EdgeList L, int64_t n, const int32_t* __restrict__ ptr,
                                 int32_t* __restrict__ eid, int32_t* __restrict__ out, int which) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int beg = ptr[i], end = ptr[i + 1];
@@ -119,8 +150,10 @@ __global__ void k_csr_sort_emit(const int64_t* __restrict__ ei, int64_t E, int64
             while (b >= beg && eid[b] > key) { eid[b + 1] = eid[b]; --b; }
             eid[b + 1] = key;
         }
-        const int64_t* other = ei + (which ? E : 0);
-        for (int a = beg; a < end; ++a) out[a] = (int32_t)other[eid[a]];
+        for (int a = beg; a < end; ++a) {
+            const int64_t e = eid[a];
+            out[a] = (int32_t)(edge_raw(L, which, e) + edge_offset(L, e));
+        }
     }
 }
 
@@ -167,12 +200,13 @@ static int scan_exclusive(const int32_t* in, int32_t* out, int32_t* block_sums, 
     return (int)cudaGetLastError();
 }
 
-extern "C" int s2v_csr_build(const int64_t* edge_index, int64_t E, int64_t n,
-                             int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t, int32_t* indeg,
-                             void* workspace, int64_t workspace_bytes, void* stream) {
+static int csr_build_impl(const EdgeList& L, int64_t n,
+                          int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t, int32_t* indeg,
+                          void* workspace, int64_t workspace_bytes, void* stream) {
+    const int64_t E = L.E;
     if (E < 0 || n < 0 || n >= INT32_MAX || E >= INT32_MAX) return S2V_ERR_BAD_ARG;
     if (!rowptr || !rowptr_t || !workspace || (n > 0 && !indeg)) return S2V_ERR_BAD_ARG;
-    if (E > 0 && (!edge_index || !col || !col_t)) return S2V_ERR_BAD_ARG;
+    if (E > 0 && (!L.ei || !col || !col_t)) return S2V_ERR_BAD_ARG;
     if (workspace_bytes < s2v_csr_workspace_bytes(n, E)) return S2V_ERR_WORKSPACE;
     cudaStream_t st = (cudaStream_t)stream;
     int32_t* w = (int32_t*)workspace;
@@ -192,15 +226,32 @@ extern "C" int s2v_csr_build(const int64_t* edge_index, int64_t E, int64_t n,
     int rb = (int)((n + 127) / 128);
     if (rb > 148 * 32) rb = 148 * 32;
     if (rb < 1) rb = 1;
-    if (E > 0) k_csr_count<<<eb, 256, 0, st>>>(edge_index, E, n, cnt_row, cnt_col, err);
+    if (E > 0) k_csr_count<<<eb, 256, 0, st>>>(L, n, cnt_row, cnt_col, err);
     if (n > 0) S2V_RETURN_IF(cudaMemcpyAsync(indeg, cnt_col, n * 4, cudaMemcpyDeviceToDevice, st));
     S2V_RETURN_IF(scan_exclusive(cnt_row, rowptr, bs_row, totals, n, st));
     S2V_RETURN_IF(scan_exclusive(cnt_col, rowptr_t, bs_col, totals + 1, n, st));
     if (E > 0) {
         S2V_RETURN_IF(cudaMemsetAsync(cnt_row, 0, align_up(n, 64) * 2 * 4, st));
-        k_csr_fill<<<eb, 256, 0, st>>>(edge_index, E, n, rowptr, rowptr_t, cnt_row, cnt_col, eid_row, eid_col);
-        k_csr_sort_emit<<<rb, 128, 0, st>>>(edge_index, E, n, rowptr, eid_row, col, 1);
-        k_csr_sort_emit<<<rb, 128, 0, st>>>(edge_index, E, n, rowptr_t, eid_col, col_t, 0);
+        k_csr_fill<<<eb, 256, 0, st>>>(L, n, rowptr, rowptr_t, cnt_row, cnt_col, eid_row, eid_col);
+        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr, eid_row, col, 1);
+        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr_t, eid_col, col_t, 0);
     }
     return (int)cudaGetLastError();
+}
+
+extern "C" int s2v_csr_build(const int64_t* edge_index, int64_t E, int64_t n,
+                             int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t, int32_t* indeg,
+                             void* workspace, int64_t workspace_bytes, void* stream) {
+    EdgeList L{edge_index, E, nullptr, nullptr, 0, 0};
+    return csr_build_impl(L, n, rowptr, col, rowptr_t, col_t, indeg, workspace, workspace_bytes, stream);
+}
+
+extern "C" int s2v_csr_build_local(const void* edge_index, int32_t index_bytes, int64_t E, int64_t n,
+                                   const int32_t* eptr, const int32_t* nptr, int32_t num_graphs,
+                                   int32_t* rowptr, int32_t* col, int32_t* rowptr_t, int32_t* col_t, int32_t* indeg,
+                                   void* workspace, int64_t workspace_bytes, void* stream) {
+    if (index_bytes != 4 && index_bytes != 8) return S2V_ERR_BAD_ARG;
+    if ((eptr == nullptr) != (nptr == nullptr) || (eptr && num_graphs < 1)) return S2V_ERR_BAD_ARG;
+    EdgeList L{edge_index, E, eptr, nptr, num_graphs, index_bytes == 4};
+    return csr_build_impl(L, n, rowptr, col, rowptr_t, col_t, indeg, workspace, workspace_bytes, stream);
 }

@@ -78,13 +78,17 @@ class GraphLayout:
 
     # ------------------------------------------------------------------
     @staticmethod
-    def build_csr(edge_index: torch.Tensor, n: int, validate: bool = True, edge_map: bool = False):
-        """edge_index int64 [2,E] on the GPU, ids in [0,n) -> (rowptr, col, rowptr_t, col_t, indeg) int32
-        (+ row_to_col int32 [E] when edge_map)."""
+    def build_csr(edge_index: torch.Tensor, n: int, validate: bool = True, edge_map: bool = False,
+                  eptr: torch.Tensor | None = None, nptr: torch.Tensor | None = None):
+        """edge_index int64 or int32 [2,E] on the GPU -> (rowptr, col, rowptr_t, col_t, indeg) int32
+        (+ row_to_col int32 [E] when edge_map).  Ids are global in [0,n), or -- with eptr / nptr (int32 [B+1]: first
+        edge / first node of every graph) -- local to their graph; the offsets are then added on the device."""
         _require_cuda(edge_index, "edge_index")
         if edge_index.dim() != 2 or edge_index.shape[0] != 2:
             raise ValueError("edge_index must have shape [2,E]")
-        ei = edge_index.to(torch.int64).contiguous()
+        if edge_index.dtype not in (torch.int32, torch.int64):
+            edge_index = edge_index.to(torch.int64)
+        ei = edge_index.contiguous()
         E = int(ei.shape[1])
         dev = ei.device
         L = _lib.lib()
@@ -95,8 +99,14 @@ class GraphLayout:
         indeg = torch.empty(n, dtype=torch.int32, device=dev)
         ws = torch.empty(L.s2v_csr_workspace_bytes(n, E), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            _lib.check(L.s2v_csr_build(_p(ei), E, n, _p(rowptr), _p(col), _p(rowptr_t), _p(col_t), _p(indeg),
-                                       _p(ws), ws.numel(), _stream()), "s2v_csr_build")
+            if eptr is None and ei.dtype == torch.int64:
+                _lib.check(L.s2v_csr_build(_p(ei), E, n, _p(rowptr), _p(col), _p(rowptr_t), _p(col_t), _p(indeg),
+                                           _p(ws), ws.numel(), _stream()), "s2v_csr_build")
+            else:
+                nb = 0 if eptr is None else int(eptr.numel() - 1)
+                _lib.check(L.s2v_csr_build_local(_p(ei), ei.element_size(), E, n, _p(eptr), _p(nptr), nb, _p(rowptr), _p(col),
+                                                 _p(rowptr_t), _p(col_t), _p(indeg), _p(ws), ws.numel(), _stream()),
+                           "s2v_csr_build_local")
         _lib.launch_count += 10 if E > 0 else 6
         if validate and int(ws[:4].view(torch.int32).item()) != 0:
             raise ValueError("edge_index contains node ids outside [0, %d)" % n)
@@ -111,9 +121,12 @@ class GraphLayout:
 
     @classmethod
     def from_batch(cls, edge_index: torch.Tensor, ptr: torch.Tensor, n_pad, batch: torch.Tensor | None = None,
-                   validate: bool = True, edge_map: bool = False) -> "GraphLayout":
+                   validate: bool = True, edge_map: bool = False, eptr: torch.Tensor | None = None) -> "GraphLayout":
         """Batched layout from a PyG-style (edge_index, ptr[, batch]) triple.
-        n_pad: int (xv.shape[1] of the reference call) or per-graph tensor."""
+        n_pad: int (xv.shape[1] of the reference call) or per-graph tensor.
+        edge_index may be int64 or int32.  With ``eptr`` ([B+1], first edge of every graph) the ids are LOCAL to
+        their graph (what a replay buffer holds before Batch.from_data_list adds the offsets, comb_opt.py:299,344):
+        the node offsets ptr[g] are added inside the CSR kernels -- half the host-to-device bytes, no host pass."""
         _require_cuda(edge_index, "edge_index")
         dev = edge_index.device
         ptr32 = ptr.to(device=dev, dtype=torch.int32).contiguous()
@@ -126,10 +139,46 @@ class GraphLayout:
             gid = batch.to(device=dev, dtype=torch.int32).contiguous()
         if gid.numel() != n:
             raise ValueError("batch vector length %d != ptr[-1] %d" % (gid.numel(), n))
-        rowptr, col, rowptr_t, col_t, indeg, *r2c = cls.build_csr(edge_index, n, validate, edge_map)
+        eptr32 = None if eptr is None else eptr.to(device=dev, dtype=torch.int32).contiguous()
+        if eptr32 is not None and eptr32.numel() != B + 1:
+            raise ValueError("eptr must have %d entries" % (B + 1))
+        rowptr, col, rowptr_t, col_t, indeg, *r2c = cls.build_csr(edge_index, n, validate, edge_map, eptr32,
+                                                                  ptr32 if eptr32 is not None else None)
         if isinstance(n_pad, torch.Tensor):
             n_pad = n_pad.to(device=dev, dtype=torch.int32).contiguous()
         return cls(n, B, 0, rowptr, col, rowptr_t, col_t, indeg, ptr32, gid, n_pad, r2c[0] if r2c else None)
+
+    @classmethod
+    def from_topologies(cls, topologies, topo_of_graph: torch.Tensor, n_pad=None, validate: bool = True,
+                        edge_map: bool = False) -> "GraphLayout":
+        """Batch described the way a trainer holds it: a table of DISTINCT topologies -- ``topologies[t] =
+        (edge_index_local [2,E_t] int32|int64 on the GPU, num_nodes_t)`` -- and ``topo_of_graph`` ([B] ints, host or
+        device) naming the topology of every graph.  A replay batch drawn from one world (the reference's DQN / PPO
+        training on a single map, comb_opt.py:342: Ws of identical graphs) ships its 2 850 edges once instead of
+        B times: one topology -> replicated layout (period = num_nodes, no per-graph edge list at all); several ->
+        the batched edge list is expanded on the device and goes through the same CSR builder as from_batch."""
+        if len(topologies) == 0:
+            raise ValueError("no topology given")
+        B = int(topo_of_graph.numel())
+        if len(topologies) == 1:
+            ei, n = topologies[0]
+            return cls.replicated(ei, int(n), B, n_pad, validate, edge_map)
+        dev = topologies[0][0].device
+        tog = topo_of_graph.to(device=dev, dtype=torch.int64)
+        n_t = torch.tensor([int(n) for _, n in topologies], device=dev, dtype=torch.int64)
+        e_t = torch.tensor([int(ei.shape[1]) for ei, _ in topologies], device=dev, dtype=torch.int64)
+        eoff_t = torch.cumsum(e_t, 0) - e_t
+        ei_cat = torch.cat([ei.to(torch.int32) for ei, _ in topologies], dim=1)
+        ptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+        ptr[1:] = torch.cumsum(n_t[tog], 0)
+        eptr = torch.zeros(B + 1, dtype=torch.int64, device=dev)
+        eptr[1:] = torch.cumsum(e_t[tog], 0)
+        goe = torch.repeat_interleave(torch.arange(B, device=dev), e_t[tog])
+        src = eoff_t[tog][goe] + (torch.arange(int(eptr[-1]), device=dev) - eptr[:-1][goe])
+        ei_local = ei_cat[:, src].contiguous()                       # int32, graph-local ids
+        if n_pad is None:
+            n_pad = int(n_t.max())
+        return cls.from_batch(ei_local, ptr, n_pad, validate=validate, edge_map=edge_map, eptr=eptr)
 
     @classmethod
     def replicated(cls, edge_index: torch.Tensor, num_nodes: int, copies: int, n_pad=None,

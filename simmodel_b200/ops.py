@@ -69,13 +69,13 @@ def _embed_forward(layout, T, x, w):
     return base, mus
 
 
-def _embed_backward(layout, T, x, w, base, mus, dmu, dmu_masked, dus=None):
+def _embed_backward(layout, T, x, w, base, mus, dmu, dmu_masked, dus=None, grad_out=None):
     L = _lib.lib()
     n, P, F = layout.num_nodes, int(w[0].shape[0]), int(w[0].shape[1])
     if dus is None:
         dus = torch.empty(T, n, P, dtype=torch.float32, device=x.device)
     ws = torch.empty(L.s2v_embed_backward_workspace_bytes(F, P), dtype=torch.uint8, device=x.device)
-    grad = torch.empty(L.s2v_embed_grad_floats(F, P), dtype=torch.float32, device=x.device)
+    grad = grad_out if grad_out is not None else torch.empty(L.s2v_embed_grad_floats(F, P), dtype=torch.float32, device=x.device)
     prm = _embed_struct(T, w)
     with torch.cuda.device(x.device):
         _lib.check(L.s2v_embed_backward(C.byref(layout.c_struct()), C.byref(prm), _p(x), _p(base), _p(mus), _p(dmu),
@@ -99,13 +99,13 @@ def _head_forward(layout, norm_agg, mu, w):
     return pool, gstate, q
 
 
-def _head_backward(layout, norm_agg, mu, w, pool, gstate, dq, mask_relu, dmu_out=None):
+def _head_backward(layout, norm_agg, mu, w, pool, gstate, dq, mask_relu, dmu_out=None, grad_out=None):
     L = _lib.lib()
     n, B, P = layout.num_nodes, layout.num_graphs, int(w[2].shape[0])
     if dmu_out is None:
         dmu_out = torch.empty(n, P, dtype=torch.float32, device=mu.device)
     ws = torch.empty(L.s2v_head_backward_workspace_bytes(P, B), dtype=torch.uint8, device=mu.device)
-    grad = torch.empty(L.s2v_head_grad_floats(P), dtype=torch.float32, device=mu.device)
+    grad = grad_out if grad_out is not None else torch.empty(L.s2v_head_grad_floats(P), dtype=torch.float32, device=mu.device)
     prm = _head_struct(norm_agg, w)
     with torch.cuda.device(mu.device):
         _lib.check(L.s2v_head_backward(C.byref(layout.c_struct()), C.byref(prm), _p(mu), _p(pool), _p(gstate), _p(dq),
@@ -169,9 +169,14 @@ class _QNetFn(torch.autograd.Function):
         T, layout = ctx.T, ctx.layout
         n, P = layout.num_nodes, int(w[0].shape[0])
         dus = torch.empty(T, n, P, dtype=torch.float32, device=x.device)
+        # ONE flat gradient buffer [embed | head] in QNet.parameters() order: the 16 .grad tensors autograd hands to the
+        # parameters are views of it, so a data-parallel step all-reduces this buffer in place (dist.allreduce_gradients)
+        L = _lib.lib()
+        ne, nh = int(L.s2v_embed_grad_floats(int(w[0].shape[1]), P)), int(L.s2v_head_grad_floats(P))
+        flat = torch.empty(ne + nh, dtype=torch.float32, device=x.device)
         _, hgrads, _ = _head_backward(layout, ctx.norm_agg, mus[T - 1], w[10:], pool, gstate, _f32c(dq, "dq"), True,
-                                      dmu_out=dus[T - 1])
-        egrads, _ = _embed_backward(layout, T, x, w[:10], base, mus, dus[T - 1], True, dus=dus)
+                                      dmu_out=dus[T - 1], grad_out=flat[ne:])
+        egrads, _ = _embed_backward(layout, T, x, w[:10], base, mus, dus[T - 1], True, dus=dus, grad_out=flat[:ne])
         return (None, None, None, None, *egrads, *hgrads)
 
 

@@ -13,8 +13,11 @@ import torch
 
 from conftest import golden_cases, load_golden
 
+import os
+
 pytestmark = pytest.mark.gpu
 TOL = 1e-5
+REPORT = bool(os.environ.get("S2V_TEST_REPORT"))     # pytest -s: print every measured error next to its bound
 
 
 def _scale(a):
@@ -33,9 +36,13 @@ def _check(name, new, ref, ref64=None, tol=TOL, abs_floor=0.0):
         own = float(np.abs(ref - ref64).max()) / _scale(ref64)
         bound = max(tol, 2.0 * own)
         err = float(np.abs(new - ref64).max()) / _scale(ref64)
+        if REPORT:
+            print("    [parity] %-28s err vs fp64 %.2e  (fp32 reference's own %.2e, bound %.1e)" % (name, err, own, bound))
         if err <= bound:
             return err
     err = float(np.abs(new - ref).max()) / _scale(ref)
+    if REPORT and ref64 is None:
+        print("    [parity] %-28s err vs fp32 reference %.2e (bound %.1e)" % (name, err, bound))
     assert err <= bound, "%s: rel-to-scale error %.3e > %.1e" % (name, err, bound)
     return err
 
@@ -380,16 +387,19 @@ def test_random_small_graphs_vs_dense_oracle(seed, cuda_device):
     q_ref = R.qnet_forward_dense(Pg, xv, Ws, batch.ptr, batch.batch, T, norm_agg).reshape(-1)
     w = torch.from_numpy(rng.standard_normal(int(batch.ptr[-1])).astype(np.float32))
     (q_ref * w).sum().backward()
+    P64 = {k: v.double().requires_grad_(True) for k, v in P.items()}       # fp64 adjudicator of the same arithmetic
+    q64 = R.qnet_forward_dense(P64, xv.double(), Ws.double(), batch.ptr, batch.batch, T, norm_agg).reshape(-1)
+    (q64 * w.double()).sum().backward()
     dev = cuda_device
     net = sb.QNet({"emb_dim": p, "emb_iter_T": T, "norm_agg": norm_agg, "node_dim": sb.graphs.NODE_DIM}, verbose=False)
     net.load_state_dict(P)
     net = net.to(dev)
     pyg = sb.Batch(batch.ptr, batch.batch, batch.edge_index)
     q = net(xv, Ws, pyg).reshape(-1)
-    _check("q", q.detach().cpu().numpy(), q_ref.detach().numpy())
+    _check("q", q.detach().cpu().numpy(), q_ref.detach().numpy(), q64.detach().numpy())
     (q * w.to(dev)).sum().backward()
     for k, prm in net.named_parameters():
-        _check("grad " + k, prm.grad.cpu().numpy(), Pg[k].grad.numpy(), tol=2e-5)
+        _check("grad " + k, prm.grad.cpu().numpy(), Pg[k].grad.numpy(), P64[k].grad.numpy())
 
 
 @pytest.mark.parametrize("path", ["ffma", "tcws"])
@@ -412,15 +422,18 @@ def test_node_dim_variants_vs_sparse_oracle(node_dim, path, cuda_device, monkeyp
     q_ref = R.qnet_forward_sparse(Pg, x, ei, ptr, topo.num_nodes, T, True)
     w = torch.randn(q_ref.numel(), generator=gen)
     (q_ref * w).sum().backward()
+    P64 = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    q64 = R.qnet_forward_sparse(P64, x.double(), ei, ptr, topo.num_nodes, T, True)
+    (q64 * w.double()).sum().backward()
     net = sb.QNet({"emb_dim": 64, "emb_iter_T": T, "norm_agg": True, "node_dim": node_dim}, verbose=False)
     net.load_state_dict(P)
     net = net.to(dev)
     layout = sb.GraphLayout.from_batch(ei.to(dev), ptr.to(dev), topo.num_nodes)
     q = net.forward_graph(x.to(dev), layout)
     (q * w.to(dev)).sum().backward()
-    _check("q", q.detach().cpu().numpy(), q_ref.detach().numpy())
+    _check("q", q.detach().cpu().numpy(), q_ref.detach().numpy(), q64.detach().numpy())
     for (k, prm) in net.named_parameters():
-        _check("grad " + k, prm.grad.cpu().numpy(), Pg[k].grad.numpy(), tol=2e-5)
+        _check("grad " + k, prm.grad.cpu().numpy(), Pg[k].grad.numpy(), P64[k].grad.numpy())
 
 
 @pytest.mark.parametrize("topo_name,B", [("NWB_AMS", 32), ("NWB_ROT", 8), ("NWB_UTR", 5)])
@@ -441,6 +454,9 @@ def test_real_topologies_vs_sparse_oracle(topo_name, B, cuda_device):
     actions = torch.randint(0, topo.num_nodes, (B,), generator=gen)
     targets = torch.randn(B, generator=gen)
     R.dqn_loss(q_ref, actions, ptr, targets).backward()
+    P64 = {k: v.double().requires_grad_(True) for k, v in P.items()}
+    q64 = R.qnet_forward_sparse(P64, x.double(), ei, ptr, topo.num_nodes, 5, True)
+    R.dqn_loss(q64, actions, ptr, targets.double()).backward()
     net = sb.QNet({"emb_dim": 64, "emb_iter_T": 5, "norm_agg": True, "node_dim": sb.graphs.NODE_DIM}, verbose=False)
     net.load_state_dict(P)
     net = net.to(dev)
@@ -454,9 +470,9 @@ def test_real_topologies_vs_sparse_oracle(topo_name, B, cuda_device):
         outs.append([q.detach().clone()] + [p_.grad.clone() for p_ in net.parameters()])
     for a, b in zip(*outs):
         assert torch.equal(a, b), "results must be run-to-run bit-stable (atomics-free reductions)"
-    _check("q", outs[0][0].cpu().numpy(), q_ref.detach().numpy())
+    _check("q", outs[0][0].cpu().numpy(), q_ref.detach().numpy(), q64.detach().numpy())
     for (k, prm) in net.named_parameters():
-        _check("grad " + k, prm.grad.cpu().numpy(), Pg[k].grad.numpy(), tol=2e-5)
+        _check("grad " + k, prm.grad.cpu().numpy(), Pg[k].grad.numpy(), P64[k].grad.numpy())
     # replicated layout (shared topology) must give bit-identical results to the batched one
     lay_r = sb.GraphLayout.replicated(topo.edge_index.to(dev), topo.num_nodes, B)
     q_r = net.forward_graph(x.to(dev), lay_r)
