@@ -185,6 +185,21 @@ int s2v_debug_tc_gemm(int32_t mode, const float* A, const float* B, float* out, 
 int s2v_head_forward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu,
                      float* pool, float* gstate, float* q, void* stream);
 
+/* The same head with the invalid-action mask and the per-graph reduction in ONE launch (one CTA per graph: pool,
+ * theta6, the graph's q rows, then the masked reduction over them).  Outputs pool / gstate / q as s2v_head_forward, plus
+ *   mode 0: nothing else (QNet.forward, comb_opt.py:248-273)
+ *   mode 1: prob [num_nodes] = softmax of q over mask != 0, masked entries exactly 0 (models_basic_lstm.py:530-540)
+ *   mode 2: arg_out [B] (local node id, -1 if the mask is empty), val_out [B] = masked max (models_basic_lstm.py:548-564)
+ *   mode 3: arg_out [B] = position in the neighbour list, node_out [B], val_out [B] (comb_opt.py:319-326)
+ * Bit-identical to s2v_head_forward followed by the s2v_masked_* / s2v_list_argmax call whenever
+ * s2v_head_fused_eligible() is 1 (the problem runs the CUDA-core head: emb_dim != 64, flags == 1, or fewer than 4096
+ * rows); for large batches the tcgen05 head + separate reduction is faster and launches do not matter. */
+int s2v_head_fused_forward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu, int32_t mode,
+                           const uint8_t* mask, const int32_t* reach_ptr, const int32_t* reach_idx,
+                           float* pool, float* gstate, float* q, float* prob, int64_t* arg_out, int64_t* node_out,
+                           float* val_out, void* stream);
+int s2v_head_fused_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes);
+
 /* Head backward.  dq [num_nodes]; dmu [num_nodes,p] out (multiplied by [mu>0] when
  * mask_relu != 0, i.e. it is du^T); per_graph [B, 2p+4] workspace;
  * grad [s2v_head_grad_floats] out, overwritten. */

@@ -5,6 +5,7 @@
 //   G_g    = theta6 pool_g + b6 ;  L_i = theta7 mu_i + b7
 //   q_i    = w5[:p] . relu(G_g(i)) + w5[p:] . relu(L_i) + b5
 #include "s2v_common.cuh"
+#include "s2v_reduce.cuh"
 
 // ------------------------------------------------------------------------------------
 // pooling: one CTA per graph, fixed summation order
@@ -133,6 +134,141 @@ k_head(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const
             float s = b5;
             for (int k = 0; k < C::TXP; ++k) s += red[t * C::TXP + k];
             q[row0 + t] = s;
+        }
+        __syncthreads();
+    }
+}
+
+// ------------------------------------------------------------------------------------
+// fused head: pool -> theta6 -> tile head -> invalid-action mask + per-graph reduction, ONE launch.
+// One CTA per graph (persistent over graphs).  The three phases are the bodies of k_pool, k_head and the mask kernels
+// (s2v_mask.cu) run back to back by the same 128 threads with the same thread mapping and summation orders, so every
+// output is bit-identical to the three-launch sequence pool / head / mask on the CUDA-core path; q stays in L1/L2
+// between the phases.  Used where launches are the cost (acting, small batches, the per-rollout PPO call pattern):
+//   mode 0  q only                                  QNet.forward                        comb_opt.py:248-273
+//   mode 1  prob = softmax(q | reachable)           PPO pi                              models_basic_lstm.py:530-540
+//   mode 2  (max, argmax) of q over reachable       PPO v (critic q), greedy evaluation models_basic_lstm.py:548-564
+//   mode 3  argmax over a neighbour list            DQN greedy action                   comb_opt.py:319-326
+// ------------------------------------------------------------------------------------
+template <int P>
+__global__ void __launch_bounds__(S2V_THREADS)
+k_head_fused(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, int mode,
+             const uint8_t* __restrict__ mask, const int32_t* __restrict__ reach_ptr, const int32_t* __restrict__ reach_idx,
+             float* __restrict__ pool, float* __restrict__ gstate, float* q, float* __restrict__ prob,
+             int64_t* __restrict__ arg_out, int64_t* __restrict__ node_out, float* __restrict__ val_out) {
+    using C = Cfg<P>;
+    static_assert(S2V_THREADS == MK_THREADS, "the fused kernel runs the mask reductions with their own thread count");
+    extern __shared__ __align__(16) float smem[];
+    float* Wt7 = smem;                        // Wt[k][n] = theta7[n][k]
+    float* As = Wt7 + C::W_FLOATS;            // mu tile
+    float* red = As + C::TILE_FLOATS;         // [TM][TXP]
+    float* vec = red + S2V_TM * C::TXP;       // b7, w5a, w5b
+    float* scratch = vec + 3 * P;             // [RG][P] pooling partials
+    float* pool_s = scratch + C::RG * P;      // [P]
+    float* g_s = pool_s + P;                  // [P] theta6 pool + b6
+    __shared__ ArgPair sh_arg[MK_THREADS / 32];
+    __shared__ float sh_f[MK_THREADS / 32];
+    float* b7 = vec, *w5a = vec + P, *w5b = vec + 2 * P;
+    const int t = threadIdx.x;
+    const int tx = t % C::TXP, ty = t / C::TXP;
+    const bool active = t < C::ACTIVE;
+    load_w_transposed<P>(Wt7, prm.theta7_w);
+    if (t < P) {
+        b7[t] = __ldg(prm.theta7_b + t);
+        w5a[t] = __ldg(prm.theta5_w + t);
+        w5b[t] = __ldg(prm.theta5_w + P + t);
+    }
+    const float b5 = __ldg(prm.theta5_b);
+    __syncthreads();
+    for (int gi = blockIdx.x; gi < g.num_graphs; gi += gridDim.x) {
+        int lo, hi;
+        graph_range(g, gi, lo, hi);
+        const int n = hi - lo;
+        // ---- phase 1: pool + theta6 (k_pool) ----
+        pool_graph<P>(mu, lo, hi, scratch, pool_s, 1.f);
+        if (t < P) {
+            float pv = prm.norm_agg ? pool_s[t] / (float)(n > 1 ? n : 1) : pool_s[t];
+            pool_s[t] = pv;
+            pool[(size_t)gi * P + t] = pv;
+        }
+        __syncthreads();
+        if (t < P) {
+            float a = __ldg(prm.theta6_b + t);
+            for (int k = 0; k < P; ++k) a = fmaf(__ldg(prm.theta6_w + t * P + k), pool_s[k], a);
+            g_s[t] = a;
+            gstate[(size_t)gi * P + t] = a;
+        }
+        __syncthreads();
+        // ---- phase 2: q of the graph's rows, 64 at a time (k_head) ----
+        for (int row0 = lo; row0 < hi; row0 += S2V_TM) {
+            const int rows = min(S2V_TM, hi - row0);
+            load_tile<P>(As, mu + (size_t)row0 * P, rows);
+            __syncthreads();
+            if (active) {
+                float acc[C::NR][4];
+#pragma unroll
+                for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+                tile_gemm<P>(As, Wt7, acc, tx, ty);
+                const float4 bb = ld4(b7 + 4 * tx), wa = ld4(w5a + 4 * tx), wb = ld4(w5b + 4 * tx), G = ld4(g_s + 4 * tx);
+#pragma unroll
+                for (int i = 0; i < C::NR; ++i) {
+                    int rl = ty + C::RG * i;
+                    if (rl >= S2V_TM) continue;
+                    float sacc = 0.f;
+                    if (rl < rows) {
+                        sacc = fmaf(wa.x, relu(G.x), sacc); sacc = fmaf(wa.y, relu(G.y), sacc);
+                        sacc = fmaf(wa.z, relu(G.z), sacc); sacc = fmaf(wa.w, relu(G.w), sacc);
+                        sacc = fmaf(wb.x, relu(acc[i][0] + bb.x), sacc); sacc = fmaf(wb.y, relu(acc[i][1] + bb.y), sacc);
+                        sacc = fmaf(wb.z, relu(acc[i][2] + bb.z), sacc); sacc = fmaf(wb.w, relu(acc[i][3] + bb.w), sacc);
+                    }
+                    red[rl * C::TXP + tx] = sacc;
+                }
+            }
+            __syncthreads();
+            if (t < rows) {
+                float sacc = b5;
+                for (int k = 0; k < C::TXP; ++k) sacc += red[t * C::TXP + k];
+                q[row0 + t] = sacc;
+            }
+            __syncthreads();                   // also orders the q stores of this CTA before the reads of phase 3
+        }
+        // ---- phase 3: invalid-action mask + per-graph reduction (s2v_mask.cu) ----
+        if (mode == 1) {
+            float m = -CUDART_INF_F;
+            for (int r = lo + t; r < hi; r += MK_THREADS)
+                if (mask[r]) m = fmaxf(m, q[r]);
+            m = block_max(m, sh_f);
+            float ssum = 0.f;
+            for (int r = lo + t; r < hi; r += MK_THREADS)
+                if (mask[r]) ssum += expf(q[r] - m);
+            ssum = block_sum(ssum, sh_f);
+            for (int r = lo + t; r < hi; r += MK_THREADS) {
+                float v = mask[r] ? expf(q[r] - m) / ssum : 0.f;
+                if (m == -CUDART_INF_F) v = CUDART_NAN_F;
+                prob[r] = v;
+            }
+        } else if (mode == 2) {
+            ArgPair p; p.v = -CUDART_INF_F; p.i = -1;
+            for (int r = lo + t; r < hi; r += MK_THREADS)
+                if (mask[r]) { ArgPair c; c.v = q[r]; c.i = r - lo; p = better(p, c); }
+            p = block_argmax(p, sh_arg);
+            if (t == 0) {
+                arg_out[gi] = p.i;
+                val_out[gi] = p.i >= 0 ? p.v : -CUDART_INF_F;
+            }
+        } else if (mode == 3) {
+            const int beg = reach_ptr[gi], end = reach_ptr[gi + 1];
+            ArgPair p; p.v = -CUDART_INF_F; p.i = -1;
+            for (int k = beg + t; k < end; k += MK_THREADS) {
+                ArgPair c; c.v = q[lo + reach_idx[k]]; c.i = k - beg;
+                p = better(p, c);
+            }
+            p = block_argmax(p, sh_arg);
+            if (t == 0) {
+                arg_out[gi] = p.i;
+                node_out[gi] = p.i >= 0 ? (int64_t)reach_idx[beg + p.i] : -1;
+                val_out[gi] = p.i >= 0 ? p.v : -CUDART_INF_F;
+            }
         }
         __syncthreads();
     }
@@ -662,6 +798,38 @@ extern "C" int s2v_head_backward(const s2v_graph_t* g, const s2v_head_params_t* 
     S2V_DISPATCH_P(prm->emb_dim, return head_backward_impl<PP>(*g, *prm, mu, pool, gstate, dq, mask_relu, dmu,
                                                                 (float*)workspace, grad, st));
     return 0;
+}
+
+extern "C" int s2v_head_fused_forward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu, int32_t mode,
+                                      const uint8_t* mask, const int32_t* reach_ptr, const int32_t* reach_idx,
+                                      float* pool, float* gstate, float* q, float* prob, int64_t* arg_out, int64_t* node_out,
+                                      float* val_out, void* stream) {
+    S2V_RETURN_IF(check_graph_h(g));
+    if (!prm || !mu || !pool || !gstate || !q || mode < 0 || mode > 3) return S2V_ERR_BAD_ARG;
+    if (mode == 1 && (!mask || !prob)) return S2V_ERR_BAD_ARG;
+    if (mode == 2 && (!mask || !arg_out || !val_out)) return S2V_ERR_BAD_ARG;
+    if (mode == 3 && (!reach_ptr || !arg_out || !node_out || !val_out)) return S2V_ERR_BAD_ARG;
+    if (g->num_graphs == 0) return 0;
+    cudaStream_t st = (cudaStream_t)stream;
+#define S2V_HEAD_FUSED_LAUNCH(P_)                                                                                          \
+    {                                                                                                                      \
+        using C = Cfg<P_>;                                                                                                 \
+        const int smem = (C::W_FLOATS + C::TILE_FLOATS + S2V_TM * C::TXP + 3 * P_ + C::RG * P_ + 2 * P_) * 4;             \
+        S2V_RETURN_IF(cudaFuncSetAttribute(k_head_fused<P_>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));          \
+        const int grid = s2v_persistent_grid((const void*)k_head_fused<P_>, smem, g->num_graphs);                          \
+        k_head_fused<P_><<<grid, S2V_THREADS, smem, st>>>(*g, *prm, mu, mode, mask, reach_ptr, reach_idx, pool, gstate, q,   \
+                                                         prob, arg_out, node_out, val_out);                                \
+        return (int)cudaGetLastError();                                                                                    \
+    }
+    S2V_DISPATCH_P(prm->emb_dim, S2V_HEAD_FUSED_LAUNCH(PP));
+#undef S2V_HEAD_FUSED_LAUNCH
+    return 0;
+}
+
+/* 1 when s2v_head_forward would run the CUDA-core tile kernel for this problem (the fused launch is then bit-identical
+ * to pool / head / mask), 0 when it would pick the tcgen05 head (large batches: keep the three launches). */
+extern "C" int s2v_head_fused_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes) {
+    return head_tensor_path(emb_dim, flags, (int)(num_nodes > 0x7fffffff ? 0x7fffffff : num_nodes)) ? 0 : 1;
 }
 
 extern "C" int s2v_pool_forward(const s2v_graph_t* g, int32_t P, int32_t norm_agg, const float* mu, float* pool, void* stream) {

@@ -294,18 +294,25 @@ class QNet_GATv2(nn.Module):
         """x f32[sum N, F], GAT layout (self loops stripped) -> q f32[sum N]."""
         if self.device.type != "cuda":
             raise S2VError("simmodel_b200.QNet_GATv2 runs on CUDA only: call .to('cuda') first (no CPU fallback)")
-        mu = self.gat.forward_layout(x, layout)
-        return ops.s2v_head(layout, mu, self.head_weights(), self.norm_agg)
+        return ops.s2v_head(layout, self.embed_graph(x, layout), self.head_weights(), self.norm_agg)
+
+    def embed_graph(self, x, layout: GraphLayout):
+        return self.gat.forward_layout(x, layout)
 
     def forward(self, xv, Ws, pyg_data):
         """Reference contract: xv and Ws are ignored (comb_opt.py:84-94 reads pyg_data.x / .edge_index / .ptr /
         .batch only); returns q over all nodes of the batch, squeezed."""
+        x, layout = self.prepare(xv, Ws, pyg_data)
+        return self.forward_graph(x, layout).squeeze()
+
+    def prepare(self, xv, Ws, pyg_data):
+        """The reference call's arguments -> (x f32[sum N, F], GAT layout)."""
         dev = self.device
         if dev.type != "cuda":
             raise S2VError("simmodel_b200.QNet_GATv2 runs on CUDA only: call .to('cuda') first (no CPU fallback)")
         x = pyg_data.x.to(dev, torch.float32).contiguous()
         layout = gat_layout_from_batch(pyg_data.edge_index.to(dev), pyg_data.ptr.to(dev), pyg_data.batch.to(dev))
-        return self.forward_graph(x, layout).squeeze()
+        return x, layout
 
     def numTrainableParameters(self, verbose=True):
         total = 0

@@ -99,6 +99,36 @@ def _head_forward(layout, norm_agg, mu, w):
     return pool, gstate, q
 
 
+def head_fused_eligible(layout, w) -> bool:
+    """True when the fused head launch (pool + head + mask + reduction, csrc/s2v_head.cu:k_head_fused) computes the
+    same bits as the three-launch sequence: the problem runs the CUDA-core head (small batches, acting)."""
+    return bool(_lib.lib().s2v_head_fused_eligible(int(w[2].shape[0]), _lib.path_flag(), layout.num_nodes))
+
+
+_FUSED_MODES = {"q": 0, "softmax": 1, "max": 2, "list": 3}
+
+
+def _head_fused_forward(layout, norm_agg, mu, w, mode, mask_u8=None, reach_ptr=None, reach_idx=None):
+    """ONE launch: pool, gstate, q and -- per mode -- prob | (arg, val) | (pos, node, val)."""
+    L = _lib.lib()
+    n, B, P = layout.num_nodes, layout.num_graphs, int(w[2].shape[0])
+    dev = mu.device
+    pool = torch.empty(B, P, dtype=torch.float32, device=dev)
+    gstate = torch.empty(B, P, dtype=torch.float32, device=dev)
+    q = torch.empty(n, dtype=torch.float32, device=dev)
+    prob = torch.empty(n, dtype=torch.float32, device=dev) if mode == "softmax" else None
+    arg = torch.empty(B, dtype=torch.int64, device=dev) if mode in ("max", "list") else None
+    node = torch.empty(B, dtype=torch.int64, device=dev) if mode == "list" else None
+    val = torch.empty(B, dtype=torch.float32, device=dev) if mode in ("max", "list") else None
+    prm = _head_struct(norm_agg, w)
+    with torch.cuda.device(dev):
+        _lib.check(L.s2v_head_fused_forward(C.byref(layout.c_struct()), C.byref(prm), _p(mu), _FUSED_MODES[mode], _p(mask_u8),
+                                            _p(reach_ptr), _p(reach_idx), _p(pool), _p(gstate), _p(q), _p(prob), _p(arg),
+                                            _p(node), _p(val), _stream()), "s2v_head_fused_forward")
+    _lib.launch_count += 1
+    return pool, gstate, q, prob, arg, node, val
+
+
 def _head_backward(layout, norm_agg, mu, w, pool, gstate, dq, mask_relu, dmu_out=None, grad_out=None):
     L = _lib.lib()
     n, B, P = layout.num_nodes, layout.num_graphs, int(w[2].shape[0])
@@ -158,7 +188,10 @@ class _QNetFn(torch.autograd.Function):
         w = [_f32c(t.detach(), "parameter") for t in w]
         x = _f32c(x, "x")
         base, mus = _embed_forward(layout, T, x, w[:10])
-        pool, gstate, q = _head_forward(layout, norm_agg, mus[T - 1], w[10:])
+        if head_fused_eligible(layout, w[10:]):
+            pool, gstate, q = _head_fused_forward(layout, norm_agg, mus[T - 1], w[10:], "q")[:3]
+        else:
+            pool, gstate, q = _head_forward(layout, norm_agg, mus[T - 1], w[10:])
         ctx.layout, ctx.T, ctx.norm_agg = layout, T, norm_agg
         ctx.save_for_backward(x, base, mus, pool, gstate, *w)
         return q
@@ -278,6 +311,75 @@ class _MaskedMaxFn(torch.autograd.Function):
         return None, dq, None
 
 
+class _HeadSoftmaxFn(torch.autograd.Function):
+    """logits = head(mu); prob = softmax(logits | mask) -- one launch forward when the fused kernel applies
+    (models_basic_lstm.py:530-540).  Backward: masked-softmax backward, then the head backward."""
+
+    @staticmethod
+    def forward(ctx, layout, norm_agg, mask_u8, mu, *w):
+        w = [_f32c(t.detach(), "parameter") for t in w]
+        mu = _f32c(mu, "mu")
+        if head_fused_eligible(layout, w):
+            pool, gstate, _, prob = _head_fused_forward(layout, norm_agg, mu, w, "softmax", mask_u8)[:4]
+        else:
+            pool, gstate, q = _head_forward(layout, norm_agg, mu, w)
+            prob = _MaskedSoftmaxFn.forward(_Ctx(), layout, q, mask_u8)
+        ctx.layout, ctx.norm_agg = layout, norm_agg
+        ctx.save_for_backward(mu, pool, gstate, prob, *w)
+        return prob
+
+    @staticmethod
+    def backward(ctx, dprob):
+        L = _lib.lib()
+        mu, pool, gstate, prob, *w = ctx.saved_tensors
+        dprob = _f32c(dprob, "dprob")
+        dq = torch.empty_like(prob)
+        with torch.cuda.device(prob.device):
+            _lib.check(L.s2v_masked_softmax_backward(C.byref(ctx.layout.c_struct()), _p(prob), _p(dprob), _p(dq), _stream()),
+                       "s2v_masked_softmax_backward")
+        _lib.launch_count += 1
+        dmu, grads, _ = _head_backward(ctx.layout, ctx.norm_agg, mu, w, pool, gstate, dq, False)
+        return (None, None, None, dmu, *grads)
+
+
+class _HeadMaxFn(torch.autograd.Function):
+    """(max, argmax) of head(mu) over the reachable nodes of every graph (models_basic_lstm.py:548-564)."""
+
+    @staticmethod
+    def forward(ctx, layout, norm_agg, mask_u8, mu, *w):
+        w = [_f32c(t.detach(), "parameter") for t in w]
+        mu = _f32c(mu, "mu")
+        if head_fused_eligible(layout, w):
+            pool, gstate, _, _, arg, _, val = _head_fused_forward(layout, norm_agg, mu, w, "max", mask_u8)
+        else:
+            pool, gstate, q = _head_forward(layout, norm_agg, mu, w)
+            arg, val = _masked_argmax_raw(layout, q, mask_u8)
+        ctx.layout, ctx.norm_agg = layout, norm_agg
+        ctx.save_for_backward(mu, pool, gstate, arg, *w)
+        ctx.mark_non_differentiable(arg)
+        return val, arg
+
+    @staticmethod
+    def backward(ctx, dval, _darg):
+        L = _lib.lib()
+        mu, pool, gstate, arg, *w = ctx.saved_tensors
+        dval = _f32c(dval, "dval")
+        dq = torch.empty(ctx.layout.num_nodes, dtype=torch.float32, device=dval.device)
+        with torch.cuda.device(dval.device):
+            _lib.check(L.s2v_scatter_rows(C.byref(ctx.layout.c_struct()), _p(arg), _p(dval), _p(dq), _stream()),
+                       "s2v_scatter_rows")
+        _lib.launch_count += 1
+        dmu, grads, _ = _head_backward(ctx.layout, ctx.norm_agg, mu, w, pool, gstate, dq, False)
+        return (None, None, None, dmu, *grads)
+
+
+class _Ctx:
+    """Stand-in context for calling an autograd.Function's forward as a plain function."""
+
+    def save_for_backward(self, *a):
+        pass
+
+
 # ----------------------------------------------------------------------------------
 # public functional API (the native contract of SURVEY.md §8b)
 # ----------------------------------------------------------------------------------
@@ -340,3 +442,48 @@ def list_argmax(layout: GraphLayout, q: torch.Tensor, reach_ptr: torch.Tensor, r
                                      _p(val), _stream()), "s2v_list_argmax")
     _lib.launch_count += 1
     return pos, node, val
+
+
+def s2v_head_softmax(layout: GraphLayout, mu: torch.Tensor, head_weights, mask: torch.Tensor, norm_agg: bool = True):
+    """prob [num_nodes] = softmax over the reachable nodes of every graph of the logit head (PPO pi,
+    models_basic_lstm.py:530-540): head, invalid-action mask and the per-graph reduction in one launch where launches
+    are the cost (csrc/s2v_head.cu:k_head_fused), head + mask kernels for large batches."""
+    return _HeadSoftmaxFn.apply(layout, bool(norm_agg), _mask_u8(mask, layout.num_nodes), mu, *head_weights)
+
+
+def s2v_head_max(layout: GraphLayout, mu: torch.Tensor, head_weights, mask: torch.Tensor, norm_agg: bool = True):
+    """(max value [B], local argmax node [B]) of the Q head over the reachable nodes (PPO critic 'q',
+    models_basic_lstm.py:548-564); differentiable in the value."""
+    return _HeadMaxFn.apply(layout, bool(norm_agg), _mask_u8(mask, layout.num_nodes), mu, *head_weights)
+
+
+@torch.no_grad()
+def s2v_head_argmax(layout: GraphLayout, mu: torch.Tensor, head_weights, mask: torch.Tensor, norm_agg: bool = True):
+    """Greedy evaluation (rl_policy.py:533-536): (local argmax node [B], value [B]); softmax is monotone, so the
+    arg-max of the logits is the arg-max of the probabilities."""
+    w = [_f32c(t.detach(), "parameter") for t in head_weights]
+    mu = _f32c(mu, "mu")
+    m8 = _mask_u8(mask, layout.num_nodes)
+    if head_fused_eligible(layout, w):
+        _, _, _, _, arg, _, val = _head_fused_forward(layout, bool(norm_agg), mu, w, "max", m8)
+        return arg, val
+    _, _, q = _head_forward(layout, bool(norm_agg), mu, w)
+    return _masked_argmax_raw(layout, q, m8)
+
+
+@torch.no_grad()
+def s2v_head_list_argmax(layout: GraphLayout, mu: torch.Tensor, head_weights, reach_ptr: torch.Tensor,
+                         reach_idx: torch.Tensor, norm_agg: bool = True):
+    """DQN greedy action (comb_opt.py:319-326) from the embedding: (position in the neighbour list, node id, value,
+    q) -- Q head and list arg-max in one launch when the fused kernel applies."""
+    w = [_f32c(t.detach(), "parameter") for t in head_weights]
+    mu = _f32c(mu, "mu")
+    _require_cuda(reach_ptr, "reach_ptr")
+    reach_ptr = reach_ptr.to(torch.int32).contiguous()
+    reach_idx = reach_idx.to(device=mu.device, dtype=torch.int32).contiguous()
+    if head_fused_eligible(layout, w):
+        _, _, q, _, pos, node, val = _head_fused_forward(layout, bool(norm_agg), mu, w, "list", None, reach_ptr, reach_idx)
+        return pos, node, val, q
+    _, _, q = _head_forward(layout, bool(norm_agg), mu, w)
+    pos, node, val = list_argmax(layout, q, reach_ptr, reach_idx)
+    return pos, node, val, q

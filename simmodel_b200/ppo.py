@@ -201,8 +201,8 @@ class S2VKernelMixin:
         """Masked policy: prob f32[S,N] (models_basic_lstm.py:526-542)."""
         num_nodes, seq_len, nfm, ei, reachable, lstm_hidden = self.process_input(nfm, ei, reachable, hidden)
         mu, lstm_hidden, layout = self._create_embeddings(seq_len, nfm, ei, lstm_hidden)
-        logits = ops.s2v_head(layout, mu.reshape(seq_len * num_nodes, self.emb_dim), self.head_weights("_pi"), True)
-        prob = ops.masked_softmax(layout, logits, reachable)
+        # logit head + reachable-node mask + per-graph softmax: one launch (ops.s2v_head_softmax)
+        prob = ops.s2v_head_softmax(layout, mu.reshape(seq_len * num_nodes, self.emb_dim), self.head_weights("_pi"), reachable)
         return prob.view(seq_len, num_nodes), lstm_hidden
 
     def v(self, nfm, ei, reachable, hidden):
@@ -214,8 +214,7 @@ class S2VKernelMixin:
             pool = ops.segment_pool(layout, flat, True)                       # mu.mean(dim=1)
             v = F.linear(pool, self.theta5_v.weight, self.theta5_v.bias)      # (S,1): B scalars, stays torch
         else:
-            qvals = ops.s2v_head(layout, flat, self.head_weights("_v"), True)
-            v, _ = ops.masked_max(layout, qvals, reachable)
+            v, _ = ops.s2v_head_max(layout, flat, self.head_weights("_v"), reachable)    # Q head + mask + max: one launch
             v = v.unsqueeze(-1)
         return v, lstm_hidden
 
@@ -260,14 +259,13 @@ class S2VKernelMixin:
         flat_s = mu_s.reshape(R * S * N, p).contiguous()
         flat_p = mu_p.reshape(R * S * N, p).contiguous()
         reach_s, reach_p = reachable.to(dev).reshape(R * S, N), reachable_prime.to(dev).reshape(R * S, N)
-        logits = ops.s2v_head(lay_s, flat_s, self.head_weights("_pi"), True)
-        prob = ops.masked_softmax(lay_s, logits, reach_s).view(R, S, N)
+        prob = ops.s2v_head_softmax(lay_s, flat_s, self.head_weights("_pi"), reach_s).view(R, S, N)
         if self.config["critic"] == "v":
             v_s = F.linear(ops.segment_pool(lay_s, flat_s, True), self.theta5_v.weight, self.theta5_v.bias)
             v_p = F.linear(ops.segment_pool(lay_s, flat_p, True), self.theta5_v.weight, self.theta5_v.bias)
         else:
-            v_s, _ = ops.masked_max(lay_s, ops.s2v_head(lay_s, flat_s, self.head_weights("_v"), True), reach_s)
-            v_p, _ = ops.masked_max(lay_s, ops.s2v_head(lay_s, flat_p, self.head_weights("_v"), True), reach_p)
+            v_s, _ = ops.s2v_head_max(lay_s, flat_s, self.head_weights("_v"), reach_s)
+            v_p, _ = ops.s2v_head_max(lay_s, flat_p, self.head_weights("_v"), reach_p)
         return prob, v_s.reshape(R, S, 1), v_p.reshape(R, S, 1)
 
     @torch.no_grad()
@@ -275,8 +273,7 @@ class S2VKernelMixin:
         """probs.argmax() of the deterministic policy (rl_policy.py:533-536), on the GPU."""
         num_nodes, seq_len, nfm, ei, reachable, lstm_hidden = self.process_input(nfm, ei, reachable, hidden)
         mu, lstm_hidden, layout = self._create_embeddings(seq_len, nfm, ei, lstm_hidden)
-        logits = ops.s2v_head(layout, mu.reshape(seq_len * num_nodes, self.emb_dim), self.head_weights("_pi"), True)
-        arg, _ = ops.masked_argmax(layout, logits, reachable)
+        arg, _ = ops.s2v_head_argmax(layout, mu.reshape(seq_len * num_nodes, self.emb_dim), self.head_weights("_pi"), reachable)
         return arg, lstm_hidden
 
 

@@ -109,6 +109,12 @@ class QNet(nn.Module):
     def forward(self, xv, Ws, pyg_data):
         """xv f32[B,Npad,F], Ws f32[B,Npad,Npad] (0/1), pyg_data with .ptr/.batch
         (and optionally a real .edge_index) -> f32[sum N], squeezed (comb_opt.py:217-275)."""
+        x, layout = self.prepare(xv, Ws, pyg_data)
+        return self.forward_graph(x, layout).squeeze()
+
+    def prepare(self, xv, Ws, pyg_data):
+        """The reference call's arguments -> (x f32[sum N, F] of the real nodes, GraphLayout): un-padding
+        (comb_opt.py:252-259) and the CSR that replaces the dense Ws."""
         dev = self.device
         if dev.type != "cuda":
             raise S2VError("simmodel_b200.QNet runs on CUDA only: call .to('cuda') first (no CPU fallback)")
@@ -136,8 +142,7 @@ class QNet(nn.Module):
             off = ptr[nz[:, 0]]
             ei = torch.stack((nz[:, 1] + off, nz[:, 2] + off))
         layout = GraphLayout.from_batch(ei, ptr, n_pad, batch)
-        out = self.forward_graph(x.contiguous(), layout)
-        return out.squeeze()
+        return x.contiguous(), layout
 
     def numTrainableParameters(self, verbose=True):
         total = 0
@@ -215,14 +220,14 @@ class QFunction:
         """Greedy action: (index in reachable_nodes, node id, value) (comb_opt.py:309-331).
         The masked argmax runs on the GPU (s2v_list_argmax); only three scalars come back."""
         dev = self.model.device
-        self.model.eval()
-        estimated_rewards = self.predict(state_tsr.to(dev), W, pyg_data)
-        self.model.train()
-        n = int(estimated_rewards.numel())
-        layout = _single_graph_ranges(n, dev)
+        m = self.model
+        pyg_batch = self._batch_with_edges([W], [pyg_data], dev)
         reach = torch.as_tensor(np.asarray(reachable_nodes), dtype=torch.int32, device=dev)
         rptr = torch.tensor([0, reach.numel()], dtype=torch.int32, device=dev)
-        pos, node, val = ops.list_argmax(layout, estimated_rewards, rptr, reach)
+        with torch.no_grad():                   # embedding, then Q head + neighbour-list arg-max in ONE launch
+            x, layout = m.prepare(state_tsr.to(dev).unsqueeze(0), None, pyg_batch)
+            mu = m.embed_graph(x, layout)
+            pos, node, val, _ = ops.s2v_head_list_argmax(layout, mu, m.head_weights(), rptr, reach, m.norm_agg)
         # one D2H copy; int ids and the fp32 value are exact in float64
         res = torch.stack((pos.to(torch.float64), node.to(torch.float64), val.to(torch.float64))).cpu().numpy()
         action, action_nodeselect = int(res[0, 0]), int(res[1, 0])
@@ -237,12 +242,10 @@ class QFunction:
         replaces the 32 per-experience target-network calls of comb_opt.py:580-589.
         x f32[sum N, F], layout GraphLayout, reach_ptr i32[B+1], reach_idx i32 local node ids
         (ascending neighbour lists).  Returns device tensors (position in list, node id, value), each [B]."""
-        was_training = self.model.training
-        self.model.eval()
-        q = self.model.forward_graph(x, layout)
-        if was_training:
-            self.model.train()
-        return ops.list_argmax(layout, q, reach_ptr, reach_idx)
+        m = self.model
+        mu = m.embed_graph(x, layout)
+        pos, node, val, _ = ops.s2v_head_list_argmax(layout, mu, m.head_weights(), reach_ptr, reach_idx, m.norm_agg)
+        return pos, node, val
 
     def batch_update(self, states_tsrs, Ws, pyg_data, actions, targets):
         """comb_opt.py:334-366."""

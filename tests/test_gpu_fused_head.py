@@ -1,0 +1,121 @@
+"""Fused head launch (pool + theta6 + head + invalid-action mask + per-graph reduction, csrc/s2v_head.cu:k_head_fused)
+against the three-launch sequence it replaces: every output bit-identical, gradients identical.
+Reference ops replaced: models_basic_lstm.py:530-540 (pi), 548-564 (v), comb_opt.py:319-326 (greedy action)."""
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _case(seed, p, dev):
+    import simmodel_b200 as sb
+    rng = np.random.default_rng(seed)
+    sizes = rng.integers(1, 200, size=11).tolist() + [1, 64, 65, 128]
+    n = int(sum(sizes))
+    ptr = torch.zeros(len(sizes) + 1, dtype=torch.int64)
+    ptr[1:] = torch.cumsum(torch.tensor(sizes), 0)
+    ei = torch.zeros(2, 0, dtype=torch.int64)
+    layout = sb.GraphLayout.from_batch(ei.to(dev), ptr.to(dev), max(sizes))
+    gen = torch.Generator().manual_seed(seed)
+    mu = torch.randn(n, p, generator=gen).to(dev)
+    w = [torch.randn(1, 2 * p, generator=gen) / 4, torch.randn(1, generator=gen), torch.randn(p, p, generator=gen) / 8,
+         torch.randn(p, generator=gen) / 8, torch.randn(p, p, generator=gen) / 8, torch.randn(p, generator=gen) / 8]
+    w = [t.to(dev) for t in w]
+    mask = torch.rand(n, generator=gen) < 0.3
+    mask[int(ptr[3]):int(ptr[4])] = False                       # a graph without any reachable node
+    mask[int(ptr[5])] = True
+    return layout, mu, w, mask.to(dev), ptr, sizes
+
+
+@pytest.mark.parametrize("p", [16, 64])
+@pytest.mark.parametrize("norm_agg", [True, False])
+def test_fused_head_bit_identical_to_three_launches(p, norm_agg, cuda_device):
+    import simmodel_b200 as sb
+    from simmodel_b200 import ops
+    dev = cuda_device
+    layout, mu, w, mask, ptr, sizes = _case(3 + p, p, dev)
+    assert ops.head_fused_eligible(layout, w)
+    m8 = ops._mask_u8(mask, layout.num_nodes)
+    pool0, g0, q0 = ops._head_forward(layout, norm_agg, mu, w)
+    # mode q
+    pool, gst, q = ops._head_fused_forward(layout, norm_agg, mu, w, "q")[:3]
+    assert torch.equal(pool, pool0) and torch.equal(gst, g0) and torch.equal(q, q0)
+    # softmax (NaN rows of the all-masked graph compare equal as NaN)
+    prob0 = ops.masked_softmax(layout, q0, mask)
+    prob = ops._head_fused_forward(layout, norm_agg, mu, w, "softmax", m8)[3]
+    assert torch.equal(torch.isnan(prob), torch.isnan(prob0))
+    assert torch.equal(torch.nan_to_num(prob), torch.nan_to_num(prob0))
+    # masked max / argmax
+    arg0, val0 = ops.masked_argmax(layout, q0, mask)
+    _, _, _, _, arg, _, val = ops._head_fused_forward(layout, norm_agg, mu, w, "max", m8)
+    assert torch.equal(arg, arg0) and torch.equal(val, val0)
+    assert int(arg[3]) == -1 and float(val[3]) == float("-inf")
+    # neighbour-list arg-max
+    rng = np.random.default_rng(1)
+    lists = [np.sort(rng.choice(s, size=rng.integers(0, min(s, 6) + 1), replace=False)) for s in sizes]
+    rptr = torch.tensor(np.concatenate([[0], np.cumsum([len(l) for l in lists])]), dtype=torch.int32, device=dev)
+    ridx = torch.tensor(np.concatenate(lists) if sum(len(l) for l in lists) else np.zeros(0), dtype=torch.int32, device=dev)
+    pos0, node0, v0 = ops.list_argmax(layout, q0, rptr, ridx)
+    pos, node, v, qq = ops.s2v_head_list_argmax(layout, mu, w, rptr, ridx, norm_agg)
+    assert torch.equal(pos, pos0) and torch.equal(node, node0) and torch.equal(v, v0) and torch.equal(qq, q0)
+
+
+def test_fused_head_gradients_equal_unfused(cuda_device):
+    from simmodel_b200 import ops
+    dev = cuda_device
+    layout, mu, w, mask, ptr, sizes = _case(11, 64, dev)
+    keep = torch.ones(layout.num_graphs, dtype=torch.bool, device=dev)
+    keep[3] = False                                              # the all-masked graph is NaN on both sides
+
+    def run(fused):
+        mu_ = mu.clone().requires_grad_(True)
+        w_ = [t.clone().requires_grad_(True) for t in w]
+        if fused:
+            prob = ops.s2v_head_softmax(layout, mu_, w_, mask)
+            val, _ = ops.s2v_head_max(layout, mu_, w_, mask)
+        else:
+            prob = ops.masked_softmax(layout, ops.s2v_head(layout, mu_, w_, True), mask)
+            val, _ = ops.masked_max(layout, ops.s2v_head(layout, mu_, w_, True), mask)
+        gid = layout.gid.long()
+        wts = torch.linspace(0.5, 1.5, layout.num_nodes, device=dev)
+        loss = (prob * wts)[keep[gid]].sum() + val[keep].sum()
+        loss.backward()
+        return [mu_.grad] + [t.grad for t in w_]
+    a, b = run(True), run(False)
+    for x, y in zip(a, b):
+        assert torch.equal(torch.nan_to_num(x), torch.nan_to_num(y))
+
+
+def test_ppo_calls_use_one_head_launch(cuda_device):
+    """pi(), v() and greedy_action() of the PPO model: exactly one k_head_fused launch and no stand-alone pool / head /
+    mask kernel in the forward pass (counted from a CUPTI trace when the profiler is available)."""
+    import types
+    import simmodel_b200 as sb
+    dev = cuda_device
+    try:
+        from torch.profiler import ProfilerActivity, profile
+    except Exception:
+        pytest.skip("torch.profiler unavailable")
+    topo = sb.graphs.load_topology("Manhattan5")
+    hp = types.SimpleNamespace(node_dim=sb.graphs.NODE_DIM, emb_dim=64, parallel_rollouts=1, batch_size=1, learning_rate=1e-3)
+    model = sb.PPO_GNN_Single_LSTM({"lstm_type": "None", "qnet": "s2v", "critic": "q", "emb_dim": 64, "emb_iterT": 5}, hp,
+                                   {"base_checkpoint_path": None}, device=dev)
+    gen = torch.Generator().manual_seed(0)
+    nfm = sb.graphs.synth_nfm(topo, 6, gen)
+    reach = torch.rand(6, topo.num_nodes, generator=gen) < 0.4
+    reach[:, 0] = True
+    ei = topo.edge_index
+    for fn in (model.pi, model.v, model.greedy_action):
+        with torch.no_grad():
+            fn(nfm, ei, reach, None)
+            torch.cuda.synchronize()
+            with profile(activities=[ProfilerActivity.CUDA]) as prof:
+                fn(nfm, ei, reach, None)
+                torch.cuda.synchronize()
+        names = [e.name for e in prof.events() if "cuda" in str(getattr(e, "device_type", "")).lower()]
+        if not names:
+            pytest.skip("empty CUPTI trace")
+        fused = [nm for nm in names if "k_head_fused" in nm]
+        apart = [nm for nm in names if any(k in nm for k in ("k_pool", "k_head<", "k_head_tc", "k_masked", "k_list_argmax"))]
+        assert len(fused) == 1 and not apart, (fn.__name__, names)
