@@ -192,13 +192,28 @@ int s2v_head_forward(const s2v_graph_t* g, const s2v_head_params_t* prm, const f
  *   mode 2: arg_out [B] (local node id, -1 if the mask is empty), val_out [B] = masked max (models_basic_lstm.py:548-564)
  *   mode 3: arg_out [B] = position in the neighbour list, node_out [B], val_out [B] (comb_opt.py:319-326)
  * Bit-identical to s2v_head_forward followed by the s2v_masked_* / s2v_list_argmax call whenever
- * s2v_head_fused_eligible() is 1 (the problem runs the CUDA-core head: emb_dim != 64, flags == 1, or fewer than 4096
- * rows); for large batches the tcgen05 head + separate reduction is faster and launches do not matter. */
+ * s2v_head_fused_eligible() is 1: the problem runs the CUDA-core head (emb_dim != 64, flags == 1, or fewer than 4096
+ * rows) and its graphs are small (<= 256 nodes on average: one CTA walks a whole graph).  Large batches keep the tcgen05
+ * head + separate reduction (launches do not matter there), a few large graphs the tile-parallel CUDA-core head. */
 int s2v_head_fused_forward(const s2v_graph_t* g, const s2v_head_params_t* prm, const float* mu, int32_t mode,
                            const uint8_t* mask, const int32_t* reach_ptr, const int32_t* reach_idx,
                            float* pool, float* gstate, float* q, float* prob, int64_t* arg_out, int64_t* node_out,
                            float* val_out, void* stream);
-int s2v_head_fused_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes);
+int s2v_head_fused_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes, int64_t num_graphs);
+
+/* Small-graph fast path: the whole forward pass -- node MLP, T rounds, pool, head, mask, reduction -- in ONE cooperative
+ * launch with grid-wide barriers between the stages (csrc/s2v_small.cu).  For acting (B = 1), the reference's
+ * Manhattan5 / MemTask batches and the per-rollout PPO calls, where a stage is microseconds and T + 3 launches are the
+ * cost.  Same stage code as the per-stage CUDA-core kernels: results bit-identical to s2v_embed_forward followed by
+ * s2v_head_fused_forward.  mode -1: embedding only (hprm and the head outputs may be NULL); 0..3 as
+ * s2v_head_fused_forward.  s2v_qnet_small_eligible(): 1 when the problem runs the CUDA-core path, has at most 65 536 rows
+ * and graphs of at most 256 nodes on average; otherwise s2v_qnet_small_forward returns S2V_ERR_UNSUPPORTED.
+ * Replaces comb_opt.py:297-331 (predict / get_best_action) and models_basic_lstm.py:526-566 (pi / v per rollout). */
+int s2v_qnet_small_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes, int64_t num_graphs);
+int s2v_qnet_small_forward(const s2v_graph_t* g, const s2v_embed_params_t* eprm, const s2v_head_params_t* hprm,
+                           const float* x, float* base, float* mus, int32_t mode, const uint8_t* mask,
+                           const int32_t* reach_ptr, const int32_t* reach_idx, float* pool, float* gstate, float* q,
+                           float* prob, int64_t* arg_out, int64_t* node_out, float* val_out, void* stream);
 
 /* Head backward.  dq [num_nodes]; dmu [num_nodes,p] out (multiplied by [mu>0] when
  * mask_relu != 0, i.e. it is du^T); per_graph [B, 2p+4] workspace;

@@ -55,7 +55,9 @@ SIGNATURES = {
     "s2v_debug_tc_gemm": (C.c_int, [i32, vp, vp, vp, i64, vp]),
     "s2v_head_forward": (C.c_int, [GP, HP, vp, vp, vp, vp, vp]),
     "s2v_head_fused_forward": (C.c_int, [GP, HP, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
-    "s2v_head_fused_eligible": (C.c_int, [i32, i32, i64]),
+    "s2v_head_fused_eligible": (C.c_int, [i32, i32, i64, i64]),
+    "s2v_qnet_small_eligible": (C.c_int, [i32, i32, i64, i64]),
+    "s2v_qnet_small_forward": (C.c_int, [GP, EP, HP, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
     "s2v_head_backward_workspace_bytes": (i64, [i32, i32]),
     "s2v_head_backward": (C.c_int, [GP, HP, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp]),
     "s2v_pool_forward": (C.c_int, [GP, i32, i32, vp, vp, vp]),

@@ -42,6 +42,15 @@ __device__ __forceinline__ float4 f4zero() { return make_float4(0.f, 0.f, 0.f, 0
 __device__ __forceinline__ float4 f4add(float4 a, float4 b) { return make_float4(a.x + b.x, a.y + b.y, a.z + b.z, a.w + b.w); }
 __device__ __forceinline__ float relu(float v) { return v > 0.f ? v : 0.f; }
 
+// Row loads of the gathers.  LD = 0: ld.global.nc (the source is read-only for the whole kernel: one launch per round);
+// LD = 1: ld.global.cg (L2): the single-launch small-graph kernel reads rows other CTAs wrote earlier in the SAME launch.
+template <int LD>
+__device__ __forceinline__ float4 ld_row4(const float* p) {
+    if constexpr (LD == 1) return __ldcg(reinterpret_cast<const float4*>(p));
+    else return __ldg(reinterpret_cast<const float4*>(p));
+}
+
+
 // Row r of the batch -> (row in the CSR, offset to add to CSR column ids, graph id).
 __device__ __forceinline__ void row_info(const s2v_graph_t& g, int r, int& li, int& off, int& gi) {
     if (g.period > 0) {
@@ -62,12 +71,36 @@ __device__ __forceinline__ void graph_range(const s2v_graph_t& g, int gi, int& l
     else { lo = __ldg(g.ptr + gi); hi = __ldg(g.ptr + gi + 1); }
 }
 
+// a + sum_k w_row[k] * v[k], k ascending (the order of the plain loop), with the P/4 row loads issued together: a thread
+// that walks a weight row with scalar loads pays one L2 round trip per element -- 64 in a row are ~10 us, the whole
+// budget of a small-graph launch.
+template <int P>
+__device__ __forceinline__ float row_dot(const float* __restrict__ w_row, const float* v, float a) {
+    float4 w[P / 4];
+#pragma unroll
+    for (int k4 = 0; k4 < P / 4; ++k4) w[k4] = ldg4(w_row + 4 * k4);
+#pragma unroll
+    for (int k4 = 0; k4 < P / 4; ++k4) {
+        a = fmaf(w[k4].x, v[4 * k4], a); a = fmaf(w[k4].y, v[4 * k4 + 1], a);
+        a = fmaf(w[k4].z, v[4 * k4 + 2], a); a = fmaf(w[k4].w, v[4 * k4 + 3], a);
+    }
+    return a;
+}
+
 // smem Wt[k*P + n] = W[n*P + k]   (y = x * W^T form)
 template <int P>
 __device__ __forceinline__ void load_w_transposed(float* Ws, const float* __restrict__ W) {
-    for (int e = threadIdx.x; e < P * P; e += S2V_THREADS) {
-        int n = e / P, k = e - n * P;
-        Ws[k * P + n] = __ldg(W + e);
+    // consecutive threads take consecutive rows n: the transposed shared-memory stores are conflict-free and the
+    // P*P/4/128 vector loads of a thread are independent (one L2 round trip for the whole matrix)
+    constexpr int V = P / 4;
+#pragma unroll
+    for (int e0 = 0; e0 < P * V; e0 += S2V_THREADS) {
+        const int e = e0 + threadIdx.x;
+        if (P * V % S2V_THREADS != 0 && e >= P * V) break;
+        const int c = e / P, n = e - c * P;
+        const float4 w = ldg4(W + n * P + 4 * c);
+        Ws[(4 * c) * P + n] = w.x; Ws[(4 * c + 1) * P + n] = w.y;
+        Ws[(4 * c + 2) * P + n] = w.z; Ws[(4 * c + 3) * P + n] = w.w;
     }
 }
 // smem Ws[n*P + k] = W[n*P + k]   (y = g * W form)
@@ -77,13 +110,13 @@ __device__ __forceinline__ void load_w_plain(float* Ws, const float* __restrict_
 }
 
 // Copy `rows` consecutive rows of a [*,P] global matrix into a row tile; rows beyond are zeroed.
-template <int P>
-__device__ __forceinline__ void load_tile(float* As, const float* __restrict__ src, int rows) {
+template <int P, int LD = 0>
+__device__ __forceinline__ void load_tile(float* As, const float* src, int rows) {
     constexpr int LDA = Cfg<P>::LDA;
     constexpr int V = P / 4;
     for (int e = threadIdx.x; e < S2V_TM * V; e += S2V_THREADS) {
         int r = e / V, c = e - r * V;
-        float4 v = r < rows ? ldg4(src + (size_t)r * P + 4 * c) : f4zero();
+        float4 v = r < rows ? ld_row4<LD>(src + (size_t)r * P + 4 * c) : f4zero();
         st4(As + r * LDA + 4 * c, v);
     }
 }
@@ -187,6 +220,7 @@ __device__ __forceinline__ void reduce_columns(float* scratch, const float (&v)[
 }
 
 // Sum of the neighbour rows of CSR row `li` (float4 slice c4 of each row), fixed order.
+template <int LD = 0>
 __device__ __forceinline__ float4 gather_row(const float* __restrict__ src, const int32_t* __restrict__ rowptr,
                                              const int32_t* __restrict__ col, int li, int off, int P, int c4) {
     int beg = __ldg(rowptr + li), end = __ldg(rowptr + li + 1);
@@ -194,10 +228,10 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ src, cons
     int k = beg;
     for (; k + 4 <= end; k += 4) {
         int j0 = __ldg(col + k), j1 = __ldg(col + k + 1), j2 = __ldg(col + k + 2), j3 = __ldg(col + k + 3);
-        float4 v0 = ldg4(src + (size_t)(off + j0) * P + 4 * c4);
-        float4 v1 = ldg4(src + (size_t)(off + j1) * P + 4 * c4);
-        float4 v2 = ldg4(src + (size_t)(off + j2) * P + 4 * c4);
-        float4 v3 = ldg4(src + (size_t)(off + j3) * P + 4 * c4);
+        float4 v0 = ld_row4<LD>(src + (size_t)(off + j0) * P + 4 * c4);
+        float4 v1 = ld_row4<LD>(src + (size_t)(off + j1) * P + 4 * c4);
+        float4 v2 = ld_row4<LD>(src + (size_t)(off + j2) * P + 4 * c4);
+        float4 v3 = ld_row4<LD>(src + (size_t)(off + j3) * P + 4 * c4);
         acc = f4add(f4add(f4add(f4add(acc, v0), v1), v2), v3);
     }
     if (k < end) {
@@ -205,9 +239,9 @@ __device__ __forceinline__ float4 gather_row(const float* __restrict__ src, cons
         int j0 = __ldg(col + k);
         int j1 = n > 1 ? __ldg(col + k + 1) : j0;
         int j2 = n > 2 ? __ldg(col + k + 2) : j0;
-        float4 v0 = ldg4(src + (size_t)(off + j0) * P + 4 * c4);
-        float4 v1 = n > 1 ? ldg4(src + (size_t)(off + j1) * P + 4 * c4) : f4zero();
-        float4 v2 = n > 2 ? ldg4(src + (size_t)(off + j2) * P + 4 * c4) : f4zero();
+        float4 v0 = ld_row4<LD>(src + (size_t)(off + j0) * P + 4 * c4);
+        float4 v1 = n > 1 ? ld_row4<LD>(src + (size_t)(off + j1) * P + 4 * c4) : f4zero();
+        float4 v2 = n > 2 ? ld_row4<LD>(src + (size_t)(off + j2) * P + 4 * c4) : f4zero();
         acc = f4add(acc, v0);
         if (n > 1) acc = f4add(acc, v1);
         if (n > 2) acc = f4add(acc, v2);
@@ -248,7 +282,7 @@ __device__ __forceinline__ void gather8_prefetch(Gather8Meta& m, const s2v_graph
     }
 }
 
-template <class Sink>
+template <int LD = 0, class Sink>
 __device__ __forceinline__ void gather8_consume(const Gather8Meta& m, const int32_t* __restrict__ col,
                                                 const float* __restrict__ src, int rl0, Sink&& sink) {
     const unsigned FULL = 0xffffffffu;
@@ -271,7 +305,7 @@ __device__ __forceinline__ void gather8_consume(const Gather8Meta& m, const int3
         for (int i = 0; i < 4; ++i)
 #pragma unroll
             for (int k = 0; k < 4; ++k)
-                v[i][k] = dd[4 * h + i] > k ? ldg4(src + (size_t)(oo[4 * h + i] + jj[4 * h + i][k]) * 64 + 4 * c) : f4zero();
+                v[i][k] = dd[4 * h + i] > k ? ld_row4<LD>(src + (size_t)(oo[4 * h + i] + jj[4 * h + i][k]) * 64 + 4 * c) : f4zero();
 #pragma unroll
         for (int i = 0; i < 4; ++i)
             acc[4 * h + i] = f4add(f4add(f4add(f4add(f4zero(), v[i][0]), v[i][1]), v[i][2]), v[i][3]);
@@ -283,7 +317,7 @@ __device__ __forceinline__ void gather8_consume(const Gather8Meta& m, const int3
             int bi = __shfl_sync(FULL, m.b, i, 16);
             for (int k = 4; k < dmax; ++k) {
                 int j = k < 16 ? __shfl_sync(FULL, m.idx[i], k, 16) : (k < dd[i] ? __ldg(col + bi + k) : 0);
-                if (k < dd[i]) acc[i] = f4add(acc[i], ldg4(src + (size_t)(oo[i] + j) * 64 + 4 * c));
+                if (k < dd[i]) acc[i] = f4add(acc[i], ld_row4<LD>(src + (size_t)(oo[i] + j) * 64 + 4 * c));
             }
         }
         sink(rl0 + i, acc[i]);
@@ -481,17 +515,17 @@ __device__ __forceinline__ void gather4_pipe_step(GatherPipe4& p, const s2v_grap
     p.ext1 = ext2;
 }
 
-template <class Sink>
+template <int LD = 0, class Sink>
 __device__ __forceinline__ void gather8_p64(const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
                                             const int32_t* __restrict__ col, const float* __restrict__ src,
                                             int row0, int rows, int rl0, Sink&& sink) {
     Gather8Meta m;
     gather8_prefetch(m, g, rowptr, col, row0, rows, rl0);
-    gather8_consume(m, col, src, rl0, sink);
+    gather8_consume<LD>(m, col, src, rl0, sink);
 }
 
 // Gather a tile: As[rl][:] = sum of neighbour rows of batch row row0+rl (zeros past num_nodes).
-template <int P>
+template <int P, int LD = 0>
 __device__ __forceinline__ void gather_tile(float* As, const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
                                             const int32_t* __restrict__ col, const float* __restrict__ src,
                                             int row0, int rows) {
@@ -499,7 +533,7 @@ __device__ __forceinline__ void gather_tile(float* As, const s2v_graph_t& g, con
     constexpr int ROWS_PER_WARP = S2V_TM / (S2V_THREADS / 32);
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     if constexpr (P == 64) {
-        gather8_p64(g, rowptr, col, src, row0, rows, warp * ROWS_PER_WARP + 8 * (lane >> 4),
+        gather8_p64<LD>(g, rowptr, col, src, row0, rows, warp * ROWS_PER_WARP + 8 * (lane >> 4),
                     [&](int rl, const float4& acc) { st4(As + rl * LDA + 4 * (lane & 15), acc); });
         return;
     }
@@ -513,7 +547,7 @@ __device__ __forceinline__ void gather_tile(float* As, const s2v_graph_t& g, con
             int r = row0 + rl;
             if (g.period > 0) { gi = r / g.period; off = gi * g.period; li = r - off; }
             else { li = r; off = 0; }
-            acc = gather_row(src, rowptr, col, li, off, P, c4);
+            acc = gather_row<LD>(src, rowptr, col, li, off, P, c4);
         }
         st4(As + rl * LDA + 4 * c4, acc);
     }

@@ -11,6 +11,7 @@
 //
 // FP32 CUDA-core path (FFMA); see s2v_common.cuh for the tile model.
 #include "s2v_common.cuh"
+#include "s2v_bodies.cuh"
 
 // ------------------------------------------------------------------------------------
 // forward
@@ -19,123 +20,16 @@ template <int P>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_embed_first(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict__ x,
               float* __restrict__ base, float* __restrict__ mu1, int num_tiles) {
-    using C = Cfg<P>;
     extern __shared__ __align__(16) float smem[];
-    const int F = prm.node_dim;
-    float* Wt1b = smem;                       // [P][P]  Wt[k][n] = theta1b[n][k]
-    float* As = Wt1b + C::W_FLOATS;           // h tile
-    float* W1a = As + C::TILE_FLOATS;         // [F][P]  W1a[f][n] = theta1a[n][f]
-    float* xs = W1a + S2V_MAX_F * P;          // [TM][F]
-    float* vec = xs + S2V_TM * S2V_MAX_F;     // b1a, cst, u1, u0, r1, r0   (6 x P)
-    float* b1a = vec, *cst = vec + P, *u1 = vec + 2 * P, *u0 = vec + 3 * P, *r1 = vec + 4 * P, *r0 = vec + 5 * P;
-    const int t = threadIdx.x;
-    const int tx = t % C::TXP, ty = t / C::TXP;
-    const bool active = t < C::ACTIVE;
-
-    load_w_transposed<P>(Wt1b, prm.theta1b_w);
-    for (int e = t; e < P * F; e += S2V_THREADS) { int n = e / F, f = e - n * F; W1a[f * P + n] = __ldg(prm.theta1a_w + e); }
-    if (t < P) {
-        b1a[t] = __ldg(prm.theta1a_b + t);
-        float w4 = __ldg(prm.theta4_w + t), b4 = __ldg(prm.theta4_b + t);
-        r1[t] = relu(w4 + b4);
-        r0[t] = relu(b4);
-    }
-    __syncthreads();
-    if (t < P) {
-        float a1 = 0.f, a0 = 0.f;
-        for (int k = 0; k < P; ++k) {
-            float w = __ldg(prm.theta3_w + t * P + k);
-            a1 = fmaf(w, r1[k], a1);
-            a0 = fmaf(w, r0[k], a0);
-        }
-        u1[t] = a1;
-        u0[t] = a0;
-        cst[t] = __ldg(prm.theta1b_b + t) + __ldg(prm.theta2_b + t) + __ldg(prm.theta3_b + t);
-    }
-    __syncthreads();
-
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = tile * S2V_TM;
-        const int rows = min(S2V_TM, g.num_nodes - row0);
-        for (int e = t; e < S2V_TM * F; e += S2V_THREADS)
-            xs[e] = e < rows * F ? __ldg(x + (size_t)row0 * F + e) : 0.f;
-        __syncthreads();
-        if (active) {
-#pragma unroll
-            for (int i = 0; i < C::NR; ++i) {
-                int r = ty + C::RG * i;
-                if (r >= S2V_TM) continue;
-                float4 h = ld4(b1a + 4 * tx);
-                for (int f = 0; f < F; ++f) {
-                    float xv = xs[r * F + f];
-                    float4 w = ld4(W1a + f * P + 4 * tx);
-                    h.x = fmaf(xv, w.x, h.x); h.y = fmaf(xv, w.y, h.y); h.z = fmaf(xv, w.z, h.z); h.w = fmaf(xv, w.w, h.w);
-                }
-                st4(As + r * C::LDA + 4 * tx, make_float4(relu(h.x), relu(h.y), relu(h.z), relu(h.w)));
-            }
-        }
-        __syncthreads();
-        if (active) {
-            float acc[C::NR][4];
-#pragma unroll
-            for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-            tile_gemm<P>(As, Wt1b, acc, tx, ty);
-            float4 c0 = ld4(cst + 4 * tx), v1 = ld4(u1 + 4 * tx), v0 = ld4(u0 + 4 * tx);
-#pragma unroll
-            for (int i = 0; i < C::NR; ++i) {
-                int rl = ty + C::RG * i;
-                if (rl >= rows) continue;
-                int r = row0 + rl, li, off, gi;
-                row_info(g, r, li, off, gi);
-                float c = (float)__ldg(g.indeg + li);
-                float d = (float)graph_npad(g, gi) - c;
-                float4 b;
-                b.x = acc[i][0] + (c0.x + (c * v1.x + d * v0.x));
-                b.y = acc[i][1] + (c0.y + (c * v1.y + d * v0.y));
-                b.z = acc[i][2] + (c0.z + (c * v1.z + d * v0.z));
-                b.w = acc[i][3] + (c0.w + (c * v1.w + d * v0.w));
-                st4(base + (size_t)r * P + 4 * tx, b);
-                st4(mu1 + (size_t)r * P + 4 * tx, make_float4(relu(b.x), relu(b.y), relu(b.z), relu(b.w)));
-            }
-        }
-        __syncthreads();
-    }
+    embed_first_body<P>(smem, g, prm, x, base, mu1, num_tiles);
 }
 
 template <int P>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_embed_round(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ base,
               const float* __restrict__ mu_prev, float* __restrict__ mu_next, int num_tiles) {
-    using C = Cfg<P>;
     extern __shared__ __align__(16) float smem[];
-    float* Wt2 = smem;                        // Wt[k][n] = theta2[n][k]
-    float* As = Wt2 + C::W_FLOATS;            // gathered tile
-    const int t = threadIdx.x;
-    const int tx = t % C::TXP, ty = t / C::TXP;
-    const bool active = t < C::ACTIVE;
-    load_w_transposed<P>(Wt2, theta2_w);
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = tile * S2V_TM;
-        const int rows = min(S2V_TM, g.num_nodes - row0);
-        gather_tile<P>(As, g, g.rowptr, g.col, mu_prev, row0, rows);
-        __syncthreads();
-        if (active) {
-            float acc[C::NR][4];
-#pragma unroll
-            for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-            tile_gemm<P>(As, Wt2, acc, tx, ty);
-#pragma unroll
-            for (int i = 0; i < C::NR; ++i) {
-                int rl = ty + C::RG * i;
-                if (rl >= rows) continue;
-                size_t o = (size_t)(row0 + rl) * P + 4 * tx;
-                float4 b = ldg4(base + o);
-                st4(mu_next + o, make_float4(relu(acc[i][0] + b.x), relu(acc[i][1] + b.y),
-                                             relu(acc[i][2] + b.z), relu(acc[i][3] + b.w)));
-            }
-        }
-        __syncthreads();
-    }
+    embed_round_body<P, 0>(smem, g, theta2_w, base, mu_prev, mu_next, num_tiles);
 }
 
 // ------------------------------------------------------------------------------------

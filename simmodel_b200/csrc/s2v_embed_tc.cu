@@ -539,14 +539,8 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
     }
     __syncthreads();
     if (t < 64) {
-        float a1 = 0.f, a0 = 0.f;
-        for (int k = 0; k < 64; ++k) {
-            float w = __ldg(prm.theta3_w + t * 64 + k);
-            a1 = fmaf(w, r1[k], a1);
-            a0 = fmaf(w, r0[k], a0);
-        }
-        u1[t] = a1;
-        u0[t] = a0;
+        u1[t] = row_dot<64>(prm.theta3_w + t * 64, r1, 0.f);
+        u0[t] = row_dot<64>(prm.theta3_w + t * 64, r0, 0.f);
         cst[t] = __ldg(prm.theta1b_b + t) + __ldg(prm.theta2_b + t) + __ldg(prm.theta3_b + t);
     }
     tc::fence_proxy_async_smem();

@@ -6,29 +6,11 @@
 //   q_i    = w5[:p] . relu(G_g(i)) + w5[p:] . relu(L_i) + b5
 #include "s2v_common.cuh"
 #include "s2v_reduce.cuh"
+#include "s2v_bodies.cuh"
 
 // ------------------------------------------------------------------------------------
 // pooling: one CTA per graph, fixed summation order
 // ------------------------------------------------------------------------------------
-template <int P>
-__device__ __forceinline__ void pool_graph(const float* __restrict__ mu, int lo, int hi, float* scratch, float* pool_s,
-                                           float scale) {
-    using C = Cfg<P>;
-    const int t = threadIdx.x;
-    const int tx = t % C::TXP, ty = t / C::TXP;
-    float4 s = f4zero();
-    if (t < C::ACTIVE)
-        for (int r = lo + ty; r < hi; r += C::RG) s = f4add(s, ldg4(mu + (size_t)r * P + 4 * tx));
-    if (t < C::ACTIVE) st4(scratch + ty * P + 4 * tx, s);
-    __syncthreads();
-    if (t < P) {
-        float a = 0.f;
-        for (int k = 0; k < C::RG; ++k) a += scratch[k * P + t];
-        pool_s[t] = a * scale;
-    }
-    __syncthreads();
-}
-
 template <int P>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_pool(s2v_graph_t g, int norm_agg, const float* __restrict__ mu, float* __restrict__ pool,
@@ -52,8 +34,7 @@ k_pool(s2v_graph_t g, int norm_agg, const float* __restrict__ mu, float* __restr
     (void)scale;
     __syncthreads();
     if (gstate != nullptr && t < P) {
-        float a = __ldg(theta6_b + t);
-        for (int k = 0; k < P; ++k) a = fmaf(__ldg(theta6_w + t * P + k), pool_s[k], a);
+        float a = row_dot<P>(theta6_w + t * P, pool_s, __ldg(theta6_b + t));
         gstate[(size_t)gi * P + t] = a;
     }
 }
@@ -156,122 +137,8 @@ k_head_fused(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu,
              const uint8_t* __restrict__ mask, const int32_t* __restrict__ reach_ptr, const int32_t* __restrict__ reach_idx,
              float* __restrict__ pool, float* __restrict__ gstate, float* q, float* __restrict__ prob,
              int64_t* __restrict__ arg_out, int64_t* __restrict__ node_out, float* __restrict__ val_out) {
-    using C = Cfg<P>;
-    static_assert(S2V_THREADS == MK_THREADS, "the fused kernel runs the mask reductions with their own thread count");
     extern __shared__ __align__(16) float smem[];
-    float* Wt7 = smem;                        // Wt[k][n] = theta7[n][k]
-    float* As = Wt7 + C::W_FLOATS;            // mu tile
-    float* red = As + C::TILE_FLOATS;         // [TM][TXP]
-    float* vec = red + S2V_TM * C::TXP;       // b7, w5a, w5b
-    float* scratch = vec + 3 * P;             // [RG][P] pooling partials
-    float* pool_s = scratch + C::RG * P;      // [P]
-    float* g_s = pool_s + P;                  // [P] theta6 pool + b6
-    __shared__ ArgPair sh_arg[MK_THREADS / 32];
-    __shared__ float sh_f[MK_THREADS / 32];
-    float* b7 = vec, *w5a = vec + P, *w5b = vec + 2 * P;
-    const int t = threadIdx.x;
-    const int tx = t % C::TXP, ty = t / C::TXP;
-    const bool active = t < C::ACTIVE;
-    load_w_transposed<P>(Wt7, prm.theta7_w);
-    if (t < P) {
-        b7[t] = __ldg(prm.theta7_b + t);
-        w5a[t] = __ldg(prm.theta5_w + t);
-        w5b[t] = __ldg(prm.theta5_w + P + t);
-    }
-    const float b5 = __ldg(prm.theta5_b);
-    __syncthreads();
-    for (int gi = blockIdx.x; gi < g.num_graphs; gi += gridDim.x) {
-        int lo, hi;
-        graph_range(g, gi, lo, hi);
-        const int n = hi - lo;
-        // ---- phase 1: pool + theta6 (k_pool) ----
-        pool_graph<P>(mu, lo, hi, scratch, pool_s, 1.f);
-        if (t < P) {
-            float pv = prm.norm_agg ? pool_s[t] / (float)(n > 1 ? n : 1) : pool_s[t];
-            pool_s[t] = pv;
-            pool[(size_t)gi * P + t] = pv;
-        }
-        __syncthreads();
-        if (t < P) {
-            float a = __ldg(prm.theta6_b + t);
-            for (int k = 0; k < P; ++k) a = fmaf(__ldg(prm.theta6_w + t * P + k), pool_s[k], a);
-            g_s[t] = a;
-            gstate[(size_t)gi * P + t] = a;
-        }
-        __syncthreads();
-        // ---- phase 2: q of the graph's rows, 64 at a time (k_head) ----
-        for (int row0 = lo; row0 < hi; row0 += S2V_TM) {
-            const int rows = min(S2V_TM, hi - row0);
-            load_tile<P>(As, mu + (size_t)row0 * P, rows);
-            __syncthreads();
-            if (active) {
-                float acc[C::NR][4];
-#pragma unroll
-                for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-                tile_gemm<P>(As, Wt7, acc, tx, ty);
-                const float4 bb = ld4(b7 + 4 * tx), wa = ld4(w5a + 4 * tx), wb = ld4(w5b + 4 * tx), G = ld4(g_s + 4 * tx);
-#pragma unroll
-                for (int i = 0; i < C::NR; ++i) {
-                    int rl = ty + C::RG * i;
-                    if (rl >= S2V_TM) continue;
-                    float sacc = 0.f;
-                    if (rl < rows) {
-                        sacc = fmaf(wa.x, relu(G.x), sacc); sacc = fmaf(wa.y, relu(G.y), sacc);
-                        sacc = fmaf(wa.z, relu(G.z), sacc); sacc = fmaf(wa.w, relu(G.w), sacc);
-                        sacc = fmaf(wb.x, relu(acc[i][0] + bb.x), sacc); sacc = fmaf(wb.y, relu(acc[i][1] + bb.y), sacc);
-                        sacc = fmaf(wb.z, relu(acc[i][2] + bb.z), sacc); sacc = fmaf(wb.w, relu(acc[i][3] + bb.w), sacc);
-                    }
-                    red[rl * C::TXP + tx] = sacc;
-                }
-            }
-            __syncthreads();
-            if (t < rows) {
-                float sacc = b5;
-                for (int k = 0; k < C::TXP; ++k) sacc += red[t * C::TXP + k];
-                q[row0 + t] = sacc;
-            }
-            __syncthreads();                   // also orders the q stores of this CTA before the reads of phase 3
-        }
-        // ---- phase 3: invalid-action mask + per-graph reduction (s2v_mask.cu) ----
-        if (mode == 1) {
-            float m = -CUDART_INF_F;
-            for (int r = lo + t; r < hi; r += MK_THREADS)
-                if (mask[r]) m = fmaxf(m, q[r]);
-            m = block_max(m, sh_f);
-            float ssum = 0.f;
-            for (int r = lo + t; r < hi; r += MK_THREADS)
-                if (mask[r]) ssum += expf(q[r] - m);
-            ssum = block_sum(ssum, sh_f);
-            for (int r = lo + t; r < hi; r += MK_THREADS) {
-                float v = mask[r] ? expf(q[r] - m) / ssum : 0.f;
-                if (m == -CUDART_INF_F) v = CUDART_NAN_F;
-                prob[r] = v;
-            }
-        } else if (mode == 2) {
-            ArgPair p; p.v = -CUDART_INF_F; p.i = -1;
-            for (int r = lo + t; r < hi; r += MK_THREADS)
-                if (mask[r]) { ArgPair c; c.v = q[r]; c.i = r - lo; p = better(p, c); }
-            p = block_argmax(p, sh_arg);
-            if (t == 0) {
-                arg_out[gi] = p.i;
-                val_out[gi] = p.i >= 0 ? p.v : -CUDART_INF_F;
-            }
-        } else if (mode == 3) {
-            const int beg = reach_ptr[gi], end = reach_ptr[gi + 1];
-            ArgPair p; p.v = -CUDART_INF_F; p.i = -1;
-            for (int k = beg + t; k < end; k += MK_THREADS) {
-                ArgPair c; c.v = q[lo + reach_idx[k]]; c.i = k - beg;
-                p = better(p, c);
-            }
-            p = block_argmax(p, sh_arg);
-            if (t == 0) {
-                arg_out[gi] = p.i;
-                node_out[gi] = p.i >= 0 ? (int64_t)reach_idx[beg + p.i] : -1;
-                val_out[gi] = p.i >= 0 ? p.v : -CUDART_INF_F;
-            }
-        }
-        __syncthreads();
-    }
+    head_fused_body<P, 0>(smem, g, prm, mu, mode, mask, reach_ptr, reach_idx, pool, gstate, q, prob, arg_out, node_out, val_out);
 }
 
 // ------------------------------------------------------------------------------------
@@ -826,10 +693,13 @@ extern "C" int s2v_head_fused_forward(const s2v_graph_t* g, const s2v_head_param
     return 0;
 }
 
-/* 1 when s2v_head_forward would run the CUDA-core tile kernel for this problem (the fused launch is then bit-identical
- * to pool / head / mask), 0 when it would pick the tcgen05 head (large batches: keep the three launches). */
-extern "C" int s2v_head_fused_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes) {
-    return head_tensor_path(emb_dim, flags, (int)(num_nodes > 0x7fffffff ? 0x7fffffff : num_nodes)) ? 0 : 1;
+/* 1 when the fused launch is the better choice: the problem runs the CUDA-core head (so the fused launch is
+ * bit-identical to pool / head / mask) and its graphs are small (at most 256 nodes on average). */
+extern "C" int s2v_head_fused_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes, int64_t num_graphs) {
+    if (head_tensor_path(emb_dim, flags, (int)(num_nodes > 0x7fffffff ? 0x7fffffff : num_nodes))) return 0;
+    // one CTA walks a whole graph: right for many small graphs (Manhattan5, MemTask, rollout steps of small worlds); a
+    // few large graphs (B = 1 acting on a 975-node road network) keep the tile-parallel head + separate reduction
+    return num_nodes <= 256 * num_graphs ? 1 : 0;
 }
 
 extern "C" int s2v_pool_forward(const s2v_graph_t* g, int32_t P, int32_t norm_agg, const float* mu, float* pool, void* stream) {

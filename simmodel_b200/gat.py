@@ -299,6 +299,12 @@ class QNet_GATv2(nn.Module):
     def embed_graph(self, x, layout: GraphLayout):
         return self.gat.forward_layout(x, layout)
 
+    @torch.no_grad()
+    def greedy_actions_graph(self, x, layout, reach_ptr, reach_idx):
+        """Greedy action per graph over its neighbour list: GATv2 embedding, then Q head + list arg-max in one launch."""
+        return ops.s2v_head_list_argmax(layout, self.embed_graph(x, layout), self.head_weights(), reach_ptr, reach_idx,
+                                        self.norm_agg)[:3]
+
     def forward(self, xv, Ws, pyg_data):
         """Reference contract: xv and Ws are ignored (comb_opt.py:84-94 reads pyg_data.x / .edge_index / .ptr /
         .batch only); returns q over all nodes of the batch, squeezed."""

@@ -69,6 +69,41 @@ def _embed_forward(layout, T, x, w):
     return base, mus
 
 
+def qnet_small_eligible(layout, w) -> bool:
+    """True when the single-launch small-graph kernel (csrc/s2v_small.cu) applies: the problem runs the CUDA-core path
+    and is small enough that launches, not bytes, are the cost (acting, Manhattan5 / MemTask batches, PPO rollouts)."""
+    return bool(_lib.lib().s2v_qnet_small_eligible(int(w[0].shape[0]), _lib.path_flag(), layout.num_nodes, layout.num_graphs))
+
+
+def _qnet_small_forward(layout, T, x, ew, hw, norm_agg, mode, mask_u8=None, reach_ptr=None, reach_idx=None):
+    """Whole forward pass in ONE cooperative launch.  mode None: embedding only.  Returns
+    (base, mus, pool, gstate, q, prob, arg, node, val) -- entries a mode does not produce are None."""
+    L = _lib.lib()
+    n, B, P = layout.num_nodes, layout.num_graphs, int(ew[0].shape[0])
+    dev = x.device
+    if x.shape[0] != n or x.shape[1] != ew[0].shape[1]:
+        raise ValueError("x has shape %s, expected (%d, %d)" % (tuple(x.shape), n, ew[0].shape[1]))
+    base = torch.empty(n, P, dtype=torch.float32, device=dev)
+    mus = torch.empty(T, n, P, dtype=torch.float32, device=dev)
+    head = mode is not None
+    pool = torch.empty(B, P, dtype=torch.float32, device=dev) if head else None
+    gstate = torch.empty(B, P, dtype=torch.float32, device=dev) if head else None
+    q = torch.empty(n, dtype=torch.float32, device=dev) if head else None
+    prob = torch.empty(n, dtype=torch.float32, device=dev) if mode == "softmax" else None
+    arg = torch.empty(B, dtype=torch.int64, device=dev) if mode in ("max", "list") else None
+    node = torch.empty(B, dtype=torch.int64, device=dev) if mode == "list" else None
+    val = torch.empty(B, dtype=torch.float32, device=dev) if mode in ("max", "list") else None
+    eprm = _embed_struct(T, ew)
+    hprm = _head_struct(norm_agg, hw) if head else None
+    with torch.cuda.device(dev):
+        _lib.check(L.s2v_qnet_small_forward(C.byref(layout.c_struct()), C.byref(eprm), C.byref(hprm) if head else None, _p(x),
+                                            _p(base), _p(mus), _FUSED_MODES[mode] if head else -1, _p(mask_u8), _p(reach_ptr),
+                                            _p(reach_idx), _p(pool), _p(gstate), _p(q), _p(prob), _p(arg), _p(node), _p(val),
+                                            _stream()), "s2v_qnet_small_forward")
+    _lib.launch_count += 1
+    return base, mus, pool, gstate, q, prob, arg, node, val
+
+
 def _embed_backward(layout, T, x, w, base, mus, dmu, dmu_masked, dus=None, grad_out=None):
     L = _lib.lib()
     n, P, F = layout.num_nodes, int(w[0].shape[0]), int(w[0].shape[1])
@@ -102,7 +137,7 @@ def _head_forward(layout, norm_agg, mu, w):
 def head_fused_eligible(layout, w) -> bool:
     """True when the fused head launch (pool + head + mask + reduction, csrc/s2v_head.cu:k_head_fused) computes the
     same bits as the three-launch sequence: the problem runs the CUDA-core head (small batches, acting)."""
-    return bool(_lib.lib().s2v_head_fused_eligible(int(w[2].shape[0]), _lib.path_flag(), layout.num_nodes))
+    return bool(_lib.lib().s2v_head_fused_eligible(int(w[2].shape[0]), _lib.path_flag(), layout.num_nodes, layout.num_graphs))
 
 
 _FUSED_MODES = {"q": 0, "softmax": 1, "max": 2, "list": 3}
@@ -150,7 +185,10 @@ class _EmbedFn(torch.autograd.Function):
     def forward(ctx, layout, T, x, *w):
         w = [_f32c(t.detach(), "parameter") for t in w]
         x = _f32c(x, "x")
-        base, mus = _embed_forward(layout, T, x, w)
+        if qnet_small_eligible(layout, w):
+            base, mus = _qnet_small_forward(layout, T, x, w, None, True, None)[:2]
+        else:
+            base, mus = _embed_forward(layout, T, x, w)
         ctx.layout, ctx.T = layout, T
         ctx.save_for_backward(x, base, mus, *w)
         return mus[T - 1]
@@ -187,11 +225,14 @@ class _QNetFn(torch.autograd.Function):
     def forward(ctx, layout, T, norm_agg, x, *w):
         w = [_f32c(t.detach(), "parameter") for t in w]
         x = _f32c(x, "x")
-        base, mus = _embed_forward(layout, T, x, w[:10])
-        if head_fused_eligible(layout, w[10:]):
-            pool, gstate, q = _head_fused_forward(layout, norm_agg, mus[T - 1], w[10:], "q")[:3]
+        if qnet_small_eligible(layout, w[:10]):
+            base, mus, pool, gstate, q = _qnet_small_forward(layout, T, x, w[:10], w[10:], norm_agg, "q")[:5]
         else:
-            pool, gstate, q = _head_forward(layout, norm_agg, mus[T - 1], w[10:])
+            base, mus = _embed_forward(layout, T, x, w[:10])
+            if head_fused_eligible(layout, w[10:]):
+                pool, gstate, q = _head_fused_forward(layout, norm_agg, mus[T - 1], w[10:], "q")[:3]
+            else:
+                pool, gstate, q = _head_forward(layout, norm_agg, mus[T - 1], w[10:])
         ctx.layout, ctx.T, ctx.norm_agg = layout, T, norm_agg
         ctx.save_for_backward(x, base, mus, pool, gstate, *w)
         return q
@@ -487,3 +528,35 @@ def s2v_head_list_argmax(layout: GraphLayout, mu: torch.Tensor, head_weights, re
     _, _, q = _head_forward(layout, bool(norm_agg), mu, w)
     pos, node, val = list_argmax(layout, q, reach_ptr, reach_idx)
     return pos, node, val, q
+
+
+@torch.no_grad()
+def s2v_qnet_list_argmax(layout: GraphLayout, x: torch.Tensor, embed_weights, head_weights, T: int, reach_ptr, reach_idx,
+                         norm_agg: bool = True):
+    """Acting (comb_opt.py:297-331): node features -> greedy action per graph over its neighbour list, in ONE launch
+    for small problems (csrc/s2v_small.cu).  Returns (position in the list, node id, value) [B] each and q."""
+    ew = [_f32c(t.detach(), "parameter") for t in embed_weights]
+    hw = [_f32c(t.detach(), "parameter") for t in head_weights]
+    x = _f32c(x, "x")
+    _require_cuda(reach_ptr, "reach_ptr")
+    reach_ptr = reach_ptr.to(torch.int32).contiguous()
+    reach_idx = reach_idx.to(device=x.device, dtype=torch.int32).contiguous()
+    if qnet_small_eligible(layout, ew):
+        out = _qnet_small_forward(layout, int(T), x, ew, hw, bool(norm_agg), "list", None, reach_ptr, reach_idx)
+        return out[6], out[7], out[8], out[4]
+    _, mus = _embed_forward(layout, int(T), x, ew)
+    return s2v_head_list_argmax(layout, mus[int(T) - 1], hw, reach_ptr, reach_idx, norm_agg)
+
+
+@torch.no_grad()
+def s2v_qnet_forward(layout: GraphLayout, x: torch.Tensor, embed_weights, head_weights, T: int, norm_agg: bool = True):
+    """q [num_nodes] without autograd (QFunction.predict, comb_opt.py:297-307): one launch for small problems."""
+    ew = [_f32c(t.detach(), "parameter") for t in embed_weights]
+    hw = [_f32c(t.detach(), "parameter") for t in head_weights]
+    x = _f32c(x, "x")
+    if qnet_small_eligible(layout, ew):
+        return _qnet_small_forward(layout, int(T), x, ew, hw, bool(norm_agg), "q")[4]
+    _, mus = _embed_forward(layout, int(T), x, ew)
+    if head_fused_eligible(layout, hw):
+        return _head_fused_forward(layout, bool(norm_agg), mus[int(T) - 1], hw, "q")[2]
+    return _head_forward(layout, bool(norm_agg), mus[int(T) - 1], hw)[2]

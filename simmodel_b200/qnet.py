@@ -105,6 +105,13 @@ class QNet(nn.Module):
     def embed_graph(self, x: torch.Tensor, layout: GraphLayout) -> torch.Tensor:
         return ops.s2v_embed(layout, x, self.embed_weights(), self.T)
 
+    @torch.no_grad()
+    def greedy_actions_graph(self, x, layout, reach_ptr, reach_idx):
+        """Greedy action of every graph over its neighbour list (comb_opt.py:319-326): (position, node id, value).
+        Small problems: node MLP, T rounds, pool, Q head and the list arg-max are ONE launch (csrc/s2v_small.cu)."""
+        return ops.s2v_qnet_list_argmax(layout, x, self.embed_weights(), self.head_weights(), self.T, reach_ptr, reach_idx,
+                                        self.norm_agg)[:3]
+
     # -- reference contract ---------------------------------------------------------------
     def forward(self, xv, Ws, pyg_data):
         """xv f32[B,Npad,F], Ws f32[B,Npad,Npad] (0/1), pyg_data with .ptr/.batch
@@ -226,8 +233,7 @@ class QFunction:
         rptr = torch.tensor([0, reach.numel()], dtype=torch.int32, device=dev)
         with torch.no_grad():                   # embedding, then Q head + neighbour-list arg-max in ONE launch
             x, layout = m.prepare(state_tsr.to(dev).unsqueeze(0), None, pyg_batch)
-            mu = m.embed_graph(x, layout)
-            pos, node, val, _ = ops.s2v_head_list_argmax(layout, mu, m.head_weights(), rptr, reach, m.norm_agg)
+            pos, node, val = m.greedy_actions_graph(x, layout, rptr, reach)
         # one D2H copy; int ids and the fp32 value are exact in float64
         res = torch.stack((pos.to(torch.float64), node.to(torch.float64), val.to(torch.float64))).cpu().numpy()
         action, action_nodeselect = int(res[0, 0]), int(res[1, 0])
@@ -243,9 +249,7 @@ class QFunction:
         x f32[sum N, F], layout GraphLayout, reach_ptr i32[B+1], reach_idx i32 local node ids
         (ascending neighbour lists).  Returns device tensors (position in list, node id, value), each [B]."""
         m = self.model
-        mu = m.embed_graph(x, layout)
-        pos, node, val, _ = ops.s2v_head_list_argmax(layout, mu, m.head_weights(), reach_ptr, reach_idx, m.norm_agg)
-        return pos, node, val
+        return m.greedy_actions_graph(x, layout, reach_ptr, reach_idx)
 
     def batch_update(self, states_tsrs, Ws, pyg_data, actions, targets):
         """comb_opt.py:334-366."""

@@ -119,3 +119,54 @@ def test_ppo_calls_use_one_head_launch(cuda_device):
         fused = [nm for nm in names if "k_head_fused" in nm]
         apart = [nm for nm in names if any(k in nm for k in ("k_pool", "k_head<", "k_head_tc", "k_masked", "k_list_argmax"))]
         assert len(fused) == 1 and not apart, (fn.__name__, names)
+
+
+@pytest.mark.parametrize("topo_name,B,p", [("Manhattan5", 32, 64), ("MemTask", 50, 64), ("Manhattan3", 7, 64),
+                                           ("MemTask", 1, 16), ("Manhattan5", 1, 32)])
+def test_small_graph_single_launch_bit_identical(topo_name, B, p, cuda_device):
+    """One cooperative launch (csrc/s2v_small.cu) == per-stage launches, bit for bit: embeddings of every round, pool,
+    q, probabilities, arg-max; batched and replicated layouts; also when replayed from a CUDA graph."""
+    import simmodel_b200 as sb
+    from simmodel_b200 import ops
+    from oracle import s2v_ref as R
+    dev = cuda_device
+    topo = sb.graphs.load_topology(topo_name)
+    N, T = topo.num_nodes, 4
+    gen = torch.Generator().manual_seed(B + p)
+    x = sb.graphs.synth_nfm(topo, B, gen).reshape(-1, sb.graphs.NODE_DIM).to(dev)
+    P = R.make_qnet_params(sb.graphs.NODE_DIM, p, seed=p)
+    ew = [P[k + s].to(dev) for k in ops.EMBED_NAMES for s in (".weight", ".bias")]
+    hw = [P[k + s].to(dev) for k in ops.HEAD_NAMES for s in (".weight", ".bias")]
+    mask = (torch.rand(B * N, generator=gen) < 0.3).to(dev)
+    mask[::N] = True
+    m8 = ops._mask_u8(mask, B * N)
+    ptr = torch.arange(B + 1, dtype=torch.int64) * N
+    layouts = [sb.GraphLayout.replicated(topo.edge_index.to(dev), N, B, n_pad=N + 3),
+               sb.GraphLayout.from_batch(sb.graphs.batch_edge_index(topo, B, device=dev), ptr.to(dev), N + 3)]
+    big = sb.GraphLayout.replicated(sb.graphs.load_topology("NWB_AMS").edge_index.to(dev), 975, 2)
+    assert not ops.qnet_small_eligible(big, ew) and not ops.head_fused_eligible(big, hw)     # few large graphs: per-stage path
+    for lay in layouts:
+        assert ops.qnet_small_eligible(lay, ew)
+        base0, mus0 = ops._embed_forward(lay, T, x, ew)
+        pool0, g0, q0, prob0 = ops._head_fused_forward(lay, True, mus0[T - 1], hw, "softmax", m8)[:4]
+        arg0, val0 = ops._head_fused_forward(lay, True, mus0[T - 1], hw, "max", m8)[4::2]
+        base, mus, pool, gst, q, prob = ops._qnet_small_forward(lay, T, x, ew, hw, True, "softmax", m8)[:6]
+        for a, b in ((base, base0), (mus, mus0), (pool, pool0), (gst, g0), (q, q0), (prob, prob0)):
+            assert torch.equal(a, b)
+        out = ops._qnet_small_forward(lay, T, x, ew, hw, True, "max", m8)
+        assert torch.equal(out[6], arg0) and torch.equal(out[8], val0)
+        assert torch.equal(ops._qnet_small_forward(lay, T, x, ew, None, True, None)[1], mus0)
+    # CUDA-graph replay of the cooperative launch
+    lay = layouts[0]
+    side = torch.cuda.Stream()
+    side.wait_stream(torch.cuda.current_stream())
+    with torch.cuda.stream(side):
+        ops.s2v_qnet_forward(lay, x, ew, hw, T)
+    torch.cuda.current_stream().wait_stream(side)
+    graph = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(graph):
+        qg = ops.s2v_qnet_forward(lay, x, ew, hw, T)
+    qg.zero_()
+    graph.replay()
+    torch.cuda.synchronize()
+    assert torch.equal(qg, q0)
