@@ -160,6 +160,14 @@ int s2v_embed_backward(const s2v_graph_t* g, const s2v_embed_params_t* prm, cons
                        const float* base, const float* mus, const float* dmu, int32_t dmu_masked,
                        float* dus, void* workspace, int64_t workspace_bytes, float* grad, void* stream);
 
+/* The same with the gradient w.r.t. the node features: dx [num_nodes, F] out (NULL = not wanted).  Needed when a
+ * trainable module feeds x: lstm_type 'FE' runs an LSTM over the node features before the GNN
+ * (models_basic_lstm.py:442-444,473).  dx = dh theta1a with dh = (sum_t du^t theta1b) * [h > 0]; the last backward
+ * stage then runs on the CUDA cores (the tcgen05 variant does not keep dh). */
+int s2v_embed_backward_dx(const s2v_graph_t* g, const s2v_embed_params_t* prm, const float* x,
+                          const float* base, const float* mus, const float* dmu, int32_t dmu_masked,
+                          float* dus, void* workspace, int64_t workspace_bytes, float* grad, float* dx, void* stream);
+
 /* One propagation round alone (comb_opt.py:241-242): mu_next = relu(base + theta2 (W mu_prev)),
  * and one backward round: g = W^T du_t ; du_prev = (theta2^T g) * [mu_prev > 0] (the per-CTA
  * partial sums of dtheta2 land in workspace).  Used by unit tests and to time the dominant

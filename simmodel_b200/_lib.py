@@ -50,6 +50,7 @@ SIGNATURES = {
     "s2v_embed_forward": (C.c_int, [GP, EP, vp, vp, vp, vp]),
     "s2v_embed_backward_workspace_bytes": (i64, [i32, i32]),
     "s2v_embed_backward": (C.c_int, [GP, EP, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp]),
+    "s2v_embed_backward_dx": (C.c_int, [GP, EP, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp, vp]),
     "s2v_embed_round_forward": (C.c_int, [GP, i32, i32, vp, vp, vp, vp, vp]),
     "s2v_embed_round_backward": (C.c_int, [GP, i32, i32, i32, vp, vp, vp, vp, vp, i64, vp]),
     "s2v_debug_tc_gemm": (C.c_int, [i32, vp, vp, vp, i64, vp]),

@@ -100,7 +100,7 @@ template <int P>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_embed_final_bwd(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict__ x,
                   const float* __restrict__ dus, const float* __restrict__ du_last, int T,
-                  float* __restrict__ partial, int partial_stride, int num_tiles) {
+                  float* __restrict__ partial, int partial_stride, int num_tiles, float* __restrict__ dx) {
     using C = Cfg<P>;
     using EP = EmbedPartial<P>;
     extern __shared__ __align__(16) float smem[];
@@ -197,6 +197,14 @@ k_embed_final_bwd(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict
             }
         }
         __syncthreads();
+        if (dx != nullptr) {                   // gradient w.r.t. the node features (lstm_type 'FE': an LSTM feeds x): dx = dh theta1a
+            for (int e = t; e < rows * F; e += S2V_THREADS) {
+                const int r = e / F, f = e - r * F;
+                float s = 0.f;
+                for (int k = 0; k < P; ++k) s = fmaf(As[r * C::LDA + k], W1a[f * P + k], s);
+                dx[(size_t)row0 * F + e] = s;
+            }
+        }
 #pragma unroll
         for (int i = 0; i < MAXE; ++i) {
             int e = t + i * S2V_THREADS;
@@ -361,7 +369,7 @@ static int embed_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& pr
 template <int P>
 static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x,
                                const float* base, const float* mus, const float* dmu, int dmu_masked,
-                               float* dus, float* partial, float* grad, cudaStream_t st) {
+                               float* dus, float* partial, float* grad, float* dx, cudaStream_t st) {
     using C = Cfg<P>;
     using EP = EmbedPartial<P>;
     const int T = prm.rounds;
@@ -409,14 +417,14 @@ static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& p
                                                                       t != T, tiles);
         }
     }
-    if (use_tensor_path(P, prm.flags, g.num_nodes) && use_ws_bwd_round(prm.flags) && s2v_tc_final_backward_ws_ok(prm.node_dim)) {
+    if (dx == nullptr && use_tensor_path(P, prm.flags, g.num_nodes) && use_ws_bwd_round(prm.flags) && s2v_tc_final_backward_ws_ok(prm.node_dim)) {
         grid_f = s2v_tc_round_backward_ws_grid(g.num_nodes);
         S2V_RETURN_IF(s2v_tc_final_backward_ws(g, prm, x, dus, du_last, partial, stride, grid_f, st));
-    } else if (S2V_TENSOR_FINAL && use_tensor_path(P, prm.flags, g.num_nodes)) {
+    } else if (dx == nullptr && S2V_TENSOR_FINAL && use_tensor_path(P, prm.flags, g.num_nodes)) {
         grid_f = s2v_tc_final_backward_grid(g.num_nodes);
         S2V_RETURN_IF(s2v_tc_final_backward(g, prm, x, dus, du_last, partial, stride, grid_f, st));
     } else {
-        k_embed_final_bwd<P><<<grid_f, S2V_THREADS, smem_f, st>>>(g, prm, x, dus, du_last, T, partial, stride, tiles);
+        k_embed_final_bwd<P><<<grid_f, S2V_THREADS, smem_f, st>>>(g, prm, x, dus, du_last, T, partial, stride, tiles, dx);   // dx != NULL: CUDA-core last stage
     }
     if (T >= 2) s2v_reduce_partials(partial, stride, grid_r, EP::TH2, P * P, sums, st);
     s2v_reduce_partials(partial, stride, grid_f, EP::TH1B, stride - EP::TH1B, sums, st);
@@ -454,9 +462,19 @@ extern "C" int s2v_embed_forward(const s2v_graph_t* g, const s2v_embed_params_t*
     return 0;
 }
 
+extern "C" int s2v_embed_backward_dx(const s2v_graph_t* g, const s2v_embed_params_t* prm, const float* x,
+                                     const float* base, const float* mus, const float* dmu, int32_t dmu_masked,
+                                     float* dus, void* workspace, int64_t workspace_bytes, float* grad, float* dx, void* stream);
+
 extern "C" int s2v_embed_backward(const s2v_graph_t* g, const s2v_embed_params_t* prm, const float* x,
                                   const float* base, const float* mus, const float* dmu, int32_t dmu_masked,
                                   float* dus, void* workspace, int64_t workspace_bytes, float* grad, void* stream) {
+    return s2v_embed_backward_dx(g, prm, x, base, mus, dmu, dmu_masked, dus, workspace, workspace_bytes, grad, nullptr, stream);
+}
+
+extern "C" int s2v_embed_backward_dx(const s2v_graph_t* g, const s2v_embed_params_t* prm, const float* x,
+                                     const float* base, const float* mus, const float* dmu, int32_t dmu_masked,
+                                     float* dus, void* workspace, int64_t workspace_bytes, float* grad, float* dx, void* stream) {
     S2V_RETURN_IF(check_graph(g));
     if (!prm || !x || !mus || !dmu || !dus || !workspace || !grad || prm->rounds < 1) return S2V_ERR_BAD_ARG;
     if (prm->node_dim < 1 || prm->node_dim > S2V_MAX_F) return S2V_ERR_UNSUPPORTED;
@@ -466,7 +484,7 @@ extern "C" int s2v_embed_backward(const s2v_graph_t* g, const s2v_embed_params_t
         return (int)cudaMemsetAsync(grad, 0, s2v_embed_grad_floats(prm->node_dim, prm->emb_dim) * 4, st);
     }
     S2V_DISPATCH_P(prm->emb_dim, return embed_backward_impl<PP>(*g, *prm, x, base, mus, dmu, dmu_masked, dus,
-                                                                 (float*)workspace, grad, st));
+                                                                 (float*)workspace, grad, dx, st));
     return 0;
 }
 

@@ -104,7 +104,7 @@ def _qnet_small_forward(layout, T, x, ew, hw, norm_agg, mode, mask_u8=None, reac
     return base, mus, pool, gstate, q, prob, arg, node, val
 
 
-def _embed_backward(layout, T, x, w, base, mus, dmu, dmu_masked, dus=None, grad_out=None):
+def _embed_backward(layout, T, x, w, base, mus, dmu, dmu_masked, dus=None, grad_out=None, want_dx=False):
     L = _lib.lib()
     n, P, F = layout.num_nodes, int(w[0].shape[0]), int(w[0].shape[1])
     if dus is None:
@@ -112,11 +112,14 @@ def _embed_backward(layout, T, x, w, base, mus, dmu, dmu_masked, dus=None, grad_
     ws = torch.empty(L.s2v_embed_backward_workspace_bytes(F, P), dtype=torch.uint8, device=x.device)
     grad = grad_out if grad_out is not None else torch.empty(L.s2v_embed_grad_floats(F, P), dtype=torch.float32, device=x.device)
     prm = _embed_struct(T, w)
+    dx = torch.empty(n, F, dtype=torch.float32, device=x.device) if want_dx else None
     with torch.cuda.device(x.device):
-        _lib.check(L.s2v_embed_backward(C.byref(layout.c_struct()), C.byref(prm), _p(x), _p(base), _p(mus), _p(dmu),
-                                        int(dmu_masked), _p(dus), _p(ws), ws.numel(), _p(grad), _stream()),
+        _lib.check(L.s2v_embed_backward_dx(C.byref(layout.c_struct()), C.byref(prm), _p(x), _p(base), _p(mus), _p(dmu),
+                                           int(dmu_masked), _p(dus), _p(ws), ws.numel(), _p(grad), _p(dx), _stream()),
                    "s2v_embed_backward")
     _lib.launch_count += T + 3 + (0 if dmu_masked else 1)
+    if want_dx:
+        return _split_embed_grad(grad, F, P), grad, dx
     return _split_embed_grad(grad, F, P), grad
 
 
@@ -196,6 +199,9 @@ class _EmbedFn(torch.autograd.Function):
     @staticmethod
     def backward(ctx, dmu):
         x, base, mus, *w = ctx.saved_tensors
+        if ctx.needs_input_grad[2]:            # node features produced by a trainable module (lstm_type 'FE')
+            grads, _, dx = _embed_backward(ctx.layout, ctx.T, x, w, base, mus, _f32c(dmu, "dmu"), False, want_dx=True)
+            return (None, None, dx, *grads)
         grads, _ = _embed_backward(ctx.layout, ctx.T, x, w, base, mus, _f32c(dmu, "dmu"), False)
         return (None, None, None, *grads)
 
@@ -250,6 +256,10 @@ class _QNetFn(torch.autograd.Function):
         flat = torch.empty(ne + nh, dtype=torch.float32, device=x.device)
         _, hgrads, _ = _head_backward(layout, ctx.norm_agg, mus[T - 1], w[10:], pool, gstate, _f32c(dq, "dq"), True,
                                       dmu_out=dus[T - 1], grad_out=flat[ne:])
+        if ctx.needs_input_grad[3]:
+            egrads, _, dx = _embed_backward(layout, T, x, w[:10], base, mus, dus[T - 1], True, dus=dus, grad_out=flat[:ne],
+                                            want_dx=True)
+            return (None, None, None, dx, *egrads, *hgrads)
         egrads, _ = _embed_backward(layout, T, x, w[:10], base, mus, dus[T - 1], True, dus=dus, grad_out=flat[:ne])
         return (None, None, None, None, *egrads, *hgrads)
 
@@ -426,9 +436,7 @@ class _Ctx:
 # ----------------------------------------------------------------------------------
 def s2v_embed(layout: GraphLayout, x: torch.Tensor, embed_weights, T: int) -> torch.Tensor:
     """mu^T [num_nodes,p].  embed_weights: theta1a.w,b theta1b.w,b theta2.w,b theta3.w,b theta4.w,b."""
-    if x.requires_grad:
-        raise NotImplementedError("gradients w.r.t. node features are not part of the reference path")
-    return _EmbedFn.apply(layout, int(T), x, *embed_weights)
+    return _EmbedFn.apply(layout, int(T), x, *embed_weights)         # x.requires_grad (lstm_type 'FE'): dx comes back too
 
 
 def s2v_head(layout: GraphLayout, mu: torch.Tensor, head_weights, norm_agg: bool = True) -> torch.Tensor:
@@ -438,8 +446,6 @@ def s2v_head(layout: GraphLayout, mu: torch.Tensor, head_weights, norm_agg: bool
 
 def s2v_qnet(layout: GraphLayout, x: torch.Tensor, embed_weights, head_weights, T: int, norm_agg: bool = True):
     """Fused embedding + head: q [num_nodes] (QNet.forward, comb_opt.py:217-275)."""
-    if x.requires_grad:
-        raise NotImplementedError("gradients w.r.t. node features are not part of the reference path")
     return _QNetFn.apply(layout, int(T), bool(norm_agg), x, *embed_weights, *head_weights)
 
 

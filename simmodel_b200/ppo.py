@@ -233,11 +233,18 @@ class S2VKernelMixin:
         dev = self.device
         if dev.type != "cuda":
             raise S2VError("simmodel_b200.PPO_GNN_Single_LSTM runs on CUDA only (no CPU fallback)")
-        if self.config["lstm_type"] == "FE":
-            raise NotImplementedError("evaluate_rollouts covers lstm_type 'None' and 'EMB'")
         nfm, nfm_prime = nfm.to(dev), nfm_prime.to(dev)
         R, S, N, Fd = nfm.shape
         p = self.emb_dim
+        if self.config["lstm_type"] == "FE":
+            # the LSTM runs over the node FEATURES before the GNN (process_input, models_basic_lstm.py:473): s and s'
+            # are two sequences with their own initial states, so the shifted-sequence shortcut does not apply; the
+            # embedding backward returns dx and the LSTM trains through the kernels (s2v_embed_backward_dx)
+            def run_fe(m, hidden):                                             # (seq S, batch R*N, F), rollout-major batch
+                out, _ = self.lstm(m.permute(1, 0, 2, 3).reshape(S, R * N, Fd), hidden)
+                return out.view(S, R, N, Fd).permute(1, 0, 2, 3)
+            nfm, nfm_prime = run_fe(nfm, first_hidden), run_fe(nfm_prime, second_hidden)
+            prime_is_shift = False
         extra = nfm_prime[:, -1:] if prime_is_shift else nfm_prime
         allx = torch.cat((nfm, extra), dim=1)                                  # [R, S+1 | 2S, N, F]
         G = int(allx.shape[1])

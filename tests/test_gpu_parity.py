@@ -188,6 +188,49 @@ def test_ppo_golden(case, cuda_device):
     assert np.array_equal(arg.cpu().numpy(), G["out"]["greedy"])
 
 
+@pytest.mark.parametrize("case", golden_cases("ppofe"))
+def test_ppo_fe_golden(case, cuda_device):
+    """lstm_type 'FE' (an LSTM over the node features feeds the GNN, models_basic_lstm.py:442-444,473) against the
+    unmodified reference: pi, v, greedy action and ALL parameter gradients -- the LSTM's come through dx of the
+    embedding backward (s2v_embed_backward_dx).  The cuDNN LSTM is kept in full fp32."""
+    import types
+    import simmodel_b200 as sb
+    meta, G = load_golden(case)
+    dev = cuda_device
+    torch.backends.cudnn.allow_tf32 = False
+    torch.backends.cuda.matmul.allow_tf32 = False
+    config = {"lstm_type": "FE", "qnet": "s2v", "critic": meta["critic"], "emb_dim": meta["emb_dim"], "emb_iterT": meta["T"]}
+    hp = types.SimpleNamespace(node_dim=sb.graphs.NODE_DIM, emb_dim=meta["emb_dim"], parallel_rollouts=4, batch_size=2,
+                               learning_rate=1e-3)
+    model = sb.PPO_GNN_Single_LSTM(config, hp, {"base_checkpoint_path": None}, device=dev)
+    model.load_state_dict({k: torch.from_numpy(v) for k, v in G["P"].items()}, strict=True)
+    nfm = torch.from_numpy(G["inp"]["nfm"])
+    ei = torch.from_numpy(G["inp"]["edge_index"].astype(np.int64))
+    reach = torch.from_numpy(G["inp"]["reachable"])
+    hidden = (torch.from_numpy(G["inp"]["h0"]).to(dev), torch.from_numpy(G["inp"]["c0"]).to(dev))
+    prob, _ = model.pi(nfm, ei, reach, hidden)
+    v, _ = model.v(nfm, ei, reach, hidden)
+    tol = TOL                                # 1e-5 (or 2x the reference's own fp32 error) even with a cuDNN LSTM in front of the kernels
+    _check("prob", prob.detach().cpu().numpy(), G["out"]["prob"], G["out"]["prob_f64"], tol=tol)
+    _check("v", v.detach().cpu().numpy(), G["out"]["v"], G["out"]["v_f64"], tol=tol)
+    assert np.array_equal(prob.detach().cpu().numpy() == 0.0, G["out"]["prob"] == 0.0)
+    loss = (prob * torch.from_numpy(G["inp"]["wprob"]).to(dev)).sum() + (v * torch.from_numpy(G["inp"]["wv"]).to(dev)).sum()
+    loss.backward()
+    assert model.lstm.weight_ih_l0.grad is not None and float(model.lstm.weight_ih_l0.grad.abs().max()) > 0
+    for k, prm in model.named_parameters():
+        g = prm.grad.cpu().numpy() if prm.grad is not None else np.zeros(tuple(prm.shape), dtype=np.float32)
+        _check("grad " + k, g, G["grad"][k], G["grad64"][k], tol=tol, abs_floor=2e-7)
+    arg, _ = model.greedy_action(nfm, ei, reach, hidden)
+    assert np.array_equal(arg.cpu().numpy(), G["out"]["greedy"])
+    # batched rollouts: one rollout through evaluate_rollouts == the per-rollout calls (the FE LSTM runs inside)
+    S = meta["S"]
+    with torch.no_grad():
+        pi_b, v_s, v_p = model.evaluate_rollouts(nfm[None].to(dev), nfm[None].to(dev), ei, reach[None], reach[None],
+                                                 hidden, hidden)
+    assert float((pi_b[0] - prob.detach()).abs().max()) <= 1e-6 and float((v_s[0] - v.detach()).abs().max()) <= 1e-5 * _scale(v.detach().cpu().numpy())
+    assert torch.equal(v_s, v_p)
+
+
 @pytest.mark.parametrize("qnet,lstm,critic,shift", [("s2v", "None", "q", True), ("s2v", "EMB", "q", False),
                                                     ("gat2", "EMB", "q", True), ("s2v", "None", "v", False)])
 def test_ppo_evaluate_rollouts_equals_per_rollout_calls(qnet, lstm, critic, shift, cuda_device):
