@@ -36,12 +36,35 @@ def sources():
     return sorted(glob.glob(os.path.join(CSRC, "*.cu")))
 
 
+HASH_FILE = os.path.join(HERE, "libs2v_b200.srchash")
+
+
+def _deps():
+    return sorted(sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h")))
+
+
+def source_hash() -> str:
+    """sha256 over the names and contents of every source the library is built from (+ the compiler flags)."""
+    import hashlib
+    h = hashlib.sha256(" ".join(NVCC_FLAGS[:8]).encode())
+    for d in _deps():
+        h.update(os.path.basename(d).encode())
+        with open(d, "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()
+
+
 def stale() -> bool:
+    """True when libs2v_b200.so was not built from the sources in this tree.  Content-based (the hash build() records
+    next to the library), so a snapshot copied to another box with different file times is still recognised as fresh --
+    and a library left over from other sources is not."""
     if not os.path.exists(LIB):
         return True
+    if os.path.exists(HASH_FILE):
+        with open(HASH_FILE) as f:
+            return f.read().strip() != source_hash()
     t = os.path.getmtime(LIB)
-    deps = sources() + glob.glob(os.path.join(CSRC, "*.cuh")) + glob.glob(os.path.join(ROOT, "include", "*.h"))
-    return any(os.path.getmtime(d) > t for d in deps)
+    return any(os.path.getmtime(d) > t for d in _deps())
 
 
 def build(force: bool = False, verbose: bool = False) -> str:
@@ -68,6 +91,8 @@ def build(force: bool = False, verbose: bool = False) -> str:
         raise RuntimeError("nvcc failed")
     subprocess.check_call([_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
                                                                      "-Xcompiler", "-fPIC", "-lcudart"])
+    with open(HASH_FILE, "w") as f:
+        f.write(source_hash() + "\n")
     return LIB
 
 

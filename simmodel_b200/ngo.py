@@ -70,14 +70,20 @@ class FeatureExtractor(nn.Module):
         el = obs[:, node_dim * max_nodes: node_dim * max_nodes + 2 * max_edges].reshape(G, 2, max_edges)
         ei = el[egid, :, elocal].t().to(torch.int64) + ptr[egid]        # first num_edges columns, offset per graph
         layout = gat_layout_from_batch(ei.contiguous(), ptr, gid)
-        mu_raw = self.gat.forward_layout(x, layout)                      # (nodes_in_batch, emb_dim)
-        nodes_in_batch = total
-        num_nodes = torch.cat((n_dev.to(torch.float32), torch.zeros(nodes_in_batch - G, device=dev)))
-        splitval = nodes_in_batch // seq_len
-        decoupled_batch = gid[:splitval].repeat(seq_len).to(torch.float32)
-        num_nodes = num_nodes[:splitval].repeat(seq_len)
-        features = torch.cat((mu_raw, decoupled_batch[:, None], reachable[:, None], num_nodes[:, None]), dim=1)
-        return features.reshape(seq_len, nodes_in_batch // seq_len, self.emb_dim + 3), nodes_in_batch, None, num_nodes
+        emb = self.gat.forward_layout(x, layout)                        # [total, emb_dim]
+        # Feature rows = [embedding | graph id within one step | reachable flag | node-count column].  The reference
+        # fills the node-count column with the first rows-per-step entries of (per-graph node counts, zero padded to
+        # one entry per node) and tiles columns 2 and 4 over the steps (models_ngo.py:286-298); the consumers read
+        # only its first batch_size entries of step 0, the same values here.
+        per_step = total // seq_len
+        counts = torch.zeros(total, dtype=torch.float32, device=dev)
+        counts[:G] = n_dev
+        feat = torch.empty(seq_len, per_step, self.emb_dim + 3, dtype=torch.float32, device=dev)
+        feat[:, :, :self.emb_dim] = emb.view(seq_len, per_step, self.emb_dim)
+        feat[:, :, self.emb_dim] = gid[:per_step].to(torch.float32)
+        feat[:, :, self.emb_dim + 1] = reachable.view(seq_len, per_step)
+        feat[:, :, self.emb_dim + 2] = counts[:per_step]
+        return feat, total, None, counts[:per_step].repeat(seq_len)
 
 
 class _HeadBase(nn.Module):
@@ -100,18 +106,14 @@ class _HeadBase(nn.Module):
         reachable = reachable.squeeze(-1).bool()
         if self.hidden_cell is None or max_nodes * batch_size != self.hidden_cell[0].shape[1]:
             self.reset_init_state(max_nodes * batch_size, dev)
-        if terminal is not None:
-            terminal_dense = torch.repeat_interleave(terminal.to(torch.bool), torch.ones(batch_size, dtype=torch.int64) * max_nodes, dim=0)
-            assert self.hidden_cell[0][:, terminal_dense, :].sum() == 0
-            assert self.hidden_cell[1][:, terminal_dense, :].sum() == 0
+        if terminal is not None:                  # state slots of finished episodes must have been cleared by the caller
+            done_slots = terminal.to(torch.bool).reshape(batch_size, 1).expand(batch_size, max_nodes).reshape(-1)
+            for state in self.hidden_cell:
+                assert float(state[:, done_slots, :].abs().sum()) == 0
         sizes = num_nodes_list[0].squeeze(-1)[:batch_size].to(torch.int64)             # nodes per graph
         if self.lstm_on:
-            if selector is None:
-                sz = sizes.cpu().tolist()
-                sel = []
-                for i in range(batch_size):
-                    sel += [True] * int(sz[i]) + [False] * (max_nodes - int(sz[i]))
-                selector = torch.tensor(sel, dtype=torch.bool)
+            if selector is None:                  # slot b*max_nodes + i belongs to node i of graph b, i < its node count
+                selector = (torch.arange(max_nodes)[None, :] < sizes.cpu()[:, None]).reshape(-1)
             full_output, out_hc = self.lstm(mu_raw.contiguous(), (self.hidden_cell[0][:, selector, :], self.hidden_cell[1][:, selector, :]))
             self.hidden_cell[0][:, selector, :] = out_hc[0]
             self.hidden_cell[1][:, selector, :] = out_hc[1]

@@ -162,3 +162,34 @@ def test_ngo_mirror_state_dict_keys():
         assert list(pol.state_dict().keys()) == list(G["P"].keys())
         total, _ = pol.numTrainableParameters()
         assert total == sum(p.numel() for p in pol.parameters() if p.requires_grad)
+
+
+def test_torch_library_ops_registered_with_fake_impls():
+    """The kernels are dispatcher-level custom ops (namespace s2v_b200) with schemas and fake (meta) implementations:
+    shapes propagate without a GPU, which is what torch.compile / export need."""
+    import torch
+    import simmodel_b200 as sb
+    from torch._subclasses.fake_tensor import FakeTensorMode
+    for name in sb.torch_ops.OPS:
+        assert hasattr(torch.ops.s2v_b200, name), name
+    n, B, F, p, T, E = 50, 2, 7, 64, 5, 120
+    with FakeTensorMode():
+        i32 = dict(dtype=torch.int32)
+        x = torch.empty(n, F)
+        shapes = [(p, F), (p,), (p, p), (p,), (p, p), (p,), (p, p), (p,), (p, 1), (p,), (1, 2 * p), (1,), (p, p), (p,), (p, p), (p,)]
+        w = [torch.empty(s) for s in shapes]
+        rp, col = torch.empty(n + 1, **i32), torch.empty(E, **i32)
+        ptr, gid = torch.empty(B + 1, **i32), torch.empty(n, **i32)
+        q, base, mus, pool, gst = torch.ops.s2v_b200.qnet_fwd(x, w, T, True, rp, col, rp, col, torch.empty(n, **i32), ptr, gid, None,
+                                                             n, B, 0, 25)
+        assert q.shape == (n,) and base.shape == (n, p) and mus.shape == (T, n, p) and pool.shape == (B, p)
+        flat = torch.ops.s2v_b200.qnet_bwd(q, x, w, base, mus, pool, gst, T, True, rp, col, rp, col, torch.empty(n, **i32), ptr,
+                                           gid, None, n, B, 0, 25)
+        import math
+        assert flat.numel() == sum(math.prod(s) for s in shapes)
+        outs = torch.ops.s2v_b200.csr_build(torch.empty(2, E, dtype=torch.int64), n)
+        assert outs[0].shape == (n + 1,) and outs[1].shape == (E,)
+        prob = torch.ops.s2v_b200.masked_softmax(q, torch.empty(n, dtype=torch.bool), ptr, B, 0)
+        assert prob.shape == q.shape
+        arg, val = torch.ops.s2v_b200.masked_argmax(q, torch.empty(n, dtype=torch.bool), ptr, B, 0)
+        assert arg.shape == (B,) and arg.dtype == torch.int64

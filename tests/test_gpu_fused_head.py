@@ -170,3 +170,38 @@ def test_small_graph_single_launch_bit_identical(topo_name, B, p, cuda_device):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(qg, q0)
+
+
+def test_torch_library_ops_match_the_module_path(cuda_device):
+    """torch.ops.s2v_b200.qnet_fwd (+ registered autograd) == QNet.forward_graph, values and all 16 gradients, and the op
+    is traceable as one node by torch.compile(fullgraph=True) (eager backend: no code generation involved)."""
+    import simmodel_b200 as sb
+    from simmodel_b200 import torch_ops
+    dev = cuda_device
+    topo = sb.graphs.load_topology("NWB_UTR")
+    B, T = 6, 5
+    gen = torch.Generator().manual_seed(2)
+    x = sb.graphs.synth_nfm(topo, B, gen).reshape(-1, sb.graphs.NODE_DIM).to(dev)
+    torch.manual_seed(1)
+    net = sb.QNet({"emb_dim": 64, "emb_iter_T": T, "norm_agg": True, "node_dim": sb.graphs.NODE_DIM}, verbose=False).to(dev)
+    ptr = (torch.arange(B + 1) * topo.num_nodes).to(dev)
+    lay = sb.GraphLayout.from_batch(sb.graphs.batch_edge_index(topo, B, device=dev), ptr, topo.num_nodes)
+    wts = torch.randn(B * topo.num_nodes, generator=gen).to(dev)
+    q0 = net.forward_graph(x, lay)
+    (q0 * wts).sum().backward()
+    g0 = [p.grad.clone() for p in net.parameters()]
+    net.zero_grad()
+    weights = net.embed_weights() + net.head_weights()
+    q1 = torch_ops.qnet(x, weights, T, True, lay)
+    (q1 * wts).sum().backward()
+    assert torch.equal(q1, q0)
+    for a, p in zip(g0, net.parameters()):
+        assert torch.equal(a, p.grad)
+    rp, col, rpt, colt, indeg = torch.ops.s2v_b200.csr_build(sb.graphs.batch_edge_index(topo, B, device=dev), B * topo.num_nodes)
+    assert torch.equal(rp, lay.rowptr) and torch.equal(colt, lay.col_t)
+    mask = (torch.rand(B * topo.num_nodes, generator=gen) < 0.2).to(dev)
+    prob = torch.ops.s2v_b200.masked_softmax(q0.detach(), mask, lay.ptr, B, 0)
+    assert torch.equal(prob, sb.ops.masked_softmax(lay, q0.detach(), mask))
+    compiled = torch.compile(lambda xx: torch_ops.qnet(xx, weights, T, True, lay) * 2.0, backend="eager", fullgraph=True)
+    with torch.no_grad():
+        assert torch.equal(compiled(x), q0.detach() * 2.0)
