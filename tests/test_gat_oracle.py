@@ -95,3 +95,37 @@ def test_qnet_gatv2_mirror_keys_and_heads_fallback():
     assert [(c.heads, c.out_channels) for c in g.convs] == [(1, 30), (1, 30), (1, 15)]
     with pytest.raises(NotImplementedError):
         sb.GATv2Conv(7, 64, heads=4)                       # heads*channels > 128 is outside the kernels
+
+
+@pytest.mark.parametrize("case", golden_cases("gat_dqn") + [c for c in golden_cases("gat_ppo") if "checkpoint" not in c])
+def test_two_independent_gatv2_restatements_agree(case):
+    """oracle/gat_ref.py (PyG's edge-list / segment-softmax form) vs oracle/gat_dense_ref.py (the paper's formula on a
+    dense N x N neighbourhood matrix, written without reference to the first): the same embedding to fp64 rounding on
+    every golden input -- self-loop handling, attention direction, bias placement and multi-edge weighting included."""
+    from oracle import gat_dense_ref as D
+    meta, Z = load_golden(case)
+    P = {k: torch.from_numpy(v).double() for k, v in Z["P"].items()}
+    if "x" in Z["inp"]:
+        x = torch.from_numpy(Z["inp"]["x"]).double()
+        ei = torch.from_numpy(Z["inp"]["edge_index"].astype(np.int64))
+        layers = 5
+    else:
+        nfm = torch.from_numpy(Z["inp"]["nfm"])
+        bt = G.batch_from_data_list([G.Data(e, torch.from_numpy(Z["inp"]["edge_index"].astype(np.int64))) for e in nfm])
+        x, ei, layers = bt.x.double(), bt.edge_index, meta["T"]
+    a = G.gat_forward(P, x, ei, layers)
+    b = D.gat_forward_dense(P, x, ei, layers)
+    assert float((a - b).abs().max()) <= 1e-11 * float(a.abs().max())
+
+
+def test_dense_restatement_counts_multi_edges_and_ignores_given_self_loops():
+    from oracle import gat_dense_ref as D
+    ei = torch.tensor([[0, 0, 1, 2, 2, 3], [1, 1, 1, 0, 2, 0]])           # (0->1) twice, loops on 1 and 2
+    M = D.neighbourhood_matrix(ei, 4)
+    assert M.tolist() == [[1, 0, 1, 1], [2, 1, 0, 0], [0, 0, 1, 0], [0, 0, 0, 1]]
+    torch.manual_seed(0)
+    P = {"gat.convs.0." + k: v.double() for k, v in dict(att=torch.randn(1, 2, 4), bias=torch.randn(8), **{
+        "lin_l.weight": torch.randn(8, 3), "lin_l.bias": torch.randn(8), "lin_r.weight": torch.randn(8, 3),
+        "lin_r.bias": torch.randn(8)}).items()}
+    x = torch.randn(4, 3).double()
+    assert float((G.gat_forward(P, x, ei, 1) - D.gat_forward_dense(P, x, ei, 1)).abs().max()) <= 1e-12
