@@ -959,8 +959,9 @@ def measure_cpu_baseline():
     import torch
     cores = os.cpu_count() or 1
     torch.set_num_threads(cores)
-    step, gps, desc = cpu_reference_step_fn("dense", 2)
-    times = time_cpu(step, 3, 8.0)
+    dense_b = 2 if TOPO_SHAPES[TOPO][0] <= 1200 else 1          # the (B,N,N,p) tensor: 1.7 GB per ROT graph
+    step, gps, desc = cpu_reference_step_fn("dense", dense_b)
+    times = time_cpu(step, 3 if dense_b == 2 else 2, 8.0)
     dense = gps / statistics.mean(times)
     step2, gps2, desc2 = cpu_reference_step_fn("sparse", 64)
     times2 = time_cpu(step2, 3, 6.0)
