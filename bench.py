@@ -62,6 +62,9 @@ def parse():
     ap.add_argument("--ref-kind", default="dense", choices=["dense", "sparse"],
                     help="--impl reference: dense = the reference's own arithmetic (dense W, (B,N,N,p) theta4 tensor; B = 2 "
                          "graphs per step is what fits), sparse = the index_add restatement of the same math (B = 64 per step)")
+    ap.add_argument("--ppo-graph", action="store_true",
+                    help="ppo workload: capture one whole epoch (the per-rollout v(s'), v(s), pi(s) calls, loss, backward, Adam) "
+                         "in a CUDA graph after warm-up and time its replays -- same kernels, no per-launch host cost")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     return ap.parse_args()
@@ -815,6 +818,26 @@ def run_ppo(args):
     def step():
         return epoch_batched(resident_stacked) if args.ppo_batched else epoch(resident)
 
+    if args.ppo_graph:                      # whole-epoch capture: shapes, layouts and buffers are static across epochs
+        if world > 1:
+            raise SystemExit("--ppo-graph is a single-GPU option")
+        model.optimizer = torch.optim.Adam(model.parameters(), lr=hp.learning_rate, capturable=True)
+        eager_step = step
+        side = torch.cuda.Stream()
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):
+            for _ in range(3):
+                eager_step()
+        torch.cuda.current_stream().wait_stream(side)
+        cgraph = torch.cuda.CUDAGraph()
+        model.optimizer.zero_grad(set_to_none=True)
+        with torch.cuda.graph(cgraph):
+            graph_loss = eager_step()
+
+        def step():
+            cgraph.replay()
+            return graph_loss
+
     def step_e2e():
         if args.ppo_batched:
             return float(epoch_batched(stack([to_dev(b) for b in host])).detach())
@@ -839,14 +862,14 @@ def run_ppo(args):
         return float(ms_t.item())
     for _ in range(args.warmup):
         step()
-    launch_info = count_kernel_launches(step)
+    launch_info = count_kernel_launches(eager_step if args.ppo_graph else step)
     launches = launch_info["own"]
     sampler = ClockSampler(dev.index or 0)
     if rank == 0:
         sampler.start()
     ms = timed(step, args.steps, 0)
     clocks = sampler.stop() if rank == 0 else None
-    e2e_ms = None if args.no_e2e else timed(step_e2e, max(3, min(args.steps, 10)), 1)
+    e2e_ms = None if (args.no_e2e or args.ppo_graph) else timed(step_e2e, max(3, min(args.steps, 10)), 1)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline and args.qnet == "s2v":
         # the reference's arithmetic (dense W, (S,N,N,p) theta4 tensor; oracle/s2v_ref.py restating models_basic_lstm.py:479-566)
@@ -885,7 +908,8 @@ def run_ppo(args):
             "config": {"workload": "PPO-GNN-LSTM epoch (qnet %s, lstm %s 64, critic q) on %s (N=%d, E=%d): %s, loss, backward, Adam"
                                    % (args.qnet, args.ppo_lstm, TOPO, n_t, e_t,
                                       "evaluate_rollouts: one GNN pass over all rollouts (s' embedded once)" if args.ppo_batched
-                                      else "per rollout v(s'), v(s), pi(s) through pi()/v() (the reference's call pattern)"),
+                                      else "per rollout v(s'), v(s), pi(s) through pi()/v() (the reference's call pattern)")
+                                   + (" -- whole epoch replayed from a CUDA graph" if args.ppo_graph else ""),
                        "rollouts_per_gpu": R, "steps_per_rollout": S, "global_rollouts": R * world, "nodes_per_graph": n_t,
                        "parallelism": "dp%d (whole rollouts per rank)" % world,
                        "l2": "per rollout pass %d rows x 256 B = %.1f MB per plane; %d passes per epoch"

@@ -30,6 +30,8 @@ def configs(n):
         out.append(("c0 Manhattan5 B=32 DQN step", ["--topo", "Manhattan5", "--batch", "32", "--steps", "50", "--warmup", "10"]))
         out.append(("c1 PPO EMB MemTask R=4 S=50 (reference call pattern)", ["--workload", "ppo", "--topo", "MemTask", "--batch", "4",
                                                                               "--steps", "10", "--warmup", "3"]))
+        out.append(("c1 PPO EMB MemTask R=4 S=50 (reference call pattern, CUDA-graph replay)",
+                    ["--workload", "ppo", "--ppo-graph", "--topo", "MemTask", "--batch", "4", "--steps", "20", "--warmup", "3"]))
         out.append(("c1 PPO EMB MemTask R=64 S=50 (evaluate_rollouts)", ["--workload", "ppo", "--ppo-batched", "--topo", "MemTask",
                                                                          "--batch", "64", "--steps", "10", "--warmup", "3"]))
     out.append(("c3 PPO EMB AMS R=64 S=50 (evaluate_rollouts)", ["--workload", "ppo", "--ppo-batched", "--batch", "64", "--steps", "5",
@@ -90,8 +92,8 @@ def report(paths):
             print("| %s | %d | %.4g | %s | %.2f | %s | %s | %s | %s (%s) / %s |" % (
                 nm, r["n_gpus"], r["value"], r["unit"], r["ms_per_step"], e2e, eff, cbs, ck.get("sm_mhz"), ck.get("sm_max_mhz"),
                 ",".join(ck.get("reasons") or []) or "none"))
-    print("\nFull JSON lines: the `gpurun_out/config_matrix_n*.jsonl` files this table was made from are committed next to it "
-          "as `profiles/r02_config_matrix_n*.jsonl`.")
+    print("\nFull JSON lines: `profiles/r02_config_matrix_n{1,2,4,8}.jsonl` (copies of the `gpurun_out/config_matrix_n*.jsonl` "
+          "files this table was made from).")
 
 
 if __name__ == "__main__":
