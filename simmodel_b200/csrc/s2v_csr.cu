@@ -44,7 +44,7 @@ __global__ void k_csr_count(EdgeList L, int64_t n, int32_t* __restrict__ cnt_row
     for (int64_t e = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; e < E; e += (int64_t)gridDim.x * blockDim.x) {
         const int64_t off = edge_offset(L, e);
         int64_t s = edge_raw(L, 0, e) + off, d = edge_raw(L, 1, e) + off;
-        if (s < 0 || s >= n || d < 0 || d >= n) { atomicExch(err, 1); continue; }
+        if (s < 0 || s >= n || d < 0 || d >= n) { atomicOr(err, 1); continue; }
         atomicAdd(cnt_row + s, 1);
         atomicAdd(cnt_col + d, 1);
     }
@@ -138,12 +138,19 @@ __global__ void k_csr_fill(EdgeList L, int64_t n, const int32_t* __restrict__ ro
     }
 }
 
-// One thread per row: sort the edge ids of the bucket ascending (restores the input
-// order), then emit the other endpoint.  which = 1: emit ei[1][e] (row form), 0: ei[0][e].
+// One thread per row: sort the edge ids of the bucket ascending (restores the input order), then emit the other
+// endpoint.  which = 1: emit ei[1][e] (row form), 0: ei[0][e].  Rows with more than CSR_HEAVY entries (hubs, star
+// graphs) are left to k_csr_sort_emit_heavy: an insertion sort by one thread is quadratic in the degree.
+// Duplicate edges (the same (i, j) pair twice) are flagged in err bit 1: the reference builds W with to_dense_adj,
+// which SUMS duplicates into a weight of 2 (theta4 term relu(2 w4 + b4)), while a CSR would count the edge twice
+// (2 relu(w4 + b4)) -- the layout builders reject such input instead of diverging silently.
+#define CSR_HEAVY 32
+
 __global__ void k_csr_sort_emit(EdgeList L, int64_t n, const int32_t* __restrict__ ptr,
-                                int32_t* __restrict__ eid, int32_t* __restrict__ out, int which) {
+                                int32_t* __restrict__ eid, int32_t* __restrict__ out, int which, int32_t* __restrict__ err) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int beg = ptr[i], end = ptr[i + 1];
+        if (end - beg > CSR_HEAVY) continue;
         for (int a = beg + 1; a < end; ++a) {
             int32_t key = eid[a];
             int b = a - 1;
@@ -154,6 +161,63 @@ __global__ void k_csr_sort_emit(EdgeList L, int64_t n, const int32_t* __restrict
             const int64_t e = eid[a];
             out[a] = (int32_t)(edge_raw(L, which, e) + edge_offset(L, e));
         }
+        if (which) {
+            bool dup = false;
+            for (int a = beg + 1; a < end; ++a)
+                for (int b = beg; b < a; ++b) dup |= out[a] == out[b];
+            if (dup) atomicOr(err, 2);
+        }
+    }
+}
+
+// Heavy rows: one CTA per row, bitonic sort of the edge ids in a power-of-two scratch segment (padded with INT_MAX),
+// O(d log^2 d / threads).  scratch: 2 * E ints; row i uses [2 * ptr[i], 2 * ptr[i] + n2).  Duplicate detection sorts
+// the emitted endpoints the same way and compares neighbours.
+__device__ void cta_bitonic_sort(int32_t* a, int n2) {
+    for (int k = 2; k <= n2; k <<= 1)
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int i = threadIdx.x; i < n2; i += blockDim.x) {
+                const int l = i ^ j;
+                if (l > i) {
+                    const int32_t x = a[i], y = a[l];
+                    if ((x > y) == ((i & k) == 0)) { a[i] = y; a[l] = x; }
+                }
+            }
+            __syncthreads();
+        }
+}
+
+__global__ void __launch_bounds__(256)
+k_csr_sort_emit_heavy(EdgeList L, int64_t n, const int32_t* __restrict__ ptr, int32_t* __restrict__ eid,
+                      int32_t* __restrict__ out, int which, int32_t* __restrict__ scratch, int32_t* __restrict__ err) {
+    __shared__ int dup_s;
+    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const int beg = ptr[i], end = ptr[i + 1], d = end - beg;
+        if (d <= CSR_HEAVY) continue;
+        int n2 = 1;
+        while (n2 < d) n2 <<= 1;
+        int32_t* sc = scratch + 2 * (int64_t)beg;
+        for (int k = threadIdx.x; k < n2; k += blockDim.x) sc[k] = k < d ? eid[beg + k] : INT32_MAX;
+        if (threadIdx.x == 0) dup_s = 0;
+        __syncthreads();
+        cta_bitonic_sort(sc, n2);
+        for (int k = threadIdx.x; k < d; k += blockDim.x) {
+            const int64_t e = sc[k];
+            eid[beg + k] = (int32_t)e;
+            out[beg + k] = (int32_t)(edge_raw(L, which, e) + edge_offset(L, e));
+        }
+        __syncthreads();
+        if (which) {
+            for (int k = threadIdx.x; k < n2; k += blockDim.x) sc[k] = k < d ? out[beg + k] : INT32_MAX;
+            __syncthreads();
+            cta_bitonic_sort(sc, n2);
+            int dup = 0;
+            for (int k = threadIdx.x + 1; k < d; k += blockDim.x) dup |= sc[k] == sc[k - 1];
+            if (dup) dup_s = 1;
+            __syncthreads();
+            if (threadIdx.x == 0 && dup_s) atomicOr(err, 2);
+        }
+        __syncthreads();
     }
 }
 
@@ -167,10 +231,12 @@ __global__ void k_csr_map(const int32_t* __restrict__ eid_row, const int32_t* __
 
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
-// workspace layout (int32): err[64] | cnt_row[n] | cnt_col[n] | eid_row[E] | eid_col[E] | block_sums[nb+1] x2 | totals[2]
+// workspace layout (int32): err[64] | cnt_row[n] | cnt_col[n] | eid_row[E] | eid_col[E] | block_sums[nb+1] x2 | totals[64]
+//                           | heavy-row sort scratch [2E]
+// err[0]: bit 0 = node id out of range, bit 1 = duplicate edge
 extern "C" int64_t s2v_csr_workspace_bytes(int64_t n, int64_t E) {
     int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1;
-    return (64 + align_up(n, 64) * 2 + align_up(E, 64) * 2 + align_up(nb, 64) * 2 + 64) * 4;
+    return (64 + align_up(n, 64) * 2 + align_up(E, 64) * 2 + align_up(nb, 64) * 2 + 64 + 2 * align_up(E, 64)) * 4;
 }
 
 // Entry k of row i (edge i -> col[k]) is entry row_to_col[k] of column col[k] in the transposed form.  Needs the
@@ -219,6 +285,7 @@ static int csr_build_impl(const EdgeList& L, int64_t n,
     int32_t* bs_row = eid_col + align_up(E, 64);
     int32_t* bs_col = bs_row + align_up(nb, 64);
     int32_t* totals = bs_col + align_up(nb, 64);
+    int32_t* heavy_scratch = totals + 64;
     S2V_RETURN_IF(cudaMemsetAsync(w, 0, (64 + align_up(n, 64) * 2) * 4, st));
     int eb = (int)((E + 255) / 256);
     if (eb > 148 * 32) eb = 148 * 32;
@@ -233,8 +300,12 @@ static int csr_build_impl(const EdgeList& L, int64_t n,
     if (E > 0) {
         S2V_RETURN_IF(cudaMemsetAsync(cnt_row, 0, align_up(n, 64) * 2 * 4, st));
         k_csr_fill<<<eb, 256, 0, st>>>(L, n, rowptr, rowptr_t, cnt_row, cnt_col, eid_row, eid_col);
-        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr, eid_row, col, 1);
-        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr_t, eid_col, col_t, 0);
+        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr, eid_row, col, 1, err);
+        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr_t, eid_col, col_t, 0, err);
+        int hb = (int)(n < 148 * 8 ? n : 148 * 8);            // hubs: rows / columns with more than CSR_HEAVY entries
+        if (hb < 1) hb = 1;
+        k_csr_sort_emit_heavy<<<hb, 256, 0, st>>>(L, n, rowptr, eid_row, col, 1, heavy_scratch, err);
+        k_csr_sort_emit_heavy<<<hb, 256, 0, st>>>(L, n, rowptr_t, eid_col, col_t, 0, heavy_scratch, err);
     }
     return (int)cudaGetLastError();
 }

@@ -107,9 +107,15 @@ class GraphLayout:
                 _lib.check(L.s2v_csr_build_local(_p(ei), ei.element_size(), E, n, _p(eptr), _p(nptr), nb, _p(rowptr), _p(col),
                                                  _p(rowptr_t), _p(col_t), _p(indeg), _p(ws), ws.numel(), _stream()),
                            "s2v_csr_build_local")
-        _lib.launch_count += 10 if E > 0 else 6
-        if validate and int(ws[:4].view(torch.int32).item()) != 0:
-            raise ValueError("edge_index contains node ids outside [0, %d)" % n)
+        _lib.launch_count += 12 if E > 0 else 6
+        if validate:
+            flags = int(ws[:4].view(torch.int32).item())
+            if flags & 1:
+                raise ValueError("edge_index contains node ids outside [0, %d)" % n)
+            if flags & 2:
+                raise ValueError("edge_index contains duplicate edges: the reference sums them into a weighted adjacency "
+                                 "(to_dense_adj, models_basic_lstm.py:515), which this path does not implement -- coalesce "
+                                 "the edge list first")
         if edge_map:
             r2c = torch.empty(E, dtype=torch.int32, device=dev)
             scratch = torch.empty(E, dtype=torch.int32, device=dev)

@@ -265,3 +265,36 @@ def test_two_gpu_step_equals_single_gpu_global_batch(cuda_device, tmp_path):
     torch.nn.SmoothL1Loss()(q[sel], targets.to(dev)).backward()
     ref = torch.cat([p.grad.reshape(-1) for p in net.parameters()]).cpu()
     assert float((f0 - ref).abs().max()) <= 1e-6 * float(ref.abs().max())
+
+
+def test_csr_hub_rows_and_duplicate_edges(cuda_device):
+    """A star graph with a 50 000-degree hub (both directions: one heavy row and one heavy column) builds the same CSR as
+    the stable-sort oracle, in bounded time (CTA bitonic sort for rows with more than 32 entries); duplicate edges --
+    which the reference would SUM into a weight of 2 (to_dense_adj) -- are rejected, for light and for heavy rows."""
+    import time
+    import simmodel_b200 as sb
+    from oracle import s2v_ref as R
+    dev = cuda_device
+    n = 50001
+    rng = np.random.default_rng(0)
+    leaves = np.arange(1, n)
+    star = np.concatenate([np.stack([np.zeros(n - 1, dtype=np.int64), leaves]), np.stack([leaves, np.zeros(n - 1, dtype=np.int64)])], axis=1)
+    extra = np.stack([rng.integers(1, n, 5000), rng.integers(1, n, 5000)])
+    extra = extra[:, extra[0] != extra[1]]
+    ei = np.concatenate([star, extra], axis=1)
+    ei = np.unique(ei, axis=1)                                   # no duplicates
+    ei = ei[:, rng.permutation(ei.shape[1])]                     # arbitrary input order: the CSR must keep it per row
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rowptr, col, rowptr_t, col_t, indeg = sb.GraphLayout.build_csr(torch.from_numpy(ei).to(dev), n)
+    torch.cuda.synchronize()
+    assert time.perf_counter() - t0 < 5.0
+    ref = R.csr_from_edge_index(ei, n)
+    for got, want in zip((rowptr, col, rowptr_t, col_t, indeg), ref):
+        assert np.array_equal(got.cpu().numpy(), want)
+    dup_light = np.concatenate([ei, np.array([[7], [9]]), np.array([[7], [9]])], axis=1)
+    with pytest.raises(ValueError, match="duplicate"):
+        sb.GraphLayout.build_csr(torch.from_numpy(dup_light).to(dev), n)
+    dup_heavy = np.concatenate([ei, ei[:, ei[0] == 0][:, :1]], axis=1)      # a second copy of one hub edge
+    with pytest.raises(ValueError, match="duplicate"):
+        sb.GraphLayout.build_csr(torch.from_numpy(dup_heavy).to(dev), n)
