@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2V_ABI_VERSION 3
+#define S2V_ABI_VERSION 4
 
 #define S2V_ERR_BAD_ARG        (-1)  /* null pointer / negative size / inconsistent sizes     */
 #define S2V_ERR_UNSUPPORTED    (-2)  /* emb_dim not in {8,16,24,32,48,64}, node_dim > 32; GAT: heads*channels > 128 */

@@ -101,7 +101,7 @@ def lib():
                     fn = getattr(handle, name)
                     fn.restype = res
                     fn.argtypes = args
-                if handle.s2v_abi_version() != 3:
+                if handle.s2v_abi_version() != 4:
                     raise S2VError("simmodel_b200: ABI version mismatch")
                 _lib = handle
     return _lib
