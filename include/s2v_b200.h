@@ -320,6 +320,18 @@ int s2v_gat_attn_backward(const s2v_graph_t* g, int32_t heads, int32_t channels,
  *   s2v_rows_reduce64 : out[64 ab, 64] = A[n, 64 ab]^T B[n, 64]  (weight gradient; ab = 2), per-CTA partials in
  *        workspace summed in fixed order.
  * --------------------------------------------------------------------------------- */
+/* General form (ABI 4): every lin_l / lin_r of the configurations the reference ships -- QNet_GATv2 (in 7 | 64, 2 x 32) and
+ * PPO_GNN_Single_LSTM(qnet='gat2') (in 7 | 128, hidden 128 = 4 x 32, out 64 = 4 x 16; models_basic_lstm.py:418-422,
+ * ppo_custom.py:256-257) -- runs on the tcgen05 kernels, no library GEMM left:
+ *   s2v_rows_linear : out[n, m] = A[n, k] W^T (W [m, k] row stride ldw, transpose_w = 0) or A[n, k] W (W [k, m],
+ *        transpose_w = 1), optionally * (mask > 0); k <= 256 of any value (the F = 7 input layer is zero padded), m a
+ *        multiple of 64 <= 256.  Planned as passes of <= 128 output x <= 128 contraction columns; K passes accumulate.
+ *   s2v_rows_outer  : out[m, k] = A[n, m]^T B[n, k] (dW = dY^T X), m a multiple of 64 <= 256, k <= 128 (ragged allowed);
+ *        workspace as s2v_rows_reduce64. */
+int s2v_rows_linear(const float* A, int32_t lda, int32_t k, const float* W, int32_t ldw, int32_t m, int32_t transpose_w,
+                    const float* mask, int32_t ldm, float* out, int32_t ldo, int64_t n, void* stream);
+int s2v_rows_outer(const float* A, int32_t lda, int32_t m, const float* B, int32_t ldb, int32_t k, float* out, int32_t ldo,
+                   void* workspace, int64_t workspace_bytes, int64_t n, void* stream);
 int s2v_rows_gemm64(const float* A, int32_t lda, int32_t k_blocks, const float* W, int32_t n_blocks, int32_t transpose_w,
                     const float* mask, int32_t ldm, float* out, int32_t ldo, int64_t n, void* stream);
 int64_t s2v_rows_reduce64_workspace_bytes(int32_t a_blocks);

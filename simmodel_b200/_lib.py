@@ -73,6 +73,8 @@ SIGNATURES = {
     "s2v_gat_edge_floats": (i64, [GP, i32]),
     "s2v_gat_uses_edge_alpha": (C.c_int, [i32, i32, i32]),
     "s2v_gat_attn_backward_workspace_bytes": (i64, [i32, i32, i64]),
+    "s2v_rows_linear": (C.c_int, [vp, i32, i32, vp, i32, i32, i32, vp, i32, vp, i32, i64, vp]),
+    "s2v_rows_outer": (C.c_int, [vp, i32, i32, vp, i32, i32, vp, i32, vp, i64, i64, vp]),
     "s2v_rows_gemm64": (C.c_int, [vp, i32, i32, vp, i32, i32, vp, i32, vp, i32, i64, vp]),
     "s2v_rows_reduce64_workspace_bytes": (i64, [i32]),
     "s2v_rows_reduce64": (C.c_int, [vp, i32, i32, vp, i32, vp, vp, i64, i64, vp]),

@@ -147,10 +147,14 @@ __global__ void k_csr_fill(EdgeList L, int64_t n, const int32_t* __restrict__ ro
 #define CSR_HEAVY 32
 
 __global__ void k_csr_sort_emit(EdgeList L, int64_t n, const int32_t* __restrict__ ptr,
-                                int32_t* __restrict__ eid, int32_t* __restrict__ out, int which, int32_t* __restrict__ err) {
+                                int32_t* __restrict__ eid, int32_t* __restrict__ out, int which, int32_t* __restrict__ err,
+                                int32_t* __restrict__ heavy_count, int32_t* __restrict__ heavy_list) {
     for (int64_t i = blockIdx.x * (int64_t)blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
         int beg = ptr[i], end = ptr[i + 1];
-        if (end - beg > CSR_HEAVY) continue;
+        if (end - beg > CSR_HEAVY) {            // left to k_csr_sort_emit_heavy (list order is irrelevant: one CTA per row)
+            heavy_list[atomicAdd(heavy_count, 1)] = (int32_t)i;
+            continue;
+        }
         for (int a = beg + 1; a < end; ++a) {
             int32_t key = eid[a];
             int b = a - 1;
@@ -188,12 +192,14 @@ __device__ void cta_bitonic_sort(int32_t* a, int n2) {
 }
 
 __global__ void __launch_bounds__(256)
-k_csr_sort_emit_heavy(EdgeList L, int64_t n, const int32_t* __restrict__ ptr, int32_t* __restrict__ eid,
-                      int32_t* __restrict__ out, int which, int32_t* __restrict__ scratch, int32_t* __restrict__ err) {
+k_csr_sort_emit_heavy(EdgeList L, const int32_t* __restrict__ ptr, int32_t* __restrict__ eid,
+                      int32_t* __restrict__ out, int which, int32_t* __restrict__ scratch, int32_t* __restrict__ err,
+                      const int32_t* __restrict__ heavy_count, const int32_t* __restrict__ heavy_list) {
     __shared__ int dup_s;
-    for (int64_t i = blockIdx.x; i < n; i += gridDim.x) {
+    const int count = *heavy_count;             // rows listed by k_csr_sort_emit (usually none: the kernel exits at once)
+    for (int idx = blockIdx.x; idx < count; idx += gridDim.x) {
+        const int64_t i = heavy_list[idx];
         const int beg = ptr[i], end = ptr[i + 1], d = end - beg;
-        if (d <= CSR_HEAVY) continue;
         int n2 = 1;
         while (n2 < d) n2 <<= 1;
         int32_t* sc = scratch + 2 * (int64_t)beg;
@@ -232,11 +238,12 @@ __global__ void k_csr_map(const int32_t* __restrict__ eid_row, const int32_t* __
 static inline int64_t align_up(int64_t v, int64_t a) { return (v + a - 1) / a * a; }
 
 // workspace layout (int32): err[64] | cnt_row[n] | cnt_col[n] | eid_row[E] | eid_col[E] | block_sums[nb+1] x2 | totals[64]
-//                           | heavy-row sort scratch [2E]
-// err[0]: bit 0 = node id out of range, bit 1 = duplicate edge
+//                           | heavy-row sort scratch [2E] | heavy-row lists [E/32 + 64] x2
+// err[0]: bit 0 = node id out of range, bit 1 = duplicate edge; err[1], err[2]: number of heavy rows / columns
 extern "C" int64_t s2v_csr_workspace_bytes(int64_t n, int64_t E) {
     int64_t nb = (n + SCAN_BLOCK - 1) / SCAN_BLOCK + 1;
-    return (64 + align_up(n, 64) * 2 + align_up(E, 64) * 2 + align_up(nb, 64) * 2 + 64 + 2 * align_up(E, 64)) * 4;
+    return (64 + align_up(n, 64) * 2 + align_up(E, 64) * 2 + align_up(nb, 64) * 2 + 64 + 2 * align_up(E, 64) +
+            2 * align_up(E / 32 + 64, 64)) * 4;
 }
 
 // Entry k of row i (edge i -> col[k]) is entry row_to_col[k] of column col[k] in the transposed form.  Needs the
@@ -286,6 +293,8 @@ static int csr_build_impl(const EdgeList& L, int64_t n,
     int32_t* bs_col = bs_row + align_up(nb, 64);
     int32_t* totals = bs_col + align_up(nb, 64);
     int32_t* heavy_scratch = totals + 64;
+    int32_t* heavy_rows = heavy_scratch + 2 * align_up(E, 64);
+    int32_t* heavy_cols = heavy_rows + align_up(E / 32 + 64, 64);
     S2V_RETURN_IF(cudaMemsetAsync(w, 0, (64 + align_up(n, 64) * 2) * 4, st));
     int eb = (int)((E + 255) / 256);
     if (eb > 148 * 32) eb = 148 * 32;
@@ -300,12 +309,11 @@ static int csr_build_impl(const EdgeList& L, int64_t n,
     if (E > 0) {
         S2V_RETURN_IF(cudaMemsetAsync(cnt_row, 0, align_up(n, 64) * 2 * 4, st));
         k_csr_fill<<<eb, 256, 0, st>>>(L, n, rowptr, rowptr_t, cnt_row, cnt_col, eid_row, eid_col);
-        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr, eid_row, col, 1, err);
-        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr_t, eid_col, col_t, 0, err);
-        int hb = (int)(n < 148 * 8 ? n : 148 * 8);            // hubs: rows / columns with more than CSR_HEAVY entries
-        if (hb < 1) hb = 1;
-        k_csr_sort_emit_heavy<<<hb, 256, 0, st>>>(L, n, rowptr, eid_row, col, 1, heavy_scratch, err);
-        k_csr_sort_emit_heavy<<<hb, 256, 0, st>>>(L, n, rowptr_t, eid_col, col_t, 0, heavy_scratch, err);
+        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr, eid_row, col, 1, err, err + 1, heavy_rows);
+        k_csr_sort_emit<<<rb, 128, 0, st>>>(L, n, rowptr_t, eid_col, col_t, 0, err, err + 2, heavy_cols);
+        // hubs: rows / columns with more than CSR_HEAVY entries, one CTA each (the kernels exit at once when there are none)
+        k_csr_sort_emit_heavy<<<148, 256, 0, st>>>(L, rowptr, eid_row, col, 1, heavy_scratch, err, err + 1, heavy_rows);
+        k_csr_sort_emit_heavy<<<148, 256, 0, st>>>(L, rowptr_t, eid_col, col_t, 0, heavy_scratch, err, err + 2, heavy_cols);
     }
     return (int)cudaGetLastError();
 }

@@ -1798,10 +1798,37 @@ __device__ __forceinline__ void issue_transform16_acc(uint32_t d_tmem, uint32_t 
     }
 }
 
+// Generalised operands (r02): A / mask / out are column windows of wider row-major matrices, the weight block is a
+// window of W (either orientation), K may be ragged (the F = 7 input layer: rows read with scalar loads, zero padded to
+// 64), the output may accumulate (a 256-long contraction runs as two passes of 128).
+struct RowsGemmArgs {
+    const float* A; int lda, a_col0, k_valid;          // A[:, a_col0 .. a_col0 + k_valid), k_valid <= 64 KB
+    const float* W; int ldw, w_row0, w_col0, transpose_w, w_n_valid;
+    //   transpose_w = 0: tile(nb, kb)(n, k) = W[w_row0 + 64 nb + n][w_col0 + 64 kb + k]      (out = A W^T)
+    //   transpose_w = 1: tile(nb, kb)(n, k) = W[w_row0 + 64 kb + k][w_col0 + 64 nb + n]      (out = A W)
+    const float* M; int ldm, m_col0;                   // optional mask window (same columns as out)
+    float* out; int ldo, o_col0;                       // out[:, o_col0 .. o_col0 + 64 NB)
+    int accumulate, n, num_tiles;
+};
+
+__device__ __forceinline__ void load_weight_tiles16g(uint8_t* t1, const RowsGemmArgs& a, int nb, int kb, int nthreads) {
+    for (int e = threadIdx.x; e < 64 * 16; e += nthreads) {
+        const int nrow = e >> 4, c4 = e & 15;
+        float v[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int k = 64 * kb + 4 * c4 + j, nn = 64 * nb + nrow;
+            const bool ok = k < a.k_valid && nn < a.w_n_valid;
+            v[j] = !ok ? 0.f : (a.transpose_w ? __ldg(a.W + (size_t)(a.w_row0 + k) * a.ldw + a.w_col0 + nn)
+                                              : __ldg(a.W + (size_t)(a.w_row0 + nn) * a.ldw + a.w_col0 + k));
+        }
+        store_split3(t1, nrow, c4, make_float4(v[0], v[1], v[2], v[3]));
+    }
+}
+
 template <int KB, int NB, bool MASK>
 __global__ void __launch_bounds__(TC_THREADS)
-k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W, int transpose_w,
-              const float* __restrict__ M, int ldm, float* __restrict__ out, int ldo, int n, int num_tiles) {
+k_rows_gemm16(RowsGemmArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* w1 = smem;                                   // NB x KB weight blocks, three bf16 tiles each
@@ -1809,12 +1836,11 @@ k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W,
     TcShared* sh = reinterpret_cast<TcShared*>(a1 + KB * TILE16X3);
     float* stg = reinterpret_cast<float*>(a1);
     const int t = threadIdx.x, warp = t >> 5;
+    const int n = a.n, num_tiles = a.num_tiles;
     if (warp == 0) tc::tmem_alloc<64 * NB>(&sh->tmem_base);
     if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
     for (int nb = 0; nb < NB; ++nb)
-        for (int kb = 0; kb < KB; ++kb)                    // W is [64 NB, 64] (forward) or [64 KB, 64] (transposed use)
-            load_weight_tiles16(w1 + (nb * KB + kb) * TILE16X3, W + (size_t)(transpose_w ? kb : nb) * 64 * 64, transpose_w != 0,
-                                TC_THREADS);
+        for (int kb = 0; kb < KB; ++kb) load_weight_tiles16g(w1 + (nb * KB + kb) * TILE16X3, a, nb, kb, TC_THREADS);
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -1822,6 +1848,8 @@ k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W,
     const uint32_t d = sh->tmem_base;
     const uint32_t s_a = tc::smem_u32(a1), s_w = tc::smem_u32(w1);
     uint32_t phase = 0;
+    // vector loads when the window is 16-byte aligned and complete, scalar + zero padding otherwise (F = 7)
+    const bool a_vec = a.k_valid == 64 * KB && (a.lda & 3) == 0 && (a.a_col0 & 3) == 0 && ((uintptr_t)a.A & 15) == 0;
     float4 m[KB][8];
     auto load_rows = [&](int tile) {
         const int row0 = tile * TCR, rows = min(TCR, n - row0);
@@ -1830,7 +1858,19 @@ k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W,
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
                 const int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
-                m[kb][i] = rl < rows ? ldg4(A + (size_t)(row0 + rl) * lda + 64 * kb + 4 * c4) : f4zero();
+                float4 v = f4zero();
+                if (rl < rows) {
+                    const float* src = a.A + (size_t)(row0 + rl) * a.lda + a.a_col0 + 64 * kb + 4 * c4;
+                    if (a_vec) v = ldg4(src);
+                    else {
+                        const int k0 = 64 * kb + 4 * c4;
+                        if (k0 < a.k_valid) v.x = __ldg(src);
+                        if (k0 + 1 < a.k_valid) v.y = __ldg(src + 1);
+                        if (k0 + 2 < a.k_valid) v.z = __ldg(src + 2);
+                        if (k0 + 3 < a.k_valid) v.w = __ldg(src + 3);
+                    }
+                }
+                m[kb][i] = v;
             }
     };
     if (blockIdx.x < num_tiles) load_rows(blockIdx.x);
@@ -1862,7 +1902,7 @@ k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W,
 #pragma unroll
                 for (int i = 0; i < 8; ++i) {
                     const int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
-                    mk[nb][i] = rl < rows ? ldg4(M + (size_t)(row0 + rl) * ldm + 64 * nb + 4 * c4) : f4zero();
+                    mk[nb][i] = rl < rows ? ldg4(a.M + (size_t)(row0 + rl) * a.ldm + a.m_col0 + 64 * nb + 4 * c4) : f4zero();
                 }
         }
         if (tile + (int)gridDim.x < num_tiles) load_rows(tile + gridDim.x);      // in flight during the MMAs and the epilogue
@@ -1879,11 +1919,13 @@ k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W,
                 const int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
                 if (rl < rows) {
                     float4 v = ld4(stg + rl * STG_LD + 4 * c4);
+                    float* dst = a.out + (size_t)(row0 + rl) * a.ldo + a.o_col0 + 64 * nb + 4 * c4;
+                    if (a.accumulate) v = f4add(ld4(dst), v);
                     if (MASK) {
                         const float4 k4 = mk[nb][i];
                         v = make_float4(k4.x > 0.f ? v.x : 0.f, k4.y > 0.f ? v.y : 0.f, k4.z > 0.f ? v.z : 0.f, k4.w > 0.f ? v.w : 0.f);
                     }
-                    st4(out + (size_t)(row0 + rl) * ldo + 64 * nb + 4 * c4, v);
+                    st4(dst, v);
                 }
             }
             __syncthreads();                               // staging (= A tiles) free again
@@ -1894,16 +1936,22 @@ k_rows_gemm16(const float* __restrict__ A, int lda, const float* __restrict__ W,
     if (warp == 0) tc::tmem_dealloc<64 * NB>(d);
 }
 
+struct RowsReduceArgs {
+    const float* A; int lda, a_col0;                   // A[:, a_col0 .. a_col0 + 64 AB)
+    const float* B; int ldb, b_col0, b_valid;          // B[:, b_col0 .. b_col0 + b_valid), b_valid <= 64 (zero padded)
+    float* partial; int n, num_tiles;
+};
+
 template <int AB>
 __global__ void __launch_bounds__(TC_THREADS)
-k_rows_reduce16(const float* __restrict__ A, int lda, const float* __restrict__ B, int ldb, float* __restrict__ partial,
-                int n, int num_tiles) {
+k_rows_reduce16(RowsReduceArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* a1 = smem;                                   // AB column blocks of A, three bf16 tiles each
     uint8_t* b1 = a1 + AB * TILE16X3;
     TcShared* sh = reinterpret_cast<TcShared*>(b1 + TILE16X3);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int n = a.n, num_tiles = a.num_tiles;
     if (warp == 0) tc::tmem_alloc<64 * AB>(&sh->tmem_base);
     if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
     tc::tc_fence_before_sync();
@@ -1917,6 +1965,7 @@ k_rows_reduce16(const float* __restrict__ A, int lda, const float* __restrict__ 
     for (int ab = 0; ab < AB; ++ab)
 #pragma unroll
         for (int i = 0; i < 64; ++i) racc[ab][i] = 0.f;
+    const bool b_vec = a.b_valid == 64 && (a.ldb & 3) == 0 && (a.b_col0 & 3) == 0 && ((uintptr_t)a.B & 15) == 0;
     float4 ma[AB][8], mb[8];
     auto load_rows = [&](int tile) {
         const int row0 = tile * TCR, rows = min(TCR, n - row0);
@@ -1925,8 +1974,19 @@ k_rows_reduce16(const float* __restrict__ A, int lda, const float* __restrict__ 
             const int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
 #pragma unroll
             for (int ab = 0; ab < AB; ++ab)
-                ma[ab][i] = rl < rows ? ldg4(A + (size_t)(row0 + rl) * lda + 64 * ab + 4 * c4) : f4zero();
-            mb[i] = rl < rows ? ldg4(B + (size_t)(row0 + rl) * ldb + 4 * c4) : f4zero();
+                ma[ab][i] = rl < rows ? ldg4(a.A + (size_t)(row0 + rl) * a.lda + a.a_col0 + 64 * ab + 4 * c4) : f4zero();
+            float4 v = f4zero();
+            if (rl < rows) {
+                const float* src = a.B + (size_t)(row0 + rl) * a.ldb + a.b_col0 + 4 * c4;
+                if (b_vec) v = ldg4(src);
+                else {
+                    if (4 * c4 < a.b_valid) v.x = __ldg(src);
+                    if (4 * c4 + 1 < a.b_valid) v.y = __ldg(src + 1);
+                    if (4 * c4 + 2 < a.b_valid) v.z = __ldg(src + 2);
+                    if (4 * c4 + 3 < a.b_valid) v.w = __ldg(src + 3);
+                }
+            }
+            mb[i] = v;
         }
     };
     if (blockIdx.x < num_tiles) load_rows(blockIdx.x);
@@ -1970,7 +2030,7 @@ k_rows_reduce16(const float* __restrict__ A, int lda, const float* __restrict__ 
         __syncthreads();                                   // accumulators and tiles free again
     }
     if (lane < 16) {
-        float* my = partial + (size_t)blockIdx.x * (AB * 64 * 64);
+        float* my = a.partial + (size_t)blockIdx.x * (AB * 64 * 64);
 #pragma unroll
         for (int ab = 0; ab < AB; ++ab)
 #pragma unroll
@@ -1980,6 +2040,18 @@ k_rows_reduce16(const float* __restrict__ A, int lda, const float* __restrict__ 
     tc::tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<64 * AB>(d);
+}
+
+// out[(o_row0 + r) * ldo + o_col0 + c] = sum over CTAs of partial[b][r * 64 + c], r < rows, c < cols: fixed order
+__global__ void k_sum_cta_partials_win(const float* __restrict__ partial, int nblocks, int rows, int cols, float* __restrict__ out,
+                                       int ldo, int o_row0, int o_col0) {
+    const int e = blockIdx.x * blockDim.x + threadIdx.x;
+    if (e >= rows * 64) return;
+    const int r = e >> 6, c = e & 63;
+    if (c >= cols) return;
+    float s = 0.f;
+    for (int b = 0; b < nblocks; ++b) s += partial[(size_t)b * (rows * 64) + e];
+    out[(size_t)(o_row0 + r) * ldo + o_col0 + c] = s;
 }
 
 // out[c] = sum over CTAs of partial[b][c], fixed order (one thread per element, coalesced across threads)
@@ -2157,49 +2229,104 @@ extern "C" int s2v_debug_tc_gemm(int32_t mode, const float* A, const float* B, f
 // ------------------------------------------------------------------------------------
 // C ABI: node-wise linear layers of the GATv2 branch on the tensor cores (include/s2v_b200.h)
 // ------------------------------------------------------------------------------------
-extern "C" int s2v_rows_gemm64(const float* A, int32_t lda, int32_t k_blocks, const float* W, int32_t n_blocks,
+template <int KB, int NB, bool MASK>
+static int launch_rows_gemm(const RowsGemmArgs& a, cudaStream_t st) {
+    constexpr int SMEM = (NB * KB + KB) * (int)TILE16X3 + 64 + 1024;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_rows_gemm16<KB, NB, MASK>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const int grid = tc_grid((const void*)k_rows_gemm16<KB, NB, MASK>, SMEM, 64 * NB, a.num_tiles);
+    k_rows_gemm16<KB, NB, MASK><<<grid, TC_THREADS, SMEM, st>>>(a);
+    return (int)cudaGetLastError();
+}
+
+// out[n, m] = A[n, k] W^T (W [m, k], transpose_w = 0) or A[n, k] W (W [k, m], transpose_w = 1), optionally * (mask > 0).
+// k <= 256 (any value: ragged K is zero padded), m a multiple of 64, <= 256.  Planned as passes of at most 128 output
+// columns x 128 contraction columns (144 KB of bf16x3 tiles per CTA); later K passes accumulate into out.
+extern "C" int s2v_rows_linear(const float* A, int32_t lda, int32_t k, const float* W, int32_t ldw, int32_t m,
                                int32_t transpose_w, const float* mask, int32_t ldm, float* out, int32_t ldo, int64_t n,
                                void* stream) {
-    if (!A || !W || !out || n < 0 || lda < 64 * k_blocks || ldo < 64 * n_blocks || (mask && ldm < 64 * n_blocks)) return S2V_ERR_BAD_ARG;
-    if ((lda | ldo | (mask ? ldm : 0)) % 4 != 0) return S2V_ERR_BAD_ARG;
+    if (!A || !W || !out || n < 0 || k < 1 || k > 256 || m < 64 || m > 256 || (m & 63) || lda < k || ldo < m || (ldo & 3))
+        return S2V_ERR_BAD_ARG;
+    if (mask && (ldm < m || (ldm & 3))) return S2V_ERR_BAD_ARG;
+    if (((uintptr_t)out & 15) || (mask && ((uintptr_t)mask & 15))) return S2V_ERR_BAD_ARG;
     if (n == 0) return 0;
     if (n > 0x7fffffff - 64) return S2V_ERR_BAD_ARG;
     cudaStream_t st = (cudaStream_t)stream;
-    const int tiles = (int)((n + TCR - 1) / TCR);
-#define S2V_ROWS_GEMM_LAUNCH(KB_, NB_, MASK_)                                                                              \
-    {                                                                                                                      \
-        constexpr int SMEM = (NB_ * KB_ + KB_) * (int)TILE16X3 + 64 + 1024;                                                \
-        S2V_RETURN_IF(cudaFuncSetAttribute(k_rows_gemm16<KB_, NB_, MASK_>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM)); \
-        const int grid = tc_grid((const void*)k_rows_gemm16<KB_, NB_, MASK_>, SMEM, 64 * NB_, tiles);                      \
-        k_rows_gemm16<KB_, NB_, MASK_><<<grid, TC_THREADS, SMEM, st>>>(A, lda, W, transpose_w, mask, ldm, out, ldo, (int)n, tiles); \
-        return (int)cudaGetLastError();                                                                                    \
+    RowsGemmArgs a{};
+    a.A = A; a.lda = lda; a.W = W; a.ldw = ldw; a.transpose_w = transpose_w; a.M = mask; a.ldm = ldm; a.out = out; a.ldo = ldo;
+    a.n = (int)n; a.num_tiles = (int)((n + TCR - 1) / TCR);
+    for (int oc = 0; oc < m; oc += 128) {
+        const int nb = (m - oc) >= 128 ? 2 : 1;
+        for (int kc = 0; kc < k; kc += 128) {
+            const int kv = k - kc < 128 ? k - kc : 128, kb = kv > 64 ? 2 : 1;
+            const bool last_k = kc + 128 >= k;
+            a.a_col0 = kc; a.k_valid = kv; a.o_col0 = oc; a.m_col0 = oc; a.accumulate = kc > 0; a.w_n_valid = 64 * nb;
+            if (transpose_w) { a.w_row0 = kc; a.w_col0 = oc; } else { a.w_row0 = oc; a.w_col0 = kc; }
+            const bool msk = mask != nullptr && last_k;
+            int rc;
+            if (kb == 1 && nb == 1) rc = msk ? launch_rows_gemm<1, 1, true>(a, st) : launch_rows_gemm<1, 1, false>(a, st);
+            else if (kb == 1 && nb == 2) rc = msk ? launch_rows_gemm<1, 2, true>(a, st) : launch_rows_gemm<1, 2, false>(a, st);
+            else if (kb == 2 && nb == 1) rc = msk ? launch_rows_gemm<2, 1, true>(a, st) : launch_rows_gemm<2, 1, false>(a, st);
+            else rc = msk ? launch_rows_gemm<2, 2, true>(a, st) : launch_rows_gemm<2, 2, false>(a, st);
+            S2V_RETURN_IF(rc);
+        }
     }
-    if (k_blocks == 1 && n_blocks == 2 && !transpose_w && !mask) S2V_ROWS_GEMM_LAUNCH(1, 2, false)
-    if (k_blocks == 2 && n_blocks == 1 && transpose_w && mask) S2V_ROWS_GEMM_LAUNCH(2, 1, true)
-    if (k_blocks == 2 && n_blocks == 1 && transpose_w && !mask) S2V_ROWS_GEMM_LAUNCH(2, 1, false)
-#undef S2V_ROWS_GEMM_LAUNCH
-    return S2V_ERR_UNSUPPORTED;
+    return 0;
+}
+
+extern "C" int s2v_rows_gemm64(const float* A, int32_t lda, int32_t k_blocks, const float* W, int32_t n_blocks,
+                               int32_t transpose_w, const float* mask, int32_t ldm, float* out, int32_t ldo, int64_t n,
+                               void* stream) {
+    if (k_blocks < 1 || n_blocks < 1) return S2V_ERR_BAD_ARG;
+    if (k_blocks > 4 || n_blocks > 4) return S2V_ERR_UNSUPPORTED;
+    return s2v_rows_linear(A, lda, 64 * k_blocks, W, transpose_w ? 64 * n_blocks : 64 * k_blocks, 64 * n_blocks, transpose_w, mask,
+                           ldm, out, ldo, n, stream);
 }
 
 extern "C" int64_t s2v_rows_reduce64_workspace_bytes(int32_t a_blocks) {
-    return (int64_t)S2V_MAX_GRID * a_blocks * 64 * 64 * (int64_t)sizeof(float);
+    (void)a_blocks;
+    return (int64_t)S2V_MAX_GRID * 2 * 64 * 64 * (int64_t)sizeof(float);
+}
+
+template <int AB>
+static int launch_rows_reduce(const RowsReduceArgs& a, float* out, int ldo, int o_row0, int o_col0, cudaStream_t st) {
+    constexpr int SMEM = (AB + 1) * (int)TILE16X3 + 64 + 1024;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_rows_reduce16<AB>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
+    const int grid = tc_grid((const void*)k_rows_reduce16<AB>, SMEM, 64 * AB, a.num_tiles);
+    k_rows_reduce16<AB><<<grid, TC_THREADS, SMEM, st>>>(a);
+    S2V_RETURN_IF(cudaGetLastError());
+    const int elems = AB * 64 * 64;
+    k_sum_cta_partials_win<<<(elems + 255) / 256, 256, 0, st>>>(a.partial, grid, AB * 64, a.b_valid, out, ldo, o_row0, o_col0);
+    return (int)cudaGetLastError();
+}
+
+// out[m, k] = A[n, m]^T B[n, k] (weight gradient dW = dY^T X): m a multiple of 64 <= 256, k <= 128 (ragged: F = 7).
+// Per-CTA partials in workspace (s2v_rows_reduce64_workspace_bytes), summed in fixed order.
+extern "C" int s2v_rows_outer(const float* A, int32_t lda, int32_t m, const float* B, int32_t ldb, int32_t k, float* out,
+                              int32_t ldo, void* workspace, int64_t workspace_bytes, int64_t n, void* stream) {
+    if (!A || !B || !out || !workspace || n < 0 || m < 64 || m > 256 || (m & 63) || k < 1 || k > 128 || lda < m || ldb < k ||
+        ldo < k || (lda & 3) || ((uintptr_t)A & 15))
+        return S2V_ERR_BAD_ARG;
+    if (workspace_bytes < s2v_rows_reduce64_workspace_bytes(2)) return S2V_ERR_WORKSPACE;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (n == 0) {
+        for (int r = 0; r < m; ++r) S2V_RETURN_IF(cudaMemsetAsync(out + (size_t)r * ldo, 0, sizeof(float) * k, st));
+        return 0;
+    }
+    if (n > 0x7fffffff - 64) return S2V_ERR_BAD_ARG;
+    RowsReduceArgs a{};
+    a.A = A; a.lda = lda; a.B = B; a.ldb = ldb; a.partial = (float*)workspace; a.n = (int)n; a.num_tiles = (int)((n + TCR - 1) / TCR);
+    for (int ac = 0; ac < m; ac += 128) {
+        const int ab = (m - ac) >= 128 ? 2 : 1;
+        for (int bc = 0; bc < k; bc += 64) {
+            a.a_col0 = ac; a.b_col0 = bc; a.b_valid = k - bc < 64 ? k - bc : 64;
+            S2V_RETURN_IF(ab == 2 ? launch_rows_reduce<2>(a, out, ldo, ac, bc, st) : launch_rows_reduce<1>(a, out, ldo, ac, bc, st));
+        }
+    }
+    return 0;
 }
 
 extern "C" int s2v_rows_reduce64(const float* A, int32_t lda, int32_t a_blocks, const float* B, int32_t ldb, float* out,
                                  void* workspace, int64_t workspace_bytes, int64_t n, void* stream) {
-    if (!A || !B || !out || !workspace || n < 0 || lda < 64 * a_blocks || ldb < 64 || (lda | ldb) % 4 != 0) return S2V_ERR_BAD_ARG;
-    if (a_blocks != 2) return S2V_ERR_UNSUPPORTED;
-    if (workspace_bytes < s2v_rows_reduce64_workspace_bytes(a_blocks)) return S2V_ERR_WORKSPACE;
-    cudaStream_t st = (cudaStream_t)stream;
-    const int width = a_blocks * 64 * 64;
-    if (n == 0) return (int)cudaMemsetAsync(out, 0, sizeof(float) * width, st);
-    if (n > 0x7fffffff - 64) return S2V_ERR_BAD_ARG;
-    const int tiles = (int)((n + TCR - 1) / TCR);
-    constexpr int SMEM = 3 * (int)TILE16X3 + 64 + 1024;
-    S2V_RETURN_IF(cudaFuncSetAttribute(k_rows_reduce16<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM));
-    const int grid = tc_grid((const void*)k_rows_reduce16<2>, SMEM, 128, tiles);
-    k_rows_reduce16<2><<<grid, TC_THREADS, SMEM, st>>>(A, lda, B, ldb, (float*)workspace, (int)n, tiles);
-    S2V_RETURN_IF(cudaGetLastError());
-    k_sum_cta_partials<<<(width + 255) / 256, 256, 0, st>>>((const float*)workspace, grid, width, out);
-    return (int)cudaGetLastError();
+    if (a_blocks < 1 || a_blocks > 4) return S2V_ERR_UNSUPPORTED;
+    return s2v_rows_outer(A, lda, 64 * a_blocks, B, ldb, 64, out, 64, workspace, workspace_bytes, n, stream);
 }

@@ -63,9 +63,11 @@ TENSOR_MIN_NODES = 4096
 
 
 def _tensor_lin(x_dim: int, HC: int, n: int, shared: bool) -> bool:
-    """lin_l / lin_r (and their backward) on the tcgen05 kernels: in = 64, heads*channels = 64 (the hidden layers of
-    QNet_GATv2), large batches; S2V_B200_PATH=ffma keeps every GEMM in fp32 round-to-nearest (cuBLAS)."""
-    return (not shared) and x_dim == 64 and HC == 64 and n >= TENSOR_MIN_NODES and _lib.path_flag() != _lib.PATHS["ffma"]
+    """lin_l / lin_r (and their backward) on the tcgen05 kernels (s2v_rows_linear / s2v_rows_outer, bf16x3): every layer
+    shape of the configurations the reference ships -- in = F (7, zero padded), 64 or 128; heads*channels 64 or 128;
+    separate or shared weights -- for large batches.  S2V_B200_PATH=ffma keeps every GEMM in fp32 round-to-nearest
+    (cuBLAS), small batches stay on the library GEMM (launch-bound either way)."""
+    return (1 <= x_dim <= 128 and HC in (64, 128) and n >= TENSOR_MIN_NODES and _lib.path_flag() != _lib.PATHS["ffma"])
 
 
 class _GATConvFn(torch.autograd.Function):
@@ -87,11 +89,12 @@ class _GATConvFn(torch.autograd.Function):
         bcat = torch.cat((bl.detach(), bl.detach() if shared else br.detach()), dim=0)     # lin_l.bias | lin_r.bias
         tensor = _tensor_lin(int(x.shape[1]), HC, n, shared)
         if tensor:
-            xlr = torch.empty(n, 2 * HC, dtype=torch.float32, device=x.device)
             wcat = wcat.contiguous()
+            m_out = int(wcat.shape[0])                   # 2 HC, or HC with shared weights
+            xlr = torch.empty(n, m_out, dtype=torch.float32, device=x.device)
             with torch.cuda.device(x.device):
-                _lib.check(L.s2v_rows_gemm64(_p(x), int(x.shape[1]), 1, _p(wcat), 2, 0, None, 0, _p(xlr), 2 * HC, n, _stream()),
-                           "s2v_rows_gemm64")
+                _lib.check(L.s2v_rows_linear(_p(x), int(x.shape[1]), int(x.shape[1]), _p(wcat), int(wcat.shape[1]), m_out, 0, None,
+                                             0, _p(xlr), m_out, n, _stream()), "s2v_rows_linear")
             _lib.launch_count += 1
         else:
             xlr = x.mm(wcat.t())                         # [n, 2HC]: x_l | x_r without biases (plain GEMM, no epilogue pass)
@@ -147,23 +150,36 @@ class _GATConvFn(torch.autograd.Function):
                                                _p(layout.row_to_col) if ef else None, _p(dout), _p(dxlr), dxr_ptr, _p(gab[0]), _p(gab[1]),
                                                _p(gab[2]), _p(ws), ws.numel(), _stream()), "s2v_gat_attn_backward")
         _lib.launch_count += 3
-        if shared:
-            dxs = dxlr[0] + dxlr[1]
-            dw = _rows_contract(dxs, x)
-            dx = dxs.mm(wcat) if ctx.needs_input_grad[4] else None
-            return (None, None, None, None, dx, dw, gab[2] + gab[3], None, None, gab[0].view(1, heads, Cc), gab[1])
-        if ctx.tensor:
-            dw = torch.empty(2 * HC, int(x.shape[1]), dtype=torch.float32, device=x.device)
+        def tensor_grads(dy):
+            """dW = dy^T x and dx = dy W (* [x > 0] when the producer left its ReLU mask to us) on the tcgen05 kernels."""
+            K, M = int(x.shape[1]), int(dy.shape[1])
+            dw = torch.empty(M, K, dtype=torch.float32, device=x.device)
             dx = None
             with torch.cuda.device(x.device):
                 ws2 = torch.empty(L.s2v_rows_reduce64_workspace_bytes(2), dtype=torch.uint8, device=x.device)
-                _lib.check(L.s2v_rows_reduce64(_p(dxlr), 2 * HC, 2, _p(x), int(x.shape[1]), _p(dw), _p(ws2), ws2.numel(), n,
-                                               _stream()), "s2v_rows_reduce64")
+                _lib.check(L.s2v_rows_outer(_p(dy), M, M, _p(x), K, K, _p(dw), K, _p(ws2), ws2.numel(), n, _stream()),
+                           "s2v_rows_outer")
                 if ctx.needs_input_grad[4]:
+                    if K % 64 != 0:
+                        raise NotImplementedError("gradient w.r.t. a %d-wide layer input on the tensor path" % K)
                     dx = torch.empty_like(x)
-                    _lib.check(L.s2v_rows_gemm64(_p(dxlr), 2 * HC, 2, _p(wcat), 1, 1, _p(x) if ctx.mask_dx else None,
-                                                 int(x.shape[1]), _p(dx), int(x.shape[1]), n, _stream()), "s2v_rows_gemm64")
+                    _lib.check(L.s2v_rows_linear(_p(dy), M, M, _p(wcat), K, K, 1, _p(x) if ctx.mask_dx else None, K, _p(dx), K, n,
+                                                 _stream()), "s2v_rows_linear")
             _lib.launch_count += 3
+            return dw, dx
+        if shared:
+            dxs = dxlr[0] + dxlr[1]
+            if ctx.tensor:
+                dw, dx = tensor_grads(dxs)
+            else:
+                dw = _rows_contract(dxs, x)
+                dx = dxs.mm(wcat) if ctx.needs_input_grad[4] else None
+                if dx is not None and ctx.mask_dx:
+                    with torch.cuda.device(x.device):
+                        _lib.check(L.s2v_relu_mask(_p(dx), _p(x), _p(dx), dx.numel(), _stream()), "s2v_relu_mask")
+            return (None, None, None, None, dx, dw, gab[2] + gab[3], None, None, gab[0].view(1, heads, Cc), gab[1])
+        if ctx.tensor:
+            dw, dx = tensor_grads(dxlr)
         else:
             dw = _rows_contract(dxlr, x)                                      # [2HC, in]   (plain GEMMs)
             dx = dxlr.mm(wcat) if ctx.needs_input_grad[4] else None
