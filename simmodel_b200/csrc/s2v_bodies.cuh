@@ -6,17 +6,17 @@
 #include "s2v_reduce.cuh"
 
 // node MLP + degree term + round 1 (comb_opt.py:230-238; mu^0 = 0)
-template <int P>
+template <int P, int TM = S2V_TM>
 __device__ __forceinline__ void embed_first_body(float* smem, const s2v_graph_t& g, const s2v_embed_params_t& prm,
                                                  const float* __restrict__ x, float* __restrict__ base,
                                                  float* __restrict__ mu1, int num_tiles) {
-    using C = Cfg<P>;
+    using C = Cfg<P, TM>;
     const int F = prm.node_dim;
     float* Wt1b = smem;                       // [P][P]  Wt[k][n] = theta1b[n][k]
     float* As = Wt1b + C::W_FLOATS;           // h tile
     float* W1a = As + C::TILE_FLOATS;         // [F][P]  W1a[f][n] = theta1a[n][f]
     float* xs = W1a + S2V_MAX_F * P;          // [TM][F]
-    float* vec = xs + S2V_TM * S2V_MAX_F;     // b1a, cst, u1, u0, r1, r0   (6 x P)
+    float* vec = xs + TM * S2V_MAX_F;     // b1a, cst, u1, u0, r1, r0   (6 x P)
     float* b1a = vec, *cst = vec + P, *u1 = vec + 2 * P, *u0 = vec + 3 * P, *r1 = vec + 4 * P, *r0 = vec + 5 * P;
     const int t = threadIdx.x;
     const int tx = t % C::TXP, ty = t / C::TXP;
@@ -39,16 +39,16 @@ __device__ __forceinline__ void embed_first_body(float* smem, const s2v_graph_t&
     __syncthreads();
 
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = tile * S2V_TM;
-        const int rows = min(S2V_TM, g.num_nodes - row0);
-        for (int e = t; e < S2V_TM * F; e += S2V_THREADS)
+        const int row0 = tile * TM;
+        const int rows = min(TM, g.num_nodes - row0);
+        for (int e = t; e < TM * F; e += S2V_THREADS)
             xs[e] = e < rows * F ? __ldg(x + (size_t)row0 * F + e) : 0.f;
         __syncthreads();
         if (active) {
 #pragma unroll
             for (int i = 0; i < C::NR; ++i) {
                 int r = ty + C::RG * i;
-                if (r >= S2V_TM) continue;
+                if (r >= TM) continue;
                 float4 h = ld4(b1a + 4 * tx);
                 for (int f = 0; f < F; ++f) {
                     float xv = xs[r * F + f];
@@ -63,7 +63,7 @@ __device__ __forceinline__ void embed_first_body(float* smem, const s2v_graph_t&
             float acc[C::NR][4];
 #pragma unroll
             for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-            tile_gemm<P>(As, Wt1b, acc, tx, ty);
+            tile_gemm<P, TM>(As, Wt1b, acc, tx, ty);
             float4 c0 = ld4(cst + 4 * tx), v1 = ld4(u1 + 4 * tx), v0 = ld4(u0 + 4 * tx);
 #pragma unroll
             for (int i = 0; i < C::NR; ++i) {
@@ -87,11 +87,11 @@ __device__ __forceinline__ void embed_first_body(float* smem, const s2v_graph_t&
 }
 
 // one propagation round (comb_opt.py:241-242)
-template <int P, int LD = 0>
+template <int P, int LD = 0, int TM = S2V_TM>
 __device__ __forceinline__ void embed_round_body(float* smem, const s2v_graph_t& g, const float* __restrict__ theta2_w,
                                                  const float* __restrict__ base, const float* mu_prev,
                                                  float* __restrict__ mu_next, int num_tiles, bool load_weights = true) {
-    using C = Cfg<P>;
+    using C = Cfg<P, TM>;
     float* Wt2 = smem;                        // Wt[k][n] = theta2[n][k]
     float* As = Wt2 + C::W_FLOATS;            // gathered tile
     const int t = threadIdx.x;
@@ -99,15 +99,15 @@ __device__ __forceinline__ void embed_round_body(float* smem, const s2v_graph_t&
     const bool active = t < C::ACTIVE;
     if (load_weights) { load_w_transposed<P>(Wt2, theta2_w); __syncthreads(); }
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = tile * S2V_TM;
-        const int rows = min(S2V_TM, g.num_nodes - row0);
-        gather_tile<P, LD>(As, g, g.rowptr, g.col, mu_prev, row0, rows);
+        const int row0 = tile * TM;
+        const int rows = min(TM, g.num_nodes - row0);
+        gather_tile<P, LD, TM>(As, g, g.rowptr, g.col, mu_prev, row0, rows);
         __syncthreads();
         if (active) {
             float acc[C::NR][4];
 #pragma unroll
             for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-            tile_gemm<P>(As, Wt2, acc, tx, ty);
+            tile_gemm<P, TM>(As, Wt2, acc, tx, ty);
 #pragma unroll
             for (int i = 0; i < C::NR; ++i) {
                 int rl = ty + C::RG * i;
@@ -122,26 +122,102 @@ __device__ __forceinline__ void embed_round_body(float* smem, const s2v_graph_t&
     }
 }
 
-// pooling of one graph: fixed summation order (thread ty sums rows lo + ty, + RG, ...; then the RG partials in order)
+// Pooling of one graph, fixed summation order.  Row r (relative to the graph start) belongs to thread group
+// ty = r % RG; a thread first sums its rows INSIDE every 64-row chunk of the graph (ascending), then the chunk sums
+// (ascending), and the RG group totals are added in order.  The chunked association is what lets several CTAs pool one
+// large graph (k_qnet_small: one partial per chunk and group, summed here in the same order) with bit-identical results.
+#define S2V_POOL_CHUNK 64
 template <int P, int LD = 0>
-__device__ __forceinline__ void pool_graph(const float* __restrict__ mu, int lo, int hi, float* scratch, float* pool_s,
-                                           float scale) {
+__device__ __forceinline__ float4 pool_chunk_partial(const float* mu, int lo, int c0, int c1, int ty, int tx) {
+    using C = Cfg<P>;
+    float4 c = f4zero();                                   // rows c0 <= r < c1 (relative) with r % RG == ty
+    int r = c0 + ((ty - c0 % C::RG) + C::RG) % C::RG;
+    for (; r < c1; r += C::RG) c = f4add(c, ld_row4<LD>(mu + (size_t)(lo + r) * P + 4 * tx));
+    return c;
+}
+template <int P>
+__device__ __forceinline__ void pool_finish(float4 s, float* scratch, float* pool_s, int tx, int ty, bool active) {
+    using C = Cfg<P>;
+    if (active) st4(scratch + ty * P + 4 * tx, s);
+    __syncthreads();
+    if (threadIdx.x < P) {
+        float a = 0.f;
+        for (int k = 0; k < C::RG; ++k) a += scratch[k * P + threadIdx.x];
+        pool_s[threadIdx.x] = a;
+    }
+    __syncthreads();
+}
+template <int P, int LD = 0>
+__device__ __forceinline__ void pool_graph(const float* mu, int lo, int hi, float* scratch, float* pool_s, float scale) {
     using C = Cfg<P>;
     const int t = threadIdx.x;
     const int tx = t % C::TXP, ty = t / C::TXP;
     float4 s = f4zero();
     if (t < C::ACTIVE)
-        for (int r = lo + ty; r < hi; r += C::RG) s = f4add(s, ld_row4<LD>(mu + (size_t)r * P + 4 * tx));
-    if (t < C::ACTIVE) st4(scratch + ty * P + 4 * tx, s);
-    __syncthreads();
-    if (t < P) {
-        float a = 0.f;
-        for (int k = 0; k < C::RG; ++k) a += scratch[k * P + t];
-        pool_s[t] = a * scale;
-    }
-    __syncthreads();
+        for (int c0 = 0; c0 < hi - lo; c0 += S2V_POOL_CHUNK)
+            s = f4add(s, pool_chunk_partial<P, LD>(mu, lo, c0, min(hi - lo, c0 + S2V_POOL_CHUNK), ty, tx));
+    pool_finish<P>(s, scratch, pool_s, tx, ty, t < C::ACTIVE);
+    (void)scale;
 }
 
+// Graph term of q: sg = sum over the column slices tx (ascending) of the fma chain wa[c] * relu(G[c]) over the slice's four
+// columns.  q_i = (b5 + sum_tx sL_i[tx]) + sg, with sL the same chain over wb[c] * relu(L_i[c] + b7[c]): the graph term is
+// a per-graph constant, kept apart from the row term so that rows and graphs can be finished by different CTAs.
+template <int P>
+__device__ __forceinline__ float head_graph_slice(const float* w5a, const float* G, int tx) {
+    const float4 wa = ld4(w5a + 4 * tx), g4 = ld4(G + 4 * tx);
+    float s = 0.f;
+    s = fmaf(wa.x, relu(g4.x), s); s = fmaf(wa.y, relu(g4.y), s);
+    s = fmaf(wa.z, relu(g4.z), s); s = fmaf(wa.w, relu(g4.w), s);
+    return s;
+}
+
+// Invalid-action mask + per-graph reduction over q[lo, hi) (the code of s2v_mask.cu's kernels, one CTA of MK_THREADS).
+//   mode 1 masked softmax -> prob; 2 masked max / arg-max; 3 arg-max over a neighbour list; anything else: nothing.
+__device__ __forceinline__ void masked_reduce_graph(int mode, int gi, int lo, int hi, const float* q,
+                                                    const uint8_t* __restrict__ mask, const int32_t* __restrict__ reach_ptr,
+                                                    const int32_t* __restrict__ reach_idx, float* __restrict__ prob,
+                                                    int64_t* __restrict__ arg_out, int64_t* __restrict__ node_out,
+                                                    float* __restrict__ val_out, ArgPair* sh_arg, float* sh_f) {
+    const int t = threadIdx.x;
+    if (mode == 1) {
+        float m = -CUDART_INF_F;
+        for (int r = lo + t; r < hi; r += MK_THREADS)
+            if (mask[r]) m = fmaxf(m, q[r]);
+        m = block_max(m, sh_f);
+        float ssum = 0.f;
+        for (int r = lo + t; r < hi; r += MK_THREADS)
+            if (mask[r]) ssum += expf(q[r] - m);
+        ssum = block_sum(ssum, sh_f);
+        for (int r = lo + t; r < hi; r += MK_THREADS) {
+            float v = mask[r] ? expf(q[r] - m) / ssum : 0.f;
+            if (m == -CUDART_INF_F) v = CUDART_NAN_F;
+            prob[r] = v;
+        }
+    } else if (mode == 2) {
+        ArgPair p; p.v = -CUDART_INF_F; p.i = -1;
+        for (int r = lo + t; r < hi; r += MK_THREADS)
+            if (mask[r]) { ArgPair c; c.v = q[r]; c.i = r - lo; p = better(p, c); }
+        p = block_argmax(p, sh_arg);
+        if (t == 0) {
+            arg_out[gi] = p.i;
+            val_out[gi] = p.i >= 0 ? p.v : -CUDART_INF_F;
+        }
+    } else if (mode == 3) {
+        const int beg = reach_ptr[gi], end = reach_ptr[gi + 1];
+        ArgPair p; p.v = -CUDART_INF_F; p.i = -1;
+        for (int k = beg + t; k < end; k += MK_THREADS) {
+            ArgPair c; c.v = q[lo + reach_idx[k]]; c.i = k - beg;
+            p = better(p, c);
+        }
+        p = block_argmax(p, sh_arg);
+        if (t == 0) {
+            arg_out[gi] = p.i;
+            node_out[gi] = p.i >= 0 ? (int64_t)reach_idx[beg + p.i] : -1;
+            val_out[gi] = p.i >= 0 ? p.v : -CUDART_INF_F;
+        }
+    }
+}
 
 // pool + theta6 + head + mask + per-graph reduction (see k_head_fused, s2v_head.cu)
 template <int P, int LD = 0>
@@ -192,6 +268,11 @@ __device__ __forceinline__ void head_fused_body(float* smem, const s2v_graph_t& 
             gstate[(size_t)gi * P + t] = a;
         }
         __syncthreads();
+        if (t < C::TXP) scratch[t] = head_graph_slice<P>(w5a, g_s, t);       // graph term of q (scratch is free again)
+        __syncthreads();
+        float sg = 0.f;
+        for (int k = 0; k < C::TXP; ++k) sg += scratch[k];
+        __syncthreads();
         // ---- phase 2: q of the graph's rows, 64 at a time (k_head) ----
         for (int row0 = lo; row0 < hi; row0 += S2V_TM) {
             const int rows = min(S2V_TM, hi - row0);
@@ -202,15 +283,13 @@ __device__ __forceinline__ void head_fused_body(float* smem, const s2v_graph_t& 
 #pragma unroll
                 for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
                 tile_gemm<P>(As, Wt7, acc, tx, ty);
-                const float4 bb = ld4(b7 + 4 * tx), wa = ld4(w5a + 4 * tx), wb = ld4(w5b + 4 * tx), G = ld4(g_s + 4 * tx);
+                const float4 bb = ld4(b7 + 4 * tx), wb = ld4(w5b + 4 * tx);
 #pragma unroll
                 for (int i = 0; i < C::NR; ++i) {
                     int rl = ty + C::RG * i;
                     if (rl >= S2V_TM) continue;
                     float sacc = 0.f;
                     if (rl < rows) {
-                        sacc = fmaf(wa.x, relu(G.x), sacc); sacc = fmaf(wa.y, relu(G.y), sacc);
-                        sacc = fmaf(wa.z, relu(G.z), sacc); sacc = fmaf(wa.w, relu(G.w), sacc);
                         sacc = fmaf(wb.x, relu(acc[i][0] + bb.x), sacc); sacc = fmaf(wb.y, relu(acc[i][1] + bb.y), sacc);
                         sacc = fmaf(wb.z, relu(acc[i][2] + bb.z), sacc); sacc = fmaf(wb.w, relu(acc[i][3] + bb.w), sacc);
                     }
@@ -221,48 +300,12 @@ __device__ __forceinline__ void head_fused_body(float* smem, const s2v_graph_t& 
             if (t < rows) {
                 float sacc = b5;
                 for (int k = 0; k < C::TXP; ++k) sacc += red[t * C::TXP + k];
-                q[row0 + t] = sacc;
+                q[row0 + t] = sacc + sg;
             }
             __syncthreads();                   // also orders the q stores of this CTA before the reads of phase 3
         }
         // ---- phase 3: invalid-action mask + per-graph reduction (s2v_mask.cu) ----
-        if (mode == 1) {
-            float m = -CUDART_INF_F;
-            for (int r = lo + t; r < hi; r += MK_THREADS)
-                if (mask[r]) m = fmaxf(m, q[r]);
-            m = block_max(m, sh_f);
-            float ssum = 0.f;
-            for (int r = lo + t; r < hi; r += MK_THREADS)
-                if (mask[r]) ssum += expf(q[r] - m);
-            ssum = block_sum(ssum, sh_f);
-            for (int r = lo + t; r < hi; r += MK_THREADS) {
-                float v = mask[r] ? expf(q[r] - m) / ssum : 0.f;
-                if (m == -CUDART_INF_F) v = CUDART_NAN_F;
-                prob[r] = v;
-            }
-        } else if (mode == 2) {
-            ArgPair p; p.v = -CUDART_INF_F; p.i = -1;
-            for (int r = lo + t; r < hi; r += MK_THREADS)
-                if (mask[r]) { ArgPair c; c.v = q[r]; c.i = r - lo; p = better(p, c); }
-            p = block_argmax(p, sh_arg);
-            if (t == 0) {
-                arg_out[gi] = p.i;
-                val_out[gi] = p.i >= 0 ? p.v : -CUDART_INF_F;
-            }
-        } else if (mode == 3) {
-            const int beg = reach_ptr[gi], end = reach_ptr[gi + 1];
-            ArgPair p; p.v = -CUDART_INF_F; p.i = -1;
-            for (int k = beg + t; k < end; k += MK_THREADS) {
-                ArgPair c; c.v = q[lo + reach_idx[k]]; c.i = k - beg;
-                p = better(p, c);
-            }
-            p = block_argmax(p, sh_arg);
-            if (t == 0) {
-                arg_out[gi] = p.i;
-                node_out[gi] = p.i >= 0 ? (int64_t)reach_idx[beg + p.i] : -1;
-                val_out[gi] = p.i >= 0 ? p.v : -CUDART_INF_F;
-            }
-        }
+        masked_reduce_graph(mode, gi, lo, hi, q, mask, reach_ptr, reach_idx, prob, arg_out, node_out, val_out, sh_arg, sh_f);
         __syncthreads();
     }
 }

@@ -19,16 +19,18 @@
 #define S2V_MAX_GRID 1024
 #define S2V_MAX_F 32
 
-template <int P>
+// TM = tile height.  64 everywhere except the small-problem forward stages (16: four times the CTAs, a quarter of the
+// work per stage -- the stage latency, not the throughput, is what a 975-row problem pays).
+template <int P, int TM = S2V_TM>
 struct Cfg {
     static_assert(P % 4 == 0 && P >= 8 && P <= 64, "emb_dim must be a multiple of 4 in [8,64]");
     static constexpr int TXP = P / 4;                            // float4 column groups per row
     static constexpr int RG = S2V_THREADS / TXP;                 // row groups
     static constexpr int ACTIVE = TXP * RG;                      // threads that own outputs
-    static constexpr int NR = (S2V_TM + RG - 1) / RG;            // tile rows per thread (transform)
+    static constexpr int NR = (TM + RG - 1) / RG;                // tile rows per thread (transform)
     static constexpr int NRR = (P + RG - 1) / RG;                // output rows per thread (reduction, P x P)
     static constexpr int LDA = P + 4;                            // leading dimension of row tiles
-    static constexpr int TILE_FLOATS = S2V_TM * LDA;
+    static constexpr int TILE_FLOATS = TM * LDA;
     static constexpr int W_FLOATS = P * P;
     // gather: LPR lanes (float4 each) cover one row, RPP rows per warp pass
     static constexpr int LPR = P / 4;
@@ -110,11 +112,11 @@ __device__ __forceinline__ void load_w_plain(float* Ws, const float* __restrict_
 }
 
 // Copy `rows` consecutive rows of a [*,P] global matrix into a row tile; rows beyond are zeroed.
-template <int P, int LD = 0>
+template <int P, int LD = 0, int TM = S2V_TM>
 __device__ __forceinline__ void load_tile(float* As, const float* src, int rows) {
     constexpr int LDA = Cfg<P>::LDA;
     constexpr int V = P / 4;
-    for (int e = threadIdx.x; e < S2V_TM * V; e += S2V_THREADS) {
+    for (int e = threadIdx.x; e < TM * V; e += S2V_THREADS) {
         int r = e / V, c = e - r * V;
         float4 v = r < rows ? ld_row4<LD>(src + (size_t)r * P + 4 * c) : f4zero();
         st4(As + r * LDA + 4 * c, v);
@@ -122,9 +124,9 @@ __device__ __forceinline__ void load_tile(float* As, const float* src, int rows)
 }
 
 // acc[i][0..3] += sum_k As[row_i][k] * Ws[k][4tx..4tx+3],  row_i = ty + RG*i
-template <int P>
-__device__ __forceinline__ void tile_gemm(const float* As, const float* Ws, float (&acc)[Cfg<P>::NR][4], int tx, int ty) {
-    constexpr int LDA = Cfg<P>::LDA, RG = Cfg<P>::RG, NR = Cfg<P>::NR;
+template <int P, int TM = S2V_TM>
+__device__ __forceinline__ void tile_gemm(const float* As, const float* Ws, float (&acc)[Cfg<P, TM>::NR][4], int tx, int ty) {
+    constexpr int LDA = Cfg<P>::LDA, RG = Cfg<P>::RG, NR = Cfg<P, TM>::NR;
 #pragma unroll 2
     for (int k0 = 0; k0 < P; k0 += 4) {
         float4 w0 = ld4(Ws + (k0 + 0) * P + 4 * tx);
@@ -134,7 +136,7 @@ __device__ __forceinline__ void tile_gemm(const float* As, const float* Ws, floa
 #pragma unroll
         for (int i = 0; i < NR; ++i) {
             int r = ty + RG * i;
-            if (NR * RG > S2V_TM && r >= S2V_TM) continue;
+            if (NR * RG > TM && r >= TM) continue;
             float4 a = ld4(As + r * LDA + k0);
             acc[i][0] = fmaf(a.x, w0.x, acc[i][0]); acc[i][1] = fmaf(a.x, w0.y, acc[i][1]);
             acc[i][2] = fmaf(a.x, w0.z, acc[i][2]); acc[i][3] = fmaf(a.x, w0.w, acc[i][3]);
@@ -381,9 +383,9 @@ __device__ __forceinline__ void gatherN_ids(GatherMeta<NR>& m, const GatherExt& 
     }
 }
 
-template <int NR, int BATCH, class Sink>
-__device__ __forceinline__ void gatherN_consume(const GatherMeta<NR>& m, const int32_t* __restrict__ col,
-                                                const float* __restrict__ src, int rl0, Sink&& sink) {
+template <int NR, int BATCH, int LD, class Sink>
+__device__ __forceinline__ void gatherN_consume_ld(const GatherMeta<NR>& m, const int32_t* __restrict__ col,
+                                                   const float* src, int rl0, Sink&& sink) {
     static_assert(NR % BATCH == 0, "NR must be a multiple of BATCH");
     const unsigned FULL = 0xffffffffu;
     const int c = threadIdx.x & 15;
@@ -404,7 +406,7 @@ __device__ __forceinline__ void gatherN_consume(const GatherMeta<NR>& m, const i
 #pragma unroll
             for (int k = 0; k < 4; ++k)
                 v[i][k] = dd[BATCH * h + i] > k
-                              ? ldg4(src + (size_t)(oo[BATCH * h + i] + jj[BATCH * h + i][k]) * 64 + 4 * c) : f4zero();
+                              ? ld_row4<LD>(src + (size_t)(oo[BATCH * h + i] + jj[BATCH * h + i][k]) * 64 + 4 * c) : f4zero();
 #pragma unroll
         for (int i = 0; i < BATCH; ++i)
             acc[BATCH * h + i] = f4add(f4add(f4add(f4add(f4zero(), v[i][0]), v[i][1]), v[i][2]), v[i][3]);
@@ -416,11 +418,17 @@ __device__ __forceinline__ void gatherN_consume(const GatherMeta<NR>& m, const i
             int bi = __shfl_sync(FULL, m.b, i, 16);
             for (int k = 4; k < dmax; ++k) {
                 int j = k < 16 ? __shfl_sync(FULL, m.idx[i], k, 16) : (k < dd[i] ? __ldg(col + bi + k) : 0);
-                if (k < dd[i]) acc[i] = f4add(acc[i], ldg4(src + (size_t)(oo[i] + j) * 64 + 4 * c));
+                if (k < dd[i]) acc[i] = f4add(acc[i], ld_row4<LD>(src + (size_t)(oo[i] + j) * 64 + 4 * c));
             }
         }
         sink(rl0 + i, acc[i]);
     }
+}
+
+template <int NR, int BATCH, class Sink>
+__device__ __forceinline__ void gatherN_consume(const GatherMeta<NR>& m, const int32_t* __restrict__ col,
+                                                const float* __restrict__ src, int rl0, Sink&& sink) {
+    gatherN_consume_ld<NR, BATCH, 0>(m, col, src, rl0, sink);
 }
 
 // Software-pipelined form for a persistent producer warp (p = 64, 4 rows per half-warp): one call issues, in this
@@ -525,13 +533,22 @@ __device__ __forceinline__ void gather8_p64(const s2v_graph_t& g, const int32_t*
 }
 
 // Gather a tile: As[rl][:] = sum of neighbour rows of batch row row0+rl (zeros past num_nodes).
-template <int P, int LD = 0>
+template <int P, int LD = 0, int TM = S2V_TM>
 __device__ __forceinline__ void gather_tile(float* As, const s2v_graph_t& g, const int32_t* __restrict__ rowptr,
                                             const int32_t* __restrict__ col, const float* __restrict__ src,
                                             int row0, int rows) {
     constexpr int LDA = Cfg<P>::LDA, LPR = Cfg<P>::LPR, RPP = Cfg<P>::RPP;
-    constexpr int ROWS_PER_WARP = S2V_TM / (S2V_THREADS / 32);
+    constexpr int ROWS_PER_WARP = TM / (S2V_THREADS / 32);
     int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if constexpr (P == 64 && ROWS_PER_WARP < 16) {          // short tiles: ROWS_PER_WARP / 2 rows per half-warp, same scheme
+        constexpr int NRH = ROWS_PER_WARP / 2;
+        const int rl0 = warp * ROWS_PER_WARP + NRH * (lane >> 4);
+        GatherMeta<NRH> m;
+        gatherN_prefetch<NRH>(m, g, rowptr, col, row0, rows, rl0);
+        gatherN_consume_ld<NRH, NRH, LD>(m, col, src, rl0,
+                                         [&](int rl, const float4& acc) { st4(As + rl * LDA + 4 * (lane & 15), acc); });
+        return;
+    }
     if constexpr (P == 64) {
         gather8_p64<LD>(g, rowptr, col, src, row0, rows, warp * ROWS_PER_WARP + 8 * (lane >> 4),
                     [&](int rl, const float4& acc) { st4(As + rl * LDA + 4 * (lane & 15), acc); });

@@ -16,20 +16,20 @@
 // ------------------------------------------------------------------------------------
 // forward
 // ------------------------------------------------------------------------------------
-template <int P>
+template <int P, int TM = S2V_TM>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_embed_first(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict__ x,
               float* __restrict__ base, float* __restrict__ mu1, int num_tiles) {
     extern __shared__ __align__(16) float smem[];
-    embed_first_body<P>(smem, g, prm, x, base, mu1, num_tiles);
+    embed_first_body<P, TM>(smem, g, prm, x, base, mu1, num_tiles);
 }
 
-template <int P>
+template <int P, int TM = S2V_TM>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_embed_round(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ base,
               const float* __restrict__ mu_prev, float* __restrict__ mu_next, int num_tiles) {
     extern __shared__ __align__(16) float smem[];
-    embed_round_body<P, 0>(smem, g, theta2_w, base, mu_prev, mu_next, num_tiles);
+    embed_round_body<P, 0, TM>(smem, g, theta2_w, base, mu_prev, mu_next, num_tiles);
 }
 
 // ------------------------------------------------------------------------------------
@@ -344,6 +344,22 @@ static int embed_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& pr
     const int tiles = (g.num_nodes + S2V_TM - 1) / S2V_TM;
     const size_t plane = (size_t)g.num_nodes * P;
     const bool tensor = use_tensor_path(P, prm.flags, g.num_nodes);
+    // small problems (emb_dim 64, at most 4096 rows): 16-row tiles -- stage latency, not throughput, is the cost there
+    constexpr int TS = 16;
+    if constexpr (P == 64) if (!tensor && g.num_nodes <= S2V_TENSOR_MIN_NODES) {
+        using CS = Cfg<P, TS>;
+        const int tiles_s = (g.num_nodes + TS - 1) / TS;
+        int smem = (CS::W_FLOATS + CS::TILE_FLOATS + S2V_MAX_F * P + TS * S2V_MAX_F + 6 * P) * 4;
+        S2V_RETURN_IF(set_smem(k_embed_first<P, TS>, smem));
+        int grid = s2v_persistent_grid((const void*)k_embed_first<P, TS>, smem, tiles_s);
+        k_embed_first<P, TS><<<grid, S2V_THREADS, smem, st>>>(g, prm, x, base, mus, tiles_s);
+        smem = (CS::W_FLOATS + CS::TILE_FLOATS) * 4;
+        S2V_RETURN_IF(set_smem(k_embed_round<P, TS>, smem));
+        grid = s2v_persistent_grid((const void*)k_embed_round<P, TS>, smem, tiles_s);
+        for (int t = 1; t < prm.rounds; ++t)
+            k_embed_round<P, TS><<<grid, S2V_THREADS, smem, st>>>(g, prm.theta2_w, base, mus + (t - 1) * plane, mus + t * plane, tiles_s);
+        return (int)cudaGetLastError();
+    }
     if (tensor) {
         S2V_RETURN_IF(s2v_tc_embed_first(g, prm, x, base, mus, st));
     } else {

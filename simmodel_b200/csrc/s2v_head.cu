@@ -68,8 +68,9 @@ k_head(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const
     extern __shared__ __align__(16) float smem[];
     float* Wt7 = smem;                        // Wt[k][n] = theta7[n][k]
     float* As = Wt7 + C::W_FLOATS;            // mu tile
-    float* red = As + C::TILE_FLOATS;         // [TM][TXP]
-    float* vec = red + S2V_TM * C::TXP;       // b7, w5a, w5b
+    float* red = As + C::TILE_FLOATS;         // [TM][TXP] row term slices
+    float* redg = red + S2V_TM * C::TXP;      // [TM][TXP] graph term slices of the row's graph
+    float* vec = redg + S2V_TM * C::TXP;      // b7, w5a, w5b
     float* b7 = vec, *w5a = vec + P, *w5b = vec + 2 * P;
     const int t = threadIdx.x;
     const int tx = t % C::TXP, ty = t / C::TXP;
@@ -92,29 +93,29 @@ k_head(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const
 #pragma unroll
             for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
             tile_gemm<P>(As, Wt7, acc, tx, ty);
-            float4 bb = ld4(b7 + 4 * tx), wa = ld4(w5a + 4 * tx), wb = ld4(w5b + 4 * tx);
+            float4 bb = ld4(b7 + 4 * tx), wb = ld4(w5b + 4 * tx);
 #pragma unroll
             for (int i = 0; i < C::NR; ++i) {
                 int rl = ty + C::RG * i;
                 if (rl >= S2V_TM) continue;
-                float s = 0.f;
+                float s = 0.f, sgs = 0.f;
                 if (rl < rows) {
                     int li, off, gi;
                     row_info(g, row0 + rl, li, off, gi);
-                    float4 G = ldg4(gstate + (size_t)gi * P + 4 * tx);
-                    s = fmaf(wa.x, relu(G.x), s); s = fmaf(wa.y, relu(G.y), s);
-                    s = fmaf(wa.z, relu(G.z), s); s = fmaf(wa.w, relu(G.w), s);
+                    sgs = head_graph_slice<P>(w5a, gstate + (size_t)gi * P, tx);      // graph term (same value for every row of a graph)
                     s = fmaf(wb.x, relu(acc[i][0] + bb.x), s); s = fmaf(wb.y, relu(acc[i][1] + bb.y), s);
                     s = fmaf(wb.z, relu(acc[i][2] + bb.z), s); s = fmaf(wb.w, relu(acc[i][3] + bb.w), s);
                 }
                 red[rl * C::TXP + tx] = s;
+                redg[rl * C::TXP + tx] = sgs;
             }
         }
         __syncthreads();
         if (t < rows) {
-            float s = b5;
+            float s = b5, sg = 0.f;
             for (int k = 0; k < C::TXP; ++k) s += red[t * C::TXP + k];
-            q[row0 + t] = s;
+            for (int k = 0; k < C::TXP; ++k) sg += redg[t * C::TXP + k];
+            q[row0 + t] = s + sg;
         }
         __syncthreads();
     }
@@ -571,7 +572,7 @@ static int head_forward_impl(const s2v_graph_t& g, const s2v_head_params_t& prm,
     if (tiles > 0 && head_tensor_path(P, prm.flags, g.num_nodes)) {
         S2V_RETURN_IF(s2v_tc_head_forward(g, prm, mu, gstate, q, st));
     } else if (tiles > 0) {
-        int smem = (C::W_FLOATS + C::TILE_FLOATS + S2V_TM * C::TXP + 3 * P) * 4;
+        int smem = (C::W_FLOATS + C::TILE_FLOATS + 2 * S2V_TM * C::TXP + 3 * P) * 4;
         S2V_RETURN_IF(cudaFuncSetAttribute(k_head<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         int grid = s2v_persistent_grid((const void*)k_head<P>, smem, tiles);
         k_head<P><<<grid, S2V_THREADS, smem, st>>>(g, prm, mu, gstate, q, tiles);

@@ -24,7 +24,7 @@ extern "C" int s2v_debug_small_prof(unsigned long long* out) { return (int)cudaM
 #define SP(i) do {} while (0)
 #endif
 
-template <int P>
+template <int P, int TM>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_qnet_small(s2v_graph_t g, s2v_embed_params_t eprm, s2v_head_params_t hprm, const float* __restrict__ x,
              float* base, float* mus, int mode, const uint8_t* __restrict__ mask, const int32_t* __restrict__ reach_ptr,
@@ -33,16 +33,16 @@ k_qnet_small(s2v_graph_t g, s2v_embed_params_t eprm, s2v_head_params_t hprm, con
              float* __restrict__ val_out) {
     extern __shared__ __align__(16) float smem[];
     cg::grid_group grid = cg::this_grid();
-    const int tiles = (g.num_nodes + S2V_TM - 1) / S2V_TM;
+    const int tiles = (g.num_nodes + TM - 1) / TM;          // embedding stages: TM-row tiles (the head walks graphs)
     const size_t plane = (size_t)g.num_nodes * P;
     SP(0);
-    embed_first_body<P>(smem, g, eprm, x, base, mus, tiles);
+    embed_first_body<P, TM>(smem, g, eprm, x, base, mus, tiles);
     SP(1);
     for (int t = 1; t < eprm.rounds; ++t) {
         __threadfence();
         grid.sync();
         SP(2 * t);
-        embed_round_body<P, 1>(smem, g, eprm.theta2_w, base, mus + (t - 1) * plane, mus + t * plane, tiles, t == 1);
+        embed_round_body<P, 1, TM>(smem, g, eprm.theta2_w, base, mus + (t - 1) * plane, mus + t * plane, tiles, t == 1);
         SP(2 * t + 1);
     }
     if (mode < 0) return;                         // embedding only
@@ -54,22 +54,30 @@ k_qnet_small(s2v_graph_t g, s2v_embed_params_t eprm, s2v_head_params_t hprm, con
     SP(21);
 }
 
+// Short tiles (16 rows) for emb_dim 64: a stage of one 64-row tile per CTA costs 5.6 us on 128 threads (gather round trips
+// + a 64 x 64 x 64 FFMA tile); with 16-row tiles four times as many CTAs share the rows and a stage is ~2 us.
+template <int P>
+struct SmallTile { static constexpr int TM = P == 64 ? 16 : S2V_TM; };
+
 template <int P>
 static int small_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& eprm, const s2v_head_params_t& hprm,
                               const float* x, float* base, float* mus, int mode, const uint8_t* mask,
                               const int32_t* reach_ptr, const int32_t* reach_idx, float* pool, float* gstate, float* q,
                               float* prob, int64_t* arg_out, int64_t* node_out, float* val_out, cudaStream_t st) {
     using C = Cfg<P>;
-    const int smem_first = (C::W_FLOATS + C::TILE_FLOATS + S2V_MAX_F * P + S2V_TM * S2V_MAX_F + 6 * P) * 4;
+    constexpr int TM = SmallTile<P>::TM;
+    using CT = Cfg<P, TM>;
+    const int smem_first = (CT::W_FLOATS + CT::TILE_FLOATS + S2V_MAX_F * P + TM * S2V_MAX_F + 6 * P) * 4;
     const int smem_head = (C::W_FLOATS + C::TILE_FLOATS + S2V_TM * C::TXP + 3 * P + C::RG * P + 2 * P) * 4;
     const int smem = smem_first > smem_head ? smem_first : smem_head;
-    S2V_RETURN_IF(cudaFuncSetAttribute(k_qnet_small<P>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    auto kernel = k_qnet_small<P, TM>;
+    S2V_RETURN_IF(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0, sms = 0, per_sm = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    S2V_RETURN_IF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_qnet_small<P>, S2V_THREADS, smem));
+    S2V_RETURN_IF(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, S2V_THREADS, smem));
     if (per_sm < 1) return S2V_ERR_UNSUPPORTED;
-    const int tiles = (g.num_nodes + S2V_TM - 1) / S2V_TM;
+    const int tiles = (g.num_nodes + TM - 1) / TM;
     int want = tiles > g.num_graphs ? tiles : g.num_graphs;
     int grid = sms * per_sm;                      // every CTA must be resident: cooperative launch
     if (grid > want) grid = want;
@@ -79,7 +87,7 @@ static int small_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& ep
     s2v_head_params_t hp = hprm;
     void* args[] = {&gg, &ep, &hp, (void*)&x, &base, &mus, &mode, (void*)&mask, (void*)&reach_ptr, (void*)&reach_idx,
                     &pool, &gstate, &q, &prob, &arg_out, &node_out, &val_out};
-    return (int)cudaLaunchCooperativeKernel((const void*)k_qnet_small<P>, dim3(grid), dim3(S2V_THREADS), args, smem, st);
+    return (int)cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(S2V_THREADS), args, smem, st);
 }
 
 // mode -1: embedding only (base, mus);  0..3: as s2v_head_fused_forward.  Returns S2V_ERR_UNSUPPORTED when the problem
