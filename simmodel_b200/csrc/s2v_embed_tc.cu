@@ -13,6 +13,7 @@
 //                            (both MN-major views of the same tiles; K = the 64 rows of the
 //                             tile; rows 0-63 of D2 + rows 64-127 of D2 = dtheta2 partial,
 //                             kept in TMEM across all tiles of the CTA)
+#include <cstdio>
 #include <cstdlib>
 #include "s2v_common.cuh"
 #include "s2v_tc.cuh"
@@ -1112,6 +1113,8 @@ k_embed_round_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const floa
     if (warp == 0) tc::tmem_dealloc<64>(d1);
 }
 
+#include "s2v_ring.cuh"
+
 // self-test: mode 6: out[rows x 64] = A * W;  mode 7: out[64 x 64] = A^T * B over the rows (per-tile accumulators
 // summed on the CUDA cores)
 __global__ void __launch_bounds__(TC_THREADS)
@@ -2087,6 +2090,33 @@ int tc_grid(const void* kernel, int smem, int tmem_cols, int tiles) {
     return grid < 1 ? 1 : grid;
 }
 
+template <int NS>
+int ring_forward_launch_ns(int slots, int cap, const s2v_graph_t& g, const float* theta2_w, const float* base,
+                           const float* mu_prev, float* mu_next, int tiles, cudaStream_t st) {
+    int dev = 0, sms = 0, smem_max = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaDeviceGetAttribute(&smem_max, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cudaFuncAttributes fa;
+    S2V_RETURN_IF(cudaFuncGetAttributes(&fa, k_embed_round_ring<NS>));
+    const int fixed = 1024 + (1 + NS) * (int)TILE16X3 + TCR * STG_LD * 4 + 2 * TCR * 256;
+    const int max_slots = (smem_max - (int)fa.sharedSizeBytes - fixed) / 256;
+    if (slots <= 0 || slots > max_slots) slots = max_slots;
+    if (cap < 32) cap = 32;
+    if (cap > RG_CAP_MAX) cap = RG_CAP_MAX;
+    if (cap > slots) return S2V_ERR_UNSUPPORTED;
+    const int smem = fixed + slots * 256;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_ring<NS>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    const int grid = sms < tiles ? sms : tiles;
+    k_embed_round_ring<NS><<<grid, RG_THREADS, smem, st>>>(g, theta2_w, base, mu_prev, mu_next, tiles, slots, cap);
+    return (int)cudaGetLastError();
+}
+int ring_forward_launch(int ns, int slots, int cap, const s2v_graph_t& g, const float* theta2_w, const float* base,
+                        const float* mu_prev, float* mu_next, int tiles, cudaStream_t st) {
+    return ns == 2 ? ring_forward_launch_ns<2>(slots, cap, g, theta2_w, base, mu_prev, mu_next, tiles, st)
+                   : ring_forward_launch_ns<1>(slots, cap, g, theta2_w, base, mu_prev, mu_next, tiles, st);
+}
+
 }  // namespace
 
 // Launchers used by s2v_embed.cu (p = 64 only).  grid_out: number of CTAs (= dtheta2 partials).
@@ -2099,6 +2129,13 @@ int s2v_tc_round_forward(const s2v_graph_t& g, const float* theta2_w, const floa
         int grid = tc_grid((const void*)k_embed_round_tc, FWD_SMEM, 64, tiles);
         k_embed_round_tc<<<grid, TC_THREADS, FWD_SMEM, st>>>(g, theta2_w, base, mu_prev, mu_next, tiles);
         return (int)cudaGetLastError();
+    }
+    // asynchronous-gather variant (s2v_ring.cuh): S2V_B200_FWD_RING=<stages 1|2>[,<ring slots>[,<edges per chunk>]]
+    const char* ring_env = getenv("S2V_B200_FWD_RING");
+    if (ring_env && (g.period == 0 || g.period >= TCR) && tiles > 0) {
+        int ns = 1, slots = 0, cap = 128;
+        sscanf(ring_env, "%d,%d,%d", &ns, &slots, &cap);
+        return ring_forward_launch(ns == 2 ? 2 : 1, slots, cap, g, theta2_w, base, mu_prev, mu_next, tiles, st);
     }
     constexpr int FWD16_SMEM = 2 * (int)TILE16X3 + 64 + 1024;
     S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD16_SMEM));
@@ -2166,6 +2203,11 @@ int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const flo
     return (int)cudaGetLastError();
 }
 
+#ifdef S2V_RING_PROF
+extern "C" int s2v_debug_ring_prof(long long* host_out) {
+    return (int)cudaMemcpyFromSymbol(host_out, g_ring_prof, sizeof(long long) * 32);
+}
+#endif
 #ifdef S2V_TC_TIMELINE
 extern "C" int s2v_debug_timeline(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, g_timeline, sizeof(long long) * 16 * 8);
