@@ -131,8 +131,17 @@ template <int P, int LD = 0>
 __device__ __forceinline__ float4 pool_chunk_partial(const float* mu, int lo, int c0, int c1, int ty, int tx) {
     using C = Cfg<P>;
     float4 c = f4zero();                                   // rows c0 <= r < c1 (relative) with r % RG == ty
-    int r = c0 + ((ty - c0 % C::RG) + C::RG) % C::RG;
-    for (; r < c1; r += C::RG) c = f4add(c, ld_row4<LD>(mu + (size_t)(lo + r) * P + 4 * tx));
+    const int r0 = c0 + ((ty - c0 % C::RG) + C::RG) % C::RG;
+    constexpr int NPT = S2V_POOL_CHUNK / C::RG + 1;        // rows of a chunk a thread can own
+    float4 v[NPT];                                         // all loads first: one memory round trip per chunk, not one per row
+#pragma unroll
+    for (int u = 0; u < NPT; ++u) {
+        const int r = r0 + u * C::RG;
+        v[u] = r < c1 ? ld_row4<LD>(mu + (size_t)(lo + r) * P + 4 * tx) : f4zero();
+    }
+#pragma unroll
+    for (int u = 0; u < NPT; ++u)
+        if (r0 + u * C::RG < c1) c = f4add(c, v[u]);       // same order as the plain loop; absent rows add nothing
     return c;
 }
 template <int P>
@@ -153,9 +162,20 @@ __device__ __forceinline__ void pool_graph(const float* mu, int lo, int hi, floa
     const int t = threadIdx.x;
     const int tx = t % C::TXP, ty = t / C::TXP;
     float4 s = f4zero();
-    if (t < C::ACTIVE)
-        for (int c0 = 0; c0 < hi - lo; c0 += S2V_POOL_CHUNK)
-            s = f4add(s, pool_chunk_partial<P, LD>(mu, lo, c0, min(hi - lo, c0 + S2V_POOL_CHUNK), ty, tx));
+    if (t < C::ACTIVE) {
+        const int n = hi - lo;
+        int c0 = 0;
+        for (; c0 + 4 * S2V_POOL_CHUNK <= n; c0 += 4 * S2V_POOL_CHUNK) {     // four chunk sums in flight, added in chunk order
+            float4 c[4];
+#pragma unroll
+            for (int u = 0; u < 4; ++u)
+                c[u] = pool_chunk_partial<P, LD>(mu, lo, c0 + u * S2V_POOL_CHUNK, c0 + (u + 1) * S2V_POOL_CHUNK, ty, tx);
+#pragma unroll
+            for (int u = 0; u < 4; ++u) s = f4add(s, c[u]);
+        }
+        for (; c0 < n; c0 += S2V_POOL_CHUNK)
+            s = f4add(s, pool_chunk_partial<P, LD>(mu, lo, c0, min(n, c0 + S2V_POOL_CHUNK), ty, tx));
+    }
     pool_finish<P>(s, scratch, pool_s, tx, ty, t < C::ACTIVE);
     (void)scale;
 }
@@ -163,9 +183,9 @@ __device__ __forceinline__ void pool_graph(const float* mu, int lo, int hi, floa
 // Graph term of q: sg = sum over the column slices tx (ascending) of the fma chain wa[c] * relu(G[c]) over the slice's four
 // columns.  q_i = (b5 + sum_tx sL_i[tx]) + sg, with sL the same chain over wb[c] * relu(L_i[c] + b7[c]): the graph term is
 // a per-graph constant, kept apart from the row term so that rows and graphs can be finished by different CTAs.
-template <int P>
+template <int P, int LD = 0>
 __device__ __forceinline__ float head_graph_slice(const float* w5a, const float* G, int tx) {
-    const float4 wa = ld4(w5a + 4 * tx), g4 = ld4(G + 4 * tx);
+    const float4 wa = ld4(w5a + 4 * tx), g4 = LD ? ld_row4<LD>(G + 4 * tx) : ld4(G + 4 * tx);
     float s = 0.f;
     s = fmaf(wa.x, relu(g4.x), s); s = fmaf(wa.y, relu(g4.y), s);
     s = fmaf(wa.z, relu(g4.z), s); s = fmaf(wa.w, relu(g4.w), s);
@@ -306,6 +326,113 @@ __device__ __forceinline__ void head_fused_body(float* smem, const s2v_graph_t& 
         }
         // ---- phase 3: invalid-action mask + per-graph reduction (s2v_mask.cu) ----
         masked_reduce_graph(mode, gi, lo, hi, q, mask, reach_ptr, reach_idx, prob, arg_out, node_out, val_out, sh_arg, sh_f);
+        __syncthreads();
+    }
+}
+
+// ---- the head as three tile-parallel stages (k_pool | k_head | mask kernels): the per-stage kernels and the cooperative
+// ---- kernel of s2v_small.cu (graphs too large for one CTA each) run these bodies
+// pool + theta6 of the graphs blockIdx.x, + gridDim.x, ...      smem: [RG][P] scratch + [P]
+template <int P, int LD = 0>
+__device__ __forceinline__ void pool_stage_body(float* smem, const s2v_graph_t& g, int norm_agg, const float* mu,
+                                                float* __restrict__ pool, const float* __restrict__ theta6_w,
+                                                const float* __restrict__ theta6_b, float* __restrict__ gstate) {
+    using C = Cfg<P>;
+    float* scratch = smem;
+    float* pool_s = scratch + C::RG * P;
+    const int t = threadIdx.x;
+    for (int gi = blockIdx.x; gi < g.num_graphs; gi += gridDim.x) {
+        int lo, hi;
+        graph_range(g, gi, lo, hi);
+        const int n = hi - lo;
+        pool_graph<P, LD>(mu, lo, hi, scratch, pool_s, 1.f);
+        if (t < P) {
+            // torch: sum / count (a true division), not sum * (1/count)
+            float pv = norm_agg ? pool_s[t] / (float)(n > 1 ? n : 1) : pool_s[t];
+            pool_s[t] = pv;
+            pool[(size_t)gi * P + t] = pv;
+        }
+        __syncthreads();
+        if (gstate != nullptr && t < P) {
+            float a = row_dot<P>(theta6_w + t * P, pool_s, __ldg(theta6_b + t));
+            gstate[(size_t)gi * P + t] = a;
+        }
+        __syncthreads();
+    }
+}
+
+// q of the row tiles blockIdx.x, + gridDim.x, ... (TM rows each); gstate = theta6 pool + b6 per graph
+template <int P, int LD = 0, int TM = S2V_TM>
+__device__ __forceinline__ void head_rows_body(float* smem, const s2v_graph_t& g, const s2v_head_params_t& prm, const float* mu,
+                                               const float* gstate, float* __restrict__ q, int num_tiles) {
+    using C = Cfg<P, TM>;
+    float* Wt7 = smem;                        // Wt[k][n] = theta7[n][k]
+    float* As = Wt7 + C::W_FLOATS;            // mu tile
+    float* red = As + C::TILE_FLOATS;         // [TM][TXP] row term slices
+    float* redg = red + TM * C::TXP;          // [TM][TXP] graph term slices of the row's graph
+    float* vec = redg + TM * C::TXP;          // b7, w5a, w5b
+    float* b7 = vec, *w5a = vec + P, *w5b = vec + 2 * P;
+    const int t = threadIdx.x;
+    const int tx = t % C::TXP, ty = t / C::TXP;
+    const bool active = t < C::ACTIVE;
+    if ((int)blockIdx.x >= num_tiles) return;
+    load_w_transposed<P>(Wt7, prm.theta7_w);
+    if (t < P) {
+        b7[t] = __ldg(prm.theta7_b + t);
+        w5a[t] = __ldg(prm.theta5_w + t);
+        w5b[t] = __ldg(prm.theta5_w + P + t);
+    }
+    const float b5 = __ldg(prm.theta5_b);
+    __syncthreads();
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TM;
+        const int rows = min(TM, g.num_nodes - row0);
+        load_tile<P, LD, TM>(As, mu + (size_t)row0 * P, rows);
+        __syncthreads();
+        if (active) {
+            float acc[C::NR][4];
+#pragma unroll
+            for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
+            tile_gemm<P, TM>(As, Wt7, acc, tx, ty);
+            float4 bb = ld4(b7 + 4 * tx), wb = ld4(w5b + 4 * tx);
+#pragma unroll
+            for (int i = 0; i < C::NR; ++i) {
+                int rl = ty + C::RG * i;
+                if (rl >= TM) continue;
+                float s = 0.f, sgs = 0.f;
+                if (rl < rows) {
+                    int li, off, gi;
+                    row_info(g, row0 + rl, li, off, gi);
+                    sgs = head_graph_slice<P, LD>(w5a, gstate + (size_t)gi * P, tx);   // graph term (same value for every row of a graph)
+                    s = fmaf(wb.x, relu(acc[i][0] + bb.x), s); s = fmaf(wb.y, relu(acc[i][1] + bb.y), s);
+                    s = fmaf(wb.z, relu(acc[i][2] + bb.z), s); s = fmaf(wb.w, relu(acc[i][3] + bb.w), s);
+                }
+                red[rl * C::TXP + tx] = s;
+                redg[rl * C::TXP + tx] = sgs;
+            }
+        }
+        __syncthreads();
+        if (t < rows) {
+            float s = b5, sg = 0.f;
+            for (int k = 0; k < C::TXP; ++k) s += red[t * C::TXP + k];
+            for (int k = 0; k < C::TXP; ++k) sg += redg[t * C::TXP + k];
+            q[row0 + t] = s + sg;
+        }
+        __syncthreads();
+    }
+}
+
+// invalid-action mask + per-graph reduction of the graphs blockIdx.x, + gridDim.x, ...
+__device__ __forceinline__ void mask_stage_body(int mode, const s2v_graph_t& g, const float* q, const uint8_t* __restrict__ mask,
+                                                const int32_t* __restrict__ reach_ptr, const int32_t* __restrict__ reach_idx,
+                                                float* __restrict__ prob, int64_t* __restrict__ arg_out,
+                                                int64_t* __restrict__ node_out, float* __restrict__ val_out) {
+    __shared__ ArgPair sh_arg2[MK_THREADS / 32];
+    __shared__ float sh_f2[MK_THREADS / 32];
+    for (int gi = blockIdx.x; gi < g.num_graphs; gi += gridDim.x) {
+        int lo, hi;
+        graph_range(g, gi, lo, hi);
+        masked_reduce_graph(mode, gi, lo, hi, q, mask, reach_ptr, reach_idx, prob, arg_out, node_out, val_out, sh_arg2, sh_f2);
         __syncthreads();
     }
 }

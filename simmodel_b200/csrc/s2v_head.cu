@@ -16,27 +16,8 @@ __global__ void __launch_bounds__(S2V_THREADS)
 k_pool(s2v_graph_t g, int norm_agg, const float* __restrict__ mu, float* __restrict__ pool,
        const float* __restrict__ theta6_w, const float* __restrict__ theta6_b, float* __restrict__ gstate) {
     using C = Cfg<P>;
-    __shared__ __align__(16) float scratch[C::RG * P];
-    __shared__ float pool_s[P];
-    const int gi = blockIdx.x;
-    int lo, hi;
-    graph_range(g, gi, lo, hi);
-    int n = hi - lo;
-    float scale = norm_agg ? 1.f / (float)(n > 1 ? n : 1) : 1.f;
-    pool_graph<P>(mu, lo, hi, scratch, pool_s, 1.f);
-    const int t = threadIdx.x;
-    if (t < P) {
-        // torch: sum / count (a true division), not sum * (1/count)
-        float pv = norm_agg ? pool_s[t] / (float)(n > 1 ? n : 1) : pool_s[t];
-        pool_s[t] = pv;
-        pool[(size_t)gi * P + t] = pv;
-    }
-    (void)scale;
-    __syncthreads();
-    if (gstate != nullptr && t < P) {
-        float a = row_dot<P>(theta6_w + t * P, pool_s, __ldg(theta6_b + t));
-        gstate[(size_t)gi * P + t] = a;
-    }
+    __shared__ __align__(16) float pool_smem[C::RG * P + P];
+    pool_stage_body<P>(pool_smem, g, norm_agg, mu, pool, theta6_w, theta6_b, gstate);
 }
 
 template <int P>
@@ -64,61 +45,8 @@ template <int P>
 __global__ void __launch_bounds__(S2V_THREADS)
 k_head(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const float* __restrict__ gstate,
        float* __restrict__ q, int num_tiles) {
-    using C = Cfg<P>;
     extern __shared__ __align__(16) float smem[];
-    float* Wt7 = smem;                        // Wt[k][n] = theta7[n][k]
-    float* As = Wt7 + C::W_FLOATS;            // mu tile
-    float* red = As + C::TILE_FLOATS;         // [TM][TXP] row term slices
-    float* redg = red + S2V_TM * C::TXP;      // [TM][TXP] graph term slices of the row's graph
-    float* vec = redg + S2V_TM * C::TXP;      // b7, w5a, w5b
-    float* b7 = vec, *w5a = vec + P, *w5b = vec + 2 * P;
-    const int t = threadIdx.x;
-    const int tx = t % C::TXP, ty = t / C::TXP;
-    const bool active = t < C::ACTIVE;
-    load_w_transposed<P>(Wt7, prm.theta7_w);
-    if (t < P) {
-        b7[t] = __ldg(prm.theta7_b + t);
-        w5a[t] = __ldg(prm.theta5_w + t);
-        w5b[t] = __ldg(prm.theta5_w + P + t);
-    }
-    const float b5 = __ldg(prm.theta5_b);
-    __syncthreads();
-    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
-        const int row0 = tile * S2V_TM;
-        const int rows = min(S2V_TM, g.num_nodes - row0);
-        load_tile<P>(As, mu + (size_t)row0 * P, rows);
-        __syncthreads();
-        if (active) {
-            float acc[C::NR][4];
-#pragma unroll
-            for (int i = 0; i < C::NR; ++i) acc[i][0] = acc[i][1] = acc[i][2] = acc[i][3] = 0.f;
-            tile_gemm<P>(As, Wt7, acc, tx, ty);
-            float4 bb = ld4(b7 + 4 * tx), wb = ld4(w5b + 4 * tx);
-#pragma unroll
-            for (int i = 0; i < C::NR; ++i) {
-                int rl = ty + C::RG * i;
-                if (rl >= S2V_TM) continue;
-                float s = 0.f, sgs = 0.f;
-                if (rl < rows) {
-                    int li, off, gi;
-                    row_info(g, row0 + rl, li, off, gi);
-                    sgs = head_graph_slice<P>(w5a, gstate + (size_t)gi * P, tx);      // graph term (same value for every row of a graph)
-                    s = fmaf(wb.x, relu(acc[i][0] + bb.x), s); s = fmaf(wb.y, relu(acc[i][1] + bb.y), s);
-                    s = fmaf(wb.z, relu(acc[i][2] + bb.z), s); s = fmaf(wb.w, relu(acc[i][3] + bb.w), s);
-                }
-                red[rl * C::TXP + tx] = s;
-                redg[rl * C::TXP + tx] = sgs;
-            }
-        }
-        __syncthreads();
-        if (t < rows) {
-            float s = b5, sg = 0.f;
-            for (int k = 0; k < C::TXP; ++k) s += red[t * C::TXP + k];
-            for (int k = 0; k < C::TXP; ++k) sg += redg[t * C::TXP + k];
-            q[row0 + t] = s + sg;
-        }
-        __syncthreads();
-    }
+    head_rows_body<P>(smem, g, prm, mu, gstate, q, num_tiles);
 }
 
 // ------------------------------------------------------------------------------------

@@ -2,7 +2,8 @@
 //
 //   stage 0   node MLP + degree term + round 1          (embed_first_body)
 //   stage t   propagation round t = 2..T                (embed_round_body)       grid-wide barrier in between
-//   stage T+1 pool + theta6 + head + mask + reduction   (head_fused_body, one CTA per graph)
+//   stage T+1 pool + theta6 + head + mask + reduction   (head_fused_body, one CTA per graph; graphs of more than 256 nodes:
+//             pool_stage_body | head_rows_body | mask_stage_body, tile-parallel with two more grid barriers)
 //
 // For acting (B = 1: 975 rows = 16 tiles), the reference's Manhattan5 / MemTask batches and the per-rollout PPO calls
 // the work of a stage is a few microseconds, so the launch-per-stage path (T + 1 launches, each with its own drain and
@@ -49,9 +50,28 @@ k_qnet_small(s2v_graph_t g, s2v_embed_params_t eprm, s2v_head_params_t hprm, con
     __threadfence();
     grid.sync();
     SP(20);
-    head_fused_body<P, 1>(smem, g, hprm, mus + (size_t)(eprm.rounds - 1) * plane, mode, mask, reach_ptr, reach_idx, pool,
-                          gstate, q, prob, arg_out, node_out, val_out);
+    const float* muT = mus + (size_t)(eprm.rounds - 1) * plane;
+    if ((int64_t)g.num_nodes <= 256 * (int64_t)g.num_graphs) {          // small graphs: one CTA walks a whole graph
+        head_fused_body<P, 1>(smem, g, hprm, muT, mode, mask, reach_ptr, reach_idx, pool, gstate, q, prob, arg_out, node_out,
+                              val_out);
+        SP(21);
+        return;
+    }
+    // large graphs (acting on a road network: B = 1, 975 rows): the head as three tile-parallel stages -- pool + theta6
+    // per graph | q per row tile | mask + reduction per graph -- with grid barriers in between (k_pool, k_head and the
+    // mask kernels run the same bodies: bit-identical)
+    pool_stage_body<P, 1>(smem, g, hprm.norm_agg, muT, pool, hprm.theta6_w, hprm.theta6_b, gstate);
+    __threadfence();
+    grid.sync();
     SP(21);
+    head_rows_body<P, 1, TM>(smem, g, hprm, muT, gstate, q, tiles);
+    SP(22);
+    if (mode >= 1) {
+        __threadfence();
+        grid.sync();
+        mask_stage_body(mode, g, q, mask, reach_ptr, reach_idx, prob, arg_out, node_out, val_out);
+    }
+    SP(23);
 }
 
 // Short tiles (16 rows) for emb_dim 64: a stage of one 64-row tile per CTA costs 5.6 us on 128 threads (gather round trips
@@ -69,7 +89,9 @@ static int small_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& ep
     using CT = Cfg<P, TM>;
     const int smem_first = (CT::W_FLOATS + CT::TILE_FLOATS + S2V_MAX_F * P + TM * S2V_MAX_F + 6 * P) * 4;
     const int smem_head = (C::W_FLOATS + C::TILE_FLOATS + S2V_TM * C::TXP + 3 * P + C::RG * P + 2 * P) * 4;
-    const int smem = smem_first > smem_head ? smem_first : smem_head;
+    const int smem_rows = (CT::W_FLOATS + CT::TILE_FLOATS + 2 * TM * CT::TXP + 3 * P) * 4;      // head_rows_body
+    int smem = smem_first > smem_head ? smem_first : smem_head;
+    if (smem_rows > smem) smem = smem_rows;
     auto kernel = k_qnet_small<P, TM>;
     S2V_RETURN_IF(cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
     int dev = 0, sms = 0, per_sm = 0;
@@ -96,7 +118,8 @@ extern "C" int s2v_qnet_small_eligible(int32_t emb_dim, int32_t flags, int64_t n
     if (emb_dim == 64 && (flags == S2V_PATH_TENSOR || flags == S2V_PATH_TENSOR_WS)) return 0;
     if (emb_dim == 64 && flags != S2V_PATH_FFMA && num_nodes >= S2V_TENSOR_MIN_NODES) return 0;
     if (num_nodes > 16 * S2V_TENSOR_MIN_NODES) return 0;        // beyond that a stage fills the machine: per-stage launches
-    return num_nodes <= 256 * num_graphs ? 1 : 0;               // head stage = one CTA per graph (s2v_head_fused_eligible)
+    (void)num_graphs;                                           // graphs of any size: fused or tile-parallel head stage
+    return 1;
 }
 
 extern "C" int s2v_qnet_small_forward(const s2v_graph_t* g, const s2v_embed_params_t* eprm, const s2v_head_params_t* hprm,

@@ -144,7 +144,7 @@ def test_small_graph_single_launch_bit_identical(topo_name, B, p, cuda_device):
     layouts = [sb.GraphLayout.replicated(topo.edge_index.to(dev), N, B, n_pad=N + 3),
                sb.GraphLayout.from_batch(sb.graphs.batch_edge_index(topo, B, device=dev), ptr.to(dev), N + 3)]
     big = sb.GraphLayout.replicated(sb.graphs.load_topology("NWB_AMS").edge_index.to(dev), 975, 2)
-    assert not ops.qnet_small_eligible(big, ew) and not ops.head_fused_eligible(big, hw)     # few large graphs: per-stage path
+    assert not ops.head_fused_eligible(big, hw)              # few large graphs: the head is tile-parallel (next test)
     for lay in layouts:
         assert ops.qnet_small_eligible(lay, ew)
         base0, mus0 = ops._embed_forward(lay, T, x, ew)
@@ -170,6 +170,63 @@ def test_small_graph_single_launch_bit_identical(topo_name, B, p, cuda_device):
     graph.replay()
     torch.cuda.synchronize()
     assert torch.equal(qg, q0)
+
+
+@pytest.mark.parametrize("B,p,layout_kind", [(1, 64, "rep"), (3, 64, "rep"), (2, 64, "bat"), (1, 32, "rep"), (2, 16, "var")])
+def test_single_launch_large_graphs_bit_identical(B, p, layout_kind, cuda_device):
+    """Acting on a road network (AMS, 975 rows per graph, B = 1..3): the cooperative launch runs the head as three
+    tile-parallel stages (pool + theta6 | q per row tile | mask + reduction) behind grid barriers.  Everything equals the
+    per-stage launches (s2v_embed_forward, s2v_head_forward, masked softmax / max, list arg-max) bit for bit."""
+    import simmodel_b200 as sb
+    from simmodel_b200 import ops
+    from oracle import s2v_ref as R
+    dev = cuda_device
+    ams = sb.graphs.load_topology("NWB_AMS")
+    T = 5
+    gen = torch.Generator().manual_seed(7 * B + p)
+    if layout_kind == "var":                                  # graphs of different sizes in one batch (AMS + UTR)
+        utr = sb.graphs.load_topology("NWB_UTR")
+        topos = [ams, utr][:B]
+        sizes = [tp.num_nodes for tp in topos]
+        ptr = torch.tensor([0] + list(torch.tensor(sizes).cumsum(0)), dtype=torch.int64)
+        ei = torch.cat([tp.edge_index + int(ptr[i]) for i, tp in enumerate(topos)], dim=1)
+        lay = sb.GraphLayout.from_batch(ei.to(dev), ptr.to(dev), max(sizes) + 2)
+        x = torch.cat([sb.graphs.synth_nfm(tp, 1, gen).reshape(-1, sb.graphs.NODE_DIM) for tp in topos]).to(dev)
+    else:
+        N = ams.num_nodes
+        ptr = torch.arange(B + 1, dtype=torch.int64) * N
+        lay = (sb.GraphLayout.replicated(ams.edge_index.to(dev), N, B) if layout_kind == "rep" else
+               sb.GraphLayout.from_batch(sb.graphs.batch_edge_index(ams, B, device=dev), ptr.to(dev), N))
+        x = sb.graphs.synth_nfm(ams, B, gen).reshape(-1, sb.graphs.NODE_DIM).to(dev)
+    n = lay.num_nodes
+    P = R.make_qnet_params(sb.graphs.NODE_DIM, p, seed=p)
+    ew = [P[k + s].to(dev) for k in ops.EMBED_NAMES for s in (".weight", ".bias")]
+    hw = [P[k + s].to(dev) for k in ops.HEAD_NAMES for s in (".weight", ".bias")]
+    mask = (torch.rand(n, generator=gen) < 0.3).to(dev)
+    mask[ptr[:-1].to(dev)] = True
+    m8 = ops._mask_u8(mask, n)
+    nb = len(ptr) - 1
+    rptr = (torch.arange(nb + 1, dtype=torch.int32) * 3).to(dev)
+    ridx = torch.tensor([5, 17, 2] * nb, dtype=torch.int32, device=dev)
+    assert ops.qnet_small_eligible(lay, ew) and not ops.head_fused_eligible(lay, hw)
+    base0, mus0 = ops._embed_forward(lay, T, x, ew)
+    pool0, g0, q0 = ops._head_forward(lay, True, mus0[T - 1], hw)
+    prob0 = ops.masked_softmax(lay, q0, mask)
+    val0, arg0 = ops.masked_max(lay, q0, mask)
+    lpos0, lnode0, lval0 = ops.list_argmax(lay, q0, rptr, ridx)
+    base, mus, pool, gst, q, prob = ops._qnet_small_forward(lay, T, x, ew, hw, True, "softmax", m8)[:6]
+    for a, b in ((base, base0), (mus, mus0), (pool, pool0), (gst, g0), (q, q0), (prob, prob0)):
+        assert torch.equal(a, b)
+    out = ops._qnet_small_forward(lay, T, x, ew, hw, True, "max", m8)
+    assert torch.equal(out[4], q0) and torch.equal(out[6], arg0) and torch.equal(out[8], val0)
+    out = ops._qnet_small_forward(lay, T, x, ew, hw, True, "list", None, rptr, ridx)
+    assert torch.equal(out[4], q0) and torch.equal(out[6], lpos0) and torch.equal(out[7], lnode0) and torch.equal(out[8], lval0)
+    assert torch.equal(ops._qnet_small_forward(lay, T, x, ew, hw, True, "q")[4], q0)
+    # against the oracle (fp32 tolerance) -- the single launch is also RIGHT, not only equal to the other path
+    if layout_kind != "var":
+        ei_ref = sb.graphs.batch_edge_index(ams, B)
+        q_ref = R.qnet_forward_sparse(P, x.cpu(), ei_ref, ptr, ams.num_nodes, T, True)
+        assert float((q.cpu() - q_ref).abs().max() / q_ref.abs().max()) < 1e-5
 
 
 def test_torch_library_ops_match_the_module_path(cuda_device):
