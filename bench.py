@@ -97,24 +97,27 @@ def reference_config(sample_b, kind):
 # --------------------------------------------------------------------------------------
 # CPU reference arithmetic (oracle; timed as the baseline only)
 # --------------------------------------------------------------------------------------
-def cpu_reference_step_fn(kind, batch):
-    """Returns (step_fn, graphs_per_step, description). kind: 'dense' (reference arithmetic) or 'sparse'."""
+def cpu_reference_step_fn(kind, batch, device="cpu"):
+    """Returns (step_fn, graphs_per_step, description). kind: 'dense' (reference arithmetic) or 'sparse'.
+    device 'cuda': the same restatement on torch's CUDA ops (what the reference does when it finds a GPU,
+    comb_opt.py:44) -- the caller runs step() inside `with torch.device(device)`."""
     import torch
     from oracle import s2v_ref as R
     from simmodel_b200 import graphs
     topo = graphs.load_topology(TOPO)
     gen = torch.Generator().manual_seed(0)
     N = topo.num_nodes
-    xv = graphs.synth_nfm(topo, batch, gen)
-    Pm = {k: v.requires_grad_(True) for k, v in R.make_qnet_params(F, P, seed=0).items()}
+    xv = graphs.synth_nfm(topo, batch, gen).to(device)
+    Pm = {k: v.to(device).requires_grad_(True) for k, v in R.make_qnet_params(F, P, seed=0).items()}
     sizes = [N] * batch
     bt = R.batch_from_sizes(sizes, [topo.edge_index] * batch)
+    bt.ptr, bt.batch, bt.edge_index = bt.ptr.to(device), bt.batch.to(device), bt.edge_index.to(device)
     actions = torch.randint(0, N, (batch,), generator=gen).tolist()
     targets = torch.randn(batch, generator=gen).tolist()
     if kind == "dense":
         W = torch.zeros(N, N)
         W[topo.edge_index[0], topo.edge_index[1]] = 1.0
-        Ws = W.unsqueeze(0).repeat(batch, 1, 1)
+        Ws = W.unsqueeze(0).repeat(batch, 1, 1).to(device)
 
         def step():
             for v in Pm.values():
@@ -990,9 +993,38 @@ def measure_cpu_baseline():
     step2, gps2, desc2 = cpu_reference_step_fn("sparse", 64)
     times2 = time_cpu(step2, 3, 6.0)
     sparse = gps2 / statistics.mean(times2)
-    return {"value": dense, "unit": UNIT, "cores": cores, "kind": "port",
-            "sample": "%s, %d steps; torch %s CPU" % (desc, len(times), torch.__version__),
-            "sparse_port": {"value": sparse, "unit": UNIT, "sample": "%s, %d steps" % (desc2, len(times2))}}
+    out = {"value": dense, "unit": UNIT, "cores": cores, "kind": "port",
+           "sample": "%s, %d steps; torch %s CPU" % (desc, len(times), torch.__version__),
+           "sparse_port": {"value": sparse, "unit": UNIT, "sample": "%s, %d steps" % (desc2, len(times2))}}
+    out["torch_on_this_gpu"] = measure_torch_gpu_port()
+    return out
+
+
+def measure_torch_gpu_port():
+    """The same restatements on torch's CUDA ops on this GPU (the reference picks device='cuda' when it finds one,
+    comb_opt.py:44): what a user of the unmodified reference arithmetic would get from the same B200.  Bounded
+    samples; reported next to the CPU figures, not instead of them."""
+    import torch
+    res = {}
+    for kind, batch in (("dense", 8), ("sparse", 256)):
+        try:
+            step, gps, desc = cpu_reference_step_fn(kind, batch, "cuda")      # inputs built on the host, moved over
+            with torch.device("cuda"):                                        # tensors the restatement creates itself
+                for _ in range(2):
+                    step()
+                torch.cuda.synchronize()
+                t0 = time.perf_counter()
+                n = 0
+                while n < 3 or (time.perf_counter() - t0 < 3.0 and n < 50):
+                    step()
+                    n += 1
+                torch.cuda.synchronize()
+                dt = (time.perf_counter() - t0) / n
+            res[kind] = {"value": gps / dt, "unit": UNIT, "sample": desc.replace("CPU ", "") + ", torch CUDA ops, %d steps" % n}
+        except Exception as e:                                  # an OOM or a device mismatch here must not cost the bench line
+            res[kind] = {"error": "%s: %s" % (type(e).__name__, str(e)[:120])}
+        torch.cuda.empty_cache()
+    return res
 
 
 def main():

@@ -213,9 +213,12 @@ int s2v_head_fused_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes, i
  * launch with grid-wide barriers between the stages (csrc/s2v_small.cu).  For acting (B = 1), the reference's
  * Manhattan5 / MemTask batches and the per-rollout PPO calls, where a stage is microseconds and T + 3 launches are the
  * cost.  Same stage code as the per-stage CUDA-core kernels: results bit-identical to s2v_embed_forward followed by
- * s2v_head_fused_forward.  mode -1: embedding only (hprm and the head outputs may be NULL); 0..3 as
- * s2v_head_fused_forward.  s2v_qnet_small_eligible(): 1 when the problem runs the CUDA-core path, has at most 65 536 rows
- * and graphs of at most 256 nodes on average; otherwise s2v_qnet_small_forward returns S2V_ERR_UNSUPPORTED.
+ * s2v_head_fused_forward (graphs of at most 256 nodes on average: one CTA walks a graph) or by s2v_head_forward and the
+ * mask kernels (larger graphs, e.g. acting on a 975-node road network: the head stage is tile-parallel -- pool + theta6
+ * per graph | q per row tile | mask + reduction per graph -- with two more grid barriers).  mode -1: embedding only
+ * (hprm and the head outputs may be NULL); 0..3 as s2v_head_fused_forward.  s2v_qnet_small_eligible(): 1 when the
+ * problem runs the CUDA-core path and has at most 65 536 rows; otherwise s2v_qnet_small_forward returns
+ * S2V_ERR_UNSUPPORTED.
  * Replaces comb_opt.py:297-331 (predict / get_best_action) and models_basic_lstm.py:526-566 (pi / v per rollout). */
 int s2v_qnet_small_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes, int64_t num_graphs);
 int s2v_qnet_small_forward(const s2v_graph_t* g, const s2v_embed_params_t* eprm, const s2v_head_params_t* hprm,
