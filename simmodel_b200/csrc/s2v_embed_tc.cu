@@ -1213,7 +1213,19 @@ k_tc_selftest16(int mode, const float* __restrict__ A, const float* __restrict__
 // ------------------------------------------------------------------------------------
 constexpr int WS_P_WARPS = 8, WS_F_WARP0 = 8, WS_E_WARP0 = 12;
 constexpr int WS_THREADS = 512;
-constexpr int WS_STAGES = 3;
+#ifndef S2V_WS_STAGES
+#define S2V_WS_STAGES 3
+#endif
+constexpr int WS_STAGES = S2V_WS_STAGES;
+#ifndef S2V_WSF_STAGES
+#define S2V_WSF_STAGES 1
+#define S2V_WSF_SLOTS 7
+#define S2V_WSF_LAG 2
+#endif
+constexpr int WSF_STAGES = S2V_WSF_STAGES;                            // last stage: ONE operand stage (its producers hold the next tile in registers
+                                                         // while the MMAs read it) -- the other two are the TMA landing ring
+constexpr int WSF_SLOTS = S2V_WSF_SLOTS;                             // landing slots of one tile plane (64 rows x 256 B = 16 KB): 112 KB in flight
+constexpr int WSF_LAG = S2V_WSF_LAG;                               // a slot is re-armed WSF_LAG reads after it was read
 constexpr int WS_D2_GROUP = 4;                           // tiles accumulated in TMEM between two read-outs of D2x
 constexpr uint32_t WS_STAGE_BYTES = 2 * TILE16X3;        // [g3][g1][g2][m2][m1][m3]
 constexpr int WS_STG_FLOATS = TCR * STG_LD;              // one staging buffer (two: tile parity)
@@ -1276,6 +1288,14 @@ __device__ __forceinline__ void issue_ws_reduce(uint32_t d2x, uint32_t d2y, uint
 //   (Npad - c) D, dh.
 // D takes the place of g (P streams and sums the T planes instead of gathering), h = relu(theta1a x + b1a) the place
 // of mu (E recomputes it from the x tile), theta1b the place of theta2; instead of storing dh, E reduces it against x.
+#ifdef S2V_WSF_PROF
+__device__ long long g_wsf_prof[16];
+#define WSFP(i, a, b) do { if (FINAL && blockIdx.x == 0 && t == 0) wsfp[i] += (b) - (a); } while (0)
+#define WSFT(v) const long long v = clock64()
+#else
+#define WSFP(i, a, b) do {} while (0)
+#define WSFT(v) do {} while (0)
+#endif
 struct WsArgs {
     const float* w;          // theta2 | theta1b  [64][64]
     const float* src;        // du^t (gathered) | du^1..du^{T-1} planes
@@ -1298,11 +1318,17 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
     extern __shared__ __align__(1024) uint8_t smem_raw[];
     uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
     uint8_t* w_tiles = smem;                                 // W^T: tile(row n, col k) = W[k][n], pieces [t2][t1][t3]
+    // The last stage runs on TWO operand stages: the third one's 48 KB are the landing ring of its TMA plane streams.
+    constexpr int NST = FINAL ? WSF_STAGES : WS_STAGES;
     uint8_t* stage0 = w_tiles + TILE16X3;
-    float* stg0 = reinterpret_cast<float*>(stage0 + WS_STAGES * WS_STAGE_BYTES);    // 2 staging buffers
-    float* xs0 = stg0 + 2 * WS_STG_FLOATS;                   // FINAL: 3 x tiles [64][F]
-    float* pscr = xs0 + 3 * TCR * WS_MAX_F;                  // FINAL: [16][64] reduction scratch of the producers
-    WsShared* sh = reinterpret_cast<WsShared*>(pscr + 16 * 64);
+    float* stg0 = reinterpret_cast<float*>(stage0 + NST * WS_STAGE_BYTES);          // 2 staging buffers
+    float* xs0 = stg0 + 2 * WS_STG_FLOATS;                   // FINAL: NST x tiles [64][F]
+    WsShared* sh = reinterpret_cast<WsShared*>(xs0 + 3 * TCR * WS_MAX_F);
+    // FINAL: per-producer-warp landing rings (WSF_SLOTS slots of 8 rows x 256 B) + their mbarriers; the first 4 KB double as
+    // the producers' reduction scratch [16][64] once every copy has landed and been read
+    uint64_t* lbar = reinterpret_cast<uint64_t*>(reinterpret_cast<uint8_t*>(sh) + 256);     // full[WSF_SLOTS], empty[WSF_SLOTS]
+    float* land = reinterpret_cast<float*>(reinterpret_cast<uint8_t*>(lbar) + 128);
+    float* pscr = FINAL ? land : reinterpret_cast<float*>(lbar);
     const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
     const float* __restrict__ theta2_w = a.w;
     const float* __restrict__ du_t = a.src;
@@ -1332,6 +1358,8 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
             tc::mbar_init(&sh->stg_empty[i], 4);
         }
         tc::mbar_init(&sh->d2_free, 4);
+        if (FINAL)
+            for (int i = 0; i < WSF_SLOTS; ++i) { tc::mbar_init(&lbar[i], 1); tc::mbar_init(&lbar[WSF_SLOTS + i], WS_P_WARPS); }
         tc::fence_barrier_init();
     }
     for (int e = t; e < 64 * 16; e += WS_THREADS) {          // row n of the tile = column n of theta2
@@ -1370,7 +1398,32 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
             if (my_tiles > 1) { tile_rows(1, row0, rows); gatherN_extents<4>(pipe.ext1, g, g.rowptr_t, row0, rows, rl0); }
         }
         float4 pD = f4zero(), pA1 = f4zero(), pA0 = f4zero();  // FINAL: column sums of D, c D, (Npad - c) D over this lane's rows
-        int s = 0, par = 0;                                   // s = k % 3, par = (k / 3) & 1
+#ifdef S2V_WSF_PROF
+        long long wsfp[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+        const long long wsf_t0 = clock64();
+#endif
+        // FINAL: the T planes of a tile arrive by TMA.  Request r = (tile r / T, plane r % T): ONE cp.async.bulk of the
+        // tile's 64 rows (16 KB, contiguous) into slot r % WSF_SLOTS of the landing ring, completion as transaction bytes
+        // on full[slot].  All eight producer warps read their rows of the slot and arrive on empty[slot]; request
+        // r + WSF_SLOTS re-arms the slot.  A cp.async.bulk costs its issuing thread 200 - 400 cycles (scripts/bulk_rate.py),
+        // so the issues rotate over the warps -- warp r % 8 issues request r, WSF_LAG reads after the slot's previous
+        // content was read, when every warp is past it -- instead of stalling one warp five times per tile.
+        uint64_t* lfull = lbar;
+        uint64_t* lempty = lbar + WSF_SLOTS;
+        const int fT = FINAL ? a.T : 1;
+        const int ftotal = FINAL ? my_tiles * fT : 0;
+        int freq = 0, fslot = 0, fphase = 0;                   // next request to read: slot freq % WSF_SLOTS, parity (freq / WSF_SLOTS) & 1
+        auto final_request = [&](int r) {                      // one lane: issue request r
+            const int kk = r / fT, j = r - kk * fT, slot = r % WSF_SLOTS;
+            int row0, rows;
+            tile_rows(kk, row0, rows);
+            const float* src_plane = j < fT - 1 ? a.src + (size_t)j * ((size_t)g.num_nodes * 64) : a.own;
+            tc::mbar_arrive_expect_tx(&lfull[slot], rows * 256);
+            tc::bulk_g2s(tc::smem_u32(land + slot * (TCR * 64)), src_plane + (size_t)row0 * 64, rows * 256, &lfull[slot]);
+        };
+        if (FINAL && lane == 0)
+            for (int r = warp; r < WSF_SLOTS && r < ftotal; r += WS_P_WARPS) final_request(r);
+        int s = 0, par = 0;                                   // s = k % NST, par = (k / NST) & 1
         for (int k = 0; k < my_tiles; ++k) {
             uint8_t* gt = stage0 + s * WS_STAGE_BYTES;
             float4 acc[4];
@@ -1381,9 +1434,9 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
                                   [&](int& r2, int& n2) { r2 = 0; n2 = 0; if (k + 2 < my_tiles) tile_rows(k + 2, r2, n2); },
                                   [&]() {}, acc);
             } else {
+                // D = sum_t du^t, planes in the order t = 1..T, read from the landing ring
                 int row0, rows;
                 tile_rows(k, row0, rows);
-                const size_t plane = (size_t)g.num_nodes * 64;
                 float cf[4], df[4];
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -1395,20 +1448,25 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
                         df[i] = (float)graph_npad(g, gi) - cf[i];
                     }
                 }
-                for (int p0 = 0; p0 < a.T; p0 += 5) {          // fixed summation order t = 1..T, 20 loads in flight per lane
-                    float4 v[4][5];
+                for (int j = 0; j < fT; ++j, ++freq) {
+                    WSFT(p_a);
+                    tc::mbar_wait(&lfull[fslot], fphase);
+                    WSFT(p_b); WSFP(0, p_a, p_b);
+                    const float* lp = land + fslot * (TCR * 64) + rl0 * 64 + 4 * c4;
 #pragma unroll
-                    for (int j = 0; j < 5; ++j) {
-                        const int pl = p0 + j;
-                        const float* base = pl < a.T - 1 ? a.src + (size_t)pl * plane : a.own;
-#pragma unroll
-                        for (int i = 0; i < 4; ++i)
-                            v[i][j] = (pl < a.T && rl0 + i < rows) ? ldg4(base + (size_t)(row0 + rl0 + i) * 64 + 4 * c4) : f4zero();
+                    for (int i = 0; i < 4; ++i)
+                        if (rl0 + i < rows) acc[i] = f4add(acc[i], ld4(lp + i * 64));
+                    __syncwarp();
+                    if (lane == 0) tc::mbar_arrive(&lempty[fslot]);
+                    WSFT(p_c); WSFP(1, p_b, p_c);
+                    // request rq re-arms the slot that was read WSF_LAG reads ago; its issuer is warp rq % 8
+                    const int rq = freq - WSF_LAG + WSF_SLOTS;
+                    if (rq >= WSF_SLOTS && rq < ftotal && (rq % WS_P_WARPS) == warp && lane == 0) {
+                        tc::mbar_wait(&lempty[rq % WSF_SLOTS], ((rq / WSF_SLOTS) - 1) & 1);     // all eight warps have read request rq - WSF_SLOTS
+                        final_request(rq);
                     }
-#pragma unroll
-                    for (int j = 0; j < 5; ++j)
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) acc[i] = f4add(acc[i], v[i][j]);
+                    WSFT(p_d); WSFP(2, p_c, p_d);
+                    if (++fslot == WSF_SLOTS) { fslot = 0; fphase ^= 1; }
                 }
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
@@ -1420,7 +1478,9 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
                 }
             }
             TLW(t == 0, k, 1);
+            WSFT(p_e);
             tc::mbar_wait(&sh->mma_done[s], par ^ 1);            // the MMAs of tile k-3 have finished reading stage s
+            WSFT(p_f); WSFP(3, p_e, p_f);
             TLW(t == 0, k, 2);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1428,10 +1488,18 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh->full_g[s]);
+            WSFT(p_g); WSFP(4, p_f, p_g);
             TLW(t == 0, k, 3);
-            if (++s == WS_STAGES) { s = 0; par ^= 1; }
+            if (++s == NST) { s = 0; par ^= 1; }
         }
+#ifdef S2V_WSF_PROF
+        if (FINAL && blockIdx.x == 0 && t == 0) {
+            for (int i = 0; i < 5; ++i) g_wsf_prof[i] = wsfp[i];
+            g_wsf_prof[5] = clock64() - wsf_t0; g_wsf_prof[6] = my_tiles;
+        }
+#endif
         if constexpr (FINAL) {                                 // column sums over the 16 half-warps, fixed order
+            tc::named_bar_sync(3, 32 * WS_P_WARPS);            // pscr aliases the landing ring: every warp has read its last slot
             float* my = partial + (size_t)blockIdx.x * partial_stride;
             const int hw = t >> 4;                             // 0..15
             const float4 vals[3] = {pD, pA1, pA0};
@@ -1460,7 +1528,7 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
         for (int i = 0; i < 64; ++i) racc[i] = 0.f;
 
         auto drain = [&](int j) {                              // tile j: D1w -> staging; group end: D2x -> racc
-            const int sj = j % WS_STAGES, pj = (j / WS_STAGES) & 1, bj = j & 1;
+            const int sj = j % NST, pj = (j / NST) & 1, bj = j & 1;
             float* stg = stg0 + bj * WS_STG_FLOATS;
             tc::mbar_wait2(&sh->mma_done[sj], pj, &sh->stg_empty[bj], ((j >> 1) & 1) ^ 1);
             TLW(t == 32 * WS_F_WARP0, j, 13);
@@ -1516,7 +1584,7 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
                 tc::mma_commit(&sh->mma_done[s]);
                 TLW(lane == 0, k, 5);
             }
-            if (++s == WS_STAGES) { s = 0; par ^= 1; }
+            if (++s == NST) { s = 0; par ^= 1; }
         }
         if (my_tiles > 0) {
             drain(my_tiles - 1);
@@ -1587,11 +1655,11 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
             }
         };
         auto store_m = [&](int k) -> uint32_t {                // registers -> m tiles of stage k % 3; returns the sign bits
-            const int sk = k % WS_STAGES, pk = (k / WS_STAGES) & 1;
+            const int sk = k % NST, pk = (k / NST) & 1;
             uint8_t* mt = stage0 + sk * WS_STAGE_BYTES + TILE16X3;
-            const float* xs = xs0 + sk * TCR * WS_MAX_F;
-            if constexpr (FINAL) {                             // x tile -> shared memory
-                float* xw = xs0 + sk * TCR * WS_MAX_F;
+            const float* xs = xs0 + (k % 3) * TCR * WS_MAX_F;    // three x tiles whatever the number of operand stages: tile k+1
+            if constexpr (FINAL) {                             // is staged while the dh of tile k-1 is still reduced against its x
+                float* xw = xs0 + (k % 3) * TCR * WS_MAX_F;
                 tc::named_bar_sync(1, 128);                    // every E thread is done with the x tile of k-3
                 if (et < TCR) {
                     st4(xw + et * WS_MAX_F, make_float4(xr[0], xr[1], xr[2], xr[3]));
@@ -1633,7 +1701,7 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
             int row0, rows;
             tile_rows(j, row0, rows);
             const float* stg = stg0 + bj * WS_STG_FLOATS;
-            const float* xs = xs0 + (j % WS_STAGES) * TCR * WS_MAX_F;
+            const float* xs = xs0 + (j % 3) * TCR * WS_MAX_F;
             tc::mbar_wait(&sh->stg_full[bj], (j >> 1) & 1);
             TLW(et == 0, j, 9);
 #pragma unroll
@@ -1771,7 +1839,11 @@ k_tc_rate(float* __restrict__ out, int reps) {
 }
 
 constexpr int FWD_SMEM = 4 * TILE_BYTES + 64 + 1024;
-constexpr int WS_SMEM = TILE16X3 + WS_STAGES * WS_STAGE_BYTES + 2 * WS_STG_FLOATS * 4 + (3 * TCR * WS_MAX_F + 16 * 64) * 4 + 256 + 1024;
+constexpr int WS_SMEM = TILE16X3 + WS_STAGES * WS_STAGE_BYTES + 2 * WS_STG_FLOATS * 4 + (3 * TCR * WS_MAX_F + 16 * 64) * 4 + 256 + 256 + 1024;
+constexpr int WSF_SMEM = TILE16X3 + WSF_STAGES * WS_STAGE_BYTES + 2 * WS_STG_FLOATS * 4 + 3 * TCR * WS_MAX_F * 4 + 256 + 128 +
+                         WSF_SLOTS * TCR * 256 + 1024;
+static_assert(WSF_SMEM <= 232448 && 2 * WSF_SLOTS * 8 <= 128, "last-stage shared memory");
+static_assert(sizeof(WsShared) <= 256, "WsShared");
 static inline int first_smem_bytes(int F) {
     const int FS = (F + 3) & ~3;
     return 2 * (int)TILE16X3 + (FS * 64 + TCR * FS + 6 * 64 + 128) * 4 + 64 + 1024;
@@ -2186,11 +2258,11 @@ int s2v_tc_final_backward_ws(const s2v_graph_t& g, const s2v_embed_params_t& prm
     a.x = x; a.th1a_w = prm.theta1a_w; a.th1a_b = prm.theta1a_b; a.F = prm.node_dim; a.T = prm.rounds;
     a.partial = partial; a.partial_stride = partial_stride; a.accumulate = 0;
     a.num_tiles = (g.num_nodes + TCR - 1) / TCR;
-    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_bwd_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WS_SMEM));
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_bwd_ws<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, WSF_SMEM));
 #ifdef S2V_WS_EXPERIMENTS
     if (const char* e = getenv("S2V_WS_EXP_FINAL")) a.accumulate |= atoi(e) << 8;
 #endif
-    k_embed_bwd_ws<true><<<grid, WS_THREADS, WS_SMEM, st>>>(g, a);
+    k_embed_bwd_ws<true><<<grid, WS_THREADS, WSF_SMEM, st>>>(g, a);
     return (int)cudaGetLastError();
 }
 
@@ -2203,6 +2275,9 @@ int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const flo
     return (int)cudaGetLastError();
 }
 
+#ifdef S2V_WSF_PROF
+extern "C" int s2v_debug_wsf_prof(long long* host_out) { return (int)cudaMemcpyFromSymbol(host_out, g_wsf_prof, sizeof(long long) * 16); }
+#endif
 #ifdef S2V_RING_PROF
 extern "C" int s2v_debug_ring_prof(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, g_ring_prof, sizeof(long long) * 32);

@@ -300,3 +300,46 @@ extern "C" int s2v_debug_gather_probe(const s2v_graph_t* g, const float* src, co
 extern "C" int s2v_debug_gather_probe_prof(long long* host_out) {
     return (int)cudaMemcpyFromSymbol(host_out, g_probe_prof, sizeof(long long) * 16);
 }
+
+// ---- cp.async.bulk issue / service rate (debug): `warps` warps of one CTA per SM, lane 0 of each issues `n` bulk copies of
+// `bytes` bytes back to back into its own ring of 4 slots (no reuse protocol: timing only) and waits for all of them once.
+// out[0] = cycles lane 0 of warp 0 spent issuing, out[1] = cycles until everything had landed.
+namespace {
+__global__ void __launch_bounds__(512, 1)
+k_bulk_rate(const float* __restrict__ src, long long* __restrict__ out, int n, int bytes, int warps, int planes, long long plane_floats) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    __shared__ uint64_t bars[16];
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 16; ++i) tc::mbar_init(&bars[i], 1);
+        tc::fence_barrier_init();
+    }
+    __syncthreads();
+    if (warp < warps && lane == 0) {
+        uint8_t* ring = smem_raw + warp * 4 * bytes;
+        // planes > 1: copy i reads plane i % planes (planes are plane_floats apart), like the T planes of the last backward stage
+        const float* p = src + ((size_t)blockIdx.x * warps + warp) * (size_t)(n / planes + 1) * (bytes / 4);
+        const long long t0 = clock64();
+        for (int i = 0; i < n; ++i)
+            bulk_g2s(tc::smem_u32(ring + (i & 3) * bytes), p + (size_t)(i % planes) * plane_floats + (size_t)(i / planes) * (bytes / 4), bytes, &bars[warp]);
+        const long long t1 = clock64();
+        mbar_arrive_expect_tx(&bars[warp], (uint32_t)(n * bytes));
+        tc::mbar_wait(&bars[warp], 0);
+        const long long t2 = clock64();
+        if (blockIdx.x == 0 && warp == 0) { out[0] = t1 - t0; out[1] = t2 - t0; }
+    }
+}
+}  // namespace
+
+extern "C" int s2v_debug_bulk_rate(const float* src, long long* out_dev, int32_t n, int32_t bytes, int32_t warps, int32_t planes,
+                                   int64_t plane_floats, void* stream) {
+    if (planes < 1) return S2V_ERR_BAD_ARG;
+    if (warps < 1 || warps > 16 || bytes % 16 || bytes * 4 * warps > 200 * 1024 || n * bytes >= (1 << 20)) return S2V_ERR_BAD_ARG;
+    int dev = 0, sms = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    const int smem = bytes * 4 * warps + 1024;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_bulk_rate, cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+    k_bulk_rate<<<sms, 512, smem, (cudaStream_t)stream>>>(src, out_dev, n, bytes, warps, planes, plane_floats);
+    return (int)cudaGetLastError();
+}
