@@ -1214,7 +1214,7 @@ k_tc_selftest16(int mode, const float* __restrict__ A, const float* __restrict__
 constexpr int WS_P_WARPS = 8, WS_F_WARP0 = 8, WS_E_WARP0 = 12;
 constexpr int WS_THREADS = 512;
 #ifndef S2V_WS_STAGES
-#define S2V_WS_STAGES 3
+#define S2V_WS_STAGES 2      /* a third stage bought nothing: backward round 1.192 ms with two, 1.234 ms with three */
 #endif
 constexpr int WS_STAGES = S2V_WS_STAGES;
 #ifndef S2V_WSF_STAGES
