@@ -108,3 +108,55 @@ def test_parity_suite_with_tensor_path_forced(path, cuda_device):
                           "-q", "-x", "--tb=short", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
                          timeout=900, cwd=ROOT)
     assert out.returncode == 0, out.stdout[-3000:] + out.stderr[-1000:]
+
+
+@pytest.mark.parametrize("topo_name,B,kind,cfg", [("NWB_AMS", 37, "rep", "1,0,256"), ("NWB_AMS", 21, "bat", "1,0,64"),
+                                                  ("NWB_UTR", 9, "rep", "2,0,128"), ("Manhattan5", 300, "bat", "1,200,96")])
+def test_ring_forward_round_bit_identical(topo_name, B, kind, cfg, cuda_device):
+    """The asynchronous-gather forward round (k_embed_round_ring: LDGSTS ring + cp.async.bulk base tiles + tcgen05, opt-in with
+    S2V_B200_FWD_RING) computes the same bits as k_embed_round_tc16: same CSR-order sums, same split, same MMA order, same
+    epilogue.  Replicated and batched layouts, one and several chunks per tile, ragged last tile, tiles that straddle graphs."""
+    import simmodel_b200 as sb
+    from simmodel_b200 import _lib
+    from simmodel_b200.layout import _p, _stream
+    L = _lib.lib()
+    dev = cuda_device
+    topo = sb.graphs.load_topology(topo_name)
+    n = topo.num_nodes
+    N = B * n
+    if kind == "rep":
+        lay = sb.GraphLayout.replicated(topo.edge_index.to(dev), n, B)
+    else:
+        ptr = (torch.arange(B + 1, dtype=torch.int64) * n).to(dev)
+        lay = sb.GraphLayout.from_batch(sb.graphs.batch_edge_index(topo, B, device=dev), ptr, n)
+    gen = torch.Generator().manual_seed(B)
+    w2 = (torch.randn(64, 64, generator=gen) / 8).to(dev)
+    base = torch.randn(N, 64, generator=gen).to(dev)
+    mu = torch.rand(N, 64, generator=gen).to(dev)
+    g = lay.c_struct()
+
+    def run(out):
+        _lib.check(L.s2v_embed_round_forward(C.byref(g), 64, 3, _p(w2), _p(base), _p(mu), _p(out), _stream()), "round_forward")
+        torch.cuda.synchronize()
+
+    old = os.environ.pop("S2V_B200_FWD_RING", None)
+    try:
+        ref = torch.full((N, 64), float("nan"), device=dev)
+        run(ref)
+        os.environ["S2V_B200_FWD_RING"] = cfg
+        out = torch.full((N, 64), float("nan"), device=dev)
+        run(out)
+    finally:
+        os.environ.pop("S2V_B200_FWD_RING", None)
+        if old is not None:
+            os.environ["S2V_B200_FWD_RING"] = old
+    assert torch.equal(out, ref)
+    agg = torch.zeros(N, 64, device=dev).index_add_(0, lay_edge_rows(lay, topo, B, dev)[0], mu[lay_edge_rows(lay, topo, B, dev)[1]])
+    want = torch.relu(agg.double() @ w2.double().t() + base.double())
+    assert float((out.double() - want).abs().max() / want.abs().max()) < 2e-6
+
+
+def lay_edge_rows(lay, topo, B, dev):
+    import simmodel_b200 as sb
+    ei = sb.graphs.batch_edge_index(topo, B, device=dev)
+    return ei[0], ei[1]
