@@ -42,7 +42,7 @@
 extern "C" {
 #endif
 
-#define S2V_ABI_VERSION 4
+#define S2V_ABI_VERSION 5
 
 #define S2V_ERR_BAD_ARG        (-1)  /* null pointer / negative size / inconsistent sizes     */
 #define S2V_ERR_UNSUPPORTED    (-2)  /* emb_dim not in {8,16,24,32,48,64}, node_dim > 32; GAT: heads*channels > 128 */
@@ -221,6 +221,16 @@ int s2v_head_fused_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes, i
  * S2V_ERR_UNSUPPORTED.
  * Replaces comb_opt.py:297-331 (predict / get_best_action) and models_basic_lstm.py:526-566 (pi / v per rollout). */
 int s2v_qnet_small_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes, int64_t num_graphs);
+/* ABI 5: the same launch with a caller-owned workspace of s2v_qnet_small_workspace_floats() floats, which lets MANY CTAs
+ * pool the rows of a large graph (one [row group][p] partial per 64-row chunk, summed per thread in chunk order: the same
+ * association, hence the same bits, as one CTA walking the graph) -- the pool stage of B = 1 on a 975-node network drops
+ * from 11 us to ~4 us.  workspace NULL or too small, or graphs of at most 256 nodes: exactly s2v_qnet_small_forward. */
+int64_t s2v_qnet_small_workspace_floats(int32_t emb_dim, int64_t num_nodes, int64_t num_graphs);
+int s2v_qnet_small_forward_ws(const s2v_graph_t* g, const s2v_embed_params_t* eprm, const s2v_head_params_t* hprm,
+                              const float* x, float* base, float* mus, int32_t mode, const uint8_t* mask,
+                              const int32_t* reach_ptr, const int32_t* reach_idx, float* pool, float* gstate, float* q,
+                              float* prob, int64_t* arg_out, int64_t* node_out, float* val_out, float* workspace,
+                              int64_t workspace_floats, void* stream);
 int s2v_qnet_small_forward(const s2v_graph_t* g, const s2v_embed_params_t* eprm, const s2v_head_params_t* hprm,
                            const float* x, float* base, float* mus, int32_t mode, const uint8_t* mask,
                            const int32_t* reach_ptr, const int32_t* reach_idx, float* pool, float* gstate, float* q,

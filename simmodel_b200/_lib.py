@@ -59,6 +59,8 @@ SIGNATURES = {
     "s2v_head_fused_eligible": (C.c_int, [i32, i32, i64, i64]),
     "s2v_qnet_small_eligible": (C.c_int, [i32, i32, i64, i64]),
     "s2v_qnet_small_forward": (C.c_int, [GP, EP, HP, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp]),
+    "s2v_qnet_small_workspace_floats": (i64, [i32, i64, i64]),
+    "s2v_qnet_small_forward_ws": (C.c_int, [GP, EP, HP, vp, vp, vp, i32, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, vp]),
     "s2v_head_backward_workspace_bytes": (i64, [i32, i32]),
     "s2v_head_backward": (C.c_int, [GP, HP, vp, vp, vp, vp, i32, vp, vp, i64, vp, vp]),
     "s2v_pool_forward": (C.c_int, [GP, i32, i32, vp, vp, vp]),
@@ -103,7 +105,7 @@ def lib():
                     fn = getattr(handle, name)
                     fn.restype = res
                     fn.argtypes = args
-                if handle.s2v_abi_version() != 4:
+                if handle.s2v_abi_version() != 5:
                     raise S2VError("simmodel_b200: ABI version mismatch")
                 _lib = handle
     return _lib

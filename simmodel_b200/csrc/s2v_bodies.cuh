@@ -361,6 +361,76 @@ __device__ __forceinline__ void pool_stage_body(float* smem, const s2v_graph_t& 
     }
 }
 
+// The same pooling by MANY CTAs (one large graph: acting on a road network).  Item = (graph, 64-row chunk of the graph);
+// items blockIdx.x, + gridDim.x, ... : thread (ty, tx) stores its chunk partial to ws[(item * RG + ty) * P + 4 tx].
+// pool_reduce_body then sums a graph's chunk partials per thread in chunk order and finishes as pool_graph does: the same
+// association, so the result has the same bits as one CTA walking the whole graph.
+template <int P, int LD = 0>
+__device__ __forceinline__ void pool_partials_body(const s2v_graph_t& g, const float* mu, float* __restrict__ ws) {
+    using C = Cfg<P>;
+    const int t = threadIdx.x;
+    const int tx = t % C::TXP, ty = t / C::TXP;
+    if (t >= C::ACTIVE) return;
+    int item0 = 0;
+    for (int gi = 0; gi < g.num_graphs; ++gi) {
+        int lo, hi;
+        graph_range(g, gi, lo, hi);
+        const int n = hi - lo, nch = (n + S2V_POOL_CHUNK - 1) / S2V_POOL_CHUNK;
+        const int first = item0 + (((int)blockIdx.x - item0 % (int)gridDim.x) + (int)gridDim.x) % (int)gridDim.x;
+        for (int it = first; it < item0 + nch; it += gridDim.x) {
+            const int c0 = (it - item0) * S2V_POOL_CHUNK;
+            const float4 c = pool_chunk_partial<P, LD>(mu, lo, c0, min(n, c0 + S2V_POOL_CHUNK), ty, tx);
+            st4(ws + ((size_t)it * C::RG + ty) * P + 4 * tx, c);
+        }
+        item0 += nch;
+    }
+}
+
+template <int P>
+__device__ __forceinline__ void pool_reduce_body(float* smem, const s2v_graph_t& g, int norm_agg, const float* ws,
+                                                 float* __restrict__ pool, const float* __restrict__ theta6_w,
+                                                 const float* __restrict__ theta6_b, float* __restrict__ gstate) {
+    using C = Cfg<P>;
+    float* scratch = smem;
+    float* pool_s = scratch + C::RG * P;
+    const int t = threadIdx.x;
+    const int tx = t % C::TXP, ty = t / C::TXP;
+    int item0 = 0;
+    for (int gi = 0; gi < g.num_graphs; ++gi) {
+        int lo, hi;
+        graph_range(g, gi, lo, hi);
+        const int n = hi - lo, nch = (n + S2V_POOL_CHUNK - 1) / S2V_POOL_CHUNK;
+        if (gi % (int)gridDim.x == (int)blockIdx.x) {
+            float4 s = f4zero();
+            if (t < C::ACTIVE) {
+                const float* base = ws + ((size_t)item0 * C::RG + ty) * P + 4 * tx;
+                int c = 0;
+                for (; c + 8 <= nch; c += 8) {               // eight chunk partials in flight, added in chunk order
+                    float4 v[8];
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) v[u] = ld_row4<1>(base + (size_t)(c + u) * C::RG * P);
+#pragma unroll
+                    for (int u = 0; u < 8; ++u) s = f4add(s, v[u]);
+                }
+                for (; c < nch; ++c) s = f4add(s, ld_row4<1>(base + (size_t)c * C::RG * P));
+            }
+            pool_finish<P>(s, scratch, pool_s, tx, ty, t < C::ACTIVE);
+            if (t < P) {
+                float pv = norm_agg ? pool_s[t] / (float)(n > 1 ? n : 1) : pool_s[t];
+                pool_s[t] = pv;
+                pool[(size_t)gi * P + t] = pv;
+            }
+            __syncthreads();
+            if (t < P) {
+                float a = row_dot<P>(theta6_w + t * P, pool_s, __ldg(theta6_b + t));
+                gstate[(size_t)gi * P + t] = a;
+            }
+            __syncthreads();
+        }
+        item0 += nch;
+    }
+}
+
 // q of the row tiles blockIdx.x, + gridDim.x, ... (TM rows each); gstate = theta6 pool + b6 per graph
 template <int P, int LD = 0, int TM = S2V_TM>
 __device__ __forceinline__ void head_rows_body(float* smem, const s2v_graph_t& g, const s2v_head_params_t& prm, const float* mu,

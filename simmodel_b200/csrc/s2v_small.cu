@@ -31,7 +31,7 @@ k_qnet_small(s2v_graph_t g, s2v_embed_params_t eprm, s2v_head_params_t hprm, con
              float* base, float* mus, int mode, const uint8_t* __restrict__ mask, const int32_t* __restrict__ reach_ptr,
              const int32_t* __restrict__ reach_idx, float* __restrict__ pool, float* __restrict__ gstate, float* q,
              float* __restrict__ prob, int64_t* __restrict__ arg_out, int64_t* __restrict__ node_out,
-             float* __restrict__ val_out) {
+             float* __restrict__ val_out, float* pool_ws) {
     extern __shared__ __align__(16) float smem[];
     cg::grid_group grid = cg::this_grid();
     const int tiles = (g.num_nodes + TM - 1) / TM;          // embedding stages: TM-row tiles (the head walks graphs)
@@ -60,7 +60,14 @@ k_qnet_small(s2v_graph_t g, s2v_embed_params_t eprm, s2v_head_params_t hprm, con
     // large graphs (acting on a road network: B = 1, 975 rows): the head as three tile-parallel stages -- pool + theta6
     // per graph | q per row tile | mask + reduction per graph -- with grid barriers in between (k_pool, k_head and the
     // mask kernels run the same bodies: bit-identical)
-    pool_stage_body<P, 1>(smem, g, hprm.norm_agg, muT, pool, hprm.theta6_w, hprm.theta6_b, gstate);
+    if (pool_ws != nullptr) {                     // the rows of a graph pooled by many CTAs: chunk partials | per-graph finish
+        pool_partials_body<P, 1>(g, muT, pool_ws);
+        __threadfence();
+        grid.sync();
+        pool_reduce_body<P>(smem, g, hprm.norm_agg, pool_ws, pool, hprm.theta6_w, hprm.theta6_b, gstate);
+    } else {
+        pool_stage_body<P, 1>(smem, g, hprm.norm_agg, muT, pool, hprm.theta6_w, hprm.theta6_b, gstate);
+    }
     __threadfence();
     grid.sync();
     SP(21);
@@ -83,7 +90,8 @@ template <int P>
 static int small_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& eprm, const s2v_head_params_t& hprm,
                               const float* x, float* base, float* mus, int mode, const uint8_t* mask,
                               const int32_t* reach_ptr, const int32_t* reach_idx, float* pool, float* gstate, float* q,
-                              float* prob, int64_t* arg_out, int64_t* node_out, float* val_out, cudaStream_t st) {
+                              float* prob, int64_t* arg_out, int64_t* node_out, float* val_out, float* pool_ws,
+                              cudaStream_t st) {
     using C = Cfg<P>;
     constexpr int TM = SmallTile<P>::TM;
     using CT = Cfg<P, TM>;
@@ -108,7 +116,7 @@ static int small_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& ep
     s2v_embed_params_t ep = eprm;
     s2v_head_params_t hp = hprm;
     void* args[] = {&gg, &ep, &hp, (void*)&x, &base, &mus, &mode, (void*)&mask, (void*)&reach_ptr, (void*)&reach_idx,
-                    &pool, &gstate, &q, &prob, &arg_out, &node_out, &val_out};
+                    &pool, &gstate, &q, &prob, &arg_out, &node_out, &val_out, &pool_ws};
     return (int)cudaLaunchCooperativeKernel((const void*)kernel, dim3(grid), dim3(S2V_THREADS), args, smem, st);
 }
 
@@ -122,11 +130,28 @@ extern "C" int s2v_qnet_small_eligible(int32_t emb_dim, int32_t flags, int64_t n
     return 1;
 }
 
+// Workspace of the many-CTA pool (floats): one [RG][P] partial per 64-row chunk of every graph; 0 when the graphs are small
+// enough for one CTA each (the fused head stage).
+extern "C" int64_t s2v_qnet_small_workspace_floats(int32_t emb_dim, int64_t num_nodes, int64_t num_graphs) {
+    if (emb_dim < 8 || emb_dim > 64 || emb_dim % 4 || num_nodes <= 256 * num_graphs) return 0;
+    const int64_t rg = S2V_THREADS / (emb_dim / 4);
+    return (num_nodes / S2V_POOL_CHUNK + num_graphs) * rg * emb_dim;
+}
+
 extern "C" int s2v_qnet_small_forward(const s2v_graph_t* g, const s2v_embed_params_t* eprm, const s2v_head_params_t* hprm,
                                       const float* x, float* base, float* mus, int32_t mode, const uint8_t* mask,
                                       const int32_t* reach_ptr, const int32_t* reach_idx, float* pool, float* gstate,
                                       float* q, float* prob, int64_t* arg_out, int64_t* node_out, float* val_out,
                                       void* stream) {
+    return s2v_qnet_small_forward_ws(g, eprm, hprm, x, base, mus, mode, mask, reach_ptr, reach_idx, pool, gstate, q, prob,
+                                     arg_out, node_out, val_out, nullptr, 0, stream);
+}
+
+extern "C" int s2v_qnet_small_forward_ws(const s2v_graph_t* g, const s2v_embed_params_t* eprm, const s2v_head_params_t* hprm,
+                                         const float* x, float* base, float* mus, int32_t mode, const uint8_t* mask,
+                                         const int32_t* reach_ptr, const int32_t* reach_idx, float* pool, float* gstate,
+                                         float* q, float* prob, int64_t* arg_out, int64_t* node_out, float* val_out,
+                                         float* workspace, int64_t workspace_floats, void* stream) {
     if (!g || !eprm || !x || !base || !mus || eprm->rounds < 1 || mode < -1 || mode > 3) return S2V_ERR_BAD_ARG;
     if (g->num_nodes < 0 || g->num_graphs < 0 || g->period < 0 || !g->rowptr || !g->indeg) return S2V_ERR_BAD_ARG;
     if (g->num_edges > 0 && !g->col) return S2V_ERR_BAD_ARG;
@@ -142,7 +167,11 @@ extern "C" int s2v_qnet_small_forward(const s2v_graph_t* g, const s2v_embed_para
     s2v_head_params_t hp{};
     if (hprm) hp = *hprm;
     cudaStream_t st = (cudaStream_t)stream;
+    // the many-CTA pool needs its workspace; without one (or with too small a one) one CTA pools each graph
+    float* pool_ws = workspace;
+    const int64_t need = s2v_qnet_small_workspace_floats(eprm->emb_dim, g->num_nodes, g->num_graphs);
+    if (mode < 0 || need == 0 || workspace_floats < need) pool_ws = nullptr;
     S2V_DISPATCH_P(eprm->emb_dim, return small_forward_impl<PP>(*g, *eprm, hp, x, base, mus, mode, mask, reach_ptr, reach_idx,
-                                                                 pool, gstate, q, prob, arg_out, node_out, val_out, st));
+                                                                 pool, gstate, q, prob, arg_out, node_out, val_out, pool_ws, st));
     return 0;
 }

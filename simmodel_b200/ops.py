@@ -95,11 +95,13 @@ def _qnet_small_forward(layout, T, x, ew, hw, norm_agg, mode, mask_u8=None, reac
     val = torch.empty(B, dtype=torch.float32, device=dev) if mode in ("max", "list") else None
     eprm = _embed_struct(T, ew)
     hprm = _head_struct(norm_agg, hw) if head else None
+    ws_floats = int(L.s2v_qnet_small_workspace_floats(P, n, B)) if head else 0       # many-CTA pool of large graphs
+    ws = torch.empty(ws_floats, dtype=torch.float32, device=dev) if ws_floats else None
     with torch.cuda.device(dev):
-        _lib.check(L.s2v_qnet_small_forward(C.byref(layout.c_struct()), C.byref(eprm), C.byref(hprm) if head else None, _p(x),
-                                            _p(base), _p(mus), _FUSED_MODES[mode] if head else -1, _p(mask_u8), _p(reach_ptr),
-                                            _p(reach_idx), _p(pool), _p(gstate), _p(q), _p(prob), _p(arg), _p(node), _p(val),
-                                            _stream()), "s2v_qnet_small_forward")
+        _lib.check(L.s2v_qnet_small_forward_ws(C.byref(layout.c_struct()), C.byref(eprm), C.byref(hprm) if head else None, _p(x),
+                                               _p(base), _p(mus), _FUSED_MODES[mode] if head else -1, _p(mask_u8),
+                                               _p(reach_ptr), _p(reach_idx), _p(pool), _p(gstate), _p(q), _p(prob), _p(arg),
+                                               _p(node), _p(val), _p(ws), ws_floats, _stream()), "s2v_qnet_small_forward_ws")
     _lib.launch_count += 1
     return base, mus, pool, gstate, q, prob, arg, node, val
 

@@ -28,7 +28,7 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(L, s), "missing export " + s
         assert s in _lib.SIGNATURES, "no ctypes signature for " + s
     assert set(_lib.SIGNATURES) == set(syms)
-    assert L.s2v_abi_version() == 4
+    assert L.s2v_abi_version() == 5
     assert L.s2v_embed_grad_floats(7, 64) + L.s2v_head_grad_floats(64) == 21569      # comb_opt.py QNet size
     assert b"workspace" in L.s2v_error_string(-3)
 
