@@ -15,5 +15,5 @@ for _ in range(3):
 torch.cuda.synchronize()
 H = C.CDLL(_lib.LIB_PATH); buf = (C.c_longlong * 16)(); assert H.s2v_debug_wsf_prof(buf) == 0
 v = list(buf); nt = max(v[6], 1)
-print('%s: P warp 0, cycles per tile (%d tiles): wait landed %d | read+add %d | fence+re-arm %d | wait stage %d | split+store %d | total %d'
+print('%s: P warp 0, cycles per tile (%d tiles): [0] %d | [1] %d | [2] %d | [3] %d | [4] %d | total %d   (PROF=1: wait landed, read+add, re-arm, wait stage, split+store; PROF=3: [1] before the plane loop, [2] plane loop, [3] column sums)'
       % (sys.argv[1], nt, v[0] / nt, v[1] / nt, v[2] / nt, v[3] / nt, v[4] / nt, v[5] / nt))

@@ -1292,9 +1292,27 @@ __device__ __forceinline__ void issue_ws_reduce(uint32_t d2x, uint32_t d2y, uint
 __device__ long long g_wsf_prof[16];
 #define WSFP(i, a, b) do { if (FINAL && blockIdx.x == 0 && t == 0) wsfp[i] += (b) - (a); } while (0)
 #define WSFT(v) const long long v = clock64()
+#if S2V_WSF_PROF == 3
+#define WSFP3(i, a, b) WSFP(i, a, b)
+#define WSFT3(v) WSFT(v)
+#else
+#define WSFP3(i, a, b) do {} while (0)
+#define WSFT3(v) do {} while (0)
+#endif
+#if S2V_WSF_PROF >= 2
+#define WSFP2(i, a, b) do {} while (0)
+#define WSFT2(v) do {} while (0)
+#else
+#define WSFP2(i, a, b) WSFP(i, a, b)
+#define WSFT2(v) WSFT(v)
+#endif
 #else
 #define WSFP(i, a, b) do {} while (0)
 #define WSFT(v) do {} while (0)
+#define WSFP2(i, a, b) do {} while (0)
+#define WSFT2(v) do {} while (0)
+#define WSFP3(i, a, b) do {} while (0)
+#define WSFT3(v) do {} while (0)
 #endif
 struct WsArgs {
     const float* w;          // theta2 | theta1b  [64][64]
@@ -1423,6 +1441,47 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
         };
         if (FINAL && lane == 0)
             for (int r = warp; r < WSF_SLOTS && r < ftotal; r += WS_P_WARPS) final_request(r);
+        // FINAL: in-degree c and padded size Npad of this lane's rows, requested one tile ahead.  The (graph, local row) of a
+        // row advance from tile to tile by a fixed stride, so the only division is done once, here (four divisions, two
+        // dependent index loads and the branches around them cost the producers ~1.9 k cycles per tile inside the loop).
+        int cdi[4] = {0, 0, 0, 0}, npi[4] = {0, 0, 0, 0};
+        int nli[4] = {0, 0, 0, 0}, ngi[4] = {0, 0, 0, 0};       // local row / graph of row i of the next tile to request (period > 0)
+        int step_q = 0, step_r = 0;
+        if (FINAL && g.period > 0) {
+            const int stride = (int)gridDim.x * TCR;
+            step_q = stride / g.period; step_r = stride - step_q * g.period;
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                const int r = (int)blockIdx.x * TCR + rl0 + i;
+                ngi[i] = r / g.period; nli[i] = r - ngi[i] * g.period;
+            }
+        }
+        auto load_cd = [&](int kk) {                           // tiles are requested in order kk = 0, 1, 2, ...
+            int row0, rows;
+            tile_rows(kk, row0, rows);
+#pragma unroll
+            for (int i = 0; i < 4; ++i) {
+                cdi[i] = 0; npi[i] = g.npad_scalar;
+                if (rl0 + i < rows) {
+                    // volatile: the compiler may not re-issue these loads at their use a tile later
+                    const int r = row0 + rl0 + i;
+                    if (g.period > 0) {
+                        asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(cdi[i]) : "l"(g.indeg + nli[i]));
+                        if (g.npad) asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(npi[i]) : "l"(g.npad + ngi[i]));
+                    } else {
+                        asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(cdi[i]) : "l"(g.indeg + r));
+                        if (g.npad) {
+                            int gi;
+                            asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(gi) : "l"(g.gid + r));
+                            asm volatile("ld.global.nc.s32 %0, [%1];" : "=r"(npi[i]) : "l"(g.npad + gi));
+                        }
+                    }
+                }
+                nli[i] += step_r; ngi[i] += step_q;
+                if (nli[i] >= g.period && g.period > 0) { nli[i] -= g.period; ++ngi[i]; }
+            }
+        };
+        if (FINAL && my_tiles > 0) load_cd(0);
         int s = 0, par = 0;                                   // s = k % NST, par = (k / NST) & 1
         for (int k = 0; k < my_tiles; ++k) {
             uint8_t* gt = stage0 + s * WS_STAGE_BYTES;
@@ -1435,19 +1494,12 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
                                   [&]() {}, acc);
             } else {
                 // D = sum_t du^t, planes in the order t = 1..T, read from the landing ring
+                WSFT3(q_a);
                 int row0, rows;
                 tile_rows(k, row0, rows);
-                float cf[4], df[4];
 #pragma unroll
-                for (int i = 0; i < 4; ++i) {
-                    cf[i] = 0.f; df[i] = 0.f; acc[i] = f4zero();
-                    if (rl0 + i < rows) {
-                        int li, off, gi;
-                        row_info(g, row0 + rl0 + i, li, off, gi);
-                        cf[i] = (float)__ldg(g.indeg + li);
-                        df[i] = (float)graph_npad(g, gi) - cf[i];
-                    }
-                }
+                for (int i = 0; i < 4; ++i) acc[i] = f4zero();
+                WSFT3(q_b); WSFP3(1, q_a, q_b);
                 for (int j = 0; j < fT; ++j, ++freq) {
                     WSFT(p_a);
                     tc::mbar_wait(&lfull[fslot], fphase);
@@ -1458,16 +1510,21 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
                         if (rl0 + i < rows) acc[i] = f4add(acc[i], ld4(lp + i * 64));
                     __syncwarp();
                     if (lane == 0) tc::mbar_arrive(&lempty[fslot]);
-                    WSFT(p_c); WSFP(1, p_b, p_c);
+                    WSFT2(p_c); WSFP2(1, p_b, p_c);
                     // request rq re-arms the slot that was read WSF_LAG reads ago; its issuer is warp rq % 8
                     const int rq = freq - WSF_LAG + WSF_SLOTS;
                     if (rq >= WSF_SLOTS && rq < ftotal && (rq % WS_P_WARPS) == warp && lane == 0) {
                         tc::mbar_wait(&lempty[rq % WSF_SLOTS], ((rq / WSF_SLOTS) - 1) & 1);     // all eight warps have read request rq - WSF_SLOTS
                         final_request(rq);
                     }
-                    WSFT(p_d); WSFP(2, p_c, p_d);
+                    WSFT2(p_d); WSFP2(2, p_c, p_d);
                     if (++fslot == WSF_SLOTS) { fslot = 0; fphase ^= 1; }
                 }
+                WSFT3(q_c); WSFP3(2, q_b, q_c);
+                float cf[4], df[4];                            // in-degree c and Npad - c of the rows (raw values requested a tile ago)
+#pragma unroll
+                for (int i = 0; i < 4; ++i) { cf[i] = (float)cdi[i]; df[i] = (float)npi[i] - cf[i]; }
+                if (k + 1 < my_tiles) load_cd(k + 1);           // dependent index loads: a tile period to land, nothing waits for them
 #pragma unroll
                 for (int i = 0; i < 4; ++i) {
                     pD = f4add(pD, acc[i]);
@@ -1476,11 +1533,12 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
                     pA0.x = fmaf(df[i], acc[i].x, pA0.x); pA0.y = fmaf(df[i], acc[i].y, pA0.y);
                     pA0.z = fmaf(df[i], acc[i].z, pA0.z); pA0.w = fmaf(df[i], acc[i].w, pA0.w);
                 }
+                WSFT3(q_d); WSFP3(3, q_c, q_d);
             }
             TLW(t == 0, k, 1);
-            WSFT(p_e);
+            WSFT2(p_e);
             tc::mbar_wait(&sh->mma_done[s], par ^ 1);            // the MMAs of tile k-3 have finished reading stage s
-            WSFT(p_f); WSFP(3, p_e, p_f);
+            WSFT2(p_f); WSFP2(3, p_e, p_f);
             TLW(t == 0, k, 2);
 #pragma unroll
             for (int i = 0; i < 4; ++i)
@@ -1488,7 +1546,7 @@ k_embed_bwd_ws(s2v_graph_t g, WsArgs a) {
             tc::fence_proxy_async_smem();
             __syncwarp();
             if (lane == 0) tc::mbar_arrive(&sh->full_g[s]);
-            WSFT(p_g); WSFP(4, p_f, p_g);
+            WSFT2(p_g); WSFP2(4, p_f, p_g);
             TLW(t == 0, k, 3);
             if (++s == NST) { s = 0; par ^= 1; }
         }
