@@ -553,22 +553,37 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
     uint32_t phase = 0;
     const int c4 = t & 15, rbase = t >> 4;       // this thread's chunks: rows rbase + 8*i, columns 4*c4..4*c4+3
 
-    float xr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, cn = 0.f, dn = 0.f;
-    auto prefetch = [&](int tl) {                // row t of tile tl: features (F <= 8), in-degree, Npad - in-degree
+    // Row t of the CTA's next tile, requested one tile ahead: features (F <= 8), in-degree c and padded size Npad as RAW
+    // integers -- converting them here would make the 64 staging threads (and the barrier behind them) wait for the index
+    // loads every tile (1.3 k cycles on the timeline).  The (graph, local row) of a row advances by a fixed stride per tile:
+    // the only division is done once.
+    float xr[8] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    int ci = 0, npi = 0, nli = 0, ngi = 0, step_q = 0, step_r = 0;
+    if (g.period > 0) {
+        const int stride = (int)gridDim.x * TCR, r = (int)blockIdx.x * TCR + (t < TCR ? t : 0);
+        step_q = stride / g.period; step_r = stride - step_q * g.period;
+        ngi = r / g.period; nli = r - ngi * g.period;
+    }
+    auto prefetch = [&](int tl) {                // tiles are requested in the order the CTA visits them
         const int r = tl * TCR + t;
-        cn = 0.f; dn = 0.f;
+        ci = 0; npi = g.npad_scalar;
 #pragma unroll
         for (int f = 0; f < 8; ++f) xr[f] = 0.f;
         if (r < g.num_nodes) {
-            int li, off, gi;
-            row_info(g, r, li, off, gi);
-            cn = (float)__ldg(g.indeg + li);
-            dn = (float)graph_npad(g, gi) - cn;
+            if (g.period > 0) {
+                ci = __ldg(g.indeg + nli);
+                if (g.npad) npi = __ldg(g.npad + ngi);
+            } else {
+                ci = __ldg(g.indeg + r);
+                if (g.npad) npi = __ldg(g.npad + __ldg(g.gid + r));
+            }
             if (F <= 8) {
 #pragma unroll
                 for (int f = 0; f < 8; ++f) if (f < F) xr[f] = __ldg(x + (size_t)r * F + f);
             }
         }
+        nli += step_r; ngi += step_q;
+        if (g.period > 0 && nli >= g.period) { nli -= g.period; ++ngi; }
     };
     if (t < TCR && blockIdx.x < num_tiles) prefetch(blockIdx.x);
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -587,8 +602,9 @@ k_embed_first_tc(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict_
                 st4(xs + t * FS, make_float4(xr[0], xr[1], xr[2], xr[3]));
                 if (FS > 4) st4(xs + t * FS + 4, make_float4(xr[4], xr[5], xr[6], xr[7]));
             }
+            const float cn = (float)ci;
             cw[t] = cn;
-            cw[64 + t] = dn;
+            cw[64 + t] = (float)npi - cn;                // rows past the end: x = 0 and c = 0 (their outputs are not stored)
             prefetch(tile + gridDim.x);                  // zeros past the last row
         }
         __syncthreads();
