@@ -41,6 +41,20 @@ __device__ __forceinline__ void embed_first_body(float* smem, const s2v_graph_t&
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * TM;
         const int rows = min(TM, g.num_nodes - row0);
+        // in-degree and padded size of this thread's output rows: requested here, used in the epilogue (as raw integers,
+        // so that nothing waits for them before the tile product is done)
+        int ci[C::NR], npi[C::NR];
+#pragma unroll
+        for (int i = 0; i < C::NR; ++i) {
+            const int rl = ty + C::RG * i;
+            ci[i] = 0; npi[i] = 0;
+            if (active && rl < rows) {
+                int li, off, gi;
+                row_info(g, row0 + rl, li, off, gi);
+                ci[i] = __ldg(g.indeg + li);
+                npi[i] = graph_npad(g, gi);
+            }
+        }
         for (int e = t; e < TM * F; e += S2V_THREADS)
             xs[e] = e < rows * F ? __ldg(x + (size_t)row0 * F + e) : 0.f;
         __syncthreads();
@@ -69,10 +83,9 @@ __device__ __forceinline__ void embed_first_body(float* smem, const s2v_graph_t&
             for (int i = 0; i < C::NR; ++i) {
                 int rl = ty + C::RG * i;
                 if (rl >= rows) continue;
-                int r = row0 + rl, li, off, gi;
-                row_info(g, r, li, off, gi);
-                float c = (float)__ldg(g.indeg + li);
-                float d = (float)graph_npad(g, gi) - c;
+                const int r = row0 + rl;
+                const float c = (float)ci[i];
+                const float d = (float)npi[i] - c;
                 float4 b;
                 b.x = acc[i][0] + (c0.x + (c * v1.x + d * v0.x));
                 b.y = acc[i][1] + (c0.y + (c * v1.y + d * v0.y));

@@ -160,3 +160,54 @@ def lay_edge_rows(lay, topo, B, dev):
     import simmodel_b200 as sb
     ei = sb.graphs.batch_edge_index(topo, B, device=dev)
     return ei[0], ei[1]
+
+
+@pytest.mark.parametrize("T,topo_name,B", [(9, "NWB_AMS", 5), (2, "NWB_UTR", 4), (7, "Manhattan5", 170), (1, "NWB_AMS", 5)])
+def test_last_stage_plane_ring_any_T(T, topo_name, B, cuda_device, monkeypatch):
+    """The last backward stage takes the T gradient planes of a tile by cp.async.bulk into a 7-slot landing ring: more planes
+    than slots (T = 9), fewer (T = 1, 2), ragged last tiles.  All 16 gradients of the tensor path against the fp64 oracle
+    (1e-5 of scale, or twice the fp32 oracle's own error) and against the CUDA-core path."""
+    import simmodel_b200 as sb
+    from oracle import s2v_ref as R
+    dev = cuda_device
+    topo = sb.graphs.load_topology(topo_name)
+    n = topo.num_nodes
+    gen = torch.Generator().manual_seed(T * 31 + B)
+    x = sb.graphs.synth_nfm(topo, B, gen).reshape(-1, sb.graphs.NODE_DIM)
+    ei = sb.graphs.batch_edge_index(topo, B)
+    ptr = torch.arange(B + 1, dtype=torch.int64) * n
+    actions = torch.randint(0, n, (B,), generator=gen).tolist()
+    targets = torch.randn(B, generator=gen).tolist()
+    P0 = R.make_qnet_params(sb.graphs.NODE_DIM, 64, seed=T)
+
+    def oracle(dtype):
+        P = {k: v.to(dtype).clone().requires_grad_(True) for k, v in P0.items()}
+        q = R.qnet_forward_sparse(P, x.to(dtype), ei, ptr, n, T, True)
+        R.dqn_loss(q, actions, ptr, [float(v) for v in targets]).backward()
+        return q.detach(), {k: v.grad for k, v in P.items()}
+
+    q64, g64 = oracle(torch.float64)
+    q32, g32 = oracle(torch.float32)
+
+    def ours(path):
+        monkeypatch.setenv("S2V_B200_PATH", path)
+        torch.manual_seed(0)
+        net = sb.QNet({"emb_dim": 64, "emb_iter_T": T, "norm_agg": True, "node_dim": sb.graphs.NODE_DIM}, verbose=False).to(dev)
+        net.load_state_dict({k: v.to(dev) for k, v in P0.items()}, strict=True)
+        lay = sb.GraphLayout.from_batch(ei.to(dev), ptr.to(dev), n)
+        q = net.forward_graph(x.to(dev), lay)
+        sel = torch.tensor(actions, device=dev) + ptr[:-1].to(dev)
+        torch.nn.SmoothL1Loss()(q[sel], torch.tensor(targets, device=dev)).backward()
+        torch.cuda.synchronize()
+        return q.detach().cpu(), {k: p.grad.detach().cpu() for k, p in net.named_parameters()}
+
+    q_tc, g_tc = ours("tcws")
+    q_ff, g_ff = ours("ffma")
+    scale = float(q64.abs().max())
+    assert float((q_tc.double() - q64).abs().max()) / scale < 1e-5
+    for k in g64:
+        s = float(g64[k].abs().max()) + 1e-30
+        own = float((g32[k].double() - g64[k]).abs().max()) / s
+        bound = max(1e-5, 2 * own)
+        assert float((g_tc[k].double() - g64[k]).abs().max()) / s < bound, (k, T)
+        assert float((g_ff[k].double() - g64[k]).abs().max()) / s < bound, (k, T)
