@@ -1097,15 +1097,16 @@ k_embed_round_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const floa
             tc::mma_commit(&sh->bar);
         }
         __syncwarp();
-        {
-            const int nt = tile + gridDim.x;     // CSR metadata of the next tile: overlaps MMA + epilogue
-            if (nt < num_tiles) gather8_prefetch(meta, g, g.rowptr, g.col, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
-        }
-        float4 bv[8];                            // base rows of the epilogue while the tensor core works
-#pragma unroll
+        float4 bv[8];                            // base rows of the epilogue while the tensor core works: requested FIRST -- the
+#pragma unroll                                   // metadata prefetch below stalls on its own dependent loads (rowptr -> col)
         for (int i = 0; i < 8; ++i) {
             int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
             bv[i] = rl < rows ? ldg4(base + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero();
+        }
+        {
+            const int nt = tile + gridDim.x;     // CSR metadata of the next tile: overlaps MMA + epilogue.  (Extents a tile earlier
+            // than the ids -- no dependent stall at all -- measured 0.936 ms against 0.895 ms: the extra registers spill.)
+            if (nt < num_tiles) gather8_prefetch(meta, g, g.rowptr, g.col, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
         }
         tc::mbar_wait(&sh->bar, phase);
         phase ^= 1;
