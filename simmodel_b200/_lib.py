@@ -116,11 +116,11 @@ def check(code: int, what: str):
         raise S2VError("%s failed: %s (code %d)" % (what, lib().s2v_error_string(code).decode(), code))
 
 
-PATHS = {"auto": 0, "ffma": 1, "tc": 2, "tcws": 3}
+PATHS = {"auto": 0, "ffma": 1, "tc": 2, "tcws": 3, "tc16": 4}
 
 
 def path_flag() -> int:
-    """Kernel path selector from $S2V_B200_PATH (auto | ffma | tc | tcws); see s2v_embed_params_t.flags."""
+    """Kernel path selector from $S2V_B200_PATH (auto | ffma | tc | tcws | tc16); see s2v_embed_params_t.flags."""
     return PATHS[os.environ.get("S2V_B200_PATH", "auto").lower()]
 
 

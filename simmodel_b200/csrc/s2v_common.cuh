@@ -613,6 +613,7 @@ static inline void s2v_reduce_partials(const float* partial, int stride, int n_p
 #define S2V_PATH_FFMA 1
 #define S2V_PATH_TENSOR 2
 #define S2V_PATH_TENSOR_WS 3    // tensor path with the warp-specialised (producer / MMA / consumer) backward round
+#define S2V_PATH_TENSOR_16 4    // tensor path with the forward-shaped bf16x3 backward round (k_embed_round_bwd_tc16)
 #define S2V_TENSOR_MIN_NODES 4096
 #ifndef S2V_TENSOR_FINAL
 #define S2V_TENSOR_FINAL 0      // tensor-core variant of the last backward stage (slower than FFMA so far)

@@ -310,6 +310,11 @@ int s2v_tc_round_backward_ws(const s2v_graph_t& g, const float* theta2_w, const 
                              float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st);
 int s2v_tc_round_backward(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
                           float* du_prev, float* partial, int partial_stride, int accumulate, int grid, cudaStream_t st);
+// the tensor path's default backward round: warp-specialised or forward-shaped (S2V_B200_BWD_ROUND, s2v_embed_tc.cu)
+int s2v_tc_round_backward_sel_grid(int num_nodes, int flags);
+int s2v_tc_round_backward_sel(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
+                              float* du_prev, float* partial, int partial_stride, int accumulate, int grid, int flags,
+                              cudaStream_t st);
 bool s2v_tc_final_backward_ws_ok(int node_dim);
 int s2v_tc_final_backward_ws(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, const float* dus,
                              const float* du_last, float* partial, int partial_stride, int grid, cudaStream_t st);
@@ -324,7 +329,7 @@ int s2v_tc_final_backward(const s2v_graph_t& g, const s2v_embed_params_t& prm, c
 // backward round, 3 = tensor-core path with the warp-specialised backward round (what auto picks for large batches)
 static bool use_tensor_path(int P, int flags, int num_nodes) {
     if (P != 64 || flags == S2V_PATH_FFMA) return false;
-    if (flags >= S2V_PATH_TENSOR && flags <= S2V_PATH_TENSOR_WS) return true;
+    if (flags >= S2V_PATH_TENSOR && flags <= S2V_PATH_TENSOR_16) return true;
     return num_nodes >= S2V_TENSOR_MIN_NODES;
 }
 // Backward round.  Three implementations of the same tile math (profiles/ holds the timings, AMS, 4.0 M rows):
@@ -412,12 +417,12 @@ static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& p
     // rounds T..2 : du^t -> du^{t-1}
     if (use_tensor_path_bwd_round(P, prm.flags, g.num_nodes)) {
         const bool ws = use_ws_bwd_round(prm.flags);
-        grid_r = ws ? s2v_tc_round_backward_ws_grid(g.num_nodes) : s2v_tc_round_backward_grid(g.num_nodes);
+        grid_r = ws ? s2v_tc_round_backward_sel_grid(g.num_nodes, prm.flags) : s2v_tc_round_backward_grid(g.num_nodes);
         for (int t = T; t >= 2; --t) {
             const float* du_t = (t == T) ? du_last : dus + (size_t)(t - 1) * plane;
             if (ws)
-                S2V_RETURN_IF(s2v_tc_round_backward_ws(g, prm.theta2_w, du_t, mus + (size_t)(t - 2) * plane,
-                                                       dus + (size_t)(t - 2) * plane, partial, stride, t != T, grid_r, st));
+                S2V_RETURN_IF(s2v_tc_round_backward_sel(g, prm.theta2_w, du_t, mus + (size_t)(t - 2) * plane,
+                                                        dus + (size_t)(t - 2) * plane, partial, stride, t != T, grid_r, prm.flags, st));
             else
                 S2V_RETURN_IF(s2v_tc_round_backward(g, prm.theta2_w, du_t, mus + (size_t)(t - 2) * plane,
                                                     dus + (size_t)(t - 2) * plane, partial, stride, t != T, grid_r, st));
@@ -563,8 +568,8 @@ extern "C" int s2v_embed_round_backward(const s2v_graph_t* g, int32_t node_dim, 
     if (use_tensor_path_bwd_round(emb_dim, flags, g->num_nodes)) {
         const int pstride = 2 * emb_dim * emb_dim + 4 * emb_dim + emb_dim * node_dim;
         if (use_ws_bwd_round(flags))
-            return s2v_tc_round_backward_ws(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace, pstride, 0,
-                                            s2v_tc_round_backward_ws_grid(g->num_nodes), (cudaStream_t)stream);
+            return s2v_tc_round_backward_sel(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace, pstride, 0,
+                                             s2v_tc_round_backward_sel_grid(g->num_nodes, flags), flags, (cudaStream_t)stream);
         return s2v_tc_round_backward(*g, theta2_w, du_t, mu_prev, du_prev, (float*)workspace, pstride, 0,
                                      s2v_tc_round_backward_grid(g->num_nodes), (cudaStream_t)stream);
     }

@@ -15,6 +15,7 @@
 //                             kept in TMEM across all tiles of the CTA)
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 #include "s2v_common.cuh"
 #include "s2v_tc.cuh"
 
@@ -1128,6 +1129,135 @@ k_embed_round_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const floa
     tc::tc_fence_before_sync();
     __syncthreads();
     if (warp == 0) tc::tmem_dealloc<64>(d1);
+}
+
+// ------------------------------------------------------------------------------------
+// backward round in the shape of the forward round (r02d): 4-warp CTAs, three per SM, no roles.
+//   du^{t-1} = (g theta2) * [mu^{t-1} > 0],  dtheta2 += g^T mu^{t-1},  g = gather of du^t over the transposed CSR.
+// The forward round reaches 0.87 of the copy peak with four independent 4-warp CTAs per SM whose gather / MMA /
+// epilogue phases interleave; the warp-specialised backward kernel (one 16-warp CTA per SM, below) sits at 0.64 because
+// only its eight producer warps have loads in flight.  Here every warp gathers (16 neighbour loads + 8 own-row loads per
+// lane) and the SM holds three such CTAs: 72 KB of operand tiles (theta2^T, g, mu^{t-1}: three bf16 tiles each, one
+// SWIZZLE_128B tile serves the K-major and the MN-major view) and 128 TMEM columns per CTA (D1 = g theta2, D2 = g^T mu,
+// M = N = 64, six products each).  D2 is read out every `d2_group` tiles (the tensor core's accumulator truncates:
+// chains stay short) into 32 registers per thread: lanes 0-15 of a warp own the TMEM lanes M = 64 uses and keep
+// columns 0-31, lanes 16-31 take columns 32-63 by shuffle.  Partials per CTA, summed in fixed order by
+// k_reduce_partials: bit-stable run to run.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS, 3)
+k_embed_round_bwd_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ du_t,
+                       const float* __restrict__ mu_prev, float* __restrict__ du_prev, float* __restrict__ partial,
+                       int partial_stride, int accumulate, int num_tiles, int d2_group) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w1 = smem;                          // theta2^T: tile(row k, col n) = theta2[n][k]
+    uint8_t* a1 = w1 + TILE16X3;                 // gathered du^t tile; reused as staging
+    uint8_t* m1 = a1 + TILE16X3;                 // own mu^{t-1} tile
+    TcShared* sh = reinterpret_cast<TcShared*>(m1 + TILE16X3);
+    float* stg = reinterpret_cast<float*>(a1);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const unsigned FULL = 0xffffffffu;
+
+    if (warp == 0) tc::tmem_alloc<128>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    load_weight_tiles16(w1, theta2_w, true, TC_THREADS);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d1 = sh->tmem_base, d2 = sh->tmem_base + 64;
+    const uint32_t s_a = tc::smem_u32(a1), s_w = tc::smem_u32(w1), s_m = tc::smem_u32(m1);
+    const uint32_t lane_sel = (uint32_t)(32 * warp) << 16;
+    uint32_t phase = 0;
+    const int c4 = lane & 15, rl0 = warp * 16 + 8 * (lane >> 4);
+    float racc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) racc[i] = 0.f;
+    int chained = 0;                             // tiles accumulated in D2 since it was last read out
+#ifdef S2V_BWD16_EXPERIMENTS
+    const int exp_bits = d2_group >> 8;          // 1: no reduce MMAs, 2: no MMAs at all, 4: no m-tile stores, 8: no D2 read-out, 16: no du stores
+    d2_group &= 255;
+#else
+    constexpr int exp_bits = 0;
+#endif
+    Gather8Meta meta;
+    if (blockIdx.x < num_tiles)
+        gather8_prefetch(meta, g, g.rowptr_t, g.col_t, blockIdx.x * TCR, min(TCR, g.num_nodes - blockIdx.x * TCR), rl0);
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+        uint32_t mbits = 0;                      // [mu^{t-1} > 0] of this lane's 8 rows x 4 columns
+        {
+            float4 mv[8];                        // own rows first: they are in flight together with the gather
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                mv[i] = rl0 + i < rows ? ldg4(mu_prev + (size_t)(row0 + rl0 + i) * 64 + 4 * c4) : f4zero();
+            gather8_consume(meta, g.col_t, du_t, rl0,
+                            [&](int rl, const float4& acc) { store_split3(a1, rl, c4, acc); });
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                if (!(exp_bits & 4)) store_split3(m1, rl0 + i, c4, mv[i]);
+                mbits |= (mv[i].x > 0.f ? 1u : 0u) << (4 * i) | (mv[i].y > 0.f ? 2u : 0u) << (4 * i) |
+                         (mv[i].z > 0.f ? 4u : 0u) << (4 * i) | (mv[i].w > 0.f ? 8u : 0u) << (4 * i);
+            }
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            tc::tc_fence_after_sync();
+            if (!(exp_bits & 2)) issue_transform16(d1, s_a, s_w);
+            if (!(exp_bits & 3)) issue_reduce16(d2, s_a, s_m, chained != 0);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        {
+            const int nt = tile + gridDim.x;     // CSR metadata of the next tile: overlaps MMA + epilogue
+            if (nt < num_tiles) gather8_prefetch(meta, g, g.rowptr_t, g.col_t, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
+        }
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        d1_to_staging(d1, stg);                 // the g tiles are dead once the MMAs have completed
+        if ((++chained >= d2_group || tile + (int)gridDim.x >= num_tiles) && !(exp_bits & 8)) {
+            chained = 0;
+            float v[32];
+            tc::tmem_ld32(d2 + lane_sel, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (lane < 16) racc[i] += v[i];
+            tc::tmem_ld32(d2 + lane_sel + 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                float o = __shfl_sync(FULL, v[i], lane & 15);
+                if (lane >= 16) racc[i] += o;
+            }
+        }
+        tc::tc_fence_before_sync();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rl = rl0 + i;
+            if (rl < rows && !(exp_bits & 16)) {
+                float4 v = ld4(stg + rl * STG_LD + 4 * c4);
+                const uint32_t b = mbits >> (4 * i);
+                st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * c4,
+                    make_float4(b & 1u ? v.x : 0.f, b & 2u ? v.y : 0.f, b & 4u ? v.z : 0.f, b & 8u ? v.w : 0.f));
+            }
+        }
+        __syncthreads();                        // staging is overwritten by the next gather
+    }
+    {   // thread (warp, lane) holds dtheta2[n = 16 warp + lane % 16][32 (lane / 16) .. + 32)
+        float* my = partial + (size_t)blockIdx.x * partial_stride + (16 * warp + (lane & 15)) * 64 + 32 * (lane >> 4);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
+            float4 x4 = make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]);
+            if (accumulate) x4 = f4add(ld4(my + i), x4);
+            st4(my + i, x4);
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<128>(sh->tmem_base);
 }
 
 #include "s2v_ring.cuh"
@@ -2321,6 +2451,54 @@ int s2v_tc_round_backward_ws(const s2v_graph_t& g, const float* theta2_w, const 
     if (const char* e = getenv("S2V_WS_EXP")) a.accumulate |= atoi(e) << 8;
 #endif
     k_embed_bwd_ws<false><<<grid, WS_THREADS, WS_SMEM, st>>>(g, a);
+    return (int)cudaGetLastError();
+}
+
+#ifndef S2V_BWD16_DEFAULT_GROUP
+#define S2V_BWD16_DEFAULT_GROUP 1      /* tiles chained in D2 between two read-outs */
+#endif
+#ifndef S2V_BWD16_DEFAULT
+#define S2V_BWD16_DEFAULT 0            /* auto: 0 = warp-specialised backward round, 1 = k_embed_round_bwd_tc16 */
+#endif
+// Which backward-round kernel the tensor path runs: flags S2V_PATH_TENSOR_WS -> warp-specialised, S2V_PATH_TENSOR_16 ->
+// k_embed_round_bwd_tc16, auto -> S2V_B200_BWD_ROUND=ws|tc16 (default: S2V_BWD16_DEFAULT).  Returns 0 for the
+// warp-specialised kernel, else the number of tiles k_embed_round_bwd_tc16 chains in D2 (S2V_B200_BWD16_GROUP, 1..8).
+static int bwd16_group(int flags) {
+    static const int grp = [] {
+        const char* e = getenv("S2V_B200_BWD16_GROUP");
+        int v = e ? atoi(e) : S2V_BWD16_DEFAULT_GROUP;
+        return v < 1 ? 1 : (v > 8 ? 8 : v);
+    }();
+    static const bool dflt16 = [] {
+        const char* e = getenv("S2V_B200_BWD_ROUND");
+        return e ? strncmp(e, "tc16", 4) == 0 : (S2V_BWD16_DEFAULT != 0);
+    }();
+    if (flags == S2V_PATH_TENSOR_WS) return 0;
+    if (flags == S2V_PATH_TENSOR_16) return grp;
+    return dflt16 ? grp : 0;
+}
+constexpr int BWD16_SMEM = 3 * (int)TILE16X3 + 64 + 1024;
+
+int s2v_tc_round_backward_sel_grid(int num_nodes, int flags) {
+    if (bwd16_group(flags) == 0) return s2v_tc_round_backward_ws_grid(num_nodes);
+    const int tiles = (num_nodes + TCR - 1) / TCR;
+    cudaFuncSetAttribute(k_embed_round_bwd_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16_SMEM);
+    return tc_grid((const void*)k_embed_round_bwd_tc16, BWD16_SMEM, 128, tiles);
+}
+
+int s2v_tc_round_backward_sel(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
+                              float* du_prev, float* partial, int partial_stride, int accumulate, int grid, int flags,
+                              cudaStream_t st) {
+    const int grp = bwd16_group(flags);
+    if (grp == 0) return s2v_tc_round_backward_ws(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride, accumulate, grid, st);
+    const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16_SMEM));
+    int grp_arg = grp;
+#ifdef S2V_BWD16_EXPERIMENTS
+    if (const char* e = getenv("S2V_B200_BWD16_EXP")) grp_arg |= atoi(e) << 8;
+#endif
+    k_embed_round_bwd_tc16<<<grid, TC_THREADS, BWD16_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
+                                                                accumulate, tiles, grp_arg);
     return (int)cudaGetLastError();
 }
 

@@ -487,7 +487,7 @@ int s2v_tc_head_forward(const s2v_graph_t& g, const s2v_head_params_t& prm, cons
 // same rule as the embedding (s2v_embed.cu:use_tensor_path)
 static bool head_tensor_path(int P, int flags, int num_nodes) {
     if (P != 64 || flags == S2V_PATH_FFMA) return false;
-    if (flags >= S2V_PATH_TENSOR && flags <= S2V_PATH_TENSOR_WS) return true;
+    if (flags >= S2V_PATH_TENSOR && flags <= S2V_PATH_TENSOR_16) return true;
     return num_nodes >= S2V_TENSOR_MIN_NODES;
 }
 

@@ -123,7 +123,7 @@ static int small_forward_impl(const s2v_graph_t& g, const s2v_embed_params_t& ep
 // mode -1: embedding only (base, mus);  0..3: as s2v_head_fused_forward.  Returns S2V_ERR_UNSUPPORTED when the problem
 // belongs to the tensor-core path (s2v_qnet_small_eligible() == 0): the caller then uses the per-stage launches.
 extern "C" int s2v_qnet_small_eligible(int32_t emb_dim, int32_t flags, int64_t num_nodes, int64_t num_graphs) {
-    if (emb_dim == 64 && (flags == S2V_PATH_TENSOR || flags == S2V_PATH_TENSOR_WS)) return 0;
+    if (emb_dim == 64 && flags >= S2V_PATH_TENSOR && flags <= S2V_PATH_TENSOR_16) return 0;
     if (emb_dim == 64 && flags != S2V_PATH_FFMA && num_nodes >= S2V_TENSOR_MIN_NODES) return 0;
     if (num_nodes > 16 * S2V_TENSOR_MIN_NODES) return 0;        // beyond that a stage fills the machine: per-stage launches
     (void)num_graphs;                                           // graphs of any size: fused or tile-parallel head stage
