@@ -73,8 +73,9 @@ typedef struct s2v_embed_params {
     int32_t rounds;           /* T  */
     int32_t flags;            /* kernel path: 0 auto (tensor cores when p == 64 and num_nodes >= 4096),
                                  1 CUDA-core FP32 (FFMA), 2 tcgen05 with the 8-warp 3xTF32 backward round,
-                                 3 tcgen05 with the warp-specialised bf16x3 backward round (= auto's choice);
-                                 2 and 3 need p == 64                                                  */
+                                 3 tcgen05 with the warp-specialised bf16x3 backward round (= auto's choice),
+                                 4 tcgen05 with the forward-shaped bf16x3 backward round (no warp roles);
+                                 2, 3 and 4 need p == 64                                               */
     const float* theta1a_w;   /* [p,F] */
     const float* theta1a_b;   /* [p]   */
     const float* theta1b_w;   /* [p,p] */

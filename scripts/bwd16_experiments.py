@@ -14,7 +14,8 @@ ws = torch.empty(L.s2v_embed_backward_workspace_bytes(7, 64), dtype=torch.uint8,
 g = lay.c_struct()
 L.s2v_embed_round_backward.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_int32] + [C.c_void_p] * 5 + [C.c_int64, C.c_void_p]
 names = {0: 'everything on', 1: 'no reduce MMAs', 2: 'no MMAs', 4: 'no m smem stores', 8: 'no D2 read-out', 16: 'no du global stores',
-         5: 'no reduce MMAs, no m stores', 13: 'no reduce MMAs / m stores / read-out', 30: 'gather + g stores + barriers only'}
+         5: 'no reduce MMAs, no m stores', 13: 'no reduce MMAs / m stores / read-out', 30: 'gather + g stores + barriers only',
+         32: 'no g smem stores', 64: 'no staging', 94: 'gather + g stores + barriers, no staging', 126: 'loads + barriers only'}
 for x, nm in names.items():
     os.environ['S2V_B200_BWD16_EXP'] = str(x)
     def run(): assert L.s2v_embed_round_backward(C.byref(g), 7, 64, 4, _p(w2), _p(du), _p(mu), _p(out), _p(ws), ws.numel(), _stream()) == 0

@@ -1260,6 +1260,167 @@ k_embed_round_bwd_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const 
     if (warp == 0) tc::tmem_dealloc<128>(sh->tmem_base);
 }
 
+// ------------------------------------------------------------------------------------
+// The same round with the MMAs off the critical path (r02d): 8-warp CTAs, two per SM, TWO g stages.
+// In k_embed_round_bwd_tc16 the 48 MMAs of a tile (~1.7 k cycles + commit / wait latency) sit in every CTA's serial
+// chain (ablation: 0.27 ms of 1.24 ms).  Here the MMAs of tile k run while the CTA gathers tile k+1 into the other g
+// stage; the own mu^{t-1} rows of tile k+1 wait in 16 registers per thread and are split into the (single) m tile once
+// the MMAs of tile k have completed.  Per tile: gather(k+1) | wait MMA(k) | D1(k) -> staging (the dead g stage) |
+// [D2 read-out] | sync | du^{t-1}(k) stores, m(k+1) stores | sync | issue MMA(k+1).  All 16 warps of the SM gather
+// (4 rows per half-warp: 16 neighbour loads + 4 own-row loads per lane).  96 KB of shared memory and 128 TMEM columns
+// per CTA.  Warp w reads TMEM lane quarter w & 3, column half w >> 2.
+// ------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(TC_THREADS2, 2)
+k_embed_round_bwd_tc16p(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ du_t,
+                        const float* __restrict__ mu_prev, float* __restrict__ du_prev, float* __restrict__ partial,
+                        int partial_stride, int accumulate, int num_tiles, int d2_group) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w1 = smem;                          // theta2^T: tile(row k, col n) = theta2[n][k]
+    uint8_t* ga = w1 + TILE16X3;                 // gathered du^t tile, stage 0 / 1; a dead stage is the staging buffer
+    uint8_t* m1 = ga + 2 * TILE16X3;             // own mu^{t-1} tile
+    TcShared* sh = reinterpret_cast<TcShared*>(m1 + TILE16X3);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const int q = warp & 3, hh = warp >> 2;
+    const unsigned FULL = 0xffffffffu;
+
+    if (warp == 0) tc::tmem_alloc<128>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 2); tc::fence_barrier_init(); }
+    load_weight_tiles16(w1, theta2_w, true, TC_THREADS2);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const uint32_t d1 = sh->tmem_base, d2 = sh->tmem_base + 64;
+    const uint32_t s_g = tc::smem_u32(ga), s_w = tc::smem_u32(w1), s_m = tc::smem_u32(m1);
+    const uint32_t lane_sel = (uint32_t)(32 * q) << 16;
+    uint32_t phase = 0;
+    const int c4 = lane & 15, rl0 = 4 * (2 * warp + (lane >> 4));
+    float racc[16];
+#pragma unroll
+    for (int i = 0; i < 16; ++i) racc[i] = 0.f;
+    int chained = 0;                             // tiles accumulated in D2 since it was last read out
+    uint32_t mbits = 0;                          // [mu^{t-1} > 0] of this lane's 4 rows x 4 columns, tile k
+    GatherMeta<4> meta;
+#ifdef S2V_BWD16_EXPERIMENTS
+    const int exp_bits = d2_group >> 8;          // 1: no reduce MMAs, 2: no MMAs at all, 4: no m-tile stores, 8: no D2 read-out, 16: no du stores,
+    d2_group &= 255;                             // 32: no g-tile stores, 64: no staging
+#else
+    constexpr int exp_bits = 0;
+#endif
+
+    auto own_rows = [&](int tile, float4 (&mv)[4]) {
+        const int row0 = tile * TCR, rows = min(TCR, g.num_nodes - row0);
+#pragma unroll
+        for (int i = 0; i < 4; ++i)
+            mv[i] = rl0 + i < rows ? ldg4(mu_prev + (size_t)(row0 + rl0 + i) * 64 + 4 * c4) : f4zero();
+    };
+    auto store_m = [&](const float4 (&mv)[4]) {
+        mbits = 0;
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (!(exp_bits & 4)) store_split3(m1, rl0 + i, c4, mv[i]);
+            mbits |= (mv[i].x > 0.f ? 1u : 0u) << (4 * i) | (mv[i].y > 0.f ? 2u : 0u) << (4 * i) |
+                     (mv[i].z > 0.f ? 4u : 0u) << (4 * i) | (mv[i].w > 0.f ? 8u : 0u) << (4 * i);
+        }
+    };
+    auto prefetch = [&](int tile) {
+        if (tile < num_tiles)
+            gatherN_prefetch<4>(meta, g, g.rowptr_t, g.col_t, tile * TCR, min(TCR, g.num_nodes - tile * TCR), rl0);
+    };
+    auto issue = [&](int stage) {
+        if (warp == 0) {                         // two issuing warps (one per accumulator: the order inside each stays fixed)
+            tc::tc_fence_after_sync();
+            if (!(exp_bits & 2)) issue_transform16(d1, s_g + stage * TILE16X3, s_w);
+            tc::mma_commit(&sh->bar);
+        } else if (warp == 4) {
+            tc::tc_fence_after_sync();
+            if (!(exp_bits & 3)) issue_reduce16(d2, s_g + stage * TILE16X3, s_m, chained != 0);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+    };
+
+    if (blockIdx.x < num_tiles) {                // tile 0 of this CTA
+        float4 mv[4];
+        prefetch(blockIdx.x);
+        own_rows(blockIdx.x, mv);
+        gatherN_consume<4, 4>(meta, g.col_t, du_t, rl0, [&](int rl, const float4& acc) { if (!(exp_bits & 32)) store_split3(ga, rl, c4, acc); else if (acc.x == 123.f) mbits = 7; });
+        store_m(mv);
+        prefetch(blockIdx.x + gridDim.x);
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        issue(0);
+    }
+    int s = 0;
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x, s ^= 1) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+        const int nt = tile + gridDim.x;
+        const bool more = nt < num_tiles;        // CTA-uniform
+        float4 mv[4];
+        if (more) {                              // gather tile k+1 into the other stage while the tensor core works on tile k
+            uint8_t* gn = ga + (s ^ 1) * TILE16X3;
+            own_rows(nt, mv);
+            gatherN_consume<4, 4>(meta, g.col_t, du_t, rl0, [&](int rl, const float4& acc) { if (!(exp_bits & 32)) store_split3(gn, rl, c4, acc); else if (acc.x == 123.f) mbits = 7; });
+            prefetch(nt + gridDim.x);            // (extents a tile ahead of the ids, no dependent stall: 1.204 -> 1.247 ms, not kept)
+        }
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        float* stg = reinterpret_cast<float*>(ga + s * TILE16X3);      // the g pieces of tile k are dead
+        if (!(exp_bits & 64)) {
+            float v[32];
+            tc::tmem_ld32(d1 + lane_sel + 32 * hh, v);
+            if (lane < 16) {
+                float* dst = stg + (16 * q + lane) * STG_LD + 32 * hh;
+#pragma unroll
+                for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(v[i], v[i + 1], v[i + 2], v[i + 3]));
+            }
+        }
+        if ((++chained >= d2_group || !more) && !(exp_bits & 8)) {    // D2 -> registers: lanes 0-15 own the TMEM lanes M = 64 uses and keep 16 columns,
+            chained = 0;                         // lanes 16-31 take the other 16 by shuffle
+            float v[32];
+            tc::tmem_ld32(d2 + lane_sel + 32 * hh, v);
+#pragma unroll
+            for (int i = 0; i < 16; ++i) {
+                float o = __shfl_sync(FULL, v[16 + i], lane & 15);
+                racc[i] += lane < 16 ? v[i] : o;
+            }
+        }
+        tc::tc_fence_before_sync();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            const int rl = rl0 + i;
+            if (rl < rows && !(exp_bits & 16)) {
+                float4 v = ld4(stg + rl * STG_LD + 4 * c4);
+                const uint32_t b = mbits >> (4 * i);
+                st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * c4,
+                    make_float4(b & 1u ? v.x : 0.f, b & 2u ? v.y : 0.f, b & 4u ? v.z : 0.f, b & 8u ? v.w : 0.f));
+            }
+        }
+        if (more) {
+            store_m(mv);                         // the MMAs reading the m tile of tile k have completed
+            tc::fence_proxy_async_smem();
+        }
+        __syncthreads();                         // staging read out, m tile complete
+        if (more) issue(s ^ 1);
+    }
+    {   // thread holds dtheta2[n = 16 q + lane % 16][32 hh + 16 (lane / 16) .. + 16)
+        float* my = partial + (size_t)blockIdx.x * partial_stride + (16 * q + (lane & 15)) * 64 + 32 * hh + 16 * (lane >> 4);
+#pragma unroll
+        for (int i = 0; i < 16; i += 4) {
+            float4 x4 = make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]);
+            if (accumulate) x4 = f4add(ld4(my + i), x4);
+            st4(my + i, x4);
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<128>(sh->tmem_base);
+}
+
 #include "s2v_ring.cuh"
 
 // self-test: mode 6: out[rows x 64] = A * W;  mode 7: out[64 x 64] = A^T * B over the rows (per-tile accumulators
@@ -2457,6 +2618,9 @@ int s2v_tc_round_backward_ws(const s2v_graph_t& g, const float* theta2_w, const 
 #ifndef S2V_BWD16_DEFAULT_GROUP
 #define S2V_BWD16_DEFAULT_GROUP 1      /* tiles chained in D2 between two read-outs */
 #endif
+#ifndef S2V_BWD16_PIPELINED
+#define S2V_BWD16_PIPELINED 1
+#endif
 #ifndef S2V_BWD16_DEFAULT
 #define S2V_BWD16_DEFAULT 0            /* auto: 0 = warp-specialised backward round, 1 = k_embed_round_bwd_tc16 */
 #endif
@@ -2478,10 +2642,22 @@ static int bwd16_group(int flags) {
     return dflt16 ? grp : 0;
 }
 constexpr int BWD16_SMEM = 3 * (int)TILE16X3 + 64 + 1024;
+constexpr int BWD16P_SMEM = 4 * (int)TILE16X3 + 64 + 1024;
+static bool bwd16_pipelined() {              // S2V_B200_BWD16_KERNEL=s: 4-warp CTAs, MMAs in the serial chain; p: 8-warp CTAs, two g stages
+    static const bool p = [] { const char* e = getenv("S2V_B200_BWD16_KERNEL"); return e ? e[0] == 'p' : (S2V_BWD16_PIPELINED != 0); }();
+    return p;
+}
 
 int s2v_tc_round_backward_sel_grid(int num_nodes, int flags) {
     if (bwd16_group(flags) == 0) return s2v_tc_round_backward_ws_grid(num_nodes);
     const int tiles = (num_nodes + TCR - 1) / TCR;
+    if (bwd16_pipelined()) {
+        int dev = 0, sms = 0;
+        cudaGetDevice(&dev);
+        cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        const int grid = 2 * sms;                // two 8-warp CTAs per SM (97 KB, 128 registers, 128 TMEM columns each)
+        return grid < tiles ? grid : (tiles < 1 ? 1 : tiles);
+    }
     cudaFuncSetAttribute(k_embed_round_bwd_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16_SMEM);
     return tc_grid((const void*)k_embed_round_bwd_tc16, BWD16_SMEM, 128, tiles);
 }
@@ -2492,6 +2668,16 @@ int s2v_tc_round_backward_sel(const s2v_graph_t& g, const float* theta2_w, const
     const int grp = bwd16_group(flags);
     if (grp == 0) return s2v_tc_round_backward_ws(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride, accumulate, grid, st);
     const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    if (bwd16_pipelined()) {
+        S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc16p, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16P_SMEM));
+        int grp_p = grp;
+#ifdef S2V_BWD16_EXPERIMENTS
+        if (const char* e = getenv("S2V_B200_BWD16_EXP")) grp_p |= atoi(e) << 8;
+#endif
+        k_embed_round_bwd_tc16p<<<grid, TC_THREADS2, BWD16P_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
+                                                                       accumulate, tiles, grp_p);
+        return (int)cudaGetLastError();
+    }
     S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16_SMEM));
     int grp_arg = grp;
 #ifdef S2V_BWD16_EXPERIMENTS

@@ -80,7 +80,7 @@ def test_single_round_tc_vs_ffma(topo_name, B, cuda_device):
     st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     g = lay.c_struct()
     outs = {}
-    for flag in (1, 2, 3):
+    for flag in (1, 2, 3, 4):
         o = torch.empty(n, 64, device=dev)
         _lib.check(L.s2v_embed_round_forward(C.byref(g), 64, flag, _ptr(w2), _ptr(base), _ptr(mu), _ptr(o), st), "fwd")
         d = torch.empty(n, 64, device=dev)
@@ -91,7 +91,7 @@ def test_single_round_tc_vs_ffma(topo_name, B, cuda_device):
         stride = 2 * 64 * 64 + 4 * 64 + 64 * 7
         part = ws.view(torch.float32)[: 1024 * stride].view(1024, stride)[:, : 64 * 64].sum(0)
         outs[flag] = (o, d, part)
-    for flag in (2, 3):                      # 2: 8-warp CTAs (3xTF32), 3: warp-specialised pipeline (bf16x3)
+    for flag in (2, 3, 4):                   # 2: 8-warp CTAs (3xTF32), 3: warp-specialised pipeline (bf16x3), 4: forward-shaped bf16x3 round
         for a, b, name in zip(outs[1], outs[flag], ("mu_next", "du_prev", "dtheta2")):
             err = float((a - b).abs().max() / a.abs().max())
             assert err < 3e-6, (flag, name, err)
@@ -99,11 +99,14 @@ def test_single_round_tc_vs_ffma(topo_name, B, cuda_device):
         assert torch.equal(outs[1][1] == 0, outs[flag][1] == 0)
 
 
-@pytest.mark.parametrize("path", ["tc", "tcws"])
+@pytest.mark.parametrize("path", ["tc", "tcws", "tc16", "tc16s"])
 def test_parity_suite_with_tensor_path_forced(path, cuda_device):
     """Every p = 64 parity case again with the tcgen05 kernels forced on for all sizes (tc: 8-warp 3xTF32 backward
-    round, tcws: warp-specialised bf16x3 backward round -- the one auto picks for large batches)."""
-    env = dict(os.environ, S2V_B200_PATH=path)
+    round, tcws: warp-specialised bf16x3 backward round -- the one auto picks for large batches, tc16 / tc16s: the
+    forward-shaped bf16x3 backward round, 8-warp CTAs with the MMAs behind the next gather / 4-warp CTAs)."""
+    env = dict(os.environ, S2V_B200_PATH="tc16" if path == "tc16s" else path)
+    if path == "tc16s":
+        env["S2V_B200_BWD16_KERNEL"] = "s"
     out = subprocess.run([sys.executable, "-m", "pytest", os.path.join(ROOT, "tests", "test_gpu_parity.py"), "-m", "gpu",
                           "-q", "-x", "--tb=short", "-p", "no:cacheprovider"], env=env, capture_output=True, text=True,
                          timeout=900, cwd=ROOT)
