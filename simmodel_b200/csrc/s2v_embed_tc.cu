@@ -16,6 +16,8 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <cmath>
+#include <cuda_fp16.h>
 #include "s2v_common.cuh"
 #include "s2v_tc.cuh"
 
@@ -1144,6 +1146,56 @@ k_embed_round_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const floa
 // columns 0-31, lanes 16-31 take columns 32-63 by shuffle.  Partials per CTA, summed in fixed order by
 // k_reduce_partials: bit-stable run to run.
 // ------------------------------------------------------------------------------------
+constexpr uint32_t TILE16X2 = 2 * TILE16;
+
+__device__ __forceinline__ float pow2_scale_for(float amax) {      // 2^k with amax 2^k in [2^14, 2^15); 2^127 for (near-)zero tiles
+    const int e = (__float_as_int(amax) >> 23) & 255;
+    int k = 141 - e;
+    k = k > 127 ? 127 : (k < -126 ? -126 : k);
+    return __int_as_float((k + 127) << 23);
+}
+__device__ __forceinline__ void split2h(const float4& v, float s, uint2& p1, uint2& p2) {
+    const float x = v.x * s, y = v.y * s, z = v.z * s, w = v.w * s;
+    const __half2 a = __floats2half2_rn(x, y), b = __floats2half2_rn(z, w);
+    const float2 fa = __half22float2(a), fb = __half22float2(b);
+    const __half2 c = __floats2half2_rn(x - fa.x, y - fa.y), d = __floats2half2_rn(z - fb.x, w - fb.y);
+    p1.x = *reinterpret_cast<const uint32_t*>(&a); p1.y = *reinterpret_cast<const uint32_t*>(&b);
+    p2.x = *reinterpret_cast<const uint32_t*>(&c); p2.y = *reinterpret_cast<const uint32_t*>(&d);
+}
+__device__ __forceinline__ void store_split2h(uint8_t* t1, int r, int c4, const float4& v, float s) {
+    uint2 p1, p2;
+    split2h(v, s, p1, p2);
+    const uint32_t off = tc::tile_off16(r, c4);
+    *reinterpret_cast<uint2*>(t1 + off) = p1;
+    *reinterpret_cast<uint2*>(t1 + TILE16 + off) = p2;
+}
+__host__ __device__ constexpr uint32_t idesc_f16(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4) | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+// the three products with the smallest first: (h2, h1'), (h1, h2'), (h1, h1')
+__device__ __forceinline__ void issue_transform_h2(uint32_t d_tmem, uint32_t a1, uint32_t b1) {
+    constexpr uint32_t idesc = idesc_f16(64, 64, 0, 0);
+    const int ii[3] = {1, 0, 0}, jj[3] = {0, 1, 0};
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            tc::mma_bf16(d_tmem, tc::desc_k16(a1 + ii[p] * TILE16, ks), tc::desc_k16(b1 + jj[p] * TILE16, ks), idesc, p > 0 || ks > 0);
+}
+__device__ __forceinline__ void issue_reduce_h2(uint32_t d_tmem, uint32_t a1, uint32_t b1) {
+    constexpr uint32_t idesc = idesc_f16(64, 64, 1, 1);
+    const int ii[3] = {1, 0, 0}, jj[3] = {0, 1, 0};
+#pragma unroll
+    for (int p = 0; p < 3; ++p)
+#pragma unroll
+        for (int ks = 0; ks < 4; ++ks)
+            tc::mma_bf16(d_tmem, tc::desc_mn16(a1 + ii[p] * TILE16, ks, TILE16), tc::desc_mn16(b1 + jj[p] * TILE16, ks, TILE16), idesc,
+                         p > 0 || ks > 0);
+}
+// swizzled fp32 staging tile [64][64]: 16-byte chunk c of row r lives at chunk c ^ (r & 15)
+__device__ __forceinline__ uint32_t stg_off(int r, int chunk) { return (uint32_t)(r * 64 + ((chunk ^ (r & 15)) << 2)); }
+
+template <bool H2X>                              // H2X (timing experiment): two fp16 pieces, fixed scales 2^11 / 2^14 / 2^3
 __global__ void __launch_bounds__(TC_THREADS, 3)
 k_embed_round_bwd_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ du_t,
                        const float* __restrict__ mu_prev, float* __restrict__ du_prev, float* __restrict__ partial,
@@ -1160,7 +1212,13 @@ k_embed_round_bwd_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const 
 
     if (warp == 0) tc::tmem_alloc<128>(&sh->tmem_base);
     if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
-    load_weight_tiles16(w1, theta2_w, true, TC_THREADS);
+    if constexpr (H2X) {
+        for (int e = t; e < 64 * 16; e += TC_THREADS) {
+            const int row = e >> 4, cc = e & 15;
+            store_split2h(w1, row, cc, make_float4(__ldg(theta2_w + (4 * cc) * 64 + row), __ldg(theta2_w + (4 * cc + 1) * 64 + row),
+                                                   __ldg(theta2_w + (4 * cc + 2) * 64 + row), __ldg(theta2_w + (4 * cc + 3) * 64 + row)), 8.f);
+        }
+    } else load_weight_tiles16(w1, theta2_w, true, TC_THREADS);
     tc::fence_proxy_async_smem();
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -1194,10 +1252,10 @@ k_embed_round_bwd_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const 
             for (int i = 0; i < 8; ++i)
                 mv[i] = rl0 + i < rows ? ldg4(mu_prev + (size_t)(row0 + rl0 + i) * 64 + 4 * c4) : f4zero();
             gather8_consume(meta, g.col_t, du_t, rl0,
-                            [&](int rl, const float4& acc) { store_split3(a1, rl, c4, acc); });
+                            [&](int rl, const float4& acc) { if constexpr (H2X) store_split2h(a1, rl, c4, acc, 2048.f); else store_split3(a1, rl, c4, acc); });
 #pragma unroll
             for (int i = 0; i < 8; ++i) {
-                if (!(exp_bits & 4)) store_split3(m1, rl0 + i, c4, mv[i]);
+                if (!(exp_bits & 4)) { if constexpr (H2X) store_split2h(m1, rl0 + i, c4, mv[i], 16384.f); else store_split3(m1, rl0 + i, c4, mv[i]); }
                 mbits |= (mv[i].x > 0.f ? 1u : 0u) << (4 * i) | (mv[i].y > 0.f ? 2u : 0u) << (4 * i) |
                          (mv[i].z > 0.f ? 4u : 0u) << (4 * i) | (mv[i].w > 0.f ? 8u : 0u) << (4 * i);
             }
@@ -1206,8 +1264,8 @@ k_embed_round_bwd_tc16(s2v_graph_t g, const float* __restrict__ theta2_w, const 
         __syncthreads();
         if (warp == 0) {
             tc::tc_fence_after_sync();
-            if (!(exp_bits & 2)) issue_transform16(d1, s_a, s_w);
-            if (!(exp_bits & 3)) issue_reduce16(d2, s_a, s_m, chained != 0);
+            if (!(exp_bits & 2)) { if constexpr (H2X) issue_transform_h2(d1, s_a, s_w); else issue_transform16(d1, s_a, s_w); }
+            if (!(exp_bits & 3)) { if constexpr (H2X) issue_reduce_h2(d2, s_a, s_m); else issue_reduce16(d2, s_a, s_m, chained != 0); }
             tc::mma_commit(&sh->bar);
         }
         __syncwarp();
@@ -1411,6 +1469,185 @@ k_embed_round_bwd_tc16p(s2v_graph_t g, const float* __restrict__ theta2_w, const
         float* my = partial + (size_t)blockIdx.x * partial_stride + (16 * q + (lane & 15)) * 64 + 32 * hh + 16 * (lane >> 4);
 #pragma unroll
         for (int i = 0; i < 16; i += 4) {
+            float4 x4 = make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]);
+            if (accumulate) x4 = f4add(ld4(my + i), x4);
+            st4(my + i, x4);
+        }
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<128>(sh->tmem_base);
+}
+
+// ------------------------------------------------------------------------------------
+// The backward round on TWO fp16 pieces per operand with per-tile power-of-two scaling (r02d, k_embed_round_bwd_h2).
+// bf16x3 costs three 8 KB pieces per operand tile and six products per contraction; fp16 carries 11 significand bits,
+// so x s = h1 + h2 (h1 = RN16(x s), h2 = RN16(x s - h1)) is exact to 2^-22 |x| and three products (h2 h1', h1 h2',
+// h1 h1') give the same ~2^-22 -- IF nothing underflows: fp16 has 5 exponent bits, and gradient tiles live at 1e-8.
+// Every operand tile is therefore scaled by a power of two (exact) that puts its largest magnitude in [2^14, 2^15):
+// elements down to 2^-18 of the tile's largest keep all 22 bits (h2 stays normal), below that the error is the fp16
+// subnormal spacing, 2^-40 of the largest -- the absolute error of a tile is <= 2^-22 of its largest entry, the
+// quantity the parity bound is stated in.  The scales leave through the epilogue (D1 2^-(eg + ew)) and the read-out of
+// D2 (per tile, 2^-(eg + em): D2 is never chained across tiles, so the tensor core's truncating accumulator sees 12 MMAs).
+// What it buys on chip: 16 KB instead of 24 KB per operand tile, 24 MMAs instead of 48 per tile, a third fewer split
+// instructions and shared-memory stores: 1.24 -> 1.0x ms in the otherwise identical 4-warp kernel.  (Running the MMAs
+// of tile k behind the gather of tile k+1 on a second g stage -- 64 KB, still three CTAs -- measured 1.33 - 1.37 ms.)
+// Staging is a 16 KB swizzled [64][64] fp32 tile in the dead g tile.
+// ------------------------------------------------------------------------------------
+struct H2Shared {
+    uint64_t bar;
+    uint32_t tmem_base;
+    uint32_t pad;
+    float wmax[8];           // per warp: max |g|, max |m| of the tile being produced
+    float wscale;
+};
+
+template <int CTAS>
+__global__ void __launch_bounds__(TC_THREADS, CTAS)
+k_embed_round_bwd_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ du_t,
+                     const float* __restrict__ mu_prev, float* __restrict__ du_prev, float* __restrict__ partial,
+                     int partial_stride, int accumulate, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w1 = smem;                          // theta2^T 2^ew: tile(row k, col n) = theta2[n][k], two fp16 pieces
+    uint8_t* a1 = w1 + TILE16X2;                 // gathered du^t tile 2^eg; reused as the staging tile
+    uint8_t* m1 = a1 + TILE16X2;                 // own mu^{t-1} tile 2^em
+    H2Shared* sh = reinterpret_cast<H2Shared*>(m1 + TILE16X2);
+    float* stg = reinterpret_cast<float*>(a1);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const unsigned FULL = 0xffffffffu;
+
+    if (warp == 0) tc::tmem_alloc<128>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 2); tc::fence_barrier_init(); }
+    {   // weights: largest magnitude -> scale -> two scaled fp16 pieces (transposed)
+        float wm = 0.f;
+        for (int e = t; e < 64 * 64; e += TC_THREADS) wm = fmaxf(wm, fabsf(__ldg(theta2_w + e)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(FULL, wm, o));
+        if (lane == 0) sh->wmax[warp] = wm;
+        __syncthreads();
+        if (t == 0) sh->wscale = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+        __syncthreads();
+        const float sw = sh->wscale;
+        for (int e = t; e < 64 * 16; e += TC_THREADS) {
+            const int row = e >> 4, cc = e & 15;
+            const float4 v = make_float4(__ldg(theta2_w + (4 * cc) * 64 + row), __ldg(theta2_w + (4 * cc + 1) * 64 + row),
+                                         __ldg(theta2_w + (4 * cc + 2) * 64 + row), __ldg(theta2_w + (4 * cc + 3) * 64 + row));
+            store_split2h(w1, row, cc, v, sw);
+        }
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const float inv_sw = 1.0f / sh->wscale;
+    const uint32_t d1 = sh->tmem_base, d2 = sh->tmem_base + 64;
+    const uint32_t s_a = tc::smem_u32(a1), s_w = tc::smem_u32(w1), s_m = tc::smem_u32(m1);
+    const uint32_t lane_sel = (uint32_t)(32 * warp) << 16;
+    uint32_t phase = 0;
+    const int c4 = lane & 15, rl0 = warp * 16 + 8 * (lane >> 4);
+    float racc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) racc[i] = 0.f;
+    Gather8Meta meta;
+    if (blockIdx.x < num_tiles)
+        gather8_prefetch(meta, g, g.rowptr_t, g.col_t, blockIdx.x * TCR, min(TCR, g.num_nodes - blockIdx.x * TCR), rl0);
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+        uint32_t mbits = 0;                      // [mu^{t-1} > 0] of this lane's 8 rows x 4 columns
+        float inv_g, inv_m;
+        {
+            float4 mv[8], gv[8];                 // own rows first: they are in flight together with the gather
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                mv[i] = rl0 + i < rows ? ldg4(mu_prev + (size_t)(row0 + rl0 + i) * 64 + 4 * c4) : f4zero();
+            gather8_consume(meta, g.col_t, du_t, rl0, [&](int rl, const float4& acc) { gv[rl - rl0] = acc; });
+            float gm = 0.f, mm = 0.f;            // the tile's largest magnitudes: per lane, per warp, per CTA
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                gm = fmaxf(gm, fmaxf(fmaxf(fabsf(gv[i].x), fabsf(gv[i].y)), fmaxf(fabsf(gv[i].z), fabsf(gv[i].w))));
+                mm = fmaxf(mm, fmaxf(fmaxf(fabsf(mv[i].x), fabsf(mv[i].y)), fmaxf(fabsf(mv[i].z), fabsf(mv[i].w))));
+            }
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) { gm = fmaxf(gm, __shfl_xor_sync(FULL, gm, o)); mm = fmaxf(mm, __shfl_xor_sync(FULL, mm, o)); }
+            if (lane == 0) { sh->wmax[warp] = gm; sh->wmax[4 + warp] = mm; }
+            __syncthreads();
+            const float sg = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+            const float sm = pow2_scale_for(fmaxf(fmaxf(sh->wmax[4], sh->wmax[5]), fmaxf(sh->wmax[6], sh->wmax[7])));
+            inv_g = 1.0f / sg; inv_m = 1.0f / sm;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) {
+                store_split2h(a1, rl0 + i, c4, gv[i], sg);
+                store_split2h(m1, rl0 + i, c4, mv[i], sm);
+                mbits |= (mv[i].x > 0.f ? 1u : 0u) << (4 * i) | (mv[i].y > 0.f ? 2u : 0u) << (4 * i) |
+                         (mv[i].z > 0.f ? 4u : 0u) << (4 * i) | (mv[i].w > 0.f ? 8u : 0u) << (4 * i);
+            }
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {                         // two issuing warps, one per accumulator (the order inside each stays fixed)
+            tc::tc_fence_after_sync();
+            issue_transform_h2(d1, s_a, s_w);
+            tc::mma_commit(&sh->bar);
+        } else if (warp == 2) {
+            tc::tc_fence_after_sync();
+            issue_reduce_h2(d2, s_a, s_m);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        {
+            const int nt = tile + gridDim.x;     // CSR metadata of the next tile: overlaps MMA + epilogue
+            if (nt < num_tiles) gather8_prefetch(meta, g, g.rowptr_t, g.col_t, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
+        }
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        {
+            const float c1 = inv_g * inv_sw;    // the g pieces are dead once the MMAs have completed: D1 -> staging
+            float v[32];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                tc::tmem_ld32(d1 + lane_sel + 32 * half, v);
+                if (lane < 16) {
+                    const int r = 16 * warp + lane;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        st4(stg + stg_off(r, 8 * half + i), make_float4(v[4 * i] * c1, v[4 * i + 1] * c1, v[4 * i + 2] * c1, v[4 * i + 3] * c1));
+                }
+            }
+            // D2 of this tile alone (its scales are its own): lanes 0-15 own the TMEM lanes M = 64 uses and keep columns 0-31,
+            // lanes 16-31 take columns 32-63 by shuffle; the long sum is fp32 adds in tile order
+            const float c2 = inv_g * inv_m;
+            tc::tmem_ld32(d2 + lane_sel, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (lane < 16) racc[i] = fmaf(v[i], c2, racc[i]);
+            tc::tmem_ld32(d2 + lane_sel + 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float o = __shfl_sync(FULL, v[i], lane & 15);
+                if (lane >= 16) racc[i] = fmaf(o, c2, racc[i]);
+            }
+        }
+        tc::tc_fence_before_sync();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rl = rl0 + i;
+            if (rl < rows) {
+                float4 v = ld4(stg + stg_off(rl, c4));
+                const uint32_t b = mbits >> (4 * i);
+                st4(du_prev + (size_t)(row0 + rl) * 64 + 4 * c4,
+                    make_float4(b & 1u ? v.x : 0.f, b & 2u ? v.y : 0.f, b & 4u ? v.z : 0.f, b & 8u ? v.w : 0.f));
+            }
+        }
+        __syncthreads();                        // staging is overwritten by the next tile's g pieces
+    }
+    {   // thread (warp, lane) holds dtheta2[n = 16 warp + lane % 16][32 (lane / 16) .. + 32)
+        float* my = partial + (size_t)blockIdx.x * partial_stride + (16 * warp + (lane & 15)) * 64 + 32 * (lane >> 4);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) {
             float4 x4 = make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]);
             if (accumulate) x4 = f4add(ld4(my + i), x4);
             st4(my + i, x4);
@@ -2618,11 +2855,14 @@ int s2v_tc_round_backward_ws(const s2v_graph_t& g, const float* theta2_w, const 
 #ifndef S2V_BWD16_DEFAULT_GROUP
 #define S2V_BWD16_DEFAULT_GROUP 1      /* tiles chained in D2 between two read-outs */
 #endif
+#ifndef S2V_BWD16_H2
+#define S2V_BWD16_H2 1
+#endif
 #ifndef S2V_BWD16_PIPELINED
 #define S2V_BWD16_PIPELINED 1
 #endif
 #ifndef S2V_BWD16_DEFAULT
-#define S2V_BWD16_DEFAULT 0            /* auto: 0 = warp-specialised backward round, 1 = k_embed_round_bwd_tc16 */
+#define S2V_BWD16_DEFAULT 1            /* auto: 0 = warp-specialised backward round, 1 = the S2V_B200_BWD16_KERNEL family (default: k_embed_round_bwd_h2) */
 #endif
 // Which backward-round kernel the tensor path runs: flags S2V_PATH_TENSOR_WS -> warp-specialised, S2V_PATH_TENSOR_16 ->
 // k_embed_round_bwd_tc16, auto -> S2V_B200_BWD_ROUND=ws|tc16 (default: S2V_BWD16_DEFAULT).  Returns 0 for the
@@ -2643,6 +2883,12 @@ static int bwd16_group(int flags) {
 }
 constexpr int BWD16_SMEM = 3 * (int)TILE16X3 + 64 + 1024;
 constexpr int BWD16P_SMEM = 4 * (int)TILE16X3 + 64 + 1024;
+constexpr int BWDH2_SMEM = 3 * (int)TILE16X2 + 128 + 1024;
+static int bwdh2_ctas() { static const int c = [] { const char* e = getenv("S2V_B200_H2_CTAS"); return e && atoi(e) == 4 ? 4 : 3; }(); return c; }
+static bool bwd16_h2() {                     // S2V_B200_BWD16_KERNEL=h: two fp16 pieces per operand, per-tile scales (k_embed_round_bwd_h2)
+    static const bool h = [] { const char* e = getenv("S2V_B200_BWD16_KERNEL"); return e ? e[0] == 'h' : (S2V_BWD16_H2 != 0); }();
+    return h;
+}
 static bool bwd16_pipelined() {              // S2V_B200_BWD16_KERNEL=s: 4-warp CTAs, MMAs in the serial chain; p: 8-warp CTAs, two g stages
     static const bool p = [] { const char* e = getenv("S2V_B200_BWD16_KERNEL"); return e ? e[0] == 'p' : (S2V_BWD16_PIPELINED != 0); }();
     return p;
@@ -2651,6 +2897,14 @@ static bool bwd16_pipelined() {              // S2V_B200_BWD16_KERNEL=s: 4-warp 
 int s2v_tc_round_backward_sel_grid(int num_nodes, int flags) {
     if (bwd16_group(flags) == 0) return s2v_tc_round_backward_ws_grid(num_nodes);
     const int tiles = (num_nodes + TCR - 1) / TCR;
+    if (bwd16_h2()) {
+        if (bwdh2_ctas() == 4) {
+            cudaFuncSetAttribute(k_embed_round_bwd_h2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWDH2_SMEM);
+            return tc_grid((const void*)k_embed_round_bwd_h2<4>, BWDH2_SMEM, 128, tiles);
+        }
+        cudaFuncSetAttribute(k_embed_round_bwd_h2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWDH2_SMEM);
+        return tc_grid((const void*)k_embed_round_bwd_h2<3>, BWDH2_SMEM, 128, tiles);
+    }
     if (bwd16_pipelined()) {
         int dev = 0, sms = 0;
         cudaGetDevice(&dev);
@@ -2658,8 +2912,8 @@ int s2v_tc_round_backward_sel_grid(int num_nodes, int flags) {
         const int grid = 2 * sms;                // two 8-warp CTAs per SM (97 KB, 128 registers, 128 TMEM columns each)
         return grid < tiles ? grid : (tiles < 1 ? 1 : tiles);
     }
-    cudaFuncSetAttribute(k_embed_round_bwd_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16_SMEM);
-    return tc_grid((const void*)k_embed_round_bwd_tc16, BWD16_SMEM, 128, tiles);
+    cudaFuncSetAttribute(k_embed_round_bwd_tc16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16_SMEM);
+    return tc_grid((const void*)k_embed_round_bwd_tc16<false>, BWD16_SMEM, 128, tiles);
 }
 
 int s2v_tc_round_backward_sel(const s2v_graph_t& g, const float* theta2_w, const float* du_t, const float* mu_prev,
@@ -2668,6 +2922,18 @@ int s2v_tc_round_backward_sel(const s2v_graph_t& g, const float* theta2_w, const
     const int grp = bwd16_group(flags);
     if (grp == 0) return s2v_tc_round_backward_ws(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride, accumulate, grid, st);
     const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    if (bwd16_h2()) {
+        if (bwdh2_ctas() == 4) {
+            S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_h2<4>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWDH2_SMEM));
+            k_embed_round_bwd_h2<4><<<grid, TC_THREADS, BWDH2_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
+                                                                        accumulate, tiles);
+            return (int)cudaGetLastError();
+        }
+        S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_h2<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWDH2_SMEM));
+        k_embed_round_bwd_h2<3><<<grid, TC_THREADS, BWDH2_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
+                                                                    accumulate, tiles);
+        return (int)cudaGetLastError();
+    }
     if (bwd16_pipelined()) {
         S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc16p, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16P_SMEM));
         int grp_p = grp;
@@ -2678,12 +2944,18 @@ int s2v_tc_round_backward_sel(const s2v_graph_t& g, const float* theta2_w, const
                                                                        accumulate, tiles, grp_p);
         return (int)cudaGetLastError();
     }
-    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16_SMEM));
+    if (getenv("S2V_B200_H2X")) {              // timing experiment: garbage scales unless |du| < 16, mu < 2, |theta2| < 4096
+        S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc16<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16_SMEM));
+        k_embed_round_bwd_tc16<true><<<grid, TC_THREADS, BWD16_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
+                                                                         accumulate, tiles, 1);
+        return (int)cudaGetLastError();
+    }
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_bwd_tc16<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BWD16_SMEM));
     int grp_arg = grp;
 #ifdef S2V_BWD16_EXPERIMENTS
     if (const char* e = getenv("S2V_B200_BWD16_EXP")) grp_arg |= atoi(e) << 8;
 #endif
-    k_embed_round_bwd_tc16<<<grid, TC_THREADS, BWD16_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
+    k_embed_round_bwd_tc16<false><<<grid, TC_THREADS, BWD16_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
                                                                 accumulate, tiles, grp_arg);
     return (int)cudaGetLastError();
 }
