@@ -21,6 +21,10 @@
 #include "s2v_common.cuh"
 #include "s2v_tc.cuh"
 
+#ifndef S2V_FWD_H2_DEFAULT
+#define S2V_FWD_H2_DEFAULT 5           /* forward round: 0 = bf16x3 (k_embed_round_tc16), 4..6 = fp16x2 with that many CTAs per SM */
+#endif
+
 #ifdef S2V_TC_TIMELINE
 __device__ long long g_timeline[16 * 8];
 #define TL(slot) do { if (blockIdx.x == 0 && threadIdx.x == 32 && tl_n < 8) g_timeline[tl_n * 16 + (slot)] = clock64(); } while (0)
@@ -1658,6 +1662,122 @@ k_embed_round_bwd_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
     if (warp == 0) tc::tmem_dealloc<128>(sh->tmem_base);
 }
 
+// ------------------------------------------------------------------------------------
+// Forward round on two fp16 pieces per operand (same arithmetic scheme as k_embed_round_bwd_h2): 32 KB of tiles and 12
+// MMAs per tile instead of 48 KB and 24; the gathered tile is scaled by the power of two that puts its largest entry in
+// [2^14, 2^15), theta2 once per CTA, both leave through the epilogue.
+// ------------------------------------------------------------------------------------
+template <int CTAS>
+__global__ void __launch_bounds__(TC_THREADS, CTAS)
+k_embed_round_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const float* __restrict__ base,
+                 const float* __restrict__ mu_prev, float* __restrict__ mu_next, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w1 = smem;                          // theta2 [n][k] 2^ew, two fp16 pieces
+    uint8_t* a1 = w1 + TILE16X2;                 // gathered tile 2^ea, two fp16 pieces; reused as the staging tile
+    H2Shared* sh = reinterpret_cast<H2Shared*>(a1 + TILE16X2);
+    float* stg = reinterpret_cast<float*>(a1);
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const unsigned FULL = 0xffffffffu;
+
+    if (warp == 0) tc::tmem_alloc<64>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    {
+        float wm = 0.f;
+        for (int e = t; e < 64 * 64; e += TC_THREADS) wm = fmaxf(wm, fabsf(__ldg(theta2_w + e)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(FULL, wm, o));
+        if (lane == 0) sh->wmax[warp] = wm;
+        __syncthreads();
+        if (t == 0) sh->wscale = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+        __syncthreads();
+        const float sw = sh->wscale;
+        for (int e = t; e < 64 * 16; e += TC_THREADS) store_split2h(w1, e >> 4, e & 15, ldg4(theta2_w + (e >> 4) * 64 + 4 * (e & 15)), sw);
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const float inv_sw = 1.0f / sh->wscale;
+    const uint32_t d1 = sh->tmem_base;
+    const uint32_t s_a = tc::smem_u32(a1), s_w = tc::smem_u32(w1);
+    const uint32_t lane_sel = (uint32_t)(32 * warp) << 16;
+    uint32_t phase = 0;
+    const int c4 = lane & 15, rl0 = warp * 16 + 8 * (lane >> 4);
+    Gather8Meta meta;
+    if (blockIdx.x < num_tiles)
+        gather8_prefetch(meta, g, g.rowptr, g.col, blockIdx.x * TCR, min(TCR, g.num_nodes - blockIdx.x * TCR), rl0);
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+        float c1;
+        {
+            float4 gv[8];
+            gather8_consume(meta, g.col, mu_prev, rl0, [&](int rl, const float4& acc) { gv[rl - rl0] = acc; });
+            float gm = 0.f;
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+                gm = fmaxf(gm, fmaxf(fmaxf(fabsf(gv[i].x), fabsf(gv[i].y)), fmaxf(fabsf(gv[i].z), fabsf(gv[i].w))));
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(FULL, gm, o));
+            if (lane == 0) sh->wmax[warp] = gm;
+            __syncthreads();
+            const float sa = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+            c1 = (1.0f / sa) * inv_sw;
+#pragma unroll
+            for (int i = 0; i < 8; ++i) store_split2h(a1, rl0 + i, c4, gv[i], sa);
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            tc::tc_fence_after_sync();
+            issue_transform_h2(d1, s_a, s_w);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        float4 bv[8];                            // base rows of the epilogue while the tensor core works (requested before the
+#pragma unroll                                   // metadata prefetch, which stalls on its own dependent loads)
+        for (int i = 0; i < 8; ++i)
+            bv[i] = rl0 + i < rows ? ldg4(base + (size_t)(row0 + rl0 + i) * 64 + 4 * c4) : f4zero();
+        {
+            const int nt = tile + gridDim.x;
+            if (nt < num_tiles) gather8_prefetch(meta, g, g.rowptr, g.col, nt * TCR, min(TCR, g.num_nodes - nt * TCR), rl0);
+        }
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        {
+            float v[32];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                tc::tmem_ld32(d1 + lane_sel + 32 * half, v);
+                if (lane < 16) {
+                    const int r = 16 * warp + lane;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        st4(stg + stg_off(r, 8 * half + i), make_float4(v[4 * i] * c1, v[4 * i + 1] * c1, v[4 * i + 2] * c1, v[4 * i + 3] * c1));
+                }
+            }
+        }
+        tc::tc_fence_before_sync();
+        __syncthreads();
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rl = rl0 + i;
+            if (rl < rows) {
+                float4 v = ld4(stg + stg_off(rl, c4));
+                st4(mu_next + (size_t)(row0 + rl) * 64 + 4 * c4,
+                    make_float4(relu(v.x + bv[i].x), relu(v.y + bv[i].y), relu(v.z + bv[i].z), relu(v.w + bv[i].w)));
+            }
+        }
+        __syncthreads();                        // staging is overwritten by the next tile's pieces
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(d1);
+}
+
 #include "s2v_ring.cuh"
 
 // self-test: mode 6: out[rows x 64] = A * W;  mode 7: out[64 x 64] = A^T * B over the rows (per-tile accumulators
@@ -2811,6 +2931,26 @@ int s2v_tc_round_forward(const s2v_graph_t& g, const float* theta2_w, const floa
         int ns = 1, slots = 0, cap = 128;
         sscanf(ring_env, "%d,%d,%d", &ns, &slots, &cap);
         return ring_forward_launch(ns == 2 ? 2 : 1, slots, cap, g, theta2_w, base, mu_prev, mu_next, tiles, st);
+    }
+    static const int h2_ctas = [] {            // S2V_B200_FWD_ROUND=tc16 | h2[,<CTAs per SM: 4 5 6>]
+        const char* e = getenv("S2V_B200_FWD_ROUND");
+        if (!e) return S2V_FWD_H2_DEFAULT;
+        if (strncmp(e, "h2", 2) != 0) return 0;
+        int c = 4;
+        if (e[2] == ',') c = atoi(e + 3);
+        return c < 4 ? 4 : (c > 6 ? 6 : c);
+    }();
+    if (h2_ctas) {
+        constexpr int FWDH2_SMEM = 2 * (int)TILE16X2 + 128 + 1024;
+        auto launch = [&](auto kern) -> int {
+            S2V_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, FWDH2_SMEM));
+            int grid = tc_grid((const void*)kern, FWDH2_SMEM, 64, tiles);
+            kern<<<grid, TC_THREADS, FWDH2_SMEM, st>>>(g, theta2_w, base, mu_prev, mu_next, tiles);
+            return (int)cudaGetLastError();
+        };
+        if (h2_ctas == 4) return launch(k_embed_round_h2<4>);
+        if (h2_ctas == 5) return launch(k_embed_round_h2<5>);
+        return launch(k_embed_round_h2<6>);
     }
     constexpr int FWD16_SMEM = 2 * (int)TILE16X3 + 64 + 1024;
     S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_round_tc16, cudaFuncAttributeMaxDynamicSharedMemorySize, FWD16_SMEM));
