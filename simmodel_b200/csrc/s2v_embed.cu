@@ -319,6 +319,11 @@ bool s2v_tc_final_backward_ws_ok(int node_dim);
 int s2v_tc_final_backward_ws(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, const float* dus,
                              const float* du_last, float* partial, int partial_stride, int grid, cudaStream_t st);
 
+bool s2v_tc_final_backward_h2_selected(int flags, int node_dim);
+int s2v_tc_final_backward_h2_grid(int num_nodes);
+int s2v_tc_final_backward_h2(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, const float* dus,
+                             const float* du_last, float* partial, int partial_stride, int grid, cudaStream_t st);
+
 int s2v_tc_embed_first(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, float* base, float* mu1,
                        cudaStream_t st);
 int s2v_tc_final_backward_grid(int num_nodes);
@@ -438,7 +443,11 @@ static int embed_backward_impl(const s2v_graph_t& g, const s2v_embed_params_t& p
                                                                       t != T, tiles);
         }
     }
-    if (dx == nullptr && use_tensor_path(P, prm.flags, g.num_nodes) && use_ws_bwd_round(prm.flags) && s2v_tc_final_backward_ws_ok(prm.node_dim)) {
+    if (dx == nullptr && use_tensor_path(P, prm.flags, g.num_nodes) && use_ws_bwd_round(prm.flags) &&
+        s2v_tc_final_backward_h2_selected(prm.flags, prm.node_dim)) {
+        grid_f = s2v_tc_final_backward_h2_grid(g.num_nodes);
+        S2V_RETURN_IF(s2v_tc_final_backward_h2(g, prm, x, dus, du_last, partial, stride, grid_f, st));
+    } else if (dx == nullptr && use_tensor_path(P, prm.flags, g.num_nodes) && use_ws_bwd_round(prm.flags) && s2v_tc_final_backward_ws_ok(prm.node_dim)) {
         grid_f = s2v_tc_round_backward_ws_grid(g.num_nodes);
         S2V_RETURN_IF(s2v_tc_final_backward_ws(g, prm, x, dus, du_last, partial, stride, grid_f, st));
     } else if (dx == nullptr && S2V_TENSOR_FINAL && use_tensor_path(P, prm.flags, g.num_nodes)) {

@@ -1778,6 +1778,263 @@ k_embed_round_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
     if (warp == 0) tc::tmem_dealloc<64>(d1);
 }
 
+// ------------------------------------------------------------------------------------
+// Last backward stage on two fp16 pieces per operand, in the shape of the forward round (r02d): 4-warp CTAs, three per SM.
+//   D = sum_t du^t (fixed order t = 1..T) ;  dtheta1b += D^T h ;  dh = (D theta1b) * [h > 0] ;  dtheta1a += dh^T x ;
+//   column sums of D, c D, (Npad - c) D, dh.        h = relu(theta1a x + b1a) is recomputed (K = F <= 8, CUDA cores).
+// A lane owns rows rl0 .. rl0 + 7, columns 4 c4 .. 4 c4 + 3 of the tile in every phase (plane sums, h, masks, epilogue,
+// column sums, dh x^T), so nothing but the two MMA operands and the staged D theta1b crosses threads; all long sums are
+// per-lane fp32 registers over the CTA's tiles, reduced across the eight lanes that share a column group in fixed order
+// at the end.  The D and h tiles are scaled per tile (k_embed_round_bwd_h2), D2 is read out per tile.
+// Partial layout: EmbedPartial<64> rows TH1B .. TH1A (s2v_embed.cu).
+// ------------------------------------------------------------------------------------
+constexpr int FH2_FS = 8;                        // features padded to 8 (F <= 8)
+__global__ void __launch_bounds__(TC_THREADS, 3)
+k_embed_final_bwd_h2(s2v_graph_t g, s2v_embed_params_t prm, const float* __restrict__ x, const float* __restrict__ dus,
+                     const float* __restrict__ du_last, int T, float* __restrict__ partial, int partial_stride, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w1 = smem;                          // theta1b^T 2^ew: tile(row k, col n) = theta1b[n][k]
+    uint8_t* a1 = w1 + TILE16X2;                 // D tile 2^ed; reused as the staging tile
+    uint8_t* h1 = a1 + TILE16X2;                 // h tile 2^eh
+    float* W1a = reinterpret_cast<float*>(h1 + TILE16X2);       // [FS][64]
+    float* xs = W1a + FH2_FS * 64;                              // [64][FS]
+    float* b1a = xs + TCR * FH2_FS;                             // [64]
+    float* cw = b1a + 64;                                       // [64] in-degree c_r, [64] Npad - c_r
+    H2Shared* sh = reinterpret_cast<H2Shared*>(cw + 128);
+    float* stg = reinterpret_cast<float*>(a1);
+    const int F = prm.node_dim;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const unsigned FULL = 0xffffffffu;
+    const size_t plane = (size_t)g.num_nodes * 64;
+
+    if (warp == 0) tc::tmem_alloc<128>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 2); tc::fence_barrier_init(); }
+    {
+        float wm = 0.f;
+        for (int e = t; e < 64 * 64; e += TC_THREADS) wm = fmaxf(wm, fabsf(__ldg(prm.theta1b_w + e)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(FULL, wm, o));
+        if (lane == 0) sh->wmax[warp] = wm;
+        for (int e = t; e < 64 * FH2_FS; e += TC_THREADS) { int f = e >> 6, n = e & 63; W1a[e] = f < F ? __ldg(prm.theta1a_w + n * F + f) : 0.f; }
+        if (t < 64) b1a[t] = __ldg(prm.theta1a_b + t);
+        __syncthreads();
+        if (t == 0) sh->wscale = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+        __syncthreads();
+        const float sw = sh->wscale;
+        for (int e = t; e < 64 * 16; e += TC_THREADS) {
+            const int row = e >> 4, cc = e & 15;
+            const float* W = prm.theta1b_w;
+            store_split2h(w1, row, cc, make_float4(__ldg(W + (4 * cc) * 64 + row), __ldg(W + (4 * cc + 1) * 64 + row),
+                                                   __ldg(W + (4 * cc + 2) * 64 + row), __ldg(W + (4 * cc + 3) * 64 + row)), sw);
+        }
+    }
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const float inv_sw = 1.0f / sh->wscale;
+    const uint32_t d1 = sh->tmem_base, d2 = sh->tmem_base + 64;
+    const uint32_t s_a = tc::smem_u32(a1), s_w = tc::smem_u32(w1), s_h = tc::smem_u32(h1);
+    const uint32_t lane_sel = (uint32_t)(32 * warp) << 16;
+    uint32_t phase = 0;
+    const int c4 = lane & 15, rl0 = warp * 16 + 8 * (lane >> 4);
+    float racc[32];
+#pragma unroll
+    for (int i = 0; i < 32; ++i) racc[i] = 0.f;
+    float4 pD = f4zero(), pA1 = f4zero(), pA0 = f4zero(), pB1a = f4zero();      // columns 4 c4 .. + 3, this lane's rows
+    float4 pth1a[FH2_FS];                                                      // [feature] x columns 4 c4 .. + 3
+#pragma unroll
+    for (int f = 0; f < FH2_FS; ++f) pth1a[f] = f4zero();
+
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+        // ---- requests: x elements, per-row degree data, then the T planes of the lane's rows ----
+        float xr[4];
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = t + TC_THREADS * j;
+            xr[j] = e < rows * F ? __ldg(x + (size_t)row0 * F + e) : 0.f;
+        }
+        float cn = 0.f, dn = 0.f;
+        if (t < rows) {
+            int li, off, gi;
+            row_info(g, row0 + t, li, off, gi);
+            cn = (float)__ldg(g.indeg + li);
+            dn = (float)graph_npad(g, gi) - cn;
+        }
+        float4 dv[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dv[i] = f4zero();
+        {
+            const size_t o = (size_t)(row0 + rl0) * 64 + 4 * c4;
+            int tt = 0;
+            for (; tt + 1 < T; tt += 2) {        // two planes (16 independent 128-bit loads) at a time, summed in the order t = 1..T
+                const float* pa = dus + (size_t)tt * plane + o;          // (four rows x five planes per batch: more spills, no faster)
+                const float* pb = (tt + 1 < T - 1 ? dus + (size_t)(tt + 1) * plane : du_last) + o;
+                float4 a[8], b[8];
+#pragma unroll
+                for (int i = 0; i < 8; ++i) a[i] = rl0 + i < rows ? ldg4(pa + (size_t)i * 64) : f4zero();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) b[i] = rl0 + i < rows ? ldg4(pb + (size_t)i * 64) : f4zero();
+#pragma unroll
+                for (int i = 0; i < 8; ++i) dv[i] = f4add(f4add(dv[i], a[i]), b[i]);
+            }
+            if (tt < T) {
+                const float* pa = (tt < T - 1 ? dus + (size_t)tt * plane : du_last) + o;
+#pragma unroll
+                for (int i = 0; i < 8; ++i) if (rl0 + i < rows) dv[i] = f4add(dv[i], ldg4(pa + (size_t)i * 64));
+            }
+        }
+        // ---- x tile and degree weights to shared memory (rows past the end: x = 0, c = 0) ----
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+            const int e = t + TC_THREADS * j;
+            if (e < TCR * F) xs[(e / F) * FH2_FS + (e % F)] = xr[j];
+        }
+        if (t < TCR) { cw[t] = cn; cw[64 + t] = dn; }
+        __syncthreads();
+        // ---- h, masks, column sums of D, tile maxima ----
+        float4 hv[8];
+        uint32_t hbits = 0;
+        {
+            const float4 bb = ld4(b1a + 4 * c4);
+#pragma unroll
+            for (int i = 0; i < 8; ++i) hv[i] = bb;
+#pragma unroll
+            for (int f0 = 0; f0 < FH2_FS; f0 += 4) {
+                const float4 w0 = ld4(W1a + f0 * 64 + 4 * c4), w1v = ld4(W1a + (f0 + 1) * 64 + 4 * c4),
+                             w2v = ld4(W1a + (f0 + 2) * 64 + 4 * c4), w3v = ld4(W1a + (f0 + 3) * 64 + 4 * c4);
+#pragma unroll
+                for (int i = 0; i < 8; ++i) {
+                    const float4 xv = ld4(xs + (rl0 + i) * FH2_FS + f0);
+                    hv[i].x = fmaf(xv.x, w0.x, hv[i].x); hv[i].y = fmaf(xv.x, w0.y, hv[i].y);
+                    hv[i].z = fmaf(xv.x, w0.z, hv[i].z); hv[i].w = fmaf(xv.x, w0.w, hv[i].w);
+                    hv[i].x = fmaf(xv.y, w1v.x, hv[i].x); hv[i].y = fmaf(xv.y, w1v.y, hv[i].y);
+                    hv[i].z = fmaf(xv.y, w1v.z, hv[i].z); hv[i].w = fmaf(xv.y, w1v.w, hv[i].w);
+                    hv[i].x = fmaf(xv.z, w2v.x, hv[i].x); hv[i].y = fmaf(xv.z, w2v.y, hv[i].y);
+                    hv[i].z = fmaf(xv.z, w2v.z, hv[i].z); hv[i].w = fmaf(xv.z, w2v.w, hv[i].w);
+                    hv[i].x = fmaf(xv.w, w3v.x, hv[i].x); hv[i].y = fmaf(xv.w, w3v.y, hv[i].y);
+                    hv[i].z = fmaf(xv.w, w3v.z, hv[i].z); hv[i].w = fmaf(xv.w, w3v.w, hv[i].w);
+                }
+            }
+        }
+        float gm = 0.f, hm = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            hv[i] = make_float4(relu(hv[i].x), relu(hv[i].y), relu(hv[i].z), relu(hv[i].w));
+            hbits |= (hv[i].x > 0.f ? 1u : 0u) << (4 * i) | (hv[i].y > 0.f ? 2u : 0u) << (4 * i) |
+                     (hv[i].z > 0.f ? 4u : 0u) << (4 * i) | (hv[i].w > 0.f ? 8u : 0u) << (4 * i);
+            hm = fmaxf(hm, fmaxf(fmaxf(hv[i].x, hv[i].y), fmaxf(hv[i].z, hv[i].w)));
+            gm = fmaxf(gm, fmaxf(fmaxf(fabsf(dv[i].x), fabsf(dv[i].y)), fmaxf(fabsf(dv[i].z), fabsf(dv[i].w))));
+            const float c = cw[rl0 + i], d = cw[64 + rl0 + i];
+            pD = f4add(pD, dv[i]);
+            pA1.x = fmaf(c, dv[i].x, pA1.x); pA1.y = fmaf(c, dv[i].y, pA1.y); pA1.z = fmaf(c, dv[i].z, pA1.z); pA1.w = fmaf(c, dv[i].w, pA1.w);
+            pA0.x = fmaf(d, dv[i].x, pA0.x); pA0.y = fmaf(d, dv[i].y, pA0.y); pA0.z = fmaf(d, dv[i].z, pA0.z); pA0.w = fmaf(d, dv[i].w, pA0.w);
+        }
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) { gm = fmaxf(gm, __shfl_xor_sync(FULL, gm, o)); hm = fmaxf(hm, __shfl_xor_sync(FULL, hm, o)); }
+        if (lane == 0) { sh->wmax[warp] = gm; sh->wmax[4 + warp] = hm; }
+        __syncthreads();
+        const float sd = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+        const float shh = pow2_scale_for(fmaxf(fmaxf(sh->wmax[4], sh->wmax[5]), fmaxf(sh->wmax[6], sh->wmax[7])));
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            store_split2h(a1, rl0 + i, c4, dv[i], sd);
+            store_split2h(h1, rl0 + i, c4, hv[i], shh);
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            tc::tc_fence_after_sync();
+            issue_transform_h2(d1, s_a, s_w);
+            tc::mma_commit(&sh->bar);
+        } else if (warp == 2) {
+            tc::tc_fence_after_sync();
+            issue_reduce_h2(d2, s_a, s_h);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        {
+            const float c1 = (1.0f / sd) * inv_sw;
+            float v[32];
+#pragma unroll
+            for (int half = 0; half < 2; ++half) {
+                tc::tmem_ld32(d1 + lane_sel + 32 * half, v);
+                if (lane < 16) {
+                    const int r = 16 * warp + lane;
+#pragma unroll
+                    for (int i = 0; i < 8; ++i)
+                        st4(stg + stg_off(r, 8 * half + i), make_float4(v[4 * i] * c1, v[4 * i + 1] * c1, v[4 * i + 2] * c1, v[4 * i + 3] * c1));
+                }
+            }
+            const float c2 = (1.0f / sd) * (1.0f / shh);
+            tc::tmem_ld32(d2 + lane_sel, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) if (lane < 16) racc[i] = fmaf(v[i], c2, racc[i]);
+            tc::tmem_ld32(d2 + lane_sel + 32, v);
+#pragma unroll
+            for (int i = 0; i < 32; ++i) {
+                const float o = __shfl_sync(FULL, v[i], lane & 15);
+                if (lane >= 16) racc[i] = fmaf(o, c2, racc[i]);
+            }
+        }
+        tc::tc_fence_before_sync();
+        __syncthreads();
+        // ---- dh = (D theta1b) * [h > 0];  db1a += dh;  dtheta1a += dh x^T  (rows past the end: D = 0 -> dh = 0) ----
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            const int rl = rl0 + i;
+            float4 v = ld4(stg + stg_off(rl, c4));
+            const uint32_t b = hbits >> (4 * i);
+            const float4 dh = make_float4(b & 1u ? v.x : 0.f, b & 2u ? v.y : 0.f, b & 4u ? v.z : 0.f, b & 8u ? v.w : 0.f);
+            pB1a = f4add(pB1a, dh);
+            const float4 x0 = ld4(xs + rl * FH2_FS), x1 = ld4(xs + rl * FH2_FS + 4);
+            const float xf[FH2_FS] = {x0.x, x0.y, x0.z, x0.w, x1.x, x1.y, x1.z, x1.w};
+#pragma unroll
+            for (int f = 0; f < FH2_FS; ++f) {
+                pth1a[f].x = fmaf(dh.x, xf[f], pth1a[f].x); pth1a[f].y = fmaf(dh.y, xf[f], pth1a[f].y);
+                pth1a[f].z = fmaf(dh.z, xf[f], pth1a[f].z); pth1a[f].w = fmaf(dh.w, xf[f], pth1a[f].w);
+            }
+        }
+        __syncthreads();                        // staging, xs, cw are overwritten by the next tile
+    }
+    float* my = partial + (size_t)blockIdx.x * partial_stride;
+    {   // dtheta1b[n = 16 warp + lane % 16][32 (lane / 16) .. + 32)
+        float* dst = my + EP_TH1B + (16 * warp + (lane & 15)) * 64 + 32 * (lane >> 4);
+#pragma unroll
+        for (int i = 0; i < 32; i += 4) st4(dst + i, make_float4(racc[i], racc[i + 1], racc[i + 2], racc[i + 3]));
+    }
+    // per-lane column sums -> per-CTA sums: the eight lanes (warp, half) that share a column group, in fixed order
+    float* red = reinterpret_cast<float*>(w1);   // [8][(4 + FS) * 64] floats = 24 KB: weight, D and h tiles are dead
+    {
+        const int slot = 2 * warp + (lane >> 4);
+        float* r = red + slot * ((4 + FH2_FS) * 64) + 4 * c4;
+        st4(r, pD); st4(r + 64, pA1); st4(r + 128, pA0); st4(r + 192, pB1a);
+#pragma unroll
+        for (int f = 0; f < FH2_FS; ++f) st4(r + (4 + f) * 64, pth1a[f]);
+    }
+    __syncthreads();
+    for (int e = t; e < (4 + FH2_FS) * 64; e += TC_THREADS) {
+        float sum = 0.f;
+#pragma unroll
+        for (int sl = 0; sl < 8; ++sl) sum += red[sl * ((4 + FH2_FS) * 64) + e];
+        const int q = e >> 6, col = e & 63;
+        if (q == 0) my[EP_COLD + col] = sum;
+        else if (q == 1) my[EP_A1 + col] = sum;
+        else if (q == 2) my[EP_A0 + col] = sum;
+        else if (q == 3) my[EP_B1A + col] = sum;
+        else if (q - 4 < F) my[EP_TH1A + col * F + (q - 4)] = sum;
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<128>(sh->tmem_base);
+}
+
 #include "s2v_ring.cuh"
 
 // self-test: mode 6: out[rows x 64] = A * W;  mode 7: out[64 x 64] = A^T * B over the rows (per-tile accumulators
@@ -2932,11 +3189,11 @@ int s2v_tc_round_forward(const s2v_graph_t& g, const float* theta2_w, const floa
         sscanf(ring_env, "%d,%d,%d", &ns, &slots, &cap);
         return ring_forward_launch(ns == 2 ? 2 : 1, slots, cap, g, theta2_w, base, mu_prev, mu_next, tiles, st);
     }
-    static const int h2_ctas = [] {            // S2V_B200_FWD_ROUND=tc16 | h2[,<CTAs per SM: 4 5 6>]
+    const int h2_ctas = [] {                   // S2V_B200_FWD_ROUND=tc16 | h2[,<CTAs per SM: 4 5 6>]  (read per call: tests switch it)
         const char* e = getenv("S2V_B200_FWD_ROUND");
         if (!e) return S2V_FWD_H2_DEFAULT;
         if (strncmp(e, "h2", 2) != 0) return 0;
-        int c = 4;
+        int c = S2V_FWD_H2_DEFAULT ? S2V_FWD_H2_DEFAULT : 5;
         if (e[2] == ',') c = atoi(e + 3);
         return c < 4 ? 4 : (c > 6 ? 6 : c);
     }();
@@ -3097,6 +3354,25 @@ int s2v_tc_round_backward_sel(const s2v_graph_t& g, const float* theta2_w, const
 #endif
     k_embed_round_bwd_tc16<false><<<grid, TC_THREADS, BWD16_SMEM, st>>>(g, theta2_w, du_t, mu_prev, du_prev, partial, partial_stride,
                                                                 accumulate, tiles, grp_arg);
+    return (int)cudaGetLastError();
+}
+
+// Last backward stage, fp16x2 forward-shaped kernel (node_dim <= 8): chosen with the k_embed_round_bwd_h2 family
+constexpr int FINH2_SMEM = 3 * (int)TILE16X2 + (FH2_FS * 64 + TCR * FH2_FS + 64 + 128) * 4 + 128 + 1024;
+bool s2v_tc_final_backward_h2_selected(int flags, int node_dim) {
+    static const bool off = getenv("S2V_B200_FINAL_WS") != nullptr;      // A/B: keep the warp-specialised last stage
+    return !off && node_dim <= FH2_FS && bwd16_group(flags) != 0 && bwd16_h2();
+}
+int s2v_tc_final_backward_h2_grid(int num_nodes) {
+    const int tiles = (num_nodes + TCR - 1) / TCR;
+    cudaFuncSetAttribute(k_embed_final_bwd_h2, cudaFuncAttributeMaxDynamicSharedMemorySize, FINH2_SMEM);
+    return tc_grid((const void*)k_embed_final_bwd_h2, FINH2_SMEM, 128, tiles);
+}
+int s2v_tc_final_backward_h2(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, const float* dus,
+                             const float* du_last, float* partial, int partial_stride, int grid, cudaStream_t st) {
+    const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_final_bwd_h2, cudaFuncAttributeMaxDynamicSharedMemorySize, FINH2_SMEM));
+    k_embed_final_bwd_h2<<<grid, TC_THREADS, FINH2_SMEM, st>>>(g, prm, x, dus, du_last, prm.rounds, partial, partial_stride, tiles);
     return (int)cudaGetLastError();
 }
 

@@ -143,6 +143,8 @@ def test_ring_forward_round_bit_identical(topo_name, B, kind, cfg, cuda_device):
         torch.cuda.synchronize()
 
     old = os.environ.pop("S2V_B200_FWD_RING", None)
+    old_round = os.environ.get("S2V_B200_FWD_ROUND")
+    os.environ["S2V_B200_FWD_ROUND"] = "tc16"          # the bf16x3 round the ring kernel reproduces (the default is fp16x2 now)
     try:
         ref = torch.full((N, 64), float("nan"), device=dev)
         run(ref)
@@ -153,6 +155,9 @@ def test_ring_forward_round_bit_identical(topo_name, B, kind, cfg, cuda_device):
         os.environ.pop("S2V_B200_FWD_RING", None)
         if old is not None:
             os.environ["S2V_B200_FWD_RING"] = old
+        os.environ.pop("S2V_B200_FWD_ROUND", None)
+        if old_round is not None:
+            os.environ["S2V_B200_FWD_ROUND"] = old_round
     assert torch.equal(out, ref)
     agg = torch.zeros(N, 64, device=dev).index_add_(0, lay_edge_rows(lay, topo, B, dev)[0], mu[lay_edge_rows(lay, topo, B, dev)[1]])
     want = torch.relu(agg.double() @ w2.double().t() + base.double())
@@ -205,12 +210,15 @@ def test_last_stage_plane_ring_any_T(T, topo_name, B, cuda_device, monkeypatch):
         return q.detach().cpu(), {k: p.grad.detach().cpu() for k, p in net.named_parameters()}
 
     q_tc, g_tc = ours("tcws")
+    q_h2, g_h2 = ours("tc16")                  # fp16x2 rounds + the forward-shaped fp16x2 last stage (what auto runs at scale)
     q_ff, g_ff = ours("ffma")
     scale = float(q64.abs().max())
     assert float((q_tc.double() - q64).abs().max()) / scale < 1e-5
+    assert float((q_h2.double() - q64).abs().max()) / scale < 1e-5
     for k in g64:
         s = float(g64[k].abs().max()) + 1e-30
         own = float((g32[k].double() - g64[k]).abs().max()) / s
         bound = max(1e-5, 2 * own)
         assert float((g_tc[k].double() - g64[k]).abs().max()) / s < bound, (k, T)
+        assert float((g_h2[k].double() - g64[k]).abs().max()) / s < bound, (k, T, "h2")
         assert float((g_ff[k].double() - g64[k]).abs().max()) / s < bound, (k, T)
