@@ -479,10 +479,23 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
     w2 = net.theta2.weight.detach()
 
     flag = _lib.path_flag()
-    tensor_f = flag in (2, 3) or (flag == 0 and n >= 4096)   # same rules as csrc/s2v_embed.cu:use_tensor_path
-    sfx_f = ("_tc (tcgen05 3xTF32)" if os.environ.get("S2V_B200_FWD_TF32") else "_tc16 (tcgen05 bf16x3)") if tensor_f else " (FFMA)"
-    sfx_b = (" (FFMA)" if not tensor_f else "_tc256 (tcgen05 3xTF32)" if flag == 2
-             else "_ws (tcgen05 bf16x3, warp-specialised)")
+    tensor_f = flag in (2, 3, 4) or (flag == 0 and n >= 4096)   # same rules as csrc/s2v_embed.cu:use_tensor_path
+    # kernel names as csrc/s2v_embed_tc.cu selects them (defaults: fp16x2 rounds; the env switches give the older kernels)
+    fwd_env = os.environ.get("S2V_B200_FWD_ROUND", "h2")
+    bwd_env = os.environ.get("S2V_B200_BWD_ROUND", "tc16")
+    bwd_kern = os.environ.get("S2V_B200_BWD16_KERNEL", "h")
+    if not tensor_f:
+        sfx_f = sfx_b = " (FFMA)"
+    else:
+        sfx_f = ("_tc (tcgen05 3xTF32)" if os.environ.get("S2V_B200_FWD_TF32") else
+                 "_h2 (tcgen05 fp16x2, per-tile scales)" if fwd_env.startswith("h2") else "_tc16 (tcgen05 bf16x3)")
+        if flag == 2:
+            sfx_b = "_tc256 (tcgen05 3xTF32)"
+        elif flag == 3 or (flag == 0 and not bwd_env.startswith("tc16")):
+            sfx_b = "_ws (tcgen05 bf16x3, warp-specialised)"
+        else:
+            sfx_b = {"h": "_h2 (tcgen05 fp16x2, per-tile scales)", "p": "_tc16p (tcgen05 bf16x3, 8-warp pipelined)",
+                     "s": "_tc16 (tcgen05 bf16x3, 4-warp)"}.get(bwd_kern[:1], "_h2 (tcgen05 fp16x2, per-tile scales)")
 
     def fwd():
         _lib.check(L.s2v_embed_round_forward(C.byref(g), P, flag, _p(w2), _p(base), _p(mu), _p(out), _stream()), "round fwd")

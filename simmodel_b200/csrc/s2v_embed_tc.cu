@@ -21,6 +21,9 @@
 #include "s2v_common.cuh"
 #include "s2v_tc.cuh"
 
+#ifndef S2V_HEAD_H2_DEFAULT
+#define S2V_HEAD_H2_DEFAULT 5          /* Q head: 0 = bf16x3 (k_head_tc), 4..6 = fp16x2 with that many CTAs per SM */
+#endif
 #ifndef S2V_FWD_H2_DEFAULT
 #define S2V_FWD_H2_DEFAULT 5           /* forward round: 0 = bf16x3 (k_embed_round_tc16), 4..6 = fp16x2 with that many CTAs per SM */
 #endif
@@ -2035,6 +2038,125 @@ k_embed_final_bwd_h2(s2v_graph_t g, s2v_embed_params_t prm, const float* __restr
     if (warp == 0) tc::tmem_dealloc<128>(sh->tmem_base);
 }
 
+// ------------------------------------------------------------------------------------
+// Q / logit head on two fp16 pieces per operand (k_head_tc's pipeline, k_embed_round_h2's arithmetic): 32 KB of tiles, 12
+// MMAs per tile; the mu tile is scaled per tile, theta7 once per CTA, both leave in the row owner's epilogue.
+// ------------------------------------------------------------------------------------
+template <int CTAS>
+__global__ void __launch_bounds__(TC_THREADS, CTAS)
+k_head_h2(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, const float* __restrict__ gstate,
+          float* __restrict__ q, int num_tiles) {
+    extern __shared__ __align__(1024) uint8_t smem_raw[];
+    uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+    uint8_t* w1 = smem;                          // theta7 [n][k] 2^ew, two fp16 pieces
+    uint8_t* a1 = w1 + TILE16X2;                 // mu tile 2^ea, two fp16 pieces
+    float* vec = reinterpret_cast<float*>(a1 + TILE16X2);      // b7, w5a, w5b
+    H2Shared* sh = reinterpret_cast<H2Shared*>(vec + 3 * 64);
+    float* b7 = vec, *w5a = vec + 64, *w5b = vec + 128;
+    const int t = threadIdx.x, warp = t >> 5, lane = t & 31;
+    const unsigned FULL = 0xffffffffu;
+
+    if (warp == 0) tc::tmem_alloc<64>(&sh->tmem_base);
+    if (t == 0) { tc::mbar_init(&sh->bar, 1); tc::fence_barrier_init(); }
+    {
+        float wm = 0.f;
+        for (int e = t; e < 64 * 64; e += TC_THREADS) wm = fmaxf(wm, fabsf(__ldg(prm.theta7_w + e)));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) wm = fmaxf(wm, __shfl_xor_sync(FULL, wm, o));
+        if (lane == 0) sh->wmax[warp] = wm;
+        if (t < 64) {
+            b7[t] = __ldg(prm.theta7_b + t);
+            w5a[t] = __ldg(prm.theta5_w + t);
+            w5b[t] = __ldg(prm.theta5_w + 64 + t);
+        }
+        __syncthreads();
+        if (t == 0) sh->wscale = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+        __syncthreads();
+        const float sw = sh->wscale;
+        for (int e = t; e < 64 * 16; e += TC_THREADS) store_split2h(w1, e >> 4, e & 15, ldg4(prm.theta7_w + (e >> 4) * 64 + 4 * (e & 15)), sw);
+    }
+    const float b5 = __ldg(prm.theta5_b);
+    tc::fence_proxy_async_smem();
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    tc::tc_fence_after_sync();
+    const float inv_sw = 1.0f / sh->wscale;
+    const uint32_t d1 = sh->tmem_base;
+    const uint32_t s_a = tc::smem_u32(a1), s_w = tc::smem_u32(w1);
+    uint32_t phase = 0;
+    float4 m[8];
+    auto load_rows = [&](int tile) {
+        const int row0 = tile * TCR, rows = min(TCR, g.num_nodes - row0);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+            m[i] = rl < rows ? ldg4(mu + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero();
+        }
+    };
+    if (blockIdx.x < num_tiles) load_rows(blockIdx.x);
+    for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
+        const int row0 = tile * TCR;
+        const int rows = min(TCR, g.num_nodes - row0);
+        float am = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) am = fmaxf(am, fmaxf(fmaxf(fabsf(m[i].x), fabsf(m[i].y)), fmaxf(fabsf(m[i].z), fabsf(m[i].w))));
+#pragma unroll
+        for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(FULL, am, o));
+        if (lane == 0) sh->wmax[warp] = am;
+        __syncthreads();
+        const float sa = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+        const float c1 = (1.0f / sa) * inv_sw;
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+            int e = t + TC_THREADS * i;
+            store_split2h(a1, e >> 4, e & 15, m[i], sa);
+        }
+        tc::fence_proxy_async_smem();
+        __syncthreads();
+        if (warp == 0) {
+            tc::tc_fence_after_sync();
+            issue_transform_h2(d1, s_a, s_w);
+            tc::mma_commit(&sh->bar);
+        }
+        __syncwarp();
+        if (tile + (int)gridDim.x < num_tiles) load_rows(tile + gridDim.x);     // in flight during the MMAs and the epilogue
+        const int rl = 16 * warp + (lane & 15);  // graph part of the row owner's q while the tensor core works
+        float sg = 0.f;
+        if (lane < 16 && rl < rows) {
+            int li, off, gi;
+            row_info(g, row0 + rl, li, off, gi);
+            const float* G = gstate + (size_t)gi * 64;
+#pragma unroll
+            for (int c = 0; c < 16; ++c) {
+                const float4 gv = ldg4(G + 4 * c), wa = ld4(w5a + 4 * c);
+                sg = fmaf(wa.x, relu(gv.x), sg); sg = fmaf(wa.y, relu(gv.y), sg);
+                sg = fmaf(wa.z, relu(gv.z), sg); sg = fmaf(wa.w, relu(gv.w), sg);
+            }
+        }
+        tc::mbar_wait(&sh->bar, phase);
+        phase ^= 1;
+        tc::tc_fence_after_sync();
+        float sl = 0.f;
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            float v[32];
+            tc::tmem_ld32(d1 + ((uint32_t)(32 * warp) << 16) + 32 * half, v);
+#pragma unroll
+            for (int c = 0; c < 8; ++c) {
+                const float4 bb = ld4(b7 + 32 * half + 4 * c), wb = ld4(w5b + 32 * half + 4 * c);
+                sl = fmaf(wb.x, relu(fmaf(v[4 * c], c1, bb.x)), sl); sl = fmaf(wb.y, relu(fmaf(v[4 * c + 1], c1, bb.y)), sl);
+                sl = fmaf(wb.z, relu(fmaf(v[4 * c + 2], c1, bb.z)), sl); sl = fmaf(wb.w, relu(fmaf(v[4 * c + 3], c1, bb.w)), sl);
+            }
+        }
+        if (lane < 16 && rl < rows) q[row0 + rl] = (sg + sl) + b5;
+        tc::tc_fence_before_sync();
+        __syncthreads();                        // the accumulator and the A tiles are free again
+    }
+    tc::tc_fence_before_sync();
+    __syncthreads();
+    if (warp == 0) tc::tmem_dealloc<64>(d1);
+}
+
 #include "s2v_ring.cuh"
 
 // self-test: mode 6: out[rows x 64] = A * W;  mode 7: out[64 x 64] = A^T * B over the rows (per-tile accumulators
@@ -3419,6 +3541,8 @@ extern "C" int s2v_debug_timeline(long long* host_out) {
 int s2v_tc_embed_first(const s2v_graph_t& g, const s2v_embed_params_t& prm, const float* x, float* base, float* mu1,
                        cudaStream_t st) {
     const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    // (The same stage on two fp16 pieces -- k_embed_first_h2, r02d -- measured 0.599 ms at five CTAs per SM against 0.592 ms:
+    // this stage is bound by its 2 GB of stores and its per-tile barrier chain, not by the MMAs or the tile footprint.)
     const int FIRST_SMEM = first_smem_bytes(prm.node_dim);
     S2V_RETURN_IF(cudaFuncSetAttribute(k_embed_first_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, FIRST_SMEM));
     int grid = tc_grid((const void*)k_embed_first_tc, FIRST_SMEM, 64, tiles);
@@ -3429,6 +3553,26 @@ int s2v_tc_embed_first(const s2v_graph_t& g, const s2v_embed_params_t& prm, cons
 int s2v_tc_head_forward(const s2v_graph_t& g, const s2v_head_params_t& prm, const float* mu, const float* gstate, float* q,
                         cudaStream_t st) {
     const int tiles = (g.num_nodes + TCR - 1) / TCR;
+    const int h2_ctas = [] {                   // S2V_B200_HEAD=tc16 | h2[,<CTAs per SM: 4 5 6>]
+        const char* e = getenv("S2V_B200_HEAD");
+        if (!e) return S2V_HEAD_H2_DEFAULT;
+        if (strncmp(e, "h2", 2) != 0) return 0;
+        int c = S2V_HEAD_H2_DEFAULT ? S2V_HEAD_H2_DEFAULT : 5;
+        if (e[2] == ',') c = atoi(e + 3);
+        return c < 4 ? 4 : (c > 6 ? 6 : c);
+    }();
+    if (h2_ctas) {
+        constexpr int HEADH2_SMEM = 2 * (int)TILE16X2 + 3 * 64 * 4 + 128 + 1024;
+        auto launch = [&](auto kern) -> int {
+            S2V_RETURN_IF(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, HEADH2_SMEM));
+            int grid = tc_grid((const void*)kern, HEADH2_SMEM, 64, tiles);
+            kern<<<grid, TC_THREADS, HEADH2_SMEM, st>>>(g, prm, mu, gstate, q, tiles);
+            return (int)cudaGetLastError();
+        };
+        if (h2_ctas == 4) return launch(k_head_h2<4>);
+        if (h2_ctas == 5) return launch(k_head_h2<5>);
+        return launch(k_head_h2<6>);
+    }
     constexpr int HEAD_SMEM = 2 * (int)TILE16X3 + 3 * 64 * 4 + 64 + 1024;
     S2V_RETURN_IF(cudaFuncSetAttribute(k_head_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, HEAD_SMEM));
     int grid = tc_grid((const void*)k_head_tc, HEAD_SMEM, 64, tiles);
