@@ -1649,7 +1649,8 @@ k_embed_round_bwd_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
                     make_float4(b & 1u ? v.x : 0.f, b & 2u ? v.y : 0.f, b & 4u ? v.z : 0.f, b & 8u ? v.w : 0.f));
             }
         }
-        __syncthreads();                        // staging is overwritten by the next tile's g pieces
+        // no barrier here: the next tile's pieces are stored behind ITS scale-exchange barrier, which every thread reaches
+        // only after this epilogue
     }
     {   // thread (warp, lane) holds dtheta2[n = 16 warp + lane % 16][32 (lane / 16) .. + 32)
         float* my = partial + (size_t)blockIdx.x * partial_stride + (16 * warp + (lane & 15)) * 64 + 32 * (lane >> 4);
@@ -1774,7 +1775,7 @@ k_embed_round_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
                     make_float4(relu(v.x + bv[i].x), relu(v.y + bv[i].y), relu(v.z + bv[i].z), relu(v.w + bv[i].w)));
             }
         }
-        __syncthreads();                        // staging is overwritten by the next tile's pieces
+        // no barrier here: the next tile's pieces are stored behind ITS scale-exchange barrier
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -2149,8 +2150,7 @@ k_head_h2(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, co
             }
         }
         if (lane < 16 && rl < rows) q[row0 + rl] = (sg + sl) + b5;
-        tc::tc_fence_before_sync();
-        __syncthreads();                        // the accumulator and the A tiles are free again
+        tc::tc_fence_before_sync();            // no barrier here: the next tile's pieces are stored behind ITS scale-exchange barrier
     }
     tc::tc_fence_before_sync();
     __syncthreads();
