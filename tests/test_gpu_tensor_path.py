@@ -222,3 +222,49 @@ def test_last_stage_plane_ring_any_T(T, topo_name, B, cuda_device, monkeypatch):
         assert float((g_tc[k].double() - g64[k]).abs().max()) / s < bound, (k, T)
         assert float((g_h2[k].double() - g64[k]).abs().max()) / s < bound, (k, T, "h2")
         assert float((g_ff[k].double() - g64[k]).abs().max()) / s < bound, (k, T)
+
+
+@pytest.mark.parametrize("du_scale,mu_scale,w_scale", [(1.0, 1.0, 1.0), (1e-30, 1.0, 1.0), (1e-8, 1e3, 1e-3), (1e25, 1e-6, 1.0),
+                                                       (1.0, 1e-20, 1e12), (0.0, 1.0, 1.0)])
+def test_fp16x2_rounds_dynamic_range(du_scale, mu_scale, w_scale, cuda_device):
+    """The fp16x2 round kernels (two fp16 pieces per operand, per-tile power-of-two scales) against fp64 where fp16 alone would
+    under- or overflow: gradients at 1e-30, activations at 1e-20 or 1e3, weights at 1e12, an all-zero gradient plane, and rows
+    10^4 times larger than their tile mates.  Error bound: 2e-6 of the tensor's largest entry (measured: 2e-7); no inf / nan."""
+    import simmodel_b200 as sb
+    from simmodel_b200 import _lib
+    L = _lib.lib()
+    dev = cuda_device
+    topo = sb.graphs.load_topology("NWB_UTR")
+    B = 4
+    n = B * topo.num_nodes
+    ei = sb.graphs.batch_edge_index(topo, B).to(dev)
+    lay = sb.GraphLayout.from_batch(ei, (torch.arange(B + 1) * topo.num_nodes).to(dev), topo.num_nodes)
+    gen = torch.Generator().manual_seed(17)
+    w2 = (torch.randn(64, 64, generator=gen) / 8 * w_scale).to(dev)
+    big = (torch.rand(n, 1, generator=gen) < 0.01).float() * 1e4 + 1.0              # one row in a hundred is 10^4 times larger
+    mu = (torch.randn(n, 64, generator=gen).clamp(min=0) * big * mu_scale).to(dev)
+    du = (torch.randn(n, 64, generator=gen) * big.flip(0) * du_scale).to(dev)
+    base = (torch.randn(n, 64, generator=gen) * mu_scale * w_scale).to(dev)
+    st = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    g = lay.c_struct()
+    o = torch.full((n, 64), float("nan"), device=dev)
+    _lib.check(L.s2v_embed_round_forward(C.byref(g), 64, 4, _ptr(w2), _ptr(base), _ptr(mu), _ptr(o), st), "fwd")
+    d = torch.full((n, 64), float("nan"), device=dev)
+    ws = torch.zeros(L.s2v_embed_backward_workspace_bytes(7, 64), dtype=torch.uint8, device=dev)
+    _lib.check(L.s2v_embed_round_backward(C.byref(g), 7, 64, 4, _ptr(w2), _ptr(du), _ptr(mu), _ptr(d), _ptr(ws), ws.numel(), st), "bwd")
+    torch.cuda.synchronize()
+    stride = 2 * 64 * 64 + 4 * 64 + 64 * 7
+    dth = ws.view(torch.float32)[: 1024 * stride].view(1024, stride)[:, : 64 * 64].double().sum(0).view(64, 64)
+    agg = torch.zeros(n, 64, dtype=torch.float64, device=dev).index_add_(0, ei[0], mu.double()[ei[1]])
+    ref_o = (base.double() + agg @ w2.double().t()).clamp(min=0)
+    g64 = torch.zeros(n, 64, dtype=torch.float64, device=dev).index_add_(0, ei[1], du.double()[ei[0]])
+    ref_d = (g64 @ w2.double()) * (mu > 0)
+    ref_t = g64.t() @ mu.double()
+    for name, got, ref in (("mu_next", o.double(), ref_o), ("du_prev", d.double(), ref_d), ("dtheta2", dth, ref_t)):
+        assert bool(torch.isfinite(got).all()), name
+        scale = float(ref.abs().max())
+        if scale == 0.0:
+            assert float(got.abs().max()) == 0.0, name
+        else:
+            assert float((got - ref).abs().max()) / scale < 2e-6, (name, float((got - ref).abs().max()) / scale)
+    assert torch.equal(d == 0, ref_d == 0)
