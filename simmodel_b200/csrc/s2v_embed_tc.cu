@@ -1638,7 +1638,7 @@ k_embed_round_bwd_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const fl
             }
         }
         tc::tc_fence_before_sync();
-        __syncthreads();
+        __syncwarp();                            // the warp reads back the staging rows it wrote itself (rows 16 w .. 16 w + 15)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int rl = rl0 + i;
@@ -1719,15 +1719,13 @@ k_embed_round_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
         {
             float4 gv[8];
             gather8_consume(meta, g.col, mu_prev, rl0, [&](int rl, const float4& acc) { gv[rl - rl0] = acc; });
-            float gm = 0.f;
-#pragma unroll
+            float gm = 0.f;                      // scale per WARP = per 16 rows: the rows of a row transform are independent, the warp
+#pragma unroll                                   // that splits rows 16 w .. 16 w + 15 is the warp that reads them back from TMEM -- no exchange
             for (int i = 0; i < 8; ++i)
                 gm = fmaxf(gm, fmaxf(fmaxf(fabsf(gv[i].x), fabsf(gv[i].y)), fmaxf(fabsf(gv[i].z), fabsf(gv[i].w))));
 #pragma unroll
             for (int o = 16; o > 0; o >>= 1) gm = fmaxf(gm, __shfl_xor_sync(FULL, gm, o));
-            if (lane == 0) sh->wmax[warp] = gm;
-            __syncthreads();
-            const float sa = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+            const float sa = pow2_scale_for(gm);
             c1 = (1.0f / sa) * inv_sw;
 #pragma unroll
             for (int i = 0; i < 8; ++i) store_split2h(a1, rl0 + i, c4, gv[i], sa);
@@ -1765,7 +1763,7 @@ k_embed_round_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
             }
         }
         tc::tc_fence_before_sync();
-        __syncthreads();
+        __syncwarp();                            // the warp reads back the staging rows it wrote itself (rows 16 w .. 16 w + 15)
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
             const int rl = rl0 + i;
@@ -1775,7 +1773,7 @@ k_embed_round_h2(s2v_graph_t g, const float* __restrict__ theta2_w, const float*
                     make_float4(relu(v.x + bv[i].x), relu(v.y + bv[i].y), relu(v.z + bv[i].z), relu(v.w + bv[i].w)));
             }
         }
-        // no barrier here: the next tile's pieces are stored behind ITS scale-exchange barrier
+        __syncthreads();                        // the next tile's pieces overwrite the staging rows of OTHER warps
     }
     tc::tc_fence_before_sync();
     __syncthreads();
@@ -1988,7 +1986,7 @@ k_embed_final_bwd_h2(s2v_graph_t g, s2v_embed_params_t prm, const float* __restr
             }
         }
         tc::tc_fence_before_sync();
-        __syncthreads();
+        __syncwarp();                            // the warp reads back the staging rows it wrote itself
         // ---- dh = (D theta1b) * [h > 0];  db1a += dh;  dtheta1a += dh x^T  (rows past the end: D = 0 -> dh = 0) ----
 #pragma unroll
         for (int i = 0; i < 8; ++i) {
@@ -2089,8 +2087,8 @@ k_head_h2(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, co
     auto load_rows = [&](int tile) {
         const int row0 = tile * TCR, rows = min(TCR, g.num_nodes - row0);
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int e = t + TC_THREADS * i, rl = e >> 4, c4 = e & 15;
+        for (int i = 0; i < 8; ++i) {                  // warp w holds rows 16 w .. 16 w + 15 (8 per half-warp): the rows its lanes own in TMEM
+            const int rl = 16 * warp + 8 * (lane >> 4) + i, c4 = lane & 15;
             m[i] = rl < rows ? ldg4(mu + (size_t)(row0 + rl) * 64 + 4 * c4) : f4zero();
         }
     };
@@ -2098,20 +2096,15 @@ k_head_h2(s2v_graph_t g, s2v_head_params_t prm, const float* __restrict__ mu, co
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
         const int row0 = tile * TCR;
         const int rows = min(TCR, g.num_nodes - row0);
-        float am = 0.f;
+        float am = 0.f;                          // scale per warp = per 16 rows (see k_embed_round_h2): no exchange
 #pragma unroll
         for (int i = 0; i < 8; ++i) am = fmaxf(am, fmaxf(fmaxf(fabsf(m[i].x), fabsf(m[i].y)), fmaxf(fabsf(m[i].z), fabsf(m[i].w))));
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) am = fmaxf(am, __shfl_xor_sync(FULL, am, o));
-        if (lane == 0) sh->wmax[warp] = am;
-        __syncthreads();
-        const float sa = pow2_scale_for(fmaxf(fmaxf(sh->wmax[0], sh->wmax[1]), fmaxf(sh->wmax[2], sh->wmax[3])));
+        const float sa = pow2_scale_for(am);
         const float c1 = (1.0f / sa) * inv_sw;
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            int e = t + TC_THREADS * i;
-            store_split2h(a1, e >> 4, e & 15, m[i], sa);
-        }
+        for (int i = 0; i < 8; ++i) store_split2h(a1, 16 * warp + 8 * (lane >> 4) + i, lane & 15, m[i], sa);
         tc::fence_proxy_async_smem();
         __syncthreads();
         if (warp == 0) {
