@@ -491,7 +491,7 @@ def measure_roofline(sb, _lib, net, layout, x, dev, B, N):
         sfx_f = sfx_b = " (FFMA)"
     else:
         sfx_f = ("_tc (tcgen05 3xTF32)" if os.environ.get("S2V_B200_FWD_TF32") else
-                 "_h2 (tcgen05 fp16x2, per-tile scales)" if fwd_env.startswith("h2") else "_tc16 (tcgen05 bf16x3)")
+                 "_h2 (tcgen05 fp16x2, per-warp power-of-two scales)" if fwd_env.startswith("h2") else "_tc16 (tcgen05 bf16x3)")
         if flag == 2:
             sfx_b = "_tc256 (tcgen05 3xTF32)"
         elif flag == 3 or (flag == 0 and not bwd_env.startswith("tc16")):
