@@ -71,11 +71,11 @@ typedef struct s2v_embed_params {
     int32_t node_dim;         /* F  */
     int32_t emb_dim;          /* p  */
     int32_t rounds;           /* T  */
-    int32_t flags;            /* kernel path: 0 auto (tensor cores when p == 64 and num_nodes >= 4096),
-                                 1 CUDA-core FP32 (FFMA), 2 tcgen05 with the 8-warp 3xTF32 backward round,
-                                 3 tcgen05 with the warp-specialised bf16x3 backward round (= auto's choice),
-                                 4 tcgen05 with the forward-shaped bf16x3 backward round (no warp roles);
-                                 2, 3 and 4 need p == 64                                               */
+    int32_t flags;            /* kernel path: 0 auto (tensor cores when p == 64 and num_nodes >= 4096: the fp16x2
+                                 kernels of flag 4), 1 CUDA-core FP32 (FFMA), 2 tcgen05 with the 8-warp 3xTF32 backward
+                                 round, 3 tcgen05 with the warp-specialised bf16x3 backward round and last stage,
+                                 4 tcgen05 with the forward-shaped backward round and last stage (two fp16 pieces per
+                                 operand, power-of-two tile scales) at every size; 2, 3 and 4 need p == 64       */
     const float* theta1a_w;   /* [p,F] */
     const float* theta1a_b;   /* [p]   */
     const float* theta1b_w;   /* [p,p] */
