@@ -1,4 +1,4 @@
-"""CPU restatement of the arithmetic the fp16x2 tensor-core kernels use (csrc/s2v_embed_tc.cu: pow2_scale_for, split2h,
+"""CPU restatement of the arithmetic the fp16x2 tensor-core kernels use (csrc/s2v_h2.cuh: pow2_scale_for, split2h,
 issue_transform_h2 / issue_reduce_h2) -- test infrastructure, not product code.
 
   x s = h1 + h2 + r,  h1 = RN16(x s),  h2 = RN16(x s - h1),  |r| <= 2^-22 |x s|
@@ -13,7 +13,7 @@ import torch
 
 
 def pow2_scale_for(amax: float) -> float:
-    """csrc/s2v_embed_tc.cu:pow2_scale_for -- 2^k with amax 2^k in [2^14, 2^15); 2^127 for (near-)zero tiles."""
+    """csrc/s2v_h2.cuh:pow2_scale_for -- 2^k with amax 2^k in [2^14, 2^15); 2^127 for (near-)zero tiles."""
     e = (np.float32(amax).view(np.int32) >> 23) & 255
     k = int(min(127, max(-126, 141 - int(e))))
     return float(np.ldexp(np.float32(1.0), k))
